@@ -1,0 +1,1404 @@
+// edge.cu -- collision worlds and discretised edge validity checking on the device.
+//
+// Replaces the CPU loops of graph::core::CollisionCheckerBase
+//   check(q)                         include/graph_core/collision_checkers/collision_checker_base.h:166
+//   checkConnection(c1,c2)           :207-237   (bisection order)            -> GC_EDGE_BISECT
+//   checkConnection(c1,c2,conf&)     :178-205   (linear order, first failure) -> GC_EDGE_LINEAR
+//   checkConnFromConf(conn,conf)     :264-313                                 -> GC_EDGE_FROM_CONF
+// and the reference's only concrete check(), Cube3dCollisionChecker
+//   include/graph_core/collision_checkers/cube_3d_collision_checker.h:61-64.
+//
+// The set of interpolated states of every edge is EXACTLY the reference's:
+// the state index s enumerates them in the reference's visiting order, the interpolation is done
+// in fp64 with individually rounded operations, and the result is the AND over that set, so the
+// boolean equals the reference's whatever order the GPU evaluates the states in.
+//
+// Two kernel shapes (DESIGN.md "Edge path"):
+//   edge_warp_kernel  : one warp per edge, each lane interpolates states, ballot early exit after
+//                       every round of 32 states -- light worlds (cube, boxes, C-space spheres)
+//   arm_state_kernel  : flattened (edge,state) work list for the heavy FK sphere-arm world;
+//                       G = 1 lane per state (throughput) or a whole warp per state (latency)
+#include <math_constants.h>
+
+#include <cfloat>
+#include <cmath>
+
+#include "gc_common.cuh"
+
+namespace gc
+{
+// =================================================================================================
+//  state enumeration
+// =================================================================================================
+struct EdgeGeom
+{
+  double dist;      // BISECT/LINEAR: |c2-c1| ; FROM_CONF: |conf-child|
+  double aux;       // LINEAR: (double)npnt ; FROM_CONF: this_abscissa
+  uint32_t nstates; // states in the reference's visiting order (0: reference throws)
+};
+
+template <int D>
+__device__ __forceinline__ double norm_diff(const double* a, const double* b)
+{
+  double s = 0.0;
+#pragma unroll
+  for (int i = 0; i < GC_MAX_DIM; i++)
+    if (i < D)
+    {
+      const double t = __dsub_rn(a[i], b[i]);
+      s = __dadd_rn(s, __dmul_rn(t, t));
+    }
+  return __dsqrt_rn(s);
+}
+
+// number of interior states of the bisection loop: n = 2; while (dist > n*min_d) { n/2 states; n *= 2; }
+__device__ __forceinline__ uint32_t bisect_interior(double dist, double min_d)
+{
+  double n = 2.0;
+  uint32_t count = 0;
+  while (dist > __dmul_rn(n, min_d) && count < 0x3fffffffu)
+  {
+    count += (uint32_t)(n * 0.5);
+    n *= 2.0;
+  }
+  return count;
+}
+
+// c1/c2/c3 are thread-local copies.  MODE FROM_CONF: c1 = parent, c2 = child, c3 = this_conf
+template <int D, int MODE>
+__device__ __forceinline__ EdgeGeom edge_geom(const double* c1, const double* c2, const double* c3, double min_d)
+{
+  EdgeGeom g;
+  g.aux = 0.0;
+  if (MODE == GC_EDGE_BISECT)
+  {
+    g.dist = norm_diff<D>(c2, c1);
+    g.nstates = 2u + ((g.dist < min_d) ? 0u : bisect_interior(g.dist, min_d));
+  }
+  else if (MODE == GC_EDGE_LINEAR)
+  {
+    g.dist = norm_diff<D>(c2, c1);
+    const double np = ceil(__ddiv_rn(g.dist, min_d));
+    const uint32_t npnt = (np >= 1073741824.0) ? 0x3fffffffu : (uint32_t)np;
+    g.aux = (double)npnt;
+    g.nstates = (npnt > 1u ? npnt : 1u) + 1u;
+  }
+  else
+  {
+    const double dist_child = norm_diff<D>(c3, c2);
+    const double dist_parent = norm_diff<D>(c1, c3);
+    const double dist = norm_diff<D>(c1, c2);
+    if (__dsub_rn(__dsub_rn(dist, dist_child), dist_parent) > 1e-04)
+    {
+      g.dist = 0.0;
+      g.nstates = 0u;  // reference throws std::invalid_argument (:273-277)
+      return g;
+    }
+    g.dist = dist_child;
+    g.aux = __ddiv_rn(dist_parent, dist);
+    g.nstates = 2u + ((g.dist < min_d) ? 0u : bisect_interior(g.dist, min_d));
+  }
+  return g;
+}
+
+// configuration of state s; returns false when the reference does not evaluate this state
+template <int D, int MODE>
+__device__ __forceinline__ bool state_conf(const double* c1, const double* c2, const double* c3, const EdgeGeom& g,
+                                           uint32_t s, double* conf)
+{
+  if (MODE == GC_EDGE_LINEAR)
+  {
+    const uint32_t last = g.nstates - 1u;
+    if (s == 0u || s == last)
+    {
+#pragma unroll
+      for (int i = 0; i < GC_MAX_DIM; i++)
+        if (i < D)
+          conf[i] = (s == 0u) ? c1[i] : c2[i];
+      return true;
+    }
+#pragma unroll
+    for (int i = 0; i < GC_MAX_DIM; i++)
+      if (i < D)
+      {
+        const double step = __ddiv_rn(__dsub_rn(c2[i], c1[i]), g.aux);
+        conf[i] = __dadd_rn(c1[i], __dmul_rn(step, (double)s));
+      }
+    return true;
+  }
+  if (s < 2u)
+  {
+#pragma unroll
+    for (int i = 0; i < GC_MAX_DIM; i++)
+      if (i < D)
+        conf[i] = (MODE == GC_EDGE_FROM_CONF) ? ((s == 0u) ? c3[i] : c2[i]) : ((s == 0u) ? c1[i] : c2[i]);
+    return true;
+  }
+  const uint32_t v = s - 1u;                 // 1-based interior index in visiting order
+  const int L = 31 - __clz((int)v);          // level: n = 2^(L+1)
+  const double n = (double)(2u << L);
+  const double idx = (double)(2u * (v - (1u << L)) + 1u);
+  if (MODE == GC_EDGE_FROM_CONF)
+  {
+    const double abscissa = __ddiv_rn(idx, n);
+    if (!(abscissa >= g.aux))
+      return false;
+#pragma unroll
+    for (int i = 0; i < GC_MAX_DIM; i++)
+      if (i < D)
+        conf[i] = __dadd_rn(c1[i], __dmul_rn(__dsub_rn(c2[i], c1[i]), abscissa));
+    return true;
+  }
+#pragma unroll
+  for (int i = 0; i < GC_MAX_DIM; i++)
+    if (i < D)
+      conf[i] = __dadd_rn(c1[i], __ddiv_rn(__dmul_rn(__dsub_rn(c2[i], c1[i]), idx), n));
+  return true;
+}
+
+// =================================================================================================
+//  light worlds: true = collision free
+// =================================================================================================
+struct LightWorld
+{
+  int kind;
+  uint32_t nobj;
+  double cube_thr;
+  const double* lo;  // smem copies
+  const double* hi;
+  const float* sc;
+  const float* sr2;
+};
+
+template <int D>
+__device__ __forceinline__ bool light_check(const LightWorld& w, const double* q, unsigned long long& pairs)
+{
+  if (w.kind == GC_WORLD_CUBE)
+  {
+    double m = 0.0;
+#pragma unroll
+    for (int i = 0; i < GC_MAX_DIM; i++)
+      if (i < D)
+        m = fmax(m, fabs(q[i]));
+    return m > w.cube_thr;
+  }
+  if (w.kind == GC_WORLD_BOXES)
+  {
+    for (uint32_t b = 0; b < w.nobj; b++)
+    {
+      bool inside = true;
+#pragma unroll
+      for (int i = 0; i < GC_MAX_DIM; i++)
+        if (i < D)
+          inside = inside && !(q[i] < w.lo[b * D + i] || q[i] > w.hi[b * D + i]);
+      if (inside)
+        return false;
+    }
+    return true;
+  }
+  // C-space hyperspheres, fp32 (include/gcb200_spec.h)
+  float qf[D];
+#pragma unroll
+  for (int i = 0; i < D; i++)
+    qf[i] = (float)q[i];
+  bool hit = false;
+  uint32_t s = 0;
+  for (; s < w.nobj && !hit; s++)
+  {
+    const float* c = w.sc + (size_t)s * D;
+    const float t0 = __fsub_rn(qf[0], c[0]);
+    float acc = __fmul_rn(t0, t0);
+#pragma unroll
+    for (int i = 1; i < D; i++)
+    {
+      const float t = __fsub_rn(qf[i], c[i]);
+      acc = __fmaf_rn(t, t, acc);
+    }
+    hit = acc < w.sr2[s];
+  }
+  pairs += s;
+  return !hit;
+}
+
+// one warp per edge (or per state batch of 32 in STATES mode)
+struct LightArgs
+{
+  int kind;
+  uint32_t nobj;
+  double cube_thr;
+  const double* lo;
+  const double* hi;
+  const float* sc;
+  const float* sr2;
+  const double* c1;
+  const double* c2;
+  const double* c3;
+  uint32_t n;
+  double min_d;
+  uint8_t* ok;
+  unsigned long long* first_bad;
+  unsigned long long* counters;
+};
+
+// MODE 3 = plain state batch (check(q) on n configurations)
+template <int D, int MODE>
+__global__ void __launch_bounds__(256) edge_warp_kernel(LightArgs a)
+{
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  // stage the world in shared memory (read by every lane for every state)
+  LightWorld w;
+  w.kind = a.kind;
+  w.nobj = a.nobj;
+  w.cube_thr = a.cube_thr;
+  {
+    double* slo = reinterpret_cast<double*>(smem_raw);
+    double* shi = slo + (a.kind == GC_WORLD_BOXES ? (size_t)a.nobj * D : 0);
+    float* ssc = reinterpret_cast<float*>(shi + (a.kind == GC_WORLD_BOXES ? (size_t)a.nobj * D : 0));
+    float* ssr = ssc + (a.kind == GC_WORLD_CSPHERES ? (size_t)a.nobj * D : 0);
+    if (a.kind == GC_WORLD_BOXES)
+      for (uint32_t i = threadIdx.x; i < a.nobj * D; i += blockDim.x)
+      {
+        slo[i] = a.lo[i];
+        shi[i] = a.hi[i];
+      }
+    if (a.kind == GC_WORLD_CSPHERES)
+    {
+      for (uint32_t i = threadIdx.x; i < a.nobj * D; i += blockDim.x)
+        ssc[i] = a.sc[i];
+      for (uint32_t i = threadIdx.x; i < a.nobj; i += blockDim.x)
+        ssr[i] = a.sr2[i];
+    }
+    w.lo = slo;
+    w.hi = shi;
+    w.sc = ssc;
+    w.sr2 = ssr;
+  }
+  __syncthreads();
+
+  const int lane = threadIdx.x & 31;
+  const uint32_t warps_per_block = blockDim.x >> 5;
+  const uint32_t gwarp = blockIdx.x * warps_per_block + (threadIdx.x >> 5);
+  const uint32_t nwarps = gridDim.x * warps_per_block;
+  unsigned long long states = 0, pairs = 0;
+
+  if (MODE == 3)
+  {
+    for (uint32_t i = gwarp * 32u + lane; i < a.n; i += nwarps * 32u)
+    {
+      double q[D];
+#pragma unroll
+      for (int d = 0; d < D; d++)
+        q[d] = a.c1[(size_t)i * D + d];
+      a.ok[i] = light_check<D>(w, q, pairs) ? 1 : 0;
+      states++;
+    }
+  }
+  else
+  {
+    for (uint32_t e = gwarp; e < a.n; e += nwarps)
+    {
+      double c1[D], c2[D], c3[D];
+#pragma unroll
+      for (int d = 0; d < D; d++)
+      {
+        c1[d] = a.c1[(size_t)e * D + d];
+        c2[d] = a.c2[(size_t)e * D + d];
+        c3[d] = (MODE == GC_EDGE_FROM_CONF) ? a.c3[(size_t)e * D + d] : 0.0;
+      }
+      const EdgeGeom g = edge_geom<D, MODE>(c1, c2, c3, a.min_d);
+      uint8_t result = (g.nstates == 0u) ? 255 : 1;
+      unsigned long long first = ~0ull;
+      for (uint32_t s0 = 0; s0 < g.nstates; s0 += 32u)
+      {
+        const uint32_t s = s0 + lane;
+        bool bad = false;
+        if (s < g.nstates)
+        {
+          double conf[D];
+          if (state_conf<D, MODE>(c1, c2, c3, g, s, conf))
+          {
+            bad = !light_check<D>(w, conf, pairs);
+            states++;
+          }
+        }
+        const uint32_t m = __ballot_sync(0xffffffffu, bad);
+        if (m)
+        {
+          result = 0;
+          first = s0 + (uint32_t)(__ffs((int)m) - 1);
+          break;  // ballot early exit: the reference returns at its first colliding state
+        }
+      }
+      if (lane == 0)
+      {
+        a.ok[e] = result;
+        if (MODE == GC_EDGE_LINEAR && a.first_bad)
+          a.first_bad[e] = first;
+      }
+    }
+  }
+  // counters: one atomic per warp
+  for (int o = 16; o > 0; o >>= 1)
+  {
+    states += __shfl_down_sync(0xffffffffu, states, o);
+    pairs += __shfl_down_sync(0xffffffffu, pairs, o);
+  }
+  if (lane == 0 && a.counters)
+  {
+    if (states)
+      atomicAdd(&a.counters[0], states);
+    if (pairs)
+      atomicAdd(&a.counters[1], pairs);
+  }
+}
+
+// =================================================================================================
+//  sphere-arm world
+// =================================================================================================
+__device__ __forceinline__ void sincos_spec(float q, float& s, float& c)
+{
+  const float j = rintf(__fmul_rn(q, GC_TWO_OVER_PI));
+  float r = __fmaf_rn(-j, GC_PIO2_1, q);
+  r = __fmaf_rn(-j, GC_PIO2_2, r);
+  r = __fmaf_rn(-j, GC_PIO2_3, r);
+  const float z = __fmul_rn(r, r);
+  float ps = __fmaf_rn(z, GC_SIN_S3, GC_SIN_S2);
+  ps = __fmaf_rn(z, ps, GC_SIN_S1);
+  const float rz = __fmul_rn(r, z);
+  const float sn = __fmaf_rn(rz, ps, r);
+  float pc = __fmaf_rn(z, GC_COS_C3, GC_COS_C2);
+  pc = __fmaf_rn(z, pc, GC_COS_C1);
+  const float zz = __fmul_rn(z, z);
+  float cs = __fmaf_rn(z, -0.5f, 1.0f);
+  cs = __fmaf_rn(zz, pc, cs);
+  const int qd = ((int)j) & 3;
+  s = (qd == 0) ? sn : (qd == 1) ? cs : (qd == 2) ? -sn : -cs;
+  c = (qd == 0) ? cs : (qd == 1) ? -sn : (qd == 2) ? -cs : sn;
+}
+
+// o = R*p + t with the spec's operation order
+__device__ __forceinline__ void mat3_vec(const float* R, const float* t, float p0, float p1, float p2, float* o)
+{
+#pragma unroll
+  for (int r = 0; r < 3; r++)
+  {
+    float v = __fmul_rn(R[3 * r + 0], p0);
+    v = __fmaf_rn(R[3 * r + 1], p1, v);
+    v = __fmaf_rn(R[3 * r + 2], p2, v);
+    o[r] = __fadd_rn(v, t[r]);
+  }
+}
+
+// smem image of the arm: base_tf[12] | joint_tf[J][12] | rs_local[nrs][4] | rs_link[nrs] (int bits)
+struct ArmSmem
+{
+  const float* base;
+  const float* joint;
+  const float* rs_local;
+  const int* rs_link;
+  const float4* obs;
+};
+
+// one FK joint step: (AR, At) = frame A_j on entry; writes link frame B_j to (BR, At unchanged) and
+// advances (AR, At) to A_{j+1}
+__device__ __forceinline__ void fk_joint(float* AR, float* At, float* BR, float qj, const float* F)
+{
+  float s, c;
+  sincos_spec(qj, s, c);
+#pragma unroll
+  for (int r = 0; r < 3; r++)
+  {
+    const float x = AR[3 * r + 0], y = AR[3 * r + 1];
+    BR[3 * r + 0] = __fmaf_rn(s, y, __fmul_rn(c, x));
+    BR[3 * r + 1] = __fmaf_rn(-s, x, __fmul_rn(c, y));
+    BR[3 * r + 2] = AR[3 * r + 2];
+  }
+}
+__device__ __forceinline__ void fk_advance(float* AR, float* At, const float* BR, const float* F)
+{
+  float NR[9], Nt[3];
+#pragma unroll
+  for (int r = 0; r < 3; r++)
+#pragma unroll
+    for (int c = 0; c < 3; c++)
+    {
+      float v = __fmul_rn(BR[3 * r + 0], F[0 + c]);
+      v = __fmaf_rn(BR[3 * r + 1], F[3 + c], v);
+      v = __fmaf_rn(BR[3 * r + 2], F[6 + c], v);
+      NR[3 * r + c] = v;
+    }
+  mat3_vec(BR, At, F[9], F[10], F[11], Nt);
+#pragma unroll
+  for (int i = 0; i < 9; i++)
+    AR[i] = NR[i];
+#pragma unroll
+  for (int i = 0; i < 3; i++)
+    At[i] = Nt[i];
+}
+
+__device__ __forceinline__ bool pair_hit(const float4& ob, float cx, float cy, float cz, float rs)
+{
+  const float dx = __fsub_rn(ob.x, cx), dy = __fsub_rn(ob.y, cy), dz = __fsub_rn(ob.z, cz);
+  float d2 = __fmul_rn(dx, dx);
+  d2 = __fmaf_rn(dy, dy, d2);
+  d2 = __fmaf_rn(dz, dz, d2);
+  const float rr = __fadd_rn(ob.w, rs);
+  return d2 < __fmul_rn(rr, rr);
+}
+
+// G = 1: one lane owns the state, keeps all NRS sphere centres in registers, loops over all
+// obstacles (shared memory broadcast reads).  Returns true when collision free.
+template <int J, int NRS>
+__device__ __forceinline__ bool arm_check_lane(const ArmSmem& w, uint32_t nrs, uint32_t nobs, const float* qf,
+                                               unsigned long long& pairs)
+{
+  float cx[NRS], cy[NRS], cz[NRS], rs[NRS];
+  int link[NRS];
+#pragma unroll
+  for (int k = 0; k < NRS; k++)
+  {
+    link[k] = (k < (int)nrs) ? w.rs_link[k] : -1;
+    rs[k] = (k < (int)nrs) ? w.rs_local[4 * k + 3] : 0.0f;
+    cx[k] = cy[k] = cz[k] = 1.0e18f;  // padding spheres never collide
+  }
+  float AR[9], At[3], BR[9];
+#pragma unroll
+  for (int i = 0; i < 9; i++)
+    AR[i] = w.base[i];
+#pragma unroll
+  for (int i = 0; i < 3; i++)
+    At[i] = w.base[9 + i];
+#pragma unroll
+  for (int j = 0; j <= J; j++)
+  {
+    if (j < J)
+      fk_joint(AR, At, BR, qf[j < J ? j : 0], nullptr);
+    else
+    {
+#pragma unroll
+      for (int i = 0; i < 9; i++)
+        BR[i] = AR[i];
+    }
+#pragma unroll
+    for (int k = 0; k < NRS; k++)
+      if (link[k] == j)
+      {
+        float o[3];
+        mat3_vec(BR, At, w.rs_local[4 * k + 0], w.rs_local[4 * k + 1], w.rs_local[4 * k + 2], o);
+        cx[k] = o[0];
+        cy[k] = o[1];
+        cz[k] = o[2];
+      }
+    if (j < J)
+      fk_advance(AR, At, BR, w.joint + 12 * j);
+  }
+  bool hit = false;
+  uint32_t o = 0;
+  for (; o < nobs; o++)
+  {
+    const float4 ob = w.obs[o];
+#pragma unroll
+    for (int k = 0; k < NRS; k++)
+      hit |= pair_hit(ob, cx[k], cy[k], cz[k], rs[k]);
+    if ((o & 15u) == 15u && hit)
+    {
+      o++;
+      break;
+    }
+  }
+  pairs += (unsigned long long)o * nrs;
+  return !hit;
+}
+
+// G = 32: the whole warp owns the state.  Lane = (robot sphere k, obstacle slice): every lane runs
+// the (cheap) FK chain, keeps the frame of its sphere's link, then tests its sphere against its
+// slice of the obstacle cloud; a ballot combines.  Returns true when collision free (warp-uniform).
+template <int J>
+__device__ __forceinline__ bool arm_check_warp(const ArmSmem& w, uint32_t nrs, uint32_t nobs, const float* qf,
+                                               int lane, unsigned long long& pairs)
+{
+  uint32_t nrsP = 1;
+  while (nrsP < nrs)
+    nrsP <<= 1;  // nrs <= 32
+  const uint32_t k = lane % nrsP;
+  const uint32_t slice = lane / nrsP, nslices = 32u / nrsP;
+  const bool active = k < nrs;
+  const int mylink = active ? w.rs_link[k] : -1;
+  float AR[9], At[3], BR[9], FR[9], Ft[3];
+#pragma unroll
+  for (int i = 0; i < 9; i++)
+  {
+    AR[i] = w.base[i];
+    FR[i] = 0.0f;
+  }
+#pragma unroll
+  for (int i = 0; i < 3; i++)
+  {
+    At[i] = w.base[9 + i];
+    Ft[i] = 0.0f;
+  }
+#pragma unroll
+  for (int j = 0; j <= J; j++)
+  {
+    if (j < J)
+      fk_joint(AR, At, BR, qf[j < J ? j : 0], nullptr);
+    else
+    {
+#pragma unroll
+      for (int i = 0; i < 9; i++)
+        BR[i] = AR[i];
+    }
+    if (mylink == j)
+    {
+#pragma unroll
+      for (int i = 0; i < 9; i++)
+        FR[i] = BR[i];
+#pragma unroll
+      for (int i = 0; i < 3; i++)
+        Ft[i] = At[i];
+    }
+    if (j < J)
+      fk_advance(AR, At, BR, w.joint + 12 * j);
+  }
+  float c[3] = { 1.0e18f, 1.0e18f, 1.0e18f };
+  float rs = 0.0f;
+  if (active)
+  {
+    mat3_vec(FR, Ft, w.rs_local[4 * k + 0], w.rs_local[4 * k + 1], w.rs_local[4 * k + 2], c);
+    rs = w.rs_local[4 * k + 3];
+  }
+  bool hit = false;
+  uint32_t done = 0;
+  for (uint32_t o0 = 0; o0 < nobs; o0 += nslices * 8u)
+  {
+#pragma unroll
+    for (uint32_t u = 0; u < 8u; u++)
+    {
+      const uint32_t o = o0 + u * nslices + slice;
+      if (active && o < nobs)
+      {
+        hit |= pair_hit(w.obs[o], c[0], c[1], c[2], rs);
+        done++;
+      }
+    }
+    if (__any_sync(0xffffffffu, hit))
+      break;
+  }
+  pairs += done;
+  return !__any_sync(0xffffffffu, hit);
+}
+
+// ---- plan: per-edge geometry + exclusive prefix sum of the state counts (single CTA) ----------------
+struct PlanArgs
+{
+  const double* c1;
+  const double* c2;
+  const double* c3;
+  uint32_t n;
+  double min_d;
+  double* dist;        // [n]
+  double* aux;         // [n]
+  uint32_t* offs;      // [n+1] exclusive prefix of nstates
+  uint8_t* ok;         // initialised here: 1, or 255 when the reference would throw
+  unsigned long long* first_bad;
+};
+
+template <int D, int MODE>
+__global__ void __launch_bounds__(1024) edge_plan_kernel(PlanArgs a)
+{
+  __shared__ uint32_t warp_sums[32];
+  __shared__ uint32_t carry_s;
+  if (threadIdx.x == 0)
+  {
+    carry_s = 0;
+    a.offs[0] = 0;
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  for (uint32_t base = 0; base < a.n; base += blockDim.x)
+  {
+    const uint32_t e = base + threadIdx.x;
+    uint32_t ns = 0;
+    if (e < a.n)
+    {
+      double c1[D], c2[D], c3[D];
+#pragma unroll
+      for (int d = 0; d < D; d++)
+      {
+        c1[d] = a.c1[(size_t)e * D + d];
+        c2[d] = a.c2[(size_t)e * D + d];
+        c3[d] = (MODE == GC_EDGE_FROM_CONF) ? a.c3[(size_t)e * D + d] : 0.0;
+      }
+      const EdgeGeom g = edge_geom<D, MODE>(c1, c2, c3, a.min_d);
+      a.dist[e] = g.dist;
+      a.aux[e] = g.aux;
+      a.ok[e] = (g.nstates == 0u) ? 255 : 1;
+      if (a.first_bad)
+        a.first_bad[e] = ~0ull;
+      ns = g.nstates;
+    }
+    // block-wide inclusive scan
+    uint32_t v = ns;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1)
+    {
+      const uint32_t t = __shfl_up_sync(0xffffffffu, v, o);
+      if (lane >= o)
+        v += t;
+    }
+    if (lane == 31)
+      warp_sums[wid] = v;
+    __syncthreads();
+    if (wid == 0)
+    {
+      uint32_t ws = (lane < (int)(blockDim.x >> 5)) ? warp_sums[lane] : 0;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1)
+      {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, ws, o);
+        if (lane >= o)
+          ws += t;
+      }
+      warp_sums[lane] = ws;
+    }
+    __syncthreads();
+    const uint32_t carry = carry_s;
+    const uint32_t incl = v + (wid > 0 ? warp_sums[wid - 1] : 0) + carry;
+    if (e < a.n)
+      a.offs[e + 1] = incl;
+    __syncthreads();
+    if (threadIdx.x == blockDim.x - 1)
+      carry_s = incl;
+    __syncthreads();
+  }
+}
+
+struct ArmArgs
+{
+  // world
+  const float* arm;   // global image (base | joints | rs_local | rs_link)
+  const float* obs;
+  int njoints;
+  uint32_t nrs;
+  uint32_t nobs;
+  // edges
+  const double* c1;
+  const double* c2;
+  const double* c3;
+  uint32_t n;
+  const double* dist;
+  const double* aux;
+  const uint32_t* offs;
+  uint8_t* ok;
+  unsigned long long* first_bad;
+  unsigned long long* counters;
+  int mode;  // gc_edge_mode, or 3 = plain state batch
+};
+
+template <int D>
+__device__ __forceinline__ bool state_conf_rt(int mode, const double* c1, const double* c2, const double* c3,
+                                              const EdgeGeom& g, uint32_t s, double* conf)
+{
+  if (mode == GC_EDGE_BISECT)
+    return state_conf<D, GC_EDGE_BISECT>(c1, c2, c3, g, s, conf);
+  if (mode == GC_EDGE_LINEAR)
+    return state_conf<D, GC_EDGE_LINEAR>(c1, c2, c3, g, s, conf);
+  return state_conf<D, GC_EDGE_FROM_CONF>(c1, c2, c3, g, s, conf);
+}
+
+__device__ __forceinline__ ArmSmem arm_stage(const ArmArgs& a, unsigned char* smem_raw)
+{
+  float4* sobs = reinterpret_cast<float4*>(smem_raw);
+  float* sarm = reinterpret_cast<float*>(sobs + a.nobs);
+  const uint32_t arm_words = 12u + 12u * a.njoints + 4u * a.nrs + a.nrs;
+  for (uint32_t i = threadIdx.x; i < a.nobs; i += blockDim.x)
+    sobs[i] = reinterpret_cast<const float4*>(a.obs)[i];
+  for (uint32_t i = threadIdx.x; i < arm_words; i += blockDim.x)
+    sarm[i] = a.arm[i];
+  __syncthreads();
+  ArmSmem w;
+  w.obs = sobs;
+  w.base = sarm;
+  w.joint = sarm + 12;
+  w.rs_local = w.joint + 12 * a.njoints;
+  w.rs_link = reinterpret_cast<const int*>(w.rs_local + 4 * a.nrs);
+  return w;
+}
+
+// finds e with offs[e] <= t < offs[e+1]
+__device__ __forceinline__ uint32_t find_edge(const uint32_t* __restrict__ offs, uint32_t n, uint32_t t)
+{
+  uint32_t lo = 0, hi = n;  // invariant offs[lo] <= t < offs[hi]
+  while (hi - lo > 1)
+  {
+    const uint32_t mid = (lo + hi) >> 1;
+    if (__ldg(&offs[mid]) <= t)
+      lo = mid;
+    else
+      hi = mid;
+  }
+  return lo;
+}
+
+// a.mode 3 = plain state batch.  G = 1 or 32 lanes per state.  D == njoints.
+template <int D, int NRS, int G>
+__global__ void __launch_bounds__(G == 1 ? 128 : 256) arm_state_kernel(ArmArgs a)
+{
+  const int MODE = a.mode;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const ArmSmem w = arm_stage(a, smem_raw);
+  const int lane = threadIdx.x & 31;
+  const uint32_t total = (MODE == 3) ? a.n : a.offs[a.n];
+  unsigned long long states = 0, pairs = 0;
+  const uint32_t gthread = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t nthreads = gridDim.x * blockDim.x;
+  const uint32_t item0 = (G == 1) ? gthread : (gthread >> 5);
+  const uint32_t nitems = (G == 1) ? nthreads : (nthreads >> 5);
+  // round the trip count up so that every lane of a warp takes part in the warp-wide votes
+  const uint32_t trips = (total + nitems - 1) / nitems;
+  for (uint32_t it = 0; it < trips; it++)
+  {
+    const uint32_t t = item0 + it * nitems;
+    bool have = t < total;
+    uint32_t e = 0, s = 0;
+    float qf[D];
+    if (have)
+    {
+      double conf[D];
+      if (MODE == 3)
+      {
+        e = t;
+#pragma unroll
+        for (int d = 0; d < D; d++)
+          conf[d] = a.c1[(size_t)t * D + d];
+      }
+      else
+      {
+        e = find_edge(a.offs, a.n, t);
+        s = t - a.offs[e];
+        // early exit: the reference stops at its first colliding state
+        if (MODE == GC_EDGE_LINEAR)
+          have = !(a.first_bad[e] < (unsigned long long)s);
+        else
+          have = (*reinterpret_cast<volatile uint8_t*>(a.ok + e) == 1);
+        if (have)
+        {
+          double c1[D], c2[D], c3[D];
+#pragma unroll
+          for (int d = 0; d < D; d++)
+          {
+            c1[d] = a.c1[(size_t)e * D + d];
+            c2[d] = a.c2[(size_t)e * D + d];
+            c3[d] = (MODE == GC_EDGE_FROM_CONF) ? a.c3[(size_t)e * D + d] : 0.0;
+          }
+          EdgeGeom g;
+          g.dist = a.dist[e];
+          g.aux = a.aux[e];
+          g.nstates = a.offs[e + 1] - a.offs[e];
+          have = state_conf_rt<D>(MODE, c1, c2, c3, g, s, conf);
+        }
+      }
+#pragma unroll
+      for (int d = 0; d < D; d++)
+        qf[d] = have ? (float)conf[d] : 0.0f;
+    }
+    else
+    {
+#pragma unroll
+      for (int d = 0; d < D; d++)
+        qf[d] = 0.0f;
+    }
+    bool free_state = true;
+    if (G == 1)
+    {
+      if (have)
+      {
+        free_state = arm_check_lane<D, NRS>(w, a.nrs, a.nobs, qf, pairs);
+        states++;
+      }
+    }
+    else
+    {
+      // warp-uniform: 'have' is identical in all lanes (same item)
+      if (have)
+      {
+        free_state = arm_check_warp<D>(w, a.nrs, a.nobs, qf, lane, pairs);
+        if (lane == 0)
+          states++;
+      }
+    }
+    if (have && (G == 1 || lane == 0))
+    {
+      if (MODE == 3)
+        a.ok[e] = free_state ? 1 : 0;
+      else if (!free_state)
+      {
+        a.ok[e] = 0;
+        if (MODE == GC_EDGE_LINEAR && a.first_bad)
+          atomicMin(&a.first_bad[e], (unsigned long long)s);
+      }
+    }
+  }
+  for (int o = 16; o > 0; o >>= 1)
+  {
+    states += __shfl_down_sync(0xffffffffu, states, o);
+    pairs += __shfl_down_sync(0xffffffffu, pairs, o);
+  }
+  if (lane == 0 && a.counters)
+  {
+    if (states)
+      atomicAdd(&a.counters[0], states);
+    if (pairs)
+      atomicAdd(&a.counters[1], pairs);
+  }
+}
+
+// =================================================================================================
+//  launchers
+// =================================================================================================
+#define GC_DISPATCH_DIM_E(dim, ...)                                           \
+  switch (dim)                                                                \
+  {                                                                           \
+    case 1: { constexpr int DD = 1; __VA_ARGS__; } break;                     \
+    case 2: { constexpr int DD = 2; __VA_ARGS__; } break;                     \
+    case 3: { constexpr int DD = 3; __VA_ARGS__; } break;                     \
+    case 4: { constexpr int DD = 4; __VA_ARGS__; } break;                     \
+    case 5: { constexpr int DD = 5; __VA_ARGS__; } break;                     \
+    case 6: { constexpr int DD = 6; __VA_ARGS__; } break;                     \
+    case 7: { constexpr int DD = 7; __VA_ARGS__; } break;                     \
+    case 8: { constexpr int DD = 8; __VA_ARGS__; } break;                     \
+    case 9: { constexpr int DD = 9; __VA_ARGS__; } break;                     \
+    case 10: { constexpr int DD = 10; __VA_ARGS__; } break;                   \
+    case 11: { constexpr int DD = 11; __VA_ARGS__; } break;                   \
+    case 12: { constexpr int DD = 12; __VA_ARGS__; } break;                   \
+    case 13: { constexpr int DD = 13; __VA_ARGS__; } break;                   \
+    case 14: { constexpr int DD = 14; __VA_ARGS__; } break;                   \
+    case 15: { constexpr int DD = 15; __VA_ARGS__; } break;                   \
+    case 16: { constexpr int DD = 16; __VA_ARGS__; } break;                   \
+    default: gc::set_error("dimension %d not in [1,%d]", dim, GC_MAX_DIM); return GC_E_INVALID; \
+  }
+#define GC_DISPATCH_MODE(mode, ...)                                                  \
+  switch (mode)                                                                      \
+  {                                                                                  \
+    case GC_EDGE_BISECT: { constexpr int MM = GC_EDGE_BISECT; __VA_ARGS__; } break;  \
+    case GC_EDGE_LINEAR: { constexpr int MM = GC_EDGE_LINEAR; __VA_ARGS__; } break;  \
+    case GC_EDGE_FROM_CONF: { constexpr int MM = GC_EDGE_FROM_CONF; __VA_ARGS__; } break; \
+    default: gc::set_error("unknown edge mode %d", mode); return GC_E_INVALID;       \
+  }
+
+static size_t light_smem(const gc_world* w)
+{
+  if (w->kind == GC_WORLD_BOXES)
+    return 2 * sizeof(double) * (size_t)w->nobj * w->dim;
+  if (w->kind == GC_WORLD_CSPHERES)
+    return sizeof(float) * ((size_t)w->nobj * w->dim + w->nobj);
+  return 0;
+}
+
+template <int D, int MODE>
+static int launch_light(gc_world* w, const LightArgs& a, cudaStream_t st)
+{
+  const size_t smem = light_smem(w);
+  if (smem > 200 * 1024)
+  {
+    gc::set_error("world too large for shared memory staging (%zu bytes)", smem);
+    return GC_E_UNSUPPORTED;
+  }
+  if (smem > 48 * 1024)
+    GC_CUDA(cudaFuncSetAttribute(edge_warp_kernel<D, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const uint32_t warps_needed = (MODE == 3) ? (a.n + 31) / 32 : a.n;
+  uint32_t blocks = (warps_needed + 7) / 8;
+  const uint32_t max_blocks = (uint32_t)w->sms * 8u;
+  if (blocks > max_blocks)
+    blocks = max_blocks;
+  if (blocks < 1)
+    blocks = 1;
+  edge_warp_kernel<D, MODE><<<blocks, 256, smem, st>>>(a);
+  GC_CUDA(cudaGetLastError());
+  return GC_OK;
+}
+
+template <int D, int NRS, int G>
+static int launch_arm(gc_world* w, const ArmArgs& a, uint64_t items_hint, cudaStream_t st)
+{
+  const size_t smem = sizeof(float4) * a.nobs + sizeof(float) * (12 + 12 * a.njoints + 5 * a.nrs) + 16;
+  if (smem > 200 * 1024)
+  {
+    gc::set_error("obstacle cloud too large for shared memory staging (%zu bytes)", smem);
+    return GC_E_UNSUPPORTED;
+  }
+  if (smem > 48 * 1024)
+    GC_CUDA(cudaFuncSetAttribute(arm_state_kernel<D, NRS, G>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)smem));
+  const int threads = (G == 1) ? 128 : 256;
+  const uint64_t items_per_block = (G == 1) ? threads : threads / 32;
+  uint64_t blocks = (items_hint + items_per_block - 1) / items_per_block;
+  const uint64_t max_blocks = (uint64_t)w->sms * ((G == 1) ? 4 : 8);
+  if (blocks > max_blocks)
+    blocks = max_blocks;
+  if (blocks < 1)
+    blocks = 1;
+  arm_state_kernel<D, NRS, G><<<(unsigned)blocks, threads, smem, st>>>(a);
+  GC_CUDA(cudaGetLastError());
+  return GC_OK;
+}
+
+template <int D>
+static int launch_arm_nrs(gc_world* w, const ArmArgs& a, uint64_t items_hint, cudaStream_t st)
+{
+  // lane-per-state only pays off once the flattened work list fills the machine
+  const bool lane_mode = items_hint >= (uint64_t)w->sms * 128u * 2u;
+  if (!lane_mode)
+    return launch_arm<D, 16, 32>(w, a, items_hint, st);
+  if (a.nrs <= 16)
+    return launch_arm<D, 16, 1>(w, a, items_hint, st);
+  return launch_arm<D, 32, 1>(w, a, items_hint, st);
+}
+
+static int time_begin(gc_world* w, cudaStream_t st)
+{
+  if (w->timing)
+    GC_CUDA(cudaEventRecord(w->ev0, st));
+  return GC_OK;
+}
+static int time_end(gc_world* w, cudaStream_t st)
+{
+  w->launches++;
+  if (w->timing)
+  {
+    GC_CUDA(cudaEventRecord(w->ev1, st));
+    GC_CUDA(cudaEventSynchronize(w->ev1));
+    float ms = 0.f;
+    GC_CUDA(cudaEventElapsedTime(&ms, w->ev0, w->ev1));
+    w->kernel_ns += (uint64_t)((double)ms * 1.0e6);
+  }
+  return GC_OK;
+}
+
+int check_edges_dev(gc_world* w, const double* d_c1, const double* d_c2, const double* d_c3, uint32_t n,
+                    double min_distance, int mode, uint8_t* d_ok, int64_t* d_first_bad, uint64_t states_hint,
+                    cudaStream_t st)
+{
+  if (n == 0)
+    return GC_OK;
+  GC_REQUIRE(min_distance > 0.0, "min_distance must be > 0 (got %g)", min_distance);
+  GC_REQUIRE(mode >= 0 && mode <= 2, "unknown edge mode %d", mode);
+  GC_TRY(time_begin(w, st));
+  if (w->kind != GC_WORLD_SPHERE_ARM)
+  {
+    LightArgs a{};
+    a.kind = w->kind;
+    a.nobj = w->nobj;
+    a.cube_thr = w->cube_thr;
+    a.lo = w->d_lo;
+    a.hi = w->d_hi;
+    a.sc = w->d_sc;
+    a.sr2 = w->d_sr2;
+    a.c1 = d_c1;
+    a.c2 = d_c2;
+    a.c3 = d_c3;
+    a.n = n;
+    a.min_d = min_distance;
+    a.ok = d_ok;
+    a.first_bad = reinterpret_cast<unsigned long long*>(d_first_bad);
+    a.counters = w->d_counters;
+    GC_DISPATCH_DIM_E(w->dim, GC_DISPATCH_MODE(mode, 
+                                               GC_TRY((launch_light<DD, MM>(w, a, st)))));
+  }
+  else
+  {
+    GC_TRY(w->d_plan.reserve(sizeof(double) * 2 * (size_t)n));
+    GC_TRY(w->d_offs.reserve(sizeof(uint32_t) * ((size_t)n + 1)));
+    PlanArgs p{};
+    p.c1 = d_c1;
+    p.c2 = d_c2;
+    p.c3 = d_c3;
+    p.n = n;
+    p.min_d = min_distance;
+    p.dist = w->d_plan.as<double>();
+    p.aux = p.dist + n;
+    p.offs = w->d_offs.as<uint32_t>();
+    p.ok = d_ok;
+    p.first_bad = reinterpret_cast<unsigned long long*>(d_first_bad);
+    ArmArgs a{};
+    a.arm = w->d_arm;
+    a.obs = w->d_obs;
+    a.njoints = w->njoints;
+    a.nrs = w->nrs;
+    a.nobs = w->nobj;
+    a.c1 = d_c1;
+    a.c2 = d_c2;
+    a.c3 = d_c3;
+    a.n = n;
+    a.dist = p.dist;
+    a.aux = p.aux;
+    a.offs = p.offs;
+    a.ok = d_ok;
+    a.first_bad = p.first_bad;
+    a.counters = w->d_counters;
+    a.mode = mode;
+    const int pthreads = n >= 1024 ? 1024 : (int)align_up(n, 32);
+    GC_DISPATCH_DIM_E(w->dim, GC_DISPATCH_MODE(mode, 
+                                               (edge_plan_kernel<DD, MM><<<1, pthreads, 0, st>>>(p));
+                                               GC_CUDA(cudaGetLastError())); GC_TRY((launch_arm_nrs<DD>(w, a, states_hint, st))));
+  }
+  return time_end(w, st);
+}
+
+int check_states_dev(gc_world* w, const double* d_q, uint32_t n, uint8_t* d_ok, cudaStream_t st)
+{
+  if (n == 0)
+    return GC_OK;
+  GC_TRY(time_begin(w, st));
+  if (w->kind != GC_WORLD_SPHERE_ARM)
+  {
+    LightArgs a{};
+    a.kind = w->kind;
+    a.nobj = w->nobj;
+    a.cube_thr = w->cube_thr;
+    a.lo = w->d_lo;
+    a.hi = w->d_hi;
+    a.sc = w->d_sc;
+    a.sr2 = w->d_sr2;
+    a.c1 = d_q;
+    a.n = n;
+    a.min_d = 1.0;
+    a.ok = d_ok;
+    a.counters = w->d_counters;
+    GC_DISPATCH_DIM_E(w->dim, GC_TRY((launch_light<DD, 3>(w, a, st))));
+  }
+  else
+  {
+    ArmArgs a{};
+    a.arm = w->d_arm;
+    a.obs = w->d_obs;
+    a.njoints = w->njoints;
+    a.nrs = w->nrs;
+    a.nobs = w->nobj;
+    a.c1 = d_q;
+    a.n = n;
+    a.ok = d_ok;
+    a.counters = w->d_counters;
+    a.mode = 3;
+    GC_DISPATCH_DIM_E(w->dim, GC_TRY((launch_arm_nrs<DD>(w, a, n, st))));
+  }
+  return time_end(w, st);
+}
+
+}  // namespace gc
+
+// =================================================================================================
+//  C ABI: worlds and checks
+// =================================================================================================
+using namespace gc;
+
+static int world_new(int kind, int dim, int device, gc_world** out)
+{
+  GC_REQUIRE(out != nullptr, "gc_world_create: out is NULL");
+  *out = nullptr;
+  GC_REQUIRE(dim >= 1 && dim <= GC_MAX_DIM, "gc_world_create: dim %d not in [1,%d]", dim, GC_MAX_DIM);
+  int ndev = 0;
+  GC_TRY(gc_device_count(&ndev));
+  GC_REQUIRE(device >= 0 && device < ndev, "gc_world_create: device %d of %d (no CPU fallback exists)", device, ndev);
+  GC_CUDA(cudaSetDevice(device));
+  gc_world* w = new gc_world();
+  w->device = device;
+  w->kind = kind;
+  w->dim = dim;
+  w->sms = num_sms(device);
+  cudaError_t e = cudaStreamCreateWithFlags(&w->own_stream, cudaStreamNonBlocking);
+  if (e == cudaSuccess)
+    e = cudaMalloc(&w->d_counters, 2 * sizeof(unsigned long long));
+  if (e == cudaSuccess)
+    e = cudaMemset(w->d_counters, 0, 2 * sizeof(unsigned long long));
+  if (e == cudaSuccess)
+    e = cudaEventCreate(&w->ev0);
+  if (e == cudaSuccess)
+    e = cudaEventCreate(&w->ev1);
+  if (e != cudaSuccess)
+  {
+    gc::set_error("gc_world_create: %s", cudaGetErrorString(e));
+    gc_world_destroy(w);
+    return GC_E_CUDA;
+  }
+  w->stream = w->own_stream;
+  *out = w;
+  return GC_OK;
+}
+
+template <typename T>
+static int upload(T** dst, const T* src, size_t count)
+{
+  GC_CUDA(cudaMalloc(dst, sizeof(T) * (count ? count : 1)));
+  if (count)
+    GC_CUDA(cudaMemcpy(*dst, src, sizeof(T) * count, cudaMemcpyHostToDevice));
+  return GC_OK;
+}
+
+extern "C" {
+
+int gc_world_create_cube(int dim, double threshold, int device, gc_world_t** out)
+{
+  GC_TRY(world_new(GC_WORLD_CUBE, dim, device, out));
+  (*out)->cube_thr = threshold;
+  return GC_OK;
+}
+
+int gc_world_create_boxes(int dim, uint32_t n, const double* lo, const double* hi, int device, gc_world_t** out)
+{
+  GC_REQUIRE(n == 0 || (lo && hi), "gc_world_create_boxes: NULL bounds");
+  GC_TRY(world_new(GC_WORLD_BOXES, dim, device, out));
+  gc_world* w = *out;
+  w->nobj = n;
+  int rc = upload(&w->d_lo, lo, (size_t)n * dim);
+  if (rc == GC_OK)
+    rc = upload(&w->d_hi, hi, (size_t)n * dim);
+  if (rc != GC_OK)
+  {
+    gc_world_destroy(w);
+    *out = nullptr;
+  }
+  return rc;
+}
+
+int gc_world_create_cspheres(int dim, uint32_t n, const float* centers, const float* radii, int device,
+                             gc_world_t** out)
+{
+  GC_REQUIRE(n == 0 || (centers && radii), "gc_world_create_cspheres: NULL arrays");
+  GC_TRY(world_new(GC_WORLD_CSPHERES, dim, device, out));
+  gc_world* w = *out;
+  w->nobj = n;
+  std::vector<float> r2(n);
+  for (uint32_t i = 0; i < n; i++)
+    r2[i] = radii[i] * radii[i];  // single fp32 multiply, same as the oracle
+  int rc = upload(&w->d_sc, centers, (size_t)n * dim);
+  if (rc == GC_OK)
+    rc = upload(&w->d_sr2, r2.data(), (size_t)n);
+  if (rc != GC_OK)
+  {
+    gc_world_destroy(w);
+    *out = nullptr;
+  }
+  return rc;
+}
+
+int gc_world_create_sphere_arm(int njoints, const float* base_tf, const float* joint_tf, uint32_t nrs,
+                               const int32_t* rs_link, const float* rs_local, uint32_t nobs, const float* obs,
+                               int device, gc_world_t** out)
+{
+  GC_REQUIRE(base_tf && joint_tf && rs_link && rs_local && (nobs == 0 || obs), "gc_world_create_sphere_arm: NULL");
+  GC_REQUIRE(njoints >= 1 && njoints <= GC_MAX_JOINTS, "njoints %d not in [1,%d]", njoints, GC_MAX_JOINTS);
+  GC_REQUIRE(nrs >= 1 && nrs <= GC_MAX_ROBOT_SPHERES, "robot spheres %u not in [1,%d]", nrs, GC_MAX_ROBOT_SPHERES);
+  for (uint32_t k = 0; k < nrs; k++)
+    GC_REQUIRE(rs_link[k] >= 0 && rs_link[k] <= njoints, "rs_link[%u] = %d not in [0,%d]", k, rs_link[k], njoints);
+  GC_TRY(world_new(GC_WORLD_SPHERE_ARM, njoints, device, out));
+  gc_world* w = *out;
+  w->njoints = njoints;
+  w->nrs = nrs;
+  w->nobj = nobs;
+  std::vector<float> img(12 + 12 * (size_t)njoints + 5 * (size_t)nrs);
+  memcpy(img.data(), base_tf, 12 * sizeof(float));
+  memcpy(img.data() + 12, joint_tf, 12 * sizeof(float) * njoints);
+  memcpy(img.data() + 12 + 12 * njoints, rs_local, 4 * sizeof(float) * nrs);
+  memcpy(img.data() + 12 + 12 * njoints + 4 * nrs, rs_link, sizeof(int32_t) * nrs);
+  int rc = upload(&w->d_arm, img.data(), img.size());
+  if (rc == GC_OK)
+    rc = upload(&w->d_obs, obs, 4 * (size_t)nobs);
+  if (rc != GC_OK)
+  {
+    gc_world_destroy(w);
+    *out = nullptr;
+  }
+  return rc;
+}
+
+int gc_world_retain(gc_world_t* w)
+{
+  GC_REQUIRE(w != nullptr, "gc_world_retain: NULL");
+  w->refs++;
+  return GC_OK;
+}
+
+int gc_world_destroy(gc_world_t* w)
+{
+  if (!w)
+    return GC_OK;
+  if (--w->refs > 0)
+    return GC_OK;
+  cudaSetDevice(w->device);
+  if (w->own_stream)
+    cudaStreamSynchronize(w->own_stream);
+  cudaFree(w->d_lo); cudaFree(w->d_hi); cudaFree(w->d_sc); cudaFree(w->d_sr2);
+  cudaFree(w->d_arm); cudaFree(w->d_obs); cudaFree(w->d_counters);
+  w->d_c1.release(); w->d_c2.release(); w->d_c3.release(); w->d_ok.release(); w->d_first.release();
+  w->d_plan.release(); w->d_offs.release(); w->d_blocksum.release();
+  w->h_in.release(); w->h_out.release();
+  if (w->ev0) cudaEventDestroy(w->ev0);
+  if (w->ev1) cudaEventDestroy(w->ev1);
+  if (w->own_stream) cudaStreamDestroy(w->own_stream);
+  delete w;
+  return GC_OK;
+}
+
+int gc_world_set_stream(gc_world_t* w, void* cuda_stream)
+{
+  GC_REQUIRE(w != nullptr, "gc_world_set_stream: NULL");
+  GC_CUDA(cudaStreamSynchronize(w->stream));
+  w->stream = cuda_stream ? reinterpret_cast<cudaStream_t>(cuda_stream) : w->own_stream;
+  return GC_OK;
+}
+
+int gc_world_dim(gc_world_t* w) { return w ? w->dim : GC_E_INVALID; }
+
+int gc_world_counters(gc_world_t* w, uint64_t out[4])
+{
+  GC_REQUIRE(w && out, "gc_world_counters: NULL");
+  GC_CUDA(cudaSetDevice(w->device));
+  unsigned long long c[2];
+  GC_CUDA(cudaStreamSynchronize(w->stream));
+  GC_CUDA(cudaMemcpy(c, w->d_counters, sizeof(c), cudaMemcpyDeviceToHost));
+  out[0] = c[0];
+  out[1] = c[1];
+  out[2] = w->launches;
+  out[3] = w->kernel_ns;
+  return GC_OK;
+}
+int gc_world_reset_counters(gc_world_t* w)
+{
+  GC_REQUIRE(w != nullptr, "gc_world_reset_counters: NULL");
+  GC_CUDA(cudaSetDevice(w->device));
+  GC_CUDA(cudaStreamSynchronize(w->stream));
+  GC_CUDA(cudaMemset(w->d_counters, 0, 2 * sizeof(unsigned long long)));
+  w->launches = 0;
+  w->kernel_ns = 0;
+  return GC_OK;
+}
+int gc_world_enable_timing(gc_world_t* w, int on)
+{
+  GC_REQUIRE(w != nullptr, "gc_world_enable_timing: NULL");
+  w->timing = on != 0;
+  return GC_OK;
+}
+
+int gc_check_states_dev(gc_world_t* w, const double* d_q, uint32_t n, uint8_t* d_ok)
+{
+  GC_REQUIRE(w && d_q && d_ok, "gc_check_states_dev: NULL argument");
+  GC_CUDA(cudaSetDevice(w->device));
+  return check_states_dev(w, d_q, n, d_ok, w->stream);
+}
+
+int gc_check_edges_dev(gc_world_t* w, const double* d_c1, const double* d_c2, uint32_t n, double min_distance,
+                       int mode, uint8_t* d_ok, int64_t* d_first_bad)
+{
+  GC_REQUIRE(w && d_c1 && d_c2 && d_ok, "gc_check_edges_dev: NULL argument");
+  GC_REQUIRE(mode == GC_EDGE_BISECT || mode == GC_EDGE_LINEAR, "gc_check_edges_dev: mode %d", mode);
+  GC_REQUIRE(mode != GC_EDGE_LINEAR || d_first_bad, "gc_check_edges_dev: LINEAR mode needs first_bad");
+  GC_CUDA(cudaSetDevice(w->device));
+  return check_edges_dev(w, d_c1, d_c2, nullptr, n, min_distance, mode, d_ok, d_first_bad, (uint64_t)n * 64u,
+                         w->stream);
+}
+
+int gc_check_states(gc_world_t* w, const double* q, uint32_t n, uint8_t* ok)
+{
+  GC_REQUIRE(w && q && ok, "gc_check_states: NULL argument");
+  if (n == 0)
+    return GC_OK;
+  GC_CUDA(cudaSetDevice(w->device));
+  const size_t qb = sizeof(double) * (size_t)n * w->dim;
+  GC_TRY(w->h_in.reserve(qb));
+  GC_TRY(w->h_out.reserve(n));
+  GC_TRY(w->d_c1.reserve(qb));
+  GC_TRY(w->d_ok.reserve(n));
+  GC_CUDA(cudaStreamSynchronize(w->stream));
+  memcpy(w->h_in.p, q, qb);
+  GC_CUDA(cudaMemcpyAsync(w->d_c1.p, w->h_in.p, qb, cudaMemcpyHostToDevice, w->stream));
+  GC_TRY(check_states_dev(w, w->d_c1.as<double>(), n, w->d_ok.as<uint8_t>(), w->stream));
+  GC_CUDA(cudaMemcpyAsync(w->h_out.p, w->d_ok.p, n, cudaMemcpyDeviceToHost, w->stream));
+  GC_CUDA(cudaStreamSynchronize(w->stream));
+  memcpy(ok, w->h_out.p, n);
+  return GC_OK;
+}
+
+// number of states the reference visits on a collision-free edge (host copy of edge_geom, for grid sizing only)
+static uint64_t host_states(const double* c1, const double* c2, int dim, double min_d, int mode)
+{
+  double s = 0;
+  for (int i = 0; i < dim; i++)
+    s += (c2[i] - c1[i]) * (c2[i] - c1[i]);
+  const double dist = sqrt(s);
+  if (mode == GC_EDGE_LINEAR)
+    return (uint64_t)fmin(ceil(dist / min_d), 1.0e9) + 1;
+  uint64_t cnt = 2;
+  double n = 2;
+  while (dist > n * min_d && cnt < (1ull << 30))
+  {
+    cnt += (uint64_t)(n / 2);
+    n *= 2;
+  }
+  return cnt;
+}
+
+static int check_edges_host(gc_world* w, const double* c1, const double* c2, const double* c3, uint32_t n,
+                            double min_distance, int mode, uint8_t* ok, int64_t* first_bad)
+{
+  if (n == 0)
+    return GC_OK;
+  GC_REQUIRE(min_distance > 0.0, "min_distance must be > 0 (got %g)", min_distance);
+  GC_CUDA(cudaSetDevice(w->device));
+  const size_t qb = sizeof(double) * (size_t)n * w->dim;
+  const int narr = c3 ? 3 : 2;
+  GC_TRY(w->h_in.reserve(qb * narr));
+  GC_TRY(w->h_out.reserve(n + sizeof(int64_t) * (size_t)n + 16));
+  GC_TRY(w->d_c1.reserve(qb));
+  GC_TRY(w->d_c2.reserve(qb));
+  if (c3)
+    GC_TRY(w->d_c3.reserve(qb));
+  GC_TRY(w->d_ok.reserve(n));
+  GC_TRY(w->d_first.reserve(sizeof(int64_t) * (size_t)n));
+  GC_CUDA(cudaStreamSynchronize(w->stream));
+  char* h = static_cast<char*>(w->h_in.p);
+  memcpy(h, c1, qb);
+  memcpy(h + qb, c2, qb);
+  if (c3)
+    memcpy(h + 2 * qb, c3, qb);
+  uint64_t hint = 0;
+  if (w->kind == GC_WORLD_SPHERE_ARM)
+    for (uint32_t i = 0; i < n; i++)
+      hint += host_states((c3 ? c3 : c1) + (size_t)i * w->dim, c2 + (size_t)i * w->dim, w->dim, min_distance, mode);
+  GC_CUDA(cudaMemcpyAsync(w->d_c1.p, h, qb, cudaMemcpyHostToDevice, w->stream));
+  GC_CUDA(cudaMemcpyAsync(w->d_c2.p, h + qb, qb, cudaMemcpyHostToDevice, w->stream));
+  if (c3)
+    GC_CUDA(cudaMemcpyAsync(w->d_c3.p, h + 2 * qb, qb, cudaMemcpyHostToDevice, w->stream));
+  GC_TRY(check_edges_dev(w, w->d_c1.as<double>(), w->d_c2.as<double>(), c3 ? w->d_c3.as<double>() : nullptr, n,
+                         min_distance, mode, w->d_ok.as<uint8_t>(), w->d_first.as<int64_t>(), hint, w->stream));
+  char* ho = static_cast<char*>(w->h_out.p);
+  const size_t ok_bytes = align_up(n, 16);
+  GC_CUDA(cudaMemcpyAsync(ho, w->d_ok.p, n, cudaMemcpyDeviceToHost, w->stream));
+  if (first_bad)
+    GC_CUDA(cudaMemcpyAsync(ho + ok_bytes, w->d_first.p, sizeof(int64_t) * (size_t)n, cudaMemcpyDeviceToHost,
+                            w->stream));
+  GC_CUDA(cudaStreamSynchronize(w->stream));
+  memcpy(ok, ho, n);
+  if (first_bad)
+    memcpy(first_bad, ho + ok_bytes, sizeof(int64_t) * (size_t)n);
+  return GC_OK;
+}
+
+int gc_check_edges(gc_world_t* w, const double* c1, const double* c2, uint32_t n, double min_distance, int mode,
+                   uint8_t* ok, int64_t* first_bad)
+{
+  GC_REQUIRE(w && c1 && c2 && ok, "gc_check_edges: NULL argument");
+  GC_REQUIRE(mode == GC_EDGE_BISECT || mode == GC_EDGE_LINEAR, "gc_check_edges: mode %d (use gc_check_edges_from_conf)",
+             mode);
+  GC_REQUIRE(mode != GC_EDGE_LINEAR || first_bad, "gc_check_edges: LINEAR mode needs first_bad");
+  return check_edges_host(w, c1, c2, nullptr, n, min_distance, mode, ok, mode == GC_EDGE_LINEAR ? first_bad : nullptr);
+}
+
+int gc_check_edges_from_conf(gc_world_t* w, const double* parent, const double* child, const double* conf, uint32_t n,
+                             double min_distance, uint8_t* result)
+{
+  GC_REQUIRE(w && parent && child && conf && result, "gc_check_edges_from_conf: NULL argument");
+  return check_edges_host(w, parent, child, conf, n, min_distance, GC_EDGE_FROM_CONF, result, nullptr);
+}
+
+}  // extern "C"

@@ -1,0 +1,145 @@
+// gc_common.cuh -- shared declarations of the sm_100a implementation behind include/gcb200.h
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <vector>
+
+#include "../../include/gcb200.h"
+
+namespace gc
+{
+// ---- error plumbing: C ABI never throws (SURVEY.md 8b "Error conventions") ------------------
+void set_error(const char* fmt, ...);
+#define GC_CUDA(call)                                                                          \
+  do                                                                                           \
+  {                                                                                            \
+    cudaError_t e_ = (call);                                                                   \
+    if (e_ != cudaSuccess)                                                                     \
+    {                                                                                          \
+      gc::set_error("%s failed at %s:%d: %s", #call, __FILE__, __LINE__, cudaGetErrorString(e_)); \
+      return GC_E_CUDA;                                                                        \
+    }                                                                                          \
+  } while (0)
+#define GC_REQUIRE(cond, ...)        \
+  do                                 \
+  {                                  \
+    if (!(cond))                     \
+    {                                \
+      gc::set_error(__VA_ARGS__);    \
+      return GC_E_INVALID;           \
+    }                                \
+  } while (0)
+#define GC_TRY(expr)   \
+  do                   \
+  {                    \
+    int r_ = (expr);   \
+    if (r_ < 0)        \
+      return r_;       \
+  } while (0)
+
+// ---- grow-only device / pinned scratch ---------------------------------------------------------
+struct DevBuf
+{
+  void* p = nullptr;
+  size_t cap = 0;
+  int reserve(size_t bytes);
+  void release();
+  template <typename T>
+  T* as() { return reinterpret_cast<T*>(p); }
+};
+struct PinBuf
+{
+  void* p = nullptr;
+  size_t cap = 0;
+  int reserve(size_t bytes);
+  void release();
+  template <typename T>
+  T* as() { return reinterpret_cast<T*>(p); }
+};
+
+int num_sms(int device);
+
+static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+}  // namespace gc
+
+// ---- node store ----------------------------------------------------------------------------------
+// HBM layout (DESIGN.md "Data layout"):
+//   x32 : float  [dim][cap_total]   dimension-major SoA, scanned with coalesced float4 loads
+//   x64 : double [cap_total][dim]   row-major master copy, gathered for the exact fp64 decisions
+//   used: uint32 [n_segments]       slots in use per segment
+// segment s owns slots [s*cap_seg, (s+1)*cap_seg); cap_seg is a multiple of 32 so every
+// segment row starts on a 128-byte boundary.  A tombstoned slot has x32[0][slot] = +inf.
+struct gc_store
+{
+  int device = 0;
+  int dim = 0;
+  uint32_t cap_seg = 0;
+  uint32_t nseg = 0;
+  size_t cap_total = 0;
+  float* x32 = nullptr;
+  double* x64 = nullptr;
+  uint32_t* d_used = nullptr;
+  std::vector<uint32_t> used;      // host mirror of d_used
+  std::vector<uint32_t> live;      // live (non tombstoned) nodes per segment
+  std::vector<double> max_abs;     // per segment max |coordinate| ever appended (fp32 slack bound)
+  cudaStream_t stream = nullptr;
+  cudaStream_t own_stream = nullptr;
+  int sms = 148;
+  // scratch
+  gc::DevBuf d_q, d_seg, d_radius, d_idx, d_dist, d_count, d_part, d_misc, d_rows, d_slots;
+  gc::PinBuf h_in, h_out;
+};
+
+// ---- collision world ---------------------------------------------------------------------------
+struct gc_world
+{
+  int device = 0;
+  int kind = 0;
+  int dim = 0;
+  int refs = 1;
+  // cube
+  double cube_thr = 1.0;
+  // generic object count (boxes / cspheres / obstacle spheres)
+  uint32_t nobj = 0;
+  double* d_lo = nullptr;  // boxes [n][dim]
+  double* d_hi = nullptr;
+  float* d_sc = nullptr;   // cspheres centres [n][dim]
+  float* d_sr2 = nullptr;  // cspheres radius^2 [n]
+  // sphere arm
+  int njoints = 0;
+  uint32_t nrs = 0;
+  float* d_arm = nullptr;  // base_tf[12] | joint_tf[J][12] | rs_local[nrs][4] | rs_link[nrs] (as float bits)
+  float* d_obs = nullptr;  // [nobs][4]
+  cudaStream_t stream = nullptr;
+  cudaStream_t own_stream = nullptr;
+  int sms = 148;
+  // counters (device) : [0] states evaluated, [1] pair tests
+  unsigned long long* d_counters = nullptr;
+  uint64_t launches = 0;
+  bool timing = false;
+  uint64_t kernel_ns = 0;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  // scratch
+  gc::DevBuf d_c1, d_c2, d_c3, d_ok, d_first, d_plan, d_offs, d_blocksum;
+  gc::PinBuf h_in, h_out;
+};
+
+namespace gc
+{
+// internal device-pointer entry points shared by the host wrappers and the fused planner step
+int nn1_dev(gc_store* s, const double* d_q, const uint32_t* d_seg, uint32_t nq, uint32_t* d_idx, double* d_dist,
+            bool single_segment_host_hint);
+int radius_dev(gc_store* s, const double* d_q, const uint32_t* d_seg, const double* d_radius, uint32_t nq,
+               uint32_t cap, uint32_t* d_idx, double* d_dist, uint32_t* d_count);
+int knn_dev(gc_store* s, const double* d_q, const uint32_t* d_seg, uint32_t nq, uint64_t k, uint32_t cap,
+            uint32_t* d_idx, double* d_dist, uint32_t* d_count);
+int check_edges_dev(gc_world* w, const double* d_c1, const double* d_c2, const double* d_c3, uint32_t n,
+                    double min_distance, int mode, uint8_t* d_ok, int64_t* d_first_bad, uint64_t states_hint,
+                    cudaStream_t stream);
+int check_states_dev(gc_world* w, const double* d_q, uint32_t n, uint8_t* d_ok, cudaStream_t stream);
+double store_slack(const gc_store* s);
+}  // namespace gc

@@ -1,0 +1,988 @@
+// nn.cu -- device-resident node store and the brute-force nearest / radius / k-nearest kernels.
+//
+// Replaces the reference's CPU structures behind graph::core::NearestNeighbors
+//   KdTree  src/graph_core/datastructure/kdtree.cpp:91-472
+//   Vector  src/graph_core/datastructure/vector.cpp:38-138   (the semantic twin: scan order = slot order,
+//                                                             strict '<', lowest slot wins ties)
+//
+// Design (DESIGN.md "NN path"): every query is a tiled brute-force scan of the segment's fp32
+// dimension-major SoA with coalesced float4 loads; the fp32 distance only PRE-SELECTS: any node
+// whose fp32 distance is within the rounding slack of the decision threshold is re-evaluated
+// from the fp64 master copy with exactly the oracle's arithmetic (sequential sum of squares,
+// individually rounded, then sqrt) and the reference's comparisons are applied to that value.
+#include <math_constants.h>
+
+#include <cfloat>
+#include <cmath>
+
+#include "gc_common.cuh"
+
+namespace gc
+{
+constexpr int kScanThreads = 256;
+constexpr int kNodesPerThread = 4;
+constexpr int kTile = kScanThreads * kNodesPerThread;  // 1024 nodes per tile
+constexpr int kQT = 8;                                 // queries sharing one pass over a tile
+constexpr int kRowPad = kTile;                         // floats of padding after each SoA row
+constexpr uint32_t kSortMax = 16384;                   // single-CTA bitonic capacity
+
+__device__ __forceinline__ float u2f(uint32_t u) { return __uint_as_float(u); }
+__device__ __forceinline__ uint32_t f2u(float f) { return __float_as_uint(f); }
+
+// exact fp64 Euclidean distance, operation order fixed by DESIGN.md (sequential, individually rounded)
+template <int D>
+__device__ __forceinline__ double dist64(const double* __restrict__ row, const double* __restrict__ q)
+{
+  double s = 0.0;
+#pragma unroll
+  for (int i = 0; i < D; i++)
+  {
+    double t = __dsub_rn(row[i], q[i]);
+    s = __dadd_rn(s, __dmul_rn(t, t));
+  }
+  return __dsqrt_rn(s);
+}
+
+// upper bound (squared) of the fp32 distance of any node whose fp64 distance is <= the fp64
+// distance corresponding to fp32 value m (or < radius m); see include/gcb200_spec.h
+__device__ __forceinline__ float slack_thr2(float m, float slack_abs)
+{
+  float b = m * (1.0f + 4.0e-6f) + 3.0f * slack_abs;
+  return b * b * (1.0f + 1.0e-6f);
+}
+
+// ---------------------------------------------------------------------------------------------
+// store maintenance kernels
+// ---------------------------------------------------------------------------------------------
+// rows[n][dim] (fp64) -> x64 master rows + fp32 SoA columns, gslot[i] = global slot of row i
+__global__ void store_scatter_kernel(const double* __restrict__ rows, const uint32_t* __restrict__ gslot, uint32_t n,
+                                     int dim, size_t row_stride, float* __restrict__ x32, double* __restrict__ x64)
+{
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n * (uint32_t)dim)
+    return;
+  uint32_t r = i / dim, d = i % dim;
+  double v = rows[i];
+  size_t slot = gslot[r];
+  x64[slot * dim + d] = v;
+  x32[(size_t)d * row_stride + slot] = (float)v;
+}
+
+__global__ void store_fill_slots_kernel(uint32_t* gslot, uint32_t first, uint32_t n)
+{
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n)
+    gslot[i] = first + i;
+}
+
+// ---------------------------------------------------------------------------------------------
+// tiled scan: MODE 0 = nearest (exact, lexicographic (dist64, slot) minimum per chunk)
+//             MODE 1 = radius  (exact strict dist64 < radius, unordered append to per-query lists)
+// grid = (chunks, query groups).  A group holds up to kQT queries of one segment.
+// ---------------------------------------------------------------------------------------------
+struct ScanArgs
+{
+  const float* x32;
+  const double* x64;
+  const uint32_t* used;    // [nseg]
+  const double* q;         // [nq][D]
+  const uint32_t* seg;     // [nq] or nullptr (segment 0)
+  const double* radius;    // MODE 1
+  uint32_t nq;
+  uint32_t group_size;     // queries per group (kQT when seg == nullptr, else 1)
+  uint32_t cap_seg;
+  size_t row_stride;
+  float slack_abs;
+  // MODE 0 outputs: partials [chunks][nq]
+  double* part_d;
+  uint32_t* part_i;
+  // MODE 1 outputs
+  uint32_t cap;
+  uint32_t* out_idx;
+  double* out_dist;
+  uint32_t* out_count;
+};
+
+template <int D, int MODE>
+__global__ void __launch_bounds__(kScanThreads, 2) scan_kernel(ScanArgs a)
+{
+  __shared__ float qs32[kQT][D];
+  __shared__ double qs64[kQT][D];
+  __shared__ uint32_t cur[kQT];                 // running fp32 minimum (bits) of this CTA
+  __shared__ unsigned long long best64[kQT];    // running exact minimum (bits)
+  __shared__ unsigned long long prev64[kQT];
+  __shared__ uint32_t bestidx[kQT];
+  __shared__ float thr_s[kQT];
+
+  const int tid = threadIdx.x;
+  const uint32_t q0 = blockIdx.y * a.group_size;
+  const int qcount = min(a.group_size, a.nq - q0);
+  const uint32_t seg = a.seg ? a.seg[q0] : 0u;
+  const uint32_t n_s = a.used[seg];
+  const size_t seg_base = (size_t)seg * a.cap_seg;
+
+  for (int i = tid; i < qcount * D; i += kScanThreads)
+  {
+    double v = a.q[(size_t)q0 * D + i];
+    qs64[i / D][i % D] = v;
+    qs32[i / D][i % D] = (float)v;
+  }
+  if (tid < kQT)
+  {
+    cur[tid] = 0x7f800000u;  // +inf
+    best64[tid] = 0x7ff0000000000000ull;
+    prev64[tid] = 0x7ff0000000000000ull;
+    bestidx[tid] = GC_NO_NODE;
+    if (MODE == 1 && tid < qcount)
+    {
+      double r = a.radius[q0 + tid];
+      float rf = (r > 0.0) ? (float)fmin(r, 1.0e18) : -1.0f;
+      thr_s[tid] = (rf < 0.0f) ? -1.0f : slack_thr2(rf * (1.0f + 1.0e-6f), a.slack_abs);
+    }
+  }
+  __syncthreads();
+
+  const uint32_t ntiles = (n_s + kTile - 1) / kTile;
+  for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x)
+  {
+    const uint32_t local0 = tile * kTile + tid * kNodesPerThread;  // first of this thread's 4 slots
+    float x[D][kNodesPerThread];
+#pragma unroll
+    for (int d = 0; d < D; d++)
+    {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(a.x32 + (size_t)d * a.row_stride + seg_base + local0));
+      x[d][0] = v.x;
+      x[d][1] = v.y;
+      x[d][2] = v.z;
+      x[d][3] = v.w;
+    }
+    float d2[kQT][kNodesPerThread];
+#pragma unroll
+    for (int q = 0; q < kQT; q++)
+    {
+      if (q < qcount)
+      {
+        float acc[kNodesPerThread];
+#pragma unroll
+        for (int r = 0; r < kNodesPerThread; r++)
+          acc[r] = 0.0f;
+#pragma unroll
+        for (int d = 0; d < D; d++)
+        {
+          const float qv = qs32[q][d];
+#pragma unroll
+          for (int r = 0; r < kNodesPerThread; r++)
+          {
+            const float t = x[d][r] - qv;
+            acc[r] = fmaf(t, t, acc[r]);
+          }
+        }
+#pragma unroll
+        for (int r = 0; r < kNodesPerThread; r++)
+        {
+          // slots beyond the segment's used range, tombstones (x32[0] = +inf) and NaNs never qualify
+          const bool valid = (local0 + r < n_s) && (acc[r] < CUDART_INF_F);
+          d2[q][r] = valid ? acc[r] : CUDART_INF_F;
+        }
+        if (MODE == 0)
+        {
+          const float tmin = fminf(fminf(d2[q][0], d2[q][1]), fminf(d2[q][2], d2[q][3]));
+          const uint32_t wmin = __reduce_min_sync(0xffffffffu, f2u(tmin));
+          if ((tid & 31) == 0 && wmin < cur[q])
+            atomicMin(&cur[q], wmin);
+        }
+      }
+    }
+    if (MODE == 0)
+    {
+      __syncthreads();
+      bool pass = false;
+      float thr[kQT];
+#pragma unroll
+      for (int q = 0; q < kQT; q++)
+      {
+        thr[q] = -1.0f;
+        if (q < qcount)
+        {
+          const float m2 = u2f(cur[q]);
+          thr[q] = (m2 < CUDART_INF_F) ? slack_thr2(sqrtf(m2) * (1.0f + 1.0e-6f), a.slack_abs) : -1.0f;
+#pragma unroll
+          for (int r = 0; r < kNodesPerThread; r++)
+            pass |= (d2[q][r] <= thr[q]);
+        }
+      }
+      if (__syncthreads_or(pass))
+      {
+        // step A: exact distances of the candidates -> running exact minimum
+#pragma unroll
+        for (int q = 0; q < kQT; q++)
+          if (q < qcount)
+#pragma unroll
+            for (int r = 0; r < kNodesPerThread; r++)
+              if (d2[q][r] <= thr[q])
+              {
+                const double e = dist64<D>(a.x64 + (seg_base + local0 + r) * D, qs64[q]);
+                atomicMin(&best64[q], (unsigned long long)__double_as_longlong(e));
+              }
+        __syncthreads();
+        // step B: a strictly smaller exact minimum invalidates the slot kept for the old one
+        if (tid < qcount && best64[tid] != prev64[tid])
+        {
+          bestidx[tid] = GC_NO_NODE;
+          prev64[tid] = best64[tid];
+        }
+        __syncthreads();
+        // step C: lowest slot among the candidates that attain the exact minimum
+#pragma unroll
+        for (int q = 0; q < kQT; q++)
+          if (q < qcount)
+#pragma unroll
+            for (int r = 0; r < kNodesPerThread; r++)
+              if (d2[q][r] <= thr[q])
+              {
+                const double e = dist64<D>(a.x64 + (seg_base + local0 + r) * D, qs64[q]);
+                if ((unsigned long long)__double_as_longlong(e) == best64[q])
+                  atomicMin(&bestidx[q], local0 + r);
+              }
+        __syncthreads();
+      }
+    }
+    else
+    {
+#pragma unroll
+      for (int q = 0; q < kQT; q++)
+        if (q < qcount)
+#pragma unroll
+          for (int r = 0; r < kNodesPerThread; r++)
+            if (d2[q][r] <= thr_s[q])
+            {
+              const double e = dist64<D>(a.x64 + (seg_base + local0 + r) * D, qs64[q]);
+              if (e < a.radius[q0 + q])  // strict, vector.cpp:75 / kdtree.cpp:167
+              {
+                const uint32_t pos = atomicAdd(&a.out_count[q0 + q], 1u);
+                if (pos < a.cap)
+                {
+                  a.out_idx[(size_t)(q0 + q) * a.cap + pos] = local0 + r;
+                  a.out_dist[(size_t)(q0 + q) * a.cap + pos] = e;
+                }
+              }
+            }
+    }
+  }
+  if (MODE == 0)
+  {
+    __syncthreads();
+    if (tid < qcount)
+    {
+      a.part_d[(size_t)blockIdx.x * a.nq + q0 + tid] = __longlong_as_double((long long)best64[tid]);
+      a.part_i[(size_t)blockIdx.x * a.nq + q0 + tid] = bestidx[tid];
+    }
+  }
+}
+
+// lexicographic (dist, slot) minimum over the chunk partials
+__global__ void nn1_finalize_kernel(const double* __restrict__ part_d, const uint32_t* __restrict__ part_i,
+                                    uint32_t chunks, uint32_t nq, uint32_t* __restrict__ idx,
+                                    double* __restrict__ dist)
+{
+  uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= nq)
+    return;
+  double bd = CUDART_INF;
+  uint32_t bi = GC_NO_NODE;
+  for (uint32_t c = 0; c < chunks; c++)
+  {
+    const double d = part_d[(size_t)c * nq + q];
+    const uint32_t i = part_i[(size_t)c * nq + q];
+    if (i != GC_NO_NODE && (d < bd || (d == bd && i < bi)))
+    {
+      bd = d;
+      bi = i;
+    }
+  }
+  idx[q] = bi;
+  dist[q] = bd;
+}
+
+// ---------------------------------------------------------------------------------------------
+// block-wide bitonic sort of (key, slot) pairs, ascending lexicographic; P = power of two
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void bitonic_sort(double* key, uint32_t* val, uint32_t P)
+{
+  for (uint32_t k = 2; k <= P; k <<= 1)
+    for (uint32_t j = k >> 1; j > 0; j >>= 1)
+    {
+      for (uint32_t i = threadIdx.x; i < P; i += blockDim.x)
+      {
+        const uint32_t ixj = i ^ j;
+        if (ixj > i)
+        {
+          const double ka = key[i], kb = key[ixj];
+          const uint32_t va = val[i], vb = val[ixj];
+          const bool gt = (ka > kb) || (ka == kb && va > vb);
+          const bool up = ((i & k) == 0);
+          if (gt == up)
+          {
+            key[i] = kb;
+            key[ixj] = ka;
+            val[i] = vb;
+            val[ixj] = va;
+          }
+        }
+      }
+      __syncthreads();
+    }
+}
+
+// sorts the first min(count, cap) entries of every query's list in place
+__global__ void sort_lists_kernel(uint32_t* __restrict__ idx, double* __restrict__ dist,
+                                  const uint32_t* __restrict__ count, uint32_t cap, uint32_t P)
+{
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double* key = reinterpret_cast<double*>(smem_raw);
+  uint32_t* val = reinterpret_cast<uint32_t*>(key + P);
+  const uint32_t q = blockIdx.x;
+  const uint32_t n = min(count[q], cap);
+  if (n <= 1)
+    return;
+  uint32_t p2 = 2;
+  while (p2 < n)
+    p2 <<= 1;
+  for (uint32_t i = threadIdx.x; i < p2; i += blockDim.x)
+  {
+    key[i] = (i < n) ? dist[(size_t)q * cap + i] : CUDART_INF;
+    val[i] = (i < n) ? idx[(size_t)q * cap + i] : GC_NO_NODE;
+  }
+  __syncthreads();
+  bitonic_sort(key, val, p2);
+  for (uint32_t i = threadIdx.x; i < n; i += blockDim.x)
+  {
+    dist[(size_t)q * cap + i] = key[i];
+    idx[(size_t)q * cap + i] = val[i];
+  }
+}
+
+// k-nearest for segments of at most kSortMax slots (planner regime; also the k >= N "return all,
+// sorted" case of Tree::nearK, src/graph_core/graph/tree.cpp:761-765): exact fp64 distance of
+// every live slot, block-wide sort, first min(k, live) entries.
+template <int D>
+__global__ void __launch_bounds__(1024, 1)
+    knn_all_kernel(const float* __restrict__ x32, const double* __restrict__ x64, const uint32_t* __restrict__ used,
+                   const double* __restrict__ qd, const uint32_t* __restrict__ segs, uint32_t cap_seg,
+                   size_t row_stride, unsigned long long k, uint32_t cap, uint32_t* __restrict__ out_idx,
+                   double* __restrict__ out_dist, uint32_t* __restrict__ out_count, uint32_t P)
+{
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double* key = reinterpret_cast<double*>(smem_raw);
+  uint32_t* val = reinterpret_cast<uint32_t*>(key + P);
+  __shared__ double qs[D];
+  __shared__ uint32_t live_s;
+  const uint32_t q = blockIdx.x;
+  const uint32_t seg = segs ? segs[q] : 0u;
+  const uint32_t n_s = used[seg];
+  const size_t seg_base = (size_t)seg * cap_seg;
+  if (threadIdx.x < D)
+    qs[threadIdx.x] = qd[(size_t)q * D + threadIdx.x];
+  if (threadIdx.x == 0)
+    live_s = 0;
+  __syncthreads();
+  uint32_t p2 = 2;
+  while (p2 < n_s)
+    p2 <<= 1;
+  uint32_t my_live = 0;
+  for (uint32_t i = threadIdx.x; i < p2; i += blockDim.x)
+  {
+    double e = CUDART_INF;
+    uint32_t v = GC_NO_NODE;
+    if (i < n_s && x32[seg_base + i] < CUDART_INF_F)  // row 0 of the SoA carries the tombstone mark
+    {
+      e = dist64<D>(x64 + (seg_base + i) * D, qs);
+      v = i;
+      my_live++;
+    }
+    key[i] = e;
+    val[i] = v;
+  }
+  if (my_live)
+    atomicAdd(&live_s, my_live);
+  __syncthreads();
+  bitonic_sort(key, val, p2);
+  const uint32_t live = live_s;
+  const uint32_t want = (k < (unsigned long long)live) ? (uint32_t)k : live;
+  for (uint32_t i = threadIdx.x; i < min(want, cap); i += blockDim.x)
+  {
+    out_idx[(size_t)q * cap + i] = val[i];
+    out_dist[(size_t)q * cap + i] = key[i];
+  }
+  if (threadIdx.x == 0)
+    out_count[q] = want;
+}
+
+// ---------------------------------------------------------------------------------------------
+// dispatch helpers
+// ---------------------------------------------------------------------------------------------
+#define GC_DISPATCH_DIM(dim, ...)                                  \
+  switch (dim)                                                       \
+  {                                                                  \
+    case 1: { constexpr int DD = 1; __VA_ARGS__; } break;                   \
+    case 2: { constexpr int DD = 2; __VA_ARGS__; } break;                   \
+    case 3: { constexpr int DD = 3; __VA_ARGS__; } break;                   \
+    case 4: { constexpr int DD = 4; __VA_ARGS__; } break;                   \
+    case 5: { constexpr int DD = 5; __VA_ARGS__; } break;                   \
+    case 6: { constexpr int DD = 6; __VA_ARGS__; } break;                   \
+    case 7: { constexpr int DD = 7; __VA_ARGS__; } break;                   \
+    case 8: { constexpr int DD = 8; __VA_ARGS__; } break;                   \
+    case 9: { constexpr int DD = 9; __VA_ARGS__; } break;                   \
+    case 10: { constexpr int DD = 10; __VA_ARGS__; } break;                 \
+    case 11: { constexpr int DD = 11; __VA_ARGS__; } break;                 \
+    case 12: { constexpr int DD = 12; __VA_ARGS__; } break;                 \
+    case 13: { constexpr int DD = 13; __VA_ARGS__; } break;                 \
+    case 14: { constexpr int DD = 14; __VA_ARGS__; } break;                 \
+    case 15: { constexpr int DD = 15; __VA_ARGS__; } break;                 \
+    case 16: { constexpr int DD = 16; __VA_ARGS__; } break;                 \
+    default: gc::set_error("dimension %d not in [1,%d]", dim, GC_MAX_DIM); return GC_E_INVALID; \
+  }
+
+double store_slack(const gc_store* s)
+{
+  double m = 0.0;
+  for (double v : s->max_abs)
+    m = fmax(m, v);
+  return GC_SCAN_SLACK_REL * sqrt((double)s->dim) * m;
+}
+
+static uint32_t max_used(const gc_store* s)
+{
+  uint32_t m = 0;
+  for (uint32_t v : s->used)
+    m = v > m ? v : m;
+  return m;
+}
+
+static void scan_grid(const gc_store* s, uint32_t nq, bool per_query_seg, uint32_t* groups, uint32_t* group_size,
+                      uint32_t* chunks)
+{
+  *group_size = per_query_seg ? 1u : (uint32_t)kQT;
+  *groups = (nq + *group_size - 1) / *group_size;
+  uint32_t ntiles = (max_used(s) + kTile - 1) / kTile;
+  if (ntiles == 0)
+    ntiles = 1;
+  uint32_t target = (uint32_t)s->sms * 4u;
+  uint32_t c = (target + *groups - 1) / *groups;
+  if (c > ntiles)
+    c = ntiles;
+  if (c < 1)
+    c = 1;
+  *chunks = c;
+}
+
+int nn1_dev(gc_store* s, const double* d_q, const uint32_t* d_seg, uint32_t nq, uint32_t* d_idx, double* d_dist,
+            bool)
+{
+  if (nq == 0)
+    return GC_OK;
+  uint32_t groups, gsz, chunks;
+  scan_grid(s, nq, d_seg != nullptr, &groups, &gsz, &chunks);
+  GC_TRY(s->d_part.reserve((size_t)chunks * nq * (sizeof(double) + sizeof(uint32_t))));
+  ScanArgs a{};
+  a.x32 = s->x32;
+  a.x64 = s->x64;
+  a.used = s->d_used;
+  a.q = d_q;
+  a.seg = d_seg;
+  a.nq = nq;
+  a.group_size = gsz;
+  a.cap_seg = s->cap_seg;
+  a.row_stride = s->cap_total + kRowPad;
+  a.slack_abs = (float)(store_slack(s) * 1.0000001) + FLT_MIN;
+  a.part_d = s->d_part.as<double>();
+  a.part_i = reinterpret_cast<uint32_t*>(a.part_d + (size_t)chunks * nq);
+  dim3 grid(chunks, groups);
+  GC_DISPATCH_DIM(s->dim, (scan_kernel<DD, 0><<<grid, kScanThreads, 0, s->stream>>>(a)));
+  GC_CUDA(cudaGetLastError());
+  nn1_finalize_kernel<<<(nq + 127) / 128, 128, 0, s->stream>>>(a.part_d, a.part_i, chunks, nq, d_idx, d_dist);
+  GC_CUDA(cudaGetLastError());
+  return GC_OK;
+}
+
+static int sort_lists(gc_store* s, uint32_t nq, uint32_t cap, uint32_t* d_idx, double* d_dist, uint32_t* d_count)
+{
+  uint32_t P = 2;
+  while (P < cap)
+    P <<= 1;
+  if (P > kSortMax)
+  {
+    gc::set_error("result lists longer than %u entries are not supported yet (cap %u)", kSortMax, cap);
+    return GC_E_UNSUPPORTED;
+  }
+  size_t smem = (size_t)P * (sizeof(double) + sizeof(uint32_t));
+  static bool attr_set = false;
+  if (!attr_set)
+  {
+    GC_CUDA(cudaFuncSetAttribute(sort_lists_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)(kSortMax * (sizeof(double) + sizeof(uint32_t)))));
+    attr_set = true;
+  }
+  int threads = P >= 2048 ? 1024 : (P >= 512 ? 256 : 64);
+  sort_lists_kernel<<<nq, threads, smem, s->stream>>>(d_idx, d_dist, d_count, cap, P);
+  GC_CUDA(cudaGetLastError());
+  return GC_OK;
+}
+
+int radius_dev(gc_store* s, const double* d_q, const uint32_t* d_seg, const double* d_radius, uint32_t nq,
+               uint32_t cap, uint32_t* d_idx, double* d_dist, uint32_t* d_count)
+{
+  if (nq == 0)
+    return GC_OK;
+  GC_REQUIRE(cap > 0, "gc_radius: cap must be > 0");
+  uint32_t groups, gsz, chunks;
+  scan_grid(s, nq, d_seg != nullptr, &groups, &gsz, &chunks);
+  GC_CUDA(cudaMemsetAsync(d_count, 0, sizeof(uint32_t) * nq, s->stream));
+  ScanArgs a{};
+  a.x32 = s->x32;
+  a.x64 = s->x64;
+  a.used = s->d_used;
+  a.q = d_q;
+  a.seg = d_seg;
+  a.radius = d_radius;
+  a.nq = nq;
+  a.group_size = gsz;
+  a.cap_seg = s->cap_seg;
+  a.row_stride = s->cap_total + kRowPad;
+  a.slack_abs = (float)(store_slack(s) * 1.0000001) + FLT_MIN;
+  a.cap = cap;
+  a.out_idx = d_idx;
+  a.out_dist = d_dist;
+  a.out_count = d_count;
+  dim3 grid(chunks, groups);
+  GC_DISPATCH_DIM(s->dim, (scan_kernel<DD, 1><<<grid, kScanThreads, 0, s->stream>>>(a)));
+  GC_CUDA(cudaGetLastError());
+  return sort_lists(s, nq, cap, d_idx, d_dist, d_count);
+}
+
+int knn_dev(gc_store* s, const double* d_q, const uint32_t* d_seg, uint32_t nq, uint64_t k, uint32_t cap,
+            uint32_t* d_idx, double* d_dist, uint32_t* d_count)
+{
+  if (nq == 0)
+    return GC_OK;
+  GC_REQUIRE(cap > 0, "gc_knn: cap must be > 0");
+  const uint32_t mu = max_used(s);
+  if (mu > kSortMax)
+  {
+    gc::set_error("gc_knn: segments above %u slots need the large-N selection path (not built yet)", kSortMax);
+    return GC_E_UNSUPPORTED;
+  }
+  uint32_t P = 2;
+  while (P < mu)
+    P <<= 1;
+  size_t smem = (size_t)P * (sizeof(double) + sizeof(uint32_t));
+  static bool attr_set[GC_MAX_DIM + 1] = {};
+  const size_t row_stride = s->cap_total + kRowPad;
+  GC_DISPATCH_DIM(
+      s->dim,
+      if (!attr_set[DD]) {
+        GC_CUDA(cudaFuncSetAttribute(knn_all_kernel<DD>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)(kSortMax * (sizeof(double) + sizeof(uint32_t)))));
+        attr_set[DD] = true;
+      } knn_all_kernel<DD><<<nq, 1024, smem, s->stream>>>(s->x32, s->x64, s->d_used, d_q, d_seg, s->cap_seg,
+                                                           row_stride, (unsigned long long)k, cap, d_idx, d_dist,
+                                                           d_count, P));
+  GC_CUDA(cudaGetLastError());
+  return GC_OK;
+}
+
+}  // namespace gc
+
+// =================================================================================================
+//  C ABI: store
+// =================================================================================================
+using namespace gc;
+
+extern "C" {
+
+int gc_store_create(int dim, uint32_t capacity_per_segment, uint32_t n_segments, int device, gc_store_t** out)
+{
+  GC_REQUIRE(out != nullptr, "gc_store_create: out is NULL");
+  *out = nullptr;
+  GC_REQUIRE(dim >= 1 && dim <= GC_MAX_DIM, "gc_store_create: dim %d not in [1,%d]", dim, GC_MAX_DIM);
+  GC_REQUIRE(capacity_per_segment > 0 && n_segments > 0, "gc_store_create: empty capacity");
+  int ndev = 0;
+  GC_TRY(gc_device_count(&ndev));
+  GC_REQUIRE(device >= 0 && device < ndev, "gc_store_create: device %d of %d (no CPU fallback exists)", device, ndev);
+  GC_CUDA(cudaSetDevice(device));
+  gc_store* s = new gc_store();
+  s->device = device;
+  s->dim = dim;
+  s->cap_seg = (uint32_t)align_up(capacity_per_segment, 32);
+  s->nseg = n_segments;
+  s->cap_total = (size_t)s->cap_seg * n_segments;
+  if (s->cap_total > 0xFFFFFFF0ull)
+  {
+    delete s;
+    gc::set_error("gc_store_create: %zu slots exceed the 32-bit slot space", s->cap_total);
+    return GC_E_INVALID;
+  }
+  s->sms = num_sms(device);
+  const size_t row_stride = s->cap_total + kRowPad;
+  cudaError_t e = cudaMalloc(&s->x32, sizeof(float) * row_stride * dim);
+  if (e == cudaSuccess)
+    e = cudaMalloc(&s->x64, sizeof(double) * (s->cap_total + 8) * dim);
+  if (e == cudaSuccess)
+    e = cudaMalloc(&s->d_used, sizeof(uint32_t) * n_segments);
+  if (e == cudaSuccess)
+    e = cudaStreamCreateWithFlags(&s->own_stream, cudaStreamNonBlocking);
+  if (e != cudaSuccess)
+  {
+    gc::set_error("gc_store_create: %s", cudaGetErrorString(e));
+    gc_store_destroy(s);
+    return GC_E_CUDA;
+  }
+  s->stream = s->own_stream;
+  s->used.assign(n_segments, 0);
+  s->live.assign(n_segments, 0);
+  s->max_abs.assign(n_segments, 0.0);
+  GC_CUDA(cudaMemsetAsync(s->x32, 0, sizeof(float) * row_stride * dim, s->stream));
+  GC_CUDA(cudaMemsetAsync(s->d_used, 0, sizeof(uint32_t) * n_segments, s->stream));
+  GC_CUDA(cudaStreamSynchronize(s->stream));
+  *out = s;
+  return GC_OK;
+}
+
+int gc_store_destroy(gc_store_t* s)
+{
+  if (!s)
+    return GC_OK;
+  cudaSetDevice(s->device);
+  if (s->own_stream)
+    cudaStreamSynchronize(s->own_stream);
+  cudaFree(s->x32);
+  cudaFree(s->x64);
+  cudaFree(s->d_used);
+  s->d_q.release(); s->d_seg.release(); s->d_radius.release(); s->d_idx.release(); s->d_dist.release();
+  s->d_count.release(); s->d_part.release(); s->d_misc.release(); s->d_rows.release(); s->d_slots.release();
+  s->h_in.release(); s->h_out.release();
+  if (s->own_stream)
+    cudaStreamDestroy(s->own_stream);
+  delete s;
+  return GC_OK;
+}
+
+int gc_store_set_stream(gc_store_t* s, void* cuda_stream)
+{
+  GC_REQUIRE(s != nullptr, "gc_store_set_stream: NULL store");
+  GC_CUDA(cudaStreamSynchronize(s->stream));
+  s->stream = cuda_stream ? reinterpret_cast<cudaStream_t>(cuda_stream) : s->own_stream;
+  return GC_OK;
+}
+
+int gc_store_dim(gc_store_t* s) { return s ? s->dim : GC_E_INVALID; }
+
+static void track_max_abs(gc_store* s, uint32_t seg, const double* q, size_t count)
+{
+  double m = s->max_abs[seg];
+  for (size_t i = 0; i < count; i++)
+  {
+    double v = fabs(q[i]);
+    if (v > m)
+      m = v;
+  }
+  s->max_abs[seg] = m;
+}
+
+int gc_store_append(gc_store_t* s, uint32_t segment, const double* q, uint32_t n, uint32_t* first_slot)
+{
+  GC_REQUIRE(s && q, "gc_store_append: NULL argument");
+  GC_REQUIRE(segment < s->nseg, "gc_store_append: segment %u of %u", segment, s->nseg);
+  if (n == 0)
+    return GC_OK;
+  if ((size_t)s->used[segment] + n > s->cap_seg)
+  {
+    gc::set_error("gc_store_append: segment %u full (%u + %u > %u)", segment, s->used[segment], n, s->cap_seg);
+    return GC_E_CAPACITY;
+  }
+  GC_CUDA(cudaSetDevice(s->device));
+  const size_t bytes = sizeof(double) * (size_t)n * s->dim;
+  GC_TRY(s->h_in.reserve(bytes));
+  GC_TRY(s->d_rows.reserve(bytes));
+  GC_TRY(s->d_slots.reserve(sizeof(uint32_t) * n));
+  // the pinned staging buffer may still feed an earlier asynchronous copy
+  GC_CUDA(cudaStreamSynchronize(s->stream));
+  memcpy(s->h_in.p, q, bytes);
+  track_max_abs(s, segment, q, (size_t)n * s->dim);
+  const uint32_t first = s->used[segment];
+  const uint32_t gfirst = segment * s->cap_seg + first;
+  GC_CUDA(cudaMemcpyAsync(s->d_rows.p, s->h_in.p, bytes, cudaMemcpyHostToDevice, s->stream));
+  store_fill_slots_kernel<<<(n + 255) / 256, 256, 0, s->stream>>>(s->d_slots.as<uint32_t>(), gfirst, n);
+  const uint32_t total = n * (uint32_t)s->dim;
+  store_scatter_kernel<<<(total + 255) / 256, 256, 0, s->stream>>>(s->d_rows.as<double>(), s->d_slots.as<uint32_t>(), n,
+                                                                    s->dim, s->cap_total + kRowPad, s->x32, s->x64);
+  GC_CUDA(cudaGetLastError());
+  s->used[segment] = first + n;
+  s->live[segment] += n;
+  GC_CUDA(cudaMemcpyAsync(s->d_used + segment, &s->used[segment], sizeof(uint32_t), cudaMemcpyHostToDevice, s->stream));
+  GC_CUDA(cudaStreamSynchronize(s->stream));
+  if (first_slot)
+    *first_slot = first;
+  return GC_OK;
+}
+
+int gc_store_append_multi(gc_store_t* s, const uint32_t* segments, const double* q, uint32_t n, uint32_t* slots)
+{
+  GC_REQUIRE(s && q && segments, "gc_store_append_multi: NULL argument");
+  if (n == 0)
+    return GC_OK;
+  GC_CUDA(cudaSetDevice(s->device));
+  const size_t bytes = sizeof(double) * (size_t)n * s->dim;
+  const size_t sbytes = align_up(sizeof(uint32_t) * n, 16);
+  GC_TRY(s->h_in.reserve(bytes + sbytes));
+  GC_TRY(s->d_rows.reserve(bytes));
+  GC_TRY(s->d_slots.reserve(sbytes));
+  GC_CUDA(cudaStreamSynchronize(s->stream));
+  uint32_t* hs = reinterpret_cast<uint32_t*>(static_cast<char*>(s->h_in.p) + bytes);
+  for (uint32_t i = 0; i < n; i++)
+  {
+    const uint32_t seg = segments[i];
+    GC_REQUIRE(seg < s->nseg, "gc_store_append_multi: segment %u of %u", seg, s->nseg);
+    if (s->used[seg] >= s->cap_seg)
+    {
+      // roll back the rows already accounted for
+      for (uint32_t j = 0; j < i; j++)
+      {
+        s->used[segments[j]]--;
+        s->live[segments[j]]--;
+      }
+      gc::set_error("gc_store_append_multi: segment %u full (%u slots)", seg, s->cap_seg);
+      return GC_E_CAPACITY;
+    }
+    const uint32_t slot = s->used[seg]++;
+    s->live[seg]++;
+    hs[i] = seg * s->cap_seg + slot;
+    if (slots)
+      slots[i] = slot;
+    track_max_abs(s, seg, q + (size_t)i * s->dim, s->dim);
+  }
+  memcpy(s->h_in.p, q, bytes);
+  GC_CUDA(cudaMemcpyAsync(s->d_rows.p, s->h_in.p, bytes, cudaMemcpyHostToDevice, s->stream));
+  GC_CUDA(cudaMemcpyAsync(s->d_slots.p, hs, sizeof(uint32_t) * n, cudaMemcpyHostToDevice, s->stream));
+  const uint32_t total = n * (uint32_t)s->dim;
+  store_scatter_kernel<<<(total + 255) / 256, 256, 0, s->stream>>>(s->d_rows.as<double>(), s->d_slots.as<uint32_t>(), n,
+                                                                    s->dim, s->cap_total + kRowPad, s->x32, s->x64);
+  GC_CUDA(cudaGetLastError());
+  GC_CUDA(cudaMemcpyAsync(s->d_used, s->used.data(), sizeof(uint32_t) * s->nseg, cudaMemcpyHostToDevice, s->stream));
+  GC_CUDA(cudaStreamSynchronize(s->stream));
+  return GC_OK;
+}
+
+static int poke_row0(gc_store* s, uint32_t segment, uint32_t slot, bool tombstone)
+{
+  GC_REQUIRE(s != nullptr, "NULL store");
+  GC_REQUIRE(segment < s->nseg && slot < s->used[segment], "slot %u of segment %u is not in use", slot, segment);
+  GC_CUDA(cudaSetDevice(s->device));
+  const size_t g = (size_t)segment * s->cap_seg + slot;
+  float v;
+  if (tombstone)
+    v = INFINITY;
+  else
+  {
+    double d0;
+    GC_CUDA(cudaMemcpyAsync(&d0, s->x64 + g * s->dim, sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+    GC_CUDA(cudaStreamSynchronize(s->stream));
+    v = (float)d0;
+  }
+  float cur;
+  GC_CUDA(cudaMemcpyAsync(&cur, s->x32 + g, sizeof(float), cudaMemcpyDeviceToHost, s->stream));
+  GC_CUDA(cudaStreamSynchronize(s->stream));
+  const bool was_dead = std::isinf(cur) && cur > 0;
+  if (tombstone == was_dead)
+    return GC_W_NOOP;  // nothing to change
+  GC_CUDA(cudaMemcpyAsync(s->x32 + g, &v, sizeof(float), cudaMemcpyHostToDevice, s->stream));
+  GC_CUDA(cudaStreamSynchronize(s->stream));
+  if (tombstone)
+    s->live[segment]--;
+  else
+    s->live[segment]++;
+  return GC_OK;
+}
+
+int gc_store_tombstone(gc_store_t* s, uint32_t segment, uint32_t slot) { return poke_row0(s, segment, slot, true); }
+int gc_store_restore(gc_store_t* s, uint32_t segment, uint32_t slot) { return poke_row0(s, segment, slot, false); }
+
+int gc_store_clear(gc_store_t* s, uint32_t segment)
+{
+  GC_REQUIRE(s != nullptr, "gc_store_clear: NULL store");
+  GC_REQUIRE(segment == GC_NO_NODE || segment < s->nseg, "gc_store_clear: segment %u of %u", segment, s->nseg);
+  GC_CUDA(cudaSetDevice(s->device));
+  for (uint32_t g = 0; g < s->nseg; g++)
+    if (segment == GC_NO_NODE || segment == g)
+    {
+      s->used[g] = 0;
+      s->live[g] = 0;
+      s->max_abs[g] = 0.0;
+    }
+  GC_CUDA(cudaMemcpyAsync(s->d_used, s->used.data(), sizeof(uint32_t) * s->nseg, cudaMemcpyHostToDevice, s->stream));
+  GC_CUDA(cudaStreamSynchronize(s->stream));
+  return GC_OK;
+}
+
+int gc_store_size(gc_store_t* s, uint32_t segment, uint32_t* slots_used, uint32_t* live)
+{
+  GC_REQUIRE(s != nullptr && segment < s->nseg, "gc_store_size: bad store/segment");
+  if (slots_used)
+    *slots_used = s->used[segment];
+  if (live)
+    *live = s->live[segment];
+  return GC_OK;
+}
+
+int gc_store_read(gc_store_t* s, uint32_t segment, uint32_t first_slot, uint32_t n, double* q_out)
+{
+  GC_REQUIRE(s && q_out && segment < s->nseg, "gc_store_read: bad argument");
+  GC_REQUIRE((size_t)first_slot + n <= s->used[segment], "gc_store_read: slots [%u,%u) beyond %u", first_slot,
+             first_slot + n, s->used[segment]);
+  if (n == 0)
+    return GC_OK;
+  GC_CUDA(cudaSetDevice(s->device));
+  const size_t g = (size_t)segment * s->cap_seg + first_slot;
+  GC_CUDA(cudaMemcpyAsync(q_out, s->x64 + g * s->dim, sizeof(double) * (size_t)n * s->dim, cudaMemcpyDeviceToHost,
+                          s->stream));
+  GC_CUDA(cudaStreamSynchronize(s->stream));
+  return GC_OK;
+}
+
+// =================================================================================================
+//  C ABI: queries
+// =================================================================================================
+int gc_nn1_dev(gc_store_t* s, const double* d_q, const uint32_t* d_seg, uint32_t nq, uint32_t* d_idx, double* d_dist)
+{
+  GC_REQUIRE(s && d_q && d_idx && d_dist, "gc_nn1_dev: NULL argument");
+  GC_CUDA(cudaSetDevice(s->device));
+  return nn1_dev(s, d_q, d_seg, nq, d_idx, d_dist, false);
+}
+int gc_radius_dev(gc_store_t* s, const double* d_q, const uint32_t* d_seg, const double* d_radius, uint32_t nq,
+                  uint32_t cap, uint32_t* d_idx, double* d_dist, uint32_t* d_count)
+{
+  GC_REQUIRE(s && d_q && d_radius && d_idx && d_dist && d_count, "gc_radius_dev: NULL argument");
+  GC_CUDA(cudaSetDevice(s->device));
+  return radius_dev(s, d_q, d_seg, d_radius, nq, cap, d_idx, d_dist, d_count);
+}
+int gc_knn_dev(gc_store_t* s, const double* d_q, const uint32_t* d_seg, uint32_t nq, uint64_t k, uint32_t cap,
+               uint32_t* d_idx, double* d_dist, uint32_t* d_count)
+{
+  GC_REQUIRE(s && d_q && d_idx && d_dist && d_count, "gc_knn_dev: NULL argument");
+  GC_CUDA(cudaSetDevice(s->device));
+  return knn_dev(s, d_q, d_seg, nq, k, cap, d_idx, d_dist, d_count);
+}
+
+// stage host queries (and optional per-query segments / radii) on the device
+static int stage_queries(gc_store* s, const double* q, const uint32_t* seg, const double* radius, uint32_t nq)
+{
+  const size_t qb = sizeof(double) * (size_t)nq * s->dim;
+  const size_t sb = seg ? align_up(sizeof(uint32_t) * nq, 16) : 0;
+  const size_t rb = radius ? sizeof(double) * nq : 0;
+  GC_TRY(s->h_in.reserve(qb + sb + rb));
+  GC_TRY(s->d_q.reserve(qb));
+  if (seg)
+    GC_TRY(s->d_seg.reserve(sb));
+  if (radius)
+    GC_TRY(s->d_radius.reserve(rb));
+  GC_CUDA(cudaStreamSynchronize(s->stream));
+  char* h = static_cast<char*>(s->h_in.p);
+  memcpy(h, q, qb);
+  GC_CUDA(cudaMemcpyAsync(s->d_q.p, h, qb, cudaMemcpyHostToDevice, s->stream));
+  if (seg)
+  {
+    for (uint32_t i = 0; i < nq; i++)
+      GC_REQUIRE(seg[i] < s->nseg, "query %u: segment %u of %u", i, seg[i], s->nseg);
+    memcpy(h + qb, seg, sizeof(uint32_t) * nq);
+    GC_CUDA(cudaMemcpyAsync(s->d_seg.p, h + qb, sizeof(uint32_t) * nq, cudaMemcpyHostToDevice, s->stream));
+  }
+  if (radius)
+  {
+    memcpy(h + qb + sb, radius, rb);
+    GC_CUDA(cudaMemcpyAsync(s->d_radius.p, h + qb + sb, rb, cudaMemcpyHostToDevice, s->stream));
+  }
+  return GC_OK;
+}
+
+int gc_nn1(gc_store_t* s, const double* q, const uint32_t* seg, uint32_t nq, uint32_t* idx, double* dist)
+{
+  GC_REQUIRE(s && q && idx && dist, "gc_nn1: NULL argument");
+  if (nq == 0)
+    return GC_OK;
+  GC_CUDA(cudaSetDevice(s->device));
+  GC_TRY(stage_queries(s, q, seg, nullptr, nq));
+  GC_TRY(s->d_idx.reserve(sizeof(uint32_t) * nq));
+  GC_TRY(s->d_dist.reserve(sizeof(double) * nq));
+  const size_t ob = sizeof(double) * nq + sizeof(uint32_t) * nq;
+  GC_TRY(s->h_out.reserve(ob));
+  GC_TRY(nn1_dev(s, s->d_q.as<double>(), seg ? s->d_seg.as<uint32_t>() : nullptr, nq, s->d_idx.as<uint32_t>(),
+                 s->d_dist.as<double>(), seg == nullptr));
+  double* hd = s->h_out.as<double>();
+  uint32_t* hi = reinterpret_cast<uint32_t*>(hd + nq);
+  GC_CUDA(cudaMemcpyAsync(hd, s->d_dist.p, sizeof(double) * nq, cudaMemcpyDeviceToHost, s->stream));
+  GC_CUDA(cudaMemcpyAsync(hi, s->d_idx.p, sizeof(uint32_t) * nq, cudaMemcpyDeviceToHost, s->stream));
+  GC_CUDA(cudaStreamSynchronize(s->stream));
+  memcpy(dist, hd, sizeof(double) * nq);
+  memcpy(idx, hi, sizeof(uint32_t) * nq);
+  return GC_OK;
+}
+
+static int fetch_lists(gc_store* s, uint32_t nq, uint32_t cap, uint32_t* idx, double* dist, uint32_t* count)
+{
+  const size_t n = (size_t)nq * cap;
+  GC_TRY(s->h_out.reserve(sizeof(double) * n + sizeof(uint32_t) * n + sizeof(uint32_t) * nq));
+  double* hd = s->h_out.as<double>();
+  uint32_t* hi = reinterpret_cast<uint32_t*>(hd + n);
+  uint32_t* hc = hi + n;
+  GC_CUDA(cudaMemcpyAsync(hc, s->d_count.p, sizeof(uint32_t) * nq, cudaMemcpyDeviceToHost, s->stream));
+  GC_CUDA(cudaMemcpyAsync(hd, s->d_dist.p, sizeof(double) * n, cudaMemcpyDeviceToHost, s->stream));
+  GC_CUDA(cudaMemcpyAsync(hi, s->d_idx.p, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost, s->stream));
+  GC_CUDA(cudaStreamSynchronize(s->stream));
+  memcpy(count, hc, sizeof(uint32_t) * nq);
+  int rc = GC_OK;
+  for (uint32_t i = 0; i < nq; i++)
+  {
+    const uint32_t m = hc[i] < cap ? hc[i] : cap;
+    if (hc[i] > cap)
+      rc = GC_W_TRUNCATED;
+    memcpy(idx + (size_t)i * cap, hi + (size_t)i * cap, sizeof(uint32_t) * m);
+    memcpy(dist + (size_t)i * cap, hd + (size_t)i * cap, sizeof(double) * m);
+  }
+  return rc;
+}
+
+int gc_radius(gc_store_t* s, const double* q, const uint32_t* seg, const double* radius, uint32_t nq, uint32_t cap,
+              uint32_t* idx, double* dist, uint32_t* count)
+{
+  GC_REQUIRE(s && q && radius && idx && dist && count, "gc_radius: NULL argument");
+  if (nq == 0)
+    return GC_OK;
+  GC_CUDA(cudaSetDevice(s->device));
+  GC_TRY(stage_queries(s, q, seg, radius, nq));
+  const size_t n = (size_t)nq * cap;
+  GC_TRY(s->d_idx.reserve(sizeof(uint32_t) * n));
+  GC_TRY(s->d_dist.reserve(sizeof(double) * n));
+  GC_TRY(s->d_count.reserve(sizeof(uint32_t) * nq));
+  GC_TRY(radius_dev(s, s->d_q.as<double>(), seg ? s->d_seg.as<uint32_t>() : nullptr, s->d_radius.as<double>(), nq, cap,
+                    s->d_idx.as<uint32_t>(), s->d_dist.as<double>(), s->d_count.as<uint32_t>()));
+  return fetch_lists(s, nq, cap, idx, dist, count);
+}
+
+int gc_knn(gc_store_t* s, const double* q, const uint32_t* seg, uint32_t nq, uint64_t k, uint32_t cap, uint32_t* idx,
+           double* dist, uint32_t* count)
+{
+  GC_REQUIRE(s && q && idx && dist && count, "gc_knn: NULL argument");
+  if (nq == 0)
+    return GC_OK;
+  GC_CUDA(cudaSetDevice(s->device));
+  GC_TRY(stage_queries(s, q, seg, nullptr, nq));
+  const size_t n = (size_t)nq * cap;
+  GC_TRY(s->d_idx.reserve(sizeof(uint32_t) * n));
+  GC_TRY(s->d_dist.reserve(sizeof(double) * n));
+  GC_TRY(s->d_count.reserve(sizeof(uint32_t) * nq));
+  GC_TRY(knn_dev(s, s->d_q.as<double>(), seg ? s->d_seg.as<uint32_t>() : nullptr, nq, k, cap, s->d_idx.as<uint32_t>(),
+                 s->d_dist.as<double>(), s->d_count.as<uint32_t>()));
+  return fetch_lists(s, nq, cap, idx, dist, count);
+}
+
+}  // extern "C"

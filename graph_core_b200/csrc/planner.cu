@@ -1,0 +1,261 @@
+// planner.cu -- fused device part of Tree::extend for lock-step trees, and the Philox samplers.
+//
+//   Tree::findClosestNode          src/graph_core/graph/tree.cpp:56-59
+//   Tree::selectNextConfiguration  src/graph_core/graph/tree.cpp:110-128  (steer)
+//   Tree::tryExtendFromNode        src/graph_core/graph/tree.cpp:69-81    (edge check unless dist < TOLERANCE)
+//   Tree::near                     src/graph_core/graph/tree.cpp:751-754
+//   UniformSampler::sample         src/graph_core/samplers/uniform_sampler.cpp:34-39
+//
+// All kernels of one gc_extend_batch call are enqueued on the store's stream without any host
+// round trip in between: nearest -> steer -> edge plan/check -> radius-near -> sort.
+#include <math_constants.h>
+
+#include <cmath>
+
+#include "gc_common.cuh"
+
+namespace gc
+{
+// next = q                      when |node - q| <= max_distance   (same bits as q)
+//      = node + (q - node)/dist*max_distance  otherwise          (individually rounded fp64 ops)
+__global__ void steer_kernel(const double* __restrict__ x64, const double* __restrict__ q,
+                             const uint32_t* __restrict__ seg, const uint32_t* __restrict__ closest,
+                             const double* __restrict__ dist, uint32_t n, int dim, uint32_t cap_seg,
+                             double max_distance, double* __restrict__ c1, double* __restrict__ c2)
+{
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n)
+    return;
+  const uint32_t slot = closest[i];
+  const uint32_t sg = seg ? seg[i] : 0u;
+  const double dd = dist[i];
+  for (int d = 0; d < dim; d++)
+  {
+    const double qv = q[(size_t)i * dim + d];
+    double nc = qv, nx = qv;
+    if (slot != GC_NO_NODE)
+    {
+      nc = x64[((size_t)sg * cap_seg + slot) * dim + d];
+      if (!(dd <= max_distance))
+        nx = __dadd_rn(nc, __dmul_rn(__ddiv_rn(__dsub_rn(qv, nc), dd), max_distance));
+    }
+    c1[(size_t)i * dim + d] = nc;
+    c2[(size_t)i * dim + d] = nx;
+  }
+}
+
+// ---- Philox4x32-10 ------------------------------------------------------------------------------
+__device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,
+                                              uint32_t k1, uint32_t* out)
+{
+#pragma unroll
+  for (int r = 0; r < 10; r++)
+  {
+    const uint32_t hi0 = __umulhi(GC_PHILOX_M0, c0), lo0 = GC_PHILOX_M0 * c0;
+    const uint32_t hi1 = __umulhi(GC_PHILOX_M1, c2), lo1 = GC_PHILOX_M1 * c2;
+    const uint32_t n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
+    c0 = n0;
+    c1 = n1;
+    c2 = n2;
+    c3 = n3;
+    k0 += GC_PHILOX_W0;
+    k1 += GC_PHILOX_W1;
+  }
+  out[0] = c0;
+  out[1] = c1;
+  out[2] = c2;
+  out[3] = c3;
+}
+
+__device__ __forceinline__ double u01(uint32_t hi, uint32_t lo)
+{
+  const unsigned long long x = ((unsigned long long)hi << 32) | lo;
+  return (double)(x >> 11) * 1.1102230246251565404e-16;  // 2^-53
+}
+
+// x_d = 0.5*(lb+ub) + (2u-1) * 0.5*(lb-ub)   (the reference's formula with Random() in [-1,1))
+__global__ void sample_uniform_kernel(const double* __restrict__ lb, const double* __restrict__ ub, int dim,
+                                      unsigned long long seed, unsigned long long first, uint32_t n,
+                                      double* __restrict__ out)
+{
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t pairs = (uint32_t)(dim + 1) / 2;
+  if (t >= n * pairs)
+    return;
+  const uint32_t i = t / pairs, b = t % pairs;
+  const unsigned long long ctr = first + i;
+  uint32_t r[4];
+  philox4x32_10((uint32_t)ctr, (uint32_t)(ctr >> 32), b, 0u, (uint32_t)seed, (uint32_t)(seed >> 32), r);
+  for (int h = 0; h < 2; h++)
+  {
+    const int d = 2 * (int)b + h;
+    if (d < dim)
+    {
+      const double u = u01(r[2 * h], r[2 * h + 1]);
+      const double c = __dmul_rn(0.5, __dadd_rn(lb[d], ub[d]));
+      const double hw = __dmul_rn(0.5, __dsub_rn(lb[d], ub[d]));
+      const double rr = __dsub_rn(__dmul_rn(2.0, u), 1.0);
+      out[(size_t)i * dim + d] = __dadd_rn(c, __dmul_rn(rr, hw));
+    }
+  }
+}
+}  // namespace gc
+
+using namespace gc;
+
+extern "C" {
+
+int gc_extend_batch(gc_store_t* s, gc_world_t* w, const double* q, const uint32_t* seg, uint32_t n,
+                    double max_distance, double min_distance, double tolerance, const double* radius,
+                    uint32_t near_cap, uint32_t* closest, double* dist, double* next, uint8_t* ok,
+                    uint32_t* near_idx, double* near_dist, uint32_t* near_count)
+{
+  GC_REQUIRE(s && w && q && closest && dist && next && ok, "gc_extend_batch: NULL argument");
+  GC_REQUIRE(s->dim == w->dim, "gc_extend_batch: store dim %d != world dim %d", s->dim, w->dim);
+  GC_REQUIRE(s->device == w->device, "gc_extend_batch: store and world live on different devices");
+  GC_REQUIRE(!radius || (near_cap > 0 && near_idx && near_dist && near_count), "gc_extend_batch: near outputs missing");
+  GC_REQUIRE(max_distance > 0.0 && min_distance > 0.0, "gc_extend_batch: distances must be > 0");
+  if (n == 0)
+    return GC_OK;
+  GC_CUDA(cudaSetDevice(s->device));
+  const int D = s->dim;
+  cudaStream_t st = s->stream;
+  const size_t qb = sizeof(double) * (size_t)n * D;
+  const size_t sb = seg ? align_up(sizeof(uint32_t) * n, 16) : 0;
+  const size_t rb = radius ? sizeof(double) * n : 0;
+  const size_t lists = radius ? (size_t)n * near_cap : 0;
+  GC_TRY(s->h_in.reserve(qb + sb + rb));
+  GC_TRY(s->d_q.reserve(qb));
+  if (seg)
+    GC_TRY(s->d_seg.reserve(sb));
+  if (radius)
+    GC_TRY(s->d_radius.reserve(rb));
+  GC_TRY(s->d_misc.reserve(sizeof(double) * n + sizeof(uint32_t) * n));  // dist | closest
+  GC_TRY(w->d_c1.reserve(qb));
+  GC_TRY(w->d_c2.reserve(qb));
+  GC_TRY(w->d_ok.reserve(n));
+  if (radius)
+  {
+    GC_TRY(s->d_idx.reserve(sizeof(uint32_t) * lists));
+    GC_TRY(s->d_dist.reserve(sizeof(double) * lists));
+    GC_TRY(s->d_count.reserve(sizeof(uint32_t) * n));
+  }
+  // host output staging: dist[n] | next[n*D] | near_dist[lists] | closest[n] | near_idx[lists] | near_count[n] | ok[n]
+  const size_t out_bytes =
+      sizeof(double) * (n + (size_t)n * D + lists) + sizeof(uint32_t) * (n + lists + n) + n + 64;
+  GC_TRY(s->h_out.reserve(out_bytes));
+  GC_CUDA(cudaStreamSynchronize(st));
+  for (uint32_t i = 0; seg && i < n; i++)
+    GC_REQUIRE(seg[i] < s->nseg, "sample %u: segment %u of %u", i, seg[i], s->nseg);
+  char* h = static_cast<char*>(s->h_in.p);
+  memcpy(h, q, qb);
+  GC_CUDA(cudaMemcpyAsync(s->d_q.p, h, qb, cudaMemcpyHostToDevice, st));
+  if (seg)
+  {
+    memcpy(h + qb, seg, sizeof(uint32_t) * n);
+    GC_CUDA(cudaMemcpyAsync(s->d_seg.p, h + qb, sizeof(uint32_t) * n, cudaMemcpyHostToDevice, st));
+  }
+  if (radius)
+  {
+    memcpy(h + qb + sb, radius, rb);
+    GC_CUDA(cudaMemcpyAsync(s->d_radius.p, h + qb + sb, rb, cudaMemcpyHostToDevice, st));
+  }
+  const uint32_t* d_seg = seg ? s->d_seg.as<uint32_t>() : nullptr;
+  double* d_dist = s->d_misc.as<double>();
+  uint32_t* d_closest = reinterpret_cast<uint32_t*>(d_dist + n);
+  GC_TRY(nn1_dev(s, s->d_q.as<double>(), d_seg, n, d_closest, d_dist, seg == nullptr));
+  steer_kernel<<<(n + 127) / 128, 128, 0, st>>>(s->x64, s->d_q.as<double>(), d_seg, d_closest, d_dist, n, D,
+                                                 s->cap_seg, max_distance, w->d_c1.as<double>(),
+                                                 w->d_c2.as<double>());
+  GC_CUDA(cudaGetLastError());
+  // states per edge for an edge of length max_distance (grid sizing only)
+  uint64_t per_edge = 2;
+  for (double nn = 2; max_distance > nn * min_distance && per_edge < (1u << 20); nn *= 2)
+    per_edge += (uint64_t)(nn / 2);
+  GC_TRY(check_edges_dev(w, w->d_c1.as<double>(), w->d_c2.as<double>(), nullptr, n, min_distance, GC_EDGE_BISECT,
+                         w->d_ok.as<uint8_t>(), nullptr, per_edge * n, st));
+  if (radius)
+    GC_TRY(radius_dev(s, w->d_c2.as<double>(), d_seg, s->d_radius.as<double>(), n, near_cap, s->d_idx.as<uint32_t>(),
+                      s->d_dist.as<double>(), s->d_count.as<uint32_t>()));
+  double* h_dist = s->h_out.as<double>();
+  double* h_next = h_dist + n;
+  double* h_ndist = h_next + (size_t)n * D;
+  uint32_t* h_closest = reinterpret_cast<uint32_t*>(h_ndist + lists);
+  uint32_t* h_nidx = h_closest + n;
+  uint32_t* h_ncount = h_nidx + lists;
+  uint8_t* h_ok = reinterpret_cast<uint8_t*>(h_ncount + n);
+  GC_CUDA(cudaMemcpyAsync(h_dist, d_dist, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
+  GC_CUDA(cudaMemcpyAsync(h_closest, d_closest, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost, st));
+  GC_CUDA(cudaMemcpyAsync(h_next, w->d_c2.p, qb, cudaMemcpyDeviceToHost, st));
+  GC_CUDA(cudaMemcpyAsync(h_ok, w->d_ok.p, n, cudaMemcpyDeviceToHost, st));
+  if (radius)
+  {
+    GC_CUDA(cudaMemcpyAsync(h_ncount, s->d_count.p, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost, st));
+    GC_CUDA(cudaMemcpyAsync(h_ndist, s->d_dist.p, sizeof(double) * lists, cudaMemcpyDeviceToHost, st));
+    GC_CUDA(cudaMemcpyAsync(h_nidx, s->d_idx.p, sizeof(uint32_t) * lists, cudaMemcpyDeviceToHost, st));
+  }
+  GC_CUDA(cudaStreamSynchronize(st));
+  int rc = GC_OK;
+  memcpy(dist, h_dist, sizeof(double) * n);
+  memcpy(closest, h_closest, sizeof(uint32_t) * n);
+  memcpy(next, h_next, qb);
+  for (uint32_t i = 0; i < n; i++)
+  {
+    if (h_closest[i] == GC_NO_NODE)
+      ok[i] = 0;  // empty tree: nothing to extend from
+    else
+      ok[i] = (h_dist[i] < tolerance) ? 1 : h_ok[i];  // tree.cpp:76-77
+  }
+  if (radius)
+  {
+    memcpy(near_count, h_ncount, sizeof(uint32_t) * n);
+    for (uint32_t i = 0; i < n; i++)
+    {
+      const uint32_t m = h_ncount[i] < near_cap ? h_ncount[i] : near_cap;
+      if (h_ncount[i] > near_cap)
+        rc = GC_W_TRUNCATED;
+      memcpy(near_idx + (size_t)i * near_cap, h_nidx + (size_t)i * near_cap, sizeof(uint32_t) * m);
+      memcpy(near_dist + (size_t)i * near_cap, h_ndist + (size_t)i * near_cap, sizeof(double) * m);
+    }
+  }
+  return rc;
+}
+
+int gc_sample_uniform(int device, int dim, const double* lb, const double* ub, uint64_t seed, uint64_t first_index,
+                      uint32_t n, double* out)
+{
+  GC_REQUIRE(lb && ub && out, "gc_sample_uniform: NULL argument");
+  GC_REQUIRE(dim >= 1 && dim <= GC_MAX_DIM, "gc_sample_uniform: dim %d", dim);
+  if (n == 0)
+    return GC_OK;
+  int ndev = 0;
+  GC_TRY(gc_device_count(&ndev));
+  GC_REQUIRE(device >= 0 && device < ndev, "gc_sample_uniform: device %d of %d", device, ndev);
+  GC_CUDA(cudaSetDevice(device));
+  double *d_b = nullptr, *d_out = nullptr;
+  GC_CUDA(cudaMalloc(&d_b, sizeof(double) * 2 * dim));
+  cudaError_t e = cudaMalloc(&d_out, sizeof(double) * (size_t)n * dim);
+  if (e != cudaSuccess)
+  {
+    cudaFree(d_b);
+    gc::set_error("gc_sample_uniform: %s", cudaGetErrorString(e));
+    return GC_E_CUDA;
+  }
+  cudaMemcpy(d_b, lb, sizeof(double) * dim, cudaMemcpyHostToDevice);
+  cudaMemcpy(d_b + dim, ub, sizeof(double) * dim, cudaMemcpyHostToDevice);
+  const uint32_t total = n * (uint32_t)((dim + 1) / 2);
+  sample_uniform_kernel<<<(total + 255) / 256, 256>>>(d_b, d_b + dim, dim, seed, first_index, n, d_out);
+  e = cudaGetLastError();
+  if (e == cudaSuccess)
+    e = cudaMemcpy(out, d_out, sizeof(double) * (size_t)n * dim, cudaMemcpyDeviceToHost);
+  cudaFree(d_b);
+  cudaFree(d_out);
+  if (e != cudaSuccess)
+  {
+    gc::set_error("gc_sample_uniform: %s", cudaGetErrorString(e));
+    return GC_E_CUDA;
+  }
+  return GC_OK;
+}
+
+}  // extern "C"

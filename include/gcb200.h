@@ -1,0 +1,149 @@
+/*
+ * gcb200.h -- C ABI of the B200-native graph_core hot paths.
+ *
+ * The reference (JRL-CARI-CNR-UNIBS/graph_core) has no FFI: its two hot paths sit
+ * behind C++ virtual interfaces.  This header is the NEW boundary underneath the
+ * drop-in plugin classes (graph_core_b200/host/):
+ *
+ *   graph::core::NearestNeighbors      include/graph_core/datastructure/nearest_neighbors.h:41-195
+ *     -> CudaNearestNeighbors          -> gc_store_* / gc_nn1 / gc_radius / gc_knn
+ *   graph::core::CollisionCheckerBase  include/graph_core/collision_checkers/collision_checker_base.h:118-319
+ *     -> CudaCollisionChecker          -> gc_world_* / gc_check_states / gc_check_edges*
+ *
+ * Conventions
+ *   - every function returns 0 on success, <0 on error (gc_last_error() explains),
+ *     >0 for a non-fatal condition (GC_W_TRUNCATED).  Nothing throws or aborts.
+ *   - plain pointers and sizes only.  Unless the name ends in _dev all buffers are
+ *     HOST memory owned by the caller; the call returns after the results are in them.
+ *   - *_dev entry points take DEVICE pointers, enqueue on the handle's stream and do
+ *     not synchronise (for callers that keep data resident in HBM).
+ *   - a handle is not thread-safe; distinct handles are independent.
+ *   - there is NO CPU fallback: without a CUDA device every create() fails.
+ *   - node slots are 32-bit and stable: slot = insertion order inside a segment.
+ *     "lowest slot wins" on exactly equal fp64 distances (Vector semantics,
+ *     src/graph_core/datastructure/vector.cpp:55-67).
+ */
+#ifndef GCB200_H_
+#define GCB200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#include "gcb200_spec.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GC_OK 0
+#define GC_W_TRUNCATED 1        /* an output list was longer than the caller's cap; counts hold the true sizes */
+#define GC_W_NOOP 2             /* tombstone/restore of a slot already in that state                         */
+#define GC_E_INVALID (-1)       /* bad argument                                                              */
+#define GC_E_CUDA (-2)          /* CUDA runtime error (message in gc_last_error)                             */
+#define GC_E_CAPACITY (-3)      /* store segment full                                                        */
+#define GC_E_UNSUPPORTED (-4)   /* combination not implemented on the device path                            */
+#define GC_E_NOT_ON_SEGMENT (-5)/* checkConnFromConf: conf not on the parent-child segment (reference throws) */
+
+#define GC_NO_NODE 0xFFFFFFFFu
+
+typedef struct gc_store gc_store_t; /* device-resident SoA node store (one or many trees = segments) */
+typedef struct gc_world gc_world_t; /* device-resident immutable collision world, ref-counted       */
+
+/* ---- library -------------------------------------------------------------------- */
+int gc_version(void);
+const char* gc_last_error(void);
+int gc_device_count(int* count);
+/* name[0..len) receives the device name; sms and cc (10*major+minor) may be NULL */
+int gc_device_info(int device, char* name, int len, int* sms, int* cc);
+
+/* ---- node store: replaces KdTree/Vector storage (kdtree.cpp:327-342, vector.cpp:38-43) ---- */
+int gc_store_create(int dim, uint32_t capacity_per_segment, uint32_t n_segments, int device, gc_store_t** out);
+int gc_store_destroy(gc_store_t* s);
+/* use an externally owned cudaStream_t (e.g. torch's current stream); NULL restores the private stream */
+int gc_store_set_stream(gc_store_t* s, void* cuda_stream);
+/* NearestNeighbors::insert -- appends n rows (row-major, dim doubles each) to one segment */
+int gc_store_append(gc_store_t* s, uint32_t segment, const double* q, uint32_t n, uint32_t* first_slot);
+/* one row per listed segment (lock-step planners); slots[i] receives the slot of row i */
+int gc_store_append_multi(gc_store_t* s, const uint32_t* segments, const double* q, uint32_t n, uint32_t* slots);
+/* lazy deletion as KdNode::deleteNode / restoreNode (kdtree.cpp:261-278) */
+int gc_store_tombstone(gc_store_t* s, uint32_t segment, uint32_t slot);
+int gc_store_restore(gc_store_t* s, uint32_t segment, uint32_t slot);
+/* NearestNeighbors::clear; segment == GC_NO_NODE clears every segment */
+int gc_store_clear(gc_store_t* s, uint32_t segment);
+int gc_store_size(gc_store_t* s, uint32_t segment, uint32_t* slots_used, uint32_t* live);
+int gc_store_read(gc_store_t* s, uint32_t segment, uint32_t first_slot, uint32_t n, double* q_out);
+int gc_store_dim(gc_store_t* s);
+
+/* ---- queries.  Query i runs against segment seg[i] (seg == NULL: segment 0). ------------- */
+/* NearestNeighbors::nearestNeighbor (kdtree.cpp:354-360 / vector.cpp:55-67).
+ * Empty segment: idx = GC_NO_NODE, dist = +inf.                                              */
+int gc_nn1(gc_store_t* s, const double* q, const uint32_t* seg, uint32_t nq, uint32_t* idx, double* dist);
+/* NearestNeighbors::near (kdtree.cpp:362-370 / vector.cpp:69-81): strict dist < radius[i].
+ * Query i writes min(count[i], cap) entries at idx/dist[i*cap ...], ascending (dist, slot). */
+int gc_radius(gc_store_t* s, const double* q, const uint32_t* seg, const double* radius, uint32_t nq, uint32_t cap,
+              uint32_t* idx, double* dist, uint32_t* count);
+/* NearestNeighbors::kNearestNeighbors (vector.cpp:83-96): the k closest live nodes, all of
+ * them when the segment holds fewer than k.  Same output layout as gc_radius.               */
+int gc_knn(gc_store_t* s, const double* q, const uint32_t* seg, uint32_t nq, uint64_t k, uint32_t cap, uint32_t* idx,
+           double* dist, uint32_t* count);
+/* device-pointer variants (asynchronous on the store's stream) */
+int gc_nn1_dev(gc_store_t* s, const double* d_q, const uint32_t* d_seg, uint32_t nq, uint32_t* d_idx, double* d_dist);
+int gc_radius_dev(gc_store_t* s, const double* d_q, const uint32_t* d_seg, const double* d_radius, uint32_t nq,
+                  uint32_t cap, uint32_t* d_idx, double* d_dist, uint32_t* d_count);
+int gc_knn_dev(gc_store_t* s, const double* d_q, const uint32_t* d_seg, uint32_t nq, uint64_t k, uint32_t cap,
+               uint32_t* d_idx, double* d_dist, uint32_t* d_count);
+
+/* ---- collision worlds (check(q) of collision_checker_base.h:166) --------------------------- */
+int gc_world_create_cube(int dim, double threshold, int device, gc_world_t** out);
+int gc_world_create_boxes(int dim, uint32_t n, const double* lo, const double* hi, int device, gc_world_t** out);
+int gc_world_create_cspheres(int dim, uint32_t n, const float* centers, const float* radii, int device,
+                             gc_world_t** out);
+/* base_tf[12], joint_tf[njoints][12]: 3x3 rotation row-major then translation; robot sphere k sits at
+ * rs_local[k][0..2] (radius rs_local[k][3]) in link frame rs_link[k] in [0, njoints]; obs[nobs][4] = x y z r */
+int gc_world_create_sphere_arm(int njoints, const float* base_tf, const float* joint_tf, uint32_t nrs,
+                               const int32_t* rs_link, const float* rs_local, uint32_t nobs, const float* obs,
+                               int device, gc_world_t** out);
+int gc_world_retain(gc_world_t* w);  /* CollisionCheckerBase::clone shares the immutable device world */
+int gc_world_destroy(gc_world_t* w); /* drops one reference */
+int gc_world_set_stream(gc_world_t* w, void* cuda_stream);
+int gc_world_dim(gc_world_t* w);
+/* out[0] states evaluated, out[1] sphere-pair tests executed, out[2] edge-kernel launches,
+ * out[3] edge-kernel device time in ns (only while timing is enabled) */
+int gc_world_counters(gc_world_t* w, uint64_t out[4]);
+int gc_world_reset_counters(gc_world_t* w);
+int gc_world_enable_timing(gc_world_t* w, int on);
+
+/* CollisionCheckerBase::check on n configurations: ok[i] = 1 collision free */
+int gc_check_states(gc_world_t* w, const double* q, uint32_t n, uint8_t* ok);
+/* checkConnection on n segments c1[i]->c2[i].
+ * mode GC_EDGE_BISECT (:207-237): ok only.
+ * mode GC_EDGE_LINEAR (:178-205): first_bad[i] = index of the first colliding state in the
+ *   reference's visiting order (0 = c1, 1..npnt-1 interior, npnt = c2), -1 when free.       */
+int gc_check_edges(gc_world_t* w, const double* c1, const double* c2, uint32_t n, double min_distance, int mode,
+                   uint8_t* ok, int64_t* first_bad);
+/* checkConnFromConf (:264-313): result[i] = 1 free, 0 collision, 255 conf not on the segment */
+int gc_check_edges_from_conf(gc_world_t* w, const double* parent, const double* child, const double* conf, uint32_t n,
+                             double min_distance, uint8_t* result);
+int gc_check_states_dev(gc_world_t* w, const double* d_q, uint32_t n, uint8_t* d_ok);
+int gc_check_edges_dev(gc_world_t* w, const double* d_c1, const double* d_c2, uint32_t n, double min_distance,
+                       int mode, uint8_t* d_ok, int64_t* d_first_bad);
+
+/* ---- fused planner step: Tree::extend's device part for n lock-step trees ------------------
+ * For sample i against segment seg[i]: nearest node (tree.cpp:56-59), steer to at most
+ * max_distance (tree.cpp:110-128), bisection edge check closest->next unless dist < tolerance
+ * (tree.cpp:69-81) and, when radius != NULL, the radius-near set around next (tree.cpp:751-754).
+ * Outputs: closest[i], dist[i] (unclamped), next[i][dim], ok[i]; near lists as gc_radius.     */
+int gc_extend_batch(gc_store_t* s, gc_world_t* w, const double* q, const uint32_t* seg, uint32_t n,
+                    double max_distance, double min_distance, double tolerance, const double* radius,
+                    uint32_t near_cap, uint32_t* closest, double* dist, double* next, uint8_t* ok,
+                    uint32_t* near_idx, double* near_dist, uint32_t* near_count);
+
+/* ---- Philox samplers (uniform_sampler.cpp:34-39, informed_sampler.cpp:145-180) -------------- */
+/* n uniform samples in [lb, ub]; sample i uses Philox counter (first_index + i) */
+int gc_sample_uniform(int device, int dim, const double* lb, const double* ub, uint64_t seed, uint64_t first_index,
+                      uint32_t n, double* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

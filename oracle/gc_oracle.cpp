@@ -1,0 +1,1527 @@
+/*
+ * gc_oracle.cpp -- CPU ORACLE (test infrastructure, NOT product code).
+ *
+ * A plain C++ restatement of the two graph_core hot paths and of the callers
+ * that drive them.  It exists so that the CUDA path can be checked bit for bit
+ * and so that bench.py has a host-CPU baseline ("port").  Only tests/,
+ * __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs
+ * may load this library; nothing under graph_core_b200/ links or calls it.
+ *
+ * PARITY PINNING: the reference's own tests hold no numerical vector for either
+ * path.  The restatement is pinned instead against the
+ * reference's own sources compiled in this container against stand-in headers
+ * (oracle/_ref, see oracle/Makefile and oracle/ref_driver.cpp) and against the
+ * single fixture tests/path.yaml.  Where oracle/_ref is not built the header of
+ * tests/test_oracle_vs_ref.py says "parity unpinned".
+ *
+ * Reference citations are relative to /root/reference/graph_core/ :
+ *   inc/ = include/graph_core/,  src/ = src/graph_core/
+ *
+ * Arithmetic conventions (documented in DESIGN.md, mirrored by the CUDA code):
+ *   - Euclidean norm = sqrt(sum_i (a_i-b_i)^2), i ascending, every operation
+ *     individually rounded in fp64 (build with -ffp-contract=off).
+ *   - synthetic worlds (not in the reference) follow include/gcb200_spec.h.
+ */
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <limits>
+#include <map>
+#include <memory>
+#include <stdexcept>
+#include <vector>
+
+#include "../include/gcb200_spec.h"
+
+namespace orc
+{
+static const double kInf = std::numeric_limits<double>::infinity();
+static const double TOLERANCE = 1e-06;  // inc/util.h:80
+
+// Eigen (a-b).norm() restated: sequential sum of squares, then sqrt.
+static inline double dist(const double* a, const double* b, int d)
+{
+  double s = 0.0;
+  for (int i = 0; i < d; i++)
+  {
+    double t = a[i] - b[i];
+    s = s + t * t;
+  }
+  return std::sqrt(s);
+}
+
+// ============================================================================
+//  Node set: ids are creation order; configurations immutable (src/graph/node.cpp:34-48)
+// ============================================================================
+struct NodePool
+{
+  int dim;
+  std::vector<double> q;  // [n][dim]
+  explicit NodePool(int d) : dim(d) {}
+  int add(const double* c)
+  {
+    q.insert(q.end(), c, c + dim);
+    return (int)(q.size() / dim) - 1;
+  }
+  const double* conf(int id) const { return &q[(size_t)id * dim]; }
+  int size() const { return (int)(q.size() / dim); }
+};
+
+typedef std::multimap<double, int> NearMap;  // multimap<double,NodePtr> of the reference
+
+// ============================================================================
+//  NearestNeighbors contract (inc/datastructure/nearest_neighbors.h:41-195)
+// ============================================================================
+struct NearestNeighbors
+{
+  NodePool* pool;
+  unsigned int size_ = 0;
+  unsigned int deleted_nodes_ = 0;
+  explicit NearestNeighbors(NodePool* p) : pool(p) {}
+  virtual ~NearestNeighbors() {}
+  virtual void insert(int node) = 0;
+  virtual bool clear() = 0;
+  virtual void nearestNeighbor(const double* q, int& best, double& best_distance) = 0;
+  virtual NearMap near(const double* q, double radius) = 0;
+  virtual NearMap kNearestNeighbors(const double* q, size_t k) = 0;
+  virtual bool findNode(int node) = 0;
+  virtual bool deleteNode(int node) = 0;
+  virtual bool restoreNode(int node) = 0;
+  virtual std::vector<int> getNodes() = 0;
+};
+
+// ---- Vector: brute force (src/datastructure/vector.cpp:38-138) ---------------
+struct VectorNN : NearestNeighbors
+{
+  std::vector<int> nodes_;
+  explicit VectorNN(NodePool* p) : NearestNeighbors(p) {}
+  void insert(int node) override  // vector.cpp:38-43
+  {
+    nodes_.push_back(node);
+    size_++;
+  }
+  bool clear() override  // :45-53
+  {
+    size_ = 0;
+    deleted_nodes_ = 0;
+    nodes_.clear();
+    return true;
+  }
+  void nearestNeighbor(const double* q, int& best, double& best_distance) override  // :55-67
+  {
+    best_distance = kInf;
+    for (int n : nodes_)
+    {
+      double d = dist(pool->conf(n), q, pool->dim);
+      if (d < best_distance)
+      {
+        best = n;
+        best_distance = d;
+      }
+    }
+  }
+  NearMap near(const double* q, double radius) override  // :69-81
+  {
+    NearMap out;
+    for (int n : nodes_)
+    {
+      double d = dist(pool->conf(n), q, pool->dim);
+      if (d < radius)
+        out.insert(std::make_pair(d, n));
+    }
+    return out;
+  }
+  NearMap kNearestNeighbors(const double* q, size_t k) override  // :83-96
+  {
+    NearMap all;
+    for (int n : nodes_)
+      all.insert(std::make_pair(dist(pool->conf(n), q, pool->dim), n));
+    if (all.size() < k)
+      return all;
+    return NearMap(all.begin(), std::next(all.begin(), k));
+  }
+  bool findNode(int node) override { return std::find(nodes_.begin(), nodes_.end(), node) != nodes_.end(); }
+  bool deleteNode(int node) override  // :103-119 (physical erase)
+  {
+    auto it = std::find(nodes_.begin(), nodes_.end(), node);
+    if (it == nodes_.end())
+      return false;
+    size_--;
+    deleted_nodes_++;
+    nodes_.erase(it);
+    return true;
+  }
+  bool restoreNode(int) override { return false; }  // :121-124
+  std::vector<int> getNodes() override { return nodes_; }
+};
+
+// ---- KdTree: unbalanced incremental k-d tree (src/datastructure/kdtree.cpp:91-472) ----
+struct KdNode
+{
+  int node;
+  int dimension;
+  bool deleted = false;
+  int left = -1, right = -1;
+};
+
+struct KdTreeNN : NearestNeighbors
+{
+  std::vector<KdNode> kd;  // kd[0] is the root when non-empty
+  unsigned int deleted_nodes_threshold_ = std::numeric_limits<unsigned int>::max();  // kdtree.cpp:319
+  explicit KdTreeNN(NodePool* p) : NearestNeighbors(p) {}
+
+  // KdNode::insert (kdtree.cpp:91-125); returns false when an existing node is restored
+  bool kdInsert(int cur, int node)
+  {
+    for (;;)
+    {
+      if (node == kd[cur].node)
+      {
+        kd[cur].deleted = false;
+        return false;
+      }
+      int dimn = kd[cur].dimension;
+      int next_dim = (dimn == pool->dim - 1) ? 0 : dimn + 1;
+      if (pool->conf(node)[dimn] >= pool->conf(kd[cur].node)[dimn])  // goRight
+      {
+        if (kd[cur].right < 0)
+        {
+          KdNode nn;
+          nn.node = node;
+          nn.dimension = next_dim;
+          kd.push_back(nn);
+          kd[cur].right = (int)kd.size() - 1;
+          return true;
+        }
+        cur = kd[cur].right;
+      }
+      else
+      {
+        if (kd[cur].left < 0)
+        {
+          KdNode nn;
+          nn.node = node;
+          nn.dimension = next_dim;
+          kd.push_back(nn);
+          kd[cur].left = (int)kd.size() - 1;
+          return true;
+        }
+        cur = kd[cur].left;
+      }
+    }
+  }
+  void insert(int node) override  // kdtree.cpp:327-342
+  {
+    size_++;
+    if (kd.empty())
+    {
+      KdNode r;
+      r.node = node;
+      r.dimension = 0;
+      kd.push_back(r);
+      return;
+    }
+    if (!kdInsert(0, node))
+      deleted_nodes_--;
+  }
+  bool clear() override  // :344-352
+  {
+    size_ = 0;
+    deleted_nodes_ = 0;
+    kd.clear();
+    return true;
+  }
+  // KdNode::nearestNeighbor (:127-161)
+  void nnRec(int cur, const double* q, int& best, double& best_distance)
+  {
+    const KdNode& k = kd[cur];
+    const double* c = pool->conf(k.node);
+    double distance = dist(q, c, pool->dim);
+    if (!k.deleted && distance < best_distance)
+    {
+      best_distance = distance;
+      best = k.node;
+    }
+    int dm = k.dimension;
+    int l = k.left, r = k.right;
+    bool right_first = q[dm] > c[dm];
+    if (!right_first)
+    {
+      if (l >= 0 && (q[dm] - best_distance) <= c[dm])
+        nnRec(l, q, best, best_distance);
+      if (r >= 0 && (q[dm] + best_distance) >= c[dm])
+        nnRec(r, q, best, best_distance);
+    }
+    else
+    {
+      if (r >= 0 && (q[dm] + best_distance) >= c[dm])
+        nnRec(r, q, best, best_distance);
+      if (l >= 0 && (q[dm] - best_distance) <= c[dm])
+        nnRec(l, q, best, best_distance);
+    }
+  }
+  void nearestNeighbor(const double* q, int& best, double& best_distance) override  // :354-360
+  {
+    best_distance = kInf;
+    if (kd.empty())
+      return;
+    nnRec(0, q, best, best_distance);
+  }
+  // KdNode::near (:163-180)
+  void nearRec(int cur, const double* q, double radius, NearMap& out)
+  {
+    const KdNode& k = kd[cur];
+    const double* c = pool->conf(k.node);
+    double distance = dist(q, c, pool->dim);
+    if (!k.deleted && distance < radius)
+      out.insert(std::make_pair(distance, k.node));
+    int dm = k.dimension;
+    int l = k.left, r = k.right;
+    if (l >= 0 && (q[dm] - radius) <= c[dm])
+      nearRec(l, q, radius, out);
+    if (r >= 0 && (q[dm] + radius) >= c[dm])
+      nearRec(r, q, radius, out);
+  }
+  NearMap near(const double* q, double radius) override  // :362-370
+  {
+    NearMap out;
+    if (kd.empty())
+      return out;
+    nearRec(0, q, radius, out);
+    return out;
+  }
+  // KdNode::kNearestNeighbors (:182-229)
+  void knnRec(int cur, const double* q, size_t k, NearMap& nodes)
+  {
+    const KdNode& kn = kd[cur];
+    const double* c = pool->conf(kn.node);
+    double last_distance = nodes.empty() ? kInf : std::prev(nodes.end())->first;
+    double distance = dist(q, c, pool->dim);
+    if (!kn.deleted && nodes.size() < k)
+    {
+      nodes.insert(std::make_pair(distance, kn.node));
+      last_distance = std::prev(nodes.end())->first;
+    }
+    else if (!kn.deleted && distance < last_distance)
+    {
+      nodes.erase(std::prev(nodes.end()));
+      nodes.insert(std::make_pair(distance, kn.node));
+      last_distance = std::prev(nodes.end())->first;
+    }
+    int dm = kn.dimension;
+    int l = kn.left, r = kn.right;
+    bool right_first = q[dm] > c[dm];
+    if (!right_first)
+    {
+      if (l >= 0 && (q[dm] - last_distance) <= c[dm])
+        knnRec(l, q, k, nodes);
+      if (r >= 0 && (q[dm] + last_distance) >= c[dm])
+        knnRec(r, q, k, nodes);
+    }
+    else
+    {
+      if (r >= 0 && (q[dm] + last_distance) >= c[dm])
+        knnRec(r, q, k, nodes);
+      if (l >= 0 && (q[dm] - last_distance) <= c[dm])
+        knnRec(l, q, k, nodes);
+    }
+  }
+  NearMap kNearestNeighbors(const double* q, size_t k) override  // :372-380
+  {
+    NearMap out;
+    if (kd.empty())
+      return out;
+    knnRec(0, q, k, out);
+    return out;
+  }
+  // KdNode::findNode (:231-259): descends by coordinates, fails on tombstones
+  int findKd(int node)
+  {
+    if (kd.empty())
+      return -1;
+    int cur = 0;
+    for (;;)
+    {
+      if (kd[cur].node == node)
+        return kd[cur].deleted ? -1 : cur;
+      int dm = kd[cur].dimension;
+      if (pool->conf(node)[dm] >= pool->conf(kd[cur].node)[dm])
+      {
+        if (kd[cur].right < 0)
+          return -1;
+        cur = kd[cur].right;
+      }
+      else
+      {
+        if (kd[cur].left < 0)
+          return -1;
+        cur = kd[cur].left;
+      }
+    }
+  }
+  bool findNode(int node) override { return findKd(node) >= 0; }
+  void getNodesRec(int cur, std::vector<int>& out)  // :280-288 (preorder, skips tombstones)
+  {
+    if (!kd[cur].deleted)
+      out.push_back(kd[cur].node);
+    if (kd[cur].left >= 0)
+      getNodesRec(kd[cur].left, out);
+    if (kd[cur].right >= 0)
+      getNodesRec(kd[cur].right, out);
+  }
+  std::vector<int> getNodes() override
+  {
+    std::vector<int> out;
+    if (!kd.empty())
+      getNodesRec(0, out);
+    return out;
+  }
+  bool deleteNode(int node) override  // :395-428
+  {
+    int k = findKd(node);
+    if (k < 0)
+      return false;
+    if (!kd[k].deleted)
+    {
+      kd[k].deleted = true;
+      size_--;
+      deleted_nodes_++;
+      if (deleted_nodes_ > deleted_nodes_threshold_ && size_ > 0)
+      {
+        bool root_was_deleted = kd[0].deleted;
+        int root_node = kd[0].node;
+        kd[0].deleted = false;
+        std::vector<int> nodes = getNodes();
+        clear();
+        for (int n : nodes)
+          insert(n);
+        if (root_was_deleted)
+          deleteNode(root_node);
+      }
+    }
+    return true;
+  }
+  bool restoreNode(int node) override  // :447-456 (findNode fails on tombstones => false for deleted nodes)
+  {
+    int k = findKd(node);
+    if (k < 0)
+      return false;
+    size_++;
+    deleted_nodes_--;
+    kd[k].deleted = false;
+    return true;
+  }
+};
+
+// ============================================================================
+//  Collision worlds: check(q) -> true = collision free (collision_checker_base.h:166)
+// ============================================================================
+struct World
+{
+  int kind = 0;
+  int dim = 0;
+  // cube
+  double cube_thr = 1.0;
+  // boxes: lo/hi [n][dim]
+  int nobj = 0;
+  std::vector<double> lo, hi;
+  // cspheres: centres fp32 [n][dim], radii^2 fp32
+  std::vector<float> sc, sr2;
+  // sphere arm
+  int njoints = 0, nrs = 0, nobs = 0;
+  std::vector<float> base_tf;   // 12: R row-major (9) + t (3)
+  std::vector<float> joint_tf;  // [J][12]
+  std::vector<int> rs_link;     // [nrs] in [0, J]
+  std::vector<float> rs_local;  // [nrs][4] x y z r
+  std::vector<float> obs;       // [nobs][4]
+  unsigned long long pair_tests = 0;  // executed sphere-pair tests (for flop accounting)
+  unsigned long long state_checks = 0;
+};
+
+static inline void sincos_spec(float q, float& s, float& c)
+{
+  float j = rintf(q * GC_TWO_OVER_PI);
+  float r = __builtin_fmaf(-j, GC_PIO2_1, q);
+  r = __builtin_fmaf(-j, GC_PIO2_2, r);
+  r = __builtin_fmaf(-j, GC_PIO2_3, r);
+  float z = r * r;
+  float ps = __builtin_fmaf(z, GC_SIN_S3, GC_SIN_S2);
+  ps = __builtin_fmaf(z, ps, GC_SIN_S1);
+  float rz = r * z;
+  float sn = __builtin_fmaf(rz, ps, r);
+  float pc = __builtin_fmaf(z, GC_COS_C3, GC_COS_C2);
+  pc = __builtin_fmaf(z, pc, GC_COS_C1);
+  float zz = z * z;
+  float cs = __builtin_fmaf(z, -0.5f, 1.0f);
+  cs = __builtin_fmaf(zz, pc, cs);
+  int qd = ((int)j) & 3;
+  switch (qd)
+  {
+    case 0: s = sn; c = cs; break;
+    case 1: s = cs; c = -sn; break;
+    case 2: s = -sn; c = -cs; break;
+    default: s = -cs; c = sn; break;
+  }
+}
+
+// 3x3 * 3x3 with the spec's operation order: out[r][c] = fma(a[r][2],b[2][c], fma(a[r][1],b[1][c], a[r][0]*b[0][c]))
+static inline void mat3_mul(const float* a, const float* b, float* o)
+{
+  for (int r = 0; r < 3; r++)
+    for (int c = 0; c < 3; c++)
+    {
+      float v = a[3 * r + 0] * b[0 + c];
+      v = __builtin_fmaf(a[3 * r + 1], b[3 + c], v);
+      v = __builtin_fmaf(a[3 * r + 2], b[6 + c], v);
+      o[3 * r + c] = v;
+    }
+}
+// o = R*p + t
+static inline void mat3_vec(const float* R, const float* t, const float* p, float* o)
+{
+  for (int r = 0; r < 3; r++)
+  {
+    float v = R[3 * r + 0] * p[0];
+    v = __builtin_fmaf(R[3 * r + 1], p[1], v);
+    v = __builtin_fmaf(R[3 * r + 2], p[2], v);
+    o[r] = v + t[r];
+  }
+}
+
+static bool check_sphere_arm(World& w, const double* q)
+{
+  const int J = w.njoints;
+  // link frames B_j (rotation 9 + translation 3), frame J = tool frame A_J
+  float fr[(GC_MAX_JOINTS + 1) * 12];
+  float AR[9], At[3];
+  for (int i = 0; i < 9; i++) AR[i] = w.base_tf[i];
+  for (int i = 0; i < 3; i++) At[i] = w.base_tf[9 + i];
+  for (int j = 0; j < J; j++)
+  {
+    float s, c;
+    sincos_spec((float)q[j], s, c);
+    // B = A * Rz(q): col0' = c*col0 + s*col1 ; col1' = c*col1 - s*col0 ; col2' = col2
+    float BR[9];
+    for (int r = 0; r < 3; r++)
+    {
+      float x = AR[3 * r + 0], y = AR[3 * r + 1];
+      BR[3 * r + 0] = __builtin_fmaf(s, y, c * x);
+      BR[3 * r + 1] = __builtin_fmaf(-s, x, c * y);
+      BR[3 * r + 2] = AR[3 * r + 2];
+    }
+    float* f = &fr[j * 12];
+    for (int i = 0; i < 9; i++) f[i] = BR[i];
+    for (int i = 0; i < 3; i++) f[9 + i] = At[i];
+    // A_{j+1} = B * F_j
+    const float* F = &w.joint_tf[j * 12];
+    float NR[9], Nt[3];
+    mat3_mul(BR, F, NR);
+    mat3_vec(BR, At, F + 9, Nt);
+    for (int i = 0; i < 9; i++) AR[i] = NR[i];
+    for (int i = 0; i < 3; i++) At[i] = Nt[i];
+  }
+  {
+    float* f = &fr[J * 12];
+    for (int i = 0; i < 9; i++) f[i] = AR[i];
+    for (int i = 0; i < 3; i++) f[9 + i] = At[i];
+  }
+  bool collide = false;
+  for (int k = 0; k < w.nrs && !collide; k++)
+  {
+    const float* f = &fr[w.rs_link[k] * 12];
+    float c[3];
+    mat3_vec(f, f + 9, &w.rs_local[4 * k], c);
+    float rs = w.rs_local[4 * k + 3];
+    for (int o = 0; o < w.nobs; o++)
+    {
+      const float* ob = &w.obs[4 * o];
+      float dx = ob[0] - c[0], dy = ob[1] - c[1], dz = ob[2] - c[2];
+      float d2 = dx * dx;
+      d2 = __builtin_fmaf(dy, dy, d2);
+      d2 = __builtin_fmaf(dz, dz, d2);
+      float rr = ob[3] + rs;
+      w.pair_tests++;
+      if (d2 < rr * rr)
+      {
+        collide = true;
+        break;
+      }
+    }
+  }
+  return !collide;
+}
+
+static bool world_check(World& w, const double* q)
+{
+  w.state_checks++;
+  switch (w.kind)
+  {
+    case GC_WORLD_CUBE:  // inc/collision_checkers/cube_3d_collision_checker.h:61-64
+    {
+      double m = 0.0;
+      for (int i = 0; i < w.dim; i++)
+        m = std::max(m, std::fabs(q[i]));
+      return m > w.cube_thr;
+    }
+    case GC_WORLD_BOXES:  // collide iff inside any box (closed), pure fp64 comparisons
+    {
+      for (int b = 0; b < w.nobj; b++)
+      {
+        bool inside = true;
+        for (int i = 0; i < w.dim; i++)
+        {
+          double v = q[i];
+          if (v < w.lo[(size_t)b * w.dim + i] || v > w.hi[(size_t)b * w.dim + i])
+          {
+            inside = false;
+            break;
+          }
+        }
+        if (inside)
+          return false;
+      }
+      return true;
+    }
+    case GC_WORLD_CSPHERES:  // collide iff sum (float(q_i)-c_i)^2 < r^2 in fp32 (fma chain, i ascending)
+    {
+      float qf[GC_MAX_DIM];
+      for (int i = 0; i < w.dim; i++)
+        qf[i] = (float)q[i];
+      for (int s = 0; s < w.nobj; s++)
+      {
+        const float* c = &w.sc[(size_t)s * w.dim];
+        float t0 = qf[0] - c[0];
+        float acc = t0 * t0;
+        for (int i = 1; i < w.dim; i++)
+        {
+          float t = qf[i] - c[i];
+          acc = __builtin_fmaf(t, t, acc);
+        }
+        w.pair_tests++;
+        if (acc < w.sr2[s])
+          return false;
+      }
+      return true;
+    }
+    case GC_WORLD_SPHERE_ARM:
+      return check_sphere_arm(w, q);
+  }
+  return false;
+}
+
+// ============================================================================
+//  CollisionCheckerBase discretisation logic (inc/collision_checkers/collision_checker_base.h)
+// ============================================================================
+// checkConnection(c1,c2)  :207-237 -- bisection order
+static bool checkConnectionBisect(World& w, const double* c1, const double* c2, double min_distance)
+{
+  const int d = w.dim;
+  if (!world_check(w, c1))
+    return false;
+  if (!world_check(w, c2))
+    return false;
+  double distance = dist(c2, c1, d);
+  if (distance < min_distance)
+    return true;
+  double conf[GC_MAX_DIM];
+  double n = 2;
+  while (distance > n * min_distance)
+  {
+    for (double idx = 1; idx < n; idx += 2)
+    {
+      for (int i = 0; i < d; i++)
+        conf[i] = c1[i] + ((c2[i] - c1[i]) * idx) / n;
+      if (!world_check(w, conf))
+        return false;
+    }
+    n *= 2;
+  }
+  return true;
+}
+
+// checkConnection(c1,c2,conf&) :178-205 -- linear order; returns first failing state index via *first_bad
+// (0 = c1, 1..npnt-1 interior, npnt = c2, -1 = none); conf receives the reference's "last feasible" vector.
+static bool checkConnectionLinear(World& w, const double* c1, const double* c2, double min_distance, double* conf,
+                                  long long* first_bad)
+{
+  const int d = w.dim;
+  *first_bad = -1;
+  if (!world_check(w, c1))
+  {
+    *first_bad = 0;
+    return false;
+  }
+  double dst = dist(c2, c1, d);
+  unsigned int npnt = (unsigned int)std::ceil(dst / min_distance);
+  if (npnt > 1)
+  {
+    double step[GC_MAX_DIM];
+    for (int i = 0; i < d; i++)
+      step[i] = (c2[i] - c1[i]) / (double)npnt;
+    for (unsigned int ipnt = 1; ipnt < npnt; ipnt++)
+    {
+      for (int i = 0; i < d; i++)
+        conf[i] = c1[i] + step[i] * (double)ipnt;
+      if (!world_check(w, conf))
+      {
+        for (int i = 0; i < d; i++)
+          conf[i] = c1[i] + step[i] * (double)(ipnt - 1);
+        *first_bad = ipnt;
+        return false;
+      }
+    }
+  }
+  if (!world_check(w, c2))
+  {
+    *first_bad = (npnt > 1) ? (long long)npnt : 1;
+    return false;
+  }
+  return true;
+}
+
+// checkConnFromConf(conn,this_conf) :264-313 ; returns -1 when the reference throws std::invalid_argument
+static int checkConnFromConf(World& w, const double* parent, const double* child, const double* this_conf,
+                             double min_distance)
+{
+  const int d = w.dim;
+  double dist_child = dist(this_conf, child, d);
+  double dist_parent = dist(parent, this_conf, d);
+  double dst = dist(parent, child, d);
+  if ((dst - dist_child - dist_parent) > 1e-04)
+    return -1;
+  if (!world_check(w, this_conf))
+    return 0;
+  if (!world_check(w, child))
+    return 0;
+  double distance = dist(this_conf, child, d);
+  if (distance < min_distance)
+    return 1;
+  double this_abscissa = dist(parent, this_conf, d) / dist(parent, child, d);
+  double n = 2;
+  double conf[GC_MAX_DIM];
+  while (distance > n * min_distance)
+  {
+    for (double idx = 1; idx < n; idx += 2)
+    {
+      double abscissa = idx / n;
+      if (abscissa >= this_abscissa)
+      {
+        for (int i = 0; i < d; i++)
+          conf[i] = parent[i] + (child[i] - parent[i]) * abscissa;
+        if (!world_check(w, conf))
+          return 0;
+      }
+    }
+    n *= 2;
+  }
+  return 1;
+}
+
+// ============================================================================
+//  Samplers' specific volume (inc/samplers/sampler_base.h:135-153, src/samplers/informed_sampler.cpp:181-233)
+// ============================================================================
+struct InformedSamplerState
+{
+  int ndof = 0;
+  std::vector<double> lb, ub, f1, f2;
+  double cost_ = kInf, focii_distance_ = 0, min_radius_ = 0, max_radius_ = 0, specific_volume_ = 0;
+  bool inf_cost_ = true;
+  void init(int d, const double* lower, const double* upper, const double* focus1, const double* focus2)
+  {
+    ndof = d;
+    lb.assign(lower, lower + d);
+    ub.assign(upper, upper + d);
+    f1.assign(focus1, focus1 + d);
+    f2.assign(focus2, focus2 + d);
+    focii_distance_ = dist(f1.data(), f2.data(), d);  // informed_sampler.cpp:86 (scale == 1)
+    setCost(kInf);
+  }
+  void setCost(double cost)  // informed_sampler.cpp:181-215
+  {
+    cost_ = cost;
+    inf_cost_ = cost_ >= kInf;
+    if (cost_ < focii_distance_)
+    {
+      cost_ = focii_distance_;
+      min_radius_ = 0.0;
+    }
+    else
+      min_radius_ = 0.5 * std::sqrt(std::pow(cost_, 2) - std::pow(focii_distance_, 2));
+    max_radius_ = 0.5 * cost_;
+    if (inf_cost_)
+    {
+      specific_volume_ = std::tgamma(((double)ndof) * 0.5 + 1.0) / std::pow(M_PI, (double)ndof * 0.5);
+      for (int i = 0; i < ndof; i++)
+        specific_volume_ *= (ub[i] - lb[i]);
+    }
+    else
+      specific_volume_ = max_radius_ * std::pow(min_radius_, ndof - 1);
+  }
+  bool inBoundsBox(const double* q) const
+  {
+    for (int i = 0; i < ndof; i++)
+      if (q[i] > ub[i] || q[i] < lb[i])
+        return false;
+    return true;
+  }
+};
+
+// ============================================================================
+//  Tree (src/graph/tree.cpp) -- parent-array restatement of Node/Connection bookkeeping
+// ============================================================================
+struct Counters
+{
+  unsigned long long nn1 = 0, near = 0, knn = 0, edges = 0, near_hits = 0;
+};
+
+struct Tree
+{
+  NodePool* pool;
+  std::unique_ptr<NearestNeighbors> nodes_;
+  World* checker_;
+  double min_distance_;
+  double max_distance_;
+  int root_;
+  double k_rrt_;
+  std::vector<int> parent;     // parent[id] = parent node id (-1: none)
+  std::vector<double> pcost;   // cost of the parent connection
+  Counters cnt;
+
+  Tree(NodePool* p, int root, double max_distance, World* checker, double min_distance, bool use_kdtree)
+    : pool(p), checker_(checker), min_distance_(min_distance), max_distance_(max_distance), root_(root)
+  {  // tree.cpp:34-54
+    if (use_kdtree)
+      nodes_.reset(new KdTreeNN(p));
+    else
+      nodes_.reset(new VectorNN(p));
+    nodes_->insert(root);
+    double dimension = p->dim;
+    k_rrt_ = 1.1 * std::pow(2.0, dimension + 1) * std::exp(1) * (1.0 + 1.0 / dimension);
+  }
+  void ensure(int id)
+  {
+    if ((int)parent.size() <= id)
+    {
+      parent.resize(id + 1, -1);
+      pcost.resize(id + 1, 0.0);
+    }
+  }
+  void setParent(int child, int par, double cost)
+  {
+    ensure(std::max(child, par));
+    parent[child] = par;
+    pcost[child] = cost;
+  }
+  bool checkConnection(const double* a, const double* b)
+  {
+    cnt.edges++;
+    return checkConnectionBisect(*checker_, a, b, min_distance_);
+  }
+  int findClosestNode(const double* q)  // tree.cpp:56-59
+  {
+    int best = -1;
+    double bd;
+    cnt.nn1++;
+    nodes_->nearestNeighbor(q, best, bd);
+    return best;
+  }
+  // tree.cpp:110-128
+  double selectNextConfiguration(const double* q, double* next, int node)
+  {
+    const int d = pool->dim;
+    const double* nc = pool->conf(node);
+    double distance = dist(nc, q, d);
+    if (distance <= max_distance_)
+      for (int i = 0; i < d; i++) next[i] = q[i];
+    else
+      for (int i = 0; i < d; i++) next[i] = nc[i] + (q[i] - nc[i]) / distance * max_distance_;
+    return distance;
+  }
+  bool tryExtendFromNode(const double* q, double* next, int node)  // tree.cpp:69-81
+  {
+    double distance = selectNextConfiguration(q, next, node);
+    if (distance < TOLERANCE)
+      return true;
+    return checkConnection(pool->conf(node), next);
+  }
+  bool extend(const double* q, int& new_node)  // tree.cpp:148-161 + extendOnly :130-140
+  {
+    int closest = findClosestNode(q);
+    double next[GC_MAX_DIM];
+    if (!tryExtendFromNode(q, next, closest))
+    {
+      new_node = -1;
+      return false;
+    }
+    new_node = pool->add(next);
+    double cost = dist(pool->conf(closest), pool->conf(new_node), pool->dim);  // metrics_->cost
+    setParent(new_node, closest, cost);
+    nodes_->insert(new_node);
+    return true;
+  }
+  bool isInTree(int node) { return nodes_->findNode(node); }
+  bool extendToNode(int node, int& new_node)  // tree.cpp:194-215
+  {
+    if (isInTree(node))
+      return true;
+    int closest = findClosestNode(pool->conf(node));
+    double next[GC_MAX_DIM];
+    if (!tryExtendFromNode(pool->conf(node), next, closest))
+      return false;
+    if (dist(next, pool->conf(node), pool->dim) < TOLERANCE)
+      new_node = node;
+    else
+      new_node = pool->add(next);
+    nodes_->insert(new_node);
+    double cost = dist(pool->conf(closest), pool->conf(new_node), pool->dim);
+    setParent(new_node, closest, cost);
+    return true;
+  }
+  bool connect(const double* q, int& new_node)  // tree.cpp:217-233
+  {
+    bool success = true;
+    while (success)
+    {
+      int tmp = -1;
+      success = extend(q, tmp);
+      if (success)
+      {
+        new_node = tmp;
+        if (dist(pool->conf(new_node), q, pool->dim) < TOLERANCE)
+          return true;
+      }
+    }
+    return false;
+  }
+  bool connectToNode(int node, int& new_node)  // tree.cpp:304-327 (no time limit)
+  {
+    bool success = true;
+    while (success)
+    {
+      int tmp = -1;
+      success = extendToNode(node, tmp);
+      if (success)
+      {
+        if (tmp < 0)  // node already in tree: the reference leaves tmp_node null and would crash; stop
+          return true;
+        new_node = tmp;
+        if (dist(pool->conf(new_node), pool->conf(node), pool->dim) < TOLERANCE)
+          return true;
+      }
+    }
+    return false;
+  }
+  double costToNode(int node)  // tree.cpp:767-789
+  {
+    double cost = 0;
+    while (node != root_)
+    {
+      if (node < 0 || node >= (int)parent.size() || parent[node] < 0)
+        return kInf;
+      cost += pcost[node];
+      node = parent[node];
+    }
+    return cost;
+  }
+  std::vector<int> getConnectionToNode(int node)  // tree.cpp:791-813: returns child ids root->node
+  {
+    std::vector<int> chain;
+    int t = node;
+    while (t != root_)
+    {
+      chain.push_back(t);
+      t = parent[t];
+    }
+    std::reverse(chain.begin(), chain.end());
+    return chain;
+  }
+  double pathCost(const std::vector<int>& chain)  // Path::computeCost path.cpp:285-291
+  {
+    double c = 0;
+    for (int id : chain)
+      c += pcost[id];
+    return c;
+  }
+  NearMap nearK(const double* q)  // tree.cpp:761-765
+  {
+    size_t k = (size_t)std::ceil(k_rrt_ * std::log(nodes_->size_ + 1));
+    cnt.knn++;
+    return nodes_->kNearestNeighbors(q, k);
+  }
+  // tree.cpp:381-513 (what_rewire = 0, empty white list)
+  bool rewireOnly(int node, double r_rewire)
+  {
+    const int d = pool->dim;
+    bool rewire_parent = (node != root_);
+    NearMap near_nodes;
+    if (r_rewire <= 0)
+      near_nodes = nearK(pool->conf(node));
+    else
+    {
+      cnt.near++;
+      near_nodes = nodes_->near(pool->conf(node), r_rewire);
+    }
+    cnt.near_hits += near_nodes.size();
+    double cost_to_node = costToNode(node);
+    bool improved = false;
+    if (rewire_parent)
+    {
+      int nearest_node = parent[node];
+      for (const auto& p : near_nodes)
+      {
+        int n = p.second;
+        if (n == nearest_node)
+          continue;
+        if (n == node)
+          continue;
+        double cost_to_near = costToNode(n);
+        if (cost_to_near >= cost_to_node)
+          continue;
+        double cost_near_to_node = dist(pool->conf(n), pool->conf(node), d);
+        if ((cost_to_near + cost_near_to_node) >= cost_to_node)
+          continue;
+        if (!checkConnection(pool->conf(n), pool->conf(node)))
+          continue;
+        setParent(node, n, cost_near_to_node);
+        cost_to_node = cost_to_near + cost_near_to_node;
+        improved = true;
+      }
+    }
+    int par = (node == root_) ? -1 : parent[node];
+    for (const auto& p : near_nodes)
+    {
+      int n = p.second;
+      if (n == par)
+        continue;
+      if (n == node)
+        continue;
+      if (n == root_)
+        continue;
+      double cost_to_near = costToNode(n);
+      if (cost_to_node >= cost_to_near)
+        continue;
+      double cost_node_to_near = dist(pool->conf(node), pool->conf(n), d);
+      if ((cost_to_node + cost_node_to_near) >= cost_to_near)
+        continue;
+      if (!checkConnection(pool->conf(node), pool->conf(n)))
+        continue;
+      setParent(n, node, cost_node_to_near);
+      improved = true;
+    }
+    return improved;
+  }
+  bool rewire(const double* q, double r_rewire, int& new_node)  // tree.cpp:718-726
+  {
+    if (!extend(q, new_node))
+      return false;
+    return rewireOnly(new_node, r_rewire);
+  }
+  // tree.cpp:235-302
+  bool informedExtend(const double* q, int& new_node, const double* goal, double cost2beat, double bias)
+  {
+    const int d = pool->dim;
+    NearMap closest = nearK(q);
+    if (closest.empty())
+      throw std::runtime_error("closest nodes map is empty");
+    struct Ext
+    {
+      int tree_node;
+      std::vector<double> new_conf;
+      double distance;
+    };
+    std::multimap<double, Ext> best;
+    double nc[GC_MAX_DIM];
+    for (const auto& n : closest)
+    {
+      double distance = selectNextConfiguration(q, nc, n.second);
+      double cost2node = costToNode(n.second);
+      double heuristic = bias * distance + (1 - bias) * cost2node;
+      if ((cost2node + distance + dist(goal, nc, d)) < cost2beat)
+      {
+        Ext e;
+        e.tree_node = n.second;
+        e.new_conf.assign(nc, nc + d);
+        e.distance = distance;
+        best.insert(std::make_pair(heuristic, e));
+      }
+    }
+    bool ok = false;
+    Ext ext;
+    for (const auto& n : best)
+    {
+      ext = n.second;
+      if (ext.distance < TOLERANCE)
+      {
+        ok = true;
+        break;
+      }
+      if (checkConnection(pool->conf(ext.tree_node), ext.new_conf.data()))
+      {
+        ok = true;
+        break;
+      }
+    }
+    if (!ok)
+      return false;
+    new_node = pool->add(ext.new_conf.data());
+    double cost = dist(pool->conf(ext.tree_node), pool->conf(new_node), d);
+    setParent(new_node, ext.tree_node, cost);
+    nodes_->insert(new_node);
+    return true;
+  }
+};
+
+// ============================================================================
+//  Solvers (src/solvers/{tree_solver,rrt,rrt_star}.cpp), driven by injected samples (tree_solver.h:338)
+// ============================================================================
+struct Solver
+{
+  enum Kind { RRT = 0, RRTSTAR = 1 };
+  int kind;
+  NodePool pool;
+  World* world;
+  std::unique_ptr<Tree> start_tree_;
+  InformedSamplerState sampler_;
+  int goal_node_ = -1;
+  double min_distance_, max_distance_, rewire_factor_, utopia_tolerance_;
+  bool use_kdtree_, extend_;
+  bool solved_ = false, can_improve_ = true, problem_set_ = false;
+  double goal_cost_ = 0, best_utopia_ = 0, path_cost_ = kInf, cost_ = kInf, r_rewire_ = 0;
+  std::vector<int> solution_;  // child ids root->goal
+  unsigned long long iterations = 0;
+
+  Solver(int k, int dim, World* w, const double* lb, const double* ub, const double* start, const double* goal,
+         double max_distance, double min_distance, double rewire_factor, double utopia_tolerance, bool use_kdtree,
+         bool extend)
+    : kind(k), pool(dim), world(w), min_distance_(min_distance), max_distance_(max_distance),
+      rewire_factor_(rewire_factor), use_kdtree_(use_kdtree), extend_(extend)
+  {
+    // tree_solver.cpp:34-53 config
+    utopia_tolerance_ = utopia_tolerance;
+    if (utopia_tolerance_ <= 0.0)
+      utopia_tolerance_ = 0.0;
+    utopia_tolerance_ += 1.0;
+    sampler_.init(dim, lb, ub, start, goal);
+    // addStart (rrt.cpp:58-78)
+    int s = pool.add(start);
+    start_tree_.reset(new Tree(&pool, s, max_distance_, world, min_distance_, use_kdtree_));
+    // addGoal (rrt.cpp:34-56) -> setProblem (tree_solver.cpp:55-105)
+    goal_node_ = pool.add(goal);
+    setProblem();
+  }
+  double solutionCost() { return start_tree_->pathCost(solution_); }  // Path::cost() re-sums stored connection costs
+  void makeSolution()
+  {
+    solution_ = start_tree_->getConnectionToNode(goal_node_);
+    // Path keeps the Connection objects alive: their costs never change afterwards, cache them
+    sol_costs_.clear();
+    for (int id : solution_)
+      sol_costs_.push_back(start_tree_->pcost[id]);
+  }
+  std::vector<double> sol_costs_;
+  double cachedSolutionCost()
+  {
+    double c = 0;
+    for (double v : sol_costs_)
+      c += v;
+    return c;
+  }
+  void setProblem()
+  {
+    const int d = pool.dim;
+    can_improve_ = true;
+    goal_cost_ = 0.0;  // NullGoalCostFunction
+    best_utopia_ = goal_cost_ + dist(pool.conf(start_tree_->root_), pool.conf(goal_node_), d);
+    problem_set_ = true;
+    int new_node = -1;
+    if (start_tree_->connectToNode(goal_node_, new_node))
+    {
+      makeSolution();
+      path_cost_ = cachedSolutionCost();
+      sampler_.setCost(path_cost_);
+      solved_ = true;
+    }
+    else
+      path_cost_ = kInf;
+    cost_ = path_cost_ + goal_cost_;
+  }
+  void updateRewireRadius()  // rrt_star.cpp:278-286
+  {
+    double dimension = (double)pool.dim;
+    double r_rrt = rewire_factor_ * std::pow(2.0 * (1.0 + 1.0 / dimension), 1.0 / dimension) *
+                   std::pow(sampler_.specific_volume_, 1.0 / dimension);
+    double cardDbl = start_tree_->nodes_->size_ + 1.0;
+    r_rewire_ = (r_rrt * std::pow(std::log(cardDbl) / cardDbl, 1.0 / dimension));
+  }
+  void connectGoal(int new_node)
+  {
+    const int d = pool.dim;
+    start_tree_->setParent(goal_node_, new_node, dist(pool.conf(new_node), pool.conf(goal_node_), d));
+    makeSolution();
+    start_tree_->nodes_->insert(goal_node_);  // addNode(goal) with check_if_present: not present yet
+    path_cost_ = cachedSolutionCost();
+    cost_ = path_cost_ + goal_cost_;
+    sampler_.setCost(path_cost_);
+    solved_ = true;
+  }
+  // RRTStar::update(configuration, solution)  rrt_star.cpp:89-163
+  bool updateRRTStar(const double* q)
+  {
+    const int d = pool.dim;
+    if (!problem_set_)
+      return false;
+    if (cost_ <= utopia_tolerance_ * best_utopia_)
+    {
+      can_improve_ = false;
+      return true;
+    }
+    updateRewireRadius();
+    if (!solved_)
+    {
+      int new_node = -1;
+      if (start_tree_->rewire(q, r_rewire_, new_node))
+      {
+        if (dist(pool.conf(new_node), pool.conf(goal_node_), d) < max_distance_)
+        {
+          if (start_tree_->checkConnection(pool.conf(new_node), pool.conf(goal_node_)))
+          {
+            connectGoal(new_node);
+            return true;
+          }
+        }
+      }
+      return false;
+    }
+    else
+    {
+      int nn = -1;
+      bool improved = start_tree_->rewire(q, r_rewire_, nn);
+      if (improved)
+      {
+        if (start_tree_->costToNode(goal_node_) >= (cachedSolutionCost() - 1e-8))
+          return false;
+        makeSolution();
+        path_cost_ = cachedSolutionCost();
+        cost_ = path_cost_ + goal_cost_;
+        sampler_.setCost(path_cost_);
+      }
+      return improved;
+    }
+  }
+  // RRT::update(configuration, solution)  rrt.cpp:116-157
+  bool updateRRT(const double* q)
+  {
+    const int d = pool.dim;
+    if (solved_)
+    {
+      can_improve_ = false;
+      return true;
+    }
+    int new_node = -1;
+    bool added = extend_ ? start_tree_->extend(q, new_node) : start_tree_->connect(q, new_node);
+    if (added)
+    {
+      if (dist(pool.conf(new_node), pool.conf(goal_node_), d) <= max_distance_)
+      {
+        if (start_tree_->checkConnection(pool.conf(new_node), pool.conf(goal_node_)))
+        {
+          connectGoal(new_node);
+          can_improve_ = false;
+          return true;
+        }
+      }
+    }
+    return false;
+  }
+  bool update(const double* q)
+  {
+    iterations++;
+    return kind == RRTSTAR ? updateRRTStar(q) : updateRRT(q);
+  }
+};
+
+}  // namespace orc
+
+// ============================================================================
+//  C interface (ctypes)
+// ============================================================================
+using namespace orc;
+
+struct OrcNN
+{
+  NodePool pool;
+  std::unique_ptr<NearestNeighbors> nn;
+  OrcNN(int kind, int dim) : pool(dim)
+  {
+    if (kind == 1)
+      nn.reset(new KdTreeNN(&pool));
+    else
+      nn.reset(new VectorNN(&pool));
+  }
+};
+
+static int copy_map(const NearMap& m, int* ids, double* dists, int cap)
+{
+  int n = 0;
+  for (const auto& p : m)
+  {
+    if (n < cap)
+    {
+      if (ids) ids[n] = p.second;
+      if (dists) dists[n] = p.first;
+    }
+    n++;
+  }
+  return n;
+}
+
+extern "C" {
+
+void* orc_nn_new(int kind, int dim) { return new OrcNN(kind, dim); }
+void orc_nn_free(void* h) { delete (OrcNN*)h; }
+int orc_nn_insert(void* h, const double* q)
+{
+  OrcNN* o = (OrcNN*)h;
+  int id = o->pool.add(q);
+  o->nn->insert(id);
+  return id;
+}
+void orc_nn_insert_many(void* h, const double* q, int n)
+{
+  OrcNN* o = (OrcNN*)h;
+  for (int i = 0; i < n; i++)
+    o->nn->insert(o->pool.add(q + (size_t)i * o->pool.dim));
+}
+void orc_nn_reinsert(void* h, int id) { ((OrcNN*)h)->nn->insert(id); }
+int orc_nn_delete(void* h, int id) { return ((OrcNN*)h)->nn->deleteNode(id) ? 1 : 0; }
+int orc_nn_restore(void* h, int id) { return ((OrcNN*)h)->nn->restoreNode(id) ? 1 : 0; }
+int orc_nn_find(void* h, int id) { return ((OrcNN*)h)->nn->findNode(id) ? 1 : 0; }
+int orc_nn_clear(void* h) { return ((OrcNN*)h)->nn->clear() ? 1 : 0; }
+unsigned int orc_nn_size(void* h) { return ((OrcNN*)h)->nn->size_; }
+unsigned int orc_nn_deleted(void* h) { return ((OrcNN*)h)->nn->deleted_nodes_; }
+void orc_nn_set_deleted_threshold(void* h, unsigned int t)
+{
+  KdTreeNN* k = dynamic_cast<KdTreeNN*>(((OrcNN*)h)->nn.get());
+  if (k && t > 1)
+    k->deleted_nodes_threshold_ = t;
+}
+int orc_nn_get_nodes(void* h, int* ids, int cap)
+{
+  std::vector<int> v = ((OrcNN*)h)->nn->getNodes();
+  for (int i = 0; i < (int)v.size() && i < cap; i++)
+    ids[i] = v[i];
+  return (int)v.size();
+}
+// nq queries; id = -1 and dist = +inf on an empty structure (kdtree.cpp:356-358)
+void orc_nn_nearest(void* h, const double* q, int nq, int* ids, double* dists)
+{
+  OrcNN* o = (OrcNN*)h;
+  for (int i = 0; i < nq; i++)
+  {
+    int best = -1;
+    double bd = kInf;
+    o->nn->nearestNeighbor(q + (size_t)i * o->pool.dim, best, bd);
+    ids[i] = best;
+    dists[i] = bd;
+  }
+}
+// each query writes up to cap entries at ids[i*cap..]; counts[i] = full hit count
+void orc_nn_near(void* h, const double* q, int nq, const double* radius, int cap, int* ids, double* dists,
+                 int* counts)
+{
+  OrcNN* o = (OrcNN*)h;
+  for (int i = 0; i < nq; i++)
+  {
+    NearMap m = o->nn->near(q + (size_t)i * o->pool.dim, radius[i]);
+    counts[i] = copy_map(m, ids + (size_t)i * cap, dists + (size_t)i * cap, cap);
+  }
+}
+void orc_nn_knn(void* h, const double* q, int nq, unsigned long long k, int cap, int* ids, double* dists,
+                int* counts)
+{
+  OrcNN* o = (OrcNN*)h;
+  for (int i = 0; i < nq; i++)
+  {
+    NearMap m = o->nn->kNearestNeighbors(q + (size_t)i * o->pool.dim, (size_t)k);
+    counts[i] = copy_map(m, ids + (size_t)i * cap, dists + (size_t)i * cap, cap);
+  }
+}
+
+// ---- worlds -----------------------------------------------------------------
+void* orc_world_cube(int dim, double thr)
+{
+  World* w = new World();
+  w->kind = GC_WORLD_CUBE;
+  w->dim = dim;
+  w->cube_thr = thr;
+  return w;
+}
+void* orc_world_boxes(int dim, int n, const double* lo, const double* hi)
+{
+  World* w = new World();
+  w->kind = GC_WORLD_BOXES;
+  w->dim = dim;
+  w->nobj = n;
+  w->lo.assign(lo, lo + (size_t)n * dim);
+  w->hi.assign(hi, hi + (size_t)n * dim);
+  return w;
+}
+void* orc_world_cspheres(int dim, int n, const float* centers, const float* radii)
+{
+  World* w = new World();
+  w->kind = GC_WORLD_CSPHERES;
+  w->dim = dim;
+  w->nobj = n;
+  w->sc.assign(centers, centers + (size_t)n * dim);
+  w->sr2.resize(n);
+  for (int i = 0; i < n; i++)
+    w->sr2[i] = radii[i] * radii[i];
+  return w;
+}
+void* orc_world_sphere_arm(int njoints, const float* base_tf, const float* joint_tf, int nrs, const int* rs_link,
+                           const float* rs_local, int nobs, const float* obs)
+{
+  World* w = new World();
+  w->kind = GC_WORLD_SPHERE_ARM;
+  w->dim = njoints;
+  w->njoints = njoints;
+  w->nrs = nrs;
+  w->nobs = nobs;
+  w->base_tf.assign(base_tf, base_tf + 12);
+  w->joint_tf.assign(joint_tf, joint_tf + (size_t)12 * njoints);
+  w->rs_link.assign(rs_link, rs_link + nrs);
+  w->rs_local.assign(rs_local, rs_local + (size_t)4 * nrs);
+  w->obs.assign(obs, obs + (size_t)4 * nobs);
+  return w;
+}
+void orc_world_free(void* w) { delete (World*)w; }
+unsigned long long orc_world_pair_tests(void* w) { return ((World*)w)->pair_tests; }
+unsigned long long orc_world_state_checks(void* w) { return ((World*)w)->state_checks; }
+void orc_world_reset_counters(void* w)
+{
+  ((World*)w)->pair_tests = 0;
+  ((World*)w)->state_checks = 0;
+}
+
+void orc_check_states(void* wh, const double* q, int n, unsigned char* ok)
+{
+  World* w = (World*)wh;
+  for (int i = 0; i < n; i++)
+    ok[i] = world_check(*w, q + (size_t)i * w->dim) ? 1 : 0;
+}
+// mode BISECT / LINEAR; first_bad and last_conf ([n][dim]) only written in LINEAR mode (may be NULL otherwise)
+void orc_check_edges(void* wh, const double* c1, const double* c2, int n, double min_distance, int mode,
+                     unsigned char* ok, long long* first_bad, double* last_conf)
+{
+  World* w = (World*)wh;
+  const int d = w->dim;
+  for (int i = 0; i < n; i++)
+  {
+    const double* a = c1 + (size_t)i * d;
+    const double* b = c2 + (size_t)i * d;
+    if (mode == GC_EDGE_LINEAR)
+    {
+      double tmp[GC_MAX_DIM];
+      double* conf = last_conf ? last_conf + (size_t)i * d : tmp;
+      long long fb = -1;
+      ok[i] = checkConnectionLinear(*w, a, b, min_distance, conf, &fb) ? 1 : 0;
+      if (first_bad)
+        first_bad[i] = fb;
+    }
+    else
+      ok[i] = checkConnectionBisect(*w, a, b, min_distance) ? 1 : 0;
+  }
+}
+// result[i]: 1 free, 0 collision, 255 = the reference throws invalid_argument
+void orc_check_from_conf(void* wh, const double* parent, const double* child, const double* conf, int n,
+                         double min_distance, unsigned char* result)
+{
+  World* w = (World*)wh;
+  const int d = w->dim;
+  for (int i = 0; i < n; i++)
+  {
+    int r = checkConnFromConf(*w, parent + (size_t)i * d, child + (size_t)i * d, conf + (size_t)i * d, min_distance);
+    result[i] = r < 0 ? 255 : (unsigned char)r;
+  }
+}
+
+// ---- solvers ------------------------------------------------------------------
+void* orc_solver_new(int kind, int dim, void* world, const double* lb, const double* ub, const double* start,
+                     const double* goal, double max_distance, double min_distance, double rewire_factor,
+                     double utopia_tolerance, int use_kdtree, int extend)
+{
+  return new Solver(kind, dim, (World*)world, lb, ub, start, goal, max_distance, min_distance, rewire_factor,
+                    utopia_tolerance, use_kdtree != 0, extend != 0);
+}
+void orc_solver_free(void* s) { delete (Solver*)s; }
+// feeds n injected samples; stops early when the solver reports it cannot improve; returns samples consumed
+int orc_solver_run(void* sh, const double* samples, int n)
+{
+  Solver* s = (Solver*)sh;
+  int i = 0;
+  for (; i < n; i++)
+  {
+    bool r = s->update(samples + (size_t)i * s->pool.dim);
+    if (r && !s->can_improve_)
+    {
+      i++;
+      break;
+    }
+  }
+  return i;
+}
+int orc_solver_update(void* sh, const double* q) { return ((Solver*)sh)->update(q) ? 1 : 0; }
+int orc_solver_solved(void* sh) { return ((Solver*)sh)->solved_ ? 1 : 0; }
+int orc_solver_can_improve(void* sh) { return ((Solver*)sh)->can_improve_ ? 1 : 0; }
+double orc_solver_cost(void* sh) { return ((Solver*)sh)->cost_; }
+double orc_solver_radius(void* sh) { return ((Solver*)sh)->r_rewire_; }
+double orc_solver_specific_volume(void* sh) { return ((Solver*)sh)->sampler_.specific_volume_; }
+int orc_solver_num_nodes(void* sh) { return ((Solver*)sh)->pool.size(); }
+int orc_solver_tree_size(void* sh) { return (int)((Solver*)sh)->start_tree_->nodes_->size_; }
+int orc_solver_goal_id(void* sh) { return ((Solver*)sh)->goal_node_; }
+// parents[n], pcost[n], conf[n*dim] for all created nodes (ids = creation order)
+void orc_solver_dump(void* sh, int* parents, double* pcost, double* conf)
+{
+  Solver* s = (Solver*)sh;
+  int n = s->pool.size();
+  s->start_tree_->ensure(n - 1);
+  for (int i = 0; i < n; i++)
+  {
+    parents[i] = s->start_tree_->parent[i];
+    pcost[i] = s->start_tree_->pcost[i];
+  }
+  std::memcpy(conf, s->pool.q.data(), sizeof(double) * s->pool.q.size());
+}
+int orc_solver_solution(void* sh, int* ids, int cap)
+{
+  Solver* s = (Solver*)sh;
+  if (!s->solved_)
+    return 0;
+  int n = 0;
+  if (cap > 0)
+    ids[n] = s->start_tree_->root_;
+  n++;
+  for (int id : s->solution_)
+  {
+    if (n < cap)
+      ids[n] = id;
+    n++;
+  }
+  return n;
+}
+// counters: nn1, near, knn, edges, near_hits, state_checks, pair_tests
+void orc_solver_counters(void* sh, unsigned long long* out)
+{
+  Solver* s = (Solver*)sh;
+  out[0] = s->start_tree_->cnt.nn1;
+  out[1] = s->start_tree_->cnt.near;
+  out[2] = s->start_tree_->cnt.knn;
+  out[3] = s->start_tree_->cnt.edges;
+  out[4] = s->start_tree_->cnt.near_hits;
+  out[5] = s->world->state_checks;
+  out[6] = s->world->pair_tests;
+}
+
+}  // extern "C"

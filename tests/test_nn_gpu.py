@@ -1,0 +1,261 @@
+"""GPU parity: CUDA nearest / radius-near / k-nearest vs the oracle's Vector and KdTree restatements.
+
+Reference semantics under test: src/graph_core/datastructure/vector.cpp:55-96,
+src/graph_core/datastructure/kdtree.cpp:127-229.  Indices must match bit for bit; distances are
+compared exactly (the device recomputes them in fp64 with the oracle's operation order), which is
+stricter than the 1e-5 relative tolerance BASELINE.json asks for.
+"""
+import numpy as np
+import pytest
+
+from graph_core_b200 import worlds as W
+
+pytestmark = pytest.mark.gpu
+
+NO = 0xFFFFFFFF
+
+
+def _mk(gc, orc, pts, kind="vector", cap=None):
+    d = pts.shape[1]
+    st = gc.NodeStore(d, cap or max(len(pts), 1))
+    if len(pts):
+        first = st.append(pts)
+        assert first == 0
+    o = orc.OracleNN(kind, d)
+    if len(pts):
+        o.insert(pts)
+    return st, o
+
+
+@pytest.mark.parametrize("dim,n", [(2, 1), (2, 777), (3, 4096), (6, 5000), (7, 10000), (12, 20000), (14, 3001)])
+def test_nearest_matches_vector_and_kdtree(gc, orc, dim, n):
+    pts = W.c4_nodes(n, dim, seed=11 + dim)
+    qs = W.c4_queries(67, dim, seed=12 + dim)
+    st, ov = _mk(gc, orc, pts)
+    ok = orc.OracleNN("kdtree", dim)
+    ok.insert(pts)
+    idx, dist = st.nearest(qs)
+    iv, dv = ov.nearest(qs)
+    ik, dk = ok.nearest(qs)
+    assert np.array_equal(idx.astype(np.int64), iv.astype(np.int64))
+    assert np.array_equal(dist, dv)
+    assert np.array_equal(idx.astype(np.int64), ik.astype(np.int64))
+    assert np.array_equal(dist, dk)
+
+
+def test_nearest_empty_and_single(gc, orc):
+    st = gc.NodeStore(3, 64)
+    idx, dist = st.nearest(np.zeros((2, 3)))
+    assert (idx == NO).all() and np.isinf(dist).all()  # kdtree.cpp:356-358
+    st.append(np.array([[1.0, 2.0, 3.0]]))
+    idx, dist = st.nearest(np.array([[1.0, 2.0, 3.0], [0.0, 0.0, 0.0]]))
+    assert idx.tolist() == [0, 0]
+    assert dist[0] == 0.0 and dist[1] == np.sqrt(1.0 + 4.0 + 9.0)
+
+
+def test_nearest_ties_take_lowest_slot(gc, orc):
+    # exact duplicates and mirrored points: strict '<' in scan order => lowest slot (vector.cpp:55-67)
+    base = W.c4_nodes(3000, 5, seed=5)
+    pts = np.vstack([base, base[::-1], base])  # every configuration three times
+    qs = np.vstack([base[:40], W.c4_queries(40, 5, seed=6)])
+    st, ov = _mk(gc, orc, pts)
+    idx, dist = st.nearest(qs)
+    iv, dv = ov.nearest(qs)
+    assert np.array_equal(idx.astype(np.int64), iv.astype(np.int64))
+    assert np.array_equal(dist, dv)
+    # symmetric pair around the query: both at the same distance
+    pts2 = np.array([[1.0, 0.0], [-1.0, 0.0], [0.0, 1.0], [0.0, -1.0]])
+    st2, ov2 = _mk(gc, orc, pts2)
+    idx2, _ = st2.nearest(np.zeros((1, 2)))
+    assert idx2[0] == 0
+
+
+def test_near_fp32_ties_resolved_in_fp64(gc, orc):
+    # nodes that differ by far less than fp32 resolution: the fp32 scan cannot order them,
+    # the fp64 decision must
+    rng = np.random.default_rng(3)
+    centre = rng.uniform(-3, 3, size=(1, 7))
+    pts = centre + rng.uniform(-1e-9, 1e-9, size=(500, 7))
+    pts = np.vstack([W.c4_nodes(2000, 7, seed=9), pts])
+    qs = centre + rng.uniform(-1e-9, 1e-9, size=(16, 7))
+    st, ov = _mk(gc, orc, pts)
+    idx, dist = st.nearest(qs)
+    iv, dv = ov.nearest(qs)
+    assert np.array_equal(idx.astype(np.int64), iv.astype(np.int64))
+    assert np.array_equal(dist, dv)
+    r = np.full(16, 1.0e-9)
+    gi, gd, gcnt = st.near(qs, r, cap=1024)
+    oi, od, ocnt = ov.near(qs, r, cap=1024)
+    assert np.array_equal(gcnt.astype(np.int64), ocnt.astype(np.int64))
+    for i in range(16):
+        assert np.array_equal(gi[i, :gcnt[i]].astype(np.int64), oi[i, :ocnt[i]].astype(np.int64))
+        assert np.array_equal(gd[i, :gcnt[i]], od[i, :ocnt[i]])
+
+
+@pytest.mark.parametrize("dim,n,hits", [(2, 2000, 30), (7, 10000, 40), (12, 30000, 64), (3, 5, 3)])
+def test_near_matches_oracle(gc, orc, dim, n, hits):
+    pts = W.c4_nodes(n, dim, seed=21)
+    qs = W.c4_queries(33, dim, seed=22)
+    st, ov = _mk(gc, orc, pts)
+    ok = orc.OracleNN("kdtree", dim)
+    ok.insert(pts)
+    radius = W.c4_radius(hits, n, dim)
+    gi, gd, gcnt = st.near(qs, radius, cap=2048)
+    oi, od, ocnt = ov.near(qs, radius, cap=2048)
+    ki, kd, kcnt = ok.near(qs, radius, cap=2048)
+    assert np.array_equal(gcnt.astype(np.int64), ocnt.astype(np.int64))
+    assert gcnt.sum() > 0
+    for i in range(len(qs)):
+        c = int(gcnt[i])
+        assert np.array_equal(gi[i, :c].astype(np.int64), oi[i, :c].astype(np.int64))
+        assert np.array_equal(gd[i, :c], od[i, :c])
+        # KdTree returns the same set; equal keys may differ in order only on exact ties
+        assert np.array_equal(np.sort(gi[i, :c].astype(np.int64)), np.sort(ki[i, :c].astype(np.int64)))
+        assert np.array_equal(gd[i, :c], kd[i, :c])
+
+
+def test_near_strict_radius_and_self_hit(gc, orc):
+    # dist < radius is strict (vector.cpp:75); a query that is a stored node finds itself at 0
+    pts = np.array([[0.0, 0.0], [3.0, 4.0], [6.0, 8.0]])
+    st, ov = _mk(gc, orc, pts)
+    gi, gd, gcnt = st.near(np.array([[0.0, 0.0]]), 5.0, cap=8)
+    assert gcnt[0] == 1 and gi[0, 0] == 0 and gd[0, 0] == 0.0
+    gi, gd, gcnt = st.near(np.array([[0.0, 0.0]]), np.nextafter(5.0, 6.0), cap=8)
+    assert gcnt[0] == 2 and gi[0, :2].tolist() == [0, 1]
+    gi, gd, gcnt = st.near(np.array([[0.0, 0.0]]), 0.0, cap=8)
+    assert gcnt[0] == 0
+
+
+def test_near_truncation_reports_full_count(gc, orc):
+    pts = W.c4_nodes(4000, 3, seed=31)
+    st, ov = _mk(gc, orc, pts)
+    q = np.zeros((1, 3))
+    gi, gd, gcnt = st.near(q, 100.0, cap=16, grow=False)
+    assert gcnt[0] == 4000
+    gi, gd, gcnt = st.near(q, 100.0, cap=16, grow=True)  # wrapper retries with a larger cap
+    oi, od, ocnt = ov.near(q, 100.0, cap=4096)
+    assert gcnt[0] == 4000 and np.array_equal(gi[0, :4000].astype(np.int64), oi[0, :4000].astype(np.int64))
+
+
+@pytest.mark.parametrize("dim,n,k", [(2, 100, 1), (7, 9000, 17), (7, 9000, 8058), (7, 500, 100000), (12, 16384, 64)])
+def test_knn_matches_vector(gc, orc, dim, n, k):
+    # includes Tree::nearK's huge k: k >= N returns everything, sorted
+    pts = W.c4_nodes(n, dim, seed=41)
+    qs = W.c4_queries(9, dim, seed=42)
+    st, ov = _mk(gc, orc, pts)
+    cap = min(k, n)
+    gi, gd, gcnt = st.knn(qs, k, cap=cap)
+    oi, od, ocnt = ov.knn(qs, k, cap=cap)
+    assert np.array_equal(gcnt.astype(np.int64), ocnt.astype(np.int64))
+    assert np.array_equal(gi.astype(np.int64), oi.astype(np.int64))
+    assert np.array_equal(gd, od)
+
+
+def test_tombstone_restore_clear(gc, orc):
+    pts = W.c4_nodes(3000, 6, seed=51)
+    qs = W.c4_queries(25, 6, seed=52)
+    st, ov = _mk(gc, orc, pts)
+    ok = orc.OracleNN("kdtree", 6)
+    ok.insert(pts)
+    iv, _ = ov.nearest(qs)
+    dead = sorted(set(iv.tolist()))  # delete every current nearest neighbour
+    for s in dead:
+        assert st.tombstone(s) == 0
+        assert ok.delete(s)
+    assert st.tombstone(dead[0]) == 2  # GC_W_NOOP: already tombstoned
+    used, live = st.size()
+    assert used == 3000 and live == 3000 - len(dead) == ok.size()
+    idx, dist = st.nearest(qs)
+    ik, dk = ok.nearest(qs)  # KdTree lazy deletion (kdtree.cpp:130, 261-278)
+    assert np.array_equal(idx.astype(np.int64), ik.astype(np.int64)) and np.array_equal(dist, dk)
+    gi, gd, gcnt = st.near(qs, 2.5, cap=1024)
+    ki, kd, kcnt = ok.near(qs, 2.5, cap=1024)
+    assert np.array_equal(gcnt.astype(np.int64), kcnt.astype(np.int64))
+    gi, gd, gcnt = st.knn(qs, 3000, cap=3000)
+    assert (gcnt == live).all()
+    assert not np.isin(gi[:, :live], dead).any()
+    # restore one node: it becomes the nearest neighbour of its query again
+    st.restore(dead[0])
+    idx2, _ = st.nearest(qs)
+    assert dead[0] in idx2.tolist()
+    st.clear()
+    assert st.size() == (0, 0)
+    idx3, dist3 = st.nearest(qs)
+    assert (idx3 == NO).all() and np.isinf(dist3).all()
+    st.append(pts[:10])
+    idx4, _ = st.nearest(pts[:10])
+    assert idx4.tolist() == list(range(10))
+
+
+def test_incremental_append_matches_batch(gc, orc):
+    pts = W.c4_nodes(2500, 7, seed=61)
+    qs = W.c4_queries(20, 7, seed=62)
+    st = gc.NodeStore(7, 4096)
+    ov = orc.OracleNN("vector", 7)
+    pos = 0
+    for chunk in (1, 1, 30, 1000, 1, 1467):
+        first = st.append(pts[pos:pos + chunk])
+        assert first == pos
+        ov.insert(pts[pos:pos + chunk])
+        pos += chunk
+        idx, dist = st.nearest(qs)
+        iv, dv = ov.nearest(qs)
+        assert np.array_equal(idx.astype(np.int64), iv.astype(np.int64)) and np.array_equal(dist, dv)
+    assert np.array_equal(st.read(0, 2500), pts)
+    with pytest.raises(gc.GcError):
+        st.append(np.zeros((4096, 7)))  # capacity
+
+
+def test_segments_are_independent_trees(gc, orc):
+    dim, nseg = 7, 5
+    st = gc.NodeStore(dim, 3000, segments=nseg)
+    oracles = []
+    sizes = [1, 50, 1024, 1025, 2999]
+    for s in range(nseg):
+        pts = W.c4_nodes(sizes[s], dim, seed=70 + s)
+        st.append(pts, segment=s)
+        o = orc.OracleNN("vector", dim)
+        o.insert(pts)
+        oracles.append(o)
+    qs = W.c4_queries(40, dim, seed=79)
+    seg = np.arange(40, dtype=np.uint32) % nseg
+    idx, dist = st.nearest(qs, seg=seg)
+    gi, gd, gcnt = st.near(qs, 3.0, cap=4096, seg=seg)
+    ki, kdist, kcnt = st.knn(qs, 7, cap=7, seg=seg)
+    for i in range(40):
+        o = oracles[seg[i]]
+        iv, dv = o.nearest(qs[i])
+        assert idx[i] == iv[0] and dist[i] == dv[0]
+        oi, od, oc = o.near(qs[i], 3.0, cap=4096)
+        assert gcnt[i] == oc[0]
+        assert np.array_equal(gi[i, :oc[0]].astype(np.int64), oi[0, :oc[0]].astype(np.int64))
+        assert np.array_equal(gd[i, :oc[0]], od[0, :oc[0]])
+        oi, od, oc = o.knn(qs[i], 7, cap=7)
+        assert kcnt[i] == oc[0]
+        assert np.array_equal(ki[i, :oc[0]].astype(np.int64), oi[0, :oc[0]].astype(np.int64))
+    # append_multi: one row per tree, as the lock-step planners do
+    rows = W.c4_queries(nseg, dim, seed=80)
+    slots = st.append_multi(np.arange(nseg, dtype=np.uint32), rows)
+    assert slots.tolist() == sizes
+    idx2, dist2 = st.nearest(rows, seg=np.arange(nseg, dtype=np.uint32))
+    assert idx2.tolist() == sizes and (dist2 == 0.0).all()
+
+
+def test_large_tree_c4_shape(gc, orc):
+    # BASELINE config 4 at reduced N (the full 2^20 case runs in bench.py): 12-DoF, many tiles/chunks
+    n, dim = 200_000, 12
+    pts = W.c4_nodes(n, dim)
+    qs = W.c4_queries(64, dim)
+    st, ov = _mk(gc, orc, pts)
+    idx, dist = st.nearest(qs)
+    iv, dv = ov.nearest(qs)
+    assert np.array_equal(idx.astype(np.int64), iv.astype(np.int64)) and np.array_equal(dist, dv)
+    radius = W.c4_radius(16, n, dim)
+    gi, gd, gcnt = st.near(qs, radius, cap=1024)
+    oi, od, ocnt = ov.near(qs, radius, cap=1024)
+    assert np.array_equal(gcnt.astype(np.int64), ocnt.astype(np.int64))
+    for i in range(64):
+        assert np.array_equal(gi[i, :gcnt[i]].astype(np.int64), oi[i, :ocnt[i]].astype(np.int64))
+    # one query at a time (the HBM-bound regime) gives the same answers as the tiled batch
+    idx1, dist1 = st.nearest(qs[:1])
+    assert idx1[0] == idx[0] and dist1[0] == dist[0]
