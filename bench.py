@@ -1,0 +1,415 @@
+#!/usr/bin/env python
+"""bench.py -- RRT* samples/s on BASELINE.json config 3 (7-DoF sphere-model arm vs 1k-sphere cloud).
+
+One "step" = one lock-step RRT* iteration over P independent planning problems (P samples), i.e. for
+every problem: nearest neighbour + steer + extension edge check + radius-near + the rewiring edge
+checks + append (RRTStar::update, src/graph_core/solvers/rrt_star.cpp:89-163).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--problems P] [--impl ours|reference]
+
+  value  : samples/s with the sample blocks resident in HBM (written by the device Philox sampler)
+  e2e    : samples/s through the host-facing call with HOST sample buffers (H2D of every step's samples,
+           D2H of every step's results inside the timed region)
+  roofline: the dominant kernel of the step, the arm edge-check kernel (FP32 pipe bound): executed
+           sphere-pair tests x 10 flop / device time of the check kernels (CUDA events on the launching
+           stream, inside the timed region) against the FFMA peak measured in the same run
+  cpu_baseline / --impl reference: the CPU restatement of the reference (oracle, the reference's
+           -Ofast flags) running the same problems and sample streams on the host cores.
+
+Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+METRIC = "rrtstar_samples_per_sec"
+UNIT = "samples/s"
+FLOP_PER_PAIR = 10.0  # 3 sub, 1 mul + 2 fma (=5), radius add, square, compare
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--problems", type=int, default=512, help="independent planning problems per GPU")
+    ap.add_argument("--threads", type=int, default=0, help="host replay threads (0 = all cores)")
+    ap.add_argument("--skip-nn", action="store_true", help="skip the kNN roofline side measurement")
+    ap.add_argument("--cpu-problems", type=int, default=0, help="problems of the CPU baseline sample (0 = auto)")
+    return ap.parse_args()
+
+
+def dist_env():
+    return int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+
+
+# ---- clocks ---------------------------------------------------------------------------------------
+class ClockSampler:
+    FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+              "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.proc = None
+        self.lines = []
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), "--query-gpu=" + self.FIELDS,
+                                          "--format=csv,noheader,nounits", "-lms", "200"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._pump, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append((time.time(), line.strip()))
+
+    def window(self, t0, t1):
+        sm, smax, reasons = [], [], set()
+        for t, line in self.lines:
+            if t < t0 - 0.2 or t > t1 + 0.2:
+                continue
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                smax.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(smax)), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+
+
+# ---- workload -------------------------------------------------------------------------------------
+def make_samples(sc, problems, iters, seed0=30200):
+    from graph_core_b200 import worlds as W
+    # sample of (iteration i, problem p): Philox key seed0, counter i*problems + p  -> [iters, problems, dim]
+    return W.uniform_samples(sc.lb, sc.ub, seed0, 0, iters * problems).reshape(iters, problems, sc.dim)
+
+
+def cuda_checker(world_cache={}):
+    """State checker backed by the CUDA world (product path) for problem selection."""
+    import graph_core_b200 as g
+
+    def chk(params, q):
+        key = id(params["obs"])
+        if key not in world_cache:
+            world_cache[key] = g.CollisionWorld.sphere_arm(params["base_tf"], params["joint_tf"], params["rs_link"],
+                                                           params["rs_local"], params["obs"])
+        return world_cache[key].check(q).astype(bool)
+
+    return chk
+
+
+def cpu_reference_run(sc, starts, goals, samples, warmup, steps, threads):
+    """Oracle RRT* (reference flags) on len(starts) problems, `threads` host threads; returns samples/s."""
+    sys.path.insert(0, str(ROOT / "oracle"))
+    import oracle_py as orc
+    orc.build()
+    n = len(starts)
+    solvers = []
+    worlds_ = []
+    for p in range(n):
+        w = orc.OracleWorld.from_scenario(sc, fast=True)  # one world per thread: counters are not shared
+        worlds_.append(w)
+        solvers.append(orc.OracleSolver(orc.OracleSolver.RRTSTAR, sc, w, start=starts[p], goal=goals[p],
+                                        use_kdtree=True, fast=True))
+    nthreads = max(1, min(threads, n))
+    done = [0] * n
+
+    def work(tid, lo, hi):
+        for p in range(tid, n, nthreads):
+            done[p] += solvers[p].run(samples[lo:hi, p, :])
+
+    def phase(lo, hi):
+        ts = [threading.Thread(target=work, args=(t, lo, hi)) for t in range(nthreads)]
+        t0 = time.perf_counter()
+        for t in ts:
+            t.start()
+        for t in ts:
+            t.join()
+        return time.perf_counter() - t0
+
+    phase(0, warmup)
+    before = sum(done)
+    dt = phase(warmup, warmup + steps)
+    consumed = sum(done) - before
+    return consumed / dt, dt, nthreads, solvers
+
+
+def main():
+    args = parse_args()
+    rank, local_rank, world_size = dist_env()
+    if world_size > 1 and args.gpus != world_size:
+        args.gpus = world_size
+    W_, K = args.warmup, args.steps
+    from graph_core_b200 import worlds as W
+
+    ncores = os.cpu_count() or 1
+
+    # ------------------------------------------------------------------ reference arm (CPU only)
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        sys.path.insert(0, str(ROOT / "oracle"))
+        import oracle_py as orc
+        orc.build()
+        sc = W.scenario_c3(1000, orc.arm_checker(fast=True))
+        nprob = args.cpu_problems or min(args.problems, max(ncores, 1) * 2)
+        pairs = W.c3_problems(orc.arm_checker(fast=True), sc.params, nprob)
+        starts = np.array([s for s, _ in pairs])
+        goals = np.array([g for _, g in pairs])
+        samples = make_samples(sc, nprob, W_ + K)
+        rate, dt, nthreads, _ = cpu_reference_run(sc, starts, goals, samples, W_, K, ncores)
+        line = {
+            "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": K,
+            "warmup": W_, "ms_per_step": dt / K * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64 planner / f32 collision geometry", "data": "synthetic",
+            "config": {"workload": "C3: 7-DoF sphere-arm RRT* vs 1000-sphere cloud, %d problems x %d iterations" %
+                                   (nprob, K), "problems": nprob, "max_distance": sc.max_distance,
+                       "min_distance": sc.min_distance, "sampler": "uniform (Philox, injected)"},
+            "cpu_baseline": {"value": rate, "unit": UNIT, "cores": nthreads, "kind": "port",
+                             "sample": "%d problems x %d RRT* iterations, CPU restatement of KdTree + checkConnection "
+                                       "(-O3 -Ofast), one problem per thread" % (nprob, K)},
+            "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0,
+        }
+        print(json.dumps(line))
+        return 0
+
+    # ------------------------------------------------------------------ our arm (CUDA)
+    import torch
+
+    import graph_core_b200 as g
+    from graph_core_b200.planner import LockstepRRTStar
+
+    if not torch.cuda.is_available() or g.device_count() < 1:
+        raise RuntimeError("bench.py: no CUDA device; graph_core_b200 has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = local_rank
+    if world_size > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if world_size > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    P = args.problems
+    sc = W.scenario_c3(1000, cuda_checker())
+    # rank r plans problems [r*P, (r+1)*P) of the shared stream: independent queries, no data-path collective
+    pairs = W.c3_problems(cuda_checker(), sc.params, P * world_size)[rank * P:(rank + 1) * P]
+    starts = np.array([s for s, _ in pairs])
+    goals = np.array([gl for _, gl in pairs])
+    iters = W_ + K
+    samples = make_samples(sc, P, iters, seed0=30200 + rank)
+    h_samples = torch.from_numpy(samples).pin_memory()
+    d_samples = torch.empty((iters, P, sc.dim), dtype=torch.float64, device="cuda")
+    stream = torch.cuda.Stream()
+    # device-resident sample blocks written by the device Philox sampler, outside the timed region;
+    # they must be bit-identical to the host stream the e2e run and the CPU baseline consume
+    lb64 = np.ascontiguousarray(sc.lb, dtype=np.float64)
+    ub64 = np.ascontiguousarray(sc.ub, dtype=np.float64)
+    import ctypes as C
+    rc = g.capi.load().gc_sample_uniform_dev(dev, sc.dim, lb64.ctypes.data_as(C.POINTER(C.c_double)),
+                                             ub64.ctypes.data_as(C.POINTER(C.c_double)), 30200 + rank, 0, iters * P,
+                                             d_samples.data_ptr(), None)
+    assert rc == 0, g.capi.load().gc_last_error()
+    torch.cuda.synchronize()
+    assert torch.equal(d_samples.cpu(), h_samples), "device Philox stream differs from the host stream"
+
+    clocks = ClockSampler(dev)
+    fp32_peak, fp32_mhz = g.capi.measure_fp32_peak(dev)
+
+    def timed_run(device_samples: bool):
+        world = sc.make_world(dev)
+        world.set_stream(stream.cuda_stream)
+        lock = LockstepRRTStar(sc, world, starts, goals, capacity=iters + 64, device=dev, threads=args.threads)
+        lock.set_stream(stream.cuda_stream)
+        with torch.cuda.stream(stream):
+            for i in range(W_):
+                if device_samples:
+                    lock.step_device_samples(d_samples[i].data_ptr())
+                else:
+                    lock.step(h_samples[i].numpy())
+            world.enable_timing(True)
+            world.reset_counters()
+            st0 = lock.stats()
+            l0 = g.capi.launch_count()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            barrier()
+            t0 = time.time()
+            e0.record(stream)
+            consumed = 0
+            for i in range(W_, iters):
+                if device_samples:
+                    consumed += lock.step_device_samples(d_samples[i].data_ptr())
+                else:
+                    consumed += lock.step(h_samples[i].numpy())
+            e1.record(stream)
+            barrier()
+            t1 = time.time()
+        ms = e0.elapsed_time(e1)
+        if world_size > 1:
+            t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+            c = torch.tensor([consumed], dtype=torch.float64, device="cuda")
+            dist.all_reduce(c, op=dist.ReduceOp.SUM)
+            consumed_all = float(c.item())
+        else:
+            consumed_all = float(consumed)
+        st1 = lock.stats()
+        cnt = world.counters()
+        launches = g.capi.launch_count() - l0
+        return {"ms": ms, "consumed": consumed_all, "stats": {k: st1[k] - st0[k] for k in st1}, "world": cnt,
+                "launches": launches, "t0": t0, "t1": t1, "lock": lock, "wall_world": world}
+
+    e2e_run = timed_run(device_samples=False)
+    val_run = timed_run(device_samples=True)
+    value = val_run["consumed"] / (val_run["ms"] * 1e-3)
+    e2e_value = e2e_run["consumed"] / (e2e_run["ms"] * 1e-3)
+    clk = clocks.window(val_run["t0"], val_run["t1"])
+    clocks.stop()
+
+    # both runs consumed the same samples: they must have built the same trees
+    same = all(e2e_run["lock"].info(p) == val_run["lock"].info(p) for p in range(0, P, max(1, P // 16)))
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world_size, "steps": K, "warmup": W_,
+        "ms_per_step": val_run["ms"] / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64 planner / f32 collision geometry", "data": "synthetic",
+        "config": {
+            "workload": "C3: 7-DoF sphere-arm RRT* vs 1000-sphere cloud, %d lock-step problems per GPU x %d "
+                        "iterations" % (P, K),
+            "problems_per_gpu": P, "max_distance": sc.max_distance, "min_distance": sc.min_distance,
+            "sampler": "uniform (Philox, injected)", "host_threads": args.threads or ncores,
+            "l2_policy": "every step has new samples and larger trees; no artificial L2 flush between planner "
+                         "iterations (the kNN side measurement flushes L2 between launches)",
+            "parallelism": "independent problems per GPU, no data-path collective",
+        },
+        "clocks": {"sm_mhz": clk["sm_mhz"], "sm_max_mhz": clk["sm_max_mhz"], "reasons": clk["reasons"]},
+        "gpu_launches": int(val_run["launches"]),
+    }
+    st = e2e_run["stats"]
+    line["e2e"] = {"value": e2e_value, "unit": UNIT,
+                   "h2d_bytes_per_step": int(st.get("h2d_bytes", 0) / K), "d2h_bytes_per_step": int(st.get("d2h_bytes", 0) / K),
+                   "ms_per_step": e2e_run["ms"] / K, "same_trees_as_value_run": bool(same)}
+    wc = val_run["world"]
+    achieved = FLOP_PER_PAIR * wc["pair_tests"] / max(wc["kernel_ns"], 1) / 1e3  # TFLOP/s
+    line["roofline"] = {
+        "kernel": "arm_state_kernel (edge checks)", "bound": "fp32", "achieved": achieved, "peak": fp32_peak,
+        "unit": "TFLOP/s", "frac": achieved / fp32_peak if fp32_peak > 0 else None, "traffic": None,
+        "peak_source": "FFMA micro-benchmark in this run (implies %.0f MHz); MEASURED_PEAKS.json has no FP32 entry" % fp32_mhz,
+        "pair_tests_per_launch": wc["pair_tests"] / max(wc["launches"], 1),
+        "us_per_launch": wc["kernel_ns"] / max(wc["launches"], 1) / 1e3,
+        "kernel_share_of_step": wc["kernel_ns"] / 1e6 / val_run["ms"],
+    }
+    vs = val_run["stats"]
+    line["step_breakdown"] = {"extended_per_step": vs["extended"] / K, "device_edges_per_step": vs["edges_device"] / K,
+                              "edges_used_per_step": vs["edges_used"] / K, "edge_fallbacks": vs["edges_fallback"],
+                              "near_hits_per_extension": vs["near_hits"] / max(vs["extended"], 1),
+                              "abi_calls_per_step": vs["gpu_calls"] / K}
+
+    if rank == 0:
+        # ---- in-bench parity check: problem 0 against the oracle on the same samples ----------------
+        sys.path.insert(0, str(ROOT / "oracle"))
+        import oracle_py as orc
+        orc.build()
+        ow = orc.OracleWorld.from_scenario(sc)
+        o = orc.OracleSolver(orc.OracleSolver.RRTSTAR, sc, ow, start=starts[0], goal=goals[0])
+        o.run(samples[:, 0, :])
+        par, pc, conf = o.dump()
+        gpar, gpc, gconf = val_run["lock"].dump(0)
+        line["parity"] = {"problem0_tree_bit_exact": bool(np.array_equal(par, gpar) and np.array_equal(pc, gpc) and
+                                                          np.array_equal(conf, gconf)), "nodes": int(len(par))}
+        # ---- CPU baseline on a bounded sample of the same workload ---------------------------------
+        ncpu = args.cpu_problems or min(P, ncores * 2)
+        rate, dt, nthreads, _ = cpu_reference_run(sc, starts[:ncpu], goals[:ncpu], samples[:, :ncpu, :], W_, K, ncores)
+        line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": nthreads, "kind": "port",
+                                "sample": "%d of the %d problems x %d RRT* iterations (same samples), CPU restatement "
+                                          "of KdTree + checkConnection (-O3 -Ofast), one problem per thread, %.1f s" %
+                                          (ncpu, P, K, dt)}
+        # ---- kNN side measurement: BASELINE config 4 shape, HBM-bound regime --------------------------
+        if not args.skip_nn:
+            try:
+                line["roofline_nn"] = nn_roofline(g, torch, dev)
+            except Exception as ex:  # the headline line must still be printed
+                line["roofline_nn"] = {"error": str(ex)[:200]}
+        print(json.dumps(line))
+    if world_size > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def nn_roofline(g, torch, dev, n=1 << 20, dim=12):
+    """Nearest-neighbour scan over 2^20 12-DoF nodes, 8 queries per pass (one query group), L2 flushed."""
+    from graph_core_b200 import worlds as W
+    peaks = {}
+    try:
+        peaks = json.loads((ROOT / "MEASURED_PEAKS.json").read_text())
+    except Exception:
+        pass
+    hbm = float(peaks.get("hbm_gbs", 6650.0))
+    src = "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+    st = g.NodeStore(dim, n, device=dev)
+    st.append(W.c4_nodes(n, dim))
+    stream = torch.cuda.Stream()
+    st.set_stream(stream.cuda_stream)
+    out = {}
+    for nq in (8, 4096):
+        q = torch.from_numpy(W.c4_queries(nq, dim)).cuda()
+        idx = torch.empty(nq, dtype=torch.int32, device="cuda")
+        dd = torch.empty(nq, dtype=torch.float64, device="cuda")
+        lib = g.capi.load()
+        times = []
+        for it in range(8):
+            g.capi.flush_l2(dev)
+            with torch.cuda.stream(stream):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(stream)
+                rc = lib.gc_nn1_dev(st.handle, q.data_ptr(), None, nq, idx.data_ptr(), dd.data_ptr())
+                e1.record(stream)
+            torch.cuda.synchronize()
+            assert rc == 0
+            if it >= 3:
+                times.append(e0.elapsed_time(e1))
+        ms = float(np.mean(times))
+        passes = (nq + 7) // 8
+        alg_bytes = passes * 4.0 * dim * n + 8.0 * dim * nq + 12.0 * nq
+        out["nq%d" % nq] = {"ms": ms, "queries_per_s": nq / (ms * 1e-3), "GBps": alg_bytes / (ms * 1e-3) / 1e9,
+                            "pairs_per_s": nq * n / (ms * 1e-3)}
+    a = out["nq8"]
+    return {"kernel": "scan_kernel<12,nearest> + finalize", "bound": "hbm", "achieved": a["GBps"], "peak": hbm,
+            "unit": "GB/s", "frac": a["GBps"] / hbm, "traffic": None, "peak_source": src,
+            "workload": "2^20 nodes x 12-DoF, 8 queries per pass, L2 flushed between launches", "detail": out}
+
+
+if __name__ == "__main__":
+    sys.exit(main())

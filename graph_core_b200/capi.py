@@ -91,6 +91,14 @@ PROTOTYPES = {
                                   _c_u32_p, _c_double_p, _c_u32_p]),
     "gc_sample_uniform": (C.c_int, [C.c_int, C.c_int, _c_double_p, _c_double_p, C.c_uint64, C.c_uint64, C.c_uint32,
                                     _c_double_p]),
+    "gc_sample_uniform_dev": (C.c_int, [C.c_int, C.c_int, _c_double_p, _c_double_p, C.c_uint64, C.c_uint64, C.c_uint32,
+                                        C.c_void_p, C.c_void_p]),
+    "gc_extend_batch_dsamples": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, _c_u32_p, _c_u32_p, C.c_uint32,
+                                           C.c_double, C.c_double, C.c_double, _c_double_p, C.c_uint32, _c_u32_p,
+                                           _c_double_p, _c_double_p, _c_u8_p, _c_u32_p, _c_double_p, _c_u32_p]),
+    "gc_launch_count": (C.c_int, [_c_u64_p]),
+    "gc_measure_fp32_peak": (C.c_int, [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
+    "gc_flush_l2": (C.c_int, [C.c_int, C.c_size_t]),
 }
 
 _lib = None
@@ -416,6 +424,23 @@ def extend_batch(store: NodeStore, world: CollisionWorld, q, seg, max_distance, 
                              _ptr(ndist, _c_double_p), _ptr(ncount, _c_u32_p))
     _check(rc)
     return closest, dist, nxt, ok, nidx, ndist, ncount
+
+
+def launch_count() -> int:
+    n = C.c_uint64(0)
+    _check(load().gc_launch_count(C.byref(n)))
+    return n.value
+
+
+def measure_fp32_peak(device: int = 0):
+    """(TFLOP/s, implied SM MHz) of a dependent-chain FFMA micro-benchmark."""
+    tf, mhz = C.c_double(0), C.c_double(0)
+    _check(load().gc_measure_fp32_peak(device, C.byref(tf), C.byref(mhz)))
+    return tf.value, mhz.value
+
+
+def flush_l2(device: int = 0, nbytes: int = 512 << 20):
+    _check(load().gc_flush_l2(device, nbytes))
 
 
 def sample_uniform(lb, ub, seed: int, first_index: int, n: int, device: int = 0) -> np.ndarray:

@@ -1,4 +1,6 @@
 // common.cu -- error string, scratch buffers, device info for the C ABI (include/gcb200.h)
+#include <atomic>
+
 #include "gc_common.cuh"
 
 namespace gc
@@ -61,6 +63,43 @@ int num_sms(int device)
     return 148;
   return v;
 }
+
+static std::atomic<unsigned long long> g_launches{ 0 };
+void count_launch(unsigned n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+// FFMA micro-benchmark: 8 independent dependent-chains per thread, 4096 FMAs each.  The roofline
+// denominator of the FP32-bound edge kernels (MEASURED_PEAKS.json has no FP32 entry).
+__global__ void __launch_bounds__(256) ffma_peak_kernel(float* out, float a, float b, int iters)
+{
+  float x0 = threadIdx.x * 1e-3f, x1 = x0 + 1.f, x2 = x0 + 2.f, x3 = x0 + 3.f;
+  float x4 = x0 + 4.f, x5 = x0 + 5.f, x6 = x0 + 6.f, x7 = x0 + 7.f;
+  for (int i = 0; i < iters; i++)
+  {
+#pragma unroll
+    for (int u = 0; u < 16; u++)
+    {
+      x0 = fmaf(x0, a, b);
+      x1 = fmaf(x1, a, b);
+      x2 = fmaf(x2, a, b);
+      x3 = fmaf(x3, a, b);
+      x4 = fmaf(x4, a, b);
+      x5 = fmaf(x5, a, b);
+      x6 = fmaf(x6, a, b);
+      x7 = fmaf(x7, a, b);
+    }
+  }
+  const float s = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
+  if (s == 123.456f)
+    out[0] = s;  // never true in practice; keeps the chain alive
+}
+
+__global__ void l2_flush_kernel(float4* buf, size_t n, float v)
+{
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (; i < n; i += stride)
+    buf[i] = make_float4(v, v, v, v);
+}
 }  // namespace gc
 
 extern "C" {
@@ -80,6 +119,71 @@ int gc_device_count(int* count)
     return GC_E_CUDA;
   }
   *count = n;
+  return GC_OK;
+}
+
+int gc_launch_count(uint64_t* count)
+{
+  GC_REQUIRE(count != nullptr, "gc_launch_count: NULL");
+  *count = gc::g_launches.load();
+  return GC_OK;
+}
+
+int gc_measure_fp32_peak(int device, double* tflops, double* sm_mhz_estimate)
+{
+  GC_REQUIRE(tflops != nullptr, "gc_measure_fp32_peak: NULL");
+  GC_CUDA(cudaSetDevice(device));
+  const int sms = gc::num_sms(device);
+  float* d_out = nullptr;
+  GC_CUDA(cudaMalloc(&d_out, sizeof(float)));
+  cudaEvent_t e0, e1;
+  GC_CUDA(cudaEventCreate(&e0));
+  GC_CUDA(cudaEventCreate(&e1));
+  const int iters = 256, blocks = sms * 8, threads = 256;
+  double best = 0.0;
+  for (int rep = 0; rep < 6; rep++)
+  {
+    GC_CUDA(cudaEventRecord(e0, 0));
+    gc::ffma_peak_kernel<<<blocks, threads>>>(d_out, 1.0000001f, 1e-7f, iters);
+    GC_CUDA(cudaEventRecord(e1, 0));
+    GC_CUDA(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    GC_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    const double flops = 2.0 * 8.0 * 16.0 * iters * (double)blocks * threads;
+    const double tf = flops / (ms * 1e-3) / 1e12;
+    if (rep > 0 && tf > best)
+      best = tf;
+  }
+  gc::count_launch(6);
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(d_out);
+  *tflops = best;
+  if (sm_mhz_estimate)
+    *sm_mhz_estimate = best * 1e12 / (2.0 * 128.0 * sms) / 1e6;
+  return GC_OK;
+}
+
+int gc_flush_l2(int device, size_t bytes)
+{
+  GC_CUDA(cudaSetDevice(device));
+  static void* buf = nullptr;
+  static size_t cap = 0;
+  if (bytes > cap)
+  {
+    if (buf)
+      cudaFree(buf);
+    buf = nullptr;
+    cap = 0;
+    GC_CUDA(cudaMalloc(&buf, bytes));
+    cap = bytes;
+  }
+  static float v = 0.f;
+  v += 1.f;
+  gc::l2_flush_kernel<<<gc::num_sms(device) * 8, 256>>>(reinterpret_cast<float4*>(buf), bytes / 16, v);
+  gc::count_launch();
+  GC_CUDA(cudaGetLastError());
+  GC_CUDA(cudaDeviceSynchronize());
   return GC_OK;
 }
 

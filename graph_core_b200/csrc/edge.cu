@@ -915,6 +915,7 @@ static int launch_light(gc_world* w, const LightArgs& a, cudaStream_t st)
     blocks = 1;
   edge_warp_kernel<D, MODE><<<blocks, 256, smem, st>>>(a);
   GC_CUDA(cudaGetLastError());
+  count_launch();
   return GC_OK;
 }
 
@@ -940,6 +941,7 @@ static int launch_arm(gc_world* w, const ArmArgs& a, uint64_t items_hint, cudaSt
     blocks = 1;
   arm_state_kernel<D, NRS, G><<<(unsigned)blocks, threads, smem, st>>>(a);
   GC_CUDA(cudaGetLastError());
+  count_launch();
   return GC_OK;
 }
 
@@ -955,10 +957,21 @@ static int launch_arm_nrs(gc_world* w, const ArmArgs& a, uint64_t items_hint, cu
   return launch_arm<D, 32, 1>(w, a, items_hint, st);
 }
 
+// Device time of the check kernels, measured with CUDA events on the launching stream.  The events are
+// only recorded here (no host synchronisation inside the hot path); gc_world_counters() resolves them.
 static int time_begin(gc_world* w, cudaStream_t st)
 {
-  if (w->timing)
-    GC_CUDA(cudaEventRecord(w->ev0, st));
+  if (!w->timing)
+    return GC_OK;
+  if (w->ev_used + 2 > w->ev_pool.size())
+  {
+    cudaEvent_t a, b;
+    GC_CUDA(cudaEventCreate(&a));
+    GC_CUDA(cudaEventCreate(&b));
+    w->ev_pool.push_back(a);
+    w->ev_pool.push_back(b);
+  }
+  GC_CUDA(cudaEventRecord(w->ev_pool[w->ev_used], st));
   return GC_OK;
 }
 static int time_end(gc_world* w, cudaStream_t st)
@@ -966,12 +979,21 @@ static int time_end(gc_world* w, cudaStream_t st)
   w->launches++;
   if (w->timing)
   {
-    GC_CUDA(cudaEventRecord(w->ev1, st));
-    GC_CUDA(cudaEventSynchronize(w->ev1));
+    GC_CUDA(cudaEventRecord(w->ev_pool[w->ev_used + 1], st));
+    w->ev_used += 2;
+  }
+  return GC_OK;
+}
+int resolve_timing(gc_world* w)
+{
+  for (size_t i = 0; i + 1 < w->ev_used; i += 2)
+  {
+    GC_CUDA(cudaEventSynchronize(w->ev_pool[i + 1]));
     float ms = 0.f;
-    GC_CUDA(cudaEventElapsedTime(&ms, w->ev0, w->ev1));
+    GC_CUDA(cudaEventElapsedTime(&ms, w->ev_pool[i], w->ev_pool[i + 1]));
     w->kernel_ns += (uint64_t)((double)ms * 1.0e6);
   }
+  w->ev_used = 0;
   return GC_OK;
 }
 
@@ -1040,7 +1062,7 @@ int check_edges_dev(gc_world* w, const double* d_c1, const double* d_c2, const d
     const int pthreads = n >= 1024 ? 1024 : (int)align_up(n, 32);
     GC_DISPATCH_DIM_E(w->dim, GC_DISPATCH_MODE(mode, 
                                                (edge_plan_kernel<DD, MM><<<1, pthreads, 0, st>>>(p));
-                                               GC_CUDA(cudaGetLastError())); GC_TRY((launch_arm_nrs<DD>(w, a, states_hint, st))));
+                                               GC_CUDA(cudaGetLastError()); count_launch()); GC_TRY((launch_arm_nrs<DD>(w, a, states_hint, st))));
   }
   return time_end(w, st);
 }
@@ -1111,10 +1133,6 @@ static int world_new(int kind, int dim, int device, gc_world** out)
     e = cudaMalloc(&w->d_counters, 2 * sizeof(unsigned long long));
   if (e == cudaSuccess)
     e = cudaMemset(w->d_counters, 0, 2 * sizeof(unsigned long long));
-  if (e == cudaSuccess)
-    e = cudaEventCreate(&w->ev0);
-  if (e == cudaSuccess)
-    e = cudaEventCreate(&w->ev1);
   if (e != cudaSuccess)
   {
     gc::set_error("gc_world_create: %s", cudaGetErrorString(e));
@@ -1233,8 +1251,8 @@ int gc_world_destroy(gc_world_t* w)
   w->d_c1.release(); w->d_c2.release(); w->d_c3.release(); w->d_ok.release(); w->d_first.release();
   w->d_plan.release(); w->d_offs.release(); w->d_blocksum.release();
   w->h_in.release(); w->h_out.release();
-  if (w->ev0) cudaEventDestroy(w->ev0);
-  if (w->ev1) cudaEventDestroy(w->ev1);
+  for (cudaEvent_t ev : w->ev_pool)
+    cudaEventDestroy(ev);
   if (w->own_stream) cudaStreamDestroy(w->own_stream);
   delete w;
   return GC_OK;
@@ -1259,6 +1277,7 @@ int gc_world_counters(gc_world_t* w, uint64_t out[4])
   GC_CUDA(cudaMemcpy(c, w->d_counters, sizeof(c), cudaMemcpyDeviceToHost));
   out[0] = c[0];
   out[1] = c[1];
+  GC_TRY(gc::resolve_timing(w));
   out[2] = w->launches;
   out[3] = w->kernel_ns;
   return GC_OK;
@@ -1269,6 +1288,7 @@ int gc_world_reset_counters(gc_world_t* w)
   GC_CUDA(cudaSetDevice(w->device));
   GC_CUDA(cudaStreamSynchronize(w->stream));
   GC_CUDA(cudaMemset(w->d_counters, 0, 2 * sizeof(unsigned long long)));
+  GC_TRY(gc::resolve_timing(w));
   w->launches = 0;
   w->kernel_ns = 0;
   return GC_OK;

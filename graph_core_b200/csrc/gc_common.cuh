@@ -63,6 +63,9 @@ struct PinBuf
 
 int num_sms(int device);
 
+// every kernel launch site bumps this (bench.py reports it as "gpu_launches")
+void count_launch(unsigned n = 1);
+
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 }  // namespace gc
 
@@ -122,7 +125,8 @@ struct gc_world
   uint64_t launches = 0;
   bool timing = false;
   uint64_t kernel_ns = 0;
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  std::vector<cudaEvent_t> ev_pool;  // (begin, end) pairs recorded around the check kernels
+  size_t ev_used = 0;
   // scratch
   gc::DevBuf d_c1, d_c2, d_c3, d_ok, d_first, d_plan, d_offs, d_blocksum;
   gc::PinBuf h_in, h_out;

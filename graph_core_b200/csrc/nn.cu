@@ -502,6 +502,7 @@ int nn1_dev(gc_store* s, const double* d_q, const uint32_t* d_seg, uint32_t nq, 
   GC_CUDA(cudaGetLastError());
   nn1_finalize_kernel<<<(nq + 127) / 128, 128, 0, s->stream>>>(a.part_d, a.part_i, chunks, nq, d_idx, d_dist);
   GC_CUDA(cudaGetLastError());
+  count_launch(2);
   return GC_OK;
 }
 
@@ -526,6 +527,7 @@ static int sort_lists(gc_store* s, uint32_t nq, uint32_t cap, uint32_t* d_idx, d
   int threads = P >= 2048 ? 1024 : (P >= 512 ? 256 : 64);
   sort_lists_kernel<<<nq, threads, smem, s->stream>>>(d_idx, d_dist, d_count, cap, P);
   GC_CUDA(cudaGetLastError());
+  count_launch();
   return GC_OK;
 }
 
@@ -557,6 +559,7 @@ int radius_dev(gc_store* s, const double* d_q, const uint32_t* d_seg, const doub
   dim3 grid(chunks, groups);
   GC_DISPATCH_DIM(s->dim, (scan_kernel<DD, 1><<<grid, kScanThreads, 0, s->stream>>>(a)));
   GC_CUDA(cudaGetLastError());
+  count_launch();
   return sort_lists(s, nq, cap, d_idx, d_dist, d_count);
 }
 
@@ -588,6 +591,7 @@ int knn_dev(gc_store* s, const double* d_q, const uint32_t* d_seg, uint32_t nq, 
                                                            row_stride, (unsigned long long)k, cap, d_idx, d_dist,
                                                            d_count, P));
   GC_CUDA(cudaGetLastError());
+  count_launch();
   return GC_OK;
 }
 
@@ -717,6 +721,7 @@ int gc_store_append(gc_store_t* s, uint32_t segment, const double* q, uint32_t n
   store_scatter_kernel<<<(total + 255) / 256, 256, 0, s->stream>>>(s->d_rows.as<double>(), s->d_slots.as<uint32_t>(), n,
                                                                     s->dim, s->cap_total + kRowPad, s->x32, s->x64);
   GC_CUDA(cudaGetLastError());
+  count_launch(2);
   s->used[segment] = first + n;
   s->live[segment] += n;
   GC_CUDA(cudaMemcpyAsync(s->d_used + segment, &s->used[segment], sizeof(uint32_t), cudaMemcpyHostToDevice, s->stream));
@@ -768,6 +773,7 @@ int gc_store_append_multi(gc_store_t* s, const uint32_t* segments, const double*
   store_scatter_kernel<<<(total + 255) / 256, 256, 0, s->stream>>>(s->d_rows.as<double>(), s->d_slots.as<uint32_t>(), n,
                                                                     s->dim, s->cap_total + kRowPad, s->x32, s->x64);
   GC_CUDA(cudaGetLastError());
+  count_launch();
   GC_CUDA(cudaMemcpyAsync(s->d_used, s->used.data(), sizeof(uint32_t) * s->nseg, cudaMemcpyHostToDevice, s->stream));
   GC_CUDA(cudaStreamSynchronize(s->stream));
   return GC_OK;

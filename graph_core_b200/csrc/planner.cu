@@ -44,6 +44,14 @@ __global__ void steer_kernel(const double* __restrict__ x64, const double* __res
   }
 }
 
+__global__ void gather_rows_kernel(const double* __restrict__ src, const uint32_t* __restrict__ rows, uint32_t n,
+                                   int dim, double* __restrict__ dst)
+{
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n * (uint32_t)dim)
+    dst[i] = src[(size_t)rows[i / dim] * dim + i % dim];
+}
+
 // ---- Philox4x32-10 ------------------------------------------------------------------------------
 __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,
                                               uint32_t k1, uint32_t* out)
@@ -105,12 +113,14 @@ using namespace gc;
 
 extern "C" {
 
-int gc_extend_batch(gc_store_t* s, gc_world_t* w, const double* q, const uint32_t* seg, uint32_t n,
-                    double max_distance, double min_distance, double tolerance, const double* radius,
-                    uint32_t near_cap, uint32_t* closest, double* dist, double* next, uint8_t* ok,
-                    uint32_t* near_idx, double* near_dist, uint32_t* near_count)
+// q: host samples [n][D]  -- or --  d_samples: device samples, row src_row[i] (identity when NULL) feeds sample i
+static int extend_batch_impl(gc_store_t* s, gc_world_t* w, const double* q, const double* d_samples,
+                             const uint32_t* src_row, const uint32_t* seg, uint32_t n, double max_distance,
+                             double min_distance, double tolerance, const double* radius, uint32_t near_cap,
+                             uint32_t* closest, double* dist, double* next, uint8_t* ok, uint32_t* near_idx,
+                             double* near_dist, uint32_t* near_count)
 {
-  GC_REQUIRE(s && w && q && closest && dist && next && ok, "gc_extend_batch: NULL argument");
+  GC_REQUIRE(s && w && (q || d_samples) && closest && dist && next && ok, "gc_extend_batch: NULL argument");
   GC_REQUIRE(s->dim == w->dim, "gc_extend_batch: store dim %d != world dim %d", s->dim, w->dim);
   GC_REQUIRE(s->device == w->device, "gc_extend_batch: store and world live on different devices");
   GC_REQUIRE(!radius || (near_cap > 0 && near_idx && near_dist && near_count), "gc_extend_batch: near outputs missing");
@@ -148,8 +158,26 @@ int gc_extend_batch(gc_store_t* s, gc_world_t* w, const double* q, const uint32_
   for (uint32_t i = 0; seg && i < n; i++)
     GC_REQUIRE(seg[i] < s->nseg, "sample %u: segment %u of %u", i, seg[i], s->nseg);
   char* h = static_cast<char*>(s->h_in.p);
-  memcpy(h, q, qb);
-  GC_CUDA(cudaMemcpyAsync(s->d_q.p, h, qb, cudaMemcpyHostToDevice, st));
+  const double* d_q = s->d_q.as<double>();
+  if (q)
+  {
+    memcpy(h, q, qb);
+    GC_CUDA(cudaMemcpyAsync(s->d_q.p, h, qb, cudaMemcpyHostToDevice, st));
+  }
+  else if (src_row)
+  {
+    // samples stay resident in HBM: gather the rows of the active problems on the device
+    GC_TRY(s->d_slots.reserve(sizeof(uint32_t) * n));
+    memcpy(h, src_row, sizeof(uint32_t) * n);
+    GC_CUDA(cudaMemcpyAsync(s->d_slots.p, h, sizeof(uint32_t) * n, cudaMemcpyHostToDevice, st));
+    const uint32_t total = n * (uint32_t)D;
+    gather_rows_kernel<<<(total + 255) / 256, 256, 0, st>>>(d_samples, s->d_slots.as<uint32_t>(), n, D,
+                                                             s->d_q.as<double>());
+    GC_CUDA(cudaGetLastError());
+    count_launch();
+  }
+  else
+    d_q = d_samples;
   if (seg)
   {
     memcpy(h + qb, seg, sizeof(uint32_t) * n);
@@ -163,11 +191,11 @@ int gc_extend_batch(gc_store_t* s, gc_world_t* w, const double* q, const uint32_
   const uint32_t* d_seg = seg ? s->d_seg.as<uint32_t>() : nullptr;
   double* d_dist = s->d_misc.as<double>();
   uint32_t* d_closest = reinterpret_cast<uint32_t*>(d_dist + n);
-  GC_TRY(nn1_dev(s, s->d_q.as<double>(), d_seg, n, d_closest, d_dist, seg == nullptr));
-  steer_kernel<<<(n + 127) / 128, 128, 0, st>>>(s->x64, s->d_q.as<double>(), d_seg, d_closest, d_dist, n, D,
-                                                 s->cap_seg, max_distance, w->d_c1.as<double>(),
-                                                 w->d_c2.as<double>());
+  GC_TRY(nn1_dev(s, d_q, d_seg, n, d_closest, d_dist, seg == nullptr));
+  steer_kernel<<<(n + 127) / 128, 128, 0, st>>>(s->x64, d_q, d_seg, d_closest, d_dist, n, D, s->cap_seg,
+                                                 max_distance, w->d_c1.as<double>(), w->d_c2.as<double>());
   GC_CUDA(cudaGetLastError());
+  count_launch();
   // states per edge for an edge of length max_distance (grid sizing only)
   uint64_t per_edge = 2;
   for (double nn = 2; max_distance > nn * min_distance && per_edge < (1u << 20); nn *= 2)
@@ -221,6 +249,56 @@ int gc_extend_batch(gc_store_t* s, gc_world_t* w, const double* q, const uint32_
   return rc;
 }
 
+int gc_extend_batch(gc_store_t* s, gc_world_t* w, const double* q, const uint32_t* seg, uint32_t n,
+                    double max_distance, double min_distance, double tolerance, const double* radius,
+                    uint32_t near_cap, uint32_t* closest, double* dist, double* next, uint8_t* ok,
+                    uint32_t* near_idx, double* near_dist, uint32_t* near_count)
+{
+  GC_REQUIRE(q != nullptr, "gc_extend_batch: NULL samples");
+  return extend_batch_impl(s, w, q, nullptr, nullptr, seg, n, max_distance, min_distance, tolerance, radius, near_cap,
+                           closest, dist, next, ok, near_idx, near_dist, near_count);
+}
+
+int gc_extend_batch_dsamples(gc_store_t* s, gc_world_t* w, const double* d_samples, const uint32_t* src_row,
+                             const uint32_t* seg, uint32_t n, double max_distance, double min_distance,
+                             double tolerance, const double* radius, uint32_t near_cap, uint32_t* closest,
+                             double* dist, double* next, uint8_t* ok, uint32_t* near_idx, double* near_dist,
+                             uint32_t* near_count)
+{
+  GC_REQUIRE(d_samples != nullptr, "gc_extend_batch_dsamples: NULL samples");
+  return extend_batch_impl(s, w, nullptr, d_samples, src_row, seg, n, max_distance, min_distance, tolerance, radius,
+                           near_cap, closest, dist, next, ok, near_idx, near_dist, near_count);
+}
+
+// device-resident variant of gc_sample_uniform: fills d_out[n][dim] on `cuda_stream` (NULL: default stream)
+int gc_sample_uniform_dev(int device, int dim, const double* lb, const double* ub, uint64_t seed,
+                          uint64_t first_index, uint32_t n, double* d_out, void* cuda_stream)
+{
+  GC_REQUIRE(lb && ub && d_out, "gc_sample_uniform_dev: NULL argument");
+  GC_REQUIRE(dim >= 1 && dim <= GC_MAX_DIM, "gc_sample_uniform_dev: dim %d", dim);
+  if (n == 0)
+    return GC_OK;
+  GC_CUDA(cudaSetDevice(device));
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(cuda_stream);
+  double* d_b = nullptr;
+  GC_CUDA(cudaMalloc(&d_b, sizeof(double) * 2 * dim));
+  GC_CUDA(cudaMemcpyAsync(d_b, lb, sizeof(double) * dim, cudaMemcpyHostToDevice, st));
+  GC_CUDA(cudaMemcpyAsync(d_b + dim, ub, sizeof(double) * dim, cudaMemcpyHostToDevice, st));
+  const uint32_t total = n * (uint32_t)((dim + 1) / 2);
+  sample_uniform_kernel<<<(total + 255) / 256, 256, 0, st>>>(d_b, d_b + dim, dim, seed, first_index, n, d_out);
+  cudaError_t e = cudaGetLastError();
+  count_launch();
+  if (e == cudaSuccess)
+    e = cudaStreamSynchronize(st);
+  cudaFree(d_b);
+  if (e != cudaSuccess)
+  {
+    gc::set_error("gc_sample_uniform_dev: %s", cudaGetErrorString(e));
+    return GC_E_CUDA;
+  }
+  return GC_OK;
+}
+
 int gc_sample_uniform(int device, int dim, const double* lb, const double* ub, uint64_t seed, uint64_t first_index,
                       uint32_t n, double* out)
 {
@@ -245,6 +323,7 @@ int gc_sample_uniform(int device, int dim, const double* lb, const double* ub, u
   cudaMemcpy(d_b + dim, ub, sizeof(double) * dim, cudaMemcpyHostToDevice);
   const uint32_t total = n * (uint32_t)((dim + 1) / 2);
   sample_uniform_kernel<<<(total + 255) / 256, 256>>>(d_b, d_b + dim, dim, seed, first_index, n, d_out);
+  count_launch();
   e = cudaGetLastError();
   if (e == cudaSuccess)
     e = cudaMemcpy(out, d_out, sizeof(double) * (size_t)n * dim, cudaMemcpyDeviceToHost);

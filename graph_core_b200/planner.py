@@ -1,0 +1,149 @@
+"""ctypes binding of the C++ host layer (graph_core_b200/host/lockstep.h -> libgcb200_host.so).
+
+LockstepRRTStar advances many independent RRT* problems (RRTStar::update,
+src/graph_core/solvers/rrt_star.cpp:89-163) in lock step; the hot paths of all problems are batched
+into a few CUDA launches per iteration through the C ABI of libgcb200.so.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+
+import numpy as np
+
+from . import capi
+
+_PKG = Path(__file__).resolve().parent
+HOSTLIB_PATH = _PKG / "libgcb200_host.so"
+_dp = C.POINTER(C.c_double)
+_i32p = C.POINTER(C.c_int32)
+_u32p = C.POINTER(C.c_uint32)
+_u64p = C.POINTER(C.c_uint64)
+_hlib = None
+
+
+def load_host():
+    global _hlib
+    if _hlib is not None:
+        return _hlib
+    capi.load()  # libgcb200.so first (no CPU fallback)
+    if not HOSTLIB_PATH.exists():
+        raise RuntimeError("%s is missing: build it with `python -m graph_core_b200._build`" % HOSTLIB_PATH)
+    L = C.CDLL(str(HOSTLIB_PATH))
+    vp = C.c_void_p
+    sig = {
+        "gcp_rrtstar_create": (C.c_int, [C.c_int, C.c_double, C.c_double, C.c_double, C.c_double, _dp, _dp, vp, C.c_int,
+                                         C.c_uint32, _dp, _dp, C.c_uint32, C.c_int, C.POINTER(vp)]),
+        "gcp_rrtstar_destroy": (C.c_int, [vp]),
+        "gcp_rrtstar_step": (C.c_int, [vp, _dp]),
+        "gcp_rrtstar_step_dsamples": (C.c_int, [vp, vp]),
+        "gcp_rrtstar_set_stream": (C.c_int, [vp, vp]),
+        "gcp_rrtstar_run": (C.c_int, [vp, _dp, C.c_uint32]),
+        "gcp_rrtstar_info": (C.c_int, [vp, C.c_uint32, _i32p, _i32p, _dp, _dp, _u32p, _u32p]),
+        "gcp_rrtstar_dump": (C.c_int, [vp, C.c_uint32, _i32p, _dp, _dp]),
+        "gcp_rrtstar_solution": (C.c_int, [vp, C.c_uint32, _i32p, C.c_uint32]),
+        "gcp_rrtstar_stats": (C.c_int, [vp, _u64p]),
+        "gcp_last_error": (C.c_char_p, []),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(L, name)
+        fn.restype = res
+        fn.argtypes = args
+    _hlib = L
+    return L
+
+
+def _f64(a, shape=None):
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    return a.reshape(shape) if shape is not None else a
+
+
+class LockstepRRTStar:
+    """P independent RRT* problems sharing one collision world, advanced in lock step."""
+
+    def __init__(self, scenario, world: capi.CollisionWorld, starts, goals, capacity: int = 16384, device: int = 0,
+                 threads: int = 0):
+        self.L = load_host()
+        self.dim = scenario.dim
+        self.world = world  # keep alive
+        starts = _f64(starts, (-1, self.dim))
+        goals = _f64(goals, (-1, self.dim))
+        assert starts.shape == goals.shape
+        self.n = starts.shape[0]
+        lb, ub = _f64(scenario.lb), _f64(scenario.ub)
+        h = C.c_void_p()
+        rc = self.L.gcp_rrtstar_create(self.dim, scenario.max_distance, scenario.min_distance, scenario.rewire_factor,
+                                       scenario.utopia_tolerance, lb.ctypes.data_as(_dp), ub.ctypes.data_as(_dp),
+                                       world.handle, device, self.n, starts.ctypes.data_as(_dp),
+                                       goals.ctypes.data_as(_dp), capacity, threads, C.byref(h))
+        if rc != 0:
+            raise capi.GcError(rc, self.L.gcp_last_error().decode())
+        self.h = h
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.gcp_rrtstar_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def step(self, samples) -> int:
+        s = _f64(samples, (self.n, self.dim))
+        rc = self.L.gcp_rrtstar_step(self.h, s.ctypes.data_as(_dp))
+        if rc < 0:
+            raise capi.GcError(rc, self.L.gcp_last_error().decode())
+        return rc
+
+    def step_device_samples(self, d_samples_ptr: int) -> int:
+        """d_samples_ptr: device address of a [problems, dim] float64 block (e.g. torch tensor .data_ptr())."""
+        rc = self.L.gcp_rrtstar_step_dsamples(self.h, C.c_void_p(d_samples_ptr))
+        if rc < 0:
+            raise capi.GcError(rc, self.L.gcp_last_error().decode())
+        return rc
+
+    def set_stream(self, cuda_stream: int | None):
+        rc = self.L.gcp_rrtstar_set_stream(self.h, C.c_void_p(cuda_stream or 0))
+        if rc < 0:
+            raise capi.GcError(rc, self.L.gcp_last_error().decode())
+
+    def run(self, samples) -> int:
+        """samples: [iterations, problems, dim]; returns the number of planner updates executed."""
+        s = _f64(samples)
+        assert s.ndim == 3 and s.shape[1] == self.n and s.shape[2] == self.dim
+        rc = self.L.gcp_rrtstar_run(self.h, s.ctypes.data_as(_dp), s.shape[0])
+        if rc < 0:
+            raise capi.GcError(rc, self.L.gcp_last_error().decode())
+        return rc
+
+    def info(self, p: int = 0):
+        solved, can = C.c_int32(0), C.c_int32(0)
+        cost, radius = C.c_double(0), C.c_double(0)
+        nn, ts = C.c_uint32(0), C.c_uint32(0)
+        self.L.gcp_rrtstar_info(self.h, p, C.byref(solved), C.byref(can), C.byref(cost), C.byref(radius), C.byref(nn),
+                                C.byref(ts))
+        return {"solved": bool(solved.value), "can_improve": bool(can.value), "cost": cost.value,
+                "radius": radius.value, "num_nodes": nn.value, "tree_size": ts.value}
+
+    def dump(self, p: int = 0):
+        n = self.info(p)["num_nodes"]
+        par = np.empty(n, np.int32)
+        pc = np.empty(n, np.float64)
+        conf = np.empty((n, self.dim), np.float64)
+        self.L.gcp_rrtstar_dump(self.h, p, par.ctypes.data_as(_i32p), pc.ctypes.data_as(_dp), conf.ctypes.data_as(_dp))
+        return par, pc, conf
+
+    def solution(self, p: int = 0):
+        ids = np.empty(1 << 16, np.int32)
+        n = self.L.gcp_rrtstar_solution(self.h, p, ids.ctypes.data_as(_i32p), ids.shape[0])
+        return ids[:n].copy()
+
+    def stats(self):
+        out = (C.c_uint64 * 10)()
+        self.L.gcp_rrtstar_stats(self.h, out)
+        keys = ["iterations", "extended", "edges_device", "edges_used", "edges_fallback", "near_hits", "gpu_calls",
+                "h2d_bytes", "d2h_bytes"]
+        return dict(zip(keys, [int(v) for v in out]))

@@ -166,18 +166,7 @@ def arm_model(n_joints: int = 7):
     return base, joint, np.array(link, np.int32), np.array(local, np.float32)
 
 
-def scenario_c3(n_obs: int = 1000, checker=None) -> Scenario:
-    """7-DoF sphere-model arm vs a 1k-sphere cloud.
-
-    `checker(params, q[n,7]) -> bool[n]` (True = free) filters obstacles that touch the arm at the
-    start/goal configuration; tests pass the oracle, bench passes the CUDA world.  Obstacle centres
-    are U[-1.1,1.1]^3 with radii U[0.02,0.05]; obstacles closer than 0.25 m to the base column are
-    skipped so that link 0 (which never moves) stays free.
-    """
-    d = 7
-    base, joint, link, local = arm_model(d)
-    start = np.array([0.0, -0.6, 0.0, 0.9, 0.0, 0.6, 0.0])
-    goal = np.array([1.8, 0.7, -0.8, -0.9, 0.7, -0.5, 1.0])
+def _c3_obstacles(n_obs: int):
     obs = []
     i = 0
     while len(obs) < n_obs:
@@ -186,41 +175,54 @@ def scenario_c3(n_obs: int = 1000, checker=None) -> Scenario:
         c = -1.1 + u[:3] * 2.2
         r = 0.02 + u[3] * 0.03
         if math.hypot(c[0], c[1]) < 0.25 + r and -0.1 < c[2] < 0.45:
-            continue
+            continue  # keep the base column clear: link 0 never moves
         obs.append([c[0], c[1], c[2], r])
-    obs = np.array(obs, np.float32)
+    return np.array(obs, np.float32)
+
+
+def scenario_c3(n_obs: int = 1000, checker=None, problem: int = 0) -> Scenario:
+    """7-DoF sphere-model arm vs a 1k-sphere cloud (obstacle centres U[-1.1,1.1]^3, radii U[0.02,0.05]).
+
+    `checker(params, q[n,7]) -> bool[n]` (True = free) selects the start/goal pair: pair number
+    `problem` of the Philox stream (seed 302) among those whose endpoints are free and whose straight
+    connection is blocked (so the planner has work to do).  Tests pass the oracle's checker, the
+    product passes the CUDA world's; both give the same booleans.  Without a checker a fixed pair is
+    returned unvalidated.
+    """
+    d = 7
+    base, joint, link, local = arm_model(d)
+    obs = _c3_obstacles(n_obs)
     params = {"base_tf": base, "joint_tf": joint, "rs_link": link, "rs_local": local, "obs": obs}
+    start = np.array([0.0, -0.6, 0.0, 0.9, 0.0, 0.6, 0.0])
+    goal = np.array([1.8, 0.7, -0.8, -0.9, 0.7, -0.5, 1.0])
     if checker is not None:
-        # drop the obstacles that collide with the arm at start or goal, then refill from the stream
-        for _ in range(64):
-            keep = np.ones(len(obs), bool)
-            bad_any = False
-            for q in (start, goal):
-                if checker(dict(params, obs=obs), q[None, :])[0]:
-                    continue
-                bad_any = True
-                for o in range(len(obs)):
-                    if keep[o] and not checker(dict(params, obs=obs[o:o + 1]), q[None, :])[0]:
-                        keep[o] = False
-            if not bad_any:
-                break
-            obs = obs[keep]
-            while len(obs) < n_obs:
-                u = philox_u01(301, i, 1, 4)[0]
-                i += 1
-                c = -1.1 + u[:3] * 2.2
-                r = 0.02 + u[3] * 0.03
-                if math.hypot(c[0], c[1]) < 0.25 + r and -0.1 < c[2] < 0.45:
-                    continue
-                obs = np.vstack([obs, np.array([[c[0], c[1], c[2], r]], np.float32)])
-        params["obs"] = obs
+        pairs = c3_problems(checker, params, problem + 1)
+        start, goal = pairs[problem]
     return Scenario("C3", d, "sphere_arm", np.full(d, -math.pi), np.full(d, math.pi), start, goal, max_distance=0.5,
                     params=params)
 
 
-def c3_problem_pairs(n: int, seed: int = 302):
-    """Start/goal pairs for the multi-problem C3/C5 runs (before validity filtering)."""
-    u = philox_u01(seed, 0, n, 14)
+def c3_problems(checker, params, n: int, seed: int = 302):
+    """First n start/goal pairs (Philox seed 302) with free endpoints and a blocked straight connection."""
+    out = []
+    first = 0
+    t = np.linspace(0.0, 1.0, 65)[:, None]
+    while len(out) < n:
+        s, g = c3_problem_pairs(64, seed, first)
+        first += 64
+        ok = checker(params, s) & checker(params, g)
+        for i in np.nonzero(ok)[0]:
+            line = s[i][None, :] + (g[i] - s[i])[None, :] * t
+            if not checker(params, line).all():
+                out.append((s[i].copy(), g[i].copy()))
+                if len(out) == n:
+                    break
+    return out
+
+
+def c3_problem_pairs(n: int, seed: int = 302, first: int = 0):
+    """Raw start/goal pairs for the multi-problem C3/C5 runs (before validity filtering)."""
+    u = philox_u01(seed, first, n, 14)
     q = -math.pi + u * 2 * math.pi
     return q[:, :7], q[:, 7:]
 

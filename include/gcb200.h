@@ -55,6 +55,12 @@ const char* gc_last_error(void);
 int gc_device_count(int* count);
 /* name[0..len) receives the device name; sms and cc (10*major+minor) may be NULL */
 int gc_device_info(int device, char* name, int len, int* sms, int* cc);
+/* measurement helpers used by bench.py: kernels launched by this library so far; a dependent-chain FFMA
+ * micro-benchmark (the FP32 roofline denominator, with the SM clock it implies); an L2 flush that
+ * overwrites `bytes` of scratch (bytes > L2 size) */
+int gc_launch_count(uint64_t* count);
+int gc_measure_fp32_peak(int device, double* tflops, double* sm_mhz_estimate);
+int gc_flush_l2(int device, size_t bytes);
 
 /* ---- node store: replaces KdTree/Vector storage (kdtree.cpp:327-342, vector.cpp:38-43) ---- */
 int gc_store_create(int dim, uint32_t capacity_per_segment, uint32_t n_segments, int device, gc_store_t** out);
@@ -138,10 +144,21 @@ int gc_extend_batch(gc_store_t* s, gc_world_t* w, const double* q, const uint32_
                     uint32_t near_cap, uint32_t* closest, double* dist, double* next, uint8_t* ok,
                     uint32_t* near_idx, double* near_dist, uint32_t* near_count);
 
+/* same step with the samples resident in HBM: sample i is row src_row[i] of d_samples (src_row == NULL:
+ * row i).  src_row and seg are host arrays; everything else as gc_extend_batch.                      */
+int gc_extend_batch_dsamples(gc_store_t* s, gc_world_t* w, const double* d_samples, const uint32_t* src_row,
+                             const uint32_t* seg, uint32_t n, double max_distance, double min_distance,
+                             double tolerance, const double* radius, uint32_t near_cap, uint32_t* closest,
+                             double* dist, double* next, uint8_t* ok, uint32_t* near_idx, double* near_dist,
+                             uint32_t* near_count);
+
 /* ---- Philox samplers (uniform_sampler.cpp:34-39, informed_sampler.cpp:145-180) -------------- */
 /* n uniform samples in [lb, ub]; sample i uses Philox counter (first_index + i) */
 int gc_sample_uniform(int device, int dim, const double* lb, const double* ub, uint64_t seed, uint64_t first_index,
                       uint32_t n, double* out);
+/* same samples written to device memory d_out[n][dim] (lb/ub are host arrays) */
+int gc_sample_uniform_dev(int device, int dim, const double* lb, const double* ub, uint64_t seed,
+                          uint64_t first_index, uint32_t n, double* d_out, void* cuda_stream);
 
 #ifdef __cplusplus
 }

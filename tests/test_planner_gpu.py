@@ -1,0 +1,72 @@
+"""GPU parity at planner level: lock-step CUDA RRT* vs the oracle's restatement of RRTStar::update
+(src/graph_core/solvers/rrt_star.cpp:89-163) driven by the same injected samples
+(tree_solver.h:338).  Every problem must build the SAME tree: node configurations and
+parent indices bit-exact, connection costs and path costs bit-exact (BASELINE asks for 1e-5 rel)."""
+import numpy as np
+import pytest
+
+from graph_core_b200 import worlds as W
+
+pytestmark = pytest.mark.gpu
+
+
+def _run_both(gc, orc, sc, starts, goals, iters, seed, use_kdtree=True, threads=4):
+    from graph_core_b200.planner import LockstepRRTStar
+    P = len(starts)
+    gw = sc.make_world()
+    lock = LockstepRRTStar(sc, gw, starts, goals, capacity=max(4096, iters + 64), threads=threads)
+    samples = np.stack([W.uniform_samples(sc.lb, sc.ub, seed + p, 0, iters) for p in range(P)], axis=1)
+    lock.run(samples)
+    ow = orc.OracleWorld.from_scenario(sc)
+    for p in range(P):
+        o = orc.OracleSolver(orc.OracleSolver.RRTSTAR, sc, ow, start=starts[p], goal=goals[p], use_kdtree=use_kdtree)
+        o.run(samples[:, p, :])
+        par, pc, conf = o.dump()
+        gpar, gpc, gconf = lock.dump(p)
+        info = lock.info(p)
+        assert info["num_nodes"] == len(par), (p, info, len(par))
+        assert np.array_equal(gconf, conf)
+        assert np.array_equal(gpar, par)
+        assert np.array_equal(gpc, pc)
+        assert info["solved"] == o.solved and info["tree_size"] == o.tree_size
+        assert info["cost"] == o.cost or (np.isinf(info["cost"]) and np.isinf(o.cost))
+        assert np.array_equal(lock.solution(p), o.solution())
+    st = lock.stats()
+    assert st["edges_fallback"] == 0          # the speculative edge set always covered the replay
+    assert st["edges_used"] <= st["edges_device"] + st["iterations"]
+    return lock, st
+
+
+def test_rrtstar_reference_scene_c0(gc, orc):
+    sc = W.scenario_c0()
+    lock, st = _run_both(gc, orc, sc, sc.start[None, :], sc.goal[None, :], 1500, seed=1)
+    assert lock.info(0)["solved"]
+
+
+def test_rrtstar_c1_boxes_many_problems(gc, orc):
+    sc = W.scenario_c1()
+    ow = orc.OracleWorld.from_scenario(sc)
+    cand = W.uniform_samples(sc.lb, sc.ub, 77, 0, 64)
+    cand = cand[ow.check(cand).astype(bool)]
+    starts, goals = cand[:6], cand[6:12]
+    lock, st = _run_both(gc, orc, sc, starts, goals, 1200, seed=300, use_kdtree=False)
+    assert sum(lock.info(p)["solved"] for p in range(6)) >= 4
+
+
+def test_rrtstar_c3_arm(gc, orc, c3):
+    from graph_core_b200 import worlds
+    pairs = worlds.c3_problems(orc.arm_checker(), c3.params, 3)
+    starts = np.array([s for s, _ in pairs])
+    goals = np.array([g for _, g in pairs])
+    lock, st = _run_both(gc, orc, c3, starts, goals, 700, seed=3020)
+    assert st["extended"] > 100
+
+
+def test_rrtstar_direct_connection_and_thread_counts(gc, orc):
+    # straight line start->goal is free: setProblem's connectToNode solves it without sampling
+    sc = W.scenario_c0()
+    starts = np.array([[1.5, 1.5, 1.5], [-1.5, -1.5, -1.5]])
+    goals = np.array([[2.2, 1.2, 2.0], [1.5, 1.5, 1.5]])
+    for threads in (1, 3):
+        lock, st = _run_both(gc, orc, sc, starts, goals, 300, seed=9, threads=threads)
+        assert lock.info(0)["solved"] and not lock.info(0)["can_improve"]
