@@ -36,7 +36,7 @@ sys.path.insert(0, str(ROOT))
 
 METRIC = "rrtstar_samples_per_sec"
 UNIT = "samples/s"
-FLOP_PER_PAIR = 10.0  # 3 sub, 1 mul + 2 fma (=5), radius add, square, compare
+FLOP_PER_PAIR = 9.0  # include/gcb200_spec.h: 4 fused multiply-adds (8 flop) + 1 compare per sphere pair
 
 
 def parse_args():
@@ -49,6 +49,8 @@ def parse_args():
     ap.add_argument("--threads", type=int, default=0, help="host replay threads (0 = all cores)")
     ap.add_argument("--skip-nn", action="store_true", help="skip the kNN roofline side measurement")
     ap.add_argument("--cpu-problems", type=int, default=0, help="problems of the CPU baseline sample (0 = auto)")
+    ap.add_argument("--profile", action="store_true",
+                    help="profiling run: only the device-sample arm, no CPU baseline / parity / kNN side measurement")
     return ap.parse_args()
 
 
@@ -290,8 +292,13 @@ def main():
         return {"ms": ms, "consumed": consumed_all, "stats": {k: st1[k] - st0[k] for k in st1}, "world": cnt,
                 "launches": launches, "t0": t0, "t1": t1, "lock": lock, "wall_world": world}
 
-    e2e_run = timed_run(device_samples=False)
     val_run = timed_run(device_samples=True)
+    if args.profile:
+        if rank == 0:
+            print(json.dumps({"profile_run": True, "ms_per_step": val_run["ms"] / K,
+                              "value": val_run["consumed"] / (val_run["ms"] * 1e-3)}))
+        return 0
+    e2e_run = timed_run(device_samples=False)
     value = val_run["consumed"] / (val_run["ms"] * 1e-3)
     e2e_value = e2e_run["consumed"] / (e2e_run["ms"] * 1e-3)
     clk = clocks.window(val_run["t0"], val_run["t1"])

@@ -396,8 +396,37 @@ struct ArmSmem
   const float* joint;
   const float* rs_local;
   const int* rs_link;
-  const float4* obs;
+  const float4* obs;   // x y z r
+  const float* obs_na; // r^2 - |o|^2 (include/gcb200_spec.h, "sphere pair test")
 };
+
+// Per-sphere constants of the expanded pair test  |o-c|^2 < (ro+rs)^2  <=>
+//   B + o.(-2c) + ro*(-2rs) < ro^2 - |o|^2,   B = |c|^2 - rs^2
+// evaluated as four fused multiply-adds and one compare per pair (spec order: x, y, z, r).
+struct SphereK
+{
+  float c2x, c2y, c2z, rs2, B;
+};
+__device__ __forceinline__ SphereK sphere_consts(float cx, float cy, float cz, float rs)
+{
+  SphereK k;
+  k.c2x = __fmul_rn(-2.0f, cx);
+  k.c2y = __fmul_rn(-2.0f, cy);
+  k.c2z = __fmul_rn(-2.0f, cz);
+  k.rs2 = __fmul_rn(-2.0f, rs);
+  float n2 = __fmul_rn(cx, cx);
+  n2 = __fmaf_rn(cy, cy, n2);
+  n2 = __fmaf_rn(cz, cz, n2);
+  k.B = __fsub_rn(n2, __fmul_rn(rs, rs));
+  return k;
+}
+__device__ __forceinline__ float obstacle_na(const float4& ob)
+{
+  float n2 = __fmul_rn(ob.x, ob.x);
+  n2 = __fmaf_rn(ob.y, ob.y, n2);
+  n2 = __fmaf_rn(ob.z, ob.z, n2);
+  return __fsub_rn(__fmul_rn(ob.w, ob.w), n2);
+}
 
 // one FK joint step: (AR, At) = frame A_j on entry; writes link frame B_j to (BR, At unchanged) and
 // advances (AR, At) to A_{j+1}
@@ -436,21 +465,21 @@ __device__ __forceinline__ void fk_advance(float* AR, float* At, const float* BR
     At[i] = Nt[i];
 }
 
-__device__ __forceinline__ bool pair_hit(const float4& ob, float cx, float cy, float cz, float rs)
+__device__ __forceinline__ bool pair_hit(const float4& ob, float na, const SphereK& k)
 {
-  const float dx = __fsub_rn(ob.x, cx), dy = __fsub_rn(ob.y, cy), dz = __fsub_rn(ob.z, cz);
-  float d2 = __fmul_rn(dx, dx);
-  d2 = __fmaf_rn(dy, dy, d2);
-  d2 = __fmaf_rn(dz, dz, d2);
-  const float rr = __fadd_rn(ob.w, rs);
-  return d2 < __fmul_rn(rr, rr);
+  float t = __fmaf_rn(ob.x, k.c2x, k.B);
+  t = __fmaf_rn(ob.y, k.c2y, t);
+  t = __fmaf_rn(ob.z, k.c2z, t);
+  t = __fmaf_rn(ob.w, k.rs2, t);
+  return t < na;
 }
 
-// G = 1: one lane owns the state, keeps all NRS sphere centres in registers, loops over all
-// obstacles (shared memory broadcast reads).  Returns true when collision free.
+// Lane mode: `nparts` lanes share one state; each keeps all NRS sphere constants in registers and
+// tests them against obstacles part, part+nparts, ... (shared-memory reads: broadcast within a part,
+// consecutive float4 across parts).  Returns this lane's partial "hit"; the caller ORs the parts.
 template <int J, int NRS>
 __device__ __forceinline__ bool arm_check_lane(const ArmSmem& w, uint32_t nrs, uint32_t nobs, const float* qf,
-                                               unsigned long long& pairs)
+                                               uint32_t part, uint32_t nparts, unsigned long long& pairs)
 {
   float cx[NRS], cy[NRS], cz[NRS], rs[NRS];
   int link[NRS];
@@ -459,7 +488,7 @@ __device__ __forceinline__ bool arm_check_lane(const ArmSmem& w, uint32_t nrs, u
   {
     link[k] = (k < (int)nrs) ? w.rs_link[k] : -1;
     rs[k] = (k < (int)nrs) ? w.rs_local[4 * k + 3] : 0.0f;
-    cx[k] = cy[k] = cz[k] = 1.0e18f;  // padding spheres never collide
+    cx[k] = cy[k] = cz[k] = 0.0f;
   }
   float AR[9], At[3], BR[9];
 #pragma unroll
@@ -492,22 +521,32 @@ __device__ __forceinline__ bool arm_check_lane(const ArmSmem& w, uint32_t nrs, u
     if (j < J)
       fk_advance(AR, At, BR, w.joint + 12 * j);
   }
-  bool hit = false;
-  uint32_t o = 0;
-  for (; o < nobs; o++)
-  {
-    const float4 ob = w.obs[o];
+  SphereK sk[NRS];
 #pragma unroll
-    for (int k = 0; k < NRS; k++)
-      hit |= pair_hit(ob, cx[k], cy[k], cz[k], rs[k]);
-    if ((o & 15u) == 15u && hit)
+  for (int k = 0; k < NRS; k++)
+  {
+    sk[k] = sphere_consts(cx[k], cy[k], cz[k], rs[k]);
+    if (k >= (int)nrs)  // padding spheres never collide: t = +huge
     {
-      o++;
-      break;
+      sk[k].c2x = sk[k].c2y = sk[k].c2z = sk[k].rs2 = 0.0f;
+      sk[k].B = 3.0e38f;
     }
   }
-  pairs += (unsigned long long)o * nrs;
-  return !hit;
+  bool hit = false;
+  uint32_t done = 0;
+  for (uint32_t o = part; o < nobs; o += nparts)
+  {
+    const float4 ob = w.obs[o];
+    const float na = w.obs_na[o];
+#pragma unroll
+    for (int k = 0; k < NRS; k++)
+      hit |= pair_hit(ob, na, sk[k]);
+    done++;
+    if ((done & 15u) == 0u && hit)
+      break;
+  }
+  pairs += (unsigned long long)done * nrs;
+  return hit;
 }
 
 // G = 32: the whole warp owns the state.  Lane = (robot sphere k, obstacle slice): every lane runs
@@ -560,13 +599,14 @@ __device__ __forceinline__ bool arm_check_warp(const ArmSmem& w, uint32_t nrs, u
     if (j < J)
       fk_advance(AR, At, BR, w.joint + 12 * j);
   }
-  float c[3] = { 1.0e18f, 1.0e18f, 1.0e18f };
+  float c[3] = { 0.0f, 0.0f, 0.0f };
   float rs = 0.0f;
   if (active)
   {
     mat3_vec(FR, Ft, w.rs_local[4 * k + 0], w.rs_local[4 * k + 1], w.rs_local[4 * k + 2], c);
     rs = w.rs_local[4 * k + 3];
   }
+  const SphereK sk = sphere_consts(c[0], c[1], c[2], rs);
   bool hit = false;
   uint32_t done = 0;
   for (uint32_t o0 = 0; o0 < nobs; o0 += nslices * 8u)
@@ -577,7 +617,7 @@ __device__ __forceinline__ bool arm_check_warp(const ArmSmem& w, uint32_t nrs, u
       const uint32_t o = o0 + u * nslices + slice;
       if (active && o < nobs)
       {
-        hit |= pair_hit(w.obs[o], c[0], c[1], c[2], rs);
+        hit |= pair_hit(w.obs[o], w.obs_na[o], sk);
         done++;
       }
     }
@@ -692,7 +732,8 @@ struct ArmArgs
   uint8_t* ok;
   unsigned long long* first_bad;
   unsigned long long* counters;
-  int mode;  // gc_edge_mode, or 3 = plain state batch
+  int mode;        // gc_edge_mode, or 3 = plain state batch
+  uint32_t lanes;  // lane mode: lanes per state (1, 2, 4, 8)
 };
 
 template <int D>
@@ -709,15 +750,21 @@ __device__ __forceinline__ bool state_conf_rt(int mode, const double* c1, const 
 __device__ __forceinline__ ArmSmem arm_stage(const ArmArgs& a, unsigned char* smem_raw)
 {
   float4* sobs = reinterpret_cast<float4*>(smem_raw);
-  float* sarm = reinterpret_cast<float*>(sobs + a.nobs);
+  float* sna = reinterpret_cast<float*>(sobs + a.nobs);
+  float* sarm = sna + a.nobs;
   const uint32_t arm_words = 12u + 12u * a.njoints + 4u * a.nrs + a.nrs;
   for (uint32_t i = threadIdx.x; i < a.nobs; i += blockDim.x)
-    sobs[i] = reinterpret_cast<const float4*>(a.obs)[i];
+  {
+    const float4 ob = reinterpret_cast<const float4*>(a.obs)[i];
+    sobs[i] = ob;
+    sna[i] = obstacle_na(ob);
+  }
   for (uint32_t i = threadIdx.x; i < arm_words; i += blockDim.x)
     sarm[i] = a.arm[i];
   __syncthreads();
   ArmSmem w;
   w.obs = sobs;
+  w.obs_na = sna;
   w.base = sarm;
   w.joint = sarm + 12;
   w.rs_local = w.joint + 12 * a.njoints;
@@ -740,9 +787,11 @@ __device__ __forceinline__ uint32_t find_edge(const uint32_t* __restrict__ offs,
   return lo;
 }
 
-// a.mode 3 = plain state batch.  G = 1 or 32 lanes per state.  D == njoints.
+// a.mode 3 = plain state batch.  D == njoints.
+// G = 32: a whole warp per state (latency mode).  G = 1: lane mode, a.lanes (1, 2, 4 or 8) lanes per
+// state -- the fewer states a launch has, the more lanes share each one so the machine stays full.
 template <int D, int NRS, int G>
-__global__ void __launch_bounds__(G == 1 ? 128 : 256) arm_state_kernel(ArmArgs a)
+__global__ void __launch_bounds__(G == 1 ? 128 : 256, G == 1 ? (NRS <= 16 ? 4 : 2) : 2) arm_state_kernel(ArmArgs a)
 {
   const int MODE = a.mode;
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -752,8 +801,11 @@ __global__ void __launch_bounds__(G == 1 ? 128 : 256) arm_state_kernel(ArmArgs a
   unsigned long long states = 0, pairs = 0;
   const uint32_t gthread = blockIdx.x * blockDim.x + threadIdx.x;
   const uint32_t nthreads = gridDim.x * blockDim.x;
-  const uint32_t item0 = (G == 1) ? gthread : (gthread >> 5);
-  const uint32_t nitems = (G == 1) ? nthreads : (nthreads >> 5);
+  const uint32_t lps = (G == 1) ? a.lanes : 32u;          // lanes per state
+  const uint32_t part = (G == 1) ? (gthread % lps) : 0u;  // this lane's share of the obstacle cloud
+  const int leader = lane & ~((int)lps - 1);              // first lane of this state's group
+  const uint32_t item0 = gthread / lps;
+  const uint32_t nitems = nthreads / lps;
   // round the trip count up so that every lane of a warp takes part in the warp-wide votes
   const uint32_t trips = (total + nitems - 1) / nitems;
   for (uint32_t it = 0; it < trips; it++)
@@ -761,7 +813,22 @@ __global__ void __launch_bounds__(G == 1 ? 128 : 256) arm_state_kernel(ArmArgs a
     const uint32_t t = item0 + it * nitems;
     bool have = t < total;
     uint32_t e = 0, s = 0;
+    if (have && MODE != 3)
+    {
+      e = find_edge(a.offs, a.n, t);
+      s = t - a.offs[e];
+      // early exit: the reference stops at its first colliding state
+      if (MODE == GC_EDGE_LINEAR)
+        have = !(*reinterpret_cast<volatile unsigned long long*>(a.first_bad + e) < (unsigned long long)s);
+      else
+        have = (*reinterpret_cast<volatile uint8_t*>(a.ok + e) == 1);
+    }
+    // all lanes that share a state must take the same decision (they vote together below)
+    have = __shfl_sync(0xffffffffu, have ? 1 : 0, leader) != 0;
     float qf[D];
+#pragma unroll
+    for (int d = 0; d < D; d++)
+      qf[d] = 0.0f;
     if (have)
     {
       double conf[D];
@@ -774,64 +841,44 @@ __global__ void __launch_bounds__(G == 1 ? 128 : 256) arm_state_kernel(ArmArgs a
       }
       else
       {
-        e = find_edge(a.offs, a.n, t);
-        s = t - a.offs[e];
-        // early exit: the reference stops at its first colliding state
-        if (MODE == GC_EDGE_LINEAR)
-          have = !(a.first_bad[e] < (unsigned long long)s);
-        else
-          have = (*reinterpret_cast<volatile uint8_t*>(a.ok + e) == 1);
-        if (have)
+        double c1[D], c2[D], c3[D];
+#pragma unroll
+        for (int d = 0; d < D; d++)
         {
-          double c1[D], c2[D], c3[D];
-#pragma unroll
-          for (int d = 0; d < D; d++)
-          {
-            c1[d] = a.c1[(size_t)e * D + d];
-            c2[d] = a.c2[(size_t)e * D + d];
-            c3[d] = (MODE == GC_EDGE_FROM_CONF) ? a.c3[(size_t)e * D + d] : 0.0;
-          }
-          EdgeGeom g;
-          g.dist = a.dist[e];
-          g.aux = a.aux[e];
-          g.nstates = a.offs[e + 1] - a.offs[e];
-          have = state_conf_rt<D>(MODE, c1, c2, c3, g, s, conf);
+          c1[d] = a.c1[(size_t)e * D + d];
+          c2[d] = a.c2[(size_t)e * D + d];
+          c3[d] = (MODE == GC_EDGE_FROM_CONF) ? a.c3[(size_t)e * D + d] : 0.0;
         }
+        EdgeGeom g;
+        g.dist = a.dist[e];
+        g.aux = a.aux[e];
+        g.nstates = a.offs[e + 1] - a.offs[e];
+        have = state_conf_rt<D>(MODE, c1, c2, c3, g, s, conf);  // same (e, s) in every lane of the group
       }
+      if (have)
+      {
 #pragma unroll
-      for (int d = 0; d < D; d++)
-        qf[d] = have ? (float)conf[d] : 0.0f;
+        for (int d = 0; d < D; d++)
+          qf[d] = (float)conf[d];
+      }
     }
-    else
-    {
-#pragma unroll
-      for (int d = 0; d < D; d++)
-        qf[d] = 0.0f;
-    }
-    bool free_state = true;
+    bool hit = false;
     if (G == 1)
     {
       if (have)
-      {
-        free_state = arm_check_lane<D, NRS>(w, a.nrs, a.nobs, qf, pairs);
-        states++;
-      }
+        hit = arm_check_lane<D, NRS>(w, a.nrs, a.nobs, qf, part, lps, pairs);
+      // OR over the lanes of the group (all 32 lanes execute the shuffles)
+      for (uint32_t m = 1; m < lps; m <<= 1)
+        hit |= __shfl_xor_sync(0xffffffffu, hit ? 1 : 0, m) != 0;
     }
-    else
+    else if (have)  // warp-uniform
+      hit = !arm_check_warp<D>(w, a.nrs, a.nobs, qf, lane, pairs);
+    if (have && lane == leader)
     {
-      // warp-uniform: 'have' is identical in all lanes (same item)
-      if (have)
-      {
-        free_state = arm_check_warp<D>(w, a.nrs, a.nobs, qf, lane, pairs);
-        if (lane == 0)
-          states++;
-      }
-    }
-    if (have && (G == 1 || lane == 0))
-    {
+      states++;
       if (MODE == 3)
-        a.ok[e] = free_state ? 1 : 0;
-      else if (!free_state)
+        a.ok[e] = hit ? 0 : 1;
+      else if (hit)
       {
         a.ok[e] = 0;
         if (MODE == GC_EDGE_LINEAR && a.first_bad)
@@ -922,7 +969,7 @@ static int launch_light(gc_world* w, const LightArgs& a, cudaStream_t st)
 template <int D, int NRS, int G>
 static int launch_arm(gc_world* w, const ArmArgs& a, uint64_t items_hint, cudaStream_t st)
 {
-  const size_t smem = sizeof(float4) * a.nobs + sizeof(float) * (12 + 12 * a.njoints + 5 * a.nrs) + 16;
+  const size_t smem = (sizeof(float4) + sizeof(float)) * a.nobs + sizeof(float) * (12 + 12 * a.njoints + 5 * a.nrs) + 16;
   if (smem > 200 * 1024)
   {
     gc::set_error("obstacle cloud too large for shared memory staging (%zu bytes)", smem);
@@ -932,7 +979,7 @@ static int launch_arm(gc_world* w, const ArmArgs& a, uint64_t items_hint, cudaSt
     GC_CUDA(cudaFuncSetAttribute(arm_state_kernel<D, NRS, G>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)smem));
   const int threads = (G == 1) ? 128 : 256;
-  const uint64_t items_per_block = (G == 1) ? threads : threads / 32;
+  const uint64_t items_per_block = (G == 1) ? threads / a.lanes : threads / 32;
   uint64_t blocks = (items_hint + items_per_block - 1) / items_per_block;
   const uint64_t max_blocks = (uint64_t)w->sms * ((G == 1) ? 4 : 8);
   if (blocks > max_blocks)
@@ -946,12 +993,22 @@ static int launch_arm(gc_world* w, const ArmArgs& a, uint64_t items_hint, cudaSt
 }
 
 template <int D>
-static int launch_arm_nrs(gc_world* w, const ArmArgs& a, uint64_t items_hint, cudaStream_t st)
+static int launch_arm_nrs(gc_world* w, const ArmArgs& a0, uint64_t items_hint, cudaStream_t st)
 {
-  // lane-per-state only pays off once the flattened work list fills the machine
-  const bool lane_mode = items_hint >= (uint64_t)w->sms * 128u * 2u;
-  if (!lane_mode)
+  // Lane mode keeps every sphere of a state in one thread's registers (no redundant FK); it needs
+  // about one full machine of threads (4 CTAs x 128 threads per SM).  With fewer states, 2/4/8 lanes
+  // share a state; below that a whole warp takes one state (latency mode).
+  ArmArgs a = a0;
+  const uint64_t full = (uint64_t)w->sms * 4u * 128u;
+  if (items_hint * 8u < full / 2u)
+  {
+    a.lanes = 32;
     return launch_arm<D, 16, 32>(w, a, items_hint, st);
+  }
+  uint32_t lanes = 1;
+  while (lanes < 8u && items_hint * lanes < full)
+    lanes <<= 1;
+  a.lanes = lanes;
   if (a.nrs <= 16)
     return launch_arm<D, 16, 1>(w, a, items_hint, st);
   return launch_arm<D, 32, 1>(w, a, items_hint, st);

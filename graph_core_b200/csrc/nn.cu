@@ -285,12 +285,14 @@ __global__ void nn1_finalize_kernel(const double* __restrict__ part_d, const uin
                                     uint32_t chunks, uint32_t nq, uint32_t* __restrict__ idx,
                                     double* __restrict__ dist)
 {
-  uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+  // one warp per query: lanes stride over the chunks, then a shuffle reduction (independent loads in flight)
+  const uint32_t q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
   if (q >= nq)
     return;
   double bd = CUDART_INF;
   uint32_t bi = GC_NO_NODE;
-  for (uint32_t c = 0; c < chunks; c++)
+  for (uint32_t c = lane; c < chunks; c += 32)
   {
     const double d = part_d[(size_t)c * nq + q];
     const uint32_t i = part_i[(size_t)c * nq + q];
@@ -300,8 +302,22 @@ __global__ void nn1_finalize_kernel(const double* __restrict__ part_d, const uin
       bi = i;
     }
   }
-  idx[q] = bi;
-  dist[q] = bd;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1)
+  {
+    const double od = __shfl_xor_sync(0xffffffffu, bd, o);
+    const uint32_t oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    if (oi != GC_NO_NODE && (od < bd || (od == bd && oi < bi)))
+    {
+      bd = od;
+      bi = oi;
+    }
+  }
+  if (lane == 0)
+  {
+    idx[q] = bi;
+    dist[q] = bd;
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -500,7 +516,7 @@ int nn1_dev(gc_store* s, const double* d_q, const uint32_t* d_seg, uint32_t nq, 
   dim3 grid(chunks, groups);
   GC_DISPATCH_DIM(s->dim, (scan_kernel<DD, 0><<<grid, kScanThreads, 0, s->stream>>>(a)));
   GC_CUDA(cudaGetLastError());
-  nn1_finalize_kernel<<<(nq + 127) / 128, 128, 0, s->stream>>>(a.part_d, a.part_i, chunks, nq, d_idx, d_dist);
+  nn1_finalize_kernel<<<(nq + 3) / 4, 128, 0, s->stream>>>(a.part_d, a.part_i, chunks, nq, d_idx, d_dist);
   GC_CUDA(cudaGetLastError());
   count_launch(2);
   return GC_OK;

@@ -55,6 +55,15 @@ enum gc_edge_mode
 #define GC_COS_C2 (-1.388731625493765e-3f)
 #define GC_COS_C3 (2.443315711809948e-5f)
 
+/* ---- sphere pair test of the sphere-arm world (all fp32) --------------------------
+ * robot sphere (c, rs) vs obstacle sphere (o, ro) collide iff |o-c|^2 < (ro+rs)^2, evaluated in the
+ * expanded form (4 fused multiply-adds + 1 compare per pair):
+ *   per obstacle : NA = ro*ro - fma(oz,oz, fma(oy,oy, ox*ox))
+ *   per sphere   : B  = fma(cz,cz, fma(cy,cy, cx*cx)) - rs*rs ;  c2 = -2*c ;  rs2 = -2*rs
+ *   per pair     : t = fma(ro,rs2, fma(oz,c2z, fma(oy,c2y, fma(ox,c2x, B)))) ;  collide iff t < NA
+ * 9 flop per pair (8 in the FMAs + the compare) is the unit of bench.py's FP32 roofline.          */
+#define GC_FLOP_PER_PAIR 9
+
 /* ---- Philox4x32-10 (Salmon et al. 2011) ------------------------------------- */
 #define GC_PHILOX_M0 0xD2511F53u
 #define GC_PHILOX_M1 0xCD9E8D57u

@@ -436,6 +436,7 @@ struct World
   std::vector<int> rs_link;     // [nrs] in [0, J]
   std::vector<float> rs_local;  // [nrs][4] x y z r
   std::vector<float> obs;       // [nobs][4]
+  std::vector<float> obs_na;    // [nobs] ro^2 - |o|^2 (fp32, spec order)
   unsigned long long pair_tests = 0;  // executed sphere-pair tests (for flop accounting)
   unsigned long long state_checks = 0;
 };
@@ -534,16 +535,23 @@ static bool check_sphere_arm(World& w, const double* q)
     float c[3];
     mat3_vec(f, f + 9, &w.rs_local[4 * k], c);
     float rs = w.rs_local[4 * k + 3];
+    // sphere pair test of include/gcb200_spec.h: |o-c|^2 < (ro+rs)^2 expanded to
+    //   B + ox*(-2cx) + oy*(-2cy) + oz*(-2cz) + ro*(-2rs) < ro^2 - |o|^2 ,  B = |c|^2 - rs^2
+    const float c2x = -2.0f * c[0], c2y = -2.0f * c[1], c2z = -2.0f * c[2], rs2 = -2.0f * rs;
+    float n2 = c[0] * c[0];
+    n2 = __builtin_fmaf(c[1], c[1], n2);
+    n2 = __builtin_fmaf(c[2], c[2], n2);
+    const float B = n2 - rs * rs;
     for (int o = 0; o < w.nobs; o++)
     {
       const float* ob = &w.obs[4 * o];
-      float dx = ob[0] - c[0], dy = ob[1] - c[1], dz = ob[2] - c[2];
-      float d2 = dx * dx;
-      d2 = __builtin_fmaf(dy, dy, d2);
-      d2 = __builtin_fmaf(dz, dz, d2);
-      float rr = ob[3] + rs;
+      const float na = w.obs_na[o];
+      float t = __builtin_fmaf(ob[0], c2x, B);
+      t = __builtin_fmaf(ob[1], c2y, t);
+      t = __builtin_fmaf(ob[2], c2z, t);
+      t = __builtin_fmaf(ob[3], rs2, t);
       w.pair_tests++;
-      if (d2 < rr * rr)
+      if (t < na)
       {
         collide = true;
         break;
@@ -1394,6 +1402,15 @@ void* orc_world_sphere_arm(int njoints, const float* base_tf, const float* joint
   w->rs_link.assign(rs_link, rs_link + nrs);
   w->rs_local.assign(rs_local, rs_local + (size_t)4 * nrs);
   w->obs.assign(obs, obs + (size_t)4 * nobs);
+  w->obs_na.resize(nobs);
+  for (int o = 0; o < nobs; o++)
+  {
+    const float* ob = obs + (size_t)4 * o;
+    float on2 = ob[0] * ob[0];
+    on2 = __builtin_fmaf(ob[1], ob[1], on2);
+    on2 = __builtin_fmaf(ob[2], ob[2], on2);
+    w->obs_na[o] = ob[3] * ob[3] - on2;
+  }
   return w;
 }
 void orc_world_free(void* w) { delete (World*)w; }
