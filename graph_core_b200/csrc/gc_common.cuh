@@ -92,6 +92,7 @@ struct gc_store
   cudaStream_t stream = nullptr;
   cudaStream_t own_stream = nullptr;
   int sms = 148;
+  uint32_t near_width_hint = 64;   // columns of the near lists fetched eagerly by gc_extend_batch
   // scratch
   gc::DevBuf d_q, d_seg, d_radius, d_idx, d_dist, d_count, d_part, d_misc, d_rows, d_slots;
   gc::PinBuf h_in, h_out;

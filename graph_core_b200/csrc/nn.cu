@@ -790,8 +790,9 @@ int gc_store_append_multi(gc_store_t* s, const uint32_t* segments, const double*
                                                                     s->dim, s->cap_total + kRowPad, s->x32, s->x64);
   GC_CUDA(cudaGetLastError());
   count_launch();
+  // the host mirror `used` outlives the copy; the pinned staging buffer is protected by the
+  // synchronisation every entry point performs before it refills it, so no trailing sync is needed
   GC_CUDA(cudaMemcpyAsync(s->d_used, s->used.data(), sizeof(uint32_t) * s->nseg, cudaMemcpyHostToDevice, s->stream));
-  GC_CUDA(cudaStreamSynchronize(s->stream));
   return GC_OK;
 }
 

@@ -216,13 +216,37 @@ static int extend_batch_impl(gc_store_t* s, gc_world_t* w, const double* q, cons
   GC_CUDA(cudaMemcpyAsync(h_closest, d_closest, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost, st));
   GC_CUDA(cudaMemcpyAsync(h_next, w->d_c2.p, qb, cudaMemcpyDeviceToHost, st));
   GC_CUDA(cudaMemcpyAsync(h_ok, w->d_ok.p, n, cudaMemcpyDeviceToHost, st));
+  uint32_t width = 0;
   if (radius)
   {
+    // the lists are [n][near_cap] on the device but mostly short: fetch only the first `width` columns
+    // (a guess from the previous call) and the rest only if some list turned out longer
+    width = s->near_width_hint < near_cap ? s->near_width_hint : near_cap;
     GC_CUDA(cudaMemcpyAsync(h_ncount, s->d_count.p, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost, st));
-    GC_CUDA(cudaMemcpyAsync(h_ndist, s->d_dist.p, sizeof(double) * lists, cudaMemcpyDeviceToHost, st));
-    GC_CUDA(cudaMemcpyAsync(h_nidx, s->d_idx.p, sizeof(uint32_t) * lists, cudaMemcpyDeviceToHost, st));
+    GC_CUDA(cudaMemcpy2DAsync(h_ndist, sizeof(double) * near_cap, s->d_dist.p, sizeof(double) * near_cap,
+                              sizeof(double) * width, n, cudaMemcpyDeviceToHost, st));
+    GC_CUDA(cudaMemcpy2DAsync(h_nidx, sizeof(uint32_t) * near_cap, s->d_idx.p, sizeof(uint32_t) * near_cap,
+                              sizeof(uint32_t) * width, n, cudaMemcpyDeviceToHost, st));
   }
   GC_CUDA(cudaStreamSynchronize(st));
+  if (radius)
+  {
+    uint32_t mx = 0;
+    for (uint32_t i = 0; i < n; i++)
+      mx = h_ncount[i] > mx ? h_ncount[i] : mx;
+    const uint32_t need = mx < near_cap ? mx : near_cap;
+    if (need > width)
+    {
+      const uint32_t extra = need - width;
+      GC_CUDA(cudaMemcpy2DAsync(h_ndist + width, sizeof(double) * near_cap, s->d_dist.as<double>() + width,
+                                sizeof(double) * near_cap, sizeof(double) * extra, n, cudaMemcpyDeviceToHost, st));
+      GC_CUDA(cudaMemcpy2DAsync(h_nidx + width, sizeof(uint32_t) * near_cap, s->d_idx.as<uint32_t>() + width,
+                                sizeof(uint32_t) * near_cap, sizeof(uint32_t) * extra, n, cudaMemcpyDeviceToHost, st));
+      GC_CUDA(cudaStreamSynchronize(st));
+    }
+    uint32_t hint = mx + mx / 4 + 8;
+    s->near_width_hint = hint < 32 ? 32 : hint;
+  }
   int rc = GC_OK;
   memcpy(dist, h_dist, sizeof(double) * n);
   memcpy(closest, h_closest, sizeof(uint32_t) * n);

@@ -405,8 +405,15 @@ int LockstepRRTStar::stepImpl(const double* samples, const double* d_samples)
       return fail("gc_extend_batch") ? 0 : -1;
     // samples (host path only) + segment ids + radii in; closest, dist, next, ok and the near lists out
     stats_.h2d_bytes += (uint64_t)rows * ((samples ? sizeof(double) * D_ : 0) + sizeof(uint32_t) + sizeof(double));
-    stats_.d2h_bytes += (uint64_t)rows * (sizeof(uint32_t) + sizeof(double) + sizeof(double) * D_ + 1 + sizeof(uint32_t)) +
-                        (uint64_t)rows * near_cap_ * (sizeof(uint32_t) + sizeof(double));
+    {
+      // the library fetches only as many near-list columns as the longest list needs (about)
+      uint32_t mxc = 0;
+      for (uint32_t i = 0; i < rows; i++)
+        mxc = std::max(mxc, std::min(near_count_[i], near_cap_));
+      stats_.d2h_bytes +=
+          (uint64_t)rows * (sizeof(uint32_t) + sizeof(double) + sizeof(double) * D_ + 1 + sizeof(uint32_t)) +
+          (uint64_t)rows * mxc * (sizeof(uint32_t) + sizeof(double));
+    }
     if (rc != GC_W_TRUNCATED)
       break;
     uint32_t mx = 0;
