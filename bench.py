@@ -265,6 +265,8 @@ def main():
             l0 = g.capi.launch_count()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             barrier()
+            if args.profile:
+                torch.cuda.profiler.start()  # ncu --profile-from-start off: only the timed steps are captured
             t0 = time.time()
             e0.record(stream)
             consumed = 0
@@ -276,6 +278,8 @@ def main():
             e1.record(stream)
             barrier()
             t1 = time.time()
+            if args.profile:
+                torch.cuda.profiler.stop()
         ms = e0.elapsed_time(e1)
         if world_size > 1:
             t = torch.tensor([ms], dtype=torch.float64, device="cuda")

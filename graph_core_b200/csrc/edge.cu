@@ -532,18 +532,42 @@ __device__ __forceinline__ bool arm_check_lane(const ArmSmem& w, uint32_t nrs, u
       sk[k].B = 3.0e38f;
     }
   }
+  // Obstacles part, part+nparts, ...  Any sphere hits obstacle o  <=>  min_k t_k < NA_o, so the sixteen
+  // compares collapse into a min tree (FMNMX3) and ONE compare per obstacle; the next obstacle is
+  // loaded while the current one is evaluated; the early-exit test runs once per 16 obstacles.
+  const uint32_t mycount = (part < nobs) ? (nobs - part + nparts - 1) / nparts : 0u;
   bool hit = false;
   uint32_t done = 0;
-  for (uint32_t o = part; o < nobs; o += nparts)
+  if (mycount)
   {
-    const float4 ob = w.obs[o];
-    const float na = w.obs_na[o];
+    float4 ob = w.obs[part];
+    float na = w.obs_na[part];
+    for (uint32_t base = 0; base < mycount && !hit; base += 16u)
+    {
+      const uint32_t cnt = min(16u, mycount - base);
+#pragma unroll 2
+      for (uint32_t u = 0; u < cnt; u++)
+      {
+        // prefetch the next obstacle of this lane (the last iteration re-reads its own, harmlessly)
+        const uint32_t nx = min(base + u + 1u, mycount - 1u);
+        const float4 ob_n = w.obs[part + nx * nparts];
+        const float na_n = w.obs_na[part + nx * nparts];
+        float m = 3.0e38f;
 #pragma unroll
-    for (int k = 0; k < NRS; k++)
-      hit |= pair_hit(ob, na, sk[k]);
-    done++;
-    if ((done & 15u) == 0u && hit)
-      break;
+        for (int k = 0; k < NRS; k++)
+        {
+          float t = __fmaf_rn(ob.x, sk[k].c2x, sk[k].B);
+          t = __fmaf_rn(ob.y, sk[k].c2y, t);
+          t = __fmaf_rn(ob.z, sk[k].c2z, t);
+          t = __fmaf_rn(ob.w, sk[k].rs2, t);
+          m = fminf(m, t);
+        }
+        hit |= (m < na);
+        ob = ob_n;
+        na = na_n;
+      }
+      done += cnt;
+    }
   }
   pairs += (unsigned long long)done * nrs;
   return hit;
@@ -1005,8 +1029,9 @@ static int launch_arm_nrs(gc_world* w, const ArmArgs& a0, uint64_t items_hint, c
     a.lanes = 32;
     return launch_arm<D, 16, 32>(w, a, items_hint, st);
   }
+  // just enough lanes per state to fill the machine once (every extra lane repeats the FK chain)
   uint32_t lanes = 1;
-  while (lanes < 8u && items_hint * lanes < full)
+  while (lanes < 8u && items_hint * lanes * 2u <= full + full / 4u)
     lanes <<= 1;
   a.lanes = lanes;
   if (a.nrs <= 16)
