@@ -299,8 +299,14 @@ def main():
     val_run = timed_run(device_samples=True)
     if args.profile:
         if rank == 0:
+            vs = val_run["stats"]
+            wc = val_run["world"]
             print(json.dumps({"profile_run": True, "ms_per_step": val_run["ms"] / K,
-                              "value": val_run["consumed"] / (val_run["ms"] * 1e-3)}))
+                              "value": val_run["consumed"] / (val_run["ms"] * 1e-3),
+                              "host_us_per_step": {k[3:]: round(vs[k] / K / 1e3, 1) for k in vs if k.startswith("ns_")},
+                              "edge_kernel_us_per_step": round(wc["kernel_ns"] / K / 1e3, 1),
+                              "edge_tflops": round(FLOP_PER_PAIR * wc["pair_tests"] / max(wc["kernel_ns"], 1) / 1e3, 2),
+                              "edges_per_step": vs["edges_device"] / K, "extended_per_step": vs["extended"] / K}))
         return 0
     e2e_run = timed_run(device_samples=False)
     value = val_run["consumed"] / (val_run["ms"] * 1e-3)
@@ -345,7 +351,8 @@ def main():
     line["step_breakdown"] = {"extended_per_step": vs["extended"] / K, "device_edges_per_step": vs["edges_device"] / K,
                               "edges_used_per_step": vs["edges_used"] / K, "edge_fallbacks": vs["edges_fallback"],
                               "near_hits_per_extension": vs["near_hits"] / max(vs["extended"], 1),
-                              "abi_calls_per_step": vs["gpu_calls"] / K}
+                              "abi_calls_per_step": vs["gpu_calls"] / K,
+                              "host_us_per_step": {k[3:]: vs[k] / K / 1e3 for k in vs if k.startswith("ns_")}}
 
     if rank == 0:
         # ---- in-bench parity check: problem 0 against the oracle on the same samples ----------------

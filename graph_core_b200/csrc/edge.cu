@@ -652,7 +652,16 @@ __device__ __forceinline__ bool arm_check_warp(const ArmSmem& w, uint32_t nrs, u
   return !__any_sync(0xffffffffu, hit);
 }
 
-// ---- plan: per-edge geometry + exclusive prefix sum of the state counts (single CTA) ----------------
+// ---- plan: per-edge geometry + the pass-major work list (single CTA) ---------------------------------
+// The flattened (edge, state) work list is ordered PASS-MAJOR: first the states [0,3) of every edge (both
+// endpoints and the midpoint), then [3,9), [9,33) and finally the fine levels.  A launch walks the list
+// in order, so by the time the fine states of an edge come up its coarse states have usually been
+// evaluated and a collision found there cancels the rest -- the device analogue of the early return
+// of checkConnection (collision_checker_base.h:209-234), whose bisection order exists for that reason.
+constexpr int kPasses = 4;
+__device__ __forceinline__ uint32_t pass_lo(int p) { return p == 0 ? 0u : (p == 1 ? 3u : (p == 2 ? 9u : 33u)); }
+__device__ __forceinline__ uint32_t pass_hi(int p) { return p == 0 ? 3u : (p == 1 ? 9u : (p == 2 ? 33u : 0xffffffffu)); }
+
 struct PlanArgs
 {
   const double* c1;
@@ -662,7 +671,8 @@ struct PlanArgs
   double min_d;
   double* dist;        // [n]
   double* aux;         // [n]
-  uint32_t* offs;      // [n+1] exclusive prefix of nstates
+  uint32_t* nst;       // [n] states of the edge in the reference's visiting order
+  uint32_t* offs;      // [kPasses][n+1] exclusive prefix of the per-pass state counts
   uint8_t* ok;         // initialised here: 1, or 255 when the reference would throw
   unsigned long long* first_bad;
 };
@@ -671,11 +681,11 @@ template <int D, int MODE>
 __global__ void __launch_bounds__(1024) edge_plan_kernel(PlanArgs a)
 {
   __shared__ uint32_t warp_sums[32];
-  __shared__ uint32_t carry_s;
-  if (threadIdx.x == 0)
+  __shared__ uint32_t carry_s[kPasses];
+  if (threadIdx.x < kPasses)
   {
-    carry_s = 0;
-    a.offs[0] = 0;
+    carry_s[threadIdx.x] = 0;
+    a.offs[(size_t)threadIdx.x * (a.n + 1)] = 0;
   }
   __syncthreads();
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -696,44 +706,49 @@ __global__ void __launch_bounds__(1024) edge_plan_kernel(PlanArgs a)
       const EdgeGeom g = edge_geom<D, MODE>(c1, c2, c3, a.min_d);
       a.dist[e] = g.dist;
       a.aux[e] = g.aux;
+      a.nst[e] = g.nstates;
       a.ok[e] = (g.nstates == 0u) ? 255 : 1;
       if (a.first_bad)
         a.first_bad[e] = ~0ull;
       ns = g.nstates;
     }
-    // block-wide inclusive scan
-    uint32_t v = ns;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1)
+    for (int p = 0; p < kPasses; p++)
     {
-      const uint32_t t = __shfl_up_sync(0xffffffffu, v, o);
-      if (lane >= o)
-        v += t;
-    }
-    if (lane == 31)
-      warp_sums[wid] = v;
-    __syncthreads();
-    if (wid == 0)
-    {
-      uint32_t ws = (lane < (int)(blockDim.x >> 5)) ? warp_sums[lane] : 0;
+      const uint32_t lo = pass_lo(p), hi = pass_hi(p);
+      const uint32_t cnt = ns > lo ? (ns < hi ? ns : hi) - lo : 0u;
+      // block-wide inclusive scan
+      uint32_t v = cnt;
 #pragma unroll
       for (int o = 1; o < 32; o <<= 1)
       {
-        const uint32_t t = __shfl_up_sync(0xffffffffu, ws, o);
+        const uint32_t t = __shfl_up_sync(0xffffffffu, v, o);
         if (lane >= o)
-          ws += t;
+          v += t;
       }
-      warp_sums[lane] = ws;
+      if (lane == 31)
+        warp_sums[wid] = v;
+      __syncthreads();
+      if (wid == 0)
+      {
+        uint32_t ws = (lane < (int)(blockDim.x >> 5)) ? warp_sums[lane] : 0;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1)
+        {
+          const uint32_t t = __shfl_up_sync(0xffffffffu, ws, o);
+          if (lane >= o)
+            ws += t;
+        }
+        warp_sums[lane] = ws;
+      }
+      __syncthreads();
+      const uint32_t incl = v + (wid > 0 ? warp_sums[wid - 1] : 0) + carry_s[p];
+      if (e < a.n)
+        a.offs[(size_t)p * (a.n + 1) + e + 1] = incl;
+      __syncthreads();
+      if (threadIdx.x == blockDim.x - 1)
+        carry_s[p] = incl;
+      __syncthreads();
     }
-    __syncthreads();
-    const uint32_t carry = carry_s;
-    const uint32_t incl = v + (wid > 0 ? warp_sums[wid - 1] : 0) + carry;
-    if (e < a.n)
-      a.offs[e + 1] = incl;
-    __syncthreads();
-    if (threadIdx.x == blockDim.x - 1)
-      carry_s = incl;
-    __syncthreads();
   }
 }
 
@@ -752,7 +767,8 @@ struct ArmArgs
   uint32_t n;
   const double* dist;
   const double* aux;
-  const uint32_t* offs;
+  const uint32_t* nst;
+  const uint32_t* offs;  // [kPasses][n+1], see edge_plan_kernel
   uint8_t* ok;
   unsigned long long* first_bad;
   unsigned long long* counters;
@@ -821,7 +837,13 @@ __global__ void __launch_bounds__(G == 1 ? 128 : 256, G == 1 ? (NRS <= 16 ? 4 : 
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const ArmSmem w = arm_stage(a, smem_raw);
   const int lane = threadIdx.x & 31;
-  const uint32_t total = (MODE == 3) ? a.n : a.offs[a.n];
+  // pass bases of the pass-major work list
+  uint32_t pbase[kPasses + 1];
+  pbase[0] = 0;
+#pragma unroll
+  for (int p = 0; p < kPasses; p++)
+    pbase[p + 1] = pbase[p] + ((MODE == 3) ? 0u : a.offs[(size_t)p * (a.n + 1) + a.n]);
+  const uint32_t total = (MODE == 3) ? a.n : pbase[kPasses];
   unsigned long long states = 0, pairs = 0;
   const uint32_t gthread = blockIdx.x * blockDim.x + threadIdx.x;
   const uint32_t nthreads = gridDim.x * blockDim.x;
@@ -839,8 +861,11 @@ __global__ void __launch_bounds__(G == 1 ? 128 : 256, G == 1 ? (NRS <= 16 ? 4 : 
     uint32_t e = 0, s = 0;
     if (have && MODE != 3)
     {
-      e = find_edge(a.offs, a.n, t);
-      s = t - a.offs[e];
+      const int p = (t >= pbase[1]) + (t >= pbase[2]) + (t >= pbase[3]);
+      const uint32_t* offs_p = a.offs + (size_t)p * (a.n + 1);
+      const uint32_t tp = t - pbase[p];
+      e = find_edge(offs_p, a.n, tp);
+      s = pass_lo(p) + (tp - offs_p[e]);
       // early exit: the reference stops at its first colliding state
       if (MODE == GC_EDGE_LINEAR)
         have = !(*reinterpret_cast<volatile unsigned long long*>(a.first_bad + e) < (unsigned long long)s);
@@ -876,7 +901,7 @@ __global__ void __launch_bounds__(G == 1 ? 128 : 256, G == 1 ? (NRS <= 16 ? 4 : 
         EdgeGeom g;
         g.dist = a.dist[e];
         g.aux = a.aux[e];
-        g.nstates = a.offs[e + 1] - a.offs[e];
+        g.nstates = a.nst[e];
         have = state_conf_rt<D>(MODE, c1, c2, c3, g, s, conf);  // same (e, s) in every lane of the group
       }
       if (have)
@@ -1029,10 +1054,18 @@ static int launch_arm_nrs(gc_world* w, const ArmArgs& a0, uint64_t items_hint, c
     a.lanes = 32;
     return launch_arm<D, 16, 32>(w, a, items_hint, st);
   }
-  // just enough lanes per state to fill the machine once (every extra lane repeats the FK chain)
-  uint32_t lanes = 1;
-  while (lanes < 8u && items_hint * lanes * 2u <= full + full / 4u)
-    lanes <<= 1;
+  // Several lanes per state (each repeats the cheap FK chain): the launch then walks the pass-major
+  // list in several rounds, which is what lets a collision in a coarse pass cancel the fine passes.
+  uint32_t lanes = 8;
+  if (a.mode == 3)  // plain state batch: no early exit to gain, just fill the machine once
+  {
+    lanes = 1;
+    while (lanes < 8u && items_hint * lanes * 2u <= full + full / 4u)
+      lanes <<= 1;
+  }
+  else
+    while (lanes > 1u && items_hint * lanes > 16u * full)
+      lanes >>= 1;
   a.lanes = lanes;
   if (a.nrs <= 16)
     return launch_arm<D, 16, 1>(w, a, items_hint, st);
@@ -1112,7 +1145,7 @@ int check_edges_dev(gc_world* w, const double* d_c1, const double* d_c2, const d
   else
   {
     GC_TRY(w->d_plan.reserve(sizeof(double) * 2 * (size_t)n));
-    GC_TRY(w->d_offs.reserve(sizeof(uint32_t) * ((size_t)n + 1)));
+    GC_TRY(w->d_offs.reserve(sizeof(uint32_t) * (kPasses * ((size_t)n + 1) + n)));
     PlanArgs p{};
     p.c1 = d_c1;
     p.c2 = d_c2;
@@ -1122,6 +1155,7 @@ int check_edges_dev(gc_world* w, const double* d_c1, const double* d_c2, const d
     p.dist = w->d_plan.as<double>();
     p.aux = p.dist + n;
     p.offs = w->d_offs.as<uint32_t>();
+    p.nst = p.offs + kPasses * ((size_t)n + 1);
     p.ok = d_ok;
     p.first_bad = reinterpret_cast<unsigned long long*>(d_first_bad);
     ArmArgs a{};
@@ -1137,6 +1171,7 @@ int check_edges_dev(gc_world* w, const double* d_c1, const double* d_c2, const d
     a.dist = p.dist;
     a.aux = p.aux;
     a.offs = p.offs;
+    a.nst = p.nst;
     a.ok = d_ok;
     a.first_bad = p.first_bad;
     a.counters = w->d_counters;

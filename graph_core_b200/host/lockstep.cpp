@@ -3,6 +3,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <cmath>
 #include <condition_variable>
 #include <cstring>
@@ -341,10 +342,16 @@ int LockstepRRTStar::setStream(void* cuda_stream)
   return 0;
 }
 
+static inline double secs_since(std::chrono::steady_clock::time_point t0)
+{
+  return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+}
+
 int LockstepRRTStar::stepImpl(const double* samples, const double* d_samples)
 {
   if (!store_)
     return -1;
+  auto tp = std::chrono::steady_clock::now();
   const uint32_t n = (uint32_t)P_.size();
   // ---- A: RRTStar::update prologue (rrt_star.cpp:93-108) ----------------------------------------
   uint32_t rows = 0;
@@ -381,6 +388,8 @@ int LockstepRRTStar::stepImpl(const double* samples, const double* d_samples)
   }
   if (rows == 0)
     return 0;
+  stats_.t_phase[0] += secs_since(tp);
+  tp = std::chrono::steady_clock::now();
   stats_.iterations += rows;
   // ---- B: nearest + steer + edge check + radius-near, one stream-ordered device pass ------------
   closest_.resize(rows);
@@ -422,6 +431,8 @@ int LockstepRRTStar::stepImpl(const double* samples, const double* d_samples)
     while (near_cap_ < mx)
       near_cap_ *= 2;
   }
+  stats_.t_phase[1] += secs_since(tp);
+  tp = std::chrono::steady_clock::now();
   // ---- C: extension bookkeeping + speculative edge sets (per problem, in parallel) --------------
   pool_->parallel_for(rows, [&](uint32_t r) {
     Problem& pr = P_[act[r]];
@@ -482,6 +493,8 @@ int LockstepRRTStar::stepImpl(const double* samples, const double* d_samples)
       pr.edge_count++;
     }
   });
+  stats_.t_phase[2] += secs_since(tp);
+  tp = std::chrono::steady_clock::now();
   // ---- D: append the new nodes, evaluate every candidate edge in one batch -----------------------
   uint32_t nedges = 0, napp = 0;
   for (uint32_t r = 0; r < rows; r++)
@@ -553,6 +566,8 @@ int LockstepRRTStar::stepImpl(const double* samples, const double* d_samples)
     stats_.h2d_bytes += (uint64_t)nedges * 2 * sizeof(double) * D_;
     stats_.d2h_bytes += nedges;
   }
+  stats_.t_phase[3] += secs_since(tp);
+  tp = std::chrono::steady_clock::now();
   // ---- E: sequential replay of rewireOnly + the solver epilogue (per problem, in parallel) -------
   std::vector<uint8_t> goal_joined(rows, 0);
   std::vector<uint32_t> used(rows, 0), fallback(rows, 0), hits(rows, 0);
@@ -694,6 +709,7 @@ int LockstepRRTStar::stepImpl(const double* samples, const double* d_samples)
       return fail("gc_store_append_multi") ? 0 : -1;
     stats_.gpu_calls++;
   }
+  stats_.t_phase[4] += secs_since(tp);
   return (int)rows;
 }
 
@@ -855,7 +871,7 @@ int gcp_rrtstar_solution(gcp_rrtstar_t* s, uint32_t p, int32_t* ids, uint32_t ca
   return (int)sol.size();
 }
 
-int gcp_rrtstar_stats(gcp_rrtstar_t* s, uint64_t out[10])
+int gcp_rrtstar_stats(gcp_rrtstar_t* s, uint64_t out[16])
 {
   if (!s || !out)
     return GC_E_INVALID;
@@ -870,6 +886,8 @@ int gcp_rrtstar_stats(gcp_rrtstar_t* s, uint64_t out[10])
   out[7] = st.h2d_bytes;
   out[8] = st.d2h_bytes;
   out[9] = 0;
+  for (int i = 0; i < 5; i++)
+    out[10 + i] = (uint64_t)(st.t_phase[i] * 1e9);
   return GC_OK;
 }
 

@@ -44,6 +44,9 @@ struct StepStats
   uint64_t gpu_calls = 0;    // C-ABI calls that launch kernels
   uint64_t h2d_bytes = 0;    // payload bytes handed to / received from the C ABI (host buffers)
   uint64_t d2h_bytes = 0;
+  // host wall-clock per phase of step(): prologue | fused device pass | candidate sets | append + edge
+  // batch | replay
+  double t_phase[5] = { 0, 0, 0, 0, 0 };
 };
 
 class ThreadPool;
@@ -150,6 +153,6 @@ int gcp_rrtstar_info(gcp_rrtstar_t* s, uint32_t p, int32_t* solved, int32_t* can
                      double* radius, uint32_t* num_nodes, uint32_t* tree_size);
 int gcp_rrtstar_dump(gcp_rrtstar_t* s, uint32_t p, int32_t* parents, double* pcost, double* conf);
 int gcp_rrtstar_solution(gcp_rrtstar_t* s, uint32_t p, int32_t* ids, uint32_t cap);
-int gcp_rrtstar_stats(gcp_rrtstar_t* s, uint64_t out[10]);
+int gcp_rrtstar_stats(gcp_rrtstar_t* s, uint64_t out[16]);
 const char* gcp_last_error(void);
 }

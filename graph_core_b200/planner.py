@@ -142,8 +142,9 @@ class LockstepRRTStar:
         return ids[:n].copy()
 
     def stats(self):
-        out = (C.c_uint64 * 10)()
+        out = (C.c_uint64 * 16)()
         self.L.gcp_rrtstar_stats(self.h, out)
         keys = ["iterations", "extended", "edges_device", "edges_used", "edges_fallback", "near_hits", "gpu_calls",
-                "h2d_bytes", "d2h_bytes"]
+                "h2d_bytes", "d2h_bytes", "_", "ns_prologue", "ns_fused_pass", "ns_candidates", "ns_append_edges",
+                "ns_replay"]
         return dict(zip(keys, [int(v) for v in out]))
