@@ -97,9 +97,30 @@ def build_host(force: bool = False, verbose: bool = False) -> Path | None:
     return HOSTLIB
 
 
+def build_probe(force: bool = False, verbose: bool = False) -> Path | None:
+    """Compile tests/cpp/plugin_probe.cpp (C++ exerciser of the plugin classes) against the host library."""
+    src = ROOT / "tests" / "cpp" / "plugin_probe.cpp"
+    if not src.exists():
+        return None
+    out = ROOT / "tests" / "cpp" / "plugin_probe"
+    hostlib = build_host(force=False, verbose=verbose)
+    headers = sorted(HOST.rglob("*.h")) + sorted((ROOT / "include").glob("*.h"))
+    if not force and _newer(out, [src, hostlib] + headers):
+        return out
+    cxx = shutil.which("g++") or "g++"
+    cmd = [cxx, "-std=c++17", "-O2", "-fno-fast-math", "-ffp-contract=off", "-I", str(ROOT / "include"), "-I", str(HOST),
+           "-o", str(out), str(src), "-L", str(PKG), "-lgcb200_host", "-lgcb200", "-pthread",
+           "-Wl,-rpath," + str(PKG), "-Wl,-rpath,$ORIGIN/../../graph_core_b200"]
+    if verbose:
+        print(" ".join(cmd), flush=True)
+    _run(cmd)
+    return out
+
+
 def build_all(force: bool = False, verbose: bool = False) -> None:
     build_cuda(force, verbose)
     build_host(force, verbose)
+    build_probe(force, verbose)
 
 
 if __name__ == "__main__":
