@@ -113,15 +113,15 @@ def make_samples(sc, problems, iters, seed0=30200):
     return W.uniform_samples(sc.lb, sc.ub, seed0, 0, iters * problems).reshape(iters, problems, sc.dim)
 
 
-def cuda_checker(world_cache={}):
+def cuda_checker(device=0, world_cache={}):
     """State checker backed by the CUDA world (product path) for problem selection."""
     import graph_core_b200 as g
 
     def chk(params, q):
-        key = id(params["obs"])
+        key = (id(params["obs"]), device)
         if key not in world_cache:
             world_cache[key] = g.CollisionWorld.sphere_arm(params["base_tf"], params["joint_tf"], params["rs_link"],
-                                                           params["rs_local"], params["obs"])
+                                                           params["rs_local"], params["obs"], device)
         return world_cache[key].check(q).astype(bool)
 
     return chk
@@ -223,9 +223,9 @@ def main():
         torch.cuda.synchronize()
 
     P = args.problems
-    sc = W.scenario_c3(1000, cuda_checker())
+    sc = W.scenario_c3(1000, cuda_checker(dev))
     # rank r plans problems [r*P, (r+1)*P) of the shared stream: independent queries, no data-path collective
-    pairs = W.c3_problems(cuda_checker(), sc.params, P * world_size)[rank * P:(rank + 1) * P]
+    pairs = W.c3_problems(cuda_checker(dev), sc.params, P * world_size)[rank * P:(rank + 1) * P]
     starts = np.array([s for s, _ in pairs])
     goals = np.array([gl for _, gl in pairs])
     iters = W_ + K

@@ -71,7 +71,7 @@ def build_cuda(force: bool = False, verbose: bool = False) -> Path:
     with ThreadPoolExecutor(max_workers=min(8, len(sources))) as ex:
         objs = list(ex.map(compile_one, sources))
     cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", str(LIB), *map(str, objs),
-           "--cudart=static"]
+           "--cudart=static", "-ldl"]
     if verbose:
         print(" ".join(cmd), flush=True)
     _run(cmd)

@@ -1,4 +1,6 @@
 // common.cu -- error string, scratch buffers, device info for the C ABI (include/gcb200.h)
+#include <dlfcn.h>
+
 #include <atomic>
 
 #include "gc_common.cuh"
@@ -13,6 +15,34 @@ void set_error(const char* fmt, ...)
   va_start(ap, fmt);
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
+}
+
+typedef int (*ctx_get_fn)(void**);
+typedef int (*ctx_set_fn)(void*);
+static ctx_get_fn g_ctx_get = nullptr;
+static ctx_set_fn g_ctx_set = nullptr;
+static void load_driver_once()
+{
+  static bool tried = false;
+  if (tried)
+    return;
+  tried = true;
+  void* h = dlopen("libcuda.so.1", RTLD_NOW | RTLD_GLOBAL);
+  if (!h)
+    return;
+  g_ctx_get = reinterpret_cast<ctx_get_fn>(dlsym(h, "cuCtxGetCurrent"));
+  g_ctx_set = reinterpret_cast<ctx_set_fn>(dlsym(h, "cuCtxSetCurrent"));
+}
+CtxGuard::CtxGuard()
+{
+  load_driver_once();
+  if (g_ctx_get && g_ctx_set)
+    have = (g_ctx_get(&prev) == 0);
+}
+CtxGuard::~CtxGuard()
+{
+  if (have && prev)  // nothing to restore when the caller had no context yet
+    g_ctx_set(prev);
 }
 
 int DevBuf::reserve(size_t bytes)
@@ -148,7 +178,7 @@ int gc_launch_count(uint64_t* count)
 int gc_measure_fp32_peak(int device, double* tflops, double* sm_mhz_estimate)
 {
   GC_REQUIRE(tflops != nullptr, "gc_measure_fp32_peak: NULL");
-  GC_CUDA(cudaSetDevice(device));
+  GC_SET_DEVICE(device);
   const int sms = gc::num_sms(device);
   float* d_out = nullptr;
   GC_CUDA(cudaMalloc(&d_out, sizeof(float)));
@@ -182,7 +212,7 @@ int gc_measure_fp32_peak(int device, double* tflops, double* sm_mhz_estimate)
 
 int gc_flush_l2(int device, size_t bytes)
 {
-  GC_CUDA(cudaSetDevice(device));
+  GC_SET_DEVICE(device);
   static void* buf = nullptr;
   static size_t cap = 0;
   if (bytes > cap)

@@ -1239,7 +1239,7 @@ static int world_new(int kind, int dim, int device, gc_world** out)
   int ndev = 0;
   GC_TRY(gc_device_count(&ndev));
   GC_REQUIRE(device >= 0 && device < ndev, "gc_world_create: device %d of %d (no CPU fallback exists)", device, ndev);
-  GC_CUDA(cudaSetDevice(device));
+  GC_SET_DEVICE(device);
   gc_world* w = new gc_world();
   w->device = device;
   w->kind = kind;
@@ -1360,6 +1360,7 @@ int gc_world_destroy(gc_world_t* w)
     return GC_OK;
   if (--w->refs > 0)
     return GC_OK;
+  gc::CtxGuard gc_ctx_guard_;
   cudaSetDevice(w->device);
   if (w->own_stream)
     cudaStreamSynchronize(w->own_stream);
@@ -1388,7 +1389,7 @@ int gc_world_dim(gc_world_t* w) { return w ? w->dim : GC_E_INVALID; }
 int gc_world_counters(gc_world_t* w, uint64_t out[4])
 {
   GC_REQUIRE(w && out, "gc_world_counters: NULL");
-  GC_CUDA(cudaSetDevice(w->device));
+  GC_SET_DEVICE(w->device);
   unsigned long long c[2];
   GC_CUDA(cudaStreamSynchronize(w->stream));
   GC_CUDA(cudaMemcpy(c, w->d_counters, sizeof(c), cudaMemcpyDeviceToHost));
@@ -1402,7 +1403,7 @@ int gc_world_counters(gc_world_t* w, uint64_t out[4])
 int gc_world_reset_counters(gc_world_t* w)
 {
   GC_REQUIRE(w != nullptr, "gc_world_reset_counters: NULL");
-  GC_CUDA(cudaSetDevice(w->device));
+  GC_SET_DEVICE(w->device);
   GC_CUDA(cudaStreamSynchronize(w->stream));
   GC_CUDA(cudaMemset(w->d_counters, 0, 2 * sizeof(unsigned long long)));
   GC_TRY(gc::resolve_timing(w));
@@ -1420,7 +1421,7 @@ int gc_world_enable_timing(gc_world_t* w, int on)
 int gc_check_states_dev(gc_world_t* w, const double* d_q, uint32_t n, uint8_t* d_ok)
 {
   GC_REQUIRE(w && d_q && d_ok, "gc_check_states_dev: NULL argument");
-  GC_CUDA(cudaSetDevice(w->device));
+  GC_SET_DEVICE(w->device);
   return check_states_dev(w, d_q, n, d_ok, w->stream);
 }
 
@@ -1430,7 +1431,7 @@ int gc_check_edges_dev(gc_world_t* w, const double* d_c1, const double* d_c2, ui
   GC_REQUIRE(w && d_c1 && d_c2 && d_ok, "gc_check_edges_dev: NULL argument");
   GC_REQUIRE(mode == GC_EDGE_BISECT || mode == GC_EDGE_LINEAR, "gc_check_edges_dev: mode %d", mode);
   GC_REQUIRE(mode != GC_EDGE_LINEAR || d_first_bad, "gc_check_edges_dev: LINEAR mode needs first_bad");
-  GC_CUDA(cudaSetDevice(w->device));
+  GC_SET_DEVICE(w->device);
   return check_edges_dev(w, d_c1, d_c2, nullptr, n, min_distance, mode, d_ok, d_first_bad, (uint64_t)n * 64u,
                          w->stream);
 }
@@ -1440,7 +1441,7 @@ int gc_check_states(gc_world_t* w, const double* q, uint32_t n, uint8_t* ok)
   GC_REQUIRE(w && q && ok, "gc_check_states: NULL argument");
   if (n == 0)
     return GC_OK;
-  GC_CUDA(cudaSetDevice(w->device));
+  GC_SET_DEVICE(w->device);
   const size_t qb = sizeof(double) * (size_t)n * w->dim;
   GC_TRY(w->h_in.reserve(qb));
   GC_TRY(w->h_out.reserve(n));
@@ -1481,7 +1482,7 @@ static int check_edges_host(gc_world* w, const double* c1, const double* c2, con
   if (n == 0)
     return GC_OK;
   GC_REQUIRE(min_distance > 0.0, "min_distance must be > 0 (got %g)", min_distance);
-  GC_CUDA(cudaSetDevice(w->device));
+  GC_SET_DEVICE(w->device);
   const size_t qb = sizeof(double) * (size_t)n * w->dim;
   const int narr = c3 ? 3 : 2;
   GC_TRY(w->h_in.reserve(qb * narr));

@@ -41,6 +41,23 @@ void set_error(const char* fmt, ...);
       return r_;       \
   } while (0)
 
+// ---- current-context guard ---------------------------------------------------------------------------
+// libgcb200.so links the CUDA runtime statically; a host process usually also carries another runtime
+// instance (PyTorch's).  Both share the driver's per-thread "current context", so a cudaSetDevice() in
+// here could silently redirect the other runtime's next allocation to our device.  Every C-ABI entry
+// therefore restores the caller's driver context on exit (cuCtxGetCurrent / cuCtxSetCurrent looked up
+// with dlsym, so the library still loads on a machine without libcuda for symbol checks).
+struct CtxGuard
+{
+  void* prev = nullptr;
+  bool have = false;
+  CtxGuard();
+  ~CtxGuard();
+};
+#define GC_SET_DEVICE(dev)     \
+  gc::CtxGuard gc_ctx_guard_;  \
+  GC_CUDA(::cudaSetDevice(dev))
+
 // ---- grow-only device / pinned scratch ---------------------------------------------------------
 struct DevBuf
 {
@@ -93,6 +110,8 @@ struct gc_store
   cudaStream_t own_stream = nullptr;
   int sms = 148;
   uint32_t near_width_hint = 64;   // columns of the near lists fetched eagerly by gc_extend_batch
+  uint32_t knn_cand_scale = 3;     // head-room factor of the large-N k-nearest candidate lists
+  gc::DevBuf d_cand_idx, d_cand_dist, d_cand_count, d_thr;
   // scratch
   gc::DevBuf d_q, d_seg, d_radius, d_idx, d_dist, d_count, d_part, d_misc, d_rows, d_slots;
   gc::PinBuf h_in, h_out;

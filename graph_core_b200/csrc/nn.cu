@@ -88,6 +88,7 @@ struct ScanArgs
   const double* q;         // [nq][D]
   const uint32_t* seg;     // [nq] or nullptr (segment 0)
   const double* radius;    // MODE 1
+  const float* thr2;       // MODE 2: per-query squared fp32 candidate threshold
   uint32_t nq;
   uint32_t group_size;     // queries per group (kQT when seg == nullptr, else 1)
   uint32_t cap_seg;
@@ -139,6 +140,8 @@ __global__ void __launch_bounds__(kScanThreads, 2) scan_kernel(ScanArgs a)
       float rf = (r > 0.0) ? (float)fmin(r, 1.0e18) : -1.0f;
       thr_s[tid] = (rf < 0.0f) ? -1.0f : slack_thr2(rf * (1.0f + 1.0e-6f), a.slack_abs);
     }
+    if (MODE == 2 && tid < qcount)
+      thr_s[tid] = a.thr2[q0 + tid];  // squared fp32 candidate threshold (already widened by the slack)
   }
   __syncthreads();
 
@@ -257,7 +260,8 @@ __global__ void __launch_bounds__(kScanThreads, 2) scan_kernel(ScanArgs a)
             if (d2[q][r] <= thr_s[q])
             {
               const double e = dist64<D>(a.x64 + (seg_base + local0 + r) * D, qs64[q]);
-              if (e < a.radius[q0 + q])  // strict, vector.cpp:75 / kdtree.cpp:167
+              // MODE 1: strict radius test (vector.cpp:75 / kdtree.cpp:167); MODE 2: every candidate is kept
+              if (MODE == 2 || e < a.radius[q0 + q])
               {
                 const uint32_t pos = atomicAdd(&a.out_count[q0 + q], 1u);
                 if (pos < a.cap)
@@ -435,6 +439,288 @@ __global__ void __launch_bounds__(1024, 1)
 }
 
 // ---------------------------------------------------------------------------------------------
+// k-nearest over segments larger than one CTA can sort (BASELINE config 4: 2^20 nodes):
+//   1. knn_sample_kernel : exact k-th smallest fp32 distance over a 16384-node SAMPLE of the segment.
+//      The sample is a subset, so its k-th smallest is an upper bound of the segment's k-th smallest:
+//      every true k-nearest node lies under the (slack-widened) threshold.
+//   2. scan_kernel<MODE 2>: one brute-force pass collecting the nodes under the threshold with their
+//      exact fp64 distances (a few k entries per query instead of N).
+//   3. select_topk_kernel: exact radix select of the k smallest (dist64, slot) keys, then a sort.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void bitonic_sort_keys(float* key, uint32_t P)
+{
+  for (uint32_t k = 2; k <= P; k <<= 1)
+    for (uint32_t j = k >> 1; j > 0; j >>= 1)
+    {
+      for (uint32_t i = threadIdx.x; i < P; i += blockDim.x)
+      {
+        const uint32_t ixj = i ^ j;
+        if (ixj > i)
+        {
+          const float ka = key[i], kb = key[ixj];
+          if ((ka > kb) == ((i & k) == 0))
+          {
+            key[i] = kb;
+            key[ixj] = ka;
+          }
+        }
+      }
+      __syncthreads();
+    }
+}
+
+// sample slot i of a segment with n_s used slots: everything when n_s <= kSortMax, else 16 evenly
+// spread contiguous blocks of 1024 slots (coalesced reads, spread over the insertion order)
+__device__ __forceinline__ uint32_t sample_slot(uint32_t i, uint32_t n_s)
+{
+  if (n_s <= kSortMax)
+    return i;
+  const uint32_t b = i >> 10, o = i & 1023u;
+  return b * (n_s / 16u) + o;
+}
+
+template <int D>
+__global__ void __launch_bounds__(1024, 1)
+    knn_sample_kernel(const float* __restrict__ x32, const uint32_t* __restrict__ used, const double* __restrict__ qd,
+                      const uint32_t* __restrict__ segs, uint32_t cap_seg, size_t row_stride, unsigned long long k,
+                      float slack_abs, float* __restrict__ thr2_out)
+{
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float* key = reinterpret_cast<float*>(smem_raw);
+  __shared__ float qs[D];
+  __shared__ uint32_t live_s;
+  const uint32_t q = blockIdx.x;
+  const uint32_t seg = segs ? segs[q] : 0u;
+  const uint32_t n_s = used[seg];
+  const size_t seg_base = (size_t)seg * cap_seg;
+  if (threadIdx.x < D)
+    qs[threadIdx.x] = (float)qd[(size_t)q * D + threadIdx.x];
+  if (threadIdx.x == 0)
+    live_s = 0;
+  __syncthreads();
+  const uint32_t m = n_s < kSortMax ? n_s : kSortMax;
+  uint32_t p2 = 2;
+  while (p2 < m)
+    p2 <<= 1;
+  uint32_t my_live = 0;
+  for (uint32_t i = threadIdx.x; i < p2; i += blockDim.x)
+  {
+    float acc = CUDART_INF_F;
+    if (i < m)
+    {
+      const size_t slot = seg_base + sample_slot(i, n_s);
+      acc = 0.0f;
+#pragma unroll
+      for (int d = 0; d < D; d++)
+      {
+        const float t = x32[(size_t)d * row_stride + slot] - qs[d];
+        acc = fmaf(t, t, acc);
+      }
+      if (acc < CUDART_INF_F)
+        my_live++;
+      else
+        acc = CUDART_INF_F;  // tombstone (x32[0] = +inf) or NaN
+    }
+    key[i] = acc;
+  }
+  if (my_live)
+    atomicAdd(&live_s, my_live);
+  __syncthreads();
+  bitonic_sort_keys(key, p2);
+  if (threadIdx.x == 0)
+  {
+    float thr = FLT_MAX;  // fewer than k live nodes in the sample: no bound, collect everything
+    if (k >= 1 && k <= (unsigned long long)live_s)
+      thr = slack_thr2(sqrtf(key[k - 1]) * (1.0f + 1.0e-6f), slack_abs);
+    thr2_out[q] = thr;
+  }
+}
+
+// block-wide exact radix select: returns (in shared result slots) the value of the k-th smallest key
+// among the items i < n for which pred(i) holds; keys are unsigned 64-bit.  k is 1-based, k <= #pred.
+template <typename KeyFn, typename PredFn>
+__device__ __forceinline__ unsigned long long radix_select(uint32_t n, unsigned long long k, int bytes, KeyFn keyf,
+                                                           PredFn pred, uint32_t* hist, unsigned long long* sh,
+                                                           unsigned long long* k_rest)
+{
+  unsigned long long prefix = 0, mask = 0;
+  for (int r = bytes - 1; r >= 0; r--)
+  {
+    for (uint32_t i = threadIdx.x; i < 256; i += blockDim.x)
+      hist[i] = 0;
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x)
+      if (pred(i))
+      {
+        const unsigned long long key = keyf(i);
+        if ((key & mask) == prefix)
+          atomicAdd(&hist[(uint32_t)(key >> (8 * r)) & 255u], 1u);
+      }
+    __syncthreads();
+    if (threadIdx.x == 0)
+    {
+      unsigned long long cum = 0;
+      uint32_t d = 0;
+      for (; d < 255; d++)
+      {
+        if (cum + hist[d] >= k)
+          break;
+        cum += hist[d];
+      }
+      sh[0] = (unsigned long long)d;
+      sh[1] = k - cum;
+    }
+    __syncthreads();
+    prefix |= sh[0] << (8 * r);
+    mask |= 0xffull << (8 * r);
+    k = sh[1];
+    __syncthreads();
+  }
+  *k_rest = k;  // how many items with exactly this key are needed
+  return prefix;
+}
+
+// lists [nq][cap] with counts -> the k smallest (dist, slot) per query, ascending, into [nq][out_cap]
+__global__ void __launch_bounds__(1024, 1)
+    select_topk_kernel(const uint32_t* __restrict__ idx, const double* __restrict__ dist,
+                       const uint32_t* __restrict__ count, uint32_t cap, unsigned long long k, uint32_t out_cap,
+                       uint32_t* __restrict__ out_idx, double* __restrict__ out_dist, uint32_t* __restrict__ out_count,
+                       uint32_t* __restrict__ err_flag, uint32_t P)
+{
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double* skey = reinterpret_cast<double*>(smem_raw);
+  uint32_t* sval = reinterpret_cast<uint32_t*>(skey + P);
+  __shared__ uint32_t hist[256];
+  __shared__ unsigned long long sh[2];
+  __shared__ uint32_t npicked;
+  const uint32_t q = blockIdx.x;
+  uint32_t n = count[q];
+  if (n > cap)
+  {
+    if (threadIdx.x == 0)
+      atomicOr(err_flag, 1u);  // the candidate list overflowed: the caller retries with a larger one
+    n = cap;
+  }
+  const uint32_t* li = idx + (size_t)q * cap;
+  const double* ld = dist + (size_t)q * cap;
+  const uint32_t want = (k < (unsigned long long)n) ? (uint32_t)k : n;
+  uint32_t m = 0;  // entries staged in shared memory
+  if (n <= P)
+  {
+    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x)
+    {
+      skey[i] = ld[i];
+      sval[i] = li[i];
+    }
+    m = n;
+  }
+  else
+  {
+    // exact k-th smallest distance, then the slot rank among equal distances
+    unsigned long long need_eq = 0, need_slot = 0;
+    const unsigned long long kth = radix_select(
+        n, want, 8, [&](uint32_t i) { return (unsigned long long)__double_as_longlong(ld[i]); },
+        [&](uint32_t) { return true; }, hist, sh, &need_eq);
+    const unsigned long long slot_max = radix_select(
+        n, need_eq, 4, [&](uint32_t i) { return (unsigned long long)li[i]; },
+        [&](uint32_t i) { return (unsigned long long)__double_as_longlong(ld[i]) == kth; }, hist, sh, &need_slot);
+    if (threadIdx.x == 0)
+      npicked = 0;
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x)
+    {
+      const unsigned long long key = (unsigned long long)__double_as_longlong(ld[i]);
+      if (key < kth || (key == kth && (unsigned long long)li[i] <= slot_max))
+      {
+        const uint32_t pos = atomicAdd(&npicked, 1u);
+        if (pos < P)
+        {
+          skey[pos] = ld[i];
+          sval[pos] = li[i];
+        }
+      }
+    }
+    __syncthreads();
+    m = npicked < P ? npicked : P;
+  }
+  uint32_t p2 = 2;
+  while (p2 < m)
+    p2 <<= 1;
+  for (uint32_t i = m + threadIdx.x; i < p2; i += blockDim.x)
+  {
+    skey[i] = CUDART_INF;
+    sval[i] = GC_NO_NODE;
+  }
+  __syncthreads();
+  bitonic_sort(skey, sval, p2);
+  for (uint32_t i = threadIdx.x; i < (want < out_cap ? want : out_cap); i += blockDim.x)
+  {
+    out_idx[(size_t)q * out_cap + i] = sval[i];
+    out_dist[(size_t)q * out_cap + i] = skey[i];
+  }
+  if (threadIdx.x == 0)
+    out_count[q] = want;
+}
+
+// Node-sharded trees: node i lives on shard i mod G at local slot i div G.  After the
+// all-gather of the per-shard lists this merges them: global slot = local * G + g, ascending (dist, slot),
+// first k_out entries.  parts are [G][nq][cap] / [G][nq].
+__global__ void __launch_bounds__(1024, 1)
+    merge_shard_lists_kernel(const uint32_t* __restrict__ idx, const double* __restrict__ dist,
+                             const uint32_t* __restrict__ count, uint32_t G, uint32_t nq, uint32_t cap,
+                             unsigned long long k_out, uint32_t out_cap, uint32_t* __restrict__ out_idx,
+                             double* __restrict__ out_dist, uint32_t* __restrict__ out_count, uint32_t P)
+{
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double* skey = reinterpret_cast<double*>(smem_raw);
+  uint32_t* sval = reinterpret_cast<uint32_t*>(skey + P);
+  __shared__ uint32_t total_s;
+  const uint32_t q = blockIdx.x;
+  if (threadIdx.x == 0)
+    total_s = 0;
+  __syncthreads();
+  for (uint32_t g = 0; g < G; g++)
+  {
+    const uint32_t n = min(count[(size_t)g * nq + q], cap);
+    __shared__ uint32_t base_s;
+    if (threadIdx.x == 0)
+    {
+      base_s = total_s;
+      total_s += n;
+    }
+    __syncthreads();
+    const uint32_t base = base_s;
+    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x)
+      if (base + i < P)
+      {
+        const uint32_t local = idx[((size_t)g * nq + q) * cap + i];
+        skey[base + i] = dist[((size_t)g * nq + q) * cap + i];
+        sval[base + i] = (local == GC_NO_NODE) ? GC_NO_NODE : local * G + g;
+      }
+    __syncthreads();
+  }
+  const uint32_t m = min(total_s, P);
+  uint32_t p2 = 2;
+  while (p2 < m)
+    p2 <<= 1;
+  for (uint32_t i = m + threadIdx.x; i < p2; i += blockDim.x)
+  {
+    skey[i] = CUDART_INF;
+    sval[i] = GC_NO_NODE;
+  }
+  __syncthreads();
+  bitonic_sort(skey, sval, p2);
+  const uint32_t want = (k_out < (unsigned long long)m) ? (uint32_t)k_out : m;
+  for (uint32_t i = threadIdx.x; i < min(want, out_cap); i += blockDim.x)
+  {
+    out_idx[(size_t)q * out_cap + i] = sval[i];
+    out_dist[(size_t)q * out_cap + i] = skey[i];
+  }
+  if (threadIdx.x == 0)
+    out_count[q] = want;
+}
+
+// ---------------------------------------------------------------------------------------------
 // dispatch helpers
 // ---------------------------------------------------------------------------------------------
 #define GC_DISPATCH_DIM(dim, ...)                                  \
@@ -579,6 +865,97 @@ int radius_dev(gc_store* s, const double* d_q, const uint32_t* d_seg, const doub
   return sort_lists(s, nq, cap, d_idx, d_dist, d_count);
 }
 
+// sample threshold -> one collecting scan -> exact select (see the kernels above).  Queries are processed in
+// chunks so that the candidate lists stay under ~256 MiB.  Returns GC_E_CAPACITY after a synchronisation
+// when a candidate list overflowed its estimate (the caller retries with s->knn_cand_scale doubled).
+static int knn_large_dev(gc_store* s, const double* d_q, const uint32_t* d_seg, uint32_t nq, uint64_t k, uint32_t cap,
+                         uint32_t* d_idx, double* d_dist, uint32_t* d_count)
+{
+  if (k > kSortMax)
+  {
+    gc::set_error("gc_knn: k = %llu above %u on a segment larger than %u slots is not supported yet",
+                  (unsigned long long)k, kSortMax, kSortMax);
+    return GC_E_UNSUPPORTED;
+  }
+  if (k == 0)
+  {
+    GC_CUDA(cudaMemsetAsync(d_count, 0, sizeof(uint32_t) * nq, s->stream));
+    return GC_OK;
+  }
+  const uint32_t mu = max_used(s);
+  // expected candidates per query: k * N / sample size; scale leaves room for sampling noise
+  uint64_t est = (uint64_t)k * ((mu + kSortMax - 1) / kSortMax) * s->knn_cand_scale + 1024u;
+  if (est > mu)
+    est = mu;
+  const uint32_t capB = (uint32_t)est;
+  uint32_t qchunk = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(nq, (256ull << 20) / ((uint64_t)capB * 12ull)));
+  GC_TRY(s->d_cand_idx.reserve(sizeof(uint32_t) * (size_t)qchunk * capB));
+  GC_TRY(s->d_cand_dist.reserve(sizeof(double) * (size_t)qchunk * capB));
+  GC_TRY(s->d_cand_count.reserve(sizeof(uint32_t) * ((size_t)qchunk + 4)));
+  GC_TRY(s->d_thr.reserve(sizeof(float) * nq));
+  uint32_t* d_err = s->d_cand_count.as<uint32_t>() + qchunk;
+  GC_CUDA(cudaMemsetAsync(d_err, 0, sizeof(uint32_t), s->stream));
+  const size_t row_stride = s->cap_total + kRowPad;
+  const float slack = (float)(store_slack(s) * 1.0000001) + FLT_MIN;
+  const size_t smem_sample = sizeof(float) * kSortMax;
+  GC_DISPATCH_DIM(s->dim,
+                  GC_CUDA(cudaFuncSetAttribute(knn_sample_kernel<DD>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                               (int)smem_sample));
+                  knn_sample_kernel<DD><<<nq, 1024, smem_sample, s->stream>>>(
+                      s->x32, s->d_used, d_q, d_seg, s->cap_seg, row_stride, (unsigned long long)k, slack,
+                      s->d_thr.as<float>()));
+  GC_CUDA(cudaGetLastError());
+  count_launch();
+  const size_t smem_sel = (size_t)kSortMax * (sizeof(double) + sizeof(uint32_t));
+  GC_CUDA(cudaFuncSetAttribute(select_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_sel));
+  for (uint32_t q0 = 0; q0 < nq; q0 += qchunk)
+  {
+    const uint32_t nqc = std::min(qchunk, nq - q0);
+    GC_CUDA(cudaMemsetAsync(s->d_cand_count.p, 0, sizeof(uint32_t) * nqc, s->stream));
+    uint32_t groups, gsz, chunks;
+    scan_grid(s, nqc, d_seg != nullptr, &groups, &gsz, &chunks);
+    ScanArgs a{};
+    a.x32 = s->x32;
+    a.x64 = s->x64;
+    a.used = s->d_used;
+    a.q = d_q + (size_t)q0 * s->dim;
+    a.seg = d_seg ? d_seg + q0 : nullptr;
+    a.thr2 = s->d_thr.as<float>() + q0;
+    a.nq = nqc;
+    a.group_size = gsz;
+    a.cap_seg = s->cap_seg;
+    a.row_stride = row_stride;
+    a.slack_abs = slack;
+    a.cap = capB;
+    a.out_idx = s->d_cand_idx.as<uint32_t>();
+    a.out_dist = s->d_cand_dist.as<double>();
+    a.out_count = s->d_cand_count.as<uint32_t>();
+    dim3 grid(chunks, groups);
+    GC_DISPATCH_DIM(s->dim, (scan_kernel<DD, 2><<<grid, kScanThreads, 0, s->stream>>>(a)));
+    GC_CUDA(cudaGetLastError());
+    select_topk_kernel<<<nqc, 1024, smem_sel, s->stream>>>(a.out_idx, a.out_dist, a.out_count, capB,
+                                                           (unsigned long long)k, cap, d_idx + (size_t)q0 * cap,
+                                                           d_dist + (size_t)q0 * cap, d_count + q0, d_err, kSortMax);
+    GC_CUDA(cudaGetLastError());
+    count_launch(2);
+  }
+  // overflow check (one word): the estimate is generous, so this almost never fires
+  uint32_t err = 0;
+  GC_CUDA(cudaMemcpyAsync(&err, d_err, sizeof(uint32_t), cudaMemcpyDeviceToHost, s->stream));
+  GC_CUDA(cudaStreamSynchronize(s->stream));
+  if (err)
+  {
+    if (capB >= mu)
+    {
+      gc::set_error("gc_knn: candidate list overflow with a full-size list (internal error)");
+      return GC_E_INVALID;
+    }
+    s->knn_cand_scale *= 2;
+    return GC_E_CAPACITY;
+  }
+  return GC_OK;
+}
+
 int knn_dev(gc_store* s, const double* d_q, const uint32_t* d_seg, uint32_t nq, uint64_t k, uint32_t cap,
             uint32_t* d_idx, double* d_dist, uint32_t* d_count)
 {
@@ -588,8 +965,11 @@ int knn_dev(gc_store* s, const double* d_q, const uint32_t* d_seg, uint32_t nq, 
   const uint32_t mu = max_used(s);
   if (mu > kSortMax)
   {
-    gc::set_error("gc_knn: segments above %u slots need the large-N selection path (not built yet)", kSortMax);
-    return GC_E_UNSUPPORTED;
+    int rc;
+    do
+      rc = knn_large_dev(s, d_q, d_seg, nq, k, cap, d_idx, d_dist, d_count);
+    while (rc == GC_E_CAPACITY);
+    return rc;
   }
   uint32_t P = 2;
   while (P < mu)
@@ -629,7 +1009,7 @@ int gc_store_create(int dim, uint32_t capacity_per_segment, uint32_t n_segments,
   int ndev = 0;
   GC_TRY(gc_device_count(&ndev));
   GC_REQUIRE(device >= 0 && device < ndev, "gc_store_create: device %d of %d (no CPU fallback exists)", device, ndev);
-  GC_CUDA(cudaSetDevice(device));
+  GC_SET_DEVICE(device);
   gc_store* s = new gc_store();
   s->device = device;
   s->dim = dim;
@@ -672,6 +1052,7 @@ int gc_store_destroy(gc_store_t* s)
 {
   if (!s)
     return GC_OK;
+  gc::CtxGuard gc_ctx_guard_;
   cudaSetDevice(s->device);
   if (s->own_stream)
     cudaStreamSynchronize(s->own_stream);
@@ -681,6 +1062,7 @@ int gc_store_destroy(gc_store_t* s)
   s->d_q.release(); s->d_seg.release(); s->d_radius.release(); s->d_idx.release(); s->d_dist.release();
   s->d_count.release(); s->d_part.release(); s->d_misc.release(); s->d_rows.release(); s->d_slots.release();
   s->h_in.release(); s->h_out.release();
+  s->d_cand_idx.release(); s->d_cand_dist.release(); s->d_cand_count.release(); s->d_thr.release();
   if (s->own_stream)
     cudaStreamDestroy(s->own_stream);
   delete s;
@@ -720,7 +1102,7 @@ int gc_store_append(gc_store_t* s, uint32_t segment, const double* q, uint32_t n
     gc::set_error("gc_store_append: segment %u full (%u + %u > %u)", segment, s->used[segment], n, s->cap_seg);
     return GC_E_CAPACITY;
   }
-  GC_CUDA(cudaSetDevice(s->device));
+  GC_SET_DEVICE(s->device);
   const size_t bytes = sizeof(double) * (size_t)n * s->dim;
   GC_TRY(s->h_in.reserve(bytes));
   GC_TRY(s->d_rows.reserve(bytes));
@@ -752,7 +1134,7 @@ int gc_store_append_multi(gc_store_t* s, const uint32_t* segments, const double*
   GC_REQUIRE(s && q && segments, "gc_store_append_multi: NULL argument");
   if (n == 0)
     return GC_OK;
-  GC_CUDA(cudaSetDevice(s->device));
+  GC_SET_DEVICE(s->device);
   const size_t bytes = sizeof(double) * (size_t)n * s->dim;
   const size_t sbytes = align_up(sizeof(uint32_t) * n, 16);
   GC_TRY(s->h_in.reserve(bytes + sbytes));
@@ -800,7 +1182,7 @@ static int poke_row0(gc_store* s, uint32_t segment, uint32_t slot, bool tombston
 {
   GC_REQUIRE(s != nullptr, "NULL store");
   GC_REQUIRE(segment < s->nseg && slot < s->used[segment], "slot %u of segment %u is not in use", slot, segment);
-  GC_CUDA(cudaSetDevice(s->device));
+  GC_SET_DEVICE(s->device);
   const size_t g = (size_t)segment * s->cap_seg + slot;
   float v;
   if (tombstone)
@@ -834,7 +1216,7 @@ int gc_store_clear(gc_store_t* s, uint32_t segment)
 {
   GC_REQUIRE(s != nullptr, "gc_store_clear: NULL store");
   GC_REQUIRE(segment == GC_NO_NODE || segment < s->nseg, "gc_store_clear: segment %u of %u", segment, s->nseg);
-  GC_CUDA(cudaSetDevice(s->device));
+  GC_SET_DEVICE(s->device);
   for (uint32_t g = 0; g < s->nseg; g++)
     if (segment == GC_NO_NODE || segment == g)
     {
@@ -864,7 +1246,7 @@ int gc_store_read(gc_store_t* s, uint32_t segment, uint32_t first_slot, uint32_t
              first_slot + n, s->used[segment]);
   if (n == 0)
     return GC_OK;
-  GC_CUDA(cudaSetDevice(s->device));
+  GC_SET_DEVICE(s->device);
   const size_t g = (size_t)segment * s->cap_seg + first_slot;
   GC_CUDA(cudaMemcpyAsync(q_out, s->x64 + g * s->dim, sizeof(double) * (size_t)n * s->dim, cudaMemcpyDeviceToHost,
                           s->stream));
@@ -878,22 +1260,52 @@ int gc_store_read(gc_store_t* s, uint32_t segment, uint32_t first_slot, uint32_t
 int gc_nn1_dev(gc_store_t* s, const double* d_q, const uint32_t* d_seg, uint32_t nq, uint32_t* d_idx, double* d_dist)
 {
   GC_REQUIRE(s && d_q && d_idx && d_dist, "gc_nn1_dev: NULL argument");
-  GC_CUDA(cudaSetDevice(s->device));
+  GC_SET_DEVICE(s->device);
   return nn1_dev(s, d_q, d_seg, nq, d_idx, d_dist, false);
 }
 int gc_radius_dev(gc_store_t* s, const double* d_q, const uint32_t* d_seg, const double* d_radius, uint32_t nq,
                   uint32_t cap, uint32_t* d_idx, double* d_dist, uint32_t* d_count)
 {
   GC_REQUIRE(s && d_q && d_radius && d_idx && d_dist && d_count, "gc_radius_dev: NULL argument");
-  GC_CUDA(cudaSetDevice(s->device));
+  GC_SET_DEVICE(s->device);
   return radius_dev(s, d_q, d_seg, d_radius, nq, cap, d_idx, d_dist, d_count);
 }
 int gc_knn_dev(gc_store_t* s, const double* d_q, const uint32_t* d_seg, uint32_t nq, uint64_t k, uint32_t cap,
                uint32_t* d_idx, double* d_dist, uint32_t* d_count)
 {
   GC_REQUIRE(s && d_q && d_idx && d_dist && d_count, "gc_knn_dev: NULL argument");
-  GC_CUDA(cudaSetDevice(s->device));
+  GC_SET_DEVICE(s->device);
   return knn_dev(s, d_q, d_seg, nq, k, cap, d_idx, d_dist, d_count);
+}
+
+int gc_merge_shard_lists_dev(int device, void* cuda_stream, uint32_t n_shards, uint32_t nq, uint32_t cap,
+                             const uint32_t* d_idx, const double* d_dist, const uint32_t* d_count, uint64_t k_out,
+                             uint32_t out_cap, uint32_t* d_out_idx, double* d_out_dist, uint32_t* d_out_count)
+{
+  GC_REQUIRE(d_idx && d_dist && d_count && d_out_idx && d_out_dist && d_out_count, "gc_merge_shard_lists_dev: NULL");
+  GC_REQUIRE(n_shards >= 1 && cap >= 1 && out_cap >= 1, "gc_merge_shard_lists_dev: empty shape");
+  if (nq == 0)
+    return GC_OK;
+  uint32_t P = 2;
+  while (P < n_shards * cap)
+    P <<= 1;
+  if (P > kSortMax)
+  {
+    gc::set_error("gc_merge_shard_lists_dev: %u shards x %u entries exceed the %u-entry merge buffer", n_shards, cap,
+                  kSortMax);
+    return GC_E_UNSUPPORTED;
+  }
+  GC_SET_DEVICE(device);
+  const size_t smem = (size_t)P * (sizeof(double) + sizeof(uint32_t));
+  GC_CUDA(cudaFuncSetAttribute(merge_shard_lists_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               (int)(kSortMax * (sizeof(double) + sizeof(uint32_t)))));
+  const int threads = P >= 2048 ? 1024 : (P >= 512 ? 256 : 64);
+  merge_shard_lists_kernel<<<nq, threads, smem, reinterpret_cast<cudaStream_t>(cuda_stream)>>>(
+      d_idx, d_dist, d_count, n_shards, nq, cap, (unsigned long long)k_out, out_cap, d_out_idx, d_out_dist,
+      d_out_count, P);
+  GC_CUDA(cudaGetLastError());
+  count_launch();
+  return GC_OK;
 }
 
 // stage host queries (and optional per-query segments / radii) on the device
@@ -932,7 +1344,7 @@ int gc_nn1(gc_store_t* s, const double* q, const uint32_t* seg, uint32_t nq, uin
   GC_REQUIRE(s && q && idx && dist, "gc_nn1: NULL argument");
   if (nq == 0)
     return GC_OK;
-  GC_CUDA(cudaSetDevice(s->device));
+  GC_SET_DEVICE(s->device);
   GC_TRY(stage_queries(s, q, seg, nullptr, nq));
   GC_TRY(s->d_idx.reserve(sizeof(uint32_t) * nq));
   GC_TRY(s->d_dist.reserve(sizeof(double) * nq));
@@ -980,7 +1392,7 @@ int gc_radius(gc_store_t* s, const double* q, const uint32_t* seg, const double*
   GC_REQUIRE(s && q && radius && idx && dist && count, "gc_radius: NULL argument");
   if (nq == 0)
     return GC_OK;
-  GC_CUDA(cudaSetDevice(s->device));
+  GC_SET_DEVICE(s->device);
   GC_TRY(stage_queries(s, q, seg, radius, nq));
   const size_t n = (size_t)nq * cap;
   GC_TRY(s->d_idx.reserve(sizeof(uint32_t) * n));
@@ -997,7 +1409,7 @@ int gc_knn(gc_store_t* s, const double* q, const uint32_t* seg, uint32_t nq, uin
   GC_REQUIRE(s && q && idx && dist && count, "gc_knn: NULL argument");
   if (nq == 0)
     return GC_OK;
-  GC_CUDA(cudaSetDevice(s->device));
+  GC_SET_DEVICE(s->device);
   GC_TRY(stage_queries(s, q, seg, nullptr, nq));
   const size_t n = (size_t)nq * cap;
   GC_TRY(s->d_idx.reserve(sizeof(uint32_t) * n));

@@ -127,7 +127,7 @@ static int extend_batch_impl(gc_store_t* s, gc_world_t* w, const double* q, cons
   GC_REQUIRE(max_distance > 0.0 && min_distance > 0.0, "gc_extend_batch: distances must be > 0");
   if (n == 0)
     return GC_OK;
-  GC_CUDA(cudaSetDevice(s->device));
+  GC_SET_DEVICE(s->device);
   const int D = s->dim;
   cudaStream_t st = s->stream;
   const size_t qb = sizeof(double) * (size_t)n * D;
@@ -302,7 +302,7 @@ int gc_sample_uniform_dev(int device, int dim, const double* lb, const double* u
   GC_REQUIRE(dim >= 1 && dim <= GC_MAX_DIM, "gc_sample_uniform_dev: dim %d", dim);
   if (n == 0)
     return GC_OK;
-  GC_CUDA(cudaSetDevice(device));
+  GC_SET_DEVICE(device);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(cuda_stream);
   double* d_b = nullptr;
   GC_CUDA(cudaMalloc(&d_b, sizeof(double) * 2 * dim));
@@ -333,7 +333,7 @@ int gc_sample_uniform(int device, int dim, const double* lb, const double* ub, u
   int ndev = 0;
   GC_TRY(gc_device_count(&ndev));
   GC_REQUIRE(device >= 0 && device < ndev, "gc_sample_uniform: device %d of %d", device, ndev);
-  GC_CUDA(cudaSetDevice(device));
+  GC_SET_DEVICE(device);
   double *d_b = nullptr, *d_out = nullptr;
   GC_CUDA(cudaMalloc(&d_b, sizeof(double) * 2 * dim));
   cudaError_t e = cudaMalloc(&d_out, sizeof(double) * (size_t)n * dim);

@@ -1,0 +1,139 @@
+"""Node-sharded nearest-neighbour queries over the GPUs of one box (BASELINE config 4).
+
+One process per GPU (torch.distributed, NCCL over NVLink/NVSwitch).  Node i of the logical tree lives on
+shard i mod G at local slot i div G, so shards stay balanced under incremental appends and the reference's
+"lowest index wins" tie rule survives: global slot = local * G + shard.  Every rank holds the same queries,
+answers them on its slice with the ordinary CUDA kernels (gc_nn1_dev / gc_knn_dev / gc_radius_dev), the
+per-shard lists are exchanged with ONE all-gather, and every rank merges them on its device
+(gc_merge_shard_lists_dev) into the list a single store would have returned: ascending (dist, global slot).
+
+The exchange step is the only collective; bytes per rank = nq * cap * 12 + nq * 4.
+
+`engine` / `merge` are injectable so that the partition + gather + index logic can be exercised on CPU
+with the gloo backend (tests/test_sharded_cpu.py); the product path uses CudaShardEngine.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from . import capi
+
+NO_NODE = 0xFFFFFFFF
+
+
+class CudaShardEngine:
+    """The local slice: a NodeStore driven through the device-pointer C ABI with torch-owned buffers."""
+
+    def __init__(self, dim: int, capacity: int, device: int):
+        self.dim = dim
+        self.device = device
+        self.torch_device = torch.device("cuda", device)
+        self.store = capi.NodeStore(dim, capacity, 1, device)
+        self.lib = capi.load()
+        self.store.set_stream(torch.cuda.current_stream(self.torch_device).cuda_stream)
+
+    def append(self, rows: np.ndarray):
+        if len(rows):
+            self.store.append(rows)
+
+    def _q(self, q: np.ndarray) -> torch.Tensor:
+        return torch.from_numpy(np.ascontiguousarray(q, dtype=np.float64)).to(self.torch_device)
+
+    def _out(self, nq, cap):
+        idx = torch.full((nq, cap), -1, dtype=torch.int32, device=self.torch_device)  # 0xFFFFFFFF = no node
+        dd = torch.full((nq, cap), float("inf"), dtype=torch.float64, device=self.torch_device)
+        cnt = torch.zeros(nq, dtype=torch.int32, device=self.torch_device)
+        return idx, dd, cnt
+
+    def nearest_lists(self, q):
+        dq = self._q(q)
+        nq = dq.shape[0]
+        idx, dd, cnt = self._out(nq, 1)
+        capi._check(self.lib.gc_nn1_dev(self.store.handle, dq.data_ptr(), None, nq, idx.data_ptr(), dd.data_ptr()))
+        cnt.copy_((idx[:, 0] != -1).to(torch.int32))
+        return idx, dd, cnt
+
+    def knn_lists(self, q, k):
+        dq = self._q(q)
+        nq = dq.shape[0]
+        idx, dd, cnt = self._out(nq, k)
+        capi._check(self.lib.gc_knn_dev(self.store.handle, dq.data_ptr(), None, nq, k, k, idx.data_ptr(), dd.data_ptr(),
+                                        cnt.data_ptr()))
+        return idx, dd, cnt
+
+    def near_lists(self, q, radius, cap):
+        dq = self._q(q)
+        nq = dq.shape[0]
+        r = torch.full((nq,), float(radius), dtype=torch.float64, device=self.torch_device)
+        idx, dd, cnt = self._out(nq, cap)
+        capi._check(self.lib.gc_radius_dev(self.store.handle, dq.data_ptr(), None, r.data_ptr(), nq, cap,
+                                           idx.data_ptr(), dd.data_ptr(), cnt.data_ptr()))
+        return idx, dd, cnt
+
+    def merge(self, idx, dd, cnt, k_out, out_cap):
+        G, nq, cap = idx.shape
+        oi = torch.full((nq, out_cap), -1, dtype=torch.int32, device=self.torch_device)
+        od = torch.full((nq, out_cap), float("inf"), dtype=torch.float64, device=self.torch_device)
+        oc = torch.zeros(nq, dtype=torch.int32, device=self.torch_device)
+        stream = torch.cuda.current_stream(self.torch_device).cuda_stream
+        capi._check(self.lib.gc_merge_shard_lists_dev(self.device, stream, G, nq, cap, idx.data_ptr(), dd.data_ptr(),
+                                                      cnt.data_ptr(), k_out, out_cap, oi.data_ptr(), od.data_ptr(),
+                                                      oc.data_ptr()))
+        return oi, od, oc
+
+
+class ShardedNodeStore:
+    """Logical tree of N nodes sharded round-robin over the ranks of `group`."""
+
+    def __init__(self, dim: int, capacity_total: int, engine=None, group=None, device: int | None = None):
+        self.group = group
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.dim = dim
+        self.n_global = 0
+        if engine is None:
+            if device is None:
+                device = torch.cuda.current_device()
+            engine = CudaShardEngine(dim, (capacity_total + self.world - 1) // self.world + 1, device)
+        self.engine = engine
+
+    # ---- partition -------------------------------------------------------------------------------
+    def owner_of(self, global_slot):
+        return global_slot % self.world
+
+    def append(self, rows):
+        """Every rank passes the same rows; each keeps the ones it owns.  Returns the first global slot."""
+        rows = np.ascontiguousarray(rows, dtype=np.float64).reshape(-1, self.dim)
+        first = self.n_global
+        g = np.arange(first, first + len(rows))
+        self.engine.append(rows[g % self.world == self.rank])
+        self.n_global += len(rows)
+        return first
+
+    # ---- exchange + merge --------------------------------------------------------------------------
+    def _gather(self, t: torch.Tensor) -> torch.Tensor:
+        if self.world == 1:
+            return t.unsqueeze(0)
+        t = t.contiguous()
+        out = torch.empty((self.world * t.shape[0],) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+        dist.all_gather_into_tensor(out, t, group=self.group)  # rank-major concatenation along dim 0
+        return out.view((self.world,) + tuple(t.shape))
+
+    def _exchange(self, lists, k_out, out_cap):
+        idx, dd, cnt = lists
+        return self.engine.merge(self._gather(idx), self._gather(dd), self._gather(cnt), k_out, out_cap)
+
+    def nearest(self, q):
+        """(global slot [nq], dist [nq]); NO_NODE / inf when the tree is empty."""
+        oi, od, oc = self._exchange(self.engine.nearest_lists(q), 1, 1)
+        return oi[:, 0], od[:, 0]
+
+    def knn(self, q, k: int):
+        """(global slots [nq,k], dists [nq,k], counts [nq]) ascending (dist, global slot)."""
+        return self._exchange(self.engine.knn_lists(q, k), k, k)
+
+    def near(self, q, radius: float, cap: int = 256):
+        """Radius-near; a shard list that overflows `cap` shows up as count > cap on that shard."""
+        return self._exchange(self.engine.near_lists(q, radius, cap), self.world * cap, self.world * cap)

@@ -99,6 +99,15 @@ int gc_radius_dev(gc_store_t* s, const double* d_q, const uint32_t* d_seg, const
 int gc_knn_dev(gc_store_t* s, const double* d_q, const uint32_t* d_seg, uint32_t nq, uint64_t k, uint32_t cap,
                uint32_t* d_idx, double* d_dist, uint32_t* d_count);
 
+/* Node-sharded trees over G GPUs (one process per GPU): node i lives on shard i mod G at local slot
+ * i div G; every shard answers the same queries on its slice (gc_nn1_dev with cap 1, gc_knn_dev,
+ * gc_radius_dev).  After an all-gather of the per-shard lists ([G][nq][cap] and [G][nq], e.g.
+ * torch.distributed.all_gather_into_tensor over NCCL) this merges them on the device: global slot =
+ * local*G + shard, ascending (dist, global slot), first k_out entries per query.  G*cap <= 16384.   */
+int gc_merge_shard_lists_dev(int device, void* cuda_stream, uint32_t n_shards, uint32_t nq, uint32_t cap,
+                             const uint32_t* d_idx, const double* d_dist, const uint32_t* d_count, uint64_t k_out,
+                             uint32_t out_cap, uint32_t* d_out_idx, double* d_out_dist, uint32_t* d_out_count);
+
 /* ---- collision worlds (check(q) of collision_checker_base.h:166) --------------------------- */
 int gc_world_create_cube(int dim, double threshold, int device, gc_world_t** out);
 int gc_world_create_boxes(int dim, uint32_t n, const double* lo, const double* hi, int device, gc_world_t** out);

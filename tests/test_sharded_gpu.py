@@ -1,0 +1,105 @@
+"""GPU tests of the large-N k-nearest path (sample threshold -> collecting scan -> exact radix select)
+and of the node-sharded merge (gc_merge_shard_lists_dev).  On the single GPU the driver's `-m gpu` run
+has, G shards are emulated as G stores in one process: the per-shard kernels, the global-slot arithmetic
+and the merge kernel are exactly what every rank of a multi-GPU run executes; the all-gather itself is
+covered by tests/test_sharded_cpu.py (gloo) and tools/sharded_check.py (NCCL, torchrun)."""
+import numpy as np
+import pytest
+import torch
+
+from graph_core_b200 import worlds as W
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("n,dim,k", [(20000, 12, 1), (50000, 12, 64), (70001, 7, 1024), (40000, 3, 2500)])
+def test_knn_large_tree_matches_vector(gc, orc, n, dim, k):
+    pts = W.c4_nodes(n, dim, seed=91)
+    qs = W.c4_queries(12, dim, seed=92)
+    st = gc.NodeStore(dim, n)
+    st.append(pts)
+    ov = orc.OracleNN("vector", dim)
+    ov.insert(pts)
+    gi, gd, gcnt = st.knn(qs, k, cap=k)
+    oi, od, oc = ov.knn(qs, k, k)
+    assert np.array_equal(gcnt.astype(np.int64), oc.astype(np.int64))
+    assert np.array_equal(gi.astype(np.int64), oi.astype(np.int64))
+    assert np.array_equal(gd, od)
+
+
+def test_knn_large_tree_duplicates_and_tombstones(gc, orc):
+    # many exactly equal distances across the k-th rank: the slot order decides (vector.cpp:83-96)
+    base = W.c4_nodes(6000, 5, seed=93)
+    pts = np.vstack([base, base, base, base])  # every configuration four times -> 24000 nodes
+    st = gc.NodeStore(5, len(pts))
+    st.append(pts)
+    ok = orc.OracleNN("kdtree", 5)
+    ok.insert(pts)
+    ov = orc.OracleNN("vector", 5)
+    ov.insert(pts)
+    qs = np.vstack([base[:4], W.c4_queries(4, 5, seed=94)])
+    for k in (2, 6, 50):
+        gi, gd, gcnt = st.knn(qs, k, cap=k)
+        oi, od, oc = ov.knn(qs, k, k)
+        assert np.array_equal(gi.astype(np.int64), oi.astype(np.int64)) and np.array_equal(gd, od)
+    dead = sorted(set(ov.knn(qs, 3, 3)[0].ravel().tolist()))
+    for s in dead:
+        st.tombstone(s)
+        ov.delete(s)
+    # after the deletions the Vector oracle has re-numbered its nodes: compare through configurations
+    gi, gd, gcnt = st.knn(qs, 20, cap=20)
+    oi, od, oc = ov.knn(qs, 20, 20)
+    assert np.array_equal(gd, od)
+    assert not np.isin(gi, dead).any()
+
+
+@pytest.mark.parametrize("G", [2, 4, 8])
+def test_sharded_merge_emulated_shards(gc, orc, G):
+    from graph_core_b200.sharded import CudaShardEngine
+    dim, n = 12, 30011
+    pts = W.c4_nodes(n, dim, seed=95)
+    qs = W.c4_queries(16, dim, seed=96)
+    engines = []
+    for g in range(G):
+        e = CudaShardEngine(dim, n // G + 2, 0)
+        e.append(pts[g::G])  # node i -> shard i mod G, local slot i div G
+        engines.append(e)
+    ov = orc.OracleNN("vector", dim)
+    ov.insert(pts)
+
+    def exchange(lists, k_out, out_cap):
+        idx = torch.stack([l[0] for l in lists])
+        dd = torch.stack([l[1] for l in lists])
+        cnt = torch.stack([l[2] for l in lists])
+        oi, od, oc = engines[0].merge(idx, dd, cnt, k_out, out_cap)
+        torch.cuda.synchronize()
+        return oi.cpu().numpy(), od.cpu().numpy(), oc.cpu().numpy()
+
+    oi, od, oc = exchange([e.nearest_lists(qs) for e in engines], 1, 1)
+    ri, rd = ov.nearest(qs)
+    assert np.array_equal(oi[:, 0], ri) and np.array_equal(od[:, 0], rd)
+    k = 33
+    oi, od, oc = exchange([e.knn_lists(qs, k) for e in engines], k, k)
+    ri, rd, rc = ov.knn(qs, k, k)
+    assert np.array_equal(oi, ri) and np.array_equal(od, rd) and np.array_equal(oc, rc)
+    radius = W.c4_radius(40, n, dim)
+    cap = 256
+    oi, od, oc = exchange([e.near_lists(qs, radius, cap) for e in engines], G * cap, G * cap)
+    ri, rd, rc = ov.near(qs, radius, 1024)
+    assert np.array_equal(oc, rc) and rc.sum() > 0
+    for q in range(len(qs)):
+        assert np.array_equal(oi[q, :rc[q]], ri[q, :rc[q]]) and np.array_equal(od[q, :rc[q]], rd[q, :rc[q]])
+
+
+def test_sharded_store_world_size_one(gc, orc):
+    from graph_core_b200.sharded import ShardedNodeStore
+    dim, n = 7, 5000
+    pts = W.c4_nodes(n, dim, seed=97)
+    qs = W.c4_queries(8, dim, seed=98)
+    st = ShardedNodeStore(dim, n, device=0)
+    st.append(pts)
+    ov = orc.OracleNN("vector", dim)
+    ov.insert(pts)
+    gi, gd = st.nearest(qs)
+    ri, rd = ov.nearest(qs)
+    assert np.array_equal(gi.cpu().numpy(), ri) and np.array_equal(gd.cpu().numpy(), rd)
