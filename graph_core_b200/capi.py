@@ -150,6 +150,15 @@ def _ptr(a: np.ndarray, typ):
     return a.ctypes.data_as(typ)
 
 
+def stream_handle(cuda_stream) -> int:
+    """cudaStream_t for the C ABI: None = the handle's private stream (NULL), 0 = CUDA's legacy default
+    stream (what torch.cuda.current_stream().cuda_stream is unless a stream context is active; the C ABI
+    takes it as cudaStreamLegacy = 0x1 because NULL already means "private"), anything else as is."""
+    if cuda_stream is None:
+        return 0
+    return 1 if int(cuda_stream) == 0 else int(cuda_stream)
+
+
 def device_count() -> int:
     n = C.c_int(0)
     rc = load().gc_device_count(C.byref(n))
@@ -196,7 +205,7 @@ class NodeStore:
         return self._h
 
     def set_stream(self, cuda_stream: int | None):
-        _check(self._lib.gc_store_set_stream(self._h, C.c_void_p(cuda_stream or 0)))
+        _check(self._lib.gc_store_set_stream(self._h, C.c_void_p(stream_handle(cuda_stream))))
 
     def append(self, q, segment: int = 0) -> int:
         q = _f64(q, (-1, self.dim))
@@ -352,7 +361,7 @@ class CollisionWorld:
         return self._h
 
     def set_stream(self, cuda_stream: int | None):
-        _check(self._lib.gc_world_set_stream(self._h, C.c_void_p(cuda_stream or 0)))
+        _check(self._lib.gc_world_set_stream(self._h, C.c_void_p(stream_handle(cuda_stream))))
 
     def enable_timing(self, on: bool = True):
         _check(self._lib.gc_world_enable_timing(self._h, 1 if on else 0))

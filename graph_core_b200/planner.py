@@ -106,7 +106,7 @@ class LockstepRRTStar:
         return rc
 
     def set_stream(self, cuda_stream: int | None):
-        rc = self.L.gcp_rrtstar_set_stream(self.h, C.c_void_p(cuda_stream or 0))
+        rc = self.L.gcp_rrtstar_set_stream(self.h, C.c_void_p(capi.stream_handle(cuda_stream)))
         if rc < 0:
             raise capi.GcError(rc, self.L.gcp_last_error().decode())
 

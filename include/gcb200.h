@@ -65,7 +65,8 @@ int gc_flush_l2(int device, size_t bytes);
 /* ---- node store: replaces KdTree/Vector storage (kdtree.cpp:327-342, vector.cpp:38-43) ---- */
 int gc_store_create(int dim, uint32_t capacity_per_segment, uint32_t n_segments, int device, gc_store_t** out);
 int gc_store_destroy(gc_store_t* s);
-/* use an externally owned cudaStream_t (e.g. torch's current stream); NULL restores the private stream */
+/* use an externally owned cudaStream_t (e.g. torch's current stream); NULL restores the private stream.
+ * To run on CUDA's legacy default stream pass cudaStreamLegacy ((cudaStream_t)0x1), not NULL. */
 int gc_store_set_stream(gc_store_t* s, void* cuda_stream);
 /* NearestNeighbors::insert -- appends n rows (row-major, dim doubles each) to one segment */
 int gc_store_append(gc_store_t* s, uint32_t segment, const double* q, uint32_t n, uint32_t* first_slot);
