@@ -127,19 +127,36 @@ def cuda_checker(device=0, world_cache={}):
     return chk
 
 
-def cpu_reference_run(sc, starts, goals, samples, warmup, steps, threads):
-    """Oracle RRT* (reference flags) on len(starts) problems, `threads` host threads; returns samples/s."""
+def cpu_reference_run(sc, starts, goals, samples, warmup, steps, threads, prefer_ref=True):
+    """The reference's CPU RRT* on len(starts) problems, `threads` host threads; returns samples/s.
+
+    kind "reference": oracle/_ref -- graph_core's own RRTStar / Tree / KdTree / checkConnection sources compiled with
+    its Release flags (oracle/ref_build.py), single-state checks answered by the oracle's sphere-arm world (the
+    reference ships no such checker).  kind "port": the oracle restatement, used only when oracle/_ref is absent."""
     sys.path.insert(0, str(ROOT / "oracle"))
     import oracle_py as orc
+    import ref_py
     orc.build()
+    kind = "port"
+    if prefer_ref:
+        try:
+            ref_py.lib(fast=True)
+            kind = "reference"
+        except Exception:
+            kind = "port"
     n = len(starts)
     solvers = []
     worlds_ = []
     for p in range(n):
-        w = orc.OracleWorld.from_scenario(sc, fast=True)  # one world per thread: counters are not shared
+        w = orc.OracleWorld.from_scenario(sc, fast=True)  # one world per solver: counters are not shared
         worlds_.append(w)
-        solvers.append(orc.OracleSolver(orc.OracleSolver.RRTSTAR, sc, w, start=starts[p], goal=goals[p],
-                                        use_kdtree=True, fast=True))
+        if kind == "reference":
+            chk = ref_py.RefChecker.over_oracle_world(w, sc.min_distance, fast=True)
+            solvers.append(ref_py.RefSolver(ref_py.RefSolver.RRTSTAR, sc, chk, start=starts[p], goal=goals[p],
+                                            use_kdtree=True, informed=True, fast=True))
+        else:
+            solvers.append(orc.OracleSolver(orc.OracleSolver.RRTSTAR, sc, w, start=starts[p], goal=goals[p],
+                                            use_kdtree=True, fast=True))
     nthreads = max(1, min(threads, n))
     done = [0] * n
 
@@ -160,7 +177,14 @@ def cpu_reference_run(sc, starts, goals, samples, warmup, steps, threads):
     before = sum(done)
     dt = phase(warmup, warmup + steps)
     consumed = sum(done) - before
-    return consumed / dt, dt, nthreads, solvers
+    return consumed / dt, dt, nthreads, solvers, kind
+
+
+CPU_DESC = {
+    "reference": "graph_core's own RRTStar + KdTree + checkConnection sources (oracle/_ref, -O3 -Ofast, stand-in Eigen), "
+                 "single-state sphere-arm check from the oracle",
+    "port": "CPU restatement of KdTree + checkConnection (-O3 -Ofast)",
+}
 
 
 def main():
@@ -186,7 +210,7 @@ def main():
         starts = np.array([s for s, _ in pairs])
         goals = np.array([g for _, g in pairs])
         samples = make_samples(sc, nprob, W_ + K)
-        rate, dt, nthreads, _ = cpu_reference_run(sc, starts, goals, samples, W_, K, ncores)
+        rate, dt, nthreads, _, kind = cpu_reference_run(sc, starts, goals, samples, W_, K, ncores)
         line = {
             "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": K,
             "warmup": W_, "ms_per_step": dt / K * 1e3, "higher_is_better": True, "scaling": "weak",
@@ -194,9 +218,9 @@ def main():
             "config": {"workload": "C3: 7-DoF sphere-arm RRT* vs 1000-sphere cloud, %d problems x %d iterations" %
                                    (nprob, K), "problems": nprob, "max_distance": sc.max_distance,
                        "min_distance": sc.min_distance, "sampler": "uniform (Philox, injected)"},
-            "cpu_baseline": {"value": rate, "unit": UNIT, "cores": nthreads, "kind": "port",
-                             "sample": "%d problems x %d RRT* iterations, CPU restatement of KdTree + checkConnection "
-                                       "(-O3 -Ofast), one problem per thread" % (nprob, K)},
+            "cpu_baseline": {"value": rate, "unit": UNIT, "cores": nthreads, "kind": kind,
+                             "sample": "%d problems x %d RRT* iterations, %s, one problem per thread, %.1f s" %
+                                       (nprob, K, CPU_DESC[kind], dt)},
             "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0,
         }
@@ -368,11 +392,11 @@ def main():
                                                           np.array_equal(conf, gconf)), "nodes": int(len(par))}
         # ---- CPU baseline on a bounded sample of the same workload ---------------------------------
         ncpu = args.cpu_problems or min(P, ncores * 2)
-        rate, dt, nthreads, _ = cpu_reference_run(sc, starts[:ncpu], goals[:ncpu], samples[:, :ncpu, :], W_, K, ncores)
-        line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": nthreads, "kind": "port",
-                                "sample": "%d of the %d problems x %d RRT* iterations (same samples), CPU restatement "
-                                          "of KdTree + checkConnection (-O3 -Ofast), one problem per thread, %.1f s" %
-                                          (ncpu, P, K, dt)}
+        rate, dt, nthreads, _, kind = cpu_reference_run(sc, starts[:ncpu], goals[:ncpu], samples[:, :ncpu, :], W_, K,
+                                                        ncores)
+        line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": nthreads, "kind": kind,
+                                "sample": "%d of the %d problems x %d RRT* iterations (same samples), %s, one problem "
+                                          "per thread, %.1f s" % (ncpu, P, K, CPU_DESC[kind], dt)}
         # ---- kNN side measurement: BASELINE config 4 shape, HBM-bound regime --------------------------
         if not args.skip_nn:
             try:

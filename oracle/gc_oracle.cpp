@@ -8,11 +8,21 @@
  * may load this library; nothing under graph_core_b200/ links or calls it.
  *
  * PARITY PINNING: the reference's own tests hold no numerical vector for either
- * path.  The restatement is pinned instead against the
- * reference's own sources compiled in this container against stand-in headers
- * (oracle/_ref, see oracle/Makefile and oracle/ref_driver.cpp) and against the
- * single fixture tests/path.yaml.  Where oracle/_ref is not built the header of
- * tests/test_oracle_vs_ref.py says "parity unpinned".
+ * path.  The restatement is pinned against the REFERENCE ITSELF:
+ * oracle/ref_build.py compiles graph_core's own translation units (kdtree.cpp,
+ * vector.cpp, node.cpp, connection.cpp, tree.cpp, path.cpp, rrt.cpp, rrt_star.cpp,
+ * samplers, collision_checker_base.h ...) where they lie under /root/reference
+ * against stand-in Eigen / cnr_logger / cnr_param / yaml-cpp headers
+ * (oracle/ref_shim/) into oracle/_ref/libgc_ref.so (driver: oracle/ref_driver.cpp).
+ *   tests/test_oracle_vs_ref.py      restatement == reference, bit for bit: NN ids,
+ *                                    orderings and distances (Vector and KdTree, ties,
+ *                                    tombstones, rebuild), all three checkConnection
+ *                                    forms in every world, complete RRT / RRT* trees
+ *   tests/golden/ref_golden.json     outputs of the reference committed as fixtures
+ *                                    (tests/golden/make_ref_golden.py), replayed by
+ *                                    tests/test_oracle_cpu.py and, through the CUDA
+ *                                    path, by tests/test_golden_gpu.py
+ * plus the single fixture of the reference's tests, tests/path.yaml.
  *
  * Reference citations are relative to /root/reference/graph_core/ :
  *   inc/ = include/graph_core/,  src/ = src/graph_core/

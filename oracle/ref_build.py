@@ -1,0 +1,85 @@
+#!/usr/bin/env python
+"""Builds oracle/_ref/libgc_ref.so: the graph_core reference's OWN translation units, compiled where
+they lie under /root/reference (never copied) against the stand-in headers of oracle/ref_shim/
+(Eigen, cnr_logger, cnr_param, yaml-cpp -- none of which exist in this image), plus oracle/ref_driver.cpp.
+
+Test infrastructure only.  oracle/_ref/ is git-ignored but travels to the GPU box.  Where
+/root/reference is absent (the GPU box) this script does nothing and the prebuilt library is used.
+
+  libgc_ref.so       -O2 -ffp-contract=off     parity build (pins oracle/gc_oracle.cpp)
+  libgc_ref_fast.so  the reference's Release flags (graph_core/CMakeLists.txt:13: -O3 -Ofast -funroll-loops)
+                     plus -mfma -mavx2 -fno-finite-math-only: the CPU timing baseline ("kind": "reference")
+"""
+import os
+import subprocess
+import sys
+from concurrent.futures import ThreadPoolExecutor
+from pathlib import Path
+
+HERE = Path(__file__).resolve().parent
+REF = Path(os.environ.get("GRAPH_CORE_REFERENCE", "/root/reference")) / "graph_core"
+OUT = HERE / "_ref"
+
+# the plugin registrations (src/graph_core/plugins/**) need cnr_class_loader and are not on the hot path
+SOURCES = [
+    "src/graph_core/datastructure/kdtree.cpp", "src/graph_core/datastructure/vector.cpp",
+    "src/graph_core/graph/node.cpp", "src/graph_core/graph/connection.cpp", "src/graph_core/graph/tree.cpp",
+    "src/graph_core/graph/subtree.cpp", "src/graph_core/graph/net.cpp", "src/graph_core/graph/path.cpp",
+    "src/graph_core/metrics/euclidean_metrics.cpp",
+    "src/graph_core/samplers/uniform_sampler.cpp", "src/graph_core/samplers/informed_sampler.cpp",
+    "src/graph_core/samplers/ball_sampler.cpp", "src/graph_core/samplers/tube_informed_sampler.cpp",
+    "src/graph_core/solvers/tree_solver.cpp", "src/graph_core/solvers/rrt.cpp", "src/graph_core/solvers/rrt_star.cpp",
+    "src/graph_core/solvers/birrt.cpp", "src/graph_core/solvers/anytime_rrt.cpp",
+    "src/graph_core/solvers/path_optimizers/path_optimizer_base.cpp",
+    "src/graph_core/solvers/path_optimizers/path_local_optimizer.cpp",
+]
+VARIANTS = {
+    "libgc_ref.so": ["-O2", "-fno-fast-math", "-ffp-contract=off", "-mfma"],
+    "libgc_ref_fast.so": ["-O3", "-Ofast", "-fno-finite-math-only", "-funroll-loops", "-mfma", "-mavx2"],
+}
+
+
+def newest_input():
+    files = [HERE / "ref_driver.cpp", Path(__file__)] + list((HERE / "ref_shim").rglob("*")) + [REF / s for s in SOURCES]
+    return max(f.stat().st_mtime for f in files if f.is_file())
+
+
+def build(verbose=False):
+    if not REF.exists():
+        if verbose:
+            print("ref_build: %s not present; using prebuilt oracle/_ref if any" % REF)
+        return False
+    OUT.mkdir(exist_ok=True)
+    stamp = newest_input()
+    cxx = os.environ.get("CXX", "g++")
+    inc = ["-I", str(HERE / "ref_shim"), "-I", str(REF / "include")]
+    for lib, flags in VARIANTS.items():
+        target = OUT / lib
+        if target.exists() and target.stat().st_mtime >= stamp:
+            continue
+        objdir = OUT / ("obj_" + lib.replace(".so", ""))
+        objdir.mkdir(exist_ok=True)
+        jobs = [(REF / s, objdir / (Path(s).stem + ".o")) for s in SOURCES] + [(HERE / "ref_driver.cpp", objdir / "ref_driver.o")]
+
+        def cc(job):
+            src, obj = job
+            cmd = [cxx, "-std=c++17", "-fPIC", "-w", "-DNDEBUG", *flags, *inc, "-c", str(src), "-o", str(obj)]
+            r = subprocess.run(cmd, capture_output=True, text=True)
+            if r.returncode != 0:
+                raise RuntimeError("ref_build: %s failed\n%s" % (src, r.stderr[-4000:]))
+            return obj
+
+        with ThreadPoolExecutor(max_workers=os.cpu_count() or 4) as ex:
+            objs = list(ex.map(cc, jobs))
+        cmd = [cxx, "-shared", "-o", str(target), *map(str, objs)]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError("ref_build: link failed\n" + r.stderr[-4000:])
+        if verbose:
+            print("ref_build: built", target)
+    return True
+
+
+if __name__ == "__main__":
+    build(verbose=True)
+    sys.exit(0)

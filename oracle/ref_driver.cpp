@@ -1,0 +1,424 @@
+/*
+ * ref_driver.cpp -- C entry points over the UNMODIFIED graph_core reference, compiled here from its
+ * own sources where they lie under /root/reference (never copied into this repository).
+ *
+ * TEST INFRASTRUCTURE (oracle/): the resulting oracle/_ref/libgc_ref.so is the executable form of the
+ * reference that pins oracle/gc_oracle.cpp (tests/test_oracle_vs_ref.py) and mints the golden vectors
+ * under tests/golden/ (tests/golden/make_ref_golden.py).  Nothing under graph_core_b200/ links it.
+ *
+ * What is the reference's own code here: every graph::core class used below --
+ *   KdTree / Vector                         src/graph_core/datastructure/{kdtree,vector}.cpp
+ *   Node / Connection                       src/graph_core/graph/{node,connection}.cpp
+ *   CollisionCheckerBase::checkConnection*  include/graph_core/collision_checkers/collision_checker_base.h:178-313
+ *   Cube3dCollisionChecker                  include/graph_core/collision_checkers/cube_3d_collision_checker.h
+ *   Tree, Path, RRT, RRTStar, BiRRT, AnytimeRRT, samplers, EuclideanMetrics
+ * What is a stand-in: Eigen, cnr_logger, cnr_param, yaml-cpp (oracle/ref_shim/, see mini_eigen.hpp for
+ * the arithmetic conventions) -- this image has none of them.
+ *
+ * The synthetic worlds of BASELINE.json (boxes, C-space spheres, sphere arm) are not part of the
+ * reference; CallbackChecker::check() forwards single states to a caller-supplied function (the
+ * oracle's orc_check_states), so the reference's OWN checkConnection / checkConnFromConf loops decide
+ * which states are visited and in which order.
+ */
+#include <graph_core/collision_checkers/cube_3d_collision_checker.h>
+// kdtree.h / vector.h arrive through tree.h (vector.h has no include guard upstream: include it once only)
+#include <graph_core/metrics/euclidean_metrics.h>
+#include <graph_core/samplers/informed_sampler.h>
+#include <graph_core/samplers/uniform_sampler.h>
+#include <graph_core/solvers/anytime_rrt.h>
+#include <graph_core/solvers/birrt.h>
+#include <graph_core/solvers/rrt.h>
+#include <graph_core/solvers/rrt_star.h>
+
+#include <cstring>
+#include <unordered_map>
+
+using namespace graph::core;
+
+namespace
+{
+cnr_logger::TraceLoggerPtr g_logger = std::make_shared<cnr_logger::TraceLogger>();
+
+Eigen::VectorXd toVec(const double* q, int d)
+{
+  Eigen::VectorXd v(d);
+  for (int i = 0; i < d; i++)
+    v(i) = q[i];
+  return v;
+}
+
+typedef void (*check_states_fn)(void* ctx, const double* q, int n, unsigned char* ok);
+
+class CallbackChecker : public CollisionCheckerBase
+{
+public:
+  CallbackChecker(check_states_fn fn, void* ctx, double min_distance)
+    : CollisionCheckerBase(g_logger, min_distance), fn_(fn), ctx_(ctx)
+  {
+  }
+  bool check(const Eigen::VectorXd& configuration) override
+  {
+    unsigned char ok = 0;
+    fn_(ctx_, configuration.data(), 1, &ok);
+    states++;
+    return ok != 0;
+  }
+  CollisionCheckerPtr clone() override { return std::make_shared<CallbackChecker>(fn_, ctx_, min_distance_); }
+  unsigned long long states = 0;
+
+private:
+  check_states_fn fn_;
+  void* ctx_;
+};
+
+struct RefNN
+{
+  int dim;
+  NearestNeighborsPtr nn;
+  std::vector<NodePtr> nodes;  // id = creation order
+  std::unordered_map<Node*, int> id_of;
+};
+
+int copyMap(RefNN* o, const std::multimap<double, NodePtr>& m, int* ids, double* dists, int cap)
+{
+  int n = 0;
+  for (const auto& p : m)
+  {
+    if (n < cap)
+    {
+      if (ids)
+        ids[n] = o->id_of.at(p.second.get());
+      if (dists)
+        dists[n] = p.first;
+    }
+    n++;
+  }
+  return n;
+}
+
+struct RefSolver
+{
+  int kind, dim;
+  CollisionCheckerPtr checker;
+  MetricsPtr metrics;
+  SamplerPtr sampler;
+  TreeSolverPtr solver;
+  NodePtr start, goal;
+  PathPtr solution;
+};
+}  // namespace
+
+extern "C" {
+
+const char* ref_about()
+{
+  return "graph_core reference sources compiled against oracle/ref_shim stand-ins (Eigen, cnr_logger, cnr_param, yaml-cpp)";
+}
+
+// ---- NearestNeighbors: kind 0 = Vector, 1 = KdTree -----------------------------------------------
+void* ref_nn_new(int kind, int dim)
+{
+  RefNN* o = new RefNN();
+  o->dim = dim;
+  if (kind == 1)
+    o->nn = std::make_shared<KdTree>(g_logger);
+  else
+    o->nn = std::make_shared<Vector>(g_logger);
+  return o;
+}
+void ref_nn_free(void* h) { delete (RefNN*)h; }
+void ref_nn_insert_many(void* h, const double* q, int n)
+{
+  RefNN* o = (RefNN*)h;
+  for (int i = 0; i < n; i++)
+  {
+    NodePtr node = std::make_shared<Node>(toVec(q + (size_t)i * o->dim, o->dim), g_logger);
+    o->id_of[node.get()] = (int)o->nodes.size();
+    o->nodes.push_back(node);
+    o->nn->insert(node);
+  }
+}
+void ref_nn_reinsert(void* h, int id) { ((RefNN*)h)->nn->insert(((RefNN*)h)->nodes[id]); }
+int ref_nn_delete(void* h, int id) { return ((RefNN*)h)->nn->deleteNode(((RefNN*)h)->nodes[id], false) ? 1 : 0; }
+int ref_nn_restore(void* h, int id) { return ((RefNN*)h)->nn->restoreNode(((RefNN*)h)->nodes[id]) ? 1 : 0; }
+int ref_nn_find(void* h, int id) { return ((RefNN*)h)->nn->findNode(((RefNN*)h)->nodes[id]) ? 1 : 0; }
+int ref_nn_clear(void* h) { return ((RefNN*)h)->nn->clear() ? 1 : 0; }
+unsigned int ref_nn_size(void* h) { return ((RefNN*)h)->nn->size(); }
+void ref_nn_set_deleted_threshold(void* h, unsigned int t)
+{
+  KdTree* k = dynamic_cast<KdTree*>(((RefNN*)h)->nn.get());
+  if (k)
+    k->deletedNodesThreshold(t);
+}
+int ref_nn_get_nodes(void* h, int* ids, int cap)
+{
+  RefNN* o = (RefNN*)h;
+  std::vector<NodePtr> v = o->nn->getNodes();
+  for (int i = 0; i < (int)v.size() && i < cap; i++)
+    ids[i] = o->id_of.at(v[i].get());
+  return (int)v.size();
+}
+void ref_nn_nearest(void* h, const double* q, int nq, int* ids, double* dists)
+{
+  RefNN* o = (RefNN*)h;
+  for (int i = 0; i < nq; i++)
+  {
+    NodePtr best;
+    double bd = std::numeric_limits<double>::infinity();
+    o->nn->nearestNeighbor(toVec(q + (size_t)i * o->dim, o->dim), best, bd);
+    ids[i] = best ? o->id_of.at(best.get()) : -1;
+    dists[i] = bd;
+  }
+}
+void ref_nn_near(void* h, const double* q, int nq, const double* radius, int cap, int* ids, double* dists,
+                 int* counts)
+{
+  RefNN* o = (RefNN*)h;
+  for (int i = 0; i < nq; i++)
+  {
+    std::multimap<double, NodePtr> m = o->nn->near(toVec(q + (size_t)i * o->dim, o->dim), radius[i]);
+    counts[i] = copyMap(o, m, ids + (size_t)i * cap, dists + (size_t)i * cap, cap);
+  }
+}
+void ref_nn_knn(void* h, const double* q, int nq, unsigned long long k, int cap, int* ids, double* dists,
+                int* counts)
+{
+  RefNN* o = (RefNN*)h;
+  for (int i = 0; i < nq; i++)
+  {
+    std::multimap<double, NodePtr> m = o->nn->kNearestNeighbors(toVec(q + (size_t)i * o->dim, o->dim), (size_t)k);
+    counts[i] = copyMap(o, m, ids + (size_t)i * cap, dists + (size_t)i * cap, cap);
+  }
+}
+
+// ---- collision checkers ---------------------------------------------------------------------------
+struct RefChecker
+{
+  CollisionCheckerPtr c;
+  int dim;
+};
+void* ref_checker_cube(int dim, double threshold, double min_distance)
+{
+  return new RefChecker{ std::make_shared<Cube3dCollisionChecker>(g_logger, threshold, min_distance), dim };
+}
+// fn has the signature of the oracle's orc_check_states; ctx is the oracle world handle
+void* ref_checker_callback(int dim, void* fn, void* ctx, double min_distance)
+{
+  return new RefChecker{ std::make_shared<CallbackChecker>((check_states_fn)fn, ctx, min_distance), dim };
+}
+void ref_checker_free(void* h) { delete (RefChecker*)h; }
+unsigned long long ref_checker_states(void* h)
+{
+  CallbackChecker* c = dynamic_cast<CallbackChecker*>(((RefChecker*)h)->c.get());
+  return c ? c->states : 0ull;
+}
+void ref_check_states(void* h, const double* q, int n, unsigned char* ok)
+{
+  RefChecker* r = (RefChecker*)h;
+  for (int i = 0; i < n; i++)
+    ok[i] = r->c->check(toVec(q + (size_t)i * r->dim, r->dim)) ? 1 : 0;
+}
+// mode 0: checkConnection(c1,c2) (:207-237).  mode 1: checkConnection(c1,c2,conf) (:178-205); last_conf[i] receives
+// conf (pre-filled with NaN so "left untouched" is visible).
+void ref_check_edges(void* h, const double* c1, const double* c2, int n, int mode, unsigned char* ok, double* last_conf)
+{
+  RefChecker* r = (RefChecker*)h;
+  const int d = r->dim;
+  for (int i = 0; i < n; i++)
+  {
+    Eigen::VectorXd a = toVec(c1 + (size_t)i * d, d), b = toVec(c2 + (size_t)i * d, d);
+    if (mode == 1)
+    {
+      Eigen::VectorXd conf(d);
+      conf.setConstant(std::numeric_limits<double>::quiet_NaN());
+      ok[i] = r->c->checkConnection(a, b, conf) ? 1 : 0;
+      if (last_conf)
+        for (int k = 0; k < d; k++)
+          last_conf[(size_t)i * d + k] = conf(k);
+    }
+    else
+      ok[i] = r->c->checkConnection(a, b) ? 1 : 0;
+  }
+}
+// checkConnFromConf (:264-313): 1 free, 0 collision, 255 the reference threw std::invalid_argument
+void ref_check_from_conf(void* h, const double* parent, const double* child, const double* conf, int n,
+                         unsigned char* result)
+{
+  RefChecker* r = (RefChecker*)h;
+  const int d = r->dim;
+  for (int i = 0; i < n; i++)
+  {
+    NodePtr p = std::make_shared<Node>(toVec(parent + (size_t)i * d, d), g_logger);
+    NodePtr c = std::make_shared<Node>(toVec(child + (size_t)i * d, d), g_logger);
+    ConnectionPtr conn = std::make_shared<Connection>(p, c, g_logger);
+    conn->add();
+    try
+    {
+      result[i] = r->c->checkConnFromConf(conn, toVec(conf + (size_t)i * d, d)) ? 1 : 0;
+    }
+    catch (const std::invalid_argument&)
+    {
+      result[i] = 255;
+    }
+    conn->remove();
+  }
+}
+
+// ---- solvers: kind 0 RRT, 1 RRTStar, 2 BiRRT, 3 AnytimeRRT ------------------------------------------
+void* ref_solver_new(int kind, int dim, void* checker, const double* lb, const double* ub, const double* start,
+                     const double* goal, double max_distance, double rewire_factor, double utopia_tolerance,
+                     int use_kdtree, int extend, int informed_sampler)
+{
+  RefSolver* s = new RefSolver();
+  s->kind = kind;
+  s->dim = dim;
+  s->checker = ((RefChecker*)checker)->c;
+  s->metrics = std::make_shared<EuclideanMetrics>(g_logger);
+  Eigen::VectorXd vlb = toVec(lb, dim), vub = toVec(ub, dim), vs = toVec(start, dim), vg = toVec(goal, dim);
+  if (informed_sampler)
+    s->sampler = std::make_shared<InformedSampler>(vs, vg, vlb, vub, g_logger);
+  else
+    s->sampler = std::make_shared<UniformSampler>(vlb, vub, g_logger);
+  switch (kind)
+  {
+    case 0:
+      s->solver = std::make_shared<RRT>(s->metrics, s->checker, s->sampler, g_logger);
+      break;
+    case 1:
+      s->solver = std::make_shared<RRTStar>(s->metrics, s->checker, s->sampler, g_logger);
+      break;
+    case 2:
+      s->solver = std::make_shared<BiRRT>(s->metrics, s->checker, s->sampler, g_logger);
+      break;
+    default:
+      s->solver = std::make_shared<AnytimeRRT>(s->metrics, s->checker, s->sampler, g_logger);
+      break;
+  }
+  const std::string ns = "/ref_driver";
+  cnr::param::shim_set(ns + "/max_distance", max_distance);
+  cnr::param::shim_set(ns + "/use_kdtree", use_kdtree ? 1.0 : 0.0);
+  cnr::param::shim_set(ns + "/extend", extend ? 1.0 : 0.0);
+  cnr::param::shim_set(ns + "/utopia_tolerance", utopia_tolerance);
+  cnr::param::shim_set(ns + "/rewire_factor", rewire_factor);
+  s->solver->config(ns);
+  s->start = std::make_shared<Node>(vs, g_logger);
+  s->goal = std::make_shared<Node>(vg, g_logger);
+  s->solver->addStart(s->start);
+  s->solver->addGoal(s->goal);
+  return s;
+}
+void ref_solver_free(void* h) { delete (RefSolver*)h; }
+// feeds n injected samples through update(configuration, solution); same stopping rule as orc_solver_run
+int ref_solver_run(void* h, const double* samples, int n)
+{
+  RefSolver* s = (RefSolver*)h;
+  int i = 0;
+  for (; i < n; i++)
+  {
+    bool r = s->solver->update(toVec(samples + (size_t)i * s->dim, s->dim), s->solution);
+    if (r && !s->solver->canImprove())
+    {
+      i++;
+      break;
+    }
+  }
+  return i;
+}
+int ref_solver_update(void* h, const double* q)
+{
+  RefSolver* s = (RefSolver*)h;
+  return s->solver->update(toVec(q, s->dim), s->solution) ? 1 : 0;
+}
+// AnytimeRRT / generic: the solver's own solve loop with its own (std::rand) sampler
+int ref_solver_solve(void* h, unsigned int max_iter, double max_time)
+{
+  RefSolver* s = (RefSolver*)h;
+  return s->solver->solve(s->solution, max_iter, max_time) ? 1 : 0;
+}
+int ref_solver_solved(void* h) { return ((RefSolver*)h)->solver->solved() ? 1 : 0; }
+int ref_solver_can_improve(void* h) { return ((RefSolver*)h)->solver->canImprove() ? 1 : 0; }
+double ref_solver_cost(void* h) { return ((RefSolver*)h)->solver->cost(); }
+double ref_solver_specific_volume(void* h) { return ((RefSolver*)h)->sampler->getSpecificVolume(); }
+int ref_solver_tree_size(void* h)
+{
+  TreePtr t = ((RefSolver*)h)->solver->getStartTree();
+  return t ? (int)t->getNumberOfNodes() : 0;
+}
+// every node of the start tree, in NearestNeighbors::getNodes() order: conf[n][dim], parent_conf[n][dim]
+// (NaN for the root), cost of the parent connection (0 for the root).  Returns n; fills at most cap rows.
+int ref_solver_dump(void* h, int cap, double* conf, double* parent_conf, double* pcost)
+{
+  RefSolver* s = (RefSolver*)h;
+  TreePtr t = s->solver->getStartTree();
+  if (!t)
+    return 0;
+  std::vector<NodePtr> nodes = t->getNodes();
+  const int d = s->dim;
+  for (int i = 0; i < (int)nodes.size() && i < cap; i++)
+  {
+    for (int k = 0; k < d; k++)
+      conf[(size_t)i * d + k] = nodes[i]->getConfiguration()(k);
+    if (nodes[i]->getParentConnectionsSize() == 1)
+    {
+      ConnectionPtr c = nodes[i]->parentConnection(0);
+      for (int k = 0; k < d; k++)
+        parent_conf[(size_t)i * d + k] = c->getParent()->getConfiguration()(k);
+      pcost[i] = c->getCost();
+    }
+    else
+    {
+      for (int k = 0; k < d; k++)
+        parent_conf[(size_t)i * d + k] = std::numeric_limits<double>::quiet_NaN();
+      pcost[i] = 0.0;
+    }
+  }
+  return (int)nodes.size();
+}
+// waypoints of the current solution, start first; returns their number
+int ref_solver_solution(void* h, int cap, double* conf)
+{
+  RefSolver* s = (RefSolver*)h;
+  PathPtr p = s->solver->getSolution();
+  if (!p || !s->solver->solved())
+    return 0;
+  std::vector<Eigen::VectorXd> wp = p->getWaypoints();
+  for (int i = 0; i < (int)wp.size() && i < cap; i++)
+    for (int k = 0; k < s->dim; k++)
+      conf[(size_t)i * s->dim + k] = wp[i](k);
+  return (int)wp.size();
+}
+double ref_solver_path_cost(void* h)
+{
+  PathPtr p = ((RefSolver*)h)->solver->getSolution();
+  return p ? p->cost() : std::numeric_limits<double>::infinity();
+}
+
+// ---- samplers: the reference's own sampling code with the shim's std::rand stream --------------------
+void ref_srand(unsigned int seed) { std::srand(seed); }
+void ref_sample_informed(int dim, const double* lb, const double* ub, const double* f1, const double* f2, double cost,
+                         int n, double* out)
+{
+  InformedSampler smp(toVec(f1, dim), toVec(f2, dim), toVec(lb, dim), toVec(ub, dim), g_logger, cost);
+  for (int i = 0; i < n; i++)
+  {
+    Eigen::VectorXd q = smp.sample();
+    for (int k = 0; k < dim; k++)
+      out[(size_t)i * dim + k] = q(k);
+  }
+}
+// ellipse parameters after setCost: out = [specific_volume, focii_distance, min_radius, max_radius]... only what the
+// public API exposes: specific volume and in-bounds tests
+double ref_informed_specific_volume(int dim, const double* lb, const double* ub, const double* f1, const double* f2,
+                                    double cost)
+{
+  InformedSampler smp(toVec(f1, dim), toVec(f2, dim), toVec(lb, dim), toVec(ub, dim), g_logger, cost);
+  return smp.getSpecificVolume();
+}
+// RRTStar::updateRewireRadius is protected; the k of Tree::nearK and Metrics::cost are reachable
+double ref_metrics_cost(int dim, const double* a, const double* b)
+{
+  EuclideanMetrics m(g_logger);
+  return m.cost(toVec(a, dim), toVec(b, dim));
+}
+
+}  // extern "C"

@@ -1,0 +1,318 @@
+"""ctypes wrapper of oracle/_ref/libgc_ref.so -- the graph_core reference's own sources compiled against
+the stand-in headers of oracle/ref_shim (see oracle/ref_build.py, oracle/ref_driver.cpp).
+
+TEST INFRASTRUCTURE ONLY: used by tests/ (to pin the oracle restatement), tests/golden/make_ref_golden.py
+and bench.py's cpu_baseline / --impl reference legs.  Never imported by graph_core_b200/.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+
+import numpy as np
+
+HERE = Path(__file__).resolve().parent
+_dp = C.POINTER(C.c_double)
+_ip = C.POINTER(C.c_int)
+_u8p = C.POINTER(C.c_uint8)
+_libs = {}
+
+
+def available(fast: bool = False) -> bool:
+    return (HERE / "_ref" / ("libgc_ref_fast.so" if fast else "libgc_ref.so")).exists()
+
+
+def build():
+    """(Re)build when the reference tree is present; otherwise rely on the prebuilt library."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("ref_build", HERE / "ref_build.py")
+    m = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(m)
+    return m.build()
+
+
+def lib(fast: bool = False):
+    key = "fast" if fast else "parity"
+    if key in _libs:
+        return _libs[key]
+    path = HERE / "_ref" / ("libgc_ref_fast.so" if fast else "libgc_ref.so")
+    if not path.exists():
+        build()
+    if not path.exists():
+        raise FileNotFoundError("%s missing: run oracle/ref_build.py where /root/reference exists" % path)
+    L = C.CDLL(str(path))
+    vp = C.c_void_p
+    sig = {
+        "ref_about": (C.c_char_p, []),
+        "ref_nn_new": (vp, [C.c_int, C.c_int]),
+        "ref_nn_free": (None, [vp]),
+        "ref_nn_insert_many": (None, [vp, _dp, C.c_int]),
+        "ref_nn_reinsert": (None, [vp, C.c_int]),
+        "ref_nn_delete": (C.c_int, [vp, C.c_int]),
+        "ref_nn_restore": (C.c_int, [vp, C.c_int]),
+        "ref_nn_find": (C.c_int, [vp, C.c_int]),
+        "ref_nn_clear": (C.c_int, [vp]),
+        "ref_nn_size": (C.c_uint, [vp]),
+        "ref_nn_set_deleted_threshold": (None, [vp, C.c_uint]),
+        "ref_nn_get_nodes": (C.c_int, [vp, _ip, C.c_int]),
+        "ref_nn_nearest": (None, [vp, _dp, C.c_int, _ip, _dp]),
+        "ref_nn_near": (None, [vp, _dp, C.c_int, _dp, C.c_int, _ip, _dp, _ip]),
+        "ref_nn_knn": (None, [vp, _dp, C.c_int, C.c_ulonglong, C.c_int, _ip, _dp, _ip]),
+        "ref_checker_cube": (vp, [C.c_int, C.c_double, C.c_double]),
+        "ref_checker_callback": (vp, [C.c_int, vp, vp, C.c_double]),
+        "ref_checker_free": (None, [vp]),
+        "ref_checker_states": (C.c_ulonglong, [vp]),
+        "ref_check_states": (None, [vp, _dp, C.c_int, _u8p]),
+        "ref_check_edges": (None, [vp, _dp, _dp, C.c_int, C.c_int, _u8p, _dp]),
+        "ref_check_from_conf": (None, [vp, _dp, _dp, _dp, C.c_int, _u8p]),
+        "ref_solver_new": (vp, [C.c_int, C.c_int, vp, _dp, _dp, _dp, _dp, C.c_double, C.c_double, C.c_double, C.c_int,
+                                C.c_int, C.c_int]),
+        "ref_solver_free": (None, [vp]),
+        "ref_solver_run": (C.c_int, [vp, _dp, C.c_int]),
+        "ref_solver_update": (C.c_int, [vp, _dp]),
+        "ref_solver_solve": (C.c_int, [vp, C.c_uint, C.c_double]),
+        "ref_solver_solved": (C.c_int, [vp]),
+        "ref_solver_can_improve": (C.c_int, [vp]),
+        "ref_solver_cost": (C.c_double, [vp]),
+        "ref_solver_specific_volume": (C.c_double, [vp]),
+        "ref_solver_tree_size": (C.c_int, [vp]),
+        "ref_solver_dump": (C.c_int, [vp, C.c_int, _dp, _dp, _dp]),
+        "ref_solver_solution": (C.c_int, [vp, C.c_int, _dp]),
+        "ref_solver_path_cost": (C.c_double, [vp]),
+        "ref_srand": (None, [C.c_uint]),
+        "ref_sample_informed": (None, [C.c_int, _dp, _dp, _dp, _dp, C.c_double, C.c_int, _dp]),
+        "ref_informed_specific_volume": (C.c_double, [C.c_int, _dp, _dp, _dp, _dp, C.c_double]),
+        "ref_metrics_cost": (C.c_double, [C.c_int, _dp, _dp]),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(L, name)
+        fn.restype = res
+        fn.argtypes = args
+    _libs[key] = L
+    return L
+
+
+def _f64(a, shape=None):
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    return a.reshape(shape) if shape is not None else a
+
+
+def _p(a, t):
+    return a.ctypes.data_as(t)
+
+
+class RefNN:
+    """graph::core::Vector ('vector') or graph::core::KdTree ('kdtree') -- the reference's own classes.
+    Same method surface as oracle_py.OracleNN."""
+
+    def __init__(self, kind: str, dim: int, fast: bool = False):
+        self.L = lib(fast)
+        self.dim = dim
+        self.h = self.L.ref_nn_new(1 if kind == "kdtree" else 0, dim)
+
+    def __del__(self):
+        try:
+            self.L.ref_nn_free(self.h)
+        except Exception:
+            pass
+
+    def insert(self, q):
+        q = _f64(q, (-1, self.dim))
+        self.L.ref_nn_insert_many(self.h, _p(q, _dp), q.shape[0])
+
+    def reinsert(self, node_id):
+        self.L.ref_nn_reinsert(self.h, node_id)
+
+    def delete(self, node_id):
+        return bool(self.L.ref_nn_delete(self.h, node_id))
+
+    def restore(self, node_id):
+        return bool(self.L.ref_nn_restore(self.h, node_id))
+
+    def find(self, node_id):
+        return bool(self.L.ref_nn_find(self.h, node_id))
+
+    def clear(self):
+        return bool(self.L.ref_nn_clear(self.h))
+
+    def size(self):
+        return self.L.ref_nn_size(self.h)
+
+    def set_deleted_threshold(self, t):
+        self.L.ref_nn_set_deleted_threshold(self.h, t)
+
+    def get_nodes(self, cap=1 << 22):
+        ids = np.empty(cap, dtype=np.int32)
+        n = self.L.ref_nn_get_nodes(self.h, _p(ids, _ip), cap)
+        return ids[:n].copy()
+
+    def nearest(self, q):
+        q = _f64(q, (-1, self.dim))
+        ids = np.empty(q.shape[0], dtype=np.int32)
+        d = np.empty(q.shape[0], dtype=np.float64)
+        self.L.ref_nn_nearest(self.h, _p(q, _dp), q.shape[0], _p(ids, _ip), _p(d, _dp))
+        return ids, d
+
+    def near(self, q, radius, cap=256):
+        q = _f64(q, (-1, self.dim))
+        nq = q.shape[0]
+        r = np.ascontiguousarray(np.broadcast_to(np.asarray(radius, dtype=np.float64), (nq,)))
+        ids = np.full((nq, cap), -1, dtype=np.int32)
+        d = np.full((nq, cap), np.inf, dtype=np.float64)
+        cnt = np.zeros(nq, dtype=np.int32)
+        self.L.ref_nn_near(self.h, _p(q, _dp), nq, _p(r, _dp), cap, _p(ids, _ip), _p(d, _dp), _p(cnt, _ip))
+        return ids, d, cnt
+
+    def knn(self, q, k, cap):
+        q = _f64(q, (-1, self.dim))
+        nq = q.shape[0]
+        ids = np.full((nq, cap), -1, dtype=np.int32)
+        d = np.full((nq, cap), np.inf, dtype=np.float64)
+        cnt = np.zeros(nq, dtype=np.int32)
+        self.L.ref_nn_knn(self.h, _p(q, _dp), nq, int(k), cap, _p(ids, _ip), _p(d, _dp), _p(cnt, _ip))
+        return ids, d, cnt
+
+
+class RefChecker:
+    """The reference's CollisionCheckerBase loops over either its own Cube3dCollisionChecker::check or
+    a per-state callback into an oracle world (for the synthetic worlds the reference does not ship)."""
+
+    def __init__(self, h, dim, L, min_distance, keep=()):
+        self.h, self.dim, self.L, self.min_distance, self._keep = h, dim, L, min_distance, keep
+
+    @classmethod
+    def cube(cls, dim, threshold=1.0, min_distance=0.01, fast=False):
+        L = lib(fast)
+        return cls(L.ref_checker_cube(dim, threshold, min_distance), dim, L, min_distance)
+
+    @classmethod
+    def over_oracle_world(cls, world, min_distance=0.01, fast=False):
+        """world: oracle_py.OracleWorld; its orc_check_states answers the single-state checks."""
+        L = lib(fast)
+        fn = C.cast(world.L.orc_check_states, C.c_void_p)
+        return cls(L.ref_checker_callback(world.dim, fn, world.h, min_distance), world.dim, L, min_distance, keep=(world,))
+
+    def __del__(self):
+        try:
+            self.L.ref_checker_free(self.h)
+        except Exception:
+            pass
+
+    def states(self):
+        return int(self.L.ref_checker_states(self.h))
+
+    def check(self, q):
+        q = _f64(q, (-1, self.dim))
+        ok = np.empty(q.shape[0], np.uint8)
+        self.L.ref_check_states(self.h, _p(q, _dp), q.shape[0], _p(ok, _u8p))
+        return ok
+
+    def check_connection(self, c1, c2, mode=0):
+        c1, c2 = _f64(c1, (-1, self.dim)), _f64(c2, (-1, self.dim))
+        n = c1.shape[0]
+        ok = np.empty(n, np.uint8)
+        if mode == 1:
+            conf = np.full((n, self.dim), np.nan)
+            self.L.ref_check_edges(self.h, _p(c1, _dp), _p(c2, _dp), n, 1, _p(ok, _u8p), _p(conf, _dp))
+            return ok, conf
+        self.L.ref_check_edges(self.h, _p(c1, _dp), _p(c2, _dp), n, 0, _p(ok, _u8p), None)
+        return ok
+
+    def check_conn_from_conf(self, parent, child, conf):
+        p, c, f = _f64(parent, (-1, self.dim)), _f64(child, (-1, self.dim)), _f64(conf, (-1, self.dim))
+        res = np.empty(p.shape[0], np.uint8)
+        self.L.ref_check_from_conf(self.h, _p(p, _dp), _p(c, _dp), _p(f, _dp), p.shape[0], _p(res, _u8p))
+        return res
+
+
+class RefSolver:
+    """graph::core::{RRT, RRTStar, BiRRT, AnytimeRRT} with EuclideanMetrics and a Uniform/Informed sampler."""
+    RRT, RRTSTAR, BIRRT, ANYTIME = 0, 1, 2, 3
+
+    def __init__(self, kind, scenario, checker: RefChecker, start=None, goal=None, use_kdtree=True, extend=False,
+                 informed=True, fast=False):
+        self.L = lib(fast)
+        self.checker = checker
+        self.dim = scenario.dim
+        s = _f64(scenario.start if start is None else start)
+        g = _f64(scenario.goal if goal is None else goal)
+        lb, ub = _f64(scenario.lb), _f64(scenario.ub)
+        self.h = self.L.ref_solver_new(kind, self.dim, checker.h, _p(lb, _dp), _p(ub, _dp), _p(s, _dp), _p(g, _dp),
+                                       scenario.max_distance, scenario.rewire_factor, scenario.utopia_tolerance,
+                                       1 if use_kdtree else 0, 1 if extend else 0, 1 if informed else 0)
+
+    def __del__(self):
+        try:
+            self.L.ref_solver_free(self.h)
+        except Exception:
+            pass
+
+    def run(self, samples):
+        s = _f64(samples, (-1, self.dim))
+        return self.L.ref_solver_run(self.h, _p(s, _dp), s.shape[0])
+
+    def update(self, q):
+        q = _f64(q)
+        return bool(self.L.ref_solver_update(self.h, _p(q, _dp)))
+
+    def solve(self, max_iter, max_time=float("inf")):
+        return bool(self.L.ref_solver_solve(self.h, max_iter, max_time))
+
+    @property
+    def solved(self):
+        return bool(self.L.ref_solver_solved(self.h))
+
+    @property
+    def can_improve(self):
+        return bool(self.L.ref_solver_can_improve(self.h))
+
+    @property
+    def cost(self):
+        return self.L.ref_solver_cost(self.h)
+
+    @property
+    def specific_volume(self):
+        return self.L.ref_solver_specific_volume(self.h)
+
+    @property
+    def tree_size(self):
+        return self.L.ref_solver_tree_size(self.h)
+
+    def dump(self):
+        """conf[n][dim], parent_conf[n][dim] (NaN for the root), pcost[n] in getNodes() order."""
+        n = self.L.ref_solver_dump(self.h, 0, None, None, None)
+        conf = np.empty((n, self.dim))
+        par = np.empty((n, self.dim))
+        pc = np.empty(n)
+        self.L.ref_solver_dump(self.h, n, _p(conf, _dp), _p(par, _dp), _p(pc, _dp))
+        return conf, par, pc
+
+    def solution(self):
+        wp = np.empty((1 << 14, self.dim))
+        n = self.L.ref_solver_solution(self.h, wp.shape[0], _p(wp, _dp))
+        return wp[:n].copy()
+
+    @property
+    def path_cost(self):
+        return self.L.ref_solver_path_cost(self.h)
+
+
+def tree_as_edges(conf, parent_conf, pcost):
+    """Canonical, order-free form of a tree dump: {child conf bytes: (parent conf bytes | None, cost)}."""
+    out = {}
+    for i in range(conf.shape[0]):
+        p = None if np.isnan(parent_conf[i]).any() else parent_conf[i].tobytes()
+        out[conf[i].tobytes()] = (p, float(pcost[i]))
+    return out
+
+
+def oracle_tree_as_edges(parents, pcost, conf, in_tree=None):
+    """Same canonical form from oracle_py.OracleSolver.dump() / LockstepRRTStar.dump() (ids = creation order);
+    nodes with parent -1 other than the root (id 0) are not in the tree yet (e.g. an unconnected goal)."""
+    out = {}
+    for i in range(len(parents)):
+        if parents[i] < 0 and i != 0:
+            continue
+        p = None if parents[i] < 0 else conf[parents[i]].tobytes()
+        out[conf[i].tobytes()] = (p, float(pcost[i]) if parents[i] >= 0 else 0.0)
+    return out

@@ -1,9 +1,7 @@
 """Mints tests/golden/oracle_golden.json from the oracle restatement (seeded Philox inputs).
 
-The reference's tests hold no numerical vector for the NN or edge path and the
-reference cannot be built here (Eigen/cnr_* absent), so these vectors come from the restatement
-itself; they pin it against drift and are what the CUDA path is compared with on the GPU box
-(tests/test_golden_gpu.py).  Regenerate with:  python tests/golden/make_golden.py
+These vectors come from the restatement itself and guard it against drift.  The vectors that pin the
+restatement to the REFERENCE are tests/golden/ref_golden.json (make_ref_golden.py).  Regenerate with:  python tests/golden/make_golden.py
 """
 import json
 import sys

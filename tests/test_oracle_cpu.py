@@ -138,6 +138,17 @@ def test_golden_vectors(orc):
     assert now == g
 
 
+def test_ref_golden_vectors(orc):
+    """tests/golden/ref_golden.json holds outputs of the REFERENCE ITSELF (oracle/_ref, minted by
+    tests/golden/make_ref_golden.py): NN ids/distances, edge booleans, last feasible configurations and complete
+    RRT* trees.  The restatement must reproduce every one of them bit for bit."""
+    import make_ref_golden as m
+    want = json.loads((GOLD / "ref_golden.json").read_text())
+    assert "reference sources" in want.pop("_about")
+    got = m.compute(m.OracleBackend(None, orc))
+    assert got == want
+
+
 def test_rrtstar_oracle_solves_reference_scene(orc):
     """compute_path_test.cpp:51-132 with injected samples: RRT* finds and improves a path in C0."""
     sc = W.scenario_c0()
