@@ -111,7 +111,8 @@ struct gc_store
   int sms = 148;
   uint32_t near_width_hint = 64;   // columns of the near lists fetched eagerly by gc_extend_batch
   uint32_t knn_cand_scale = 3;     // head-room factor of the large-N k-nearest candidate lists
-  gc::DevBuf d_cand_idx, d_cand_dist, d_cand_count, d_thr;
+  gc::DevBuf d_cand_idx, d_cand_dist, d_cand_count, d_thr, d_gmin;
+  size_t stream_ctl_q = 0, stream_ctl_g = 0;  // initialised extent of d_gmin (streaming-scan control words)
   // scratch
   gc::DevBuf d_q, d_seg, d_radius, d_idx, d_dist, d_count, d_part, d_misc, d_rows, d_slots;
   gc::PinBuf h_in, h_out;

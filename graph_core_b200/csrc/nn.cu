@@ -94,6 +94,9 @@ struct ScanArgs
   uint32_t cap_seg;
   size_t row_stride;
   float slack_abs;
+  float xn_max;            // streaming scan: upper bound of |x|^2 over the store (fp32)
+  uint32_t* gmin;          // streaming scan MODE 0: [nq] shared running fp32 minima (order-preserving keys)
+  uint32_t* ctl;           // streaming scan: [groups][2] tile hand-out and finished-CTA counters (self-resetting)
   // MODE 0 outputs: partials [chunks][nq]
   double* part_d;
   uint32_t* part_i;
@@ -280,6 +283,555 @@ __global__ void __launch_bounds__(kScanThreads, 2) scan_kernel(ScanArgs a)
     {
       a.part_d[(size_t)blockIdx.x * a.nq + q0 + tid] = __longlong_as_double((long long)best64[tid]);
       a.part_i[(size_t)blockIdx.x * a.nq + q0 + tid] = bestidx[tid];
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// streaming scan for LARGE single-segment stores (BASELINE config 4: 2^20 nodes x 12 DoF):
+//   - node tiles of kStTile slots x D dimensions land in shared memory through 1-D bulk async copies
+//     (cp.async.bulk ... mbarrier::complete_tx, the TMA copy engine; kStStages tiles in flight per CTA,
+//     several CTAs per SM) and are consumed into registers at once, so HBM latency is hidden by the
+//     copy engine instead of by load instructions;
+//   - up to kStGQ queries share every tile: the node data is read once per query GROUP, the inner
+//     loop is the expanded form  c2 = |x|^2 + |q|^2 - 2 x.q  = D fused multiply-adds per (node, query)
+//     pair (half the instructions of sum (x-q)^2);
+//   - as everywhere in this file the fp32 value only PRE-SELECTS: its absolute error is bounded by
+//     e2 (see stream_e2), every node within the widened threshold goes to the fp64 decision.
+// MODE 0 nearest (per-CTA exact (dist, slot) minimum -> nn1_finalize_kernel), MODE 1 radius,
+// MODE 2 collect under a given per-query threshold (large-N k-nearest).
+// ---------------------------------------------------------------------------------------------
+constexpr int kStThreads = 128;
+constexpr int kStTile = kStThreads * kNodesPerThread;  // 512 nodes per tile
+constexpr int kStStages = 2;
+constexpr int kStGQ = 64;     // queries per group
+constexpr int kStList = 512;  // candidate list entries per CTA (MODE 0)
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count)
+{
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes)
+{
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
+{
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "GC_MBAR_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra GC_MBAR_DONE;\n"
+      "bra GC_MBAR_WAIT;\n"
+      "GC_MBAR_DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar)
+{
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+// order-preserving map float -> uint32 (negative values included: c2 can round slightly below zero)
+__device__ __forceinline__ uint32_t fkey(float f)
+{
+  const uint32_t b = __float_as_uint(f);
+  return b ^ ((uint32_t)((int32_t)b >> 31) | 0x80000000u);
+}
+// candidate threshold for a running minimum cmin of the expanded-form value c2 (absolute error <= e2 each):
+// a node whose fp64 distance is <= that of the argmin node has c2 <= (sqrt(cmin + e2) + 2 s_abs)^2 + e2
+__device__ __forceinline__ float stream_thr(float cmin, float e2, float slack_abs)
+{
+  const float b = sqrtf(fmaxf(cmin + e2, 0.0f)) * (1.0f + 1.0e-6f) + 3.0f * slack_abs;
+  return b * b * (1.0f + 1.0e-6f) + e2 * (1.0f + 1.0e-6f);
+}
+
+__device__ __forceinline__ float funkey(uint32_t k)
+{
+  return __uint_as_float((k & 0x80000000u) ? (k ^ 0x80000000u) : ~k);
+}
+
+constexpr int kStQPT = 4;              // queries per trip of the sweep (independent accumulator chains)
+constexpr uint32_t kStNoTile = 0xFFFFFFFFu;
+
+struct StreamSmem
+{
+  float* xs;            // [kStStages][D][kStTile]
+  uint64_t* bars;       // [kStStages]
+  double* q64;          // [kStGQ][D]
+  double* le;           // [kStList]  candidate: fp32 pre-selection value, then its exact distance
+  unsigned long long* best64;  // [kStGQ]
+  unsigned long long* prev64;  // [kStGQ]
+  float* qm2;           // [kStGQ][DP]  -2 * q (fp32)
+  float* qn;            // [kStGQ]      |q|^2 (fp32)
+  float* e2;            // [kStGQ]
+  float* thr;           // [kStGQ]
+  uint32_t* curkey;     // [kStGQ]
+  uint32_t* bestidx;    // [kStGQ]
+  uint32_t* lq;         // [kStList]
+  uint32_t* ls;         // [kStList]
+  uint32_t* cnt;        // [0] list length, [1] "this CTA finished last", [2..2+kStStages) tile of each stage
+};
+template <int D>
+__host__ __device__ constexpr size_t stream_smem_bytes()
+{
+  constexpr int DP = (D + 3) & ~3;
+  return sizeof(float) * kStStages * D * kStTile + 8 * kStStages + sizeof(double) * kStGQ * D + 8 * kStList +
+         16 * kStGQ + sizeof(float) * kStGQ * DP + 4 * 5 * kStGQ + 8 * kStList + 32;
+}
+
+// Tiles are handed out dynamically (one counter per query group), so CTAs that start late or run on a
+// busier SM simply take fewer tiles; the CTA that finishes last for its group resets the counters and, in
+// MODE 0, reduces the per-CTA (dist, slot) minima to the final answer (no separate finalize launch).
+template <int D, int MODE>
+__global__ void __launch_bounds__(kStThreads, 3) scan_stream_kernel(ScanArgs a)
+{
+  constexpr int DP = (D + 3) & ~3;
+  extern __shared__ __align__(128) unsigned char st_raw[];
+  StreamSmem m;
+  {
+    unsigned char* p = st_raw;
+    m.xs = reinterpret_cast<float*>(p);
+    p += sizeof(float) * kStStages * D * kStTile;
+    m.bars = reinterpret_cast<uint64_t*>(p);
+    p += 8 * kStStages;
+    m.q64 = reinterpret_cast<double*>(p);
+    p += sizeof(double) * kStGQ * D;
+    m.le = reinterpret_cast<double*>(p);
+    p += 8 * kStList;
+    m.best64 = reinterpret_cast<unsigned long long*>(p);
+    p += 8 * kStGQ;
+    m.prev64 = reinterpret_cast<unsigned long long*>(p);
+    p += 8 * kStGQ;
+    m.qm2 = reinterpret_cast<float*>(p);
+    p += sizeof(float) * kStGQ * DP;
+    m.qn = reinterpret_cast<float*>(p);
+    p += 4 * kStGQ;
+    m.e2 = reinterpret_cast<float*>(p);
+    p += 4 * kStGQ;
+    m.thr = reinterpret_cast<float*>(p);
+    p += 4 * kStGQ;
+    m.curkey = reinterpret_cast<uint32_t*>(p);
+    p += 4 * kStGQ;
+    m.bestidx = reinterpret_cast<uint32_t*>(p);
+    p += 4 * kStGQ;
+    m.lq = reinterpret_cast<uint32_t*>(p);
+    p += 4 * kStList;
+    m.ls = reinterpret_cast<uint32_t*>(p);
+    p += 4 * kStList;
+    m.cnt = reinterpret_cast<uint32_t*>(p);
+  }
+  const int tid = threadIdx.x;
+  const uint32_t q0 = blockIdx.y * a.group_size;
+  const int gq = (int)min(a.group_size, a.nq - q0);
+  const int gqp = (gq + kStQPT - 1) / kStQPT * kStQPT;  // padded with inert queries up to a whole trip
+  const uint32_t n_s = a.used[0];
+  const uint32_t ntiles = (n_s + kStTile - 1) / kStTile;
+  uint32_t* tile_ctr = a.ctl + 2 * blockIdx.y;
+  uint32_t* done_ctr = tile_ctr + 1;
+  volatile uint32_t* tile_of = m.cnt + 2;
+
+  // take the next tile of this group and put its D rows in flight (thread 0 only)
+  auto fetch = [&](int stage) {
+    const uint32_t t = atomicAdd(tile_ctr, 1u);
+    if (t < ntiles)
+    {
+      tile_of[stage] = t;
+      mbar_expect_tx(&m.bars[stage], (uint32_t)(D * kStTile * sizeof(float)));
+#pragma unroll
+      for (int d = 0; d < D; d++)
+        bulk_g2s(m.xs + ((size_t)stage * D + d) * kStTile, a.x32 + (size_t)d * a.row_stride + (size_t)t * kStTile,
+                 (uint32_t)(kStTile * sizeof(float)), &m.bars[stage]);
+    }
+    else
+      tile_of[stage] = kStNoTile;
+  };
+  if (tid == 0)
+  {
+    for (int s = 0; s < kStStages; s++)
+      mbar_init(&m.bars[s], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    m.cnt[0] = 0;
+    m.cnt[1] = 0;
+    for (int s = 0; s < kStStages; s++)  // the node data starts moving before the queries are even read
+      fetch(s);
+  }
+  for (int i = tid; i < gqp * DP; i += kStThreads)
+  {
+    const int q = i / DP, d = i % DP;
+    const double v = (q < gq && d < D) ? a.q[(size_t)(q0 + q) * D + d] : 0.0;
+    if (d < D)
+      m.q64[q * D + d] = v;
+    m.qm2[i] = -2.0f * (float)v;
+  }
+  __syncthreads();
+  if (tid < gqp)
+  {
+    float qn = 0.0f;
+#pragma unroll
+    for (int d = 0; d < D; d++)
+    {
+      const float v = (float)m.q64[tid * D + d];
+      qn = fmaf(v, v, qn);
+    }
+    // absolute error bound of the expanded form: each of its ~3D+2 roundings is <= 2^-24 times a partial sum that
+    // never exceeds 2 (|x|^2 + |q|^2); a factor 1.5 on top
+    const float e2 = (float)(3 * D + 8) * 5.9604645e-8f * 1.5f * (a.xn_max + qn) * 2.0f + FLT_MIN;
+    m.e2[tid] = e2;
+    m.curkey[tid] = fkey(CUDART_INF_F);
+    m.best64[tid] = 0x7ff0000000000000ull;
+    m.prev64[tid] = 0x7ff0000000000000ull;
+    m.bestidx[tid] = GC_NO_NODE;
+    float thr = CUDART_INF_F;
+    if (MODE == 1 && tid < gq)
+    {
+      const double r = a.radius[q0 + tid];
+      const float rf = (r > 0.0) ? (float)fmin(r, 1.0e18) : -1.0f;
+      if (rf < 0.0f)
+        thr = -CUDART_INF_F;
+      else
+      {
+        const float b = rf * (1.0f + 1.0e-6f) + 3.0f * a.slack_abs;
+        thr = b * b * (1.0f + 1.0e-6f) + e2 * (1.0f + 1.0e-6f);
+      }
+    }
+    if (MODE == 2 && tid < gq)
+      thr = a.thr2[q0 + tid] * (1.0f + 8.0e-6f) + e2 * (1.0f + 1.0e-6f);
+    if (tid >= gq)  // inert query: |q|^2 = +inf makes every value +inf, which never passes "< +inf"
+    {
+      qn = CUDART_INF_F;
+      thr = -CUDART_INF_F;
+    }
+    m.qn[tid] = qn;
+    m.thr[tid] = thr;
+  }
+  __syncthreads();
+
+  volatile float* thr_v = m.thr;
+  // MODE 0: the running fp32 minimum is shared between the CTAs of a query group through a.gmin (relaxed: a stale
+  // value only makes the candidate threshold looser)
+  auto exchange = [&]() {
+    if (tid < gq)
+    {
+      const uint32_t mine = m.curkey[tid];
+      uint32_t g = *reinterpret_cast<volatile uint32_t*>(a.gmin + q0 + tid);
+      if (mine < g)
+        g = min(mine, atomicMin(a.gmin + q0 + tid, mine));
+      if (g < mine)
+        m.curkey[tid] = g;
+      if (g != fkey(CUDART_INF_F) && g <= mine)
+        thr_v[tid] = stream_thr(funkey(g), m.e2[tid], a.slack_abs);
+    }
+  };
+  for (uint32_t it = 0;; it++)
+  {
+    const int stage = (int)(it % kStStages);
+    const uint32_t tile = tile_of[stage];
+    if (tile == kStNoTile)  // CTA-uniform
+      break;
+    mbar_wait(&m.bars[stage], (it / kStStages) & 1u);
+    const uint32_t local0 = tile * kStTile + tid * kNodesPerThread;
+    float x[D][kNodesPerThread];
+#pragma unroll
+    for (int d = 0; d < D; d++)
+    {
+      const float4 v = *reinterpret_cast<const float4*>(m.xs + ((size_t)stage * D + d) * kStTile + tid * kNodesPerThread);
+      x[d][0] = v.x;
+      x[d][1] = v.y;
+      x[d][2] = v.z;
+      x[d][3] = v.w;
+    }
+    __syncthreads();  // every thread holds its nodes in registers: the stage can be refilled
+    if (tid == 0)
+      fetch(stage);
+    float xn[kNodesPerThread];
+#pragma unroll
+    for (int r = 0; r < kNodesPerThread; r++)
+    {
+      float s2 = 0.0f;
+#pragma unroll
+      for (int d = 0; d < D; d++)
+        s2 = fmaf(x[d][r], x[d][r], s2);
+      // slots beyond the used range, tombstones (x32[0] = +inf) and NaNs never qualify: |x|^2 = +inf, x = 0
+      const bool valid = (local0 + r < n_s) && (s2 < CUDART_INF_F);
+      xn[r] = valid ? s2 : CUDART_INF_F;
+      if (!valid)
+      {
+#pragma unroll
+        for (int d = 0; d < D; d++)
+          x[d][r] = 0.0f;
+      }
+    }
+    // expanded-form values of this thread's four nodes against queries q .. q+kStQPT-1
+    auto trip_values = [&](int q, float (&acc)[kStQPT][kNodesPerThread]) {
+      const float4 qn4 = *reinterpret_cast<const float4*>(m.qn + q);
+      const float qna[4] = { qn4.x, qn4.y, qn4.z, qn4.w };
+#pragma unroll
+      for (int h = 0; h < kStQPT; h++)
+#pragma unroll
+        for (int r = 0; r < kNodesPerThread; r++)
+          acc[h][r] = xn[r] + qna[h];
+#pragma unroll
+      for (int d4 = 0; d4 < DP; d4 += 4)
+      {
+        float qa[kStQPT][4];
+#pragma unroll
+        for (int h = 0; h < kStQPT; h++)
+        {
+          const float4 u = *reinterpret_cast<const float4*>(m.qm2 + (q + h) * DP + d4);
+          qa[h][0] = u.x;
+          qa[h][1] = u.y;
+          qa[h][2] = u.z;
+          qa[h][3] = u.w;
+        }
+#pragma unroll
+        for (int j = 0; j < 4; j++)
+          if (d4 + j < D)
+          {
+#pragma unroll
+            for (int h = 0; h < kStQPT; h++)
+#pragma unroll
+              for (int r = 0; r < kNodesPerThread; r++)
+                acc[h][r] = fmaf(x[d4 + j][r], qa[h][j], acc[h][r]);
+          }
+      }
+    };
+    if (MODE == 0 && it == 0)
+    {
+      // priming pass over the CTA's first tile: only the running minima (warp reduction, one atomic per warp)
+      for (int q = 0; q < gqp; q += kStQPT)
+      {
+        float acc[kStQPT][kNodesPerThread];
+        trip_values(q, acc);
+#pragma unroll
+        for (int h = 0; h < kStQPT; h++)
+        {
+          const float tmin = fminf(fminf(acc[h][0], acc[h][1]), fminf(acc[h][2], acc[h][3]));
+          const uint32_t wmin = __reduce_min_sync(0xffffffffu, fkey(tmin));  // NaN keys sort above +inf
+          if ((tid & 31) == 0 && wmin < m.curkey[q + h])
+            atomicMin(&m.curkey[q + h], wmin);
+        }
+      }
+      __syncthreads();
+      exchange();
+      __syncthreads();
+    }
+    for (int q = 0; q < gqp; q += kStQPT)
+    {
+      float acc[kStQPT][kNodesPerThread];
+      trip_values(q, acc);
+      const float4 th4 = *reinterpret_cast<const float4*>(m.thr + q);
+      const float tha[4] = { th4.x, th4.y, th4.z, th4.w };
+      float tmin[kStQPT];
+      bool any = false;
+#pragma unroll
+      for (int h = 0; h < kStQPT; h++)
+      {
+        tmin[h] = fminf(fminf(acc[h][0], acc[h][1]), fminf(acc[h][2], acc[h][3]));
+        any |= (tmin[h] <= tha[h]);
+      }
+      if (any)  // rare: at least one of this thread's 16 values is a candidate
+      {
+#pragma unroll
+        for (int h = 0; h < kStQPT; h++)
+        {
+          float thr = tha[h];
+          if (tmin[h] <= thr && tmin[h] < CUDART_INF_F)
+          {
+            const int qq = q + h;
+            if (MODE == 0)
+            {
+              const uint32_t key = fkey(tmin[h]);
+              if (key < m.curkey[qq] && key < atomicMin(&m.curkey[qq], key))
+              {
+                thr = stream_thr(tmin[h], m.e2[qq], a.slack_abs);
+                thr_v[qq] = thr;  // a racing larger value is still a valid (looser) bound
+              }
+#pragma unroll
+              for (int r = 0; r < kNodesPerThread; r++)
+                if (acc[h][r] <= thr)
+                {
+                  const uint32_t pos = atomicAdd(m.cnt, 1u);
+                  if (pos < (uint32_t)kStList)
+                  {
+                    m.lq[pos] = (uint32_t)qq;
+                    m.ls[pos] = local0 + r;
+                    m.le[pos] = (double)acc[h][r];
+                  }
+                }
+            }
+            else
+            {
+#pragma unroll
+              for (int r = 0; r < kNodesPerThread; r++)
+                if (acc[h][r] <= thr && acc[h][r] < CUDART_INF_F)
+                {
+                  const double e = dist64<D>(a.x64 + (size_t)(local0 + r) * D, m.q64 + qq * D);
+                  if (MODE == 2 || e < a.radius[q0 + qq])
+                  {
+                    const uint32_t pos = atomicAdd(&a.out_count[q0 + qq], 1u);
+                    if (pos < a.cap)
+                    {
+                      a.out_idx[(size_t)(q0 + qq) * a.cap + pos] = local0 + r;
+                      a.out_dist[(size_t)(q0 + qq) * a.cap + pos] = e;
+                    }
+                  }
+                }
+            }
+          }
+        }
+      }
+    }
+    if (MODE == 0)
+    {
+      __syncthreads();
+      const uint32_t cnt = m.cnt[0];
+      const bool last = (tile_of[(it + 1) % kStStages] == kStNoTile);
+      if (it < 4 || (it & 7u) == 7u || last)
+        exchange();
+      // the candidate list is kept across tiles and resolved when it is half full or at the end: by then the
+      // (shared) thresholds are much tighter than when the entries were made and most of them drop out
+      if (cnt > (uint32_t)kStList / 2 || (last && cnt > 0))  // CTA-uniform
+      {
+        __syncthreads();
+        const uint32_t nl = min(cnt, (uint32_t)kStList);
+        // A: exact distances of the surviving candidates -> running exact minimum per query
+        for (uint32_t i = tid; i < nl; i += kStThreads)
+        {
+          const uint32_t q = m.lq[i];
+          double e = CUDART_INF;
+          if ((float)m.le[i] <= thr_v[q])
+          {
+            e = dist64<D>(a.x64 + (size_t)m.ls[i] * D, m.q64 + q * D);
+            atomicMin(&m.best64[q], (unsigned long long)__double_as_longlong(e));
+          }
+          else
+            m.ls[i] = GC_NO_NODE;
+          m.le[i] = e;
+        }
+        double eo[kNodesPerThread];
+        bool co[kNodesPerThread];
+        if (cnt > (uint32_t)kStList)
+        {
+          // the list overflowed inside this tile (massively duplicated points): exact pass over the tile's
+          // nodes, query by query (entries that did fit are handled twice, harmlessly)
+          for (int q = 0; q < gq; q++)
+          {
+            const float qn = m.qn[q];
+            const float thr = thr_v[q];
+#pragma unroll
+            for (int r = 0; r < kNodesPerThread; r++)
+            {
+              float acc = xn[r] + qn;
+#pragma unroll
+              for (int d = 0; d < D; d++)
+                acc = fmaf(x[d][r], m.qm2[q * DP + d], acc);
+              co[r] = (acc <= thr) && (acc < CUDART_INF_F);
+              eo[r] = 0.0;
+              if (co[r])
+              {
+                eo[r] = dist64<D>(a.x64 + (size_t)(local0 + r) * D, m.q64 + q * D);
+                atomicMin(&m.best64[q], (unsigned long long)__double_as_longlong(eo[r]));
+              }
+            }
+            __syncthreads();
+            if (tid == 0 && m.best64[q] != m.prev64[q])
+            {
+              m.bestidx[q] = GC_NO_NODE;
+              m.prev64[q] = m.best64[q];
+            }
+            __syncthreads();
+#pragma unroll
+            for (int r = 0; r < kNodesPerThread; r++)
+              if (co[r] && (unsigned long long)__double_as_longlong(eo[r]) == m.best64[q])
+                atomicMin(&m.bestidx[q], local0 + r);
+          }
+        }
+        __syncthreads();
+        // B: a strictly smaller exact minimum invalidates the slot kept for the old one
+        if (tid < gq && m.best64[tid] != m.prev64[tid])
+        {
+          m.bestidx[tid] = GC_NO_NODE;
+          m.prev64[tid] = m.best64[tid];
+        }
+        __syncthreads();
+        // C: lowest slot among the candidates that attain the exact minimum
+        for (uint32_t i = tid; i < nl; i += kStThreads)
+        {
+          const uint32_t q = m.lq[i];
+          if (m.ls[i] != GC_NO_NODE && (unsigned long long)__double_as_longlong(m.le[i]) == m.best64[q])
+            atomicMin(&m.bestidx[q], m.ls[i]);
+        }
+        __syncthreads();
+        if (tid == 0)
+          m.cnt[0] = 0;
+        // the next tile's first list append happens after that tile's own barriers
+      }
+    }
+  }
+  // ---- epilogue: per-CTA partials, last-CTA-done reduction, counter reset ---------------------------------
+  __syncthreads();
+  if (MODE == 0 && tid < gq)
+  {
+    a.part_d[(size_t)blockIdx.x * a.nq + q0 + tid] = __longlong_as_double((long long)m.best64[tid]);
+    a.part_i[(size_t)blockIdx.x * a.nq + q0 + tid] = m.bestidx[tid];
+  }
+  __threadfence();
+  __syncthreads();
+  if (tid == 0)
+    m.cnt[1] = (atomicAdd(done_ctr, 1u) == gridDim.x - 1) ? 1u : 0u;
+  __syncthreads();
+  if (m.cnt[1])
+  {
+    __threadfence();
+    if (MODE == 0)
+    {
+      // lexicographic (dist, slot) minimum over the CTAs of this group: one warp per query, lanes over CTAs
+      const int lane = tid & 31, warp = tid >> 5;
+      for (int q = warp; q < gq; q += kStThreads / 32)
+      {
+        double bd = CUDART_INF;
+        uint32_t bi = GC_NO_NODE;
+        for (uint32_t c = lane; c < gridDim.x; c += 32)
+        {
+          const double d = __ldcg(a.part_d + (size_t)c * a.nq + q0 + q);
+          const uint32_t i = __ldcg(a.part_i + (size_t)c * a.nq + q0 + q);
+          if (i != GC_NO_NODE && (d < bd || (d == bd && i < bi)))
+          {
+            bd = d;
+            bi = i;
+          }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1)
+        {
+          const double od = __shfl_xor_sync(0xffffffffu, bd, o);
+          const uint32_t oi = __shfl_xor_sync(0xffffffffu, bi, o);
+          if (oi != GC_NO_NODE && (od < bd || (od == bd && oi < bi)))
+          {
+            bd = od;
+            bi = oi;
+          }
+        }
+        if (lane == 0)
+        {
+          a.out_idx[q0 + q] = bi;
+          a.out_dist[q0 + q] = bd;
+          a.gmin[q0 + q] = 0xFFFFFFFFu;  // ready for the next launch
+        }
+      }
+    }
+    if (tid == 0)
+    {
+      *tile_ctr = 0;
+      *done_ctr = 0;
     }
   }
 }
@@ -778,6 +1330,68 @@ static void scan_grid(const gc_store* s, uint32_t nq, bool per_query_seg, uint32
   *chunks = c;
 }
 
+// streaming scan (scan_stream_kernel): single-segment stores from kStreamMinNodes slots up
+constexpr uint32_t kStreamMinNodes = 32768;
+static bool use_stream(const gc_store* s, const uint32_t* d_seg)
+{
+  return d_seg == nullptr && s->used[0] >= kStreamMinNodes;
+}
+// control words of the streaming scan: gmin[nq] (0xFF..) then ctl[groups][2] (0).  The kernels leave them in
+// their initial state, so they are only (re)initialised when the buffer has to grow.
+static int ensure_stream_ctl(gc_store* s, uint32_t nq, uint32_t groups, uint32_t** gmin, uint32_t** ctl)
+{
+  const size_t need_q = std::max<size_t>(nq, 4096), need_g = std::max<size_t>(groups, 4096);
+  if (s->stream_ctl_q < need_q || s->stream_ctl_g < need_g)
+  {
+    GC_CUDA(cudaStreamSynchronize(s->stream));
+    GC_TRY(s->d_gmin.reserve(sizeof(uint32_t) * (need_q + 2 * need_g)));
+    GC_CUDA(cudaMemsetAsync(s->d_gmin.p, 0xFF, sizeof(uint32_t) * need_q, s->stream));
+    GC_CUDA(cudaMemsetAsync(s->d_gmin.as<uint32_t>() + need_q, 0, sizeof(uint32_t) * 2 * need_g, s->stream));
+    s->stream_ctl_q = need_q;
+    s->stream_ctl_g = need_g;
+  }
+  *gmin = s->d_gmin.as<uint32_t>();
+  *ctl = s->d_gmin.as<uint32_t>() + s->stream_ctl_q;
+  return GC_OK;
+}
+
+// MODE 0 writes the final (idx, dist) itself: a.out_idx / a.out_dist must point at the [nq] result arrays
+template <int MODE>
+static int launch_stream(gc_store* s, ScanArgs& a, uint32_t nq)
+{
+  const uint32_t groups = (nq + kStGQ - 1) / kStGQ;
+  a.group_size = (nq + groups - 1) / groups;
+  const uint32_t ntiles = (s->used[0] + kStTile - 1) / kStTile;
+  double m = 0.0;
+  for (double v : s->max_abs)
+    m = fmax(m, v);
+  a.xn_max = (float)fmin((double)s->dim * m * m * 1.000001, 3.0e38);
+  GC_TRY(ensure_stream_ctl(s, nq, groups, &a.gmin, &a.ctl));
+  static int occ[GC_MAX_DIM + 1] = {};
+  int blocks = 0;
+  GC_DISPATCH_DIM(
+      s->dim, constexpr size_t smem = stream_smem_bytes<DD>(); if (!occ[DD]) {
+        GC_CUDA(cudaFuncSetAttribute(scan_stream_kernel<DD, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        GC_CUDA(cudaFuncSetAttribute(scan_stream_kernel<DD, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        GC_CUDA(cudaFuncSetAttribute(scan_stream_kernel<DD, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int b = 0;
+        GC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, scan_stream_kernel<DD, 0>, kStThreads, smem));
+        occ[DD] = b > 0 ? b : 1;
+      } blocks = occ[DD];
+      // CTAs per group: enough to fill every SM slot; tiles are handed out dynamically, so a few CTAs more than
+      // slots cost nothing (late starters find the counter exhausted)
+      uint32_t chunks = ((uint32_t)(s->sms * blocks) + groups - 1) / groups; if (chunks > ntiles) chunks = ntiles;
+      if (chunks < 1) chunks = 1; if (MODE == 0) {
+        GC_TRY(s->d_part.reserve((size_t)chunks * nq * (sizeof(double) + sizeof(uint32_t))));
+        a.part_d = s->d_part.as<double>();
+        a.part_i = reinterpret_cast<uint32_t*>(a.part_d + (size_t)chunks * nq);
+      } dim3 grid(chunks, groups);
+      (scan_stream_kernel<DD, MODE><<<grid, kStThreads, smem, s->stream>>>(a)));
+  GC_CUDA(cudaGetLastError());
+  count_launch();
+  return GC_OK;
+}
+
 int nn1_dev(gc_store* s, const double* d_q, const uint32_t* d_seg, uint32_t nq, uint32_t* d_idx, double* d_dist,
             bool)
 {
@@ -799,6 +1413,12 @@ int nn1_dev(gc_store* s, const double* d_q, const uint32_t* d_seg, uint32_t nq, 
   a.slack_abs = (float)(store_slack(s) * 1.0000001) + FLT_MIN;
   a.part_d = s->d_part.as<double>();
   a.part_i = reinterpret_cast<uint32_t*>(a.part_d + (size_t)chunks * nq);
+  if (use_stream(s, d_seg))
+  {
+    a.out_idx = d_idx;
+    a.out_dist = d_dist;
+    return launch_stream<0>(s, a, nq);
+  }
   dim3 grid(chunks, groups);
   GC_DISPATCH_DIM(s->dim, (scan_kernel<DD, 0><<<grid, kScanThreads, 0, s->stream>>>(a)));
   GC_CUDA(cudaGetLastError());
@@ -858,6 +1478,11 @@ int radius_dev(gc_store* s, const double* d_q, const uint32_t* d_seg, const doub
   a.out_idx = d_idx;
   a.out_dist = d_dist;
   a.out_count = d_count;
+  if (use_stream(s, d_seg))
+  {
+    GC_TRY(launch_stream<1>(s, a, nq));
+    return sort_lists(s, nq, cap, d_idx, d_dist, d_count);
+  }
   dim3 grid(chunks, groups);
   GC_DISPATCH_DIM(s->dim, (scan_kernel<DD, 1><<<grid, kScanThreads, 0, s->stream>>>(a)));
   GC_CUDA(cudaGetLastError());
@@ -930,9 +1555,14 @@ static int knn_large_dev(gc_store* s, const double* d_q, const uint32_t* d_seg, 
     a.out_idx = s->d_cand_idx.as<uint32_t>();
     a.out_dist = s->d_cand_dist.as<double>();
     a.out_count = s->d_cand_count.as<uint32_t>();
-    dim3 grid(chunks, groups);
-    GC_DISPATCH_DIM(s->dim, (scan_kernel<DD, 2><<<grid, kScanThreads, 0, s->stream>>>(a)));
-    GC_CUDA(cudaGetLastError());
+    if (use_stream(s, d_seg))
+      GC_TRY(launch_stream<2>(s, a, nqc));
+    else
+    {
+      dim3 grid(chunks, groups);
+      GC_DISPATCH_DIM(s->dim, (scan_kernel<DD, 2><<<grid, kScanThreads, 0, s->stream>>>(a)));
+      GC_CUDA(cudaGetLastError());
+    }
     select_topk_kernel<<<nqc, 1024, smem_sel, s->stream>>>(a.out_idx, a.out_dist, a.out_count, capB,
                                                            (unsigned long long)k, cap, d_idx + (size_t)q0 * cap,
                                                            d_dist + (size_t)q0 * cap, d_count + q0, d_err, kSortMax);
@@ -1063,6 +1693,7 @@ int gc_store_destroy(gc_store_t* s)
   s->d_count.release(); s->d_part.release(); s->d_misc.release(); s->d_rows.release(); s->d_slots.release();
   s->h_in.release(); s->h_out.release();
   s->d_cand_idx.release(); s->d_cand_dist.release(); s->d_cand_count.release(); s->d_thr.release();
+  s->d_gmin.release();
   if (s->own_stream)
     cudaStreamDestroy(s->own_stream);
   delete s;

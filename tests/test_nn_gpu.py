@@ -259,3 +259,72 @@ def test_large_tree_c4_shape(gc, orc):
     # one query at a time (the HBM-bound regime) gives the same answers as the tiled batch
     idx1, dist1 = st.nearest(qs[:1])
     assert idx1[0] == idx[0] and dist1[0] == dist[0]
+
+
+# ---- streaming scan (scan_stream_kernel: bulk-copy staged tiles, expanded-form fp32 pre-selection) -------
+@pytest.mark.parametrize("dim,n,nq", [(2, 40_000, 5), (7, 70_001, 65), (12, 120_000, 200), (16, 33_000, 1)])
+def test_stream_scan_matches_oracle(gc, orc, dim, n, nq):
+    pts = W.c4_nodes(n, dim, seed=500 + dim)
+    qs = W.c4_queries(nq, dim, seed=600 + dim)
+    qs[0] = pts[n // 3]                       # a query that coincides with a node (distance exactly 0)
+    st, ov = _mk(gc, orc, pts)
+    idx, dist = st.nearest(qs)
+    iv, dv = ov.nearest(qs)
+    assert np.array_equal(idx.astype(np.int64), iv.astype(np.int64)) and np.array_equal(dist, dv)
+    assert idx[0] == n // 3 and dist[0] == 0.0
+    radius = W.c4_radius(40, n, dim)
+    gi, gd, gcnt = st.near(qs, radius, cap=2048)
+    oi, od, ocnt = ov.near(qs, radius, cap=2048)
+    assert np.array_equal(gcnt.astype(np.int64), ocnt.astype(np.int64))
+    for i in range(nq):
+        assert np.array_equal(gi[i, :gcnt[i]].astype(np.int64), oi[i, :ocnt[i]].astype(np.int64))
+        assert np.array_equal(gd[i, :gcnt[i]], od[i, :ocnt[i]])
+    for k in (1, 9, 130):
+        ki, kd, kc = st.knn(qs, k, cap=k)
+        oi, od, oc = ov.knn(qs, k, cap=k)
+        assert np.array_equal(kc.astype(np.int64), oc.astype(np.int64))
+        assert np.array_equal(ki.astype(np.int64), oi.astype(np.int64)) and np.array_equal(kd, od)
+    # tombstones: the nearest node of every query disappears, then comes back
+    victims = np.unique(idx)
+    for v in victims:
+        st.tombstone(int(v))
+        ov.delete(int(v))
+    idx2, dist2 = st.nearest(qs)
+    iv2, dv2 = ov.nearest(qs)
+    assert np.array_equal(idx2.astype(np.int64), iv2.astype(np.int64)) and np.array_equal(dist2, dv2)  # ids = pool ids
+    for v in victims:
+        st.restore(int(v))
+    idx3, dist3 = st.nearest(qs)
+    assert np.array_equal(idx3, idx) and np.array_equal(dist3, dist)
+
+
+def test_stream_scan_massive_duplicates_take_lowest_slot(gc, orc):
+    """Every node is one of three points: all of them tie exactly, the candidate list overflows and the exact
+    per-tile pass must still return the lowest slot (vector.cpp:55-67 strict '<' in insertion order)."""
+    n, dim = 50_000, 7
+    base = W.c4_nodes(3, dim, seed=9)
+    which = (np.arange(n) * 7919 % 3)
+    pts = base[which]
+    st = gc.NodeStore(dim, n)
+    st.append(pts)
+    qs = np.concatenate([base, base + 1e-9, W.c4_queries(6, dim, seed=10)])
+    idx, dist = st.nearest(qs)
+    d = np.sqrt(((base[None, :, :] - qs[:, None, :]) ** 2).sum(-1))
+    for i in range(len(qs)):
+        b = int(np.argmin(d[i]))
+        first = int(np.nonzero(which == b)[0][0])
+        assert idx[i] == first, (i, idx[i], first)
+    # fp64 near-ties that fp32 cannot separate: the fp64 decision picks the truly closer point
+    a = np.zeros((40_000, 3))
+    a[:, 0] = 1.0 + np.arange(40_000) * 1e-3
+    a[1234] = [0.5, 0.0, 0.0]
+    a[30_000] = [0.5 - 1e-12, 0.0, 0.0]
+    st2 = gc.NodeStore(3, 40_000)
+    st2.append(a)
+    i2, d2 = st2.nearest(np.zeros((1, 3)))
+    assert i2[0] == 30_000 and d2[0] == 0.5 - 1e-12
+    a[30_000] = [0.5, 0.0, 0.0]                # exact tie now: lowest slot
+    st3 = gc.NodeStore(3, 40_000)
+    st3.append(a)
+    i3, d3 = st3.nearest(np.zeros((1, 3)))
+    assert i3[0] == 1234 and d3[0] == 0.5
