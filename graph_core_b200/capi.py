@@ -72,6 +72,7 @@ PROTOTYPES = {
     "gc_world_create_sphere_arm": (C.c_int, [C.c_int, _c_float_p, _c_float_p, C.c_uint32, _c_i32_p, _c_float_p,
                                              C.c_uint32, _c_float_p, C.c_int, C.POINTER(C.c_void_p)]),
     "gc_world_retain": (C.c_int, [C.c_void_p]),
+    "gc_world_clone": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
     "gc_world_destroy": (C.c_int, [C.c_void_p]),
     "gc_world_set_stream": (C.c_int, [C.c_void_p, C.c_void_p]),
     "gc_world_dim": (C.c_int, [C.c_void_p]),
@@ -342,8 +343,9 @@ class CollisionWorld:
 
     def clone(self):
         """CollisionCheckerBase::clone: an independent host object sharing the immutable device world."""
-        _check(self._lib.gc_world_retain(self._h))
-        return CollisionWorld(self._h, self.dim, self._lib)
+        h = C.c_void_p()
+        _check(self._lib.gc_world_clone(self._h, C.byref(h)))
+        return CollisionWorld(h, self.dim, self._lib)
 
     def close(self):
         if getattr(self, "_h", None):

@@ -23,6 +23,8 @@
 #include <cfloat>
 #include <cmath>
 
+#include <cstdlib>
+
 #include "gc_common.cuh"
 
 namespace gc
@@ -532,6 +534,9 @@ __device__ __forceinline__ bool arm_check_lane(const ArmSmem& w, uint32_t nrs, u
       sk[k].B = 3.0e38f;
     }
   }
+  // Obstacles part, part+nparts, ...  Any sphere hits obstacle o  <=>  min_k t_k < NA_o, so the sixteen
+  // compares collapse into a min tree (FMNMX3) and ONE compare per obstacle; the next obstacle is
+  // loaded while the current one is evaluated; the early-exit test runs once per 16 obstacles.
   // Obstacles part, part+nparts, ...  Any sphere hits obstacle o  <=>  min_k t_k < NA_o, so the sixteen
   // compares collapse into a min tree (FMNMX3) and ONE compare per obstacle; the next obstacle is
   // loaded while the current one is evaluated; the early-exit test runs once per 16 obstacles.
@@ -1350,7 +1355,31 @@ int gc_world_create_sphere_arm(int njoints, const float* base_tf, const float* j
 int gc_world_retain(gc_world_t* w)
 {
   GC_REQUIRE(w != nullptr, "gc_world_retain: NULL");
-  w->refs++;
+  __atomic_add_fetch(&w->refs, 1, __ATOMIC_SEQ_CST);
+  return GC_OK;
+}
+
+// An independent handle on the same immutable device world: own stream, scratch buffers, counters and timing,
+// so clones can be driven from different host threads (CollisionCheckerBase::clone, :319, exists for that).
+int gc_world_clone(gc_world_t* w, gc_world_t** out)
+{
+  GC_REQUIRE(w != nullptr && out != nullptr, "gc_world_clone: NULL");
+  gc_world* root = w->parent ? w->parent : w;
+  gc_world* c = nullptr;
+  GC_TRY(world_new(w->kind, w->dim, w->device, &c));
+  c->cube_thr = root->cube_thr;
+  c->nobj = root->nobj;
+  c->njoints = root->njoints;
+  c->nrs = root->nrs;
+  c->d_lo = root->d_lo;
+  c->d_hi = root->d_hi;
+  c->d_sc = root->d_sc;
+  c->d_sr2 = root->d_sr2;
+  c->d_arm = root->d_arm;
+  c->d_obs = root->d_obs;
+  c->parent = root;
+  __atomic_add_fetch(&root->refs, 1, __ATOMIC_SEQ_CST);
+  *out = c;
   return GC_OK;
 }
 
@@ -1358,12 +1387,15 @@ int gc_world_destroy(gc_world_t* w)
 {
   if (!w)
     return GC_OK;
-  if (--w->refs > 0)
+  if (__atomic_sub_fetch(&w->refs, 1, __ATOMIC_SEQ_CST) > 0)
     return GC_OK;
   gc::CtxGuard gc_ctx_guard_;
   cudaSetDevice(w->device);
   if (w->own_stream)
     cudaStreamSynchronize(w->own_stream);
+  gc_world* parent = w->parent;
+  if (parent)  // the device world belongs to the parent
+    w->d_lo = w->d_hi = nullptr, w->d_sc = w->d_sr2 = w->d_arm = w->d_obs = nullptr;
   cudaFree(w->d_lo); cudaFree(w->d_hi); cudaFree(w->d_sc); cudaFree(w->d_sr2);
   cudaFree(w->d_arm); cudaFree(w->d_obs); cudaFree(w->d_counters);
   w->d_c1.release(); w->d_c2.release(); w->d_c3.release(); w->d_ok.release(); w->d_first.release();
@@ -1373,6 +1405,8 @@ int gc_world_destroy(gc_world_t* w)
     cudaEventDestroy(ev);
   if (w->own_stream) cudaStreamDestroy(w->own_stream);
   delete w;
+  if (parent)
+    gc_world_destroy(parent);
   return GC_OK;
 }
 

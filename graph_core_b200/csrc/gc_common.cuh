@@ -125,6 +125,7 @@ struct gc_world
   int kind = 0;
   int dim = 0;
   int refs = 1;
+  gc_world* parent = nullptr;  // gc_world_clone: the world that owns the immutable device data
   // cube
   double cube_thr = 1.0;
   // generic object count (boxes / cspheres / obstacle spheres)

@@ -326,7 +326,12 @@ CudaCollisionChecker::~CudaCollisionChecker()
 // CollisionCheckerBase::clone (:319): an independent host object; the immutable device world is shared
 CollisionCheckerPtr CudaCollisionChecker::clone()
 {
-  return std::make_shared<CudaCollisionChecker>(logger_, world_, min_distance_);
+  gc_world_t* c = nullptr;
+  if (gc_world_clone(world_, &c) != GC_OK)
+    raise("gc_world_clone");
+  auto out = std::make_shared<CudaCollisionChecker>(logger_, c, min_distance_);  // retains c
+  gc_world_destroy(c);                                                           // drop the creation reference
+  return out;
 }
 
 bool CudaCollisionChecker::check(const Eigen::VectorXd& configuration)

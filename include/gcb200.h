@@ -119,7 +119,10 @@ int gc_world_create_cspheres(int dim, uint32_t n, const float* centers, const fl
 int gc_world_create_sphere_arm(int njoints, const float* base_tf, const float* joint_tf, uint32_t nrs,
                                const int32_t* rs_link, const float* rs_local, uint32_t nobs, const float* obs,
                                int device, gc_world_t** out);
-int gc_world_retain(gc_world_t* w);  /* CollisionCheckerBase::clone shares the immutable device world */
+int gc_world_retain(gc_world_t* w);  /* one more owner of the SAME handle (not for concurrent use)         */
+/* CollisionCheckerBase::clone (:319): a new handle with its own stream, scratch and counters that shares the
+ * immutable device world; handle and clone may be used from different host threads */
+int gc_world_clone(gc_world_t* w, gc_world_t** out);
 int gc_world_destroy(gc_world_t* w); /* drops one reference */
 int gc_world_set_stream(gc_world_t* w, void* cuda_stream);
 int gc_world_dim(gc_world_t* w);

@@ -164,3 +164,29 @@ def test_large_edge_batch_lane_per_state_path(gc, orc, c3):
     ok, fb = gw.check_connection(a, b, c3.min_distance, mode=1)
     wok, wfb, _ = ow.check_connection(a, b, c3.min_distance, mode=1)
     assert np.array_equal(ok, wok) and np.array_equal(fb, wfb)
+
+
+def test_clones_are_independent_handles_across_threads(gc, orc, c3):
+    """CollisionCheckerBase::clone (:319) exists so that several threads can check at once: gc_world_clone gives
+    every thread its own stream / scratch / counters over the one immutable device world."""
+    import threading
+    root = c3.make_world()
+    ow = orc.OracleWorld.from_scenario(c3)
+    batches = [_segments(c3, 300, 960 + t, 0.2, 0.9) for t in range(4)]
+    want = [ow.check_connection(a, b, c3.min_distance) for a, b in batches]
+    clones = [root.clone() for _ in range(4)]
+    root.close()  # clones keep the device world alive
+    got = [None] * 4
+
+    def work(t):
+        for _ in range(5):
+            got[t] = clones[t].check_connection(*batches[t], c3.min_distance)
+
+    th = [threading.Thread(target=work, args=(t,)) for t in range(4)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    for t in range(4):
+        assert np.array_equal(got[t], want[t])
+        assert clones[t].counters()["launches"] == 5
