@@ -37,7 +37,7 @@ class CudaNearestNeighbors : public NearestNeighbors
 public:
   // capacity grows on demand (the store is re-created at twice the size and refilled on the device)
   CudaNearestNeighbors(const cnr_logger::TraceLoggerPtr& logger, int device = 0, uint32_t capacity = 4096);
-  ~CudaNearestNeighbors() override;
+  ~CudaNearestNeighbors();  // the upstream base has no virtual destructor: objects live in shared_ptr
 
   void insert(const NodePtr& node) override;
   bool clear() override;
@@ -103,7 +103,7 @@ public:
                        const double& min_distance = 0.01);
   // shares an existing device world (one more reference is taken)
   CudaCollisionChecker(const cnr_logger::TraceLoggerPtr& logger, gc_world_t* world, const double& min_distance = 0.01);
-  ~CudaCollisionChecker() override;
+  ~CudaCollisionChecker();  // as above
 
   bool check(const Eigen::VectorXd& configuration) override;
   bool checkConnection(const Eigen::VectorXd& configuration1, const Eigen::VectorXd& configuration2,

@@ -80,6 +80,50 @@ def build(verbose=False):
     return True
 
 
+def build_dropin(verbose=False):
+    """oracle/_ref/libgc_ref_dropin.so: the reference's objects + graph_core_b200/host/cuda_plugins.cpp compiled with
+    -DGCB200_WITH_GRAPH_CORE against the GENUINE graph_core headers + oracle/ref_dropin.cpp, linked with libgcb200.so
+    (loads anywhere; needs a GPU only when a CUDA world is actually used)."""
+    if not REF.exists():
+        return False
+    root = HERE.parent
+    pkg = root / "graph_core_b200"
+    lib = pkg / "libgcb200.so"
+    if not lib.exists():
+        raise RuntimeError("ref_build: build graph_core_b200/libgcb200.so first")
+    target = OUT / "libgc_ref_dropin.so"
+    srcs = [HERE / "ref_dropin.cpp", HERE / "ref_driver.cpp", pkg / "host" / "cuda_plugins.cpp", pkg / "host" / "cuda_plugins.h",
+            pkg / "host" / "compat" / "graph_core_min.h", root / "include" / "gcb200.h", Path(__file__), lib]
+    stamp = max(max(f.stat().st_mtime for f in srcs), newest_input())
+    if target.exists() and target.stat().st_mtime >= stamp:
+        return True
+    build(verbose)  # the reference objects
+    cxx = os.environ.get("CXX", "g++")
+    flags = VARIANTS["libgc_ref.so"]
+    inc = ["-I", str(HERE / "ref_shim"), "-I", str(REF / "include"), "-I", str(root / "include"), "-I", str(pkg / "host"),
+           "-I", str(HERE)]
+    objdir = OUT / "obj_libgc_ref"
+    objs = [o for o in objdir.glob("*.o") if o.name != "ref_driver.o"]  # ref_dropin.cpp includes ref_driver.cpp
+    extra = []
+    for src in (HERE / "ref_dropin.cpp", pkg / "host" / "cuda_plugins.cpp"):
+        obj = OUT / ("dropin_" + src.stem + ".o")
+        cmd = [cxx, "-std=c++17", "-fPIC", "-w", "-DNDEBUG", "-DGCB200_WITH_GRAPH_CORE", *flags, *inc, "-c", str(src), "-o",
+               str(obj)]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError("ref_build: %s failed\n%s" % (src, r.stderr[-4000:]))
+        extra.append(obj)
+    cmd = [cxx, "-shared", "-o", str(target), *map(str, objs), *map(str, extra), "-L", str(pkg), "-lgcb200",
+           "-Wl,-rpath,$ORIGIN/../../graph_core_b200"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("ref_build: drop-in link failed\n" + r.stderr[-4000:])
+    if verbose:
+        print("ref_build: built", target)
+    return True
+
+
 if __name__ == "__main__":
     build(verbose=True)
+    build_dropin(verbose=True)
     sys.exit(0)

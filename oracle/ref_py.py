@@ -31,11 +31,11 @@ def build():
     return m.build()
 
 
-def lib(fast: bool = False):
-    key = "fast" if fast else "parity"
+def lib(fast: bool = False, dropin: bool = False):
+    key = "dropin" if dropin else ("fast" if fast else "parity")
     if key in _libs:
         return _libs[key]
-    path = HERE / "_ref" / ("libgc_ref_fast.so" if fast else "libgc_ref.so")
+    path = HERE / "_ref" / ("libgc_ref_dropin.so" if dropin else ("libgc_ref_fast.so" if fast else "libgc_ref.so"))
     if not path.exists():
         build()
     if not path.exists():
@@ -84,6 +84,11 @@ def lib(fast: bool = False):
         "ref_informed_specific_volume": (C.c_double, [C.c_int, _dp, _dp, _dp, _dp, C.c_double]),
         "ref_metrics_cost": (C.c_double, [C.c_int, _dp, _dp]),
     }
+    if dropin:
+        sig["dropin_solver_new"] = (vp, [C.c_int, C.c_int, vp, _dp, _dp, _dp, _dp, C.c_double, C.c_double, C.c_double,
+                                         C.c_double, C.c_int, C.c_int, C.c_int, C.c_int])
+        sig["dropin_checker_device_calls"] = (C.c_ulonglong, [vp])
+        sig["dropin_uses_cuda_nn"] = (C.c_int, [vp])
     for name, (res, args) in sig.items():
         fn = getattr(L, name)
         fn.restype = res
@@ -295,6 +300,34 @@ class RefSolver:
     @property
     def path_cost(self):
         return self.L.ref_solver_path_cost(self.h)
+
+
+class DropinSolver(RefSolver):
+    """The reference's solver classes with this repository's CUDA plugin classes plugged in (oracle/ref_dropin.cpp):
+    CudaCollisionChecker for every solver, CudaNearestNeighbors for the start tree when cuda_nn is set."""
+
+    def __init__(self, kind, scenario, cuda_world, start=None, goal=None, extend=False, informed=True, cuda_nn=True,
+                 device=0):
+        self.L = lib(dropin=True)
+        self.checker = cuda_world  # keep alive
+        self.dim = scenario.dim
+        s = _f64(scenario.start if start is None else start)
+        g = _f64(scenario.goal if goal is None else goal)
+        lb, ub = _f64(scenario.lb), _f64(scenario.ub)
+        self.h = self.L.dropin_solver_new(kind, self.dim, cuda_world.handle, _p(lb, _dp), _p(ub, _dp), _p(s, _dp),
+                                          _p(g, _dp), scenario.max_distance, scenario.min_distance,
+                                          scenario.rewire_factor, scenario.utopia_tolerance, 1 if extend else 0,
+                                          1 if informed else 0, 1 if cuda_nn else 0, device)
+        if not self.h:
+            raise RuntimeError("dropin_solver_new failed (no CUDA device?)")
+
+    @property
+    def device_calls(self):
+        return int(self.L.dropin_checker_device_calls(self.h))
+
+    @property
+    def uses_cuda_nn(self):
+        return bool(self.L.dropin_uses_cuda_nn(self.h))
 
 
 def tree_as_edges(conf, parent_conf, pcost):
