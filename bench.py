@@ -45,7 +45,7 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--problems", type=int, default=2048, help="independent planning problems per GPU")
+    ap.add_argument("--problems", type=int, default=4096, help="independent planning problems per GPU")
     ap.add_argument("--threads", type=int, default=0, help="host replay threads (0 = all cores)")
     ap.add_argument("--instances", type=int, default=4,
                     help="lock-step planner instances per GPU, each with problems/instances problems, its own stream and "
@@ -199,6 +199,11 @@ def main():
     from graph_core_b200 import worlds as W
 
     ncores = os.cpu_count() or 1
+    try:
+        ncores = len(os.sched_getaffinity(0)) or ncores
+    except Exception:
+        pass
+    ncores_rank = max(1, ncores // max(world_size, 1))  # the ranks of one box share its host cores
 
     # ------------------------------------------------------------------ reference arm (CPU only)
     if args.impl == "reference":
@@ -281,7 +286,7 @@ def main():
         """K lock-step iterations of all P problems, split over `instances` independent planner instances."""
         G = max(1, min(instances, P))
         bounds = [P * i // G for i in range(G + 1)]
-        thr_each = max(1, (args.threads or ncores) // G)
+        thr_each = max(1, (args.threads or ncores_rank) // G)
         inst = []
         for i in range(G):
             lo, hi = bounds[i], bounds[i + 1]
@@ -401,7 +406,7 @@ def main():
             "workload": "C3: 7-DoF sphere-arm RRT* vs 1000-sphere cloud, %d lock-step problems per GPU x %d "
                         "iterations" % (P, K),
             "problems_per_gpu": P, "max_distance": sc.max_distance, "min_distance": sc.min_distance,
-            "sampler": "uniform (Philox, injected)", "host_threads": args.threads or ncores,
+            "sampler": "uniform (Philox, injected)", "host_threads": args.threads or ncores_rank,
             "instances_per_gpu": val_run["instances"],
             "l2_policy": "every step has new samples and larger trees; no artificial L2 flush between planner "
                          "iterations (the kNN side measurement flushes L2 between launches)",

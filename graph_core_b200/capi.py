@@ -94,6 +94,11 @@ PROTOTYPES = {
                                     _c_double_p]),
     "gc_sample_uniform_dev": (C.c_int, [C.c_int, C.c_int, _c_double_p, _c_double_p, C.c_uint64, C.c_uint64, C.c_uint32,
                                         C.c_void_p, C.c_void_p]),
+    "gc_sample_informed": (C.c_int, [C.c_int, C.c_int, _c_double_p, _c_double_p, _c_double_p, _c_double_p, _c_double_p,
+                                     C.c_uint64, C.c_uint64, C.c_uint32, _c_double_p, _c_u32_p]),
+    "gc_sample_informed_dev": (C.c_int, [C.c_int, C.c_int, _c_double_p, _c_double_p, C.c_void_p, C.c_void_p,
+                                         C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint32, C.c_void_p, C.c_void_p,
+                                         C.c_void_p]),
     "gc_extend_batch_dsamples": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, _c_u32_p, _c_u32_p, C.c_uint32,
                                            C.c_double, C.c_double, C.c_double, _c_double_p, C.c_uint32, _c_u32_p,
                                            _c_double_p, _c_double_p, _c_u8_p, _c_u32_p, _c_double_p, _c_u32_p]),
@@ -464,3 +469,19 @@ def sample_uniform(lb, ub, seed: int, first_index: int, n: int, device: int = 0)
     _check(load().gc_sample_uniform(device, lb.shape[0], _ptr(lb, _c_double_p), _ptr(ub, _c_double_p), seed,
                                     first_index, n, _ptr(out, _c_double_p)))
     return out
+
+
+def sample_informed(lb, ub, f1, f2, cost, seed: int, first_index: int = 0, device: int = 0):
+    """InformedSampler::sample for n problems (foci f1/f2 [n][dim], cost [n] or scalar) on the device Philox stream.
+    Returns (samples [n][dim], attempts [n])."""
+    lb, ub = _f64(lb), _f64(ub)
+    dim = lb.shape[0]
+    f1, f2 = _f64(f1, (-1, dim)), _f64(f2, (-1, dim))
+    n = f1.shape[0]
+    cost = np.ascontiguousarray(np.broadcast_to(np.asarray(cost, dtype=np.float64), (n,)))
+    out = np.empty((n, dim), dtype=np.float64)
+    att = np.empty(n, dtype=np.uint32)
+    _check(load().gc_sample_informed(device, dim, _ptr(lb, _c_double_p), _ptr(ub, _c_double_p), _ptr(f1, _c_double_p),
+                                     _ptr(f2, _c_double_p), _ptr(cost, _c_double_p), seed, first_index, n,
+                                     _ptr(out, _c_double_p), _ptr(att, _c_u32_p)))
+    return out, att

@@ -107,6 +107,182 @@ __global__ void sample_uniform_kernel(const double* __restrict__ lb, const doubl
     }
   }
 }
+
+// ---- informed sampler -----------------------------------------------------------------------------------
+// InformedSampler::sample (informed_sampler.cpp:145-180) for n independent problems: problem i has its own foci
+// and cost.  cost = +inf -> uniform in the box (:149).  Otherwise up to 100 attempts (:154-173): a point of the
+// unit ball -- direction = D uniforms in [-1,1] divided by their 2-norm (the reference's setRandom()/norm(), a
+// cube-normalised direction, reproduced on purpose), radius = u^(1/D) -- is stretched by the ellipse axes
+// (max_radius = cost/2 along the focal line, min_radius = sqrt(cost^2 - focii^2)/2 elsewhere, :181-207), rotated by
+// the Gram-Schmidt basis of computeRotationMatrix (:107-143), moved to the centre and accepted when inside the
+// bounds; after 100 rejections the uniform fallback (:178).
+// Random stream of sample i: Philox4x32-10, counter (i, draw/2, 1), key = seed; draws are consumed in the order
+// written above (D direction draws, then the radius draw, per attempt).  u^(1/D) is a 64-step bisection built from
+// multiplications only, so that the oracle's CPU restatement produces the same bits (pow() is not portable).
+__device__ __forceinline__ double informed_root(double u, int D)
+{
+  double lo = 0.0, hi = 1.0;
+  for (int it = 0; it < 64; it++)
+  {
+    const double mid = __dmul_rn(0.5, __dadd_rn(lo, hi));
+    double p = mid;
+    for (int k = 1; k < D; k++)
+      p = __dmul_rn(p, mid);
+    if (p < u)
+      lo = mid;
+    else
+      hi = mid;
+  }
+  return __dmul_rn(0.5, __dadd_rn(lo, hi));
+}
+
+struct InformedArgs
+{
+  int dim;
+  uint32_t n;
+  const double* lb;
+  const double* ub;
+  const double* f1;    // [n][dim]
+  const double* f2;    // [n][dim]
+  const double* cost;  // [n]
+  unsigned long long seed, first;
+  double* out;         // [n][dim]
+  uint32_t* attempts;  // optional [n]: rejection rounds used (101 = fallback, 0 = infinite cost)
+};
+
+__global__ void sample_informed_kernel(InformedArgs a)
+{
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= a.n)
+    return;
+  const int D = a.dim;
+  const unsigned long long ctr = a.first + i;
+  uint32_t cached_block = 0xFFFFFFFFu;
+  uint32_t r[4];
+  auto draw = [&](uint32_t j) {
+    const uint32_t b = j >> 1;
+    if (b != cached_block)
+    {
+      philox4x32_10((uint32_t)ctr, (uint32_t)(ctr >> 32), b, 1u, (uint32_t)a.seed, (uint32_t)(a.seed >> 32), r);
+      cached_block = b;
+    }
+    return (j & 1u) ? u01(r[2], r[3]) : u01(r[0], r[1]);
+  };
+  auto uniform = [&](uint32_t j0) {
+    for (int d = 0; d < D; d++)
+    {
+      const double u = draw(j0 + (uint32_t)d);
+      const double c = __dmul_rn(0.5, __dadd_rn(a.lb[d], a.ub[d]));
+      const double hw = __dmul_rn(0.5, __dsub_rn(a.lb[d], a.ub[d]));
+      a.out[(size_t)i * D + d] = __dadd_rn(c, __dmul_rn(__dsub_rn(__dmul_rn(2.0, u), 1.0), hw));
+    }
+  };
+  double cost = a.cost[i];
+  if (!(cost < CUDART_INF))
+  {
+    uniform(0u);
+    if (a.attempts)
+      a.attempts[i] = 0;
+    return;
+  }
+  const double* f1 = a.f1 + (size_t)i * D;
+  const double* f2 = a.f2 + (size_t)i * D;
+  double R[GC_MAX_DIM][GC_MAX_DIM];  // R[row][col]
+  double v[GC_MAX_DIM], centre[GC_MAX_DIM], axis[GC_MAX_DIM];
+  double s2 = 0.0;
+  for (int d = 0; d < D; d++)
+  {
+    v[d] = __dsub_rn(f1[d], f2[d]);
+    s2 = __dadd_rn(s2, __dmul_rn(v[d], v[d]));
+    centre[d] = __dmul_rn(0.5, __dadd_rn(f1[d], f2[d]));
+  }
+  const double fd = __dsqrt_rn(s2);
+  for (int d = 0; d < D; d++)
+    v[d] = __ddiv_rn(v[d], fd);
+  for (int r0 = 0; r0 < D; r0++)
+    for (int c0 = 0; c0 < D; c0++)
+      R[r0][c0] = (r0 == c0) ? 1.0 : 0.0;
+  bool standard = false;
+  for (int ic = 0; ic < D; ic++)
+    if (fabs(v[ic]) > 0.999)
+    {
+      standard = true;  // swap columns ic and 0 of the identity
+      for (int r0 = 0; r0 < D; r0++)
+      {
+        const double t = R[r0][ic];
+        R[r0][ic] = R[r0][0];
+        R[r0][0] = t;
+      }
+      break;
+    }
+  if (!standard)
+  {
+    for (int r0 = 0; r0 < D; r0++)
+      R[r0][0] = v[r0];
+    for (int ic = 1; ic < D; ic++)
+    {
+      for (int il = 0; il < ic; il++)
+      {
+        double dot = 0.0;
+        for (int r0 = 0; r0 < D; r0++)
+          dot = __dadd_rn(dot, __dmul_rn(R[r0][ic], R[r0][il]));
+        for (int r0 = 0; r0 < D; r0++)
+          R[r0][ic] = __dsub_rn(R[r0][ic], __dmul_rn(dot, R[r0][il]));
+      }
+      double n2 = 0.0;
+      for (int r0 = 0; r0 < D; r0++)
+        n2 = __dadd_rn(n2, __dmul_rn(R[r0][ic], R[r0][ic]));
+      const double nn = __dsqrt_rn(n2);
+      for (int r0 = 0; r0 < D; r0++)
+        R[r0][ic] = __ddiv_rn(R[r0][ic], nn);
+    }
+  }
+  double rmin;
+  if (cost < fd)
+  {
+    cost = fd;
+    rmin = 0.0;
+  }
+  else
+    rmin = __dmul_rn(0.5, __dsqrt_rn(__dsub_rn(__dmul_rn(cost, cost), __dmul_rn(fd, fd))));
+  const double rmax = __dmul_rn(0.5, cost);
+  for (int d = 0; d < D; d++)
+    axis[d] = (d == 0) ? rmax : rmin;
+  for (uint32_t t = 0; t < 100u; t++)
+  {
+    const uint32_t j0 = t * (uint32_t)(D + 1);
+    double ball[GC_MAX_DIM];
+    double b2 = 0.0;
+    for (int d = 0; d < D; d++)
+    {
+      ball[d] = __dsub_rn(__dmul_rn(2.0, draw(j0 + (uint32_t)d)), 1.0);
+      b2 = __dadd_rn(b2, __dmul_rn(ball[d], ball[d]));
+    }
+    const double scale = __ddiv_rn(informed_root(draw(j0 + (uint32_t)D), D), __dsqrt_rn(b2));
+    bool inside = true;
+    double q[GC_MAX_DIM];
+    for (int r0 = 0; r0 < D; r0++)
+    {
+      double acc = 0.0;
+      for (int c0 = 0; c0 < D; c0++)
+        acc = __dadd_rn(acc, __dmul_rn(__dmul_rn(R[r0][c0], axis[c0]), __dmul_rn(ball[c0], scale)));
+      q[r0] = __dadd_rn(acc, centre[r0]);
+      if (q[r0] > a.ub[r0] || q[r0] < a.lb[r0])
+        inside = false;
+    }
+    if (inside)
+    {
+      for (int d = 0; d < D; d++)
+        a.out[(size_t)i * D + d] = q[d];
+      if (a.attempts)
+        a.attempts[i] = t + 1u;
+      return;
+    }
+  }
+  uniform(100u * (uint32_t)(D + 1));
+  if (a.attempts)
+    a.attempts[i] = 101u;
+}
 }  // namespace gc
 
 using namespace gc;
@@ -359,6 +535,88 @@ int gc_sample_uniform(int device, int dim, const double* lb, const double* ub, u
     return GC_E_CUDA;
   }
   return GC_OK;
+}
+
+// informed sampling for n problems (foci f1/f2 [n][dim], cost [n]); all pointers DEVICE pointers except lb/ub (host)
+int gc_sample_informed_dev(int device, int dim, const double* lb, const double* ub, const double* d_f1,
+                           const double* d_f2, const double* d_cost, uint64_t seed, uint64_t first_index, uint32_t n,
+                           double* d_out, uint32_t* d_attempts, void* cuda_stream)
+{
+  GC_REQUIRE(lb && ub && d_f1 && d_f2 && d_cost && d_out, "gc_sample_informed_dev: NULL argument");
+  GC_REQUIRE(dim >= 1 && dim <= GC_MAX_DIM, "gc_sample_informed_dev: dim %d", dim);
+  if (n == 0)
+    return GC_OK;
+  GC_SET_DEVICE(device);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(cuda_stream);
+  double* d_b = nullptr;
+  GC_CUDA(cudaMalloc(&d_b, sizeof(double) * 2 * dim));
+  GC_CUDA(cudaMemcpyAsync(d_b, lb, sizeof(double) * dim, cudaMemcpyHostToDevice, st));
+  GC_CUDA(cudaMemcpyAsync(d_b + dim, ub, sizeof(double) * dim, cudaMemcpyHostToDevice, st));
+  InformedArgs a{};
+  a.dim = dim;
+  a.n = n;
+  a.lb = d_b;
+  a.ub = d_b + dim;
+  a.f1 = d_f1;
+  a.f2 = d_f2;
+  a.cost = d_cost;
+  a.seed = seed;
+  a.first = first_index;
+  a.out = d_out;
+  a.attempts = d_attempts;
+  sample_informed_kernel<<<(n + 127) / 128, 128, 0, st>>>(a);
+  cudaError_t e = cudaGetLastError();
+  count_launch();
+  if (e == cudaSuccess)
+    e = cudaStreamSynchronize(st);
+  cudaFree(d_b);
+  if (e != cudaSuccess)
+  {
+    gc::set_error("gc_sample_informed_dev: %s", cudaGetErrorString(e));
+    return GC_E_CUDA;
+  }
+  return GC_OK;
+}
+
+int gc_sample_informed(int device, int dim, const double* lb, const double* ub, const double* f1, const double* f2,
+                       const double* cost, uint64_t seed, uint64_t first_index, uint32_t n, double* out,
+                       uint32_t* attempts)
+{
+  GC_REQUIRE(lb && ub && f1 && f2 && cost && out, "gc_sample_informed: NULL argument");
+  GC_REQUIRE(dim >= 1 && dim <= GC_MAX_DIM, "gc_sample_informed: dim %d", dim);
+  if (n == 0)
+    return GC_OK;
+  int ndev = 0;
+  GC_TRY(gc_device_count(&ndev));
+  GC_REQUIRE(device >= 0 && device < ndev, "gc_sample_informed: device %d of %d", device, ndev);
+  GC_SET_DEVICE(device);
+  const size_t nd = (size_t)n * dim;
+  double* d_buf = nullptr;  // f1 | f2 | out | cost
+  uint32_t* d_att = nullptr;
+  GC_CUDA(cudaMalloc(&d_buf, sizeof(double) * (3 * nd + n)));
+  cudaError_t e = cudaMalloc(&d_att, sizeof(uint32_t) * n);
+  if (e == cudaSuccess)
+    e = cudaMemcpy(d_buf, f1, sizeof(double) * nd, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess)
+    e = cudaMemcpy(d_buf + nd, f2, sizeof(double) * nd, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess)
+    e = cudaMemcpy(d_buf + 3 * nd, cost, sizeof(double) * n, cudaMemcpyHostToDevice);
+  int rc = GC_OK;
+  if (e == cudaSuccess)
+    rc = gc_sample_informed_dev(device, dim, lb, ub, d_buf, d_buf + nd, d_buf + 3 * nd, seed, first_index, n,
+                                d_buf + 2 * nd, d_att, cudaStreamLegacy);
+  if (e == cudaSuccess && rc == GC_OK)
+    e = cudaMemcpy(out, d_buf + 2 * nd, sizeof(double) * nd, cudaMemcpyDeviceToHost);
+  if (e == cudaSuccess && rc == GC_OK && attempts)
+    e = cudaMemcpy(attempts, d_att, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost);
+  cudaFree(d_buf);
+  cudaFree(d_att);
+  if (e != cudaSuccess)
+  {
+    gc::set_error("gc_sample_informed: %s", cudaGetErrorString(e));
+    return GC_E_CUDA;
+  }
+  return rc;
 }
 
 }  // extern "C"

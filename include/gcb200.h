@@ -173,6 +173,18 @@ int gc_sample_uniform(int device, int dim, const double* lb, const double* ub, u
 int gc_sample_uniform_dev(int device, int dim, const double* lb, const double* ub, uint64_t seed,
                           uint64_t first_index, uint32_t n, double* d_out, void* cuda_stream);
 
+/* InformedSampler::sample (informed_sampler.cpp:145-180) for n problems at once: problem i samples the prolate
+ * hyperspheroid with foci f1[i], f2[i] and transverse diameter cost[i] (cost = +inf: uniform in the box), rejecting
+ * points outside [lb, ub] up to 100 times.  Philox counter of problem i = first_index + i.  attempts (may be NULL)
+ * receives the rounds used: 0 infinite cost, 1..100 accepted round, 101 uniform fallback.                       */
+int gc_sample_informed(int device, int dim, const double* lb, const double* ub, const double* f1, const double* f2,
+                       const double* cost, uint64_t seed, uint64_t first_index, uint32_t n, double* out,
+                       uint32_t* attempts);
+/* d_f1, d_f2, d_cost, d_out, d_attempts are device pointers; lb/ub host arrays */
+int gc_sample_informed_dev(int device, int dim, const double* lb, const double* ub, const double* d_f1,
+                           const double* d_f2, const double* d_cost, uint64_t seed, uint64_t first_index, uint32_t n,
+                           double* d_out, uint32_t* d_attempts, void* cuda_stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1263,6 +1263,163 @@ struct Solver
 }  // namespace orc
 
 // ============================================================================
+//  Informed sampling with the repository's Philox stream (include/gcb200.h gc_sample_informed).
+//  Algorithm: src/samplers/informed_sampler.cpp:107-143 (rotation basis), :145-180 (sample),
+//  :181-207 (ellipse radii).  The random stream and u^(1/D) (64-step bisection) are this
+//  repository's specification, restated here independently of csrc/planner.cu.
+// ============================================================================
+namespace orc
+{
+static void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1, uint32_t* out)
+{
+  for (int r = 0; r < 10; r++)
+  {
+    const uint64_t p0 = (uint64_t)GC_PHILOX_M0 * c0, p1 = (uint64_t)GC_PHILOX_M1 * c2;
+    const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0, n1 = (uint32_t)p1, n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1,
+                   n3 = (uint32_t)p0;
+    c0 = n0;
+    c1 = n1;
+    c2 = n2;
+    c3 = n3;
+    k0 += GC_PHILOX_W0;
+    k1 += GC_PHILOX_W1;
+  }
+  out[0] = c0;
+  out[1] = c1;
+  out[2] = c2;
+  out[3] = c3;
+}
+struct PhiloxDraws
+{
+  uint64_t ctr, seed;
+  double operator()(uint32_t j) const
+  {
+    uint32_t r[4];
+    philox4x32_10((uint32_t)ctr, (uint32_t)(ctr >> 32), j >> 1, 1u, (uint32_t)seed, (uint32_t)(seed >> 32), r);
+    const uint64_t x = (j & 1u) ? (((uint64_t)r[2] << 32) | r[3]) : (((uint64_t)r[0] << 32) | r[1]);
+    return (double)(x >> 11) * 1.1102230246251565404e-16;
+  }
+};
+static double dth_root(double u, int D)
+{
+  double lo = 0.0, hi = 1.0;
+  for (int it = 0; it < 64; it++)
+  {
+    const double mid = 0.5 * (lo + hi);
+    double p = mid;
+    for (int k = 1; k < D; k++)
+      p = p * mid;
+    if (p < u)
+      lo = mid;
+    else
+      hi = mid;
+  }
+  return 0.5 * (lo + hi);
+}
+// returns the attempts code of gc_sample_informed
+static unsigned informed_sample(int D, const double* lb, const double* ub, const double* f1, const double* f2,
+                                double cost, const PhiloxDraws& draw, double* out)
+{
+  auto uniform = [&](uint32_t j0) {
+    for (int d = 0; d < D; d++)
+    {
+      const double u = draw(j0 + d);
+      out[d] = 0.5 * (lb[d] + ub[d]) + (2.0 * u - 1.0) * (0.5 * (lb[d] - ub[d]));
+    }
+  };
+  if (!(cost < kInf))
+  {
+    uniform(0);
+    return 0;
+  }
+  std::vector<double> v(D), centre(D), axis(D), R((size_t)D * D, 0.0);  // R[row * D + col]
+  double s2 = 0.0;
+  for (int d = 0; d < D; d++)
+  {
+    v[d] = f1[d] - f2[d];
+    s2 += v[d] * v[d];
+    centre[d] = 0.5 * (f1[d] + f2[d]);
+  }
+  const double fd = std::sqrt(s2);
+  for (int d = 0; d < D; d++)
+    v[d] = v[d] / fd;
+  for (int d = 0; d < D; d++)
+    R[(size_t)d * D + d] = 1.0;
+  bool standard = false;
+  for (int ic = 0; ic < D && !standard; ic++)
+    if (std::fabs(v[ic]) > 0.999)  // main_versor . e_ic (:118)
+    {
+      standard = true;
+      for (int r = 0; r < D; r++)
+        std::swap(R[(size_t)r * D + ic], R[(size_t)r * D]);
+    }
+  if (!standard)
+  {
+    for (int r = 0; r < D; r++)
+      R[(size_t)r * D] = v[r];
+    for (int ic = 1; ic < D; ic++)
+    {
+      for (int il = 0; il < ic; il++)
+      {
+        double dot = 0.0;
+        for (int r = 0; r < D; r++)
+          dot += R[(size_t)r * D + ic] * R[(size_t)r * D + il];
+        for (int r = 0; r < D; r++)
+          R[(size_t)r * D + ic] = R[(size_t)r * D + ic] - dot * R[(size_t)r * D + il];
+      }
+      double n2 = 0.0;
+      for (int r = 0; r < D; r++)
+        n2 += R[(size_t)r * D + ic] * R[(size_t)r * D + ic];
+      const double nn = std::sqrt(n2);
+      for (int r = 0; r < D; r++)
+        R[(size_t)r * D + ic] = R[(size_t)r * D + ic] / nn;
+    }
+  }
+  double rmin;
+  if (cost < fd)
+  {
+    cost = fd;
+    rmin = 0.0;
+  }
+  else
+    rmin = 0.5 * std::sqrt(cost * cost - fd * fd);
+  const double rmax = 0.5 * cost;
+  for (int d = 0; d < D; d++)
+    axis[d] = d == 0 ? rmax : rmin;
+  std::vector<double> ball(D), q(D);
+  for (unsigned t = 0; t < 100; t++)
+  {
+    const uint32_t j0 = t * (uint32_t)(D + 1);
+    double b2 = 0.0;
+    for (int d = 0; d < D; d++)
+    {
+      ball[d] = 2.0 * draw(j0 + d) - 1.0;
+      b2 += ball[d] * ball[d];
+    }
+    const double scale = dth_root(draw(j0 + D), D) / std::sqrt(b2);
+    bool inside = true;
+    for (int r = 0; r < D; r++)
+    {
+      double acc = 0.0;
+      for (int c = 0; c < D; c++)
+        acc += (R[(size_t)r * D + c] * axis[c]) * (ball[c] * scale);
+      q[r] = acc + centre[r];
+      if (q[r] > ub[r] || q[r] < lb[r])
+        inside = false;
+    }
+    if (inside)
+    {
+      for (int d = 0; d < D; d++)
+        out[d] = q[d];
+      return t + 1;
+    }
+  }
+  uniform(100u * (uint32_t)(D + 1));
+  return 101;
+}
+}  // namespace orc
+
+// ============================================================================
 //  C interface (ctypes)
 // ============================================================================
 using namespace orc;
@@ -1471,6 +1628,21 @@ void orc_check_from_conf(void* wh, const double* parent, const double* child, co
   {
     int r = checkConnFromConf(*w, parent + (size_t)i * d, child + (size_t)i * d, conf + (size_t)i * d, min_distance);
     result[i] = r < 0 ? 255 : (unsigned char)r;
+  }
+}
+
+// ---- samplers ------------------------------------------------------------------
+void orc_sample_informed(int dim, int n, const double* lb, const double* ub, const double* f1, const double* f2,
+                         const double* cost, unsigned long long seed, unsigned long long first, double* out,
+                         unsigned int* attempts)
+{
+  for (int i = 0; i < n; i++)
+  {
+    PhiloxDraws d{ first + (unsigned long long)i, seed };
+    const unsigned a = informed_sample(dim, lb, ub, f1 + (size_t)i * dim, f2 + (size_t)i * dim, cost[i], d,
+                                       out + (size_t)i * dim);
+    if (attempts)
+      attempts[i] = a;
   }
 }
 

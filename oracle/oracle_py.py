@@ -67,6 +67,8 @@ def lib(fast: bool = False):
         "orc_check_states": (None, [vp, _dp, C.c_int, _u8p]),
         "orc_check_edges": (None, [vp, _dp, _dp, C.c_int, C.c_double, C.c_int, _u8p, _i64p, _dp]),
         "orc_check_from_conf": (None, [vp, _dp, _dp, _dp, C.c_int, C.c_double, _u8p]),
+        "orc_sample_informed": (None, [C.c_int, C.c_int, _dp, _dp, _dp, _dp, _dp, C.c_ulonglong, C.c_ulonglong, _dp,
+                                       C.POINTER(C.c_uint)]),
         "orc_solver_new": (vp, [C.c_int, C.c_int, vp, _dp, _dp, _dp, _dp, C.c_double, C.c_double, C.c_double,
                                 C.c_double, C.c_int, C.c_int]),
         "orc_solver_free": (None, [vp]),
@@ -256,6 +258,21 @@ class OracleWorld:
         res = np.empty(p.shape[0], np.uint8)
         self.L.orc_check_from_conf(self.h, _p(p, _dp), _p(c, _dp), _p(f, _dp), p.shape[0], min_distance, _p(res, _u8p))
         return res
+
+
+def sample_informed(lb, ub, f1, f2, cost, seed, first=0, fast=False):
+    """gc_sample_informed restated on the CPU: f1/f2 [n][dim], cost [n] -> samples [n][dim], attempts [n]."""
+    L = lib(fast)
+    lb, ub = _f64(lb), _f64(ub)
+    dim = lb.shape[0]
+    f1, f2 = _f64(f1, (-1, dim)), _f64(f2, (-1, dim))
+    n = f1.shape[0]
+    cost = np.ascontiguousarray(np.broadcast_to(np.asarray(cost, dtype=np.float64), (n,)))
+    out = np.empty((n, dim))
+    att = np.empty(n, np.uint32)
+    L.orc_sample_informed(dim, n, _p(lb, _dp), _p(ub, _dp), _p(f1, _dp), _p(f2, _dp), _p(cost, _dp), seed, first,
+                          _p(out, _dp), att.ctypes.data_as(C.POINTER(C.c_uint)))
+    return out, att
 
 
 def arm_checker(fast=False):

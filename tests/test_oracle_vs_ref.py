@@ -304,3 +304,53 @@ def test_euclidean_metrics_and_specific_volume(orc, ref):
         for i in range(d):
             s += (a[i] - b[i]) * (a[i] - b[i])
         assert want == np.sqrt(s)
+
+
+# ---------------------------------------------------------------------------------------------------
+# Informed sampler: the restated algorithm (Philox stream) against the reference's own sampler (std::rand stream)
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dim", [2, 3, 7])
+def test_informed_sampler_distribution_matches_reference(orc, ref, dim):
+    """informed_sampler.cpp:145-180.  The streams differ, so the comparison is distributional: support (bounds and
+    the prolate hyperspheroid), first and second moments -- including the anisotropy of the reference's
+    cube-normalised ball direction, which an isotropic sampler would not reproduce."""
+    import ctypes as C
+    L = ref.lib()
+    dp = C.POINTER(C.c_double)
+    rng = np.random.default_rng(dim)
+    lb, ub = np.full(dim, -3.0), np.full(dim, 3.0)
+    f1, f2 = rng.uniform(-1.0, 0.0, dim), rng.uniform(0.0, 1.0, dim)
+    fd = np.linalg.norm(f1 - f2)
+    n = 40000
+    for cost in (1.05 * fd, 1.6 * fd, 2.6 * fd):  # the widest ellipse sticks out of the box: rejection path
+        want = np.empty((n, dim))
+        L.ref_srand(7)
+        L.ref_sample_informed(dim, lb.ctypes.data_as(dp), ub.ctypes.data_as(dp), f1.ctypes.data_as(dp),
+                              f2.ctypes.data_as(dp), cost, n, want.ctypes.data_as(dp))
+        got, att = orc.sample_informed(lb, ub, np.tile(f1, (n, 1)), np.tile(f2, (n, 1)), cost, seed=11)
+        inside = []
+        for s in (want, got):
+            assert (s >= lb).all() and (s <= ub).all()
+            m = np.linalg.norm(s - f1, axis=1) + np.linalg.norm(s - f2, axis=1) <= cost * (1 + 1e-12)
+            assert m.mean() > 0.97  # the rest took the uniform fallback after 100 rejections (:175-178) on both sides
+            inside.append(m)
+        assert np.array_equal(inside[1], att <= 100)
+        assert att.min() >= 1
+        want, got = want[inside[0]], got[inside[1]]
+        sd = want.std(axis=0)
+        assert np.all(np.abs(got.mean(axis=0) - want.mean(axis=0)) < 5 * sd / np.sqrt(min(len(got), len(want))) + 1e-12)
+        cw, cg = np.cov(want.T), np.cov(got.T)
+        assert np.allclose(cg, cw, atol=0.04 * np.abs(cw).max())
+        # 4th moment along the focal axis: sensitive to the radial law u^(1/D) and the direction law
+        ax = (f1 - f2) / fd
+        kw = np.mean(((want - want.mean(0)) @ ax) ** 4)
+        kg = np.mean(((got - got.mean(0)) @ ax) ** 4)
+        assert abs(kg - kw) < 0.06 * kw
+    # infinite cost: uniform in the box
+    got, att = orc.sample_informed(lb, ub, np.tile(f1, (1000, 1)), np.tile(f2, (1000, 1)), np.inf, seed=3)
+    assert (att == 0).all() and (got >= lb).all() and (got <= ub).all()
+    assert np.all(np.abs(got.mean(0)) < 0.2)
+    # cost below the focal distance: degenerate ellipse = the focal segment (informed_sampler.cpp:186-193)
+    got, att = orc.sample_informed(lb, ub, f1[None], f2[None], 0.5 * fd, seed=5)
+    t = (got[0] - f2) @ (f1 - f2) / fd ** 2
+    assert np.allclose(f2 + t * (f1 - f2), got[0], atol=1e-12) and -1e-12 <= t <= 1 + 1e-12
