@@ -421,9 +421,16 @@ def main():
                    "ms_per_step": e2e_run["ms"] / K, "same_trees_as_value_run": bool(same)}
     wc = roof_run["world"]
     achieved = FLOP_PER_PAIR * wc["pair_tests"] / max(wc["kernel_ns"], 1) / 1e3  # TFLOP/s
+    traffic = {}
+    try:
+        traffic = json.loads((ROOT / "profiles" / "r01_ncu_traffic.json").read_text())
+    except Exception:
+        pass
     line["roofline"] = {
         "kernel": "arm_state_kernel (edge checks)", "bound": "fp32", "achieved": achieved, "peak": fp32_peak,
-        "unit": "TFLOP/s", "frac": achieved / fp32_peak if fp32_peak > 0 else None, "traffic": None,
+        "unit": "TFLOP/s", "frac": achieved / fp32_peak if fp32_peak > 0 else None,
+        "traffic": traffic.get("arm_state_kernel", {}).get("dram_bytes_per_launch"),
+        "traffic_source": traffic.get("arm_state_kernel", {}).get("capture"),
         "peak_source": "FFMA micro-benchmark in this run (implies %.0f MHz); MEASURED_PEAKS.json has no FP32 entry" % fp32_mhz,
         "pair_tests_per_launch": wc["pair_tests"] / max(wc["launches"], 1),
         "us_per_launch": wc["kernel_ns"] / max(wc["launches"], 1) / 1e3,
