@@ -111,6 +111,7 @@ struct gc_store
   int sms = 148;
   uint32_t near_width_hint = 64;   // columns of the near lists fetched eagerly by gc_extend_batch
   uint32_t knn_cand_scale = 3;     // head-room factor of the large-N k-nearest candidate lists
+  bool knn_force_fp64 = false;     // large-N k-nearest: candidates carry fp64 distances (massive near-ties met)
   gc::DevBuf d_cand_idx, d_cand_dist, d_cand_count, d_thr, d_gmin;
   size_t stream_ctl_q = 0, stream_ctl_g = 0;  // initialised extent of d_gmin (streaming-scan control words)
   // scratch

@@ -97,6 +97,7 @@ struct ScanArgs
   float xn_max;            // streaming scan: upper bound of |x|^2 over the store (fp32)
   uint32_t* gmin;          // streaming scan MODE 0: [nq] shared running fp32 minima (order-preserving keys)
   uint32_t* ctl;           // streaming scan: [groups][2] tile hand-out and finished-CTA counters (self-resetting)
+  float* out_c2;           // streaming scan MODE 2: candidates keep their fp32 pre-selection value (no fp64 here)
   // MODE 0 outputs: partials [chunks][nq]
   double* part_d;
   uint32_t* part_i;
@@ -673,14 +674,28 @@ __global__ void __launch_bounds__(kStThreads, 3) scan_stream_kernel(ScanArgs a)
               for (int r = 0; r < kNodesPerThread; r++)
                 if (acc[h][r] <= thr && acc[h][r] < CUDART_INF_F)
                 {
-                  const double e = dist64<D>(a.x64 + (size_t)(local0 + r) * D, m.q64 + qq * D);
-                  if (MODE == 2 || e < a.radius[q0 + qq])
+                  if (MODE == 2)
                   {
+                    // k-nearest collect: the exact distance is only needed for the few candidates next to the
+                    // k-th one (select_topk_f32_kernel); here the candidate keeps its fp32 value
                     const uint32_t pos = atomicAdd(&a.out_count[q0 + qq], 1u);
                     if (pos < a.cap)
                     {
                       a.out_idx[(size_t)(q0 + qq) * a.cap + pos] = local0 + r;
-                      a.out_dist[(size_t)(q0 + qq) * a.cap + pos] = e;
+                      a.out_c2[(size_t)(q0 + qq) * a.cap + pos] = acc[h][r];
+                    }
+                  }
+                  else
+                  {
+                    const double e = dist64<D>(a.x64 + (size_t)(local0 + r) * D, m.q64 + qq * D);
+                    if (e < a.radius[q0 + qq])
+                    {
+                      const uint32_t pos = atomicAdd(&a.out_count[q0 + qq], 1u);
+                      if (pos < a.cap)
+                      {
+                        a.out_idx[(size_t)(q0 + qq) * a.cap + pos] = local0 + r;
+                        a.out_dist[(size_t)(q0 + qq) * a.cap + pos] = e;
+                      }
                     }
                   }
                 }
@@ -1214,6 +1229,152 @@ __global__ void __launch_bounds__(1024, 1)
     out_count[q] = want;
 }
 
+// k-th smallest fp32 distance of the sample by radix select (4 histogram passes) instead of a full sort
+template <int D>
+__global__ void __launch_bounds__(1024, 1)
+    knn_sample_select_kernel(const float* __restrict__ x32, const uint32_t* __restrict__ used,
+                             const double* __restrict__ qd, const uint32_t* __restrict__ segs, uint32_t cap_seg,
+                             size_t row_stride, unsigned long long k, float slack_abs, float* __restrict__ thr2_out)
+{
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float* key = reinterpret_cast<float*>(smem_raw);
+  __shared__ float qs[D];
+  __shared__ uint32_t live_s;
+  __shared__ uint32_t hist[256];
+  __shared__ unsigned long long sh[2];
+  const uint32_t q = blockIdx.x;
+  const uint32_t seg = segs ? segs[q] : 0u;
+  const uint32_t n_s = used[seg];
+  const size_t seg_base = (size_t)seg * cap_seg;
+  if (threadIdx.x < D)
+    qs[threadIdx.x] = (float)qd[(size_t)q * D + threadIdx.x];
+  if (threadIdx.x == 0)
+    live_s = 0;
+  __syncthreads();
+  const uint32_t m = n_s < kSortMax ? n_s : kSortMax;
+  uint32_t my_live = 0;
+  for (uint32_t i = threadIdx.x; i < m; i += blockDim.x)
+  {
+    const size_t slot = seg_base + sample_slot(i, n_s);
+    float acc = 0.0f;
+#pragma unroll
+    for (int d = 0; d < D; d++)
+    {
+      const float t = x32[(size_t)d * row_stride + slot] - qs[d];
+      acc = fmaf(t, t, acc);
+    }
+    if (acc < CUDART_INF_F)
+      my_live++;
+    else
+      acc = CUDART_INF_F;  // tombstone (x32[0] = +inf) or NaN
+    key[i] = acc;
+  }
+  if (my_live)
+    atomicAdd(&live_s, my_live);
+  __syncthreads();
+  const uint32_t live = live_s;
+  float thr = FLT_MAX;  // fewer than k live nodes in the sample: no bound, collect everything
+  if (k >= 1 && k <= (unsigned long long)live)
+  {
+    unsigned long long rest = 0;
+    const unsigned long long kk = radix_select(
+        m, k, 4, [&](uint32_t i) { return (unsigned long long)fkey(key[i]); },
+        [&](uint32_t i) { return key[i] < CUDART_INF_F; }, hist, sh, &rest);
+    thr = slack_thr2(sqrtf(funkey((uint32_t)kk)) * (1.0f + 1.0e-6f), slack_abs);
+  }
+  if (threadIdx.x == 0)
+    thr2_out[q] = thr;
+}
+
+// Candidate lists with fp32 values (scan_stream_kernel MODE 2) -> the k nearest, exactly.
+// The k-th smallest fp32 value c_k bounds the true k-th distance from above (some node among the k smallest values
+// is at least the k-th in truth), so every true k-nearest node has a value <= stream_thr(c_k): only those -- k plus
+// a handful -- get their fp64 distance, are sorted by (dist64, slot) and the first k are the answer.
+template <int D>
+__global__ void __launch_bounds__(1024, 1)
+    select_topk_f32_kernel(const uint32_t* __restrict__ idx, const float* __restrict__ c2,
+                           const uint32_t* __restrict__ count, uint32_t cap, const double* __restrict__ x64,
+                           const double* __restrict__ qd, unsigned long long k, float xn_max, float slack_abs,
+                           uint32_t out_cap, uint32_t* __restrict__ out_idx, double* __restrict__ out_dist,
+                           uint32_t* __restrict__ out_count, uint32_t* __restrict__ err_flag, uint32_t P)
+{
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double* skey = reinterpret_cast<double*>(smem_raw);
+  uint32_t* sval = reinterpret_cast<uint32_t*>(skey + P);
+  __shared__ uint32_t hist[256];
+  __shared__ unsigned long long sh[2];
+  __shared__ uint32_t npicked;
+  __shared__ double qs[D];
+  const uint32_t q = blockIdx.x;
+  uint32_t n = count[q];
+  if (n > cap)
+  {
+    if (threadIdx.x == 0)
+      atomicOr(err_flag, 1u);  // the candidate list overflowed: the caller retries with a larger one
+    n = cap;
+  }
+  const uint32_t* li = idx + (size_t)q * cap;
+  const float* lc = c2 + (size_t)q * cap;
+  if (threadIdx.x < D)
+    qs[threadIdx.x] = qd[(size_t)q * D + threadIdx.x];
+  if (threadIdx.x == 0)
+    npicked = 0;
+  __syncthreads();
+  const uint32_t want = (k < (unsigned long long)n) ? (uint32_t)k : n;
+  float thr = CUDART_INF_F;
+  if (want < n)
+  {
+    unsigned long long rest = 0;
+    const unsigned long long kk = radix_select(
+        n, want, 4, [&](uint32_t i) { return (unsigned long long)fkey(lc[i]); }, [&](uint32_t) { return true; }, hist,
+        sh, &rest);
+    float qn = 0.0f;
+#pragma unroll
+    for (int d = 0; d < D; d++)
+    {
+      const float v = (float)qs[d];
+      qn = fmaf(v, v, qn);
+    }
+    const float e2 = (float)(3 * D + 8) * 5.9604645e-8f * 1.5f * (xn_max + qn) * 2.0f + FLT_MIN;
+    thr = stream_thr(funkey((uint32_t)kk), e2, slack_abs);
+  }
+  for (uint32_t i = threadIdx.x; i < n; i += blockDim.x)
+    if (lc[i] <= thr)
+    {
+      const uint32_t pos = atomicAdd(&npicked, 1u);
+      if (pos < P)
+      {
+        skey[pos] = dist64<D>(x64 + (size_t)li[i] * D, qs);
+        sval[pos] = li[i];
+      }
+    }
+  __syncthreads();
+  uint32_t m = npicked;
+  if (m > P)
+  {
+    if (threadIdx.x == 0)
+      atomicOr(err_flag, 2u);  // more near-ties than the sort buffer holds: the caller takes the all-fp64 path
+    m = P;
+  }
+  uint32_t p2 = 2;
+  while (p2 < m)
+    p2 <<= 1;
+  for (uint32_t i = m + threadIdx.x; i < p2; i += blockDim.x)
+  {
+    skey[i] = CUDART_INF;
+    sval[i] = GC_NO_NODE;
+  }
+  __syncthreads();
+  bitonic_sort(skey, sval, p2);
+  for (uint32_t i = threadIdx.x; i < (want < out_cap ? want : out_cap); i += blockDim.x)
+  {
+    out_idx[(size_t)q * out_cap + i] = sval[i];
+    out_dist[(size_t)q * out_cap + i] = skey[i];
+  }
+  if (threadIdx.x == 0)
+    out_count[q] = want;
+}
+
 // Node-sharded trees: node i lives on shard i mod G at local slot i div G.  After the
 // all-gather of the per-shard lists this merges them: global slot = local * G + g, ascending (dist, slot),
 // first k_out entries.  parts are [G][nq][cap] / [G][nq].
@@ -1523,10 +1684,28 @@ static int knn_large_dev(gc_store* s, const double* d_q, const uint32_t* d_seg, 
   const size_t row_stride = s->cap_total + kRowPad;
   const float slack = (float)(store_slack(s) * 1.0000001) + FLT_MIN;
   const size_t smem_sample = sizeof(float) * kSortMax;
+  // streaming stores keep fp32 candidates and refine only around the k-th (select_topk_f32_kernel); if that ever
+  // meets more near-ties than its sort buffer holds the call is redone on the all-fp64 path
+  const bool f32_path = use_stream(s, d_seg) && !s->knn_force_fp64;
+  uint32_t P32 = 2048;
+  while (P32 < 4 * k && P32 < kSortMax)
+    P32 <<= 1;
+  const size_t smem_sel32 = (size_t)P32 * (sizeof(double) + sizeof(uint32_t));
+  double xm = 0.0;
+  for (double v : s->max_abs)
+    xm = fmax(xm, v);
+  const float xn_max = (float)fmin((double)s->dim * xm * xm * 1.000001, 3.0e38);
   GC_DISPATCH_DIM(s->dim,
                   GC_CUDA(cudaFuncSetAttribute(knn_sample_kernel<DD>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                (int)smem_sample));
-                  knn_sample_kernel<DD><<<nq, 1024, smem_sample, s->stream>>>(
+                  GC_CUDA(cudaFuncSetAttribute(knn_sample_select_kernel<DD>,
+                                               cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_sample));
+                  GC_CUDA(cudaFuncSetAttribute(select_topk_f32_kernel<DD>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                               (int)(kSortMax * (sizeof(double) + sizeof(uint32_t)))));
+                  if (f32_path) knn_sample_select_kernel<DD><<<nq, 1024, smem_sample, s->stream>>>(
+                      s->x32, s->d_used, d_q, d_seg, s->cap_seg, row_stride, (unsigned long long)k, slack,
+                      s->d_thr.as<float>());
+                  else knn_sample_kernel<DD><<<nq, 1024, smem_sample, s->stream>>>(
                       s->x32, s->d_used, d_q, d_seg, s->cap_seg, row_stride, (unsigned long long)k, slack,
                       s->d_thr.as<float>()));
   GC_CUDA(cudaGetLastError());
@@ -1555,9 +1734,18 @@ static int knn_large_dev(gc_store* s, const double* d_q, const uint32_t* d_seg, 
     a.out_idx = s->d_cand_idx.as<uint32_t>();
     a.out_dist = s->d_cand_dist.as<double>();
     a.out_count = s->d_cand_count.as<uint32_t>();
-    if (use_stream(s, d_seg))
+    if (f32_path)
+    {
+      a.out_c2 = reinterpret_cast<float*>(s->d_cand_dist.p);
       GC_TRY(launch_stream<2>(s, a, nqc));
-    else
+      GC_DISPATCH_DIM(s->dim, (select_topk_f32_kernel<DD><<<nqc, 1024, smem_sel32, s->stream>>>(
+                                  a.out_idx, a.out_c2, a.out_count, capB, s->x64, a.q, (unsigned long long)k, xn_max,
+                                  slack, cap, d_idx + (size_t)q0 * cap, d_dist + (size_t)q0 * cap, d_count + q0, d_err,
+                                  P32)));
+      GC_CUDA(cudaGetLastError());
+      count_launch();
+      continue;
+    }
     {
       dim3 grid(chunks, groups);
       GC_DISPATCH_DIM(s->dim, (scan_kernel<DD, 2><<<grid, kScanThreads, 0, s->stream>>>(a)));
@@ -1573,6 +1761,11 @@ static int knn_large_dev(gc_store* s, const double* d_q, const uint32_t* d_seg, 
   uint32_t err = 0;
   GC_CUDA(cudaMemcpyAsync(&err, d_err, sizeof(uint32_t), cudaMemcpyDeviceToHost, s->stream));
   GC_CUDA(cudaStreamSynchronize(s->stream));
+  if (err & 2u)
+  {
+    s->knn_force_fp64 = true;  // this store holds massive near-ties: stay on the all-fp64 path from now on
+    return GC_E_CAPACITY;
+  }
   if (err)
   {
     if (capB >= mu)

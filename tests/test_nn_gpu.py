@@ -314,6 +314,13 @@ def test_stream_scan_massive_duplicates_take_lowest_slot(gc, orc):
         b = int(np.argmin(d[i]))
         first = int(np.nonzero(which == b)[0][0])
         assert idx[i] == first, (i, idx[i], first)
+    # k-nearest over the same store: more exact ties than the fp32-candidate selection can hold -> the store switches
+    # to the all-fp64 path and still returns the k lowest slots of the nearest point, then the next point's
+    ki, kd, kc = st.knn(qs[:3], 10, cap=10)
+    for i in range(3):
+        assert ki[i].tolist() == np.nonzero(which == i)[0][:10].tolist() and (kd[i] == 0.0).all()
+    ki, kd, kc = st.knn(qs[:1], 12000, cap=12000)
+    assert kc[0] == 12000 and ki[0].tolist() == np.nonzero(which == 0)[0][:12000].tolist()
     # fp64 near-ties that fp32 cannot separate: the fp64 decision picks the truly closer point
     a = np.zeros((40_000, 3))
     a[:, 0] = 1.0 + np.arange(40_000) * 1e-3
