@@ -28,6 +28,7 @@
 #include <graph_core/solvers/anytime_rrt.h>
 #include <graph_core/solvers/birrt.h>
 #include <graph_core/solvers/rrt.h>
+#include <graph_core/solvers/path_optimizers/path_local_optimizer.h>
 #include <graph_core/solvers/rrt_star.h>
 
 #include <cstring>
@@ -391,6 +392,74 @@ double ref_solver_path_cost(void* h)
 {
   PathPtr p = ((RefSolver*)h)->solver->getSolution();
   return p ? p->cost() : std::numeric_limits<double>::infinity();
+}
+
+// ---- Path validity and local optimisation with the SOLVER'S OWN checker ------------
+// Path::isValid (path.cpp:1230-1260 -> isValidFromConn): every connection of the solution is re-checked, invalid
+// ones get cost +inf.  costs[i] receives the cost of connection i afterwards; returns 1 valid, 0 invalid, -1 no path.
+// other_checker (a RefChecker*, may be NULL) replaces the path's checker, e.g. the same scene with new obstacles.
+int ref_solution_is_valid(void* h, void* other_checker, int cap, double* costs)
+{
+  RefSolver* s = (RefSolver*)h;
+  PathPtr p = s->solver->getSolution();
+  if (!p || !s->solver->solved())
+    return -1;
+  CollisionCheckerPtr chk = other_checker ? ((RefChecker*)other_checker)->c : CollisionCheckerPtr();
+  const bool valid = p->isValid(chk);
+  const std::vector<ConnectionPtr>& conns = p->getConnectionsConst();
+  for (int i = 0; i < (int)conns.size() && i < cap; i++)
+    costs[i] = conns[i]->getCost();
+  return valid ? 1 : 0;
+}
+// Path::isValidFromConf (path.cpp:1262-1407) from the point at fraction t of connection conn_idx
+int ref_solution_is_valid_from(void* h, void* other_checker, int conn_idx, double t)
+{
+  RefSolver* s = (RefSolver*)h;
+  PathPtr p = s->solver->getSolution();
+  if (!p || !s->solver->solved())
+    return -1;
+  CollisionCheckerPtr chk = other_checker ? ((RefChecker*)other_checker)->c : CollisionCheckerPtr();
+  const std::vector<ConnectionPtr>& conns = p->getConnectionsConst();
+  if (conn_idx < 0 || conn_idx >= (int)conns.size())
+    return -1;
+  const Eigen::VectorXd a = conns[conn_idx]->getParent()->getConfiguration();
+  const Eigen::VectorXd b = conns[conn_idx]->getChild()->getConfiguration();
+  const Eigen::VectorXd conf = a + (b - a) * t;
+  return p->isValidFromConf(conf, (size_t)conn_idx, chk) ? 1 : 0;
+}
+// PathLocalOptimizer (path_local_optimizer.cpp:59-204) on a CLONE of the solution: mode 0 warp, 1 simplify, 2 solve();
+// the optimised waypoints go to conf, returns their number (0 = no path)
+int ref_solution_optimize(void* h, int mode, int max_iter, int cap, double* conf, double* cost_out)
+{
+  RefSolver* s = (RefSolver*)h;
+  PathPtr p = s->solver->getSolution();
+  if (!p || !s->solver->solved())
+    return 0;
+  PathPtr q = p->clone();
+  PathLocalOptimizer opt(s->checker, s->metrics, g_logger);
+  opt.config("/ref_driver/path_optimizer");
+  opt.setPath(q);
+  if (mode == 0)
+    for (int i = 0; i < max_iter; i++)
+      opt.warp();
+  else if (mode == 1)
+    for (int i = 0; i < max_iter; i++)
+      opt.simplify();
+  else
+    opt.solve((unsigned int)max_iter, 1.0e9);
+  std::vector<Eigen::VectorXd> wp = q->getWaypoints();
+  for (int i = 0; i < (int)wp.size() && i < cap; i++)
+    for (int k = 0; k < s->dim; k++)
+      conf[(size_t)i * s->dim + k] = wp[i](k);
+  if (cost_out)
+    *cost_out = q->cost();
+  return (int)wp.size();
+}
+// Tree::recheckCollision (tree.cpp:1405-1429): re-validates the whole start tree with the solver's checker
+int ref_tree_recheck(void* h)
+{
+  TreePtr t = ((RefSolver*)h)->solver->getStartTree();
+  return (t && t->recheckCollision()) ? 1 : 0;
 }
 
 // ---- samplers: the reference's own sampling code with the shim's std::rand stream --------------------

@@ -90,6 +90,19 @@ void* dropin_solver_new(int kind, int dim, void* world, const double* lb, const 
   return s;
 }
 
+// a RefChecker (as ref_checker_* make them) backed by a CUDA world: usable wherever the ref_* entry points take one
+void* dropin_checker_new(int dim, void* world, double min_distance)
+{
+  try
+  {
+    return new RefChecker{ std::make_shared<CudaCollisionChecker>(g_logger, (gc_world_t*)world, min_distance), dim };
+  }
+  catch (const std::exception&)
+  {
+    return nullptr;
+  }
+}
+
 // device calls made by the checker of a drop-in solver (proof that the CUDA path answered)
 unsigned long long dropin_checker_device_calls(void* h)
 {

@@ -79,6 +79,10 @@ def lib(fast: bool = False, dropin: bool = False):
         "ref_solver_dump": (C.c_int, [vp, C.c_int, _dp, _dp, _dp]),
         "ref_solver_solution": (C.c_int, [vp, C.c_int, _dp]),
         "ref_solver_path_cost": (C.c_double, [vp]),
+        "ref_solution_is_valid": (C.c_int, [vp, vp, C.c_int, _dp]),
+        "ref_solution_is_valid_from": (C.c_int, [vp, vp, C.c_int, C.c_double]),
+        "ref_solution_optimize": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, _dp, _dp]),
+        "ref_tree_recheck": (C.c_int, [vp]),
         "ref_srand": (None, [C.c_uint]),
         "ref_sample_informed": (None, [C.c_int, _dp, _dp, _dp, _dp, C.c_double, C.c_int, _dp]),
         "ref_informed_specific_volume": (C.c_double, [C.c_int, _dp, _dp, _dp, _dp, C.c_double]),
@@ -87,6 +91,7 @@ def lib(fast: bool = False, dropin: bool = False):
     if dropin:
         sig["dropin_solver_new"] = (vp, [C.c_int, C.c_int, vp, _dp, _dp, _dp, _dp, C.c_double, C.c_double, C.c_double,
                                          C.c_double, C.c_int, C.c_int, C.c_int, C.c_int])
+        sig["dropin_checker_new"] = (vp, [C.c_int, vp, C.c_double])
         sig["dropin_checker_device_calls"] = (C.c_ulonglong, [vp])
         sig["dropin_uses_cuda_nn"] = (C.c_int, [vp])
     for name, (res, args) in sig.items():
@@ -300,6 +305,37 @@ class RefSolver:
     @property
     def path_cost(self):
         return self.L.ref_solver_path_cost(self.h)
+
+    def solution_is_valid(self, other_checker=None):
+        """Path::isValid with the path's own checker or another RefChecker; returns (valid, connection costs)."""
+        costs = np.empty(1 << 14)
+        r = self.L.ref_solution_is_valid(self.h, other_checker.h if other_checker is not None else None, costs.shape[0],
+                                         _p(costs, _dp))
+        n = max(len(self.solution()) - 1, 0)
+        return r, costs[:n].copy()
+
+    def solution_is_valid_from(self, conn_idx, t, other_checker=None):
+        return self.L.ref_solution_is_valid_from(self.h, other_checker.h if other_checker is not None else None,
+                                                 conn_idx, t)
+
+    def optimize_solution(self, mode, max_iter):
+        """PathLocalOptimizer on a clone of the solution: mode 0 warp, 1 simplify, 2 solve; (waypoints, cost)."""
+        wp = np.empty((1 << 14, self.dim))
+        cost = C.c_double(0.0)
+        n = self.L.ref_solution_optimize(self.h, mode, max_iter, wp.shape[0], _p(wp, _dp), C.byref(cost))
+        return wp[:n].copy(), cost.value
+
+    def recheck_tree(self):
+        return bool(self.L.ref_tree_recheck(self.h))
+
+
+def cuda_ref_checker(cuda_world, min_distance):
+    """A RefChecker whose CollisionCheckerBase is graph::core::CudaCollisionChecker over a CUDA world."""
+    L = lib(dropin=True)
+    h = L.dropin_checker_new(cuda_world.dim, cuda_world.handle, min_distance)
+    if not h:
+        raise RuntimeError("dropin_checker_new failed")
+    return RefChecker(h, cuda_world.dim, L, min_distance, keep=(cuda_world,))
 
 
 class DropinSolver(RefSolver):

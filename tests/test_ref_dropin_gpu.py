@@ -95,3 +95,73 @@ def test_anytime_rrt_with_cuda_checker(gc, orc, ref, c3, name):
     assert ok_cpu == ok_gpu
     _same(ref, cpu, gpu)
     assert gpu.device_calls > 10
+
+
+def _box_scene_with_new_obstacle(sc, path):
+    """The C1 scene plus one box dropped onto the middle of the given path."""
+    import copy
+    mid = path[len(path) // 2]
+    sc2 = copy.deepcopy(sc)
+    sc2.params = {"lo": np.vstack([sc.params["lo"], mid - 0.04]), "hi": np.vstack([sc.params["hi"], mid + 0.04])}
+    return sc2
+
+
+def test_path_validity_and_local_optimizer_through_the_cuda_checker(gc, orc, ref):
+    """SURVEY 8f rows N1-N3 at the reference's own call sites: Path::isValid / isValidFromConf (path.cpp:1230-1407),
+    Tree::recheckCollision (tree.cpp:1405-1429) and PathLocalOptimizer::warp / simplify
+    (path_local_optimizer.cpp:59-204) issue their checkConnection / checkConnFromConf calls to CudaCollisionChecker
+    and must decide exactly as with the CPU checker."""
+    sc = W.scenario_c1()
+    samples = W.uniform_samples(sc.lb, sc.ub, 9400, 0, 2500)
+    # both solvers live in the drop-in library so that checkers can be exchanged between them
+    L = ref.lib(dropin=True)
+
+    cpu_chk_in_dropin = ref.RefChecker(L.ref_checker_callback(sc.dim, *_cb(orc, sc), sc.min_distance), sc.dim, L,
+                                       sc.min_distance)
+    cpu = ref.RefSolver.__new__(ref.RefSolver)
+    cpu.L, cpu.checker, cpu.dim = L, cpu_chk_in_dropin, sc.dim
+    lb, ub, s0, g0 = (np.ascontiguousarray(x, dtype=np.float64) for x in (sc.lb, sc.ub, sc.start, sc.goal))
+    import ctypes as C
+    dp = C.POINTER(C.c_double)
+    cpu.h = L.ref_solver_new(ref.RefSolver.RRTSTAR, sc.dim, cpu_chk_in_dropin.h, lb.ctypes.data_as(dp),
+                             ub.ctypes.data_as(dp), s0.ctypes.data_as(dp), g0.ctypes.data_as(dp), sc.max_distance,
+                             sc.rewire_factor, sc.utopia_tolerance, 1, 0, 1)
+    gw = sc.make_world()
+    gpu = ref.DropinSolver(ref.RefSolver.RRTSTAR, sc, gw, informed=True, cuda_nn=True)
+    assert cpu.run(samples) == gpu.run(samples)
+    _same(ref, cpu, gpu)
+    assert cpu.solved
+    path = cpu.solution()
+    # N2: the untouched path is valid on both sides, connection costs re-evaluated identically
+    v_cpu, c_cpu = cpu.solution_is_valid()
+    v_gpu, c_gpu = gpu.solution_is_valid()
+    assert v_cpu == v_gpu == 1 and np.array_equal(c_cpu, c_gpu)
+    # N1: whole-tree re-validation
+    assert cpu.recheck_tree() == gpu.recheck_tree()
+    # a new obstacle on the path: same connections become infinite, same verdict from any point of the path on
+    sc2 = _box_scene_with_new_obstacle(sc, path)
+    ow2 = orc.OracleWorld.from_scenario(sc2)
+    cpu_chk2 = ref.RefChecker(L.ref_checker_callback(sc.dim, C.cast(ow2.L.orc_check_states, C.c_void_p), ow2.h,
+                                                     sc.min_distance), sc.dim, L, sc.min_distance, keep=(ow2,))
+    gpu_chk2 = ref.cuda_ref_checker(sc2.make_world(), sc.min_distance)
+    v_cpu, c_cpu = cpu.solution_is_valid(cpu_chk2)
+    v_gpu, c_gpu = gpu.solution_is_valid(gpu_chk2)
+    assert v_cpu == v_gpu == 0 and np.array_equal(c_cpu, c_gpu) and np.isinf(c_cpu).any()
+    for ci in range(len(path) - 1):
+        for t in (0.0, 0.37, 1.0):
+            assert cpu.solution_is_valid_from(ci, t, cpu_chk2) == gpu.solution_is_valid_from(ci, t, gpu_chk2), (ci, t)
+    # N3: local optimisation of the (restored) path takes the same decisions
+    cpu.solution_is_valid()
+    gpu.solution_is_valid()
+    for mode, iters in ((0, 5), (1, 5), (2, 30)):
+        wc, cc = cpu.optimize_solution(mode, iters)
+        wg, cg = gpu.optimize_solution(mode, iters)
+        assert np.array_equal(wc, wg) and cc == cg, mode
+    assert gpu.device_calls > 100
+
+
+def _cb(orc, sc):
+    import ctypes as C
+    ow = orc.OracleWorld.from_scenario(sc)
+    _cb.keep = getattr(_cb, "keep", []) + [ow]
+    return C.cast(ow.L.orc_check_states, C.c_void_p), ow.h
