@@ -680,6 +680,7 @@ struct PlanArgs
   uint32_t* offs;      // [kPasses][n+1] exclusive prefix of the per-pass state counts
   uint8_t* ok;         // initialised here: 1, or 255 when the reference would throw
   unsigned long long* first_bad;
+  uint32_t* work_ctr;  // zeroed here for the check kernel that follows
 };
 
 template <int D, int MODE>
@@ -692,6 +693,8 @@ __global__ void __launch_bounds__(1024) edge_plan_kernel(PlanArgs a)
     carry_s[threadIdx.x] = 0;
     a.offs[(size_t)threadIdx.x * (a.n + 1)] = 0;
   }
+  if (threadIdx.x == 0 && a.work_ctr)
+    *a.work_ctr = 0;
   __syncthreads();
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   for (uint32_t base = 0; base < a.n; base += blockDim.x)
@@ -779,6 +782,7 @@ struct ArmArgs
   unsigned long long* counters;
   int mode;        // gc_edge_mode, or 3 = plain state batch
   uint32_t lanes;  // lane mode: lanes per state (1, 2, 4, 8)
+  uint32_t* work_ctr;  // items handed out so far beyond the first one of every group (zeroed before the launch)
 };
 
 template <int D>
@@ -857,11 +861,21 @@ __global__ void __launch_bounds__(G == 1 ? 128 : 256, G == 1 ? (NRS <= 16 ? 4 : 
   const int leader = lane & ~((int)lps - 1);              // first lane of this state's group
   const uint32_t item0 = gthread / lps;
   const uint32_t nitems = nthreads / lps;
-  // round the trip count up so that every lane of a warp takes part in the warp-wide votes
-  const uint32_t trips = (total + nitems - 1) / nitems;
-  for (uint32_t it = 0; it < trips; it++)
+  // Every group starts on item `item0`; further items are handed out through one atomic counter, in list order
+  // (pass-major), so that groups whose states exit early simply take more of them: no tail of idle lanes behind
+  // a static partition.  The next index is requested before the current item is processed (latency hidden).
+  // Whole warps iterate together (the votes below need every lane) until all their groups have run dry.
+  uint32_t t = item0;
+  while (true)
   {
-    const uint32_t t = item0 + it * nitems;
+    if (__all_sync(0xffffffffu, t >= total))
+      break;
+    uint32_t t_next = 0xFFFFFFFFu;
+    if (lane == leader && t < total)
+    {
+      const uint32_t k = atomicAdd(a.work_ctr, 1u);
+      t_next = (k < 0xFFFFFFFFu - nitems) ? nitems + k : 0xFFFFFFFFu;
+    }
     bool have = t < total;
     uint32_t e = 0, s = 0;
     if (have && MODE != 3)
@@ -939,6 +953,7 @@ __global__ void __launch_bounds__(G == 1 ? 128 : 256, G == 1 ? (NRS <= 16 ? 4 : 
           atomicMin(&a.first_bad[e], (unsigned long long)s);
       }
     }
+    t = __shfl_sync(0xffffffffu, t_next, leader);
   }
   for (int o = 16; o > 0; o >>= 1)
   {
@@ -1150,7 +1165,7 @@ int check_edges_dev(gc_world* w, const double* d_c1, const double* d_c2, const d
   else
   {
     GC_TRY(w->d_plan.reserve(sizeof(double) * 2 * (size_t)n));
-    GC_TRY(w->d_offs.reserve(sizeof(uint32_t) * (kPasses * ((size_t)n + 1) + n)));
+    GC_TRY(w->d_offs.reserve(sizeof(uint32_t) * (kPasses * ((size_t)n + 1) + n + 1)));
     PlanArgs p{};
     p.c1 = d_c1;
     p.c2 = d_c2;
@@ -1161,6 +1176,7 @@ int check_edges_dev(gc_world* w, const double* d_c1, const double* d_c2, const d
     p.aux = p.dist + n;
     p.offs = w->d_offs.as<uint32_t>();
     p.nst = p.offs + kPasses * ((size_t)n + 1);
+    p.work_ctr = p.nst + n;
     p.ok = d_ok;
     p.first_bad = reinterpret_cast<unsigned long long*>(d_first_bad);
     ArmArgs a{};
@@ -1181,6 +1197,7 @@ int check_edges_dev(gc_world* w, const double* d_c1, const double* d_c2, const d
     a.first_bad = p.first_bad;
     a.counters = w->d_counters;
     a.mode = mode;
+    a.work_ctr = p.work_ctr;
     const int pthreads = n >= 1024 ? 1024 : (int)align_up(n, 32);
     GC_DISPATCH_DIM_E(w->dim, GC_DISPATCH_MODE(mode, 
                                                (edge_plan_kernel<DD, MM><<<1, pthreads, 0, st>>>(p));
@@ -1224,6 +1241,9 @@ int check_states_dev(gc_world* w, const double* d_q, uint32_t n, uint8_t* d_ok, 
     a.ok = d_ok;
     a.counters = w->d_counters;
     a.mode = 3;
+    GC_TRY(w->d_offs.reserve(sizeof(uint32_t) * 4));
+    a.work_ctr = w->d_offs.as<uint32_t>();
+    GC_CUDA(cudaMemsetAsync(a.work_ctr, 0, sizeof(uint32_t), st));
     GC_DISPATCH_DIM_E(w->dim, GC_TRY((launch_arm_nrs<DD>(w, a, n, st))));
   }
   return time_end(w, st);
