@@ -570,15 +570,22 @@ __global__ void __launch_bounds__(kStThreads, 3) scan_stream_kernel(ScanArgs a)
           x[d][r] = 0.0f;
       }
     }
-    // expanded-form values of this thread's four nodes against queries q .. q+kStQPT-1
+    // expanded-form values of this thread's four nodes against queries q .. q+kStQPT-1.  The D fused multiply-adds
+    // per pair run as packed FFMA2 (fma.rn.f32x2, sm_100): two NODES per 64-bit register pair, the query coordinate
+    // as a scalar operand broadcast to both halves -- 1.5 register operands per FMA instead of 2 (the register
+    // file's operand delivery, not the issue rate, bounds the scalar form; tools/ffma_forms4.cu).  Each half is an
+    // ordinary IEEE fma: the values are bit-identical to the scalar loop's.
+    const float2 xn01 = make_float2(xn[0], xn[1]), xn23 = make_float2(xn[2], xn[3]);
     auto trip_values = [&](int q, float (&acc)[kStQPT][kNodesPerThread]) {
       const float4 qn4 = *reinterpret_cast<const float4*>(m.qn + q);
       const float qna[4] = { qn4.x, qn4.y, qn4.z, qn4.w };
+      float2 lo[kStQPT], hi[kStQPT];
 #pragma unroll
       for (int h = 0; h < kStQPT; h++)
-#pragma unroll
-        for (int r = 0; r < kNodesPerThread; r++)
-          acc[h][r] = xn[r] + qna[h];
+      {
+        lo[h] = __fadd2_rn(xn01, make_float2(qna[h], qna[h]));
+        hi[h] = __fadd2_rn(xn23, make_float2(qna[h], qna[h]));
+      }
 #pragma unroll
       for (int d4 = 0; d4 < DP; d4 += 4)
       {
@@ -596,12 +603,23 @@ __global__ void __launch_bounds__(kStThreads, 3) scan_stream_kernel(ScanArgs a)
         for (int j = 0; j < 4; j++)
           if (d4 + j < D)
           {
+            const float2 x01 = make_float2(x[d4 + j][0], x[d4 + j][1]), x23 = make_float2(x[d4 + j][2], x[d4 + j][3]);
 #pragma unroll
             for (int h = 0; h < kStQPT; h++)
-#pragma unroll
-              for (int r = 0; r < kNodesPerThread; r++)
-                acc[h][r] = fmaf(x[d4 + j][r], qa[h][j], acc[h][r]);
+            {
+              const float2 qq = make_float2(qa[h][j], qa[h][j]);
+              lo[h] = __ffma2_rn(x01, qq, lo[h]);
+              hi[h] = __ffma2_rn(x23, qq, hi[h]);
+            }
           }
+      }
+#pragma unroll
+      for (int h = 0; h < kStQPT; h++)
+      {
+        acc[h][0] = lo[h].x;
+        acc[h][1] = lo[h].y;
+        acc[h][2] = hi[h].x;
+        acc[h][3] = hi[h].y;
       }
     };
     if (MODE == 0 && it == 0)
