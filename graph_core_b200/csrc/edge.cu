@@ -391,6 +391,10 @@ __device__ __forceinline__ void mat3_vec(const float* R, const float* t, float p
   }
 }
 
+// The obstacle cloud is padded in shared memory to a multiple of 128 spheres with ones that never collide
+// (NA = -inf), so the pair loop needs neither a tail nor index clamps for any lane count.
+__host__ __device__ __forceinline__ uint32_t arm_padded_obstacles(uint32_t nobs) { return (nobs + 127u) & ~127u; }
+
 // smem image of the arm: base_tf[12] | joint_tf[J][12] | rs_local[nrs][4] | rs_link[nrs] (int bits)
 struct ArmSmem
 {
@@ -535,44 +539,44 @@ __device__ __forceinline__ bool arm_check_lane(const ArmSmem& w, uint32_t nrs, u
     }
   }
   // Obstacles part, part+nparts, ...  Any sphere hits obstacle o  <=>  min_k t_k < NA_o, so the sixteen
-  // compares collapse into a min tree (FMNMX3) and ONE compare per obstacle; the next obstacle is
-  // loaded while the current one is evaluated; the early-exit test runs once per 16 obstacles.
-  // Obstacles part, part+nparts, ...  Any sphere hits obstacle o  <=>  min_k t_k < NA_o, so the sixteen
-  // compares collapse into a min tree (FMNMX3) and ONE compare per obstacle; the next obstacle is
-  // loaded while the current one is evaluated; the early-exit test runs once per 16 obstacles.
-  const uint32_t mycount = (part < nobs) ? (nobs - part + nparts - 1) / nparts : 0u;
+  // compares collapse into a min tree (FMNMX3) and ONE compare per obstacle; the early-exit test runs once
+  // per 16 obstacles.  The padded cloud (arm_stage) makes every lane's share a whole number of such blocks, so the
+  // loop carries no clamps, no tail and no register rotation: 64 FFMA + 8 FMNMX3 + ~12 others per obstacle.
+  const uint32_t npad = arm_padded_obstacles(nobs);
+  const float4* po = w.obs + part;
+  const float* pn = w.obs_na + part;
+  const float4* const pe = w.obs + npad;
   bool hit = false;
-  uint32_t done = 0;
-  if (mycount)
+  uint32_t blocks16 = 0;
+  while (po < pe && !hit)
   {
-    float4 ob = w.obs[part];
-    float na = w.obs_na[part];
-    for (uint32_t base = 0; base < mycount && !hit; base += 16u)
-    {
-      const uint32_t cnt = min(16u, mycount - base);
 #pragma unroll 2
-      for (uint32_t u = 0; u < cnt; u++)
-      {
-        // prefetch the next obstacle of this lane (the last iteration re-reads its own, harmlessly)
-        const uint32_t nx = min(base + u + 1u, mycount - 1u);
-        const float4 ob_n = w.obs[part + nx * nparts];
-        const float na_n = w.obs_na[part + nx * nparts];
-        float m = 3.0e38f;
+    for (int u = 0; u < 16; u++)
+    {
+      const float4 ob = *po;
+      const float na = *pn;
+      po += nparts;
+      pn += nparts;
+      float m = 3.0e38f;
 #pragma unroll
-        for (int k = 0; k < NRS; k++)
-        {
-          float t = __fmaf_rn(ob.x, sk[k].c2x, sk[k].B);
-          t = __fmaf_rn(ob.y, sk[k].c2y, t);
-          t = __fmaf_rn(ob.z, sk[k].c2z, t);
-          t = __fmaf_rn(ob.w, sk[k].rs2, t);
-          m = fminf(m, t);
-        }
-        hit |= (m < na);
-        ob = ob_n;
-        na = na_n;
+      for (int k = 0; k < NRS; k++)
+      {
+        float t = __fmaf_rn(ob.x, sk[k].c2x, sk[k].B);
+        t = __fmaf_rn(ob.y, sk[k].c2y, t);
+        t = __fmaf_rn(ob.z, sk[k].c2z, t);
+        t = __fmaf_rn(ob.w, sk[k].rs2, t);
+        m = fminf(m, t);
       }
-      done += cnt;
+      hit |= (m < na);
     }
+    blocks16++;
+  }
+  // pair tests on real obstacles only: this lane saw obstacles part + i*nparts, i < 16*blocks16
+  uint32_t done = 0;
+  {
+    const uint32_t seen = 16u * blocks16;
+    const uint32_t mine = (part < nobs) ? (nobs - part + nparts - 1) / nparts : 0u;
+    done = seen < mine ? seen : mine;
   }
   pairs += (unsigned long long)done * nrs;
   return hit;
@@ -798,15 +802,22 @@ __device__ __forceinline__ bool state_conf_rt(int mode, const double* c1, const 
 
 __device__ __forceinline__ ArmSmem arm_stage(const ArmArgs& a, unsigned char* smem_raw)
 {
+  const uint32_t npad = arm_padded_obstacles(a.nobs);
   float4* sobs = reinterpret_cast<float4*>(smem_raw);
-  float* sna = reinterpret_cast<float*>(sobs + a.nobs);
-  float* sarm = sna + a.nobs;
+  float* sna = reinterpret_cast<float*>(sobs + npad);
+  float* sarm = sna + npad;
   const uint32_t arm_words = 12u + 12u * a.njoints + 4u * a.nrs + a.nrs;
-  for (uint32_t i = threadIdx.x; i < a.nobs; i += blockDim.x)
+  for (uint32_t i = threadIdx.x; i < npad; i += blockDim.x)
   {
-    const float4 ob = reinterpret_cast<const float4*>(a.obs)[i];
+    float4 ob = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    float na = -CUDART_INF_F;
+    if (i < a.nobs)
+    {
+      ob = reinterpret_cast<const float4*>(a.obs)[i];
+      na = obstacle_na(ob);
+    }
     sobs[i] = ob;
-    sna[i] = obstacle_na(ob);
+    sna[i] = na;
   }
   for (uint32_t i = threadIdx.x; i < arm_words; i += blockDim.x)
     sarm[i] = a.arm[i];
@@ -1038,7 +1049,7 @@ static int launch_light(gc_world* w, const LightArgs& a, cudaStream_t st)
 template <int D, int NRS, int G>
 static int launch_arm(gc_world* w, const ArmArgs& a, uint64_t items_hint, cudaStream_t st)
 {
-  const size_t smem = (sizeof(float4) + sizeof(float)) * a.nobs + sizeof(float) * (12 + 12 * a.njoints + 5 * a.nrs) + 16;
+  const size_t smem = (sizeof(float4) + sizeof(float)) * arm_padded_obstacles(a.nobs) + sizeof(float) * (12 + 12 * a.njoints + 5 * a.nrs) + 16;
   if (smem > 200 * 1024)
   {
     gc::set_error("obstacle cloud too large for shared memory staging (%zu bytes)", smem);
