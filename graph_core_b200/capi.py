@@ -105,6 +105,9 @@ PROTOTYPES = {
     "gc_merge_shard_lists_dev": (C.c_int, [C.c_int, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p,
                                            C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32, C.c_void_p, C.c_void_p,
                                            C.c_void_p]),
+    "gc_merge_shard_lists_p2p_dev": (C.c_int, [C.c_int, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32,
+                                               C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
+                                               C.c_uint64, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]),
     "gc_launch_count": (C.c_int, [_c_u64_p]),
     "gc_measure_fp32_peak": (C.c_int, [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "gc_flush_l2": (C.c_int, [C.c_int, C.c_size_t]),

@@ -1451,6 +1451,71 @@ __global__ void __launch_bounds__(1024, 1)
     out_count[q] = want;
 }
 
+// The same merge with the exchange fused in: shard g's lists are read straight from shard g's own result buffers
+// through peer-mapped pointers (NVLink / NVSwitch loads), so there is no all-gather and no gathered copy.  The
+// callers put one cross-GPU barrier between the producing kernels and this one.
+struct PeerLists
+{
+  const uint32_t* idx[16];
+  const double* dist[16];
+  const uint32_t* count[16];
+};
+__global__ void __launch_bounds__(1024, 1)
+    merge_shard_lists_p2p_kernel(PeerLists pl, uint32_t G, uint32_t nq, uint32_t cap, unsigned long long k_out,
+                                 uint32_t out_cap, uint32_t* __restrict__ out_idx, double* __restrict__ out_dist,
+                                 uint32_t* __restrict__ out_count, uint32_t P)
+{
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double* skey = reinterpret_cast<double*>(smem_raw);
+  uint32_t* sval = reinterpret_cast<uint32_t*>(skey + P);
+  __shared__ uint32_t base_s[17];
+  const uint32_t q = blockIdx.x;
+  if (threadIdx.x == 0)
+  {
+    uint32_t tot = 0;
+    for (uint32_t g = 0; g < G; g++)
+    {
+      base_s[g] = tot;
+      tot += min(__ldcg(pl.count[g] + q), cap);
+    }
+    base_s[G] = tot;
+  }
+  __syncthreads();
+  for (uint32_t g = 0; g < G; g++)
+  {
+    const uint32_t base = base_s[g], n = base_s[g + 1] - base_s[g];
+    const uint32_t* li = pl.idx[g] + (size_t)q * cap;
+    const double* ld = pl.dist[g] + (size_t)q * cap;
+    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x)
+      if (base + i < P)
+      {
+        const uint32_t local = __ldcg(li + i);
+        skey[base + i] = __ldcg(ld + i);
+        sval[base + i] = (local == GC_NO_NODE) ? GC_NO_NODE : local * G + g;
+      }
+  }
+  __syncthreads();
+  const uint32_t m = min(base_s[G], P);
+  uint32_t p2 = 2;
+  while (p2 < m)
+    p2 <<= 1;
+  for (uint32_t i = m + threadIdx.x; i < p2; i += blockDim.x)
+  {
+    skey[i] = CUDART_INF;
+    sval[i] = GC_NO_NODE;
+  }
+  __syncthreads();
+  bitonic_sort(skey, sval, p2);
+  const uint32_t want = (k_out < (unsigned long long)m) ? (uint32_t)k_out : m;
+  for (uint32_t i = threadIdx.x; i < min(want, out_cap); i += blockDim.x)
+  {
+    out_idx[(size_t)q * out_cap + i] = sval[i];
+    out_dist[(size_t)q * out_cap + i] = skey[i];
+  }
+  if (threadIdx.x == 0)
+    out_count[q] = want;
+}
+
 // ---------------------------------------------------------------------------------------------
 // dispatch helpers
 // ---------------------------------------------------------------------------------------------
@@ -2145,6 +2210,41 @@ int gc_merge_shard_lists_dev(int device, void* cuda_stream, uint32_t n_shards, u
   merge_shard_lists_kernel<<<nq, threads, smem, reinterpret_cast<cudaStream_t>(cuda_stream)>>>(
       d_idx, d_dist, d_count, n_shards, nq, cap, (unsigned long long)k_out, out_cap, d_out_idx, d_out_dist,
       d_out_count, P);
+  GC_CUDA(cudaGetLastError());
+  count_launch();
+  return GC_OK;
+}
+
+int gc_merge_shard_lists_p2p_dev(int device, void* cuda_stream, uint32_t n_shards, uint32_t nq, uint32_t cap,
+                                 const void* const* d_idx_of_shard, const void* const* d_dist_of_shard,
+                                 const void* const* d_count_of_shard, uint64_t k_out, uint32_t out_cap,
+                                 uint32_t* d_out_idx, double* d_out_dist, uint32_t* d_out_count)
+{
+  GC_REQUIRE(d_idx_of_shard && d_dist_of_shard && d_count_of_shard && d_out_idx && d_out_dist && d_out_count,
+             "gc_merge_shard_lists_p2p_dev: NULL argument");
+  GC_REQUIRE(n_shards >= 1 && n_shards <= 16, "gc_merge_shard_lists_p2p_dev: %u shards (1..16)", n_shards);
+  GC_REQUIRE((uint64_t)n_shards * cap <= kSortMax, "gc_merge_shard_lists_p2p_dev: n_shards*cap = %llu above %u",
+             (unsigned long long)n_shards * cap, kSortMax);
+  if (nq == 0)
+    return GC_OK;
+  GC_SET_DEVICE(device);
+  PeerLists pl{};
+  for (uint32_t g = 0; g < n_shards; g++)
+  {
+    GC_REQUIRE(d_idx_of_shard[g] && d_dist_of_shard[g] && d_count_of_shard[g], "gc_merge_shard_lists_p2p_dev: shard %u", g);
+    pl.idx[g] = static_cast<const uint32_t*>(d_idx_of_shard[g]);
+    pl.dist[g] = static_cast<const double*>(d_dist_of_shard[g]);
+    pl.count[g] = static_cast<const uint32_t*>(d_count_of_shard[g]);
+  }
+  uint32_t P = 2;
+  while (P < n_shards * cap)
+    P <<= 1;
+  const size_t smem = (size_t)P * (sizeof(double) + sizeof(uint32_t));
+  GC_CUDA(cudaFuncSetAttribute(merge_shard_lists_p2p_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               (int)(kSortMax * (sizeof(double) + sizeof(uint32_t)))));
+  const int threads = P >= 2048 ? 1024 : (P >= 512 ? 256 : 64);
+  merge_shard_lists_p2p_kernel<<<nq, threads, smem, reinterpret_cast<cudaStream_t>(cuda_stream)>>>(
+      pl, n_shards, nq, cap, (unsigned long long)k_out, out_cap, d_out_idx, d_out_dist, d_out_count, P);
   GC_CUDA(cudaGetLastError());
   count_launch();
   return GC_OK;

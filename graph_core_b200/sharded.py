@@ -9,10 +9,17 @@ per-shard lists are exchanged with ONE all-gather, and every rank merges them on
 
 The exchange step is the only collective; bytes per rank = nq * cap * 12 + nq * 4.
 
+exchange="p2p": no collective at all -- every shard writes its lists into a buffer of torch symmetric memory
+(peer-mapped over NVLink) and gc_merge_shard_lists_p2p_dev loads the G lists of a query straight from the G
+GPUs inside the merge kernel; the only synchronisation is the symmetric-memory barrier (a few microseconds on
+the device) before the merge and before the buffers are reused.
+
 `engine` / `merge` are injectable so that the partition + gather + index logic can be exercised on CPU
 with the gloo backend (tests/test_sharded_cpu.py); the product path uses CudaShardEngine.
 """
 from __future__ import annotations
+
+import ctypes as C
 
 import numpy as np
 import torch
@@ -21,6 +28,33 @@ import torch.distributed as dist
 from . import capi
 
 NO_NODE = 0xFFFFFFFF
+
+
+class PeerBuffers:
+    """Result buffers of one shard in torch symmetric memory: idx [nq_max][cap_max] u32 | dist f64 | count u32,
+    peer-mapped on every rank of `group`."""
+
+    def __init__(self, group, device, nq_max: int, cap_max: int):
+        import torch.distributed._symmetric_memory as symm_mem
+        self.nq_max, self.cap_max = nq_max, cap_max
+        n = nq_max * cap_max
+        self.off_dist = (4 * n + 255) // 256 * 256
+        self.off_cnt = self.off_dist + 8 * n
+        nbytes = self.off_cnt + 4 * nq_max + 256
+        self.buf = symm_mem.empty(nbytes, dtype=torch.uint8, device=device)
+        g = group if group is not None else dist.group.WORLD
+        self.hdl = symm_mem.rendezvous(self.buf, g)
+        self.ptrs = [int(p) for p in self.hdl.buffer_ptrs]
+
+    def views(self, nq, cap):
+        assert nq <= self.nq_max and cap <= self.cap_max and nq * cap <= self.nq_max * self.cap_max
+        idx = self.buf[:4 * nq * cap].view(torch.int32).view(nq, cap)
+        dd = self.buf[self.off_dist:self.off_dist + 8 * nq * cap].view(torch.float64).view(nq, cap)
+        cnt = self.buf[self.off_cnt:self.off_cnt + 4 * nq].view(torch.int32)
+        return idx, dd, cnt
+
+    def barrier(self):
+        self.hdl.barrier(channel=0)
 
 
 class CudaShardEngine:
@@ -33,6 +67,28 @@ class CudaShardEngine:
         self.store = capi.NodeStore(dim, capacity, 1, device)
         self.lib = capi.load()
         self.store.set_stream(torch.cuda.current_stream(self.torch_device).cuda_stream)
+        self.peer = None  # PeerBuffers when the p2p exchange is enabled
+
+    def enable_p2p(self, group, nq_max: int, cap_max: int):
+        self.peer = PeerBuffers(group, self.torch_device, nq_max, cap_max)
+
+    def merge_p2p(self, nq, cap, k_out, out_cap):
+        """Merge the lists that every shard left in its PeerBuffers (same nq, cap everywhere)."""
+        pb = self.peer
+        G = len(pb.ptrs)
+        arr = C.c_void_p * G
+        idx_p = arr(*[C.c_void_p(p) for p in pb.ptrs])
+        dist_p = arr(*[C.c_void_p(p + pb.off_dist) for p in pb.ptrs])
+        cnt_p = arr(*[C.c_void_p(p + pb.off_cnt) for p in pb.ptrs])
+        oi = torch.full((nq, out_cap), -1, dtype=torch.int32, device=self.torch_device)
+        od = torch.full((nq, out_cap), float("inf"), dtype=torch.float64, device=self.torch_device)
+        oc = torch.zeros(nq, dtype=torch.int32, device=self.torch_device)
+        stream = torch.cuda.current_stream(self.torch_device).cuda_stream
+        pb.barrier()  # every shard's lists are complete
+        capi._check(self.lib.gc_merge_shard_lists_p2p_dev(self.device, stream, G, nq, cap, idx_p, dist_p, cnt_p, k_out,
+                                                          out_cap, oi.data_ptr(), od.data_ptr(), oc.data_ptr()))
+        pb.barrier()  # nobody overwrites its lists while a peer still reads them
+        return oi, od, oc
 
     def append(self, rows: np.ndarray):
         if len(rows):
@@ -42,6 +98,12 @@ class CudaShardEngine:
         return torch.from_numpy(np.ascontiguousarray(q, dtype=np.float64)).to(self.torch_device)
 
     def _out(self, nq, cap):
+        if self.peer is not None:
+            idx, dd, cnt = self.peer.views(nq, cap)
+            idx.fill_(-1)
+            dd.fill_(float("inf"))
+            cnt.zero_()
+            return idx, dd, cnt
         idx = torch.full((nq, cap), -1, dtype=torch.int32, device=self.torch_device)  # 0xFFFFFFFF = no node
         dd = torch.full((nq, cap), float("inf"), dtype=torch.float64, device=self.torch_device)
         cnt = torch.zeros(nq, dtype=torch.int32, device=self.torch_device)
@@ -87,8 +149,10 @@ class CudaShardEngine:
 class ShardedNodeStore:
     """Logical tree of N nodes sharded round-robin over the ranks of `group`."""
 
-    def __init__(self, dim: int, capacity_total: int, engine=None, group=None, device: int | None = None):
+    def __init__(self, dim: int, capacity_total: int, engine=None, group=None, device: int | None = None,
+                 exchange: str = "nccl", nq_max: int = 4096, cap_max: int = 1024):
         self.group = group
+        self.exchange = exchange
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.dim = dim
@@ -98,6 +162,8 @@ class ShardedNodeStore:
                 device = torch.cuda.current_device()
             engine = CudaShardEngine(dim, (capacity_total + self.world - 1) // self.world + 1, device)
         self.engine = engine
+        if exchange == "p2p" and self.world > 1:
+            engine.enable_p2p(group, nq_max, cap_max)
 
     # ---- partition -------------------------------------------------------------------------------
     def owner_of(self, global_slot):
@@ -123,6 +189,8 @@ class ShardedNodeStore:
 
     def _exchange(self, lists, k_out, out_cap):
         idx, dd, cnt = lists
+        if self.exchange == "p2p" and self.world > 1:
+            return self.engine.merge_p2p(idx.shape[0], idx.shape[1], k_out, out_cap)
         return self.engine.merge(self._gather(idx), self._gather(dd), self._gather(cnt), k_out, out_cap)
 
     def nearest(self, q):

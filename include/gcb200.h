@@ -109,6 +109,15 @@ int gc_merge_shard_lists_dev(int device, void* cuda_stream, uint32_t n_shards, u
                              const uint32_t* d_idx, const double* d_dist, const uint32_t* d_count, uint64_t k_out,
                              uint32_t out_cap, uint32_t* d_out_idx, double* d_out_dist, uint32_t* d_out_count);
 
+/* The same merge with the exchange fused in: entry g of the three host arrays is a DEVICE pointer to shard g's own
+ * result buffers ([nq][cap], [nq][cap], [nq]), peer-mapped into this process (CUDA IPC / VMM, e.g. torch symmetric
+ * memory): the kernel loads the lists over NVLink itself, there is no all-gather and no gathered copy.  The caller
+ * places one cross-GPU barrier between the producing kernels and this call, and one before the buffers are reused. */
+int gc_merge_shard_lists_p2p_dev(int device, void* cuda_stream, uint32_t n_shards, uint32_t nq, uint32_t cap,
+                                 const void* const* d_idx_of_shard, const void* const* d_dist_of_shard,
+                                 const void* const* d_count_of_shard, uint64_t k_out, uint32_t out_cap,
+                                 uint32_t* d_out_idx, double* d_out_dist, uint32_t* d_out_count);
+
 /* ---- collision worlds (check(q) of collision_checker_base.h:166) --------------------------- */
 int gc_world_create_cube(int dim, double threshold, int device, gc_world_t** out);
 int gc_world_create_boxes(int dim, uint32_t n, const double* lo, const double* hi, int device, gc_world_t** out);

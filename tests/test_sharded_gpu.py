@@ -103,3 +103,37 @@ def test_sharded_store_world_size_one(gc, orc):
     gi, gd = st.nearest(qs)
     ri, rd = ov.nearest(qs)
     assert np.array_equal(gi.cpu().numpy(), ri) and np.array_equal(gd.cpu().numpy(), rd)
+
+
+@pytest.mark.parametrize("G", [2, 8])
+def test_sharded_merge_p2p_kernel_emulated_shards(gc, orc, G):
+    """gc_merge_shard_lists_p2p_dev reads every shard's lists through its own pointer (peer memory on a multi-GPU
+    box; here G stores of one process) and must equal the gathered merge."""
+    import ctypes as C
+    from graph_core_b200.sharded import CudaShardEngine
+    from graph_core_b200 import capi
+    dim, n, k = 12, 20011, 21
+    pts = W.c4_nodes(n, dim, seed=195)
+    qs = W.c4_queries(9, dim, seed=196)
+    engines = []
+    for g in range(G):
+        e = CudaShardEngine(dim, n // G + 2, 0)
+        e.append(pts[g::G])
+        engines.append(e)
+    lists = [e.knn_lists(qs, k) for e in engines]
+    torch.cuda.synchronize()
+    arr = C.c_void_p * G
+    ip = arr(*[C.c_void_p(l[0].data_ptr()) for l in lists])
+    dp = arr(*[C.c_void_p(l[1].data_ptr()) for l in lists])
+    cp = arr(*[C.c_void_p(l[2].data_ptr()) for l in lists])
+    nq = len(qs)
+    oi = torch.full((nq, k), -1, dtype=torch.int32, device="cuda")
+    od = torch.full((nq, k), float("inf"), dtype=torch.float64, device="cuda")
+    oc = torch.zeros(nq, dtype=torch.int32, device="cuda")
+    capi._check(capi.load().gc_merge_shard_lists_p2p_dev(0, torch.cuda.current_stream().cuda_stream, G, nq, k, ip, dp, cp,
+                                                         k, k, oi.data_ptr(), od.data_ptr(), oc.data_ptr()))
+    torch.cuda.synchronize()
+    ov = orc.OracleNN("vector", dim)
+    ov.insert(pts)
+    ri, rd, rc = ov.knn(qs, k, k)
+    assert np.array_equal(oi.cpu().numpy(), ri) and np.array_equal(od.cpu().numpy(), rd) and np.array_equal(oc.cpu().numpy(), rc)

@@ -31,6 +31,8 @@ def main():
     ap.add_argument("--queries", type=int, default=4096)
     ap.add_argument("--reps", type=int, default=5)
     ap.add_argument("--check", action="store_true")
+    ap.add_argument("--exchange", default="nccl", choices=["nccl", "p2p"],
+                    help="nccl: all-gather + merge; p2p: the merge kernel loads the shard lists over NVLink itself")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", 0))
     local = int(os.environ.get("LOCAL_RANK", 0))
@@ -43,7 +45,7 @@ def main():
 
     pts = W.c4_nodes(args.nodes, args.dim)
     qs = W.c4_queries(args.queries, args.dim)
-    st = ShardedNodeStore(args.dim, args.nodes, device=local)
+    st = ShardedNodeStore(args.dim, args.nodes, device=local, exchange=args.exchange, nq_max=args.queries, cap_max=1024)
     st.append(pts)
     torch.cuda.synchronize()
 
@@ -71,6 +73,11 @@ def main():
     results = []
     ms, (ni, nd) = timed(lambda: st.nearest(qs))
     results.append({"op": "nearest", "k": 1, "ms": ms, "queries_per_s": args.queries / (ms * 1e-3)})
+    # latency regime: a handful of queries, where the exchange step is a visible share of the call
+    for nq_small in (1, 16):
+        ms, _ = timed(lambda: st.knn(qs[:nq_small], 16))
+        results.append({"op": "knn_small_batch", "k": 16, "batch": nq_small, "ms": ms,
+                        "queries_per_s": nq_small / (ms * 1e-3)})
     knn_out = {}
     for k in (16, 64, 256, 1024):
         ms, out = timed(lambda: st.knn(qs, k))
@@ -98,7 +105,7 @@ def main():
                 ok = ok and np.array_equal(oi[:m].cpu().numpy(), ki) and np.array_equal(od[:m].cpu().numpy(), kd)
             check = bool(ok)
         for r in results:
-            r.update({"n_gpus": world, "nodes": args.nodes, "dim": args.dim, "queries": args.queries,
+            r.update({"exchange": args.exchange if world > 1 else "none", "n_gpus": world, "nodes": args.nodes, "dim": args.dim, "queries": args.queries,
                       "oracle_check": check})
             print(json.dumps(r))
     if world > 1:
