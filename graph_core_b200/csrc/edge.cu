@@ -1483,6 +1483,11 @@ int gc_world_enable_timing(gc_world_t* w, int on)
   return GC_OK;
 }
 
+// state batches that fit in this many bytes take the zero-copy latency path of gc_check_states: the kernel reads the
+// configurations from, and stores the verdicts to, the pinned staging buffers (edge checks do not: their kernels
+// re-read the end points per state and update the verdict with atomics, which belongs in device memory)
+static constexpr size_t kZeroCopyBytes = 4096;
+
 int gc_check_states_dev(gc_world_t* w, const double* d_q, uint32_t n, uint8_t* d_ok)
 {
   GC_REQUIRE(w && d_q && d_ok, "gc_check_states_dev: NULL argument");
@@ -1514,6 +1519,13 @@ int gc_check_states(gc_world_t* w, const double* q, uint32_t n, uint8_t* ok)
   GC_TRY(w->d_ok.reserve(n));
   GC_CUDA(cudaStreamSynchronize(w->stream));
   memcpy(w->h_in.p, q, qb);
+  if (qb <= kZeroCopyBytes)
+  {
+    GC_TRY(check_states_dev(w, static_cast<const double*>(w->h_in.p), n, static_cast<uint8_t*>(w->h_out.p), w->stream));
+    GC_CUDA(cudaStreamSynchronize(w->stream));
+    memcpy(ok, w->h_out.p, n);
+    return GC_OK;
+  }
   GC_CUDA(cudaMemcpyAsync(w->d_c1.p, w->h_in.p, qb, cudaMemcpyHostToDevice, w->stream));
   GC_TRY(check_states_dev(w, w->d_c1.as<double>(), n, w->d_ok.as<uint8_t>(), w->stream));
   GC_CUDA(cudaMemcpyAsync(w->h_out.p, w->d_ok.p, n, cudaMemcpyDeviceToHost, w->stream));
@@ -1568,14 +1580,14 @@ static int check_edges_host(gc_world* w, const double* c1, const double* c2, con
   if (w->kind == GC_WORLD_SPHERE_ARM)
     for (uint32_t i = 0; i < n; i++)
       hint += host_states((c3 ? c3 : c1) + (size_t)i * w->dim, c2 + (size_t)i * w->dim, w->dim, min_distance, mode);
+  char* ho = static_cast<char*>(w->h_out.p);
+  const size_t ok_bytes = align_up(n, 16);
   GC_CUDA(cudaMemcpyAsync(w->d_c1.p, h, qb, cudaMemcpyHostToDevice, w->stream));
   GC_CUDA(cudaMemcpyAsync(w->d_c2.p, h + qb, qb, cudaMemcpyHostToDevice, w->stream));
   if (c3)
     GC_CUDA(cudaMemcpyAsync(w->d_c3.p, h + 2 * qb, qb, cudaMemcpyHostToDevice, w->stream));
   GC_TRY(check_edges_dev(w, w->d_c1.as<double>(), w->d_c2.as<double>(), c3 ? w->d_c3.as<double>() : nullptr, n,
                          min_distance, mode, w->d_ok.as<uint8_t>(), w->d_first.as<int64_t>(), hint, w->stream));
-  char* ho = static_cast<char*>(w->h_out.p);
-  const size_t ok_bytes = align_up(n, 16);
   GC_CUDA(cudaMemcpyAsync(ho, w->d_ok.p, n, cudaMemcpyDeviceToHost, w->stream));
   if (first_bad)
     GC_CUDA(cudaMemcpyAsync(ho + ok_bytes, w->d_first.p, sizeof(int64_t) * (size_t)n, cudaMemcpyDeviceToHost,

@@ -52,7 +52,7 @@ def build(verbose=False):
     OUT.mkdir(exist_ok=True)
     stamp = newest_input()
     cxx = os.environ.get("CXX", "g++")
-    inc = ["-I", str(HERE / "ref_shim"), "-I", str(REF / "include")]
+    inc = ["-I", str(HERE / "ref_shim"), "-I", str(REF / "include"), "-include", str(HERE / "ref_shim" / "shim_random.hpp")]
     for lib, flags in VARIANTS.items():
         target = OUT / lib
         if target.exists() and target.stat().st_mtime >= stamp:
@@ -101,7 +101,7 @@ def build_dropin(verbose=False):
     cxx = os.environ.get("CXX", "g++")
     flags = VARIANTS["libgc_ref.so"]
     inc = ["-I", str(HERE / "ref_shim"), "-I", str(REF / "include"), "-I", str(root / "include"), "-I", str(pkg / "host"),
-           "-I", str(HERE)]
+           "-I", str(HERE), "-include", str(HERE / "ref_shim" / "shim_random.hpp")]
     objdir = OUT / "obj_libgc_ref"
     objs = [o for o in objdir.glob("*.o") if o.name != "ref_driver.o"]  # ref_dropin.cpp includes ref_driver.cpp
     extra = []

@@ -462,8 +462,13 @@ int ref_tree_recheck(void* h)
   return (t && t->recheckCollision()) ? 1 : 0;
 }
 
-// ---- samplers: the reference's own sampling code with the shim's std::rand stream --------------------
-void ref_srand(unsigned int seed) { std::srand(seed); }
+// ---- samplers: the reference's own sampling code on the shim's seedable stream ------------------------
+// seeds the one random stream the reference draws from in this library (oracle/ref_shim/shim_random.hpp)
+void ref_srand(unsigned int seed)
+{
+  std::srand(seed);
+  gc_shim_rng::seed(seed);
+}
 void ref_sample_informed(int dim, const double* lb, const double* ub, const double* f1, const double* f2, double cost,
                          int n, double* out)
 {

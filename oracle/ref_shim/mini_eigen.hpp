@@ -19,6 +19,8 @@
 #include <ostream>
 #include <vector>
 
+#include "shim_random.hpp"
+
 #define EIGEN_MAKE_ALIGNED_OPERATOR_NEW
 #define EIGEN_WORLD_VERSION 0
 #define MINI_EIGEN_STANDIN 1
@@ -87,8 +89,10 @@ public:
     return o;
   }
 
-  // std::rand based, uniform in [-1, 1] like Eigen's default scalar random for double
-  static double randomScalar() { return 2.0 * (double)std::rand() / (double)RAND_MAX - 1.0; }
+  // uniform in [-1, 1] like Eigen's default scalar random for double.  Real Eigen draws from std::rand(); the
+  // stand-in draws from a private generator (shim_random.hpp) so that a seeded run is reproducible whatever other
+  // threads of the process (CUDA driver, BLAS pools ...) do with the C library's global stream
+  static double randomScalar() { return 2.0 * (double)(gc_shim_rng::next() >> 11) * (1.0 / 9007199254740992.0) - 1.0; }
   static MatrixXd Random(Index r, Index c)
   {
     MatrixXd o(r, c);

@@ -75,22 +75,16 @@ def test_birrt_with_cuda_checker_c2(gc, orc, ref):
 
 @pytest.mark.parametrize("name", ["C1", "C3"])
 def test_anytime_rrt_with_cuda_checker(gc, orc, ref, c3, name):
-    """BASELINE config 5's solver: AnytimeRRT::solve with its own (std::rand) informed sampler, same seed on both sides."""
+    """BASELINE config 5's solver: AnytimeRRT::solve with its own informed sampler, same seed on both sides."""
     sc = W.scenario_c1() if name == "C1" else c3
     iters = 1500 if name == "C1" else 400
-    L = ref.lib()  # std::rand is process-global: seeding through either library seeds both solvers
-    L.ref_srand(12345)
+    # every draw of the reference (Eigen Random, the random_device behind each sampler's mt19937) comes from one
+    # seedable stream per library (oracle/ref_shim/shim_random.hpp): same seed, same samples on both sides
+    ref.lib().ref_srand(12345)
     cpu = ref.RefSolver(ref.RefSolver.ANYTIME, sc, _cpu_checker(ref, orc, sc), informed=True)
     ok_cpu = cpu.solve(iters, 1.0e9)
-    # the CUDA side is fully warmed up BEFORE seeding: lazy kernel loading inside the driver may draw from rand()
-    gw = sc.make_world()
-    q = W.uniform_samples(sc.lb, sc.ub, 5, 0, 4)
-    gw.check(q)
-    gw.check_connection(q[:2], q[2:], sc.min_distance)
-    gw.check_connection(q[:2], q[2:], sc.min_distance, mode=1)
-    gw.check_conn_from_conf(q[:2], q[2:], q[:2], sc.min_distance)
-    L.ref_srand(12345)
-    gpu = ref.DropinSolver(ref.RefSolver.ANYTIME, sc, gw, informed=True, cuda_nn=False)
+    ref.lib(dropin=True).ref_srand(12345)
+    gpu = ref.DropinSolver(ref.RefSolver.ANYTIME, sc, sc.make_world(), informed=True, cuda_nn=False)
     ok_gpu = gpu.solve(iters, 1.0e9)
     assert ok_cpu == ok_gpu
     _same(ref, cpu, gpu)
