@@ -45,7 +45,7 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--problems", type=int, default=4096, help="independent planning problems per GPU")
+    ap.add_argument("--problems", type=int, default=8192, help="independent planning problems per GPU")
     ap.add_argument("--threads", type=int, default=0, help="host replay threads (0 = all cores)")
     ap.add_argument("--instances", type=int, default=4,
                     help="lock-step planner instances per GPU, each with problems/instances problems, its own stream and "
