@@ -98,6 +98,9 @@ struct ScanArgs
   uint32_t* gmin;          // streaming scan MODE 0: [nq] shared running fp32 minima (order-preserving keys)
   uint32_t* ctl;           // streaming scan: [groups][2] tile hand-out and finished-CTA counters (self-resetting)
   float* out_c2;           // streaming scan MODE 2: candidates keep their fp32 pre-selection value (no fp64 here)
+  uint32_t tile_begin;     // streaming scan: first tile and number of tiles of this launch (0, 0 = the whole store)
+  uint32_t tile_count;
+  int thr_raw;             // MODE 2: thr2 already is the final expanded-form threshold (second collecting phase)
   // MODE 0 outputs: partials [chunks][nq]
   double* part_d;
   uint32_t* part_i;
@@ -433,16 +436,19 @@ __global__ void __launch_bounds__(kStThreads, 3) scan_stream_kernel(ScanArgs a)
   const int gq = (int)min(a.group_size, a.nq - q0);
   const int gqp = (gq + kStQPT - 1) / kStQPT * kStQPT;  // padded with inert queries up to a whole trip
   const uint32_t n_s = a.used[0];
-  const uint32_t ntiles = (n_s + kStTile - 1) / kStTile;
+  const uint32_t all_tiles = (n_s + kStTile - 1) / kStTile;
+  const uint32_t tile0 = min(a.tile_begin, all_tiles);
+  const uint32_t ntiles = a.tile_count ? min(a.tile_count, all_tiles - tile0) : all_tiles - tile0;  // of this launch
   uint32_t* tile_ctr = a.ctl + 2 * blockIdx.y;
   uint32_t* done_ctr = tile_ctr + 1;
   volatile uint32_t* tile_of = m.cnt + 2;
 
   // take the next tile of this group and put its D rows in flight (thread 0 only)
   auto fetch = [&](int stage) {
-    const uint32_t t = atomicAdd(tile_ctr, 1u);
-    if (t < ntiles)
+    const uint32_t k = atomicAdd(tile_ctr, 1u);
+    if (k < ntiles)
     {
+      const uint32_t t = tile0 + k;
       tile_of[stage] = t;
       mbar_expect_tx(&m.bars[stage], (uint32_t)(D * kStTile * sizeof(float)));
 #pragma unroll
@@ -504,7 +510,7 @@ __global__ void __launch_bounds__(kStThreads, 3) scan_stream_kernel(ScanArgs a)
       }
     }
     if (MODE == 2 && tid < gq)
-      thr = a.thr2[q0 + tid] * (1.0f + 8.0e-6f) + e2 * (1.0f + 1.0e-6f);
+      thr = a.thr_raw ? a.thr2[q0 + tid] : a.thr2[q0 + tid] * (1.0f + 8.0e-6f) + e2 * (1.0f + 1.0e-6f);
     if (tid >= gq)  // inert query: |q|^2 = +inf makes every value +inf, which never passes "< +inf"
     {
       qn = CUDART_INF_F;
@@ -1393,6 +1399,43 @@ __global__ void __launch_bounds__(1024, 1)
     out_count[q] = want;
 }
 
+// Second-phase threshold of the large-N k-nearest: after the candidates of the first N/16 nodes have been collected
+// under the (loose) sample threshold, the k-th smallest of THEIR fp32 values bounds the true k-th distance much more
+// tightly -- it is the k-th of a 16 times larger sample -- and the remaining 15/16 of the store is scanned under
+// stream_thr() of it.  Fewer than k candidates so far: the old threshold stays.
+template <int D>
+__global__ void __launch_bounds__(1024, 1)
+    knn_rethreshold_kernel(const float* __restrict__ c2, const uint32_t* __restrict__ count, uint32_t cap,
+                           const double* __restrict__ qd, unsigned long long k, float xn_max, float slack_abs,
+                           float* __restrict__ thr_io)
+{
+  __shared__ uint32_t hist[256];
+  __shared__ unsigned long long sh[2];
+  const uint32_t q = blockIdx.x;
+  const uint32_t n = min(count[q], cap);
+  const float* lc = c2 + (size_t)q * cap;
+  float qn = 0.0f;
+#pragma unroll
+  for (int d = 0; d < D; d++)
+  {
+    const float v = (float)qd[(size_t)q * D + d];
+    qn = fmaf(v, v, qn);
+  }
+  const float e2 = (float)(3 * D + 8) * 5.9604645e-8f * 1.5f * (xn_max + qn) * 2.0f + FLT_MIN;
+  // the first phase ran under the sample threshold in its expanded-form version
+  float thr = thr_io[q] * (1.0f + 8.0e-6f) + e2 * (1.0f + 1.0e-6f);
+  if (k >= 1 && k <= (unsigned long long)n && count[q] <= cap)
+  {
+    unsigned long long rest = 0;
+    const unsigned long long kk = radix_select(
+        n, k, 4, [&](uint32_t i) { return (unsigned long long)fkey(lc[i]); }, [&](uint32_t) { return true; }, hist, sh,
+        &rest);
+    thr = fminf(thr, stream_thr(funkey((uint32_t)kk), e2, slack_abs));
+  }
+  if (threadIdx.x == 0)
+    thr_io[q] = thr;
+}
+
 // Node-sharded trees: node i lives on shard i mod G at local slot i div G.  After the
 // all-gather of the per-shard lists this merges them: global slot = local * G + g, ascending (dist, slot),
 // first k_out entries.  parts are [G][nq][cap] / [G][nq].
@@ -1820,6 +1863,23 @@ static int knn_large_dev(gc_store* s, const double* d_q, const uint32_t* d_seg, 
     if (f32_path)
     {
       a.out_c2 = reinterpret_cast<float*>(s->d_cand_dist.p);
+      // phase 1: the first 1/16 of the tiles under the sample threshold; re-threshold; phase 2: the rest
+      const uint32_t all_tiles = (s->used[0] + kStTile - 1) / kStTile;
+      const uint32_t first = std::max<uint32_t>(1u, all_tiles / 16u);
+      if (first < all_tiles)
+      {
+        a.tile_begin = 0;
+        a.tile_count = first;
+        GC_TRY(launch_stream<2>(s, a, nqc));
+        GC_DISPATCH_DIM(s->dim, (knn_rethreshold_kernel<DD><<<nqc, 1024, 0, s->stream>>>(
+                                    a.out_c2, a.out_count, capB, a.q, (unsigned long long)k, xn_max, slack,
+                                    s->d_thr.as<float>() + q0)));
+        GC_CUDA(cudaGetLastError());
+        count_launch();
+        a.tile_begin = first;
+        a.tile_count = all_tiles - first;
+        a.thr_raw = 1;
+      }
       GC_TRY(launch_stream<2>(s, a, nqc));
       GC_DISPATCH_DIM(s->dim, (select_topk_f32_kernel<DD><<<nqc, 1024, smem_sel32, s->stream>>>(
                                   a.out_idx, a.out_c2, a.out_count, capB, s->x64, a.q, (unsigned long long)k, xn_max,
