@@ -685,6 +685,10 @@ struct PlanArgs
   uint8_t* ok;         // initialised here: 1, or 255 when the reference would throw
   unsigned long long* first_bad;
   uint32_t* work_ctr;  // zeroed here for the check kernel that follows
+  // latency path: c1/c2/c3 point at pinned HOST memory; the plan kernel leaves device copies here for the check kernel
+  double* copy_c1;
+  double* copy_c2;
+  double* copy_c3;
 };
 
 template <int D, int MODE>
@@ -714,6 +718,17 @@ __global__ void __launch_bounds__(1024) edge_plan_kernel(PlanArgs a)
         c1[d] = a.c1[(size_t)e * D + d];
         c2[d] = a.c2[(size_t)e * D + d];
         c3[d] = (MODE == GC_EDGE_FROM_CONF) ? a.c3[(size_t)e * D + d] : 0.0;
+      }
+      if (a.copy_c1)
+      {
+#pragma unroll
+        for (int d = 0; d < D; d++)
+        {
+          a.copy_c1[(size_t)e * D + d] = c1[d];
+          a.copy_c2[(size_t)e * D + d] = c2[d];
+          if (MODE == GC_EDGE_FROM_CONF)
+            a.copy_c3[(size_t)e * D + d] = c3[d];
+        }
       }
       const EdgeGeom g = edge_geom<D, MODE>(c1, c2, c3, a.min_d);
       a.dist[e] = g.dist;
@@ -1199,6 +1214,16 @@ int check_edges_dev(gc_world* w, const double* d_c1, const double* d_c2, const d
     a.c1 = d_c1;
     a.c2 = d_c2;
     a.c3 = d_c3;
+    if (w->inputs_in_host_memory)
+    {
+      // the plan kernel reads the end points from the caller's pinned buffer and leaves device copies
+      p.copy_c1 = w->d_c1.as<double>();
+      p.copy_c2 = w->d_c2.as<double>();
+      p.copy_c3 = d_c3 ? w->d_c3.as<double>() : nullptr;
+      a.c1 = p.copy_c1;
+      a.c2 = p.copy_c2;
+      a.c3 = p.copy_c3;
+    }
     a.n = n;
     a.dist = p.dist;
     a.aux = p.aux;
@@ -1483,9 +1508,10 @@ int gc_world_enable_timing(gc_world_t* w, int on)
   return GC_OK;
 }
 
-// state batches that fit in this many bytes take the zero-copy latency path of gc_check_states: the kernel reads the
-// configurations from, and stores the verdicts to, the pinned staging buffers (edge checks do not: their kernels
-// re-read the end points per state and update the verdict with atomics, which belongs in device memory)
+// batches that fit in this many bytes take the latency path of the host entry points: gc_check_states reads the
+// configurations from, and stores the verdicts to, the pinned staging buffers; gc_check_edges lets the plan kernel
+// pull the end points from the pinned buffer into device memory (the check kernel re-reads them per state and updates
+// the verdict with atomics, which belongs in device memory) and fetches first_bad + ok in one copy
 static constexpr size_t kZeroCopyBytes = 4096;
 
 int gc_check_states_dev(gc_world_t* w, const double* d_q, uint32_t n, uint8_t* d_ok)
@@ -1582,6 +1608,30 @@ static int check_edges_host(gc_world* w, const double* c1, const double* c2, con
       hint += host_states((c3 ? c3 : c1) + (size_t)i * w->dim, c2 + (size_t)i * w->dim, w->dim, min_distance, mode);
   char* ho = static_cast<char*>(w->h_out.p);
   const size_t ok_bytes = align_up(n, 16);
+  if (w->kind == GC_WORLD_SPHERE_ARM && qb * narr <= kZeroCopyBytes)
+  {
+    // latency path (a planner asking for one edge at a time through the plugin): the plan kernel reads the end
+    // points straight from the pinned staging buffer (unified addressing) and the verdicts come back in ONE copy
+    // (first_bad and ok share a device buffer): three copy calls fewer per query
+    GC_TRY(w->d_first.reserve(ok_bytes + sizeof(int64_t) * (size_t)n));
+    int64_t* d_fb = w->d_first.as<int64_t>();
+    uint8_t* d_okz = reinterpret_cast<uint8_t*>(d_fb + n);
+    w->inputs_in_host_memory = true;
+    const int rc = check_edges_dev(w, reinterpret_cast<const double*>(h), reinterpret_cast<const double*>(h + qb),
+                                   c3 ? reinterpret_cast<const double*>(h + 2 * qb) : nullptr, n, min_distance, mode, d_okz,
+                                   d_fb, hint, w->stream);
+    w->inputs_in_host_memory = false;
+    GC_TRY(rc);
+    const size_t out_bytes = sizeof(int64_t) * (size_t)n + n;
+    GC_TRY(w->h_out.reserve(out_bytes + 16));
+    ho = static_cast<char*>(w->h_out.p);
+    GC_CUDA(cudaMemcpyAsync(ho, d_fb, out_bytes, cudaMemcpyDeviceToHost, w->stream));
+    GC_CUDA(cudaStreamSynchronize(w->stream));
+    memcpy(ok, ho + sizeof(int64_t) * (size_t)n, n);
+    if (first_bad)
+      memcpy(first_bad, ho, sizeof(int64_t) * (size_t)n);
+    return GC_OK;
+  }
   GC_CUDA(cudaMemcpyAsync(w->d_c1.p, h, qb, cudaMemcpyHostToDevice, w->stream));
   GC_CUDA(cudaMemcpyAsync(w->d_c2.p, h + qb, qb, cudaMemcpyHostToDevice, w->stream));
   if (c3)

@@ -147,6 +147,7 @@ struct gc_world
   unsigned long long* d_counters = nullptr;
   uint64_t launches = 0;
   bool timing = false;
+  bool inputs_in_host_memory = false;  // set by the host latency path around check_edges_dev (see edge.cu)
   uint64_t kernel_ns = 0;
   std::vector<cudaEvent_t> ev_pool;  // (begin, end) pairs recorded around the check kernels
   size_t ev_used = 0;
