@@ -6,6 +6,7 @@ Layout
   host/      C++ host mirror of the reference interfaces (plugin classes, lock-step planners)
   capi.py    ctypes binding used by tests, bench.py and Python callers
   worlds.py  the synthetic benchmark worlds of BASELINE.json (seeded, Philox)
+  tree_yaml.py  the reference's tree YAML format, written from / read into the SoA store
 """
 from . import capi  # noqa: F401
 from .capi import (CollisionWorld, GcError, NodeStore, device_count, device_info, extend_batch,  # noqa: F401

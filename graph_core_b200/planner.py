@@ -65,6 +65,7 @@ class LockstepRRTStar:
                  threads: int = 0):
         self.L = load_host()
         self.dim = scenario.dim
+        self.max_distance = float(scenario.max_distance)
         self.world = world  # keep alive
         starts = _f64(starts, (-1, self.dim))
         goals = _f64(goals, (-1, self.dim))
@@ -135,6 +136,17 @@ class LockstepRRTStar:
         conf = np.empty((n, self.dim), np.float64)
         self.L.gcp_rrtstar_dump(self.h, p, par.ctypes.data_as(_i32p), pc.ctypes.data_as(_dp), conf.ctypes.data_as(_dp))
         return par, pc, conf
+
+    def to_yaml(self, p: int = 0, use_kdtree: bool = True) -> str:
+        """The tree of problem p in the reference's on-disk format (`Tree::toYAML`, tree.cpp:1188-1227)."""
+        from .tree_yaml import tree_to_yaml
+        par, _, conf = self.dump(p)
+        # nodes are listed in slot (creation) order; a goal that is not connected yet (parent -1, not the root) is not
+        # part of the tree and is left out -- the reference inserts it only when it connects
+        keep = (par >= 0) | (np.arange(par.shape[0]) == 0)
+        new_id = np.cumsum(keep) - 1
+        par = np.where(par[keep] >= 0, new_id[np.maximum(par[keep], 0)], -1)
+        return tree_to_yaml(conf[keep], par, self.max_distance, use_kdtree)
 
     def solution(self, p: int = 0):
         ids = np.empty(1 << 16, np.int32)

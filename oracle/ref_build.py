@@ -39,6 +39,14 @@ VARIANTS = {
 }
 
 
+def host_compiler():
+    """The system g++ first: a $CXX wrapper that only finds libstdc++.a links the C++ runtime statically into the
+    library, and a second copy of the iostream/locale machinery inside a Python process (numpy and torch load the
+    shared one) crashes on the first formatted double (Tree::toYAML)."""
+    import shutil
+    return shutil.which("g++") or os.environ.get("CXX") or "g++"
+
+
 def newest_input():
     files = [HERE / "ref_driver.cpp", Path(__file__)] + list((HERE / "ref_shim").rglob("*")) + [REF / s for s in SOURCES]
     return max(f.stat().st_mtime for f in files if f.is_file())
@@ -51,7 +59,7 @@ def build(verbose=False):
         return False
     OUT.mkdir(exist_ok=True)
     stamp = newest_input()
-    cxx = os.environ.get("CXX", "g++")
+    cxx = host_compiler()
     inc = ["-I", str(HERE / "ref_shim"), "-I", str(REF / "include"), "-include", str(HERE / "ref_shim" / "shim_random.hpp")]
     for lib, flags in VARIANTS.items():
         target = OUT / lib
@@ -98,7 +106,7 @@ def build_dropin(verbose=False):
     if target.exists() and target.stat().st_mtime >= stamp:
         return True
     build(verbose)  # the reference objects
-    cxx = os.environ.get("CXX", "g++")
+    cxx = host_compiler()
     flags = VARIANTS["libgc_ref.so"]
     inc = ["-I", str(HERE / "ref_shim"), "-I", str(REF / "include"), "-I", str(root / "include"), "-I", str(pkg / "host"),
            "-I", str(HERE), "-include", str(HERE / "ref_shim" / "shim_random.hpp")]

@@ -462,6 +462,88 @@ int ref_tree_recheck(void* h)
   return (t && t->recheckCollision()) ? 1 : 0;
 }
 
+// ---- Tree YAML (tree.cpp:1188-1227 toYAML, :1272-1389 fromYAML): the document as arrays ---------------------
+// Tree::toYAML() of the start tree: nodes[n][dim] in document order, connections[m][2] = (parent index, child
+// index) in document order.  Returns n (or -1); *nconn = m.
+int ref_tree_to_yaml(void* h, int cap_nodes, double* conf, int cap_conn, int* conn, int* nconn, double* max_distance,
+                     int* use_kdtree)
+{
+  RefSolver* s = (RefSolver*)h;
+  TreePtr t = s->solver->getStartTree();
+  if (!t)
+    return -1;
+  YAML::Node y = t->toYAML();
+  YAML::Node nodes = y["nodes"], cs = y["connections"];
+  *max_distance = y["max_distance"].as<double>();
+  *use_kdtree = y["use_kdtree"].as<bool>() ? 1 : 0;
+  for (std::size_t i = 0; i < nodes.size() && (int)i < cap_nodes; i++)
+    for (int k = 0; k < s->dim; k++)
+      conf[i * s->dim + k] = nodes[i][k].as<double>();
+  const std::size_t m = cs.IsSequence() ? cs.size() : 0;
+  for (std::size_t i = 0; i < m && (int)i < cap_conn; i++)
+  {
+    conn[2 * i] = cs[i][0].as<int>();
+    conn[2 * i + 1] = cs[i][1].as<int>();
+  }
+  *nconn = (int)m;
+  return (int)nodes.size();
+}
+// Tree::fromYAML on a document given as arrays (max_distance NaN = field absent).  Dumps the loaded tree in
+// getNodes() order like ref_solver_dump; *max_distance_out = Tree::getMaximumDistance().  Returns the node count, -1
+// when the reference refuses the document.
+int ref_tree_from_yaml(int dim, int n, const double* conf, int m, const int* conn, double max_distance, int use_kdtree,
+                       int cap, double* out_conf, double* out_parent_conf, double* out_pcost, double* max_distance_out)
+{
+  YAML::Node y, nodes, cs;
+  for (int i = 0; i < n; i++)
+  {
+    YAML::Node q;
+    q.SetStyle(YAML::EmitterStyle::Flow);
+    for (int k = 0; k < dim; k++)
+      q.push_back(conf[(size_t)i * dim + k]);
+    nodes.push_back(q);
+  }
+  for (int i = 0; i < m; i++)
+  {
+    YAML::Node c;
+    c.SetStyle(YAML::EmitterStyle::Flow);
+    c.push_back(conn[2 * i]);
+    c.push_back(conn[2 * i + 1]);
+    cs.push_back(c);
+  }
+  if (max_distance == max_distance)
+    y["max_distance"] = max_distance;
+  y["use_kdtree"] = (use_kdtree != 0);
+  y["nodes"] = nodes;
+  y["connections"] = cs;
+  MetricsPtr metrics = std::make_shared<EuclideanMetrics>(g_logger);
+  CollisionCheckerPtr checker = std::make_shared<Cube3dCollisionChecker>(g_logger, 0.0, 0.01);
+  TreePtr t = Tree::fromYAML(y, metrics, checker, g_logger);
+  if (!t)
+    return -1;
+  *max_distance_out = t->getMaximumDistance();
+  std::vector<NodePtr> nv = t->getNodes();
+  for (int i = 0; i < (int)nv.size() && i < cap; i++)
+  {
+    for (int k = 0; k < dim; k++)
+      out_conf[(size_t)i * dim + k] = nv[i]->getConfiguration()(k);
+    if (nv[i]->getParentConnectionsSize() == 1)
+    {
+      ConnectionPtr c = nv[i]->parentConnection(0);
+      for (int k = 0; k < dim; k++)
+        out_parent_conf[(size_t)i * dim + k] = c->getParent()->getConfiguration()(k);
+      out_pcost[i] = c->getCost();
+    }
+    else
+    {
+      for (int k = 0; k < dim; k++)
+        out_parent_conf[(size_t)i * dim + k] = std::numeric_limits<double>::quiet_NaN();
+      out_pcost[i] = 0.0;
+    }
+  }
+  return (int)nv.size();
+}
+
 // ---- samplers: the reference's own sampling code on the shim's seedable stream ------------------------
 // seeds the one random stream the reference draws from in this library (oracle/ref_shim/shim_random.hpp)
 void ref_srand(unsigned int seed)

@@ -77,6 +77,10 @@ def lib(fast: bool = False, dropin: bool = False):
         "ref_solver_specific_volume": (C.c_double, [vp]),
         "ref_solver_tree_size": (C.c_int, [vp]),
         "ref_solver_dump": (C.c_int, [vp, C.c_int, _dp, _dp, _dp]),
+        "ref_tree_to_yaml": (C.c_int, [vp, C.c_int, _dp, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int),
+                                       C.POINTER(C.c_double), C.POINTER(C.c_int)]),
+        "ref_tree_from_yaml": (C.c_int, [C.c_int, C.c_int, _dp, C.c_int, C.POINTER(C.c_int), C.c_double, C.c_int,
+                                         C.c_int, _dp, _dp, _dp, C.POINTER(C.c_double)]),
         "ref_solver_solution": (C.c_int, [vp, C.c_int, _dp]),
         "ref_solver_path_cost": (C.c_double, [vp]),
         "ref_solution_is_valid": (C.c_int, [vp, vp, C.c_int, _dp]),
@@ -297,6 +301,17 @@ class RefSolver:
         self.L.ref_solver_dump(self.h, n, _p(conf, _dp), _p(par, _dp), _p(pc, _dp))
         return conf, par, pc
 
+    def tree_to_yaml(self):
+        """Tree::toYAML() of the start tree as arrays: nodes[n][dim], connections[m][2], max_distance, use_kdtree."""
+        n = self.tree_size + 8
+        conf = np.empty((n, self.dim))
+        conn = np.empty((n, 2), np.int32)
+        m, md, uk = C.c_int(0), C.c_double(0), C.c_int(0)
+        nn = self.L.ref_tree_to_yaml(self.h, n, _p(conf, _dp), n, conn.ctypes.data_as(C.POINTER(C.c_int)), C.byref(m),
+                                     C.byref(md), C.byref(uk))
+        assert 0 <= nn <= n and m.value <= n
+        return conf[:nn].copy(), conn[:m.value].astype(np.int64), md.value, bool(uk.value)
+
     def solution(self):
         wp = np.empty((1 << 14, self.dim))
         n = self.L.ref_solver_solution(self.h, wp.shape[0], _p(wp, _dp))
@@ -385,3 +400,22 @@ def oracle_tree_as_edges(parents, pcost, conf, in_tree=None):
         p = None if parents[i] < 0 else conf[parents[i]].tobytes()
         out[conf[i].tobytes()] = (p, float(pcost[i]) if parents[i] >= 0 else 0.0)
     return out
+
+
+def ref_tree_from_yaml(conf, connections, max_distance=None, use_kdtree=True, fast=False):
+    """Tree::fromYAML on a document given as arrays; returns (conf, parent_conf, pcost, max_distance) of the loaded
+    tree in getNodes() order, or None when the reference refuses the document."""
+    L = lib(fast)
+    conf = np.ascontiguousarray(conf, np.float64)
+    n, dim = conf.shape
+    conn = np.ascontiguousarray(connections, np.int32).reshape(-1, 2)
+    oc = np.empty((n + 8, dim))
+    op = np.empty((n + 8, dim))
+    pc = np.empty(n + 8)
+    md = C.c_double(0)
+    r = L.ref_tree_from_yaml(dim, n, _p(conf, _dp), conn.shape[0], conn.ctypes.data_as(C.POINTER(C.c_int)),
+                             float("nan") if max_distance is None else float(max_distance), int(use_kdtree), n + 8,
+                             _p(oc, _dp), _p(op, _dp), _p(pc, _dp), C.byref(md))
+    if r < 0:
+        return None
+    return oc[:r].copy(), op[:r].copy(), pc[:r].copy(), md.value

@@ -74,6 +74,9 @@ public:
   void push_back(const T& v) { push_back(Node(v)); }
   Node operator[](std::size_t i) const { return d_->seq.at(i); }
   Node operator[](int i) const { return d_->seq.at((std::size_t)i); }
+  // non-const twins: without them `node[0]` on a non-const Node is ambiguous with the const char* key overload
+  Node operator[](std::size_t i) { return d_->seq.at(i); }
+  Node operator[](int i) { return d_->seq.at((std::size_t)i); }
   Node operator[](const std::string& k) const
   {
     for (auto& kv : d_->map)
@@ -90,7 +93,10 @@ public:
       if (kv.first == k)
         return kv.second;
     d_->kind = Data::Map;
-    d_->map.emplace_back(k, Node());
+    d_->defined = true;
+    Node fresh;
+    fresh.d_->defined = false;  // materialised by the assignment that follows (see operator=)
+    d_->map.emplace_back(k, fresh);
     return d_->map.back().second;
   }
   Node operator[](const char* k) { return (*this)[std::string(k)]; }
