@@ -11,8 +11,9 @@ checks + append (RRTStar::update, src/graph_core/solvers/rrt_star.cpp:89-163).
   e2e    : samples/s through the host-facing call with HOST sample buffers (H2D of every step's samples,
            D2H of every step's results inside the timed region)
   roofline: the dominant kernel of the step, the arm edge-check kernel (FP32 pipe bound): executed
-           sphere-pair tests x 10 flop / device time of the check kernels (CUDA events on the launching
-           stream, inside the timed region) against the FFMA peak measured in the same run
+           sphere-pair tests x 10 flop + evaluated states x 1 kflop FK / device time of the check
+           kernels (CUDA events on the launching stream, inside the timed region) against the FFMA peak measured in
+           the same run; the executed-instruction view (9 flop per pair) is reported next to it
   cpu_baseline / --impl reference: the CPU restatement of the reference (oracle, the reference's
            -Ofast flags) running the same problems and sample streams on the host cores.
 
@@ -36,7 +37,16 @@ sys.path.insert(0, str(ROOT))
 
 METRIC = "rrtstar_samples_per_sec"
 UNIT = "samples/s"
-FLOP_PER_PAIR = 9.0  # include/gcb200_spec.h: 4 fused multiply-adds (8 flop) + 1 compare per sphere pair
+# ALGORITHMIC work of the C3 state check as SURVEY.md 8(d) counts it: 10 flop per sphere pair (3 sub, 1 mul + 2 fma,
+# radius add, square, compare) and ~1.0 kflop of forward kinematics per state.  The kernel EXECUTES less per pair
+# (expanded form, include/gcb200_spec.h: 4 fused multiply-adds + 1 compare = 9 flop); both views are reported.
+FLOP_PER_PAIR = 10.0
+FLOP_FK_PER_STATE = 1000.0
+EXECUTED_FLOP_PER_PAIR = 9.0
+
+
+def edge_flops(wc):
+    return FLOP_PER_PAIR * wc["pair_tests"] + FLOP_FK_PER_STATE * wc["states"]
 
 
 def parse_args():
@@ -383,7 +393,7 @@ def main():
                               "value": val_run["consumed"] / (val_run["ms"] * 1e-3),
                               "host_us_per_step": {k[3:]: round(vs[k] / K / 1e3, 1) for k in vs if k.startswith("ns_")},
                               "edge_kernel_us_per_step": round(wc["kernel_ns"] / K / 1e3, 1),
-                              "edge_tflops": round(FLOP_PER_PAIR * wc["pair_tests"] / max(wc["kernel_ns"], 1) / 1e3, 2),
+                              "edge_tflops": round(edge_flops(wc) / max(wc["kernel_ns"], 1) / 1e3, 2),
                               "edges_per_step": vs["edges_device"] / K, "extended_per_step": vs["extended"] / K}))
         return 0
     e2e_run = timed_run(device_samples=False, instances=args.instances)
@@ -420,7 +430,8 @@ def main():
                    "h2d_bytes_per_step": int(st.get("h2d_bytes", 0) / K), "d2h_bytes_per_step": int(st.get("d2h_bytes", 0) / K),
                    "ms_per_step": e2e_run["ms"] / K, "same_trees_as_value_run": bool(same)}
     wc = roof_run["world"]
-    achieved = FLOP_PER_PAIR * wc["pair_tests"] / max(wc["kernel_ns"], 1) / 1e3  # TFLOP/s
+    achieved = edge_flops(wc) / max(wc["kernel_ns"], 1) / 1e3  # TFLOP/s
+    executed = EXECUTED_FLOP_PER_PAIR * wc["pair_tests"] / max(wc["kernel_ns"], 1) / 1e3
     traffic = {}
     try:
         traffic = json.loads((ROOT / "profiles" / "r01_ncu_traffic.json").read_text())
@@ -432,7 +443,12 @@ def main():
         "traffic": traffic.get("arm_state_kernel", {}).get("dram_bytes_per_launch"),
         "traffic_source": traffic.get("arm_state_kernel", {}).get("capture"),
         "peak_source": "FFMA micro-benchmark in this run (implies %.0f MHz); MEASURED_PEAKS.json has no FP32 entry" % fp32_mhz,
+        "accounting": "SURVEY 8(d): %g flop per executed sphere-pair test + %g flop FK per evaluated state (counted by "
+                      "the kernel, so early exits do not inflate it)" % (FLOP_PER_PAIR, FLOP_FK_PER_STATE),
+        "executed_pair_flops": {"flop_per_pair": EXECUTED_FLOP_PER_PAIR, "achieved": executed,
+                                "frac": executed / fp32_peak if fp32_peak > 0 else None},
         "pair_tests_per_launch": wc["pair_tests"] / max(wc["launches"], 1),
+        "states_per_launch": wc["states"] / max(wc["launches"], 1),
         "us_per_launch": wc["kernel_ns"] / max(wc["launches"], 1) / 1e3,
         "kernel_share_of_step": wc["kernel_ns"] / 1e6 / roof_run["ms"],
         "measured_in": "timed run of the same %d steps with 1 planner instance (%.3f ms/step); the headline runs use %d "

@@ -1,6 +1,7 @@
 // lockstep.cpp -- see lockstep.h.  Host C++ above the C ABI; all hot-path work happens in libgcb200.so.
 #include "lockstep.h"
 
+#include <cstdlib>
 #include <algorithm>
 #include <atomic>
 #include <chrono>
@@ -124,6 +125,8 @@ LockstepRRTStar::LockstepRRTStar(const SolverConfig& cfg, gc_world_t* world, int
                                  const double* starts, const double* goals, uint32_t capacity_per_tree, int threads)
   : cfg_(cfg), D_(cfg.dim), world_(world)
 {
+  if (const char* fb = std::getenv("GCB200_FIRST_BATCH"))
+    first_batch_ = (size_t)std::max(1, std::atoi(fb));
   // TreeSolver::config (tree_solver.cpp:40-47)
   utopia_tol_ = cfg.utopia_tolerance;
   if (utopia_tol_ <= 0.0)
@@ -454,13 +457,16 @@ int LockstepRRTStar::stepImpl(const double* samples, const double* d_samples)
     pr.tree_size++;
     pr.new_node = id;
     pr.extended = true;
-    // rewireOnly (tree.cpp:419-513): which edges can the sequential replay possibly ask for?
+    // rewireOnly (tree.cpp:419-513), parent phase (:428-463): every near node that would lower the cost-to-come of
+    // the new node is a candidate; the reference walks them in near order and keeps the best collision-free one.
     pr.near_n = std::min(near_count_[r], near_cap_);
     const uint32_t* nidx = &near_idx_[(size_t)r * near_cap_];
     const double* ndist = &near_dist_[(size_t)r * near_cap_];
     const double c2n0 = costToNode(pr, id);
     pr.cost_to_node0 = c2n0;
-    double lower = c2n0;  // best cost the parent phase can reach
+    pr.par_total.clear();
+    pr.par_known = 0;
+    pr.par_winner = -1;
     for (uint32_t i = 0; i < pr.near_n; i++)
     {
       const int32_t nn = pr.id_of_slot[nidx[i]];
@@ -472,38 +478,49 @@ int LockstepRRTStar::stepImpl(const double* samples, const double* d_samples)
       if ((c2near + ndist[i]) >= c2n0)
         continue;
       pr.par_cand.push_back((int32_t)i);
-      lower = std::min(lower, c2near + ndist[i]);
+      pr.par_total.push_back(c2near + ndist[i]);
     }
-    for (uint32_t i = 0; i < pr.near_n; i++)
+    const size_t nc = pr.par_cand.size();
+    if (nc > 1)
     {
-      const int32_t nn = pr.id_of_slot[nidx[i]];
-      if (nn == id || nn == 0)
-        continue;
-      const double c2near = costToNode(pr, nn);
-      if (lower >= c2near)
-        continue;
-      if ((lower + ndist[i]) >= c2near)
-        continue;
-      pr.chi_cand.push_back((int32_t)i);
+      // by (total, near position): a later candidate replaces the parent only if strictly cheaper
+      std::vector<uint32_t>& ord = pr.sort_scratch;
+      ord.resize(nc);
+      for (size_t k = 0; k < nc; k++)
+        ord[k] = (uint32_t)k;
+      std::sort(ord.begin(), ord.end(), [&](uint32_t a, uint32_t b) {
+        return pr.par_total[a] < pr.par_total[b] || (pr.par_total[a] == pr.par_total[b] && a < b);
+      });
+      std::vector<int32_t> ci(nc);
+      std::vector<double> ct(nc);
+      for (size_t k = 0; k < nc; k++)
+      {
+        ci[k] = pr.par_cand[ord[k]];
+        ct[k] = pr.par_total[ord[k]];
+      }
+      pr.par_cand.swap(ci);
+      pr.par_total.swap(ct);
     }
-    pr.edge_count = (uint32_t)(pr.par_cand.size() + pr.chi_cand.size());
-    if (!pr.solved && dist(nx, &pr.conf[D_], D_) < cfg_.max_distance)
-    {
-      pr.goal_edge = (int32_t)pr.edge_count;
-      pr.edge_count++;
-    }
+    pr.par_ok.assign(nc, 0);
+    pr.par_resolved = (nc == 0);
+    pr.cost_to_node1 = c2n0;
+    pr.edgeA_count = (uint32_t)std::min<size_t>(nc, first_batch_);
   });
   stats_.t_phase[2] += secs_since(tp);
   tp = std::chrono::steady_clock::now();
-  // ---- D: append the new nodes, evaluate every candidate edge in one batch -----------------------
-  uint32_t nedges = 0, napp = 0;
+  // ---- D: append the new nodes; first edge batch = the best parent candidates of every problem ---
+  uint32_t nedgesA = 0, napp = 0;
   for (uint32_t r = 0; r < rows; r++)
   {
     Problem& pr = P_[act[r]];
-    pr.edge_first = nedges;
-    nedges += pr.edge_count;
+    pr.edgeA_first = nedgesA;
     if (pr.extended)
+    {
+      nedgesA += pr.edgeA_count;
       napp++;
+    }
+    else
+      pr.edgeA_count = 0;
   }
   if (napp)
   {
@@ -526,6 +543,99 @@ int LockstepRRTStar::stepImpl(const double* samples, const double* d_samples)
     stats_.extended += napp;
     stats_.h2d_bytes += (uint64_t)napp * (sizeof(double) * D_ + sizeof(uint32_t)) + sizeof(uint32_t) * n;
   }
+  auto run_edges = [&](uint32_t count) -> bool {
+    if (gc_check_edges(world_, e1_.data(), e2_.data(), count, cfg_.min_distance, GC_EDGE_BISECT, eok_.data(), nullptr) !=
+        GC_OK)
+      return false;
+    stats_.gpu_calls++;
+    stats_.edges_device += count;
+    stats_.h2d_bytes += (uint64_t)count * 2 * sizeof(double) * D_;
+    stats_.d2h_bytes += count;
+    return true;
+  };
+  if (nedgesA)
+  {
+    e1_.resize((size_t)nedgesA * D_);
+    e2_.resize((size_t)nedgesA * D_);
+    eok_.resize(nedgesA);
+    pool_->parallel_for(rows, [&](uint32_t r) {
+      Problem& pr = P_[act[r]];
+      if (!pr.edgeA_count)
+        return;
+      const uint32_t* nidx = &near_idx_[(size_t)r * near_cap_];
+      const double* me = &pr.conf[(size_t)pr.new_node * D_];
+      for (uint32_t k = 0; k < pr.edgeA_count; k++)  // n -> node
+      {
+        const int32_t nn = pr.id_of_slot[nidx[pr.par_cand[k]]];
+        std::memcpy(&e1_[(size_t)(pr.edgeA_first + k) * D_], &pr.conf[(size_t)nn * D_], sizeof(double) * D_);
+        std::memcpy(&e2_[(size_t)(pr.edgeA_first + k) * D_], me, sizeof(double) * D_);
+      }
+    });
+    if (!run_edges(nedgesA))
+      return fail("gc_check_edges") ? 0 : -1;
+  }
+  // ---- D2: resolve what the first batch decided; second batch = the remaining parent candidates of the problems
+  // it left open + the children-phase candidates (tree.cpp:471-510) + the goal edge ------------------------------
+  pool_->parallel_for(rows, [&](uint32_t r) {
+    Problem& pr = P_[act[r]];
+    pr.chi_cand.clear();
+    pr.goal_edge = -1;
+    pr.edge_count = 0;
+    pr.parB_count = 0;
+    if (!pr.extended)
+      return;
+    const uint32_t* nidx = &near_idx_[(size_t)r * near_cap_];
+    const double* ndist = &near_dist_[(size_t)r * near_cap_];
+    const int32_t id = pr.new_node;
+    for (uint32_t k = 0; k < pr.edgeA_count; k++)
+    {
+      pr.par_ok[k] = eok_[pr.edgeA_first + k];
+      if (pr.par_ok[k] && pr.par_winner < 0)
+        pr.par_winner = (int32_t)k;
+    }
+    pr.par_known = pr.edgeA_count;
+    const size_t nc = pr.par_cand.size();
+    if (pr.par_winner >= 0)
+    {
+      pr.par_resolved = true;
+      pr.cost_to_node1 = pr.par_total[pr.par_winner];
+    }
+    else if (pr.par_known == nc)
+      pr.par_resolved = true;  // nothing free: the nearest node stays the parent
+    else
+    {
+      pr.parB_count = (uint32_t)(nc - pr.par_known);
+      pr.cost_to_node1 = pr.par_total[pr.par_known];  // the best the open candidates can still reach
+    }
+    // children phase: exact cost-to-come when resolved, its lower bound otherwise (a superset either way: the
+    // cost of a near node only falls while the phase runs)
+    const double c2n1 = pr.cost_to_node1;
+    for (uint32_t i = 0; i < pr.near_n; i++)
+    {
+      const int32_t nn = pr.id_of_slot[nidx[i]];
+      if (nn == id || nn == 0)
+        continue;
+      const double c2near = costToNode(pr, nn);
+      if (c2n1 >= c2near)
+        continue;
+      if ((c2n1 + ndist[i]) >= c2near)
+        continue;
+      pr.chi_cand.push_back((int32_t)i);
+    }
+    pr.edge_count = pr.parB_count + (uint32_t)pr.chi_cand.size();
+    if (!pr.solved && dist(&pr.conf[(size_t)id * D_], &pr.conf[D_], D_) < cfg_.max_distance)
+    {
+      pr.goal_edge = (int32_t)pr.edge_count;
+      pr.edge_count++;
+    }
+  });
+  uint32_t nedges = 0;
+  for (uint32_t r = 0; r < rows; r++)
+  {
+    Problem& pr = P_[act[r]];
+    pr.edge_first = nedges;
+    nedges += pr.edge_count;
+  }
   if (nedges)
   {
     e1_.resize((size_t)nedges * D_);
@@ -538,9 +648,9 @@ int LockstepRRTStar::stepImpl(const double* samples, const double* d_samples)
       const uint32_t* nidx = &near_idx_[(size_t)r * near_cap_];
       const double* me = &pr.conf[(size_t)pr.new_node * D_];
       uint32_t e = pr.edge_first;
-      for (int32_t i : pr.par_cand)  // n -> node
+      for (uint32_t k = 0; k < pr.parB_count; k++)  // n -> node
       {
-        const int32_t nn = pr.id_of_slot[nidx[i]];
+        const int32_t nn = pr.id_of_slot[nidx[pr.par_cand[pr.par_known + k]]];
         std::memcpy(&e1_[(size_t)e * D_], &pr.conf[(size_t)nn * D_], sizeof(double) * D_);
         std::memcpy(&e2_[(size_t)e * D_], me, sizeof(double) * D_);
         e++;
@@ -558,13 +668,8 @@ int LockstepRRTStar::stepImpl(const double* samples, const double* d_samples)
         std::memcpy(&e2_[(size_t)e * D_], &pr.conf[D_], sizeof(double) * D_);
       }
     });
-    if (gc_check_edges(world_, e1_.data(), e2_.data(), nedges, cfg_.min_distance, GC_EDGE_BISECT, eok_.data(),
-                       nullptr) != GC_OK)
+    if (!run_edges(nedges))
       return fail("gc_check_edges") ? 0 : -1;
-    stats_.gpu_calls++;
-    stats_.edges_device += nedges;
-    stats_.h2d_bytes += (uint64_t)nedges * 2 * sizeof(double) * D_;
-    stats_.d2h_bytes += nedges;
   }
   stats_.t_phase[3] += secs_since(tp);
   tp = std::chrono::steady_clock::now();
@@ -596,26 +701,28 @@ int LockstepRRTStar::stepImpl(const double* samples, const double* d_samples)
     };
     double cost_to_node = pr.cost_to_node0;
     bool improved = false;
-    const int32_t nearest_node = pr.parent[node];
-    size_t cur = 0;
-    for (uint32_t i = 0; i < pr.near_n; i++)  // parent phase (tree.cpp:428-463)
+    // parent phase (tree.cpp:428-463): the first collision-free candidate in (cost, near position) order is where the
+    // reference's walk ends up
+    if (!pr.par_resolved)
     {
-      const int32_t nn = pr.id_of_slot[nidx[i]];
-      if (nn == nearest_node || nn == node)
-        continue;
-      const double c2near = costToNode(pr, nn);
-      if (c2near >= cost_to_node)
-        continue;
-      const double c = ndist[i];  // metrics_->cost(n, node) == the exact fp64 near distance
-      if ((c2near + c) >= cost_to_node)
-        continue;
-      if (!edge_result(pr.par_cand, cur, 0, (int32_t)i, &pr.conf[(size_t)nn * D_], &pr.conf[(size_t)node * D_]))
-        continue;
-      pr.parent[node] = nn;
-      pr.pcost[node] = c;
-      cost_to_node = c2near + c;
+      for (uint32_t k = 0; k < pr.parB_count; k++)
+      {
+        pr.par_ok[pr.par_known + k] = eok_[pr.edge_first + k];
+        if (pr.par_ok[pr.par_known + k] && pr.par_winner < 0)
+          pr.par_winner = (int32_t)(pr.par_known + k);
+      }
+      pr.par_known += pr.parB_count;
+    }
+    used[r] += (pr.par_winner >= 0) ? (uint32_t)pr.par_winner + 1u : pr.par_known;
+    if (pr.par_winner >= 0)
+    {
+      const int32_t i = pr.par_cand[pr.par_winner];
+      pr.parent[node] = pr.id_of_slot[nidx[i]];
+      pr.pcost[node] = ndist[i];  // metrics_->cost(n, node) == the exact fp64 near distance
+      cost_to_node = pr.par_total[pr.par_winner];
       improved = true;
     }
+    size_t cur = 0;
     const int32_t par = pr.parent[node];
     cur = 0;
     for (uint32_t i = 0; i < pr.near_n; i++)  // children phase (tree.cpp:471-510)
@@ -629,7 +736,7 @@ int LockstepRRTStar::stepImpl(const double* samples, const double* d_samples)
       const double c = ndist[i];
       if ((cost_to_node + c) >= c2near)
         continue;
-      if (!edge_result(pr.chi_cand, cur, (uint32_t)pr.par_cand.size(), (int32_t)i, &pr.conf[(size_t)node * D_],
+      if (!edge_result(pr.chi_cand, cur, pr.parB_count, (int32_t)i, &pr.conf[(size_t)node * D_],
                        &pr.conf[(size_t)nn * D_]))
         continue;
       pr.parent[nn] = node;

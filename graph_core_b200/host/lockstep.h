@@ -33,6 +33,10 @@ struct SolverConfig
   std::vector<double> lb, ub;      // sampler bounds
 };
 
+// parent candidates per problem in the first edge batch of a step (see Problem::par_cand); GCB200_FIRST_BATCH
+// overrides it for experiments
+constexpr size_t kFirstBatchCandidates = 3;
+
 struct StepStats
 {
   uint64_t iterations = 0;   // planner updates executed (samples consumed)
@@ -104,8 +108,21 @@ private:
     uint32_t row = 0;                // row in the batched device call
     uint32_t near_n = 0;
     double cost_to_node0 = 0;
-    uint32_t edge_first = 0, edge_count = 0;  // slice of the batched edge list
-    std::vector<int32_t> par_cand, chi_cand;  // positions in the near list, -1 terminated use sizes
+    // Parent phase of rewireOnly: the walk ends with the collision-free candidate of least cost-to-come (first in walk
+    // order on ties), so the candidates are tried in THAT order, the two best in a first edge batch and the rest --
+    // only for the problems both failed -- in a second one together with the children and goal edges.
+    std::vector<int32_t> par_cand;   // positions in the near list, sorted by (cost through the candidate, position)
+    std::vector<double> par_total;   // cost through the candidate, same order
+    std::vector<uint8_t> par_ok;     // verdicts, same order (valid up to par_known)
+    uint32_t par_known = 0;
+    int32_t par_winner = -1;         // index into par_cand, -1 = none free
+    bool par_resolved = false;
+    double cost_to_node1 = 0;        // cost-to-come after the parent phase (a lower bound while unresolved)
+    uint32_t edgeA_first = 0, edgeA_count = 0;  // slices of the two batched edge lists
+    uint32_t edge_first = 0, edge_count = 0;
+    uint32_t parB_count = 0;         // parent candidates in the second batch (they lead the slice)
+    std::vector<int32_t> chi_cand;   // positions in the near list, ascending
+    std::vector<uint32_t> sort_scratch;
     int32_t goal_edge = -1;
   };
 
@@ -119,6 +136,7 @@ private:
   bool fail(const char* what);
 
   SolverConfig cfg_;
+  size_t first_batch_ = kFirstBatchCandidates;
   int D_;
   gc_world_t* world_;
   gc_store_t* store_ = nullptr;
