@@ -467,12 +467,20 @@ int LockstepRRTStar::stepImpl(const double* samples, const double* d_samples)
     pr.par_total.clear();
     pr.par_known = 0;
     pr.par_winner = -1;
+    // costToNode walks the parent chain (tree.cpp:767-789): once per near node and step; the values stay valid until
+    // the children phase of the replay rewires something
+    pr.c2near.resize(pr.near_n);
+    for (uint32_t i = 0; i < pr.near_n; i++)
+    {
+      const int32_t nn = pr.id_of_slot[nidx[i]];
+      pr.c2near[i] = (nn == id) ? c2n0 : costToNode(pr, nn);
+    }
     for (uint32_t i = 0; i < pr.near_n; i++)
     {
       const int32_t nn = pr.id_of_slot[nidx[i]];
       if (nn == closest || nn == id)
         continue;
-      const double c2near = costToNode(pr, nn);
+      const double c2near = pr.c2near[i];
       if (c2near >= c2n0)
         continue;
       if ((c2near + ndist[i]) >= c2n0)
@@ -615,7 +623,7 @@ int LockstepRRTStar::stepImpl(const double* samples, const double* d_samples)
       const int32_t nn = pr.id_of_slot[nidx[i]];
       if (nn == id || nn == 0)
         continue;
-      const double c2near = costToNode(pr, nn);
+      const double c2near = pr.c2near[i];
       if (c2n1 >= c2near)
         continue;
       if ((c2n1 + ndist[i]) >= c2near)
@@ -724,13 +732,14 @@ int LockstepRRTStar::stepImpl(const double* samples, const double* d_samples)
     }
     size_t cur = 0;
     const int32_t par = pr.parent[node];
+    bool rewired = false;
     cur = 0;
     for (uint32_t i = 0; i < pr.near_n; i++)  // children phase (tree.cpp:471-510)
     {
       const int32_t nn = pr.id_of_slot[nidx[i]];
       if (nn == par || nn == node || nn == 0)
         continue;
-      const double c2near = costToNode(pr, nn);
+      const double c2near = rewired ? costToNode(pr, nn) : pr.c2near[i];
       if (cost_to_node >= c2near)
         continue;
       const double c = ndist[i];
@@ -742,6 +751,7 @@ int LockstepRRTStar::stepImpl(const double* samples, const double* d_samples)
       pr.parent[nn] = node;
       pr.pcost[nn] = c;
       improved = true;
+      rewired = true;  // descendants of nn just got cheaper: walk from here on
     }
     // RRTStar::update epilogue (rrt_star.cpp:110-162); Tree::rewire returns rewireOnly's `improved`
     if (!pr.solved)

@@ -123,6 +123,7 @@ private:
     uint32_t parB_count = 0;         // parent candidates in the second batch (they lead the slice)
     std::vector<int32_t> chi_cand;   // positions in the near list, ascending
     std::vector<uint32_t> sort_scratch;
+    std::vector<double> c2near;      // cost-to-come of every near node at the start of the step (walked once)
     int32_t goal_edge = -1;
   };
 
