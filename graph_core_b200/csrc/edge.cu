@@ -20,6 +20,7 @@
 //                       G = 1 lane per state (throughput) or a whole warp per state (latency)
 #include <math_constants.h>
 
+#include <algorithm>
 #include <cfloat>
 #include <cmath>
 
@@ -404,6 +405,9 @@ struct ArmSmem
   const int* rs_link;
   const float4* obs;   // x y z r
   const float* obs_na; // r^2 - |o|^2 (include/gcb200_spec.h, "sphere pair test")
+  const float4* blk;   // bounding sphere (inflated, see arm_block_bounds) of obstacles [16 j, 16 j + 16)
+  const float* blk_na;
+  uint32_t nblk;       // 0 = culling off
 };
 
 // Per-sphere constants of the expanded pair test  |o-c|^2 < (ro+rs)^2  <=>
@@ -543,6 +547,86 @@ __device__ __forceinline__ bool arm_check_lane(const ArmSmem& w, uint32_t nrs, u
   // per 16 obstacles.  The padded cloud (arm_stage) makes every lane's share a whole number of such blocks, so the
   // loop carries no clamps, no tail and no register rotation: 64 FFMA + 8 FMNMX3 + ~12 others per obstacle.
   const uint32_t npad = arm_padded_obstacles(nobs);
+  if (w.nblk)
+  {
+    // Block culling.  The cloud is sorted along a space-filling curve, so 16 consecutive obstacles are neighbours and
+    // have a tight bounding sphere.  Phase 1: the lanes of the state test all 16 robot spheres against the (inflated)
+    // bounding spheres with the same expanded pair test and share the result as a bit mask; phase 2: only the blocks
+    // some robot sphere reaches are tested obstacle by obstacle, split over the lanes of the state.  The inflation
+    // (arm_block_bounds) exceeds the rounding of both tests, so a skipped block cannot hold a colliding obstacle and
+    // the verdict is the brute-force one.
+    const uint32_t nbp = npad >> 4;  // <= 64, a multiple of 8
+    uint32_t m0 = 0, m1 = 0, tested = 0;
+    for (uint32_t j = part; j < nbp; j += nparts)
+    {
+      const float4 ob = w.blk[j];
+      const float na = w.blk_na[j];
+      float m = 3.0e38f;
+#pragma unroll
+      for (int k = 0; k < NRS; k++)
+      {
+        float t = __fmaf_rn(ob.x, sk[k].c2x, sk[k].B);
+        t = __fmaf_rn(ob.y, sk[k].c2y, t);
+        t = __fmaf_rn(ob.z, sk[k].c2z, t);
+        t = __fmaf_rn(ob.w, sk[k].rs2, t);
+        m = fminf(m, t);
+      }
+      if (m < na)
+      {
+        if (j < 32u)
+          m0 |= 1u << j;
+        else
+          m1 |= 1u << (j - 32u);
+      }
+      tested++;
+    }
+    // OR over the lanes that share the state (they are converged: same item, same decision to get here)
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t gmask = (nparts >= 32u ? 0xffffffffu : ((1u << nparts) - 1u)) << (lane & ~(nparts - 1u));
+    for (uint32_t d = 1; d < nparts; d <<= 1)
+    {
+      m0 |= __shfl_xor_sync(gmask, m0, d);
+      m1 |= __shfl_xor_sync(gmask, m1, d);
+    }
+    bool hit = false;
+    uint32_t done = tested;
+    const uint32_t per = 16u / nparts;  // obstacles of a block per lane (nparts <= 16)
+    while ((m0 | m1) != 0u && !hit)
+    {
+      uint32_t j;
+      if (m0)
+      {
+        j = __ffs(m0) - 1;
+        m0 &= m0 - 1;
+      }
+      else
+      {
+        j = 32u + __ffs(m1) - 1;
+        m1 &= m1 - 1;
+      }
+      const float4* po = w.obs + (j << 4) + part;
+      const float* pn = w.obs_na + (j << 4) + part;
+      for (uint32_t u = 0; u < per; u++)
+      {
+        const float4 ob = po[u * nparts];
+        const float na = pn[u * nparts];
+        float m = 3.0e38f;
+#pragma unroll
+        for (int k = 0; k < NRS; k++)
+        {
+          float t = __fmaf_rn(ob.x, sk[k].c2x, sk[k].B);
+          t = __fmaf_rn(ob.y, sk[k].c2y, t);
+          t = __fmaf_rn(ob.z, sk[k].c2z, t);
+          t = __fmaf_rn(ob.w, sk[k].rs2, t);
+          m = fminf(m, t);
+        }
+        hit |= (m < na);
+        done += ((j << 4) + part + u * nparts) < nobs ? 1u : 0u;
+      }
+    }
+    pairs += (unsigned long long)done * nrs;
+    return hit;
+  }
   const float4* po = w.obs + part;
   const float* pn = w.obs_na + part;
   const float4* const pe = w.obs + npad;
@@ -784,6 +868,7 @@ struct ArmArgs
   // world
   const float* arm;   // global image (base | joints | rs_local | rs_link)
   const float* obs;
+  uint32_t nblk;      // bounding spheres behind the obstacles in `obs` (0 = no culling)
   int njoints;
   uint32_t nrs;
   uint32_t nobs;
@@ -820,7 +905,10 @@ __device__ __forceinline__ ArmSmem arm_stage(const ArmArgs& a, unsigned char* sm
   const uint32_t npad = arm_padded_obstacles(a.nobs);
   float4* sobs = reinterpret_cast<float4*>(smem_raw);
   float* sna = reinterpret_cast<float*>(sobs + npad);
-  float* sarm = sna + npad;
+  const uint32_t nbp = a.nblk ? (npad >> 4) : 0u;
+  float4* sblk = reinterpret_cast<float4*>(sna + npad);
+  float* sbna = reinterpret_cast<float*>(sblk + nbp);
+  float* sarm = sbna + nbp;
   const uint32_t arm_words = 12u + 12u * a.njoints + 4u * a.nrs + a.nrs;
   for (uint32_t i = threadIdx.x; i < npad; i += blockDim.x)
   {
@@ -834,10 +922,25 @@ __device__ __forceinline__ ArmSmem arm_stage(const ArmArgs& a, unsigned char* sm
     sobs[i] = ob;
     sna[i] = na;
   }
+  for (uint32_t i = threadIdx.x; i < nbp; i += blockDim.x)
+  {
+    float4 ob = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    float na = -CUDART_INF_F;
+    if (i < a.nblk)
+    {
+      ob = reinterpret_cast<const float4*>(a.obs)[a.nobs + i];
+      na = obstacle_na(ob);
+    }
+    sblk[i] = ob;
+    sbna[i] = na;
+  }
   for (uint32_t i = threadIdx.x; i < arm_words; i += blockDim.x)
     sarm[i] = a.arm[i];
   __syncthreads();
   ArmSmem w;
+  w.blk = sblk;
+  w.blk_na = sbna;
+  w.nblk = a.nblk;
   w.obs = sobs;
   w.obs_na = sna;
   w.base = sarm;
@@ -1064,7 +1167,8 @@ static int launch_light(gc_world* w, const LightArgs& a, cudaStream_t st)
 template <int D, int NRS, int G>
 static int launch_arm(gc_world* w, const ArmArgs& a, uint64_t items_hint, cudaStream_t st)
 {
-  const size_t smem = (sizeof(float4) + sizeof(float)) * arm_padded_obstacles(a.nobs) + sizeof(float) * (12 + 12 * a.njoints + 5 * a.nrs) + 16;
+  const size_t npad_l = arm_padded_obstacles(a.nobs);
+  const size_t smem = (sizeof(float4) + sizeof(float)) * (npad_l + (a.nblk ? npad_l / 16 : 0)) + sizeof(float) * (12 + 12 * a.njoints + 5 * a.nrs) + 16;
   if (smem > 200 * 1024)
   {
     gc::set_error("obstacle cloud too large for shared memory staging (%zu bytes)", smem);
@@ -1208,6 +1312,7 @@ int check_edges_dev(gc_world* w, const double* d_c1, const double* d_c2, const d
     ArmArgs a{};
     a.arm = w->d_arm;
     a.obs = w->d_obs;
+    a.nblk = w->nblk;
     a.njoints = w->njoints;
     a.nrs = w->nrs;
     a.nobs = w->nobj;
@@ -1269,6 +1374,7 @@ int check_states_dev(gc_world* w, const double* d_q, uint32_t n, uint8_t* d_ok, 
     ArmArgs a{};
     a.arm = w->d_arm;
     a.obs = w->d_obs;
+    a.nblk = w->nblk;
     a.njoints = w->njoints;
     a.nrs = w->nrs;
     a.nobs = w->nobj;
@@ -1378,6 +1484,103 @@ int gc_world_create_cspheres(int dim, uint32_t n, const float* centers, const fl
   return rc;
 }
 
+// Block culling support (arm_check_lane).  Sorts the cloud along a Morton curve and appends, behind the obstacles, one
+// bounding sphere per block of 16 consecutive ones: centre b = mean of the members, radius max(|o - b| + r_o) + m.
+// The inflation m covers the rounding of the two fp32 tests involved: with E = reach of the arm + extent of the cloud
+// (every |c|, |o|, r below E) the expanded pair test is within d = 2^-20 E^2 of |c - o|^2 - (r_s + r_o)^2; a block test
+// that reports "apart" guarantees |c - b| >= r_s + R + m - d/m, hence |c - o| >= r_s + r_o + m - d/m for its members and
+// |c - o|^2 - (r_s + r_o)^2 >= (m - d/m)^2 > d when m = 2^-8 E (m^2 = 16 d).  Returns the number of blocks (0 = culling
+// off: clouds beyond 1024 obstacles, whose block mask would not fit two registers, or too small to pay).
+static uint32_t arm_block_bounds(int njoints, const float* base_tf, const float* joint_tf, uint32_t nrs,
+                                 const float* rs_local, uint32_t nobs, const float* obs, std::vector<float>& cloud)
+{
+  cloud.assign(obs, obs + 4 * (size_t)nobs);
+  if (nobs < 64 || nobs > 1024)
+    return 0;
+  double lo[3] = { 1e300, 1e300, 1e300 }, hi[3] = { -1e300, -1e300, -1e300 }, omax = 0, rmax = 0;
+  for (uint32_t i = 0; i < nobs; i++)
+  {
+    double n2 = 0;
+    for (int d = 0; d < 3; d++)
+    {
+      const double v = obs[4 * i + d];
+      if (!(std::fabs(v) < 1e18))
+        return 0;  // non-finite cloud: leave it to the plain loop
+      lo[d] = std::min(lo[d], v);
+      hi[d] = std::max(hi[d], v);
+      n2 += v * v;
+    }
+    omax = std::max(omax, std::sqrt(n2));
+    rmax = std::max(rmax, (double)std::fabs(obs[4 * i + 3]));
+  }
+  auto norm3 = [](const float* t) { return std::sqrt((double)t[0] * t[0] + (double)t[1] * t[1] + (double)t[2] * t[2]); };
+  double reach = norm3(base_tf + 9), smax = 0;
+  for (int j = 0; j < njoints; j++)
+    reach += norm3(joint_tf + 12 * j + 9);
+  for (uint32_t k = 0; k < nrs; k++)
+  {
+    smax = std::max(smax, norm3(rs_local + 4 * k));
+    rmax = std::max(rmax, (double)std::fabs(rs_local[4 * k + 3]));
+  }
+  reach += smax;
+  // Morton order of the centres
+  std::vector<std::pair<uint64_t, uint32_t>> key(nobs);
+  for (uint32_t i = 0; i < nobs; i++)
+  {
+    uint64_t code = 0;
+    for (int d = 0; d < 3; d++)
+    {
+      const double span = hi[d] - lo[d];
+      const uint32_t q = span > 0 ? (uint32_t)std::min(1023.0, (obs[4 * i + d] - lo[d]) / span * 1024.0) : 0u;
+      for (int b = 0; b < 10; b++)
+        code |= (uint64_t)((q >> b) & 1u) << (3 * b + d);
+    }
+    key[i] = { code, i };
+  }
+  std::sort(key.begin(), key.end());
+  for (uint32_t i = 0; i < nobs; i++)
+    memcpy(&cloud[4 * (size_t)i], obs + 4 * (size_t)key[i].second, 4 * sizeof(float));
+  const uint32_t nblk = (nobs + 15u) / 16u;
+  double rbmax = 0;
+  std::vector<double> bc(4 * (size_t)nblk);
+  for (uint32_t j = 0; j < nblk; j++)
+  {
+    const uint32_t b0 = 16 * j, b1 = std::min(nobs, b0 + 16);
+    double c[3] = { 0, 0, 0 };
+    for (uint32_t i = b0; i < b1; i++)
+      for (int d = 0; d < 3; d++)
+        c[d] += cloud[4 * (size_t)i + d];
+    for (int d = 0; d < 3; d++)
+      c[d] = (double)(float)(c[d] / (b1 - b0));  // the centre the kernel will see
+    double R = 0;
+    for (uint32_t i = b0; i < b1; i++)
+    {
+      double n2 = 0;
+      for (int d = 0; d < 3; d++)
+      {
+        const double v = cloud[4 * (size_t)i + d] - c[d];
+        n2 += v * v;
+      }
+      R = std::max(R, std::sqrt(n2) + std::fabs((double)cloud[4 * (size_t)i + 3]));
+    }
+    bc[4 * j + 0] = c[0];
+    bc[4 * j + 1] = c[1];
+    bc[4 * j + 2] = c[2];
+    bc[4 * j + 3] = R;
+    rbmax = std::max(rbmax, R);
+  }
+  const double E = reach + omax + rmax + rbmax;
+  const double m = E / 256.0;
+  cloud.resize(4 * ((size_t)nobs + nblk));
+  for (uint32_t j = 0; j < nblk; j++)
+  {
+    for (int d = 0; d < 3; d++)
+      cloud[4 * ((size_t)nobs + j) + d] = (float)bc[4 * j + d];
+    cloud[4 * ((size_t)nobs + j) + 3] = std::nextafter((float)((bc[4 * j + 3] + m) * (1.0 + 1e-6)), INFINITY);
+  }
+  return nblk;
+}
+
 int gc_world_create_sphere_arm(int njoints, const float* base_tf, const float* joint_tf, uint32_t nrs,
                                const int32_t* rs_link, const float* rs_local, uint32_t nobs, const float* obs,
                                int device, gc_world_t** out)
@@ -1398,8 +1601,10 @@ int gc_world_create_sphere_arm(int njoints, const float* base_tf, const float* j
   memcpy(img.data() + 12 + 12 * njoints, rs_local, 4 * sizeof(float) * nrs);
   memcpy(img.data() + 12 + 12 * njoints + 4 * nrs, rs_link, sizeof(int32_t) * nrs);
   int rc = upload(&w->d_arm, img.data(), img.size());
+  std::vector<float> cloud;
+  w->nblk = arm_block_bounds(njoints, base_tf, joint_tf, nrs, rs_local, nobs, obs, cloud);
   if (rc == GC_OK)
-    rc = upload(&w->d_obs, obs, 4 * (size_t)nobs);
+    rc = upload(&w->d_obs, cloud.data(), cloud.size());
   if (rc != GC_OK)
   {
     gc_world_destroy(w);
@@ -1433,6 +1638,7 @@ int gc_world_clone(gc_world_t* w, gc_world_t** out)
   c->d_sr2 = root->d_sr2;
   c->d_arm = root->d_arm;
   c->d_obs = root->d_obs;
+  c->nblk = root->nblk;
   c->parent = root;
   __atomic_add_fetch(&root->refs, 1, __ATOMIC_SEQ_CST);
   *out = c;

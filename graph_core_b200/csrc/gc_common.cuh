@@ -139,7 +139,8 @@ struct gc_world
   int njoints = 0;
   uint32_t nrs = 0;
   float* d_arm = nullptr;  // base_tf[12] | joint_tf[J][12] | rs_local[nrs][4] | rs_link[nrs] (as float bits)
-  float* d_obs = nullptr;  // [nobs][4]
+  float* d_obs = nullptr;  // [nobs][4], then [nblk][4] bounding spheres of the blocks of 16 (see edge.cu, culling)
+  uint32_t nblk = 0;       // 0 = no block culling for this world
   cudaStream_t stream = nullptr;
   cudaStream_t own_stream = nullptr;
   int sms = 148;
