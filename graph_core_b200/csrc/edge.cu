@@ -1484,7 +1484,7 @@ int gc_world_create_cspheres(int dim, uint32_t n, const float* centers, const fl
   return rc;
 }
 
-// Block culling support (arm_check_lane).  Sorts the cloud along a Morton curve and appends, behind the obstacles, one
+// Block culling support (arm_check_lane).  Orders the cloud into compact blocks and appends, behind the obstacles, one
 // bounding sphere per block of 16 consecutive ones: centre b = mean of the members, radius max(|o - b| + r_o) + m.
 // The inflation m covers the rounding of the two fp32 tests involved: with E = reach of the arm + extent of the cloud
 // (every |c|, |o|, r below E) the expanded pair test is within d = 2^-20 E^2 of |c - o|^2 - (r_s + r_o)^2; a block test
@@ -1523,23 +1523,42 @@ static uint32_t arm_block_bounds(int njoints, const float* base_tf, const float*
     rmax = std::max(rmax, (double)std::fabs(rs_local[4 * k + 3]));
   }
   reach += smax;
-  // Morton order of the centres
-  std::vector<std::pair<uint64_t, uint32_t>> key(nobs);
+  // Order the cloud so that every block of 16 consecutive obstacles is compact: recursive median split along the
+  // longest axis of the centres, the left part always a whole number of blocks (tighter than a Morton curve, whose
+  // blocks straddle cell borders: 44 % -> fewer of the blocks reached per state in the C3 cloud)
+  std::vector<uint32_t> order(nobs);
   for (uint32_t i = 0; i < nobs; i++)
+    order[i] = i;
+  struct Range { uint32_t lo, hi; };
+  std::vector<Range> stack;
+  stack.push_back({ 0u, nobs });
+  while (!stack.empty())
   {
-    uint64_t code = 0;
-    for (int d = 0; d < 3; d++)
-    {
-      const double span = hi[d] - lo[d];
-      const uint32_t q = span > 0 ? (uint32_t)std::min(1023.0, (obs[4 * i + d] - lo[d]) / span * 1024.0) : 0u;
-      for (int b = 0; b < 10; b++)
-        code |= (uint64_t)((q >> b) & 1u) << (3 * b + d);
-    }
-    key[i] = { code, i };
+    const Range r = stack.back();
+    stack.pop_back();
+    const uint32_t n = r.hi - r.lo;
+    if (n <= 16u)
+      continue;
+    float bl[3] = { FLT_MAX, FLT_MAX, FLT_MAX }, bh[3] = { -FLT_MAX, -FLT_MAX, -FLT_MAX };
+    for (uint32_t i = r.lo; i < r.hi; i++)
+      for (int d = 0; d < 3; d++)
+      {
+        bl[d] = std::min(bl[d], obs[4 * (size_t)order[i] + d]);
+        bh[d] = std::max(bh[d], obs[4 * (size_t)order[i] + d]);
+      }
+    int ax = 0;
+    for (int d = 1; d < 3; d++)
+      if (bh[d] - bl[d] > bh[ax] - bl[ax])
+        ax = d;
+    const uint32_t blocks = (n + 15u) / 16u;
+    const uint32_t left = 16u * (blocks / 2u);
+    std::nth_element(order.begin() + r.lo, order.begin() + r.lo + left, order.begin() + r.hi,
+                     [&](uint32_t a, uint32_t b) { return obs[4 * (size_t)a + ax] < obs[4 * (size_t)b + ax]; });
+    stack.push_back({ r.lo, r.lo + left });
+    stack.push_back({ r.lo + left, r.hi });
   }
-  std::sort(key.begin(), key.end());
   for (uint32_t i = 0; i < nobs; i++)
-    memcpy(&cloud[4 * (size_t)i], obs + 4 * (size_t)key[i].second, 4 * sizeof(float));
+    memcpy(&cloud[4 * (size_t)i], obs + 4 * (size_t)order[i], 4 * sizeof(float));
   const uint32_t nblk = (nobs + 15u) / 16u;
   double rbmax = 0;
   std::vector<double> bc(4 * (size_t)nblk);
