@@ -190,3 +190,46 @@ def test_clones_are_independent_handles_across_threads(gc, orc, c3):
     for t in range(4):
         assert np.array_equal(got[t], want[t])
         assert clones[t].counters()["launches"] == 5
+
+
+@pytest.mark.parametrize("n_obs", [48, 64, 100, 333, 1000, 1024, 1100])
+def test_block_culling_keeps_the_brute_force_verdict(gc, orc, n_obs):
+    """The arm kernel skips blocks of 16 obstacles whose inflated bounding sphere no robot sphere reaches (edge.cu,
+    arm_block_bounds): clouds below 64 and above 1024 obstacles take the plain loop, the others the culled one, with a
+    partial last block when the size is not a multiple of 16.  Verdicts must be the oracle's brute-force ones for
+    states (throughput and warp-per-state paths) and for edges in both modes, touching obstacles included."""
+    sc = W.scenario_c3(n_obs, orc.arm_checker())
+    gw = sc.make_world()
+    ow = orc.OracleWorld.from_scenario(sc)
+    q = W.uniform_samples(sc.lb, sc.ub, 4000 + n_obs, 0, 5000)
+    want = ow.check(q)
+    assert np.array_equal(gw.check(q), want)
+    assert 0 < want.sum() < len(q)
+    assert np.array_equal(gw.check(q[:5]), want[:5])
+    a, b = _segments(sc, 1200, 4100 + n_obs, 0.0, 1.5)
+    wok = ow.check_connection(a, b, sc.min_distance)
+    assert np.array_equal(gw.check_connection(a, b, sc.min_distance), wok)
+    assert 0 < wok.sum() < len(a)
+    ok, fb = gw.check_connection(a, b, sc.min_distance, mode=1)
+    lok, lfb, _ = ow.check_connection(a, b, sc.min_distance, mode=1)
+    assert np.array_equal(ok, lok) and np.array_equal(fb, lfb)
+
+
+def test_block_culling_grazing_contacts(gc, orc, c3):
+    """States whose closest sphere pair is within a few ulps of touching: the culling margin must never hide the pair
+    the exact fp32 test would call a collision.  Bisect between a free and a colliding state until they are adjacent
+    in fp32 joint space, then check the whole bracket."""
+    gw = c3.make_world()
+    ow = orc.OracleWorld.from_scenario(c3)
+    q = W.uniform_samples(c3.lb, c3.ub, 4321, 0, 4000)
+    free = ow.check(q).astype(bool)
+    lo, hi = q[free][:150], q[~free][:150]
+    n = min(len(lo), len(hi))
+    lo, hi = lo[:n].copy(), hi[:n].copy()
+    for _ in range(40):
+        mid = 0.5 * (lo + hi)
+        ok = ow.check(mid).astype(bool)
+        lo[ok] = mid[ok]
+        hi[~ok] = mid[~ok]
+    bracket = np.concatenate([lo, hi, 0.5 * (lo + hi), np.nextafter(lo, hi), np.nextafter(hi, lo)])
+    assert np.array_equal(gw.check(bracket), ow.check(bracket))
