@@ -430,6 +430,7 @@ def main():
                    "h2d_bytes_per_step": int(st.get("h2d_bytes", 0) / K), "d2h_bytes_per_step": int(st.get("d2h_bytes", 0) / K),
                    "ms_per_step": e2e_run["ms"] / K, "same_trees_as_value_run": bool(same)}
     wc = roof_run["world"]
+    brute_pairs_per_state = float(len(sc.params["rs_link"]) * len(sc.params["obs"]))
     achieved = edge_flops(wc) / max(wc["kernel_ns"], 1) / 1e3  # TFLOP/s
     executed = EXECUTED_FLOP_PER_PAIR * wc["pair_tests"] / max(wc["kernel_ns"], 1) / 1e3
     traffic = {}
@@ -447,6 +448,11 @@ def main():
                       "the kernel, so early exits do not inflate it)" % (FLOP_PER_PAIR, FLOP_FK_PER_STATE),
         "executed_pair_flops": {"flop_per_pair": EXECUTED_FLOP_PER_PAIR, "achieved": executed,
                                 "frac": executed / fp32_peak if fp32_peak > 0 else None},
+        "brute_force_equivalent": {
+            "note": "what the same states would cost without block culling (SURVEY 8(d): every robot sphere against "
+                    "every obstacle); not a roofline figure, it shows what the culling saves",
+            "tflops": (FLOP_PER_PAIR * brute_pairs_per_state + FLOP_FK_PER_STATE) * wc["states"] / max(wc["kernel_ns"], 1) / 1e3,
+            "pair_tests_executed_share": wc["pair_tests"] / max(brute_pairs_per_state * wc["states"], 1)},
         "pair_tests_per_launch": wc["pair_tests"] / max(wc["launches"], 1),
         "states_per_launch": wc["states"] / max(wc["launches"], 1),
         "us_per_launch": wc["kernel_ns"] / max(wc["launches"], 1) / 1e3,
