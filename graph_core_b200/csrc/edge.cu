@@ -1487,7 +1487,8 @@ int gc_world_create_cspheres(int dim, uint32_t n, const float* centers, const fl
 // Block culling support (arm_check_lane).  Orders the cloud into compact blocks and appends, behind the obstacles, one
 // bounding sphere per block of 16 consecutive ones: centre b = mean of the members, radius max(|o - b| + r_o) + m.
 // The inflation m covers the rounding of the two fp32 tests involved: with E = reach of the arm + extent of the cloud
-// (every |c|, |o|, r below E) the expanded pair test is within d = 2^-20 E^2 of |c - o|^2 - (r_s + r_o)^2; a block test
+// (every |c|, |o|, r below E) the expanded pair test is within d = 2^-20 E^2 of |c - o|^2 - (r_s + r_o)^2 (14 roundings
+// -- 5 for B, 4 fused multiply-adds, 5 for NA -- each below 2^-24 times a partial sum <= E^2); a block test
 // that reports "apart" guarantees |c - b| >= r_s + R + m - d/m, hence |c - o| >= r_s + r_o + m - d/m for its members and
 // |c - o|^2 - (r_s + r_o)^2 >= (m - d/m)^2 > d when m = 2^-8 E (m^2 = 16 d).  Returns the number of blocks (0 = culling
 // off: clouds beyond 1024 obstacles, whose block mask would not fit two registers, or too small to pay).
