@@ -241,6 +241,7 @@ struct LightArgs
   uint8_t* ok;
   unsigned long long* first_bad;
   unsigned long long* counters;
+  const uint32_t* n_dev;  // optional: the count lives in device memory (<= n)
 };
 
 // MODE 3 = plain state batch (check(q) on n configurations)
@@ -283,10 +284,11 @@ __global__ void __launch_bounds__(256) edge_warp_kernel(LightArgs a)
   const uint32_t gwarp = blockIdx.x * warps_per_block + (threadIdx.x >> 5);
   const uint32_t nwarps = gridDim.x * warps_per_block;
   unsigned long long states = 0, pairs = 0;
+  const uint32_t n_act = a.n_dev ? min(*a.n_dev, a.n) : a.n;
 
   if (MODE == 3)
   {
-    for (uint32_t i = gwarp * 32u + lane; i < a.n; i += nwarps * 32u)
+    for (uint32_t i = gwarp * 32u + lane; i < n_act; i += nwarps * 32u)
     {
       double q[D];
 #pragma unroll
@@ -298,7 +300,7 @@ __global__ void __launch_bounds__(256) edge_warp_kernel(LightArgs a)
   }
   else
   {
-    for (uint32_t e = gwarp; e < a.n; e += nwarps)
+    for (uint32_t e = gwarp; e < n_act; e += nwarps)
     {
       double c1[D], c2[D], c3[D];
 #pragma unroll
@@ -769,6 +771,7 @@ struct PlanArgs
   uint8_t* ok;         // initialised here: 1, or 255 when the reference would throw
   unsigned long long* first_bad;
   uint32_t* work_ctr;  // zeroed here for the check kernel that follows
+  const uint32_t* n_dev;  // optional: the edge count lives in device memory (<= n, which stays the array stride)
   // latency path: c1/c2/c3 point at pinned HOST memory; the plan kernel leaves device copies here for the check kernel
   double* copy_c1;
   double* copy_c2;
@@ -780,6 +783,7 @@ __global__ void __launch_bounds__(1024) edge_plan_kernel(PlanArgs a)
 {
   __shared__ uint32_t warp_sums[32];
   __shared__ uint32_t carry_s[kPasses];
+  const uint32_t n_act = a.n_dev ? min(*a.n_dev, a.n) : a.n;
   if (threadIdx.x < kPasses)
   {
     carry_s[threadIdx.x] = 0;
@@ -789,11 +793,11 @@ __global__ void __launch_bounds__(1024) edge_plan_kernel(PlanArgs a)
     *a.work_ctr = 0;
   __syncthreads();
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  for (uint32_t base = 0; base < a.n; base += blockDim.x)
+  for (uint32_t base = 0; base < n_act; base += blockDim.x)
   {
     const uint32_t e = base + threadIdx.x;
     uint32_t ns = 0;
-    if (e < a.n)
+    if (e < n_act)
     {
       double c1[D], c2[D], c3[D];
 #pragma unroll
@@ -853,7 +857,7 @@ __global__ void __launch_bounds__(1024) edge_plan_kernel(PlanArgs a)
       }
       __syncthreads();
       const uint32_t incl = v + (wid > 0 ? warp_sums[wid - 1] : 0) + carry_s[p];
-      if (e < a.n)
+      if (e < n_act)
         a.offs[(size_t)p * (a.n + 1) + e + 1] = incl;
       __syncthreads();
       if (threadIdx.x == blockDim.x - 1)
@@ -887,6 +891,7 @@ struct ArmArgs
   int mode;        // gc_edge_mode, or 3 = plain state batch
   uint32_t lanes;  // lane mode: lanes per state (1, 2, 4, 8)
   uint32_t* work_ctr;  // items handed out so far beyond the first one of every group (zeroed before the launch)
+  const uint32_t* n_dev;  // optional: edge count in device memory (<= n; n stays the stride of offs)
 };
 
 template <int D>
@@ -975,13 +980,14 @@ __global__ void __launch_bounds__(G == 1 ? 128 : 256, G == 1 ? (NRS <= 16 ? 4 : 
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const ArmSmem w = arm_stage(a, smem_raw);
   const int lane = threadIdx.x & 31;
+  const uint32_t n_act = a.n_dev ? min(*a.n_dev, a.n) : a.n;
   // pass bases of the pass-major work list
   uint32_t pbase[kPasses + 1];
   pbase[0] = 0;
 #pragma unroll
   for (int p = 0; p < kPasses; p++)
-    pbase[p + 1] = pbase[p] + ((MODE == 3) ? 0u : a.offs[(size_t)p * (a.n + 1) + a.n]);
-  const uint32_t total = (MODE == 3) ? a.n : pbase[kPasses];
+    pbase[p + 1] = pbase[p] + ((MODE == 3) ? 0u : a.offs[(size_t)p * (a.n + 1) + n_act]);
+  const uint32_t total = (MODE == 3) ? n_act : pbase[kPasses];
   unsigned long long states = 0, pairs = 0;
   const uint32_t gthread = blockIdx.x * blockDim.x + threadIdx.x;
   const uint32_t nthreads = gridDim.x * blockDim.x;
@@ -1012,7 +1018,7 @@ __global__ void __launch_bounds__(G == 1 ? 128 : 256, G == 1 ? (NRS <= 16 ? 4 : 
       const int p = (t >= pbase[1]) + (t >= pbase[2]) + (t >= pbase[3]);
       const uint32_t* offs_p = a.offs + (size_t)p * (a.n + 1);
       const uint32_t tp = t - pbase[p];
-      e = find_edge(offs_p, a.n, tp);
+      e = find_edge(offs_p, n_act, tp);
       s = pass_lo(p) + (tp - offs_p[e]);
       // early exit: the reference stops at its first colliding state
       if (MODE == GC_EDGE_LINEAR)
@@ -1264,7 +1270,7 @@ int resolve_timing(gc_world* w)
 
 int check_edges_dev(gc_world* w, const double* d_c1, const double* d_c2, const double* d_c3, uint32_t n,
                     double min_distance, int mode, uint8_t* d_ok, int64_t* d_first_bad, uint64_t states_hint,
-                    cudaStream_t st)
+                    cudaStream_t st, const uint32_t* d_n)
 {
   if (n == 0)
     return GC_OK;
@@ -1289,6 +1295,7 @@ int check_edges_dev(gc_world* w, const double* d_c1, const double* d_c2, const d
     a.ok = d_ok;
     a.first_bad = reinterpret_cast<unsigned long long*>(d_first_bad);
     a.counters = w->d_counters;
+    a.n_dev = d_n;
     GC_DISPATCH_DIM_E(w->dim, GC_DISPATCH_MODE(mode, 
                                                GC_TRY((launch_light<DD, MM>(w, a, st)))));
   }
@@ -1309,7 +1316,9 @@ int check_edges_dev(gc_world* w, const double* d_c1, const double* d_c2, const d
     p.work_ctr = p.nst + n;
     p.ok = d_ok;
     p.first_bad = reinterpret_cast<unsigned long long*>(d_first_bad);
+    p.n_dev = d_n;
     ArmArgs a{};
+    a.n_dev = d_n;
     a.arm = w->d_arm;
     a.obs = w->d_obs;
     a.nblk = w->nblk;

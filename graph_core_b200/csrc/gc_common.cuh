@@ -104,6 +104,8 @@ struct gc_store
   double* x64 = nullptr;
   uint32_t* d_used = nullptr;
   std::vector<uint32_t> used;      // host mirror of d_used
+  uint32_t used_bound = 0;         // > 0: a device-side owner (gc_forest) appends on the device; the host mirror is
+                                   // stale until gc_forest_sync and this is an upper bound of every segment's count
   std::vector<uint32_t> live;      // live (non tombstoned) nodes per segment
   std::vector<double> max_abs;     // per segment max |coordinate| ever appended (fp32 slack bound)
   cudaStream_t stream = nullptr;
@@ -168,7 +170,16 @@ int knn_dev(gc_store* s, const double* d_q, const uint32_t* d_seg, uint32_t nq, 
             uint32_t* d_idx, double* d_dist, uint32_t* d_count);
 int check_edges_dev(gc_world* w, const double* d_c1, const double* d_c2, const double* d_c3, uint32_t n,
                     double min_distance, int mode, uint8_t* d_ok, int64_t* d_first_bad, uint64_t states_hint,
-                    cudaStream_t stream);
+                    cudaStream_t stream, const uint32_t* d_n = nullptr);
 int check_states_dev(gc_world* w, const double* d_q, uint32_t n, uint8_t* d_ok, cudaStream_t stream);
 double store_slack(const gc_store* s);
+int steer_launch(const gc_store* s, const double* d_q, const uint32_t* d_seg, const uint32_t* d_closest,
+                 const double* d_dist, uint32_t n, double max_distance, double* d_c1, double* d_c2, cudaStream_t st);
+int sample_informed_launch(int dim, uint32_t n, const double* d_lb, const double* d_ub, const double* d_f1,
+                           const double* d_f2, const double* d_cost, unsigned long long seed,
+                           unsigned long long first, double* d_out, cudaStream_t st);
+// floats between consecutive rows of the fp32 SoA (cap_total + the padding the scans read past the last tile)
+constexpr int kStoreRowPad = 1024;
+static inline size_t store_row_stride(const gc_store* s) { return s->cap_total + kStoreRowPad; }
+int refresh_store_mirror(gc_store* s);  // d_used -> used/live after device-side appends (synchronises)
 }  // namespace gc

@@ -23,7 +23,8 @@ constexpr int kScanThreads = 256;
 constexpr int kNodesPerThread = 4;
 constexpr int kTile = kScanThreads * kNodesPerThread;  // 1024 nodes per tile
 constexpr int kQT = 8;                                 // queries sharing one pass over a tile
-constexpr int kRowPad = kTile;                         // floats of padding after each SoA row
+constexpr int kRowPad = kStoreRowPad;                  // floats of padding after each SoA row
+static_assert(kRowPad == kTile, "the scans read one tile past the last row");
 constexpr uint32_t kSortMax = 16384;                   // single-CTA bitonic capacity
 
 __device__ __forceinline__ float u2f(uint32_t u) { return __uint_as_float(u); }
@@ -1592,8 +1593,23 @@ double store_slack(const gc_store* s)
   return GC_SCAN_SLACK_REL * sqrt((double)s->dim) * m;
 }
 
+int refresh_store_mirror(gc_store* s)
+{
+  GC_CUDA(cudaStreamSynchronize(s->stream));
+  std::vector<uint32_t> now(s->nseg);
+  GC_CUDA(cudaMemcpy(now.data(), s->d_used, sizeof(uint32_t) * s->nseg, cudaMemcpyDeviceToHost));
+  for (uint32_t g = 0; g < s->nseg; g++)
+  {
+    s->live[g] += now[g] - s->used[g];  // device-side appends never tombstone
+    s->used[g] = now[g];
+  }
+  return GC_OK;
+}
+
 static uint32_t max_used(const gc_store* s)
 {
+  if (s->used_bound)
+    return s->used_bound;
   uint32_t m = 0;
   for (uint32_t v : s->used)
     m = v > m ? v : m;

@@ -283,6 +283,38 @@ __global__ void sample_informed_kernel(InformedArgs a)
   if (a.attempts)
     a.attempts[i] = 101u;
 }
+// launchers for other translation units (gc_forest): everything stays on `st`, no synchronisation
+int steer_launch(const gc_store* s, const double* d_q, const uint32_t* d_seg, const uint32_t* d_closest,
+                 const double* d_dist, uint32_t n, double max_distance, double* d_c1, double* d_c2, cudaStream_t st)
+{
+  steer_kernel<<<(n + 127) / 128, 128, 0, st>>>(s->x64, d_q, d_seg, d_closest, d_dist, n, s->dim, s->cap_seg,
+                                                 max_distance, d_c1, d_c2);
+  GC_CUDA(cudaGetLastError());
+  count_launch();
+  return GC_OK;
+}
+
+int sample_informed_launch(int dim, uint32_t n, const double* d_lb, const double* d_ub, const double* d_f1,
+                           const double* d_f2, const double* d_cost, unsigned long long seed,
+                           unsigned long long first, double* d_out, cudaStream_t st)
+{
+  InformedArgs a{};
+  a.dim = dim;
+  a.n = n;
+  a.lb = d_lb;
+  a.ub = d_ub;
+  a.f1 = d_f1;
+  a.f2 = d_f2;
+  a.cost = d_cost;
+  a.seed = seed;
+  a.first = first;
+  a.out = d_out;
+  a.attempts = nullptr;
+  sample_informed_kernel<<<(n + 127) / 128, 128, 0, st>>>(a);
+  GC_CUDA(cudaGetLastError());
+  count_launch();
+  return GC_OK;
+}
 }  // namespace gc
 
 using namespace gc;

@@ -122,9 +122,13 @@ private:
 
 // =================================================================================================
 LockstepRRTStar::LockstepRRTStar(const SolverConfig& cfg, gc_world_t* world, int device, uint32_t nproblems,
-                                 const double* starts, const double* goals, uint32_t capacity_per_tree, int threads)
+                                 const double* starts, const double* goals, uint32_t capacity_per_tree, int threads,
+                                 bool device_trees)
   : cfg_(cfg), D_(cfg.dim), world_(world)
 {
+  if (const char* hr = std::getenv("GCB200_HOST_REPLAY"))
+    if (std::atoi(hr) != 0)
+      device_trees = false;
   if (const char* fb = std::getenv("GCB200_FIRST_BATCH"))
     first_batch_ = (size_t)std::max(1, std::atoi(fb));
   // TreeSolver::config (tree_solver.cpp:40-47)
@@ -132,7 +136,8 @@ LockstepRRTStar::LockstepRRTStar(const SolverConfig& cfg, gc_world_t* world, int
   if (utopia_tol_ <= 0.0)
     utopia_tol_ = 0.0;
   utopia_tol_ += 1.0;
-  if (gc_store_create(D_, capacity_per_tree, nproblems, device, &store_) != GC_OK)
+  // device trees: one spare, always empty segment absorbs the queries of problems that stopped improving
+  if (gc_store_create(D_, capacity_per_tree, nproblems + (device_trees ? 1u : 0u), device, &store_) != GC_OK)
   {
     err_ = gc_last_error();
     store_ = nullptr;
@@ -172,11 +177,61 @@ LockstepRRTStar::LockstepRRTStar(const SolverConfig& cfg, gc_world_t* world, int
     return;
   }
   stats_.gpu_calls++;
-  initialConnect();
+  if (initialConnect() < 0)
+    return;
+  if (device_trees)
+    createForest(starts, goals, capacity_per_tree);
+}
+
+// hands the trees as they stand after TreeSolver::setProblem to the device-resident forest
+int LockstepRRTStar::createForest(const double* starts, const double* goals, uint32_t capacity_per_tree)
+{
+  const uint32_t n = (uint32_t)P_.size();
+  gc_forest_config_t fc{};
+  fc.max_distance = cfg_.max_distance;
+  fc.min_distance = cfg_.min_distance;
+  fc.tolerance = TOLERANCE;
+  fc.rewire_factor = cfg_.rewire_factor;
+  fc.utopia_tolerance = utopia_tol_;
+  fc.near_cap = 512;
+  fc.edges_cap = std::max<uint32_t>(4096u, n * 48u);
+  fc.depth_cap = std::min<uint32_t>(capacity_per_tree, 1024u);
+  fc.first_batch = (uint32_t)first_batch_;
+  if (const char* v = std::getenv("GCB200_NEAR_CAP"))
+    fc.near_cap = (uint32_t)std::max(1, std::atoi(v));
+  if (const char* v = std::getenv("GCB200_EDGES_PER_PROBLEM"))
+    fc.edges_cap = std::max<uint32_t>(64u, n * (uint32_t)std::max(1, std::atoi(v)));
+  std::vector<uint32_t> first(n + 1, 0);
+  std::vector<int32_t> par, goal_slot(n);
+  std::vector<double> pc, path_cost(n);
+  std::vector<uint8_t> solved(n);
+  for (uint32_t p = 0; p < n; p++)
+  {
+    const Problem& pr = P_[p];
+    first[p + 1] = first[p] + pr.tree_size;
+    for (uint32_t sl = 0; sl < pr.tree_size; sl++)
+    {
+      const int32_t id = pr.id_of_slot[sl];
+      par.push_back(pr.parent[id] < 0 ? -1 : pr.slot_of_id[pr.parent[id]]);
+      pc.push_back(pr.pcost[id]);
+    }
+    goal_slot[p] = pr.slot_of_id[1];
+    solved[p] = pr.solved ? 1 : 0;
+    path_cost[p] = pr.path_cost;
+  }
+  if (gc_forest_create(store_, world_, &fc, cfg_.lb.data(), cfg_.ub.data(), n, starts, goals, first.data(), par.data(),
+                       pc.data(), goal_slot.data(), solved.data(), path_cost.data(), &forest_) != GC_OK)
+  {
+    forest_ = nullptr;
+    return fail("gc_forest_create") ? 0 : -1;
+  }
+  return 0;
 }
 
 LockstepRRTStar::~LockstepRRTStar()
 {
+  if (forest_)
+    gc_forest_destroy(forest_);
   if (store_)
     gc_store_destroy(store_);
 }
@@ -350,10 +405,120 @@ static inline double secs_since(std::chrono::steady_clock::time_point t0)
   return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
 }
 
+int LockstepRRTStar::stepInformed(uint64_t seed, uint64_t first_index)
+{
+  if (!forest_)
+  {
+    err_ = "stepInformed needs device trees";
+    return -1;
+  }
+  if (gc_forest_step(forest_, nullptr, nullptr, seed, first_index) != GC_OK)
+    return fail("gc_forest_step") ? 0 : -1;
+  return (int)P_.size();
+}
+
+int LockstepRRTStar::sync()
+{
+  if (!forest_)
+    return 0;
+  if (gc_forest_sync(forest_) != GC_OK)
+    return fail("gc_forest_sync") ? 0 : -1;
+  return 0;
+}
+
+int LockstepRRTStar::readCostsAsync(double* costs)
+{
+  if (!forest_)
+  {
+    err_ = "readCostsAsync needs device trees";
+    return -1;
+  }
+  if (gc_forest_read_costs_async(forest_, costs) != GC_OK)
+    return fail("gc_forest_read_costs_async") ? 0 : -1;
+  return 0;
+}
+
+// accessors: the host mirror, or the forest's snapshot (synchronises when steps are in flight)
+bool LockstepRRTStar::solved(uint32_t p) const
+{
+  if (!forest_)
+    return P_[p].solved;
+  int32_t v = 0;
+  gc_forest_info(forest_, p, &v, nullptr, nullptr, nullptr, nullptr, nullptr);
+  return v != 0;
+}
+bool LockstepRRTStar::canImprove(uint32_t p) const
+{
+  if (!forest_)
+    return P_[p].can_improve;
+  int32_t v = 0;
+  gc_forest_info(forest_, p, nullptr, &v, nullptr, nullptr, nullptr, nullptr);
+  return v != 0;
+}
+double LockstepRRTStar::cost(uint32_t p) const
+{
+  if (!forest_)
+    return P_[p].cost;
+  double v = 0;
+  gc_forest_info(forest_, p, nullptr, nullptr, &v, nullptr, nullptr, nullptr);
+  return v;
+}
+double LockstepRRTStar::radius(uint32_t p) const
+{
+  if (!forest_)
+    return P_[p].r_rewire;
+  double v = 0;
+  gc_forest_info(forest_, p, nullptr, nullptr, nullptr, &v, nullptr, nullptr);
+  return v;
+}
+uint32_t LockstepRRTStar::numNodes(uint32_t p) const
+{
+  if (!forest_)
+    return (uint32_t)P_[p].parent.size();
+  uint32_t v = 0;
+  gc_forest_info(forest_, p, nullptr, nullptr, nullptr, nullptr, &v, nullptr);
+  return v;
+}
+uint32_t LockstepRRTStar::treeSize(uint32_t p) const
+{
+  if (!forest_)
+    return P_[p].tree_size;
+  uint32_t v = 0;
+  gc_forest_info(forest_, p, nullptr, nullptr, nullptr, nullptr, nullptr, &v);
+  return v;
+}
+const StepStats& LockstepRRTStar::stats() const
+{
+  if (forest_)
+  {
+    uint64_t o[16] = {};
+    gc_forest_stats(forest_, o);
+    stats_.iterations = o[0];
+    stats_.extended = o[1];
+    stats_.edges_device = o[2];
+    stats_.edges_used = o[3];
+    stats_.edges_fallback = o[4];
+    stats_.near_hits = o[5];
+  }
+  return stats_;
+}
+
 int LockstepRRTStar::stepImpl(const double* samples, const double* d_samples)
 {
   if (!store_)
     return -1;
+  if (forest_)
+  {
+    // device trees: everything is enqueued on the store's stream; nothing comes back here
+    if (gc_forest_step(forest_, samples, d_samples, 0, 0) != GC_OK)
+      return fail("gc_forest_step") ? 0 : -1;
+    stats_.gpu_calls++;
+    if (samples)
+      stats_.h2d_bytes += sizeof(double) * (uint64_t)P_.size() * D_;
+    stats_.h2d_bytes += sizeof(double) * (uint64_t)P_.size();           // rewire-radius factors
+    stats_.d2h_bytes += (sizeof(double) + 1) * (uint64_t)P_.size();     // path costs + changed flags
+    return (int)P_.size();
+  }
   auto tp = std::chrono::steady_clock::now();
   const uint32_t n = (uint32_t)P_.size();
   // ---- A: RRTStar::update prologue (rrt_star.cpp:93-108) ----------------------------------------
@@ -832,6 +997,11 @@ int LockstepRRTStar::stepImpl(const double* samples, const double* d_samples)
 
 void LockstepRRTStar::dump(uint32_t p, int32_t* parents, double* pcost, double* conf) const
 {
+  if (forest_)
+  {
+    gc_forest_dump(forest_, p, parents, pcost, conf);
+    return;
+  }
   const Problem& pr = P_[p];
   const size_t n = pr.parent.size();
   std::memcpy(parents, pr.parent.data(), sizeof(int32_t) * n);
@@ -842,6 +1012,16 @@ void LockstepRRTStar::dump(uint32_t p, int32_t* parents, double* pcost, double* 
 std::vector<int32_t> LockstepRRTStar::solution(uint32_t p) const
 {
   std::vector<int32_t> out;
+  if (forest_)
+  {
+    out.resize(1);
+    const int n = gc_forest_solution(forest_, p, out.data(), 1);
+    if (n <= 0)
+      return std::vector<int32_t>();
+    out.resize((size_t)n);
+    gc_forest_solution(forest_, p, out.data(), (uint32_t)n);
+    return out;
+  }
   if (!P_[p].solved)
     return out;
   out.push_back(0);
@@ -871,6 +1051,45 @@ int gcp_rrtstar_create(int dim, double max_distance, double min_distance, double
                        uint32_t nproblems, const double* starts, const double* goals, uint32_t capacity_per_tree,
                        int threads, gcp_rrtstar_t** out)
 {
+  return gcp_rrtstar_create2(dim, max_distance, min_distance, rewire_factor, utopia_tolerance, lb, ub, world, device,
+                             nproblems, starts, goals, capacity_per_tree, threads, 1, out);
+}
+
+int gcp_rrtstar_step_informed(gcp_rrtstar_t* s, uint64_t seed, uint64_t first_index)
+{
+  if (!s)
+    return GC_E_INVALID;
+  const int rc = s->impl->stepInformed(seed, first_index);
+  if (rc < 0)
+    g_perr = s->impl->error();
+  return rc;
+}
+
+int gcp_rrtstar_sync(gcp_rrtstar_t* s)
+{
+  if (!s)
+    return GC_E_INVALID;
+  const int rc = s->impl->sync();
+  if (rc < 0)
+    g_perr = s->impl->error();
+  return rc;
+}
+
+int gcp_rrtstar_read_costs_async(gcp_rrtstar_t* s, double* costs)
+{
+  if (!s || !costs)
+    return GC_E_INVALID;
+  const int rc = s->impl->readCostsAsync(costs);
+  if (rc < 0)
+    g_perr = s->impl->error();
+  return rc;
+}
+
+int gcp_rrtstar_create2(int dim, double max_distance, double min_distance, double rewire_factor,
+                        double utopia_tolerance, const double* lb, const double* ub, gc_world_t* world, int device,
+                        uint32_t nproblems, const double* starts, const double* goals, uint32_t capacity_per_tree,
+                        int threads, int device_trees, gcp_rrtstar_t** out)
+{
   if (!out || !lb || !ub || !world || !starts || !goals || nproblems == 0 || dim < 1 || dim > GC_MAX_DIM)
   {
     g_perr = "gcp_rrtstar_create: invalid argument";
@@ -887,7 +1106,8 @@ int gcp_rrtstar_create(int dim, double max_distance, double min_distance, double
   if (threads <= 0)
     threads = (int)std::max(1u, std::thread::hardware_concurrency());
   gcp_rrtstar* s = new gcp_rrtstar();
-  s->impl.reset(new LockstepRRTStar(cfg, world, device, nproblems, starts, goals, capacity_per_tree, threads));
+  s->impl.reset(new LockstepRRTStar(cfg, world, device, nproblems, starts, goals, capacity_per_tree, threads,
+                                    device_trees != 0));
   if (s->impl->error()[0] != 0)
   {
     g_perr = s->impl->error();
@@ -952,6 +1172,11 @@ int gcp_rrtstar_run(gcp_rrtstar_t* s, const double* samples, uint32_t n)
     total += rc;
     if (rc == 0)
       break;
+  }
+  if (s->impl->deviceTrees() && s->impl->sync() < 0)
+  {
+    g_perr = s->impl->error();
+    return GC_E_CAPACITY;
   }
   return (int)std::min<long>(total, 0x7fffffff);
 }

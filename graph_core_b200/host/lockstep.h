@@ -59,8 +59,11 @@ class ThreadPool;
 class LockstepRRTStar
 {
 public:
+  // device_trees (default): parent slots and connection costs live on the GPU (gc_forest, include/gcb200.h) and a
+  // step is one stream-ordered sequence of launches without a host round trip; accessors synchronise on demand.
+  // device_trees = false keeps the host replay of round 1 (the same trees; used by the tests as a cross-check).
   LockstepRRTStar(const SolverConfig& cfg, gc_world_t* world, int device, uint32_t nproblems, const double* starts,
-                  const double* goals, uint32_t capacity_per_tree, int threads);
+                  const double* goals, uint32_t capacity_per_tree, int threads, bool device_trees = true);
   ~LockstepRRTStar();
 
   // one RRTStar::update per still-improvable problem; samples is [nproblems][dim] (row p is used when
@@ -68,21 +71,29 @@ public:
   int step(const double* samples);
   // same, with the [nproblems][dim] sample block resident in device memory (e.g. written by the Philox sampler)
   int stepDeviceSamples(const double* d_samples);
+  // device trees only: the sample of problem p comes from the device informed sampler (InformedSampler::sample with the
+  // problem's current path cost; Philox key `seed`, counter first_index + p) -- rrt_star.cpp:147-161
+  int stepInformed(uint64_t seed, uint64_t first_index);
+  // device trees only: wait for the enqueued steps; <0 when a capacity was exceeded (error() says which)
+  int sync();
+  // device trees only: enqueue a D2H copy of the nproblems current path costs into `costs` (pinned memory)
+  int readCostsAsync(double* costs);
+  bool deviceTrees() const { return forest_ != nullptr; }
   // run the store's kernels on an externally owned cudaStream_t (the world keeps its own setting)
   int setStream(void* cuda_stream);
   const char* error() const { return err_.c_str(); }
 
   uint32_t size() const { return (uint32_t)P_.size(); }
-  bool solved(uint32_t p) const { return P_[p].solved; }
-  bool canImprove(uint32_t p) const { return P_[p].can_improve; }
-  double cost(uint32_t p) const { return P_[p].cost; }
-  double radius(uint32_t p) const { return P_[p].r_rewire; }
-  uint32_t numNodes(uint32_t p) const { return (uint32_t)P_[p].parent.size(); }
-  uint32_t treeSize(uint32_t p) const { return P_[p].tree_size; }
+  bool solved(uint32_t p) const;
+  bool canImprove(uint32_t p) const;
+  double cost(uint32_t p) const;
+  double radius(uint32_t p) const;
+  uint32_t numNodes(uint32_t p) const;
+  uint32_t treeSize(uint32_t p) const;
   // ids follow the reference's creation order: 0 start, 1 goal, 2.. new nodes
   void dump(uint32_t p, int32_t* parents, double* pcost, double* conf) const;
   std::vector<int32_t> solution(uint32_t p) const;
-  const StepStats& stats() const { return stats_; }
+  const StepStats& stats() const;
   gc_store_t* store() { return store_; }
   // informed-sampler parameters of problem p (cost = inf until solved)
   double pathCost(uint32_t p) const { return P_[p].path_cost; }
@@ -133,6 +144,7 @@ private:
   void makeSolution(Problem& pr);
   double solutionCost(const Problem& pr) const;
   int initialConnect();
+  int createForest(const double* starts, const double* goals, uint32_t capacity_per_tree);
   int addNode(Problem& pr, const double* conf);  // host mirror only; returns id
   bool fail(const char* what);
 
@@ -141,9 +153,10 @@ private:
   int D_;
   gc_world_t* world_;
   gc_store_t* store_ = nullptr;
+  gc_forest_t* forest_ = nullptr;
   std::vector<Problem> P_;
   std::unique_ptr<ThreadPool> pool_;
-  StepStats stats_;
+  mutable StepStats stats_;
   std::string err_;
   double utopia_tol_;
   // batched buffers
@@ -165,6 +178,13 @@ int gcp_rrtstar_create(int dim, double max_distance, double min_distance, double
 int gcp_rrtstar_destroy(gcp_rrtstar_t* s);
 int gcp_rrtstar_step(gcp_rrtstar_t* s, const double* samples);
 int gcp_rrtstar_step_dsamples(gcp_rrtstar_t* s, const double* d_samples);
+int gcp_rrtstar_step_informed(gcp_rrtstar_t* s, uint64_t seed, uint64_t first_index);
+int gcp_rrtstar_sync(gcp_rrtstar_t* s);
+int gcp_rrtstar_read_costs_async(gcp_rrtstar_t* s, double* costs);
+int gcp_rrtstar_create2(int dim, double max_distance, double min_distance, double rewire_factor,
+                        double utopia_tolerance, const double* lb, const double* ub, gc_world_t* world, int device,
+                        uint32_t nproblems, const double* starts, const double* goals, uint32_t capacity_per_tree,
+                        int threads, int device_trees, gcp_rrtstar_t** out);
 int gcp_rrtstar_set_stream(gcp_rrtstar_t* s, void* cuda_stream);
 // runs n lock-step iterations; samples is [n][nproblems][dim]
 int gcp_rrtstar_run(gcp_rrtstar_t* s, const double* samples, uint32_t n);

@@ -34,6 +34,11 @@ def load_host():
     sig = {
         "gcp_rrtstar_create": (C.c_int, [C.c_int, C.c_double, C.c_double, C.c_double, C.c_double, _dp, _dp, vp, C.c_int,
                                          C.c_uint32, _dp, _dp, C.c_uint32, C.c_int, C.POINTER(vp)]),
+        "gcp_rrtstar_create2": (C.c_int, [C.c_int, C.c_double, C.c_double, C.c_double, C.c_double, _dp, _dp, vp, C.c_int,
+                                          C.c_uint32, _dp, _dp, C.c_uint32, C.c_int, C.c_int, C.POINTER(vp)]),
+        "gcp_rrtstar_step_informed": (C.c_int, [vp, C.c_uint64, C.c_uint64]),
+        "gcp_rrtstar_sync": (C.c_int, [vp]),
+        "gcp_rrtstar_read_costs_async": (C.c_int, [vp, vp]),
         "gcp_rrtstar_destroy": (C.c_int, [vp]),
         "gcp_rrtstar_step": (C.c_int, [vp, _dp]),
         "gcp_rrtstar_step_dsamples": (C.c_int, [vp, vp]),
@@ -59,10 +64,13 @@ def _f64(a, shape=None):
 
 
 class LockstepRRTStar:
-    """P independent RRT* problems sharing one collision world, advanced in lock step."""
+    """P independent RRT* problems sharing one collision world, advanced in lock step.
+
+    device_trees=True (default): parent slots and connection costs live on the GPU (gc_forest); `step*` only enqueue
+    work on the stream and the accessors synchronise on demand.  device_trees=False: the host replay of round 1."""
 
     def __init__(self, scenario, world: capi.CollisionWorld, starts, goals, capacity: int = 16384, device: int = 0,
-                 threads: int = 0):
+                 threads: int = 0, device_trees: bool = True):
         self.L = load_host()
         self.dim = scenario.dim
         self.max_distance = float(scenario.max_distance)
@@ -73,10 +81,11 @@ class LockstepRRTStar:
         self.n = starts.shape[0]
         lb, ub = _f64(scenario.lb), _f64(scenario.ub)
         h = C.c_void_p()
-        rc = self.L.gcp_rrtstar_create(self.dim, scenario.max_distance, scenario.min_distance, scenario.rewire_factor,
-                                       scenario.utopia_tolerance, lb.ctypes.data_as(_dp), ub.ctypes.data_as(_dp),
-                                       world.handle, device, self.n, starts.ctypes.data_as(_dp),
-                                       goals.ctypes.data_as(_dp), capacity, threads, C.byref(h))
+        rc = self.L.gcp_rrtstar_create2(self.dim, scenario.max_distance, scenario.min_distance, scenario.rewire_factor,
+                                        scenario.utopia_tolerance, lb.ctypes.data_as(_dp), ub.ctypes.data_as(_dp),
+                                        world.handle, device, self.n, starts.ctypes.data_as(_dp),
+                                        goals.ctypes.data_as(_dp), capacity, threads, 1 if device_trees else 0,
+                                        C.byref(h))
         if rc != 0:
             raise capi.GcError(rc, self.L.gcp_last_error().decode())
         self.h = h
@@ -105,6 +114,24 @@ class LockstepRRTStar:
         if rc < 0:
             raise capi.GcError(rc, self.L.gcp_last_error().decode())
         return rc
+
+    def step_informed(self, seed: int, first_index: int) -> int:
+        """One iteration whose samples come from the device informed sampler (problem p: Philox counter first_index+p)."""
+        rc = self.L.gcp_rrtstar_step_informed(self.h, seed, first_index)
+        if rc < 0:
+            raise capi.GcError(rc, self.L.gcp_last_error().decode())
+        return rc
+
+    def sync(self):
+        rc = self.L.gcp_rrtstar_sync(self.h)
+        if rc < 0:
+            raise capi.GcError(rc, self.L.gcp_last_error().decode())
+
+    def read_costs_async(self, pinned_ptr: int):
+        """Enqueue a D2H copy of the P current path costs into pinned host memory at `pinned_ptr`."""
+        rc = self.L.gcp_rrtstar_read_costs_async(self.h, C.c_void_p(pinned_ptr))
+        if rc < 0:
+            raise capi.GcError(rc, self.L.gcp_last_error().decode())
 
     def set_stream(self, cuda_stream: int | None):
         rc = self.L.gcp_rrtstar_set_stream(self.h, C.c_void_p(capi.stream_handle(cuda_stream)))

@@ -174,6 +174,58 @@ int gc_extend_batch_dsamples(gc_store_t* s, gc_world_t* w, const double* d_sampl
                              double* dist, double* next, uint8_t* ok, uint32_t* near_idx, double* near_dist,
                              uint32_t* near_count);
 
+/* ---- device-resident lock-step RRT* trees (parent index + cost-to-come on the GPU) ----------
+ * A forest advances P independent RRT* problems, problem p owning segment p of `store` (which must have P + 1
+ * segments: the last one stays empty and absorbs the queries of inactive problems).  One gc_forest_step is one
+ * RRTStar::update (src/graph_core/solvers/rrt_star.cpp:89-163) of every still-improvable problem and runs entirely
+ * stream-ordered on the store's stream: nearest -> steer -> extension edge -> radius-near -> Tree::rewireOnly
+ * (src/graph_core/graph/tree.cpp:381-513: parent phase in cost order in two edge batches, children phase replayed in
+ * near order with Tree::costToNode walks, :767-789) -> goal connection / solution update.  Parent slots and
+ * connection costs live in device memory; the call returns without synchronising.  The only host work per step is a
+ * stream-ordered callback that evaluates RRTStar::updateRewireRadius' pow() terms (rrt_star.cpp:278-286,
+ * informed_sampler.cpp:181-215) with the host libm for the problems whose path cost changed, so radii are bit-identical
+ * to the reference's. */
+typedef struct gc_forest gc_forest_t;
+typedef struct gc_forest_config
+{
+  double max_distance;     /* tree_solver.cpp:37 */
+  double min_distance;     /* checker resolution */
+  double tolerance;        /* util.h:80 TOLERANCE */
+  double rewire_factor;    /* rrt_star.cpp:46 */
+  double utopia_tolerance; /* tree_solver.cpp:40-47, ALREADY 1 + the parameter */
+  uint32_t near_cap;       /* longest radius-near list (entries); overflow is reported by gc_forest_sync */
+  uint32_t edges_cap;      /* rewiring edges of one step over all problems (second batch) */
+  uint32_t depth_cap;      /* longest solution path kept verbatim (nodes) */
+  uint32_t first_batch;    /* parent candidates per problem in the first edge batch (0 = 3) */
+} gc_forest_config_t;
+/* Trees as they stand after TreeSolver::setProblem: problem p has nodes [node_first[p], node_first[p+1]) = its store
+ * slots 0.., with parent slot (-1 for the root) and connection cost each; goal_slot[p] = slot of the goal node or -1
+ * while it is not in the tree; solved/path_cost as the solver holds them (path_cost = +inf when unsolved). */
+int gc_forest_create(gc_store_t* store, gc_world_t* world, const gc_forest_config_t* cfg, const double* lb,
+                     const double* ub, uint32_t nproblems, const double* starts, const double* goals,
+                     const uint32_t* node_first, const int32_t* node_parent, const double* node_pcost,
+                     const int32_t* goal_slot, const uint8_t* solved, const double* path_cost, gc_forest_t** out);
+int gc_forest_destroy(gc_forest_t* f);
+/* one lock-step iteration; exactly one sample source: host samples [P][dim] (copied H2D on the stream; a pinned buffer
+ * must stay untouched until the next gc_forest_sync), d_samples (device) or, both NULL, the forest's own informed
+ * sampler (InformedSampler::sample per problem with its current path cost; Philox key `seed`, counter
+ * first_index + p).  Does not synchronise. */
+int gc_forest_step(gc_forest_t* f, const double* samples, const double* d_samples, uint64_t seed, uint64_t first_index);
+/* enqueues a D2H copy of the P current costs (path cost + goal cost, +inf when unsolved) into `costs` (pinned) */
+int gc_forest_read_costs_async(gc_forest_t* f, double* costs);
+/* waits for the stream; GC_E_CAPACITY (message in gc_last_error) when a near list, the edge list or a segment
+ * overflowed since the last call -- the trees are then no longer the reference's */
+int gc_forest_sync(gc_forest_t* f);
+/* out[0..9]: iterations, extended, edges_device, edges_used, speculation misses, near hits, steps, problems still
+ * improvable, problems solved, host-callback radius updates */
+int gc_forest_stats(gc_forest_t* f, uint64_t out[16]);
+int gc_forest_info(gc_forest_t* f, uint32_t p, int32_t* solved, int32_t* can_improve, double* cost, double* radius,
+                   uint32_t* num_nodes, uint32_t* tree_size);
+/* ids follow the reference's creation order: 0 start, 1 goal, 2.. new nodes; arrays sized num_nodes */
+int gc_forest_dump(gc_forest_t* f, uint32_t p, int32_t* parents, double* pcost, double* conf);
+/* node ids root -> goal of the current solution (0 when unsolved); returns the length */
+int gc_forest_solution(gc_forest_t* f, uint32_t p, int32_t* ids, uint32_t cap);
+
 /* ---- Philox samplers (uniform_sampler.cpp:34-39, informed_sampler.cpp:145-180) -------------- */
 /* n uniform samples in [lb, ub]; sample i uses Philox counter (first_index + i) */
 int gc_sample_uniform(int device, int dim, const double* lb, const double* ub, uint64_t seed, uint64_t first_index,

@@ -10,11 +10,12 @@ from graph_core_b200 import worlds as W
 pytestmark = pytest.mark.gpu
 
 
-def _run_both(gc, orc, sc, starts, goals, iters, seed, use_kdtree=True, threads=4):
+def _run_both(gc, orc, sc, starts, goals, iters, seed, use_kdtree=True, threads=4, device_trees=True):
     from graph_core_b200.planner import LockstepRRTStar
     P = len(starts)
     gw = sc.make_world()
-    lock = LockstepRRTStar(sc, gw, starts, goals, capacity=max(4096, iters + 64), threads=threads)
+    lock = LockstepRRTStar(sc, gw, starts, goals, capacity=max(4096, iters + 64), threads=threads,
+                           device_trees=device_trees)
     samples = np.stack([W.uniform_samples(sc.lb, sc.ub, seed + p, 0, iters) for p in range(P)], axis=1)
     lock.run(samples)
     ow = orc.OracleWorld.from_scenario(sc)
@@ -37,28 +38,34 @@ def _run_both(gc, orc, sc, starts, goals, iters, seed, use_kdtree=True, threads=
     return lock, st
 
 
-def test_rrtstar_reference_scene_c0(gc, orc):
+TREES = pytest.mark.parametrize("device_trees", [True, False], ids=["device_trees", "host_replay"])
+
+
+@TREES
+def test_rrtstar_reference_scene_c0(gc, orc, device_trees):
     sc = W.scenario_c0()
-    lock, st = _run_both(gc, orc, sc, sc.start[None, :], sc.goal[None, :], 1500, seed=1)
+    lock, st = _run_both(gc, orc, sc, sc.start[None, :], sc.goal[None, :], 1500, seed=1, device_trees=device_trees)
     assert lock.info(0)["solved"]
 
 
-def test_rrtstar_c1_boxes_many_problems(gc, orc):
+@TREES
+def test_rrtstar_c1_boxes_many_problems(gc, orc, device_trees):
     sc = W.scenario_c1()
     ow = orc.OracleWorld.from_scenario(sc)
     cand = W.uniform_samples(sc.lb, sc.ub, 77, 0, 64)
     cand = cand[ow.check(cand).astype(bool)]
     starts, goals = cand[:6], cand[6:12]
-    lock, st = _run_both(gc, orc, sc, starts, goals, 1200, seed=300, use_kdtree=False)
+    lock, st = _run_both(gc, orc, sc, starts, goals, 1200, seed=300, use_kdtree=False, device_trees=device_trees)
     assert sum(lock.info(p)["solved"] for p in range(6)) >= 4
 
 
-def test_rrtstar_c3_arm(gc, orc, c3):
+@TREES
+def test_rrtstar_c3_arm(gc, orc, c3, device_trees):
     from graph_core_b200 import worlds
     pairs = worlds.c3_problems(orc.arm_checker(), c3.params, 3)
     starts = np.array([s for s, _ in pairs])
     goals = np.array([g for _, g in pairs])
-    lock, st = _run_both(gc, orc, c3, starts, goals, 700, seed=3020)
+    lock, st = _run_both(gc, orc, c3, starts, goals, 700, seed=3020, device_trees=device_trees)
     assert st["extended"] > 100
 
 
@@ -67,6 +74,6 @@ def test_rrtstar_direct_connection_and_thread_counts(gc, orc):
     sc = W.scenario_c0()
     starts = np.array([[1.5, 1.5, 1.5], [-1.5, -1.5, -1.5]])
     goals = np.array([[2.2, 1.2, 2.0], [1.5, 1.5, 1.5]])
-    for threads in (1, 3):
-        lock, st = _run_both(gc, orc, sc, starts, goals, 300, seed=9, threads=threads)
+    for threads, device_trees in ((1, False), (3, False), (1, True)):
+        lock, st = _run_both(gc, orc, sc, starts, goals, 300, seed=9, threads=threads, device_trees=device_trees)
         assert lock.info(0)["solved"] and not lock.info(0)["can_improve"]
