@@ -892,6 +892,12 @@ struct ArmArgs
   uint32_t lanes;  // lane mode: lanes per state (1, 2, 4, 8)
   uint32_t* work_ctr;  // items handed out so far beyond the first one of every group (zeroed before the launch)
   const uint32_t* n_dev;  // optional: edge count in device memory (<= n; n stays the stride of offs)
+  // grid culling (arm_grid_kernel)
+  const uint32_t* gstart;
+  const uint16_t* gitems;
+  float glo[3];
+  float ginv;
+  int gn[3];
 };
 
 template <int D>
@@ -914,7 +920,7 @@ __device__ __forceinline__ ArmSmem arm_stage(const ArmArgs& a, unsigned char* sm
   float4* sblk = reinterpret_cast<float4*>(sna + npad);
   float* sbna = reinterpret_cast<float*>(sblk + nbp);
   float* sarm = sbna + nbp;
-  const uint32_t arm_words = 12u + 12u * a.njoints + 4u * a.nrs + a.nrs;
+  const uint32_t arm_words = 12u + 12u * a.njoints + 4u * a.nrs + a.nrs + (uint32_t)a.njoints + 2u;
   for (uint32_t i = threadIdx.x; i < npad; i += blockDim.x)
   {
     float4 ob = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
@@ -1104,6 +1110,173 @@ __global__ void __launch_bounds__(G == 1 ? 128 : 256, G == 1 ? (NRS <= 16 ? 4 : 
   }
 }
 
+// ---- grid culling ---------------------------------------------------------------------------------------------
+// A uniform grid covers the part of the workspace where a robot sphere can touch an obstacle.  Cell -> the obstacles o
+// with dist(o, cell box, slightly inflated) < rs_max + r_o + m, m = 2^-8 E (the margin of the block culling below,
+// arm_grid_build states the argument).  A sphere tests only the list of the cell its centre falls in: every other
+// obstacle is at least rs + r_o + m away, so the spec'd fp32 pair test (within d = m^2/16 of the exact value) would
+// call it "apart" as well and the verdict equals the brute-force one.  One thread per state: the FK chain runs once,
+// each of the 16 spheres costs a cell look-up and a handful of pair tests (C3: ~22 per state instead of 16 000).
+// The robot spheres are stored sorted by link (arm image: ... | rs_link | first sphere of every link), so the
+// chain visits them without a 16-way unrolled match.
+template <int J>
+__device__ __forceinline__ bool arm_check_grid(const ArmSmem& w, const ArmArgs& a, const float* qf,
+                                               unsigned long long& pairs)
+{
+  float AR[9], At[3], BR[9];
+#pragma unroll
+  for (int i = 0; i < 9; i++)
+    AR[i] = w.base[i];
+#pragma unroll
+  for (int i = 0; i < 3; i++)
+    At[i] = w.base[9 + i];
+  const int* lfirst = w.rs_link + a.nrs;  // [J + 2]
+  const float4* loc4 = reinterpret_cast<const float4*>(w.rs_local);
+  bool hit = false;
+  uint32_t done = 0;
+#pragma unroll
+  for (int j = 0; j <= J; j++)
+  {
+    if (j < J)
+      fk_joint(AR, At, BR, qf[j < J ? j : 0], nullptr);
+    else
+    {
+#pragma unroll
+      for (int i = 0; i < 9; i++)
+        BR[i] = AR[i];
+    }
+    const int k1 = lfirst[j + 1];
+#pragma unroll 1
+    for (int k = lfirst[j]; k < k1; k++)
+    {
+      const float4 loc = loc4[k];
+      float o[3];
+      mat3_vec(BR, At, loc.x, loc.y, loc.z, o);
+      const float fx = __fmul_rn(__fsub_rn(o[0], a.glo[0]), a.ginv);
+      const float fy = __fmul_rn(__fsub_rn(o[1], a.glo[1]), a.ginv);
+      const float fz = __fmul_rn(__fsub_rn(o[2], a.glo[2]), a.ginv);
+      // outside the grid (or NaN): no obstacle within reach of this sphere
+      if (!(fx >= 0.0f && fy >= 0.0f && fz >= 0.0f && fx < (float)a.gn[0] && fy < (float)a.gn[1] && fz < (float)a.gn[2]))
+        continue;
+      const uint32_t cell = ((uint32_t)fx * (uint32_t)a.gn[1] + (uint32_t)fy) * (uint32_t)a.gn[2] + (uint32_t)fz;
+      const uint32_t i0 = __ldg(a.gstart + cell), i1 = __ldg(a.gstart + cell + 1);
+      if (i0 == i1)
+        continue;
+      const SphereK sk = sphere_consts(o[0], o[1], o[2], loc.w);
+      for (uint32_t i = i0; i < i1; i++)
+      {
+        const uint32_t idx = __ldg(a.gitems + i);
+        hit |= pair_hit(w.obs[idx], w.obs_na[idx], sk);
+      }
+      done += i1 - i0;
+    }
+    if (j < J)
+      fk_advance(AR, At, BR, w.joint + 12 * j);
+  }
+  pairs += done;
+  return hit;
+}
+
+// one thread per (edge, state) item of the pass-major list; a warp takes 32 consecutive items at a time (one atomic
+// per warp), so the lanes of a warp work on neighbouring edges and their offset look-ups share cache lines
+template <int D>
+__global__ void __launch_bounds__(128) arm_grid_kernel(ArmArgs a)
+{
+  const int MODE = a.mode;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const ArmSmem w = arm_stage(a, smem_raw);
+  const uint32_t lane = threadIdx.x & 31;
+  const uint32_t n_act = a.n_dev ? min(*a.n_dev, a.n) : a.n;
+  uint32_t pbase[kPasses + 1];
+  pbase[0] = 0;
+#pragma unroll
+  for (int p = 0; p < kPasses; p++)
+    pbase[p + 1] = pbase[p] + ((MODE == 3) ? 0u : a.offs[(size_t)p * (a.n + 1) + n_act]);
+  const uint32_t total = (MODE == 3) ? n_act : pbase[kPasses];
+  unsigned long long states = 0, pairs = 0;
+  const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
+  uint32_t tb = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * 32u;  // first item of this warp's batch
+  while (tb < total)
+  {
+    uint32_t nb = 0;
+    if (lane == 0)
+      nb = atomicAdd(a.work_ctr, 32u);
+    const uint32_t t = tb + lane;
+    bool have = t < total;
+    uint32_t e = 0, s = 0;
+    if (have && MODE != 3)
+    {
+      const int p = (t >= pbase[1]) + (t >= pbase[2]) + (t >= pbase[3]);
+      const uint32_t* offs_p = a.offs + (size_t)p * (a.n + 1);
+      const uint32_t tp = t - pbase[p];
+      e = find_edge(offs_p, n_act, tp);
+      s = pass_lo(p) + (tp - offs_p[e]);
+      if (MODE == GC_EDGE_LINEAR)
+        have = !(*reinterpret_cast<volatile unsigned long long*>(a.first_bad + e) < (unsigned long long)s);
+      else
+        have = (*reinterpret_cast<volatile uint8_t*>(a.ok + e) == 1);
+    }
+    if (have)
+    {
+      float qf[D];
+      double conf[D];
+      if (MODE == 3)
+      {
+        e = t;
+#pragma unroll
+        for (int d = 0; d < D; d++)
+          conf[d] = a.c1[(size_t)t * D + d];
+      }
+      else
+      {
+        double c1[D], c2[D], c3[D];
+#pragma unroll
+        for (int d = 0; d < D; d++)
+        {
+          c1[d] = a.c1[(size_t)e * D + d];
+          c2[d] = a.c2[(size_t)e * D + d];
+          c3[d] = (MODE == GC_EDGE_FROM_CONF) ? a.c3[(size_t)e * D + d] : 0.0;
+        }
+        EdgeGeom g;
+        g.dist = a.dist[e];
+        g.aux = a.aux[e];
+        g.nstates = a.nst[e];
+        have = state_conf_rt<D>(MODE, c1, c2, c3, g, s, conf);
+      }
+      if (have)
+      {
+#pragma unroll
+        for (int d = 0; d < D; d++)
+          qf[d] = (float)conf[d];
+        const bool hit = arm_check_grid<D>(w, a, qf, pairs);
+        states++;
+        if (MODE == 3)
+          a.ok[e] = hit ? 0 : 1;
+        else if (hit)
+        {
+          a.ok[e] = 0;
+          if (MODE == GC_EDGE_LINEAR && a.first_bad)
+            atomicMin(&a.first_bad[e], (unsigned long long)s);
+        }
+      }
+    }
+    nb = __shfl_sync(0xffffffffu, nb, 0);
+    tb = (nb < 0xFFFFFFFFu - warps * 32u - 64u) ? warps * 32u + nb : 0xFFFFFFFFu;
+  }
+  for (int o = 16; o > 0; o >>= 1)
+  {
+    states += __shfl_down_sync(0xffffffffu, states, o);
+    pairs += __shfl_down_sync(0xffffffffu, pairs, o);
+  }
+  if (lane == 0 && a.counters)
+  {
+    if (states)
+      atomicAdd(&a.counters[0], states);
+    if (pairs)
+      atomicAdd(&a.counters[1], pairs);
+  }
+}
+
 // =================================================================================================
 //  launchers
 // =================================================================================================
@@ -1170,11 +1343,42 @@ static int launch_light(gc_world* w, const LightArgs& a, cudaStream_t st)
   return GC_OK;
 }
 
+static size_t arm_smem_bytes(const ArmArgs& a)
+{
+  const size_t npad_l = arm_padded_obstacles(a.nobs);
+  return (sizeof(float4) + sizeof(float)) * (npad_l + (a.nblk ? npad_l / 16 : 0)) +
+         sizeof(float) * (12 + 12 * a.njoints + 5 * a.nrs + a.njoints + 2) + 16;
+}
+
+// grid mode: one thread per state
+template <int D>
+static int launch_arm_grid(gc_world* w, const ArmArgs& a, uint64_t items_hint, cudaStream_t st)
+{
+  const size_t smem = arm_smem_bytes(a);
+  if (smem > 200 * 1024)
+  {
+    gc::set_error("obstacle cloud too large for shared memory staging (%zu bytes)", smem);
+    return GC_E_UNSUPPORTED;
+  }
+  if (smem > 48 * 1024)
+    GC_CUDA(cudaFuncSetAttribute(arm_grid_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  uint64_t blocks = (items_hint + 127) / 128;
+  const uint64_t max_blocks = (uint64_t)w->sms * 8;
+  if (blocks > max_blocks)
+    blocks = max_blocks;
+  if (blocks < 1)
+    blocks = 1;
+  arm_grid_kernel<D><<<(unsigned)blocks, 128, smem, st>>>(a);
+  GC_CUDA(cudaGetLastError());
+  count_launch();
+  return GC_OK;
+}
+
 template <int D, int NRS, int G>
 static int launch_arm(gc_world* w, const ArmArgs& a, uint64_t items_hint, cudaStream_t st)
 {
   const size_t npad_l = arm_padded_obstacles(a.nobs);
-  const size_t smem = (sizeof(float4) + sizeof(float)) * (npad_l + (a.nblk ? npad_l / 16 : 0)) + sizeof(float) * (12 + 12 * a.njoints + 5 * a.nrs) + 16;
+  const size_t smem = arm_smem_bytes(a);
   if (smem > 200 * 1024)
   {
     gc::set_error("obstacle cloud too large for shared memory staging (%zu bytes)", smem);
@@ -1197,6 +1401,19 @@ static int launch_arm(gc_world* w, const ArmArgs& a, uint64_t items_hint, cudaSt
   return GC_OK;
 }
 
+static void arm_grid_args(const gc_world* w, ArmArgs& a)
+{
+  const bool on = w->grid_cells != 0 && !getenv("GCB200_NO_GRID");
+  a.gstart = on ? w->d_grid_start : nullptr;
+  a.gitems = on ? w->d_grid_items : nullptr;
+  for (int d = 0; d < 3; d++)
+  {
+    a.glo[d] = w->grid_lo[d];
+    a.gn[d] = w->grid_n[d];
+  }
+  a.ginv = w->grid_inv_h;
+}
+
 template <int D>
 static int launch_arm_nrs(gc_world* w, const ArmArgs& a0, uint64_t items_hint, cudaStream_t st)
 {
@@ -1204,6 +1421,8 @@ static int launch_arm_nrs(gc_world* w, const ArmArgs& a0, uint64_t items_hint, c
   // about one full machine of threads (4 CTAs x 128 threads per SM).  With fewer states, 2/4/8 lanes
   // share a state; below that a whole warp takes one state (latency mode).
   ArmArgs a = a0;
+  if (a.gstart)
+    return launch_arm_grid<D>(w, a, items_hint, st);
   const uint64_t full = (uint64_t)w->sms * 4u * 128u;
   if (items_hint * 8u < full / 2u)
   {
@@ -1322,6 +1541,7 @@ int check_edges_dev(gc_world* w, const double* d_c1, const double* d_c2, const d
     a.arm = w->d_arm;
     a.obs = w->d_obs;
     a.nblk = w->nblk;
+    arm_grid_args(w, a);
     a.njoints = w->njoints;
     a.nrs = w->nrs;
     a.nobs = w->nobj;
@@ -1384,6 +1604,7 @@ int check_states_dev(gc_world* w, const double* d_q, uint32_t n, uint8_t* d_ok, 
     a.arm = w->d_arm;
     a.obs = w->d_obs;
     a.nblk = w->nblk;
+    arm_grid_args(w, a);
     a.njoints = w->njoints;
     a.nrs = w->nrs;
     a.nobs = w->nobj;
@@ -1610,6 +1831,144 @@ static uint32_t arm_block_bounds(int njoints, const float* base_tf, const float*
   return nblk;
 }
 
+// Grid culling support (arm_check_grid).  The grid covers the box where a robot-sphere centre can lie within
+// rs_max + r_o + m of some obstacle (clipped to the reach of the arm); cell c lists every obstacle o whose centre is
+// closer than rs_max + r_o + m to the cell's box, the box inflated by the rounding of the device's cell look-up.
+// Exactness: with E = reach of the arm + extent of the cloud + largest radius, the spec'd expanded pair test is within
+// d = 2^-20 E^2 of |c - o|^2 - (r_s + r_o)^2 (see arm_block_bounds).  For an obstacle NOT listed in the cell of c:
+// |c - o| >= rs_max + r_o + m >= r_s + r_o + m, so the exact value is >= m^2 = 16 d > d and the fp32 test reports
+// "apart" too: leaving the pair out cannot change the verdict.  Sphere centres outside the grid are farther than that
+// from every obstacle.  `cloud` is the obstacle array in device order (after arm_block_bounds).
+static void arm_grid_build(gc_world* w, int njoints, const float* base_tf, const float* joint_tf, uint32_t nrs,
+                           const float* rs_local, uint32_t nobs, const float* cloud, std::vector<uint32_t>& start,
+                           std::vector<uint16_t>& items)
+{
+  w->grid_cells = 0;
+  start.clear();
+  items.clear();
+  if (nobs < 1 || nobs > 65535)
+    return;
+  auto norm3 = [](const float* t) { return std::sqrt((double)t[0] * t[0] + (double)t[1] * t[1] + (double)t[2] * t[2]); };
+  double olo[3] = { 1e300, 1e300, 1e300 }, ohi[3] = { -1e300, -1e300, -1e300 }, omax = 0, romax = 0, rsmax = 0;
+  for (uint32_t i = 0; i < nobs; i++)
+  {
+    for (int d = 0; d < 4; d++)
+      if (!(std::fabs((double)cloud[4 * (size_t)i + d]) < 1e18))
+        return;  // non-finite cloud: leave it to the plain loop
+    for (int d = 0; d < 3; d++)
+    {
+      olo[d] = std::min(olo[d], (double)cloud[4 * (size_t)i + d]);
+      ohi[d] = std::max(ohi[d], (double)cloud[4 * (size_t)i + d]);
+    }
+    omax = std::max(omax, norm3(cloud + 4 * (size_t)i));
+    romax = std::max(romax, std::fabs((double)cloud[4 * (size_t)i + 3]));
+  }
+  double reach = norm3(base_tf + 9), smax = 0;
+  for (int j = 0; j < njoints; j++)
+    reach += norm3(joint_tf + 12 * j + 9);
+  for (uint32_t k = 0; k < nrs; k++)
+  {
+    smax = std::max(smax, norm3(rs_local + 4 * k));
+    rsmax = std::max(rsmax, std::fabs((double)rs_local[4 * k + 3]));
+  }
+  reach += smax;
+  if (!(reach < 1e18))
+    return;
+  const double E = reach + omax + std::max(rsmax, romax);
+  const double m = E / 256.0;
+  const double pad = rsmax + romax + m * (1.0 + 1e-6);
+  // |centre| <= reach for every configuration (the chain is rigid), whatever the base rotation
+  double lo[3], hi[3], ext = 0;
+  for (int d = 0; d < 3; d++)
+  {
+    lo[d] = std::max(olo[d] - pad, -reach) - 1e-6 * E;
+    hi[d] = std::min(ohi[d] + pad, reach) + 1e-6 * E;
+    if (!(hi[d] > lo[d]))
+      hi[d] = lo[d] + 1e-3 * (E + 1.0);  // nothing reachable along this axis: a degenerate, empty grid
+    ext = std::max(ext, hi[d] - lo[d]);
+  }
+  double h = std::cbrt((hi[0] - lo[0]) * (hi[1] - lo[1]) * (hi[2] - lo[2]) / (16.0 * std::max<uint32_t>(nobs, 64u)));
+  h = std::max(h, ext / 96.0);
+  for (int attempt = 0; attempt < 12; attempt++, h *= 1.3)
+  {
+    const float inv_h = (float)(1.0 / h);
+    const double he = 1.0 / (double)inv_h;  // the cell size the device's look-up implies
+    float lof[3];
+    int n[3];
+    uint64_t cells = 1;
+    for (int d = 0; d < 3; d++)
+    {
+      lof[d] = std::nextafter((float)lo[d], -INFINITY);
+      n[d] = std::max(1, (int)std::ceil((hi[d] - (double)lof[d]) / he));
+      cells *= (uint64_t)n[d];
+    }
+    if (n[0] > 128 || n[1] > 128 || n[2] > 128 || cells > (1u << 19))
+      continue;
+    const double slop = 1e-4 * he + 1e-6 * E;
+    std::vector<uint32_t> count(cells + 1, 0);
+    std::vector<uint32_t> pend;  // (cell, obstacle) pairs of the first pass
+    pend.reserve(64 * (size_t)nobs);
+    bool too_many = false;
+    for (uint32_t i = 0; i < nobs && !too_many; i++)
+    {
+      const double thr = rsmax + std::fabs((double)cloud[4 * (size_t)i + 3]) + m * (1.0 + 1e-6);
+      int c0[3], c1[3];
+      bool empty = false;
+      for (int d = 0; d < 3; d++)
+      {
+        const double oc = cloud[4 * (size_t)i + d];
+        c0[d] = (int)std::floor((oc - thr - slop - (double)lof[d]) / he);
+        c1[d] = (int)std::floor((oc + thr + slop - (double)lof[d]) / he);
+        c0[d] = std::max(c0[d], 0);
+        c1[d] = std::min(c1[d], n[d] - 1);
+        empty = empty || c0[d] > c1[d];
+      }
+      if (empty)
+        continue;
+      for (int x = c0[0]; x <= c1[0]; x++)
+        for (int y = c0[1]; y <= c1[1]; y++)
+          for (int z = c0[2]; z <= c1[2]; z++)
+          {
+            const int ci[3] = { x, y, z };
+            double d2 = 0;
+            for (int d = 0; d < 3; d++)
+            {
+              const double oc = cloud[4 * (size_t)i + d];
+              const double bl = (double)lof[d] + ci[d] * he - slop, bh = (double)lof[d] + (ci[d] + 1) * he + slop;
+              const double t = oc < bl ? bl - oc : (oc > bh ? oc - bh : 0.0);
+              d2 += t * t;
+            }
+            if (std::sqrt(d2) < thr)
+            {
+              const uint32_t cell = ((uint32_t)x * (uint32_t)n[1] + (uint32_t)y) * (uint32_t)n[2] + (uint32_t)z;
+              count[cell + 1]++;
+              pend.push_back(cell);
+              pend.push_back(i);
+              if (pend.size() > (size_t)(16u << 20))
+                too_many = true;
+            }
+          }
+    }
+    if (too_many)
+      continue;
+    for (uint64_t c = 0; c < cells; c++)
+      count[c + 1] += count[c];
+    start = count;
+    items.assign(std::max<size_t>(1, pend.size() / 2), 0);
+    std::vector<uint32_t> fill(count.begin(), count.end() - 1);
+    for (size_t q = 0; q < pend.size(); q += 2)
+      items[fill[pend[q]]++] = (uint16_t)pend[q + 1];
+    w->grid_cells = (uint32_t)cells;
+    for (int d = 0; d < 3; d++)
+    {
+      w->grid_n[d] = n[d];
+      w->grid_lo[d] = lof[d];
+    }
+    w->grid_inv_h = inv_h;
+    return;
+  }
+}
+
 int gc_world_create_sphere_arm(int njoints, const float* base_tf, const float* joint_tf, uint32_t nrs,
                                const int32_t* rs_link, const float* rs_local, uint32_t nobs, const float* obs,
                                int device, gc_world_t** out)
@@ -1624,16 +1983,44 @@ int gc_world_create_sphere_arm(int njoints, const float* base_tf, const float* j
   w->njoints = njoints;
   w->nrs = nrs;
   w->nobj = nobs;
-  std::vector<float> img(12 + 12 * (size_t)njoints + 5 * (size_t)nrs);
+  // device image: base_tf[12] | joint_tf[J][12] | rs_local[nrs][4] | rs_link[nrs] | first sphere of link 0..J+1, the
+  // spheres sorted by link (the verdict is an OR over the spheres: their order does not matter)
+  std::vector<uint32_t> order(nrs);
+  for (uint32_t k = 0; k < nrs; k++)
+    order[k] = k;
+  std::stable_sort(order.begin(), order.end(), [&](uint32_t x, uint32_t y) { return rs_link[x] < rs_link[y]; });
+  std::vector<float> img(12 + 12 * (size_t)njoints + 5 * (size_t)nrs + (size_t)njoints + 2);
   memcpy(img.data(), base_tf, 12 * sizeof(float));
   memcpy(img.data() + 12, joint_tf, 12 * sizeof(float) * njoints);
-  memcpy(img.data() + 12 + 12 * njoints, rs_local, 4 * sizeof(float) * nrs);
-  memcpy(img.data() + 12 + 12 * njoints + 4 * nrs, rs_link, sizeof(int32_t) * nrs);
+  float* img_local = img.data() + 12 + 12 * njoints;
+  int32_t* img_link = reinterpret_cast<int32_t*>(img_local + 4 * nrs);
+  int32_t* img_first = img_link + nrs;
+  for (uint32_t k = 0; k < nrs; k++)
+  {
+    memcpy(img_local + 4 * k, rs_local + 4 * order[k], 4 * sizeof(float));
+    img_link[k] = rs_link[order[k]];
+  }
+  for (int j = 0; j <= njoints + 1; j++)
+  {
+    int32_t f = 0;
+    while (f < (int32_t)nrs && img_link[f] < j)
+      f++;
+    img_first[j] = f;
+  }
   int rc = upload(&w->d_arm, img.data(), img.size());
   std::vector<float> cloud;
   w->nblk = arm_block_bounds(njoints, base_tf, joint_tf, nrs, rs_local, nobs, obs, cloud);
   if (rc == GC_OK)
     rc = upload(&w->d_obs, cloud.data(), cloud.size());
+  std::vector<uint32_t> gstart;
+  std::vector<uint16_t> gitems;
+  arm_grid_build(w, njoints, base_tf, joint_tf, nrs, rs_local, nobs, cloud.data(), gstart, gitems);
+  if (rc == GC_OK && w->grid_cells)
+  {
+    rc = upload(&w->d_grid_start, gstart.data(), gstart.size());
+    if (rc == GC_OK)
+      rc = upload(&w->d_grid_items, gitems.data(), gitems.size());
+  }
   if (rc != GC_OK)
   {
     gc_world_destroy(w);
@@ -1668,6 +2055,15 @@ int gc_world_clone(gc_world_t* w, gc_world_t** out)
   c->d_arm = root->d_arm;
   c->d_obs = root->d_obs;
   c->nblk = root->nblk;
+  c->d_grid_start = root->d_grid_start;
+  c->d_grid_items = root->d_grid_items;
+  c->grid_cells = root->grid_cells;
+  for (int d = 0; d < 3; d++)
+  {
+    c->grid_n[d] = root->grid_n[d];
+    c->grid_lo[d] = root->grid_lo[d];
+  }
+  c->grid_inv_h = root->grid_inv_h;
   c->parent = root;
   __atomic_add_fetch(&root->refs, 1, __ATOMIC_SEQ_CST);
   *out = c;
@@ -1686,7 +2082,9 @@ int gc_world_destroy(gc_world_t* w)
     cudaStreamSynchronize(w->own_stream);
   gc_world* parent = w->parent;
   if (parent)  // the device world belongs to the parent
-    w->d_lo = w->d_hi = nullptr, w->d_sc = w->d_sr2 = w->d_arm = w->d_obs = nullptr;
+    w->d_lo = w->d_hi = nullptr, w->d_sc = w->d_sr2 = w->d_arm = w->d_obs = nullptr, w->d_grid_start = nullptr,
+    w->d_grid_items = nullptr;
+  cudaFree(w->d_grid_start); cudaFree(w->d_grid_items);
   cudaFree(w->d_lo); cudaFree(w->d_hi); cudaFree(w->d_sc); cudaFree(w->d_sr2);
   cudaFree(w->d_arm); cudaFree(w->d_obs); cudaFree(w->d_counters);
   w->d_c1.release(); w->d_c2.release(); w->d_c3.release(); w->d_ok.release(); w->d_first.release();

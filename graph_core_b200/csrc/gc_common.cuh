@@ -143,6 +143,14 @@ struct gc_world
   float* d_arm = nullptr;  // base_tf[12] | joint_tf[J][12] | rs_local[nrs][4] | rs_link[nrs] (as float bits)
   float* d_obs = nullptr;  // [nobs][4], then [nblk][4] bounding spheres of the blocks of 16 (see edge.cu, culling)
   uint32_t nblk = 0;       // 0 = no block culling for this world
+  // uniform grid over the part of the workspace where a robot sphere can touch an obstacle (edge.cu, "grid culling"):
+  // cell -> the obstacles no sphere centred in the cell can rule out.  grid_cells == 0: no grid for this world
+  uint32_t* d_grid_start = nullptr;  // [grid_cells + 1]
+  uint16_t* d_grid_items = nullptr;  // obstacle indices (positions in d_obs)
+  uint32_t grid_cells = 0;
+  int grid_n[3] = { 0, 0, 0 };
+  float grid_lo[3] = { 0, 0, 0 };
+  float grid_inv_h = 0.0f;
   cudaStream_t stream = nullptr;
   cudaStream_t own_stream = nullptr;
   int sms = 148;
