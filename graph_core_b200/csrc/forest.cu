@@ -21,9 +21,12 @@
 // is applied and the lanes behind it are re-evaluated with fresh cost-to-come walks.
 #include <math_constants.h>
 
+#include <atomic>
+#include <chrono>
 #include <cmath>
 #include <limits>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "gc_common.cuh"
@@ -37,6 +40,7 @@ enum : uint32_t
   kErrSegmentFull = 4u,    // a tree reached the segment capacity
   kErrDepthOverflow = 8u,  // a solution path is longer than depth_cap
   kErrSpecMiss = 16u,      // the replay asked for an edge outside the speculative set (cannot happen by construction)
+  kErrHostTimeout = 32u,   // the host radius thread did not answer
 };
 
 struct __align__(16) FNode
@@ -71,7 +75,7 @@ struct ForestDev
   FNode* nodes;  // [P][cap_seg]
   FProb* prob;   // [P]
   double* path_cost;         // [P] (+inf while unsolved): the informed sampler's cost
-  const double* r_rrt;       // [P] rewire_factor * pow(2(1+1/d),1/d) * pow(specific_volume,1/d), host libm
+  double* r_rrt;             // [P] rewire_factor * pow(2(1+1/d),1/d) * pow(specific_volume,1/d), host libm
   const double* card_table;  // [cap_seg+1] pow(log(n+1)/(n+1), 1/d), host libm
   uint8_t* changed;          // [P] path cost changed in this step
   const double* goals;       // [P][D]
@@ -96,7 +100,14 @@ struct ForestDev
   uint8_t* okA;
   double *eB1, *eB2;
   uint8_t* okB;
-  uint32_t* ctr;              // [0] edges in batch A, [1] edges in batch B, [2] error bits
+  uint32_t* ctr;              // [0] edges in batch A, [1] edges in batch B, [2] error bits, [3] finished replay
+                              // blocks, [4] problems whose path cost changed, [5] requests made, [6] requests installed
+  uint32_t* chg_p;            // [P] the problems of [4]
+  // mapped pinned host memory shared with the radius thread
+  uint32_t* hs_ctl;           // [0] request number (device -> host), [1] entries, [2] answered request (host -> device)
+  uint32_t* hs_p;             // [P] problem
+  double* hs_cost;            // [P] its new path cost
+  double* hs_rrt;             // [P] the host's answer
   unsigned long long* stats;  // see gc_forest_stats
   uint32_t* sol_slot;         // [P][depth_cap] slots of the solution, root's child first
   double* sol_cost;
@@ -466,17 +477,9 @@ __device__ double f_make_solution(const ForestDev& f, uint32_t p, FProb& pr, con
 }
 
 // ---- replay: Tree::rewireOnly's decisions and RRTStar::update's epilogue, one warp per problem --------------
-__global__ void __launch_bounds__(128) forest_replay_kernel(ForestDev f)
+__device__ __forceinline__ void forest_replay_problem(const ForestDev& f, uint32_t p, uint32_t lane)
 {
-  const uint32_t p = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  const uint32_t lane = threadIdx.x & 31;
-  if (p == 0 && lane == 0)
-    atomicAdd(&f.stats[2], (unsigned long long)f.ctr[0] + f.ctr[1]);
-  if (p >= f.P)
-    return;
   FProb& pr = f.prob[p];
-  if (pr.extended != 1)
-    return;
   const int D = f.D;
   FNode* nodes = f.nodes + (size_t)p * f.cap_seg;
   const uint32_t* nidx = f.near_idx + (size_t)p * f.near_cap;
@@ -630,7 +633,10 @@ __global__ void __launch_bounds__(128) forest_replay_kernel(ForestDev f)
   }
   if (changed)
   {
+    // the rewire radius of this problem needs libm's pow() before the next step: queue it for the host
     f.changed[p] = 1;
+    const uint32_t k = atomicAdd(&f.ctr[4], 1u);
+    f.chg_p[k] = p;
     atomicAdd(&f.stats[9], 1ull);
   }
   atomicAdd(&f.stats[3], (unsigned long long)used);
@@ -638,6 +644,86 @@ __global__ void __launch_bounds__(128) forest_replay_kernel(ForestDev f)
   {
     atomicAdd(&f.stats[4], (unsigned long long)miss);
     atomicOr(&f.ctr[2], kErrSpecMiss);
+  }
+}
+
+__global__ void __launch_bounds__(128) forest_replay_kernel(ForestDev f)
+{
+  const uint32_t p = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const uint32_t lane = threadIdx.x & 31;
+  if (p == 0 && lane == 0)
+    atomicAdd(&f.stats[2], (unsigned long long)f.ctr[0] + f.ctr[1]);
+  if (p < f.P && f.prob[p].extended == 1)
+    forest_replay_problem(f, p, lane);
+  // the last block to finish hands the problems whose path cost changed to the host (mapped pinned memory): the
+  // radius thread answers with rewire_factor * pow(2(1+1/d),1/d) * pow(specific volume,1/d) from the host libm
+  __syncthreads();
+  __shared__ uint32_t s_last;
+  if (threadIdx.x == 0)
+  {
+    __threadfence();
+    s_last = (atomicAdd(&f.ctr[3], 1u) == gridDim.x - 1u) ? 1u : 0u;
+  }
+  __syncthreads();
+  if (!s_last)
+    return;
+  __threadfence();
+  const uint32_t n = *reinterpret_cast<volatile uint32_t*>(&f.ctr[4]);
+  if (threadIdx.x == 0)
+    f.ctr[3] = 0;
+  if (n == 0)
+    return;
+  for (uint32_t i = threadIdx.x; i < n; i += blockDim.x)
+  {
+    const uint32_t q = *reinterpret_cast<volatile uint32_t*>(&f.chg_p[i]);
+    f.hs_p[i] = q;
+    f.hs_cost[i] = *reinterpret_cast<volatile double*>(&f.path_cost[q]);
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0)
+  {
+    const uint32_t req = f.ctr[5] + 1u;
+    f.ctr[5] = req;
+    f.hs_ctl[1] = n;
+    __threadfence_system();
+    *reinterpret_cast<volatile uint32_t*>(&f.hs_ctl[0]) = req;
+  }
+}
+
+// waits for the host's answer to the last request (if one is outstanding) and installs the new radius factors
+__global__ void forest_radius_wait_kernel(ForestDev f)
+{
+  __shared__ uint32_t s_ok;
+  const uint32_t req = f.ctr[5];
+  if (f.ctr[6] == req)
+    return;  // nothing was asked since the last wait
+  if (threadIdx.x == 0)
+  {
+    const long long t0 = clock64();
+    uint32_t ok = 1;
+    while (*reinterpret_cast<volatile uint32_t*>(&f.hs_ctl[2]) != req)
+    {
+      if (clock64() - t0 > 8000000000ll)  // ~4 s: the host thread is gone
+      {
+        atomicOr(&f.ctr[2], kErrHostTimeout);
+        ok = 0;
+        break;
+      }
+      __nanosleep(200);
+    }
+    s_ok = ok;
+  }
+  __syncthreads();
+  const uint32_t n = f.ctr[4];
+  if (s_ok)
+    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x)
+      f.r_rrt[f.chg_p[i]] = *reinterpret_cast<volatile double*>(&f.hs_rrt[i]);
+  __syncthreads();
+  if (threadIdx.x == 0)
+  {
+    f.ctr[4] = 0;
+    f.ctr[6] = req;
   }
 }
 }  // namespace gc
@@ -657,14 +743,15 @@ struct gc_forest
   double *d_lb = nullptr, *d_ub = nullptr, *d_starts = nullptr, *d_samples = nullptr, *d_rrt = nullptr;
   // host side of the radius callback
   std::vector<double> lb, ub, focii;
-  double* h_path_cost = nullptr;  // pinned [P]
-  uint8_t* h_changed = nullptr;   // pinned [P]
-  double* h_rrt = nullptr;        // pinned [P]
+  // radius thread: answers the device's requests through mapped pinned memory (see forest_replay_kernel)
+  void* h_shared = nullptr;  // ctl[4] | p[P] | cost[P] | rrt[P]
+  std::thread radius_thread;
+  std::atomic<int> radius_stop{ 0 };
   double box_volume_term = 0.0;   // specific volume at infinite cost
   double r_rrt_unit = 0.0;        // rewire_factor * pow(2(1+1/d), 1/d)
   uint64_t steps = 0, steps_at_sync = 0;
   uint32_t used_at_sync = 0;
-  uint64_t radius_updates = 0;
+  std::atomic<uint64_t> radius_updates{ 0 };
   uint64_t per_edge_states = 2;
   double edgesB_per_step = 0.0;
   bool snapshot_valid = false;
@@ -700,15 +787,35 @@ double rrt_radius_unit_volume(const gc_forest* f, uint32_t p, double cost)
   return f->r_rrt_unit * std::pow(specific_volume, 1.0 / dimension);
 }
 
-void CUDART_CB forest_radius_callback(void* ud)
+// Host side of the radius handshake: spins on the request word the device writes into mapped pinned memory, evaluates
+// the pow() terms with the host libm (bit-identical to the reference's, whatever variant the C library dispatches to)
+// and publishes the answers.  Sleeps between polls after a stretch without requests.
+void forest_radius_loop(gc_forest* f)
 {
-  gc_forest* f = static_cast<gc_forest*>(ud);
-  for (uint32_t p = 0; p < f->P; p++)
-    if (f->h_changed[p])
+  volatile uint32_t* ctl = static_cast<volatile uint32_t*>(f->h_shared);
+  const uint32_t* hp = f->dev.hs_p;
+  const double* hc = f->dev.hs_cost;
+  double* hr = f->dev.hs_rrt;
+  uint32_t acked = 0;
+  uint64_t idle = 0;
+  while (!f->radius_stop.load(std::memory_order_relaxed))
+  {
+    const uint32_t req = ctl[0];
+    if (req != acked)
     {
-      f->h_rrt[p] = rrt_radius_unit_volume(f, p, f->h_path_cost[p]);
-      f->radius_updates++;
+      std::atomic_thread_fence(std::memory_order_acquire);
+      const uint32_t n = ctl[1];
+      for (uint32_t i = 0; i < n && i < f->P; i++)
+        hr[i] = rrt_radius_unit_volume(f, hp[i], hc[i]);
+      f->radius_updates.fetch_add(n, std::memory_order_relaxed);
+      std::atomic_thread_fence(std::memory_order_release);
+      ctl[2] = req;
+      acked = req;
+      idle = 0;
     }
+    else if (++idle > 200000)
+      std::this_thread::sleep_for(std::chrono::microseconds(50));
+  }
 }
 
 double host_dist(const double* a, const double* b, int d)
@@ -739,12 +846,13 @@ int forest_free(gc_forest* f)
   for (void* p : f->allocs)
     cudaFree(p);
   f->allocs.clear();
-  if (f->h_path_cost)
-    cudaFreeHost(f->h_path_cost);
-  if (f->h_changed)
-    cudaFreeHost(f->h_changed);
-  if (f->h_rrt)
-    cudaFreeHost(f->h_rrt);
+  if (f->radius_thread.joinable())
+  {
+    f->radius_stop.store(1);
+    f->radius_thread.join();
+  }
+  if (f->h_shared)
+    cudaFreeHost(f->h_shared);
   delete f;
   return GC_OK;
 }
@@ -857,7 +965,8 @@ int gc_forest_create(gc_store_t* s, gc_world_t* w, const gc_forest_config_t* cfg
   FA(d.eB1, (size_t)cfg->edges_cap * D);
   FA(d.eB2, (size_t)cfg->edges_cap * D);
   FA(d.okB, cfg->edges_cap);
-  FA(d.ctr, 4, true);
+  FA(d.ctr, 8, true);
+  FA(d.chg_p, P);
   FA(d.stats, 16, true);
   FA(d.sol_slot, (size_t)P * cfg->depth_cap);
   FA(d.sol_cost, (size_t)P * cfg->depth_cap);
@@ -866,11 +975,25 @@ int gc_forest_create(gc_store_t* s, gc_world_t* w, const gc_forest_config_t* cfg
   d.card_table = d_card;
   d.goals = d_goals;
   d.samples = f->d_samples;
-  cudaError_t e = cudaMallocHost(&f->h_path_cost, sizeof(double) * P);
+  const size_t shared_bytes = 64 + align_up(sizeof(uint32_t) * P, 64) + 2 * sizeof(double) * (size_t)P;
+  cudaError_t e = cudaHostAlloc(&f->h_shared, shared_bytes, cudaHostAllocMapped | cudaHostAllocPortable);
   if (e == cudaSuccess)
-    e = cudaMallocHost(&f->h_changed, P);
-  if (e == cudaSuccess)
-    e = cudaMallocHost(&f->h_rrt, sizeof(double) * P);
+  {
+    memset(f->h_shared, 0, shared_bytes);
+    void* dp = nullptr;
+    e = cudaHostGetDevicePointer(&dp, f->h_shared, 0);
+    char* base = static_cast<char*>(dp);
+    d.hs_ctl = reinterpret_cast<uint32_t*>(base);
+    d.hs_p = reinterpret_cast<uint32_t*>(base + 64);
+    d.hs_cost = reinterpret_cast<double*>(base + 64 + align_up(sizeof(uint32_t) * P, 64));
+    d.hs_rrt = d.hs_cost + P;
+    if (e == cudaSuccess && dp != f->h_shared)
+    {
+      gc::set_error("gc_forest_create: mapped pinned memory is not addressable at one address on this system");
+      return bail(GC_E_UNSUPPORTED);
+    }
+  }
+  std::vector<double> h_path_cost(P), h_rrt(P);
   if (e != cudaSuccess)
   {
     gc::set_error("gc_forest_create: %s", cudaGetErrorString(e));
@@ -909,9 +1032,8 @@ int gc_forest_create(gc_store_t* s, gc_world_t* w, const gc_forest_config_t* cfg
     pr.goal_slot = goal_slot[p];
     pr.tree_size = n;
     pr.can_improve = 1;
-    f->h_path_cost[p] = solved[p] ? path_cost[p] : std::numeric_limits<double>::infinity();
-    f->h_rrt[p] = rrt_radius_unit_volume(f, p, f->h_path_cost[p]);
-    f->h_changed[p] = 0;
+    h_path_cost[p] = solved[p] ? path_cost[p] : std::numeric_limits<double>::infinity();
+    h_rrt[p] = rrt_radius_unit_volume(f, p, h_path_cost[p]);
     for (int i = 0; i < D; i++)
       max_abs = fmax(max_abs, fmax(fabs(starts[(size_t)p * D + i]), fabs(goals[(size_t)p * D + i])));
   }
@@ -954,9 +1076,9 @@ int gc_forest_create(gc_store_t* s, gc_world_t* w, const gc_forest_config_t* cfg
   if (e == cudaSuccess)
     e = cudaMemcpy(d.prob, prob.data(), sizeof(FProb) * P, cudaMemcpyHostToDevice);
   if (e == cudaSuccess)
-    e = cudaMemcpy(d.path_cost, f->h_path_cost, sizeof(double) * P, cudaMemcpyHostToDevice);
+    e = cudaMemcpy(d.path_cost, h_path_cost.data(), sizeof(double) * P, cudaMemcpyHostToDevice);
   if (e == cudaSuccess)
-    e = cudaMemcpy(f->d_rrt, f->h_rrt, sizeof(double) * P, cudaMemcpyHostToDevice);
+    e = cudaMemcpy(f->d_rrt, h_rrt.data(), sizeof(double) * P, cudaMemcpyHostToDevice);
   if (e == cudaSuccess)
     e = cudaMemcpy(d_card, card.data(), sizeof(double) * card.size(), cudaMemcpyHostToDevice);
   if (e == cudaSuccess)
@@ -984,8 +1106,9 @@ int gc_forest_create(gc_store_t* s, gc_world_t* w, const gc_forest_config_t* cfg
     f->per_edge_states += (uint64_t)(nn / 2);
   f->edgesB_per_step = (double)P * 4.0;
   f->snap = prob;
-  f->snap_path_cost.assign(f->h_path_cost, f->h_path_cost + P);
+  f->snap_path_cost = h_path_cost;
   f->snapshot_valid = true;
+  f->radius_thread = std::thread(forest_radius_loop, f);
   *out = f;
   return GC_OK;
 }
@@ -1020,7 +1143,11 @@ int gc_forest_step(gc_forest_t* f, const double* samples, const double* d_sample
     GC_TRY(sample_informed_launch(D, P, f->d_lb, f->d_ub, f->d_starts, d.goals, d.path_cost, seed, first_index,
                                   f->d_samples, st));
   if (f->steps)
-    GC_CUDA(cudaMemcpyAsync(f->d_rrt, f->h_rrt, sizeof(double) * P, cudaMemcpyHostToDevice, st));
+  {
+    forest_radius_wait_kernel<<<1, 128, 0, st>>>(d);
+    GC_CUDA(cudaGetLastError());
+    count_launch();
+  }
   // every tree grows by at most two nodes per step (the new node and the goal)
   {
     const uint64_t bound = (uint64_t)f->used_at_sync + 2u * (f->steps - f->steps_at_sync + 1u);
@@ -1048,9 +1175,6 @@ int gc_forest_step(gc_forest_t* f, const double* samples, const double* d_sample
   forest_replay_kernel<<<(P + 3) / 4, 128, 0, st>>>(d);
   GC_CUDA(cudaGetLastError());
   count_launch();
-  GC_CUDA(cudaMemcpyAsync(f->h_path_cost, d.path_cost, sizeof(double) * P, cudaMemcpyDeviceToHost, st));
-  GC_CUDA(cudaMemcpyAsync(f->h_changed, d.changed, P, cudaMemcpyDeviceToHost, st));
-  GC_CUDA(cudaLaunchHostFunc(st, forest_radius_callback, f));
   f->steps++;
   f->snapshot_valid = false;
   return GC_OK;
@@ -1121,7 +1245,7 @@ int gc_forest_stats(gc_forest_t* f, uint64_t out[16])
   }
   out[7] = improvable;
   out[8] = solved;
-  out[10] = f->radius_updates;
+  out[10] = f->radius_updates.load();
   return GC_OK;
 }
 
