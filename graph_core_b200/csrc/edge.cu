@@ -867,6 +867,50 @@ __global__ void __launch_bounds__(1024) edge_plan_kernel(PlanArgs a)
   }
 }
 
+// Scan-free plan for the grid kernel: per-edge geometry only, any number of CTAs.  The work list of arm_grid_kernel is
+// a SLOT list -- pass p reserves pass_hi(p) - pass_lo(p) slots for every edge (the last pass: longest edge - 33) and a
+// slot beyond the edge's state count is simply empty -- so no prefix sums and no search are needed to map an item to
+// its (edge, state).  ctl[0] = longest state count (atomicMax), ctl[2..3] = the 64-bit hand-out counter (zeroed here).
+template <int D, int MODE>
+__global__ void __launch_bounds__(256) edge_plan_slots_kernel(PlanArgs a, uint32_t* ctl)
+{
+  const uint32_t n_act = a.n_dev ? min(*a.n_dev, a.n) : a.n;
+  uint32_t ns = 0;
+  for (uint32_t e = blockIdx.x * blockDim.x + threadIdx.x; e < n_act; e += gridDim.x * blockDim.x)
+  {
+    double c1[D], c2[D], c3[D];
+#pragma unroll
+    for (int d = 0; d < D; d++)
+    {
+      c1[d] = a.c1[(size_t)e * D + d];
+      c2[d] = a.c2[(size_t)e * D + d];
+      c3[d] = (MODE == GC_EDGE_FROM_CONF) ? a.c3[(size_t)e * D + d] : 0.0;
+    }
+    if (a.copy_c1)
+    {
+#pragma unroll
+      for (int d = 0; d < D; d++)
+      {
+        a.copy_c1[(size_t)e * D + d] = c1[d];
+        a.copy_c2[(size_t)e * D + d] = c2[d];
+        if (MODE == GC_EDGE_FROM_CONF)
+          a.copy_c3[(size_t)e * D + d] = c3[d];
+      }
+    }
+    const EdgeGeom g = edge_geom<D, MODE>(c1, c2, c3, a.min_d);
+    a.dist[e] = g.dist;
+    a.aux[e] = g.aux;
+    a.nst[e] = g.nstates;
+    a.ok[e] = (g.nstates == 0u) ? 255 : 1;
+    if (a.first_bad)
+      a.first_bad[e] = ~0ull;
+    ns = max(ns, g.nstates);
+  }
+  ns = __reduce_max_sync(0xffffffffu, ns);
+  if ((threadIdx.x & 31) == 0 && ns)
+    atomicMax(&ctl[0], ns);
+}
+
 struct ArmArgs
 {
   // world
@@ -893,6 +937,7 @@ struct ArmArgs
   uint32_t* work_ctr;  // items handed out so far beyond the first one of every group (zeroed before the launch)
   const uint32_t* n_dev;  // optional: edge count in device memory (<= n; n stays the stride of offs)
   // grid culling (arm_grid_kernel)
+  uint32_t* slot_ctl;  // [0] longest state count of the batch, [2..3] 64-bit hand-out counter
   const uint32_t* gstart;
   const uint16_t* gitems;
   float glo[3];
@@ -1177,55 +1222,108 @@ __device__ __forceinline__ bool arm_check_grid(const ArmSmem& w, const ArmArgs& 
   return hit;
 }
 
-// one thread per (edge, state) item of the pass-major list; a warp takes 32 consecutive items at a time (one atomic
-// per warp), so the lanes of a warp work on neighbouring edges and their offset look-ups share cache lines
+// One thread per state.  The work list is the slot list of edge_plan_slots_kernel, pass-major: a warp takes 32
+// consecutive slots at a time (one 64-bit atomic per warp), keeps the live ones -- state index below the edge's state
+// count, edge not yet known to collide -- in a small shared-memory queue and evaluates 32 queued states at once, so
+// empty slots and cancelled edges cost a few instructions instead of idle lanes during the FK chain.
+constexpr int kGridWarps = 4;
 template <int D>
-__global__ void __launch_bounds__(128) arm_grid_kernel(ArmArgs a)
+__global__ void __launch_bounds__(kGridWarps * 32) arm_grid_kernel(ArmArgs a)
 {
   const int MODE = a.mode;
   extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ uint32_t q_e[kGridWarps][64], q_s[kGridWarps][64];
   const ArmSmem w = arm_stage(a, smem_raw);
-  const uint32_t lane = threadIdx.x & 31;
+  const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const uint32_t n_act = a.n_dev ? min(*a.n_dev, a.n) : a.n;
-  uint32_t pbase[kPasses + 1];
+  // slots per edge in every pass
+  uint32_t S[kPasses];
+  unsigned long long pbase[kPasses + 1];
   pbase[0] = 0;
+  if (MODE == 3)
+  {
+    S[0] = 1;
+    S[1] = S[2] = S[3] = 0;
+  }
+  else
+  {
+    const uint32_t longest = a.slot_ctl[0];
+#pragma unroll
+    for (int p = 0; p < kPasses; p++)
+    {
+      const uint32_t hi = (p == kPasses - 1) ? longest : min(longest, pass_hi(p));
+      S[p] = hi > pass_lo(p) ? hi - pass_lo(p) : 0u;
+    }
+  }
 #pragma unroll
   for (int p = 0; p < kPasses; p++)
-    pbase[p + 1] = pbase[p] + ((MODE == 3) ? 0u : a.offs[(size_t)p * (a.n + 1) + n_act]);
-  const uint32_t total = (MODE == 3) ? n_act : pbase[kPasses];
+    pbase[p + 1] = pbase[p] + (unsigned long long)S[p] * n_act;
+  const unsigned long long total = pbase[kPasses];
+  unsigned long long* ctr = reinterpret_cast<unsigned long long*>(a.slot_ctl + 2);
   unsigned long long states = 0, pairs = 0;
-  const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
-  uint32_t tb = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * 32u;  // first item of this warp's batch
-  while (tb < total)
+  const unsigned long long warps = ((unsigned long long)gridDim.x * blockDim.x) >> 5;
+  unsigned long long tb = (((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5) * 32ull;
+  uint32_t qn = 0;  // queued items of this warp (warp-uniform)
+  while (true)
   {
-    uint32_t nb = 0;
-    if (lane == 0)
-      nb = atomicAdd(a.work_ctr, 32u);
-    const uint32_t t = tb + lane;
-    bool have = t < total;
-    uint32_t e = 0, s = 0;
-    if (have && MODE != 3)
+    // ---- fill: scan slots until 32 live items are queued or the list is exhausted
+    while (qn < 32u && tb < total)
     {
-      const int p = (t >= pbase[1]) + (t >= pbase[2]) + (t >= pbase[3]);
-      const uint32_t* offs_p = a.offs + (size_t)p * (a.n + 1);
-      const uint32_t tp = t - pbase[p];
-      e = find_edge(offs_p, n_act, tp);
-      s = pass_lo(p) + (tp - offs_p[e]);
-      if (MODE == GC_EDGE_LINEAR)
-        have = !(*reinterpret_cast<volatile unsigned long long*>(a.first_bad + e) < (unsigned long long)s);
-      else
-        have = (*reinterpret_cast<volatile uint8_t*>(a.ok + e) == 1);
+      unsigned long long nb = 0;
+      if (lane == 0)
+        nb = atomicAdd(ctr, 32ull);
+      const unsigned long long t = tb + lane;
+      bool live = t < total;
+      uint32_t e = 0, st = 0;
+      if (live)
+      {
+        if (MODE == 3)
+          e = (uint32_t)t;
+        else
+        {
+          const int p = (t >= pbase[1]) + (t >= pbase[2]) + (t >= pbase[3]);
+          const unsigned long long tp = t - pbase[p];
+          const uint32_t sp = S[p];
+          e = (total >> 32) ? (uint32_t)(tp / sp) : (uint32_t)tp / sp;
+          st = pass_lo(p) + (uint32_t)(tp - (unsigned long long)e * sp);
+          live = st < a.nst[e];
+          if (live)
+          {
+            // early exit: the reference stops at its first colliding state
+            if (MODE == GC_EDGE_LINEAR)
+              live = !(*reinterpret_cast<volatile unsigned long long*>(a.first_bad + e) < (unsigned long long)st);
+            else
+              live = (*reinterpret_cast<volatile uint8_t*>(a.ok + e) == 1);
+          }
+        }
+      }
+      const uint32_t m = __ballot_sync(0xffffffffu, live);
+      if (live)
+      {
+        const uint32_t pos = qn + __popc(m & ((1u << lane) - 1u));
+        q_e[wid][pos] = e;
+        q_s[wid][pos] = st;
+      }
+      qn += __popc(m);
+      nb = __shfl_sync(0xffffffffu, nb, 0);
+      tb = warps * 32ull + nb;
     }
-    if (have)
+    if (qn == 0)
+      break;
+    __syncwarp();
+    // ---- drain: the last min(qn, 32) queued items, one per lane
+    const uint32_t take = min(qn, 32u);
+    const uint32_t first = qn - take;
+    if (lane < take)
     {
-      float qf[D];
+      const uint32_t e = q_e[wid][first + lane], st = q_s[wid][first + lane];
       double conf[D];
+      bool have = true;
       if (MODE == 3)
       {
-        e = t;
 #pragma unroll
         for (int d = 0; d < D; d++)
-          conf[d] = a.c1[(size_t)t * D + d];
+          conf[d] = a.c1[(size_t)e * D + d];
       }
       else
       {
@@ -1241,10 +1339,11 @@ __global__ void __launch_bounds__(128) arm_grid_kernel(ArmArgs a)
         g.dist = a.dist[e];
         g.aux = a.aux[e];
         g.nstates = a.nst[e];
-        have = state_conf_rt<D>(MODE, c1, c2, c3, g, s, conf);
+        have = state_conf_rt<D>(MODE, c1, c2, c3, g, st, conf);
       }
       if (have)
       {
+        float qf[D];
 #pragma unroll
         for (int d = 0; d < D; d++)
           qf[d] = (float)conf[d];
@@ -1256,12 +1355,12 @@ __global__ void __launch_bounds__(128) arm_grid_kernel(ArmArgs a)
         {
           a.ok[e] = 0;
           if (MODE == GC_EDGE_LINEAR && a.first_bad)
-            atomicMin(&a.first_bad[e], (unsigned long long)s);
+            atomicMin(&a.first_bad[e], (unsigned long long)st);
         }
       }
     }
-    nb = __shfl_sync(0xffffffffu, nb, 0);
-    tb = (nb < 0xFFFFFFFFu - warps * 32u - 64u) ? warps * 32u + nb : 0xFFFFFFFFu;
+    qn = first;
+    __syncwarp();
   }
   for (int o = 16; o > 0; o >>= 1)
   {
@@ -1368,7 +1467,7 @@ static int launch_arm_grid(gc_world* w, const ArmArgs& a, uint64_t items_hint, c
     blocks = max_blocks;
   if (blocks < 1)
     blocks = 1;
-  arm_grid_kernel<D><<<(unsigned)blocks, 128, smem, st>>>(a);
+  arm_grid_kernel<D><<<(unsigned)blocks, kGridWarps * 32, smem, st>>>(a);
   GC_CUDA(cudaGetLastError());
   count_launch();
   return GC_OK;
@@ -1568,6 +1667,20 @@ int check_edges_dev(gc_world* w, const double* d_c1, const double* d_c2, const d
     a.counters = w->d_counters;
     a.mode = mode;
     a.work_ctr = p.work_ctr;
+    if (a.gstart)
+    {
+      // grid path: scan-free plan on as many CTAs as the batch needs, slot list instead of prefix sums
+      uint32_t* ctl = p.offs + (((size_t)n + 3) & ~(size_t)3);
+      p.nst = p.offs;
+      a.nst = p.nst;
+      a.slot_ctl = ctl;
+      GC_CUDA(cudaMemsetAsync(ctl, 0, 4 * sizeof(uint32_t), st));
+      const unsigned pblocks = (unsigned)std::min<uint64_t>(((uint64_t)n + 255) / 256, (uint64_t)w->sms * 4);
+      GC_DISPATCH_DIM_E(w->dim, GC_DISPATCH_MODE(mode,
+                                                 (edge_plan_slots_kernel<DD, MM><<<pblocks, 256, 0, st>>>(p, ctl));
+                                                 GC_CUDA(cudaGetLastError()); count_launch()); GC_TRY((launch_arm_nrs<DD>(w, a, states_hint, st))));
+      return time_end(w, st);
+    }
     const int pthreads = n >= 1024 ? 1024 : (int)align_up(n, 32);
     GC_DISPATCH_DIM_E(w->dim, GC_DISPATCH_MODE(mode, 
                                                (edge_plan_kernel<DD, MM><<<1, pthreads, 0, st>>>(p));
@@ -1615,7 +1728,8 @@ int check_states_dev(gc_world* w, const double* d_q, uint32_t n, uint8_t* d_ok, 
     a.mode = 3;
     GC_TRY(w->d_offs.reserve(sizeof(uint32_t) * 4));
     a.work_ctr = w->d_offs.as<uint32_t>();
-    GC_CUDA(cudaMemsetAsync(a.work_ctr, 0, sizeof(uint32_t), st));
+    a.slot_ctl = w->d_offs.as<uint32_t>();
+    GC_CUDA(cudaMemsetAsync(a.work_ctr, 0, 4 * sizeof(uint32_t), st));
     GC_DISPATCH_DIM_E(w->dim, GC_TRY((launch_arm_nrs<DD>(w, a, n, st))));
   }
   return time_end(w, st);

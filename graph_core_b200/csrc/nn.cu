@@ -917,6 +917,109 @@ __global__ void nn1_finalize_kernel(const double* __restrict__ part_d, const uin
 }
 
 // ---------------------------------------------------------------------------------------------
+// small segments (the lock-step planner regime: thousands of trees of 10^2..10^3 nodes): one warp per query walks its
+// segment with the exact fp64 distance straight away -- a tile of 1024 slots per CTA (scan_kernel) would leave most
+// lanes idle and pay a block-wide fp32 -> fp64 hand-over per query.  Same results by construction: nearest = the
+// lexicographic (dist64, slot) minimum over the live slots, radius = every live slot with dist64 < r, the list ordered
+// by (dist64, slot) -- the order sort_lists_kernel produces.
+// ---------------------------------------------------------------------------------------------
+constexpr uint32_t kSmallSegMax = 1024;   // segments up to this many slots take the warp-per-query kernels
+constexpr uint32_t kSmallCapMax = 1024;   // radius lists up to this many entries are ordered inside the kernel
+constexpr int kSmallWarps = 4;
+
+template <int D, int MODE>
+__global__ void __launch_bounds__(kSmallWarps * 32) small_scan_kernel(ScanArgs a)
+{
+  extern __shared__ __align__(16) unsigned char small_smem[];
+  const uint32_t wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t q = blockIdx.x * kSmallWarps + wid;
+  if (q >= a.nq)
+    return;
+  const uint32_t seg = a.seg ? a.seg[q] : 0u;
+  const uint32_t n = a.used[seg];
+  const size_t base = (size_t)seg * a.cap_seg;
+  double qv[D];
+#pragma unroll
+  for (int d = 0; d < D; d++)
+    qv[d] = a.q[(size_t)q * D + d];
+  const float* x0 = a.x32 + base;  // first coordinate row: +inf marks a tombstone
+  if (MODE == 0)
+  {
+    double bd = CUDART_INF;
+    uint32_t bi = GC_NO_NODE;
+    for (uint32_t slot = lane; slot < n; slot += 32)
+    {
+      if (!(x0[slot] < CUDART_INF_F))
+        continue;
+      const double e = dist64<D>(a.x64 + (base + slot) * D, qv);
+      if (e < bd)
+      {
+        bd = e;
+        bi = slot;
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+    {
+      const double od = __shfl_xor_sync(0xffffffffu, bd, o);
+      const uint32_t oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (oi != GC_NO_NODE && (od < bd || (od == bd && oi < bi)))
+      {
+        bd = od;
+        bi = oi;
+      }
+    }
+    if (lane == 0)
+    {
+      a.out_idx[q] = bi;
+      a.out_dist[q] = bd;
+    }
+    return;
+  }
+  // radius: hits staged in slot order, then rank-sorted by (dist, slot) into the caller's list
+  double* sd = reinterpret_cast<double*>(small_smem) + (size_t)wid * a.cap;
+  uint32_t* si = reinterpret_cast<uint32_t*>(reinterpret_cast<double*>(small_smem) + (size_t)kSmallWarps * a.cap) +
+                 (size_t)wid * a.cap;
+  const double r = a.radius[q];
+  uint32_t count = 0;
+  for (uint32_t s0 = 0; s0 < n; s0 += 32)
+  {
+    const uint32_t slot = s0 + lane;
+    bool hit = false;
+    double e = 0.0;
+    if (slot < n && x0[slot] < CUDART_INF_F)
+    {
+      e = dist64<D>(a.x64 + (base + slot) * D, qv);
+      hit = e < r;  // strict (vector.cpp:75 / kdtree.cpp:167)
+    }
+    const uint32_t m = __ballot_sync(0xffffffffu, hit);
+    const uint32_t pos = count + __popc(m & ((1u << lane) - 1u));
+    if (hit && pos < a.cap)
+    {
+      sd[pos] = e;
+      si[pos] = slot;
+    }
+    count += __popc(m);
+  }
+  __syncwarp();
+  const uint32_t nk = min(count, a.cap);
+  for (uint32_t i = lane; i < nk; i += 32)
+  {
+    const double di = sd[i];
+    uint32_t rank = 0;
+    for (uint32_t j = 0; j < nk; j++)
+    {
+      const double dj = sd[j];
+      rank += (dj < di || (dj == di && j < i)) ? 1u : 0u;  // staged in ascending slot order
+    }
+    a.out_idx[(size_t)q * a.cap + rank] = si[i];
+    a.out_dist[(size_t)q * a.cap + rank] = di;
+  }
+  if (lane == 0)
+    a.out_count[q] = count;
+}
+
+// ---------------------------------------------------------------------------------------------
 // block-wide bitonic sort of (key, slot) pairs, ascending lexicographic; P = power of two
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ void bitonic_sort(double* key, uint32_t* val, uint32_t P)
@@ -1716,6 +1819,16 @@ int nn1_dev(gc_store* s, const double* d_q, const uint32_t* d_seg, uint32_t nq, 
   a.slack_abs = (float)(store_slack(s) * 1.0000001) + FLT_MIN;
   a.part_d = s->d_part.as<double>();
   a.part_i = reinterpret_cast<uint32_t*>(a.part_d + (size_t)chunks * nq);
+  if (max_used(s) <= kSmallSegMax && !getenv("GCB200_NO_SMALL_SCAN"))
+  {
+    a.out_idx = d_idx;
+    a.out_dist = d_dist;
+    GC_DISPATCH_DIM(s->dim, (small_scan_kernel<DD, 0><<<(nq + kSmallWarps - 1) / kSmallWarps, kSmallWarps * 32, 0,
+                                                        s->stream>>>(a)));
+    GC_CUDA(cudaGetLastError());
+    count_launch();
+    return GC_OK;
+  }
   if (use_stream(s, d_seg))
   {
     a.out_idx = d_idx;
@@ -1781,6 +1894,19 @@ int radius_dev(gc_store* s, const double* d_q, const uint32_t* d_seg, const doub
   a.out_idx = d_idx;
   a.out_dist = d_dist;
   a.out_count = d_count;
+  if (max_used(s) <= kSmallSegMax && cap <= kSmallCapMax && !getenv("GCB200_NO_SMALL_SCAN"))
+  {
+    const size_t smem = (size_t)kSmallWarps * cap * (sizeof(double) + sizeof(uint32_t));
+    GC_DISPATCH_DIM(s->dim,
+                    if (smem > 48 * 1024) GC_CUDA(cudaFuncSetAttribute(small_scan_kernel<DD, 1>,
+                                                                       cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                                       (int)smem));
+                    (small_scan_kernel<DD, 1><<<(nq + kSmallWarps - 1) / kSmallWarps, kSmallWarps * 32, smem,
+                                               s->stream>>>(a)));
+    GC_CUDA(cudaGetLastError());
+    count_launch();
+    return GC_OK;
+  }
   if (use_stream(s, d_seg))
   {
     GC_TRY(launch_stream<1>(s, a, nq));
