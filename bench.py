@@ -65,6 +65,7 @@ def parse_args():
     ap.add_argument("--host-replay", action="store_true", help="round-1 path: trees on the host, replay on host threads")
     ap.add_argument("--skip-nn", action="store_true", help="skip the kNN roofline side measurement")
     ap.add_argument("--cpu-problems", type=int, default=0, help="problems of the CPU baseline sample (0 = auto)")
+    ap.add_argument("--kernel-timing", action="store_true", help="with --profile: CUDA events around the check kernels")
     ap.add_argument("--profile", action="store_true",
                     help="profiling run: only the device-sample arm, no CPU baseline / parity / kNN side measurement")
     return ap.parse_args()
@@ -303,7 +304,7 @@ def main():
     root_world = sc.make_world(dev)
     device_trees = not args.host_replay
 
-    def timed_run(device_samples: bool, instances: int, steps_warm=W_, steps_timed=K):
+    def timed_run(device_samples: bool, instances: int, steps_warm=W_, steps_timed=K, kernel_timing=False):
         """(steps_warm + steps_timed) x I lock-step iterations of all P problems, split over `instances` planner instances."""
         G = max(1, min(instances, P))
         bounds = [P * i // G for i in range(G + 1)]
@@ -354,7 +355,9 @@ def main():
         run_all(0, steps_warm)
         for x in inst:
             x["lock"].sync()
-            x["world"].enable_timing(True)
+            # per-call CUDA events around the check kernels: only in the roofline run (they keep the step out of its
+            # CUDA graph)
+            x["world"].enable_timing(kernel_timing)
             x["world"].reset_counters()
         st0 = [x["lock"].stats() for x in inst]
         nodes0 = float(np.mean([x["lock"].info(p)["tree_size"] for x in inst for p in range(0, x["hi"] - x["lo"], 97)]))
@@ -411,7 +414,7 @@ def main():
                 "t1": t1, "info": info, "dump": dump, "instances": G, "keep": inst, "nodes": (nodes0, nodes1)}
 
     if args.profile:
-        val_run = timed_run(device_samples=True, instances=args.instances)
+        val_run = timed_run(device_samples=True, instances=args.instances, kernel_timing=args.kernel_timing)
         if rank == 0:
             vs = val_run["stats"]
             wc = val_run["world"]
@@ -426,7 +429,7 @@ def main():
     e2e_run = timed_run(device_samples=False, instances=args.instances)
     # the dominant kernel is timed in a run of its own with ONE instance: with several instances their kernels share
     # the SMs, so a per-launch duration taken there would not be that of the kernel alone
-    roof_run = val_run if val_run["instances"] == 1 else timed_run(device_samples=True, instances=1)
+    roof_run = timed_run(device_samples=True, instances=1, kernel_timing=True)
     value = val_run["consumed"] / (val_run["ms"] * 1e-3)
     e2e_value = e2e_run["consumed"] / (e2e_run["ms"] * 1e-3)
     clk = clocks.window(val_run["t0"], val_run["t1"])
@@ -495,8 +498,9 @@ def main():
         "states_per_launch": wc["states"] / max(wc["launches"], 1),
         "us_per_launch": wc["kernel_ns"] / max(wc["launches"], 1) / 1e3,
         "kernel_share_of_step": wc["kernel_ns"] / 1e6 / roof_run["ms"],
-        "measured_in": "timed run of the same %d steps with 1 planner instance (%.3f ms/step); the headline runs use %d "
-                       "instance(s)" % (K, roof_run["ms"] / K, val_run["instances"]),
+        "measured_in": "timed run of the same %d steps with 1 planner instance, launched kernel by kernel with CUDA events "
+                       "around the check kernels (%.3f ms/step); the headline runs replay the step from a CUDA graph with "
+                       "%d instance(s)" % (K, roof_run["ms"] / K, val_run["instances"]),
     }
     vs = val_run["stats"]
     nit = K * I

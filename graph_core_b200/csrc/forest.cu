@@ -754,6 +754,12 @@ struct gc_forest
   std::atomic<uint64_t> radius_updates{ 0 };
   uint64_t per_edge_states = 2;
   double edgesB_per_step = 0.0;
+  // CUDA graph of one step (see gc_forest_step)
+  bool graph_enabled = true;
+  cudaGraphExec_t graph_exec = nullptr;
+  uint64_t graph_sig = 0;
+  unsigned graph_launches = 0;
+  double graph_hintB = 0.0;
   bool snapshot_valid = false;
   std::vector<FProb> snap;
   std::vector<double> snap_path_cost;
@@ -853,6 +859,8 @@ int forest_free(gc_forest* f)
   }
   if (f->h_shared)
     cudaFreeHost(f->h_shared);
+  if (f->graph_exec)
+    cudaGraphExecDestroy(f->graph_exec);
   delete f;
   return GC_OK;
 }
@@ -1109,6 +1117,7 @@ int gc_forest_create(gc_store_t* s, gc_world_t* w, const gc_forest_config_t* cfg
   f->snap_path_cost = h_path_cost;
   f->snapshot_valid = true;
   f->radius_thread = std::thread(forest_radius_loop, f);
+  f->graph_enabled = getenv("GCB200_NO_GRAPH") == nullptr;
   *out = f;
   return GC_OK;
 }
@@ -1124,38 +1133,17 @@ int gc_forest_destroy(gc_forest_t* f)
   return forest_free(f);
 }
 
-int gc_forest_step(gc_forest_t* f, const double* samples, const double* d_samples, uint64_t seed, uint64_t first_index)
+// the launches of one step after the samples are in place (d.samples); everything on `st`, nothing synchronises
+static int forest_enqueue(gc_forest* f, const ForestDev& d, cudaStream_t st)
 {
-  GC_REQUIRE(f != nullptr, "gc_forest_step: NULL forest");
-  GC_REQUIRE(!(samples && d_samples), "gc_forest_step: give host samples or device samples, not both");
   gc_store* s = f->store;
   gc_world* w = f->world;
-  GC_SET_DEVICE(s->device);
-  cudaStream_t st = s->stream;
-  ForestDev d = f->dev;
   const uint32_t P = f->P;
-  const int D = f->D;
-  if (samples)
-    GC_CUDA(cudaMemcpyAsync(f->d_samples, samples, sizeof(double) * (size_t)P * D, cudaMemcpyHostToDevice, st));
-  else if (d_samples)
-    d.samples = d_samples;
-  else
-    GC_TRY(sample_informed_launch(D, P, f->d_lb, f->d_ub, f->d_starts, d.goals, d.path_cost, seed, first_index,
-                                  f->d_samples, st));
-  if (f->steps)
-  {
-    forest_radius_wait_kernel<<<1, 128, 0, st>>>(d);
-    GC_CUDA(cudaGetLastError());
-    count_launch();
-  }
-  // every tree grows by at most two nodes per step (the new node and the goal)
-  {
-    const uint64_t bound = (uint64_t)f->used_at_sync + 2u * (f->steps - f->steps_at_sync + 1u);
-    s->used_bound = (uint32_t)std::min<uint64_t>(bound, s->cap_seg);
-  }
+  forest_radius_wait_kernel<<<1, 128, 0, st>>>(d);
+  GC_CUDA(cudaGetLastError());
   forest_prologue_kernel<<<(P + 127) / 128, 128, 0, st>>>(d);
   GC_CUDA(cudaGetLastError());
-  count_launch();
+  count_launch(2);
   GC_TRY(nn1_dev(s, d.samples, d.seg_q, P, d.closest, d.dist, false));
   GC_TRY(steer_launch(s, d.samples, d.seg_q, d.closest, d.dist, P, f->cfg.max_distance, d.c1, d.c2, st));
   GC_TRY(check_edges_dev(w, d.c1, d.c2, nullptr, P, f->cfg.min_distance, GC_EDGE_BISECT, d.ok_ext, nullptr,
@@ -1171,10 +1159,89 @@ int gc_forest_step(gc_forest_t* f, const double* samples, const double* d_sample
   GC_CUDA(cudaGetLastError());
   count_launch();
   GC_TRY(check_edges_dev(w, d.eB1, d.eB2, nullptr, d.edges_cap, f->cfg.min_distance, GC_EDGE_BISECT, d.okB, nullptr,
-                         f->per_edge_states * std::max<uint64_t>(1, (uint64_t)f->edgesB_per_step), st, d.ctr + 1));
+                         f->per_edge_states * std::max<uint64_t>(1, (uint64_t)f->graph_hintB), st, d.ctr + 1));
   forest_replay_kernel<<<(P + 3) / 4, 128, 0, st>>>(d);
   GC_CUDA(cudaGetLastError());
   count_launch();
+  return GC_OK;
+}
+
+int gc_forest_step(gc_forest_t* f, const double* samples, const double* d_samples, uint64_t seed, uint64_t first_index)
+{
+  GC_REQUIRE(f != nullptr, "gc_forest_step: NULL forest");
+  GC_REQUIRE(!(samples && d_samples), "gc_forest_step: give host samples or device samples, not both");
+  gc_store* s = f->store;
+  gc_world* w = f->world;
+  GC_SET_DEVICE(s->device);
+  cudaStream_t st = s->stream;
+  ForestDev d = f->dev;
+  const uint32_t P = f->P;
+  const int D = f->D;
+  // The step is replayed from a CUDA graph (one launch instead of ~20, no gaps between the kernels) unless the world
+  // records per-call timing events or GCB200_NO_GRAPH is set; the samples then go through the forest's own block.
+  const bool use_graph = f->graph_enabled && !w->timing;
+  if (samples)
+    GC_CUDA(cudaMemcpyAsync(f->d_samples, samples, sizeof(double) * (size_t)P * D, cudaMemcpyHostToDevice, st));
+  else if (d_samples)
+  {
+    if (use_graph)
+      GC_CUDA(cudaMemcpyAsync(f->d_samples, d_samples, sizeof(double) * (size_t)P * D, cudaMemcpyDeviceToDevice, st));
+    else
+      d.samples = d_samples;
+  }
+  else
+    GC_TRY(sample_informed_launch(D, P, f->d_lb, f->d_ub, f->d_starts, d.goals, d.path_cost, seed, first_index,
+                                  f->d_samples, st));
+  // every tree grows by at most two nodes per step (the new node and the goal)
+  {
+    const uint64_t bound = (uint64_t)f->used_at_sync + 2u * (f->steps - f->steps_at_sync + 1u);
+    s->used_bound = (uint32_t)std::min<uint64_t>(bound, s->cap_seg);
+  }
+  // grid-sizing hint of the second edge batch: sticky, so that the captured graph stays valid
+  if (f->graph_hintB <= 0.0 || f->edgesB_per_step > 1.5 * f->graph_hintB || f->edgesB_per_step < 0.5 * f->graph_hintB)
+    f->graph_hintB = f->edgesB_per_step;
+  if (!use_graph)
+    GC_TRY(forest_enqueue(f, d, st));
+  else
+  {
+    // launch geometry depends on: the stream, the tile count of the scans, the small-segment switch, the hint
+    const uint64_t sig = ((uint64_t)(s->used_bound <= 1024u ? 0u : (s->used_bound + 1023u) / 1024u) << 32) ^
+                         (uint64_t)(f->graph_hintB) ^ ((uint64_t)(uintptr_t)st << 20);
+    if (!f->graph_exec || sig != f->graph_sig)
+    {
+      if (f->graph_exec)
+        cudaGraphExecDestroy(f->graph_exec);
+      f->graph_exec = nullptr;
+      uint64_t l0 = 0, l1 = 0;
+      gc_launch_count(&l0);
+      GC_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeRelaxed));
+      const int rc = forest_enqueue(f, d, st);
+      cudaGraph_t g = nullptr;
+      const cudaError_t e = cudaStreamEndCapture(st, &g);
+      gc_launch_count(&l1);
+      if (rc < 0 || e != cudaSuccess || !g)
+      {
+        if (g)
+          cudaGraphDestroy(g);
+        if (rc >= 0)
+          gc::set_error("gc_forest_step: stream capture failed: %s", cudaGetErrorString(e));
+        return rc < 0 ? rc : GC_E_CUDA;
+      }
+      const cudaError_t e2 = cudaGraphInstantiate(&f->graph_exec, g, 0);
+      cudaGraphDestroy(g);
+      if (e2 != cudaSuccess)
+      {
+        f->graph_exec = nullptr;
+        gc::set_error("gc_forest_step: cudaGraphInstantiate: %s", cudaGetErrorString(e2));
+        return GC_E_CUDA;
+      }
+      f->graph_sig = sig;
+      f->graph_launches = (unsigned)(l1 - l0);
+    }
+    else
+      count_launch(f->graph_launches);
+    GC_CUDA(cudaGraphLaunch(f->graph_exec, st));
+  }
   f->steps++;
   f->snapshot_valid = false;
   return GC_OK;
