@@ -1164,6 +1164,10 @@ __global__ void __launch_bounds__(G == 1 ? 128 : 256, G == 1 ? (NRS <= 16 ? 4 : 
 // each of the 16 spheres costs a cell look-up and a handful of pair tests (C3: ~22 per state instead of 16 000).
 // The robot spheres are stored sorted by link (arm image: ... | rs_link | first sphere of every link), so the
 // chain visits them without a 16-way unrolled match.
+#ifndef GC_GRID_FK_UNROLL
+#define GC_GRID_FK_UNROLL 1
+#endif
+constexpr int kGridFkUnroll = GC_GRID_FK_UNROLL;  // 1: the joint loop stays a loop (instruction cache), 8: unrolled
 template <int J>
 __device__ __forceinline__ bool arm_check_grid(const ArmSmem& w, const ArmArgs& a, const float* qf,
                                                unsigned long long& pairs)
@@ -1179,7 +1183,7 @@ __device__ __forceinline__ bool arm_check_grid(const ArmSmem& w, const ArmArgs& 
   const float4* loc4 = reinterpret_cast<const float4*>(w.rs_local);
   bool hit = false;
   uint32_t done = 0;
-#pragma unroll
+#pragma unroll kGridFkUnroll
   for (int j = 0; j <= J; j++)
   {
     if (j < J)
@@ -1227,42 +1231,23 @@ __device__ __forceinline__ bool arm_check_grid(const ArmSmem& w, const ArmArgs& 
 // count, edge not yet known to collide -- in a small shared-memory queue and evaluates 32 queued states at once, so
 // empty slots and cancelled edges cost a few instructions instead of idle lanes during the FK chain.
 constexpr int kGridWarps = 4;
-template <int D>
-__global__ void __launch_bounds__(kGridWarps * 32) arm_grid_kernel(ArmArgs a)
+// T = uint32_t when the slot list fits 32 bits (the usual case: cheap index arithmetic), unsigned long long otherwise
+template <int D, typename T>
+__device__ __forceinline__ void arm_grid_body(const ArmArgs& a, const ArmSmem& w, const uint32_t* S, uint32_t n_act,
+                                              uint32_t (*q_e)[64], uint32_t (*q_s)[64])
 {
   const int MODE = a.mode;
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  __shared__ uint32_t q_e[kGridWarps][64], q_s[kGridWarps][64];
-  const ArmSmem w = arm_stage(a, smem_raw);
   const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  const uint32_t n_act = a.n_dev ? min(*a.n_dev, a.n) : a.n;
-  // slots per edge in every pass
-  uint32_t S[kPasses];
-  unsigned long long pbase[kPasses + 1];
+  T pbase[kPasses + 1];
   pbase[0] = 0;
-  if (MODE == 3)
-  {
-    S[0] = 1;
-    S[1] = S[2] = S[3] = 0;
-  }
-  else
-  {
-    const uint32_t longest = a.slot_ctl[0];
-#pragma unroll
-    for (int p = 0; p < kPasses; p++)
-    {
-      const uint32_t hi = (p == kPasses - 1) ? longest : min(longest, pass_hi(p));
-      S[p] = hi > pass_lo(p) ? hi - pass_lo(p) : 0u;
-    }
-  }
 #pragma unroll
   for (int p = 0; p < kPasses; p++)
-    pbase[p + 1] = pbase[p] + (unsigned long long)S[p] * n_act;
-  const unsigned long long total = pbase[kPasses];
+    pbase[p + 1] = pbase[p] + (T)S[p] * (T)n_act;
+  const T total = pbase[kPasses];
   unsigned long long* ctr = reinterpret_cast<unsigned long long*>(a.slot_ctl + 2);
   unsigned long long states = 0, pairs = 0;
-  const unsigned long long warps = ((unsigned long long)gridDim.x * blockDim.x) >> 5;
-  unsigned long long tb = (((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5) * 32ull;
+  const T warps32 = (T)(((unsigned long long)gridDim.x * blockDim.x) >> 5) * (T)32;
+  T tb = (T)((((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5) * 32ull);
   uint32_t qn = 0;  // queued items of this warp (warp-uniform)
   while (true)
   {
@@ -1272,7 +1257,7 @@ __global__ void __launch_bounds__(kGridWarps * 32) arm_grid_kernel(ArmArgs a)
       unsigned long long nb = 0;
       if (lane == 0)
         nb = atomicAdd(ctr, 32ull);
-      const unsigned long long t = tb + lane;
+      const T t = tb + lane;
       bool live = t < total;
       uint32_t e = 0, st = 0;
       if (live)
@@ -1282,10 +1267,10 @@ __global__ void __launch_bounds__(kGridWarps * 32) arm_grid_kernel(ArmArgs a)
         else
         {
           const int p = (t >= pbase[1]) + (t >= pbase[2]) + (t >= pbase[3]);
-          const unsigned long long tp = t - pbase[p];
+          const T tp = t - pbase[p];
           const uint32_t sp = S[p];
-          e = (total >> 32) ? (uint32_t)(tp / sp) : (uint32_t)tp / sp;
-          st = pass_lo(p) + (uint32_t)(tp - (unsigned long long)e * sp);
+          e = (uint32_t)(tp / (T)sp);
+          st = pass_lo(p) + (uint32_t)(tp - (T)e * (T)sp);
           live = st < a.nst[e];
           if (live)
           {
@@ -1306,7 +1291,9 @@ __global__ void __launch_bounds__(kGridWarps * 32) arm_grid_kernel(ArmArgs a)
       }
       qn += __popc(m);
       nb = __shfl_sync(0xffffffffu, nb, 0);
-      tb = warps * 32ull + nb;
+      // batches beyond the list end the loop; the clamp keeps the 32-bit variant from wrapping around
+      const unsigned long long nxt = (unsigned long long)warps32 + nb;
+      tb = (nxt < (unsigned long long)total) ? (T)nxt : total;
     }
     if (qn == 0)
       break;
@@ -1374,6 +1361,40 @@ __global__ void __launch_bounds__(kGridWarps * 32) arm_grid_kernel(ArmArgs a)
     if (pairs)
       atomicAdd(&a.counters[1], pairs);
   }
+}
+
+template <int D>
+__global__ void __launch_bounds__(kGridWarps * 32) arm_grid_kernel(ArmArgs a)
+{
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ uint32_t q_e[kGridWarps][64], q_s[kGridWarps][64];
+  const ArmSmem w = arm_stage(a, smem_raw);
+  const uint32_t n_act = a.n_dev ? min(*a.n_dev, a.n) : a.n;
+  // slots per edge in every pass
+  uint32_t S[kPasses];
+  if (a.mode == 3)
+  {
+    S[0] = 1;
+    S[1] = S[2] = S[3] = 0;
+  }
+  else
+  {
+    const uint32_t longest = a.slot_ctl[0];
+#pragma unroll
+    for (int p = 0; p < kPasses; p++)
+    {
+      const uint32_t hi = (p == kPasses - 1) ? longest : min(longest, pass_hi(p));
+      S[p] = hi > pass_lo(p) ? hi - pass_lo(p) : 0u;
+    }
+  }
+  unsigned long long slots = 0;
+#pragma unroll
+  for (int p = 0; p < kPasses; p++)
+    slots += (unsigned long long)S[p] * n_act;
+  if (slots < 0xF0000000ull)
+    arm_grid_body<D, uint32_t>(a, w, S, n_act, q_e, q_s);
+  else
+    arm_grid_body<D, unsigned long long>(a, w, S, n_act, q_e, q_s);
 }
 
 // =================================================================================================
