@@ -108,6 +108,19 @@ PROTOTYPES = {
     "gc_merge_shard_lists_p2p_dev": (C.c_int, [C.c_int, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32,
                                                C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
                                                C.c_uint64, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]),
+    # device-resident lock-step trees (driven from C++ by host/lockstep.cpp; bound here for completeness)
+    "gc_forest_create": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, _c_double_p, _c_double_p, C.c_uint32, _c_double_p,
+                                   _c_double_p, _c_u32_p, _c_i32_p, _c_double_p, _c_i32_p, _c_u8_p, _c_double_p,
+                                   C.POINTER(C.c_void_p)]),
+    "gc_forest_destroy": (C.c_int, [C.c_void_p]),
+    "gc_forest_step": (C.c_int, [C.c_void_p, _c_double_p, C.c_void_p, C.c_uint64, C.c_uint64]),
+    "gc_forest_read_costs_async": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "gc_forest_sync": (C.c_int, [C.c_void_p]),
+    "gc_forest_stats": (C.c_int, [C.c_void_p, _c_u64_p]),
+    "gc_forest_info": (C.c_int, [C.c_void_p, C.c_uint32, _c_i32_p, _c_i32_p, _c_double_p, _c_double_p, _c_u32_p,
+                                 _c_u32_p]),
+    "gc_forest_dump": (C.c_int, [C.c_void_p, C.c_uint32, _c_i32_p, _c_double_p, _c_double_p]),
+    "gc_forest_solution": (C.c_int, [C.c_void_p, C.c_uint32, _c_i32_p, C.c_uint32]),
     "gc_launch_count": (C.c_int, [_c_u64_p]),
     "gc_measure_fp32_peak": (C.c_int, [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "gc_flush_l2": (C.c_int, [C.c_int, C.c_size_t]),

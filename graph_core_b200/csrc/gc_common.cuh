@@ -116,6 +116,10 @@ struct gc_store
   bool knn_force_fp64 = false;     // large-N k-nearest: candidates carry fp64 distances (massive near-ties met)
   gc::DevBuf d_cand_idx, d_cand_dist, d_cand_count, d_thr, d_gmin;
   size_t stream_ctl_q = 0, stream_ctl_g = 0;  // initialised extent of d_gmin (streaming-scan control words)
+  // one-time kernel attribute opt-ins (dynamic shared memory) and occupancy look-ups: per store = per device context
+  int stream_occ[GC_MAX_DIM + 1] = {};
+  bool sort_attr_set = false;
+  bool knn_attr_set[GC_MAX_DIM + 1] = {};
   // scratch
   gc::DevBuf d_q, d_seg, d_radius, d_idx, d_dist, d_count, d_part, d_misc, d_rows, d_slots;
   gc::PinBuf h_in, h_out;

@@ -1773,7 +1773,7 @@ static int launch_stream(gc_store* s, ScanArgs& a, uint32_t nq)
     m = fmax(m, v);
   a.xn_max = (float)fmin((double)s->dim * m * m * 1.000001, 3.0e38);
   GC_TRY(ensure_stream_ctl(s, nq, groups, &a.gmin, &a.ctl));
-  static int occ[GC_MAX_DIM + 1] = {};
+  int* occ = s->stream_occ;  // per store, hence per device: the opt-in below is a per-context attribute
   int blocks = 0;
   GC_DISPATCH_DIM(
       s->dim, constexpr size_t smem = stream_smem_bytes<DD>(); if (!occ[DD]) {
@@ -1855,12 +1855,11 @@ static int sort_lists(gc_store* s, uint32_t nq, uint32_t cap, uint32_t* d_idx, d
     return GC_E_UNSUPPORTED;
   }
   size_t smem = (size_t)P * (sizeof(double) + sizeof(uint32_t));
-  static bool attr_set = false;
-  if (!attr_set)
+  if (!s->sort_attr_set)
   {
     GC_CUDA(cudaFuncSetAttribute(sort_lists_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)(kSortMax * (sizeof(double) + sizeof(uint32_t)))));
-    attr_set = true;
+    s->sort_attr_set = true;
   }
   int threads = P >= 2048 ? 1024 : (P >= 512 ? 256 : 64);
   sort_lists_kernel<<<nq, threads, smem, s->stream>>>(d_idx, d_dist, d_count, cap, P);
@@ -2083,7 +2082,7 @@ int knn_dev(gc_store* s, const double* d_q, const uint32_t* d_seg, uint32_t nq, 
   while (P < mu)
     P <<= 1;
   size_t smem = (size_t)P * (sizeof(double) + sizeof(uint32_t));
-  static bool attr_set[GC_MAX_DIM + 1] = {};
+  bool* attr_set = s->knn_attr_set;
   const size_t row_stride = s->cap_total + kRowPad;
   GC_DISPATCH_DIM(
       s->dim,
@@ -2126,8 +2125,8 @@ int gc_store_create(int dim, uint32_t capacity_per_segment, uint32_t n_segments,
   s->cap_total = (size_t)s->cap_seg * n_segments;
   if (s->cap_total > 0xFFFFFFF0ull)
   {
-    delete s;
     gc::set_error("gc_store_create: %zu slots exceed the 32-bit slot space", s->cap_total);
+    delete s;
     return GC_E_INVALID;
   }
   s->sms = num_sms(device);
@@ -2251,10 +2250,11 @@ int gc_store_append_multi(gc_store_t* s, const uint32_t* segments, const double*
   GC_TRY(s->d_slots.reserve(sbytes));
   GC_CUDA(cudaStreamSynchronize(s->stream));
   uint32_t* hs = reinterpret_cast<uint32_t*>(static_cast<char*>(s->h_in.p) + bytes);
+  for (uint32_t i = 0; i < n; i++)  // validate every segment id before the host mirror is touched
+    GC_REQUIRE(segments[i] < s->nseg, "gc_store_append_multi: segment %u of %u", segments[i], s->nseg);
   for (uint32_t i = 0; i < n; i++)
   {
     const uint32_t seg = segments[i];
-    GC_REQUIRE(seg < s->nseg, "gc_store_append_multi: segment %u of %u", seg, s->nseg);
     if (s->used[seg] >= s->cap_seg)
     {
       // roll back the rows already accounted for

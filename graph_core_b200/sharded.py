@@ -203,5 +203,18 @@ class ShardedNodeStore:
         return self._exchange(self.engine.knn_lists(q, k), k, k)
 
     def near(self, q, radius: float, cap: int = 256):
-        """Radius-near; a shard list that overflows `cap` shows up as count > cap on that shard."""
-        return self._exchange(self.engine.near_lists(q, radius, cap), self.world * cap, self.world * cap)
+        """Radius-near, complete: when some shard found more than `cap` neighbours of a query the per-shard lists are
+        taken again with a capacity that holds them (all ranks agree on it through a MAX all-reduce), as
+        CudaNearestNeighbors::near does for the unsharded store -- a truncated shard list never reaches the merge."""
+        while True:
+            lists = self.engine.near_lists(q, radius, cap)
+            mx = lists[2].max().to(torch.int64) if lists[2].numel() else torch.zeros((), dtype=torch.int64,
+                                                                                       device=lists[2].device)
+            if self.world > 1:
+                dist.all_reduce(mx, op=dist.ReduceOp.MAX, group=self.group)
+            need = int(mx.item())
+            if need <= cap:
+                break
+            while cap < need:
+                cap *= 2
+        return self._exchange(lists, self.world * cap, self.world * cap)
