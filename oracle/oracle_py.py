@@ -64,6 +64,7 @@ def lib(fast: bool = False):
         "orc_world_pair_tests": (C.c_ulonglong, [vp]),
         "orc_world_state_checks": (C.c_ulonglong, [vp]),
         "orc_world_reset_counters": (None, [vp]),
+        "orc_world_enable_grid": (C.c_int, [vp, C.c_int]),
         "orc_check_states": (None, [vp, _dp, C.c_int, _u8p]),
         "orc_check_edges": (None, [vp, _dp, _dp, C.c_int, C.c_double, C.c_int, _u8p, _i64p, _dp]),
         "orc_check_from_conf": (None, [vp, _dp, _dp, _dp, C.c_int, C.c_double, _u8p]),
@@ -233,6 +234,10 @@ class OracleWorld:
 
     def reset_counters(self):
         self.L.orc_world_reset_counters(self.h)
+
+    def enable_grid(self, on=True):
+        """Uniform-grid culling of the sphere-arm check (verdicts unchanged); returns the number of cells (0 = off)."""
+        return self.L.orc_world_enable_grid(self.h, 1 if on else 0)
 
     def check(self, q):
         q = _f64(q, (-1, self.dim))

@@ -207,3 +207,37 @@ def test_rewire_radius_formula(orc):
 import sys  # noqa: E402
 
 sys.path.insert(0, str(GOLD))
+
+
+def test_oracle_grid_culling_keeps_every_verdict(orc):
+    """The uniform-grid culling the CPU arm of the benchmark may switch on (orc_world_enable_grid) must not change a
+    single verdict of the sphere-arm check: random states, states on the first contact of random edges (bisected to one
+    ulp), clouds of several sizes (partial cells, empty grid regions)."""
+    from graph_core_b200 import worlds as W
+    rng = np.random.default_rng(77)
+    for nobs in (1, 37, 1000, 1500):
+        sc = W.scenario_c3(nobs)
+        plain = orc.OracleWorld.from_scenario(sc)
+        grid = orc.OracleWorld.from_scenario(sc)
+        assert grid.enable_grid(True) > 0
+        q = rng.uniform(-np.pi, np.pi, size=(6000, 7))
+        a = plain.check(q)
+        assert np.array_equal(a, grid.check(q)), nobs
+        # grazing contacts: bisect free -> colliding pairs down to neighbouring doubles along the segment
+        free, hit = q[a == 1][:60], q[a == 0][:60]
+        n = min(len(free), len(hit))
+        lo, hi = np.zeros(n), np.ones(n)
+        for _ in range(60):
+            mid = 0.5 * (lo + hi)
+            qm = free[:n] + (hit[:n] - free[:n]) * mid[:, None]
+            ok = plain.check(qm).astype(bool)
+            lo, hi = np.where(ok, mid, lo), np.where(ok, hi, mid)
+        for t in (lo, hi, np.nextafter(lo, 2.0), np.nextafter(hi, -1.0)):
+            qg = free[:n] + (hit[:n] - free[:n]) * t[:, None]
+            assert np.array_equal(plain.check(qg), grid.check(qg)), nobs
+        grid.reset_counters()
+        plain.reset_counters()
+        grid.check(q[:500])
+        plain.check(q[:500])
+        if nobs >= 1000:
+            assert grid.counters()["pair_tests"] * 20 < plain.counters()["pair_tests"]
