@@ -59,7 +59,7 @@ def parse_args():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--problems", type=int, default=8192, help="independent planning problems per GPU")
     ap.add_argument("--threads", type=int, default=0, help="host replay threads (0 = all cores)")
-    ap.add_argument("--instances", type=int, default=2,
+    ap.add_argument("--instances", type=int, default=1,
                     help="lock-step planner instances per GPU, each with problems/instances problems, its own stream and "
                          "enqueueing host thread: the serial kernels of one instance overlap the wide ones of the others")
     ap.add_argument("--host-replay", action="store_true", help="round-1 path: trees on the host, replay on host threads")

@@ -179,9 +179,14 @@ __global__ void forest_prologue_kernel(ForestDev f)
   f.changed[p] = 0;
   f.seg_q[p] = act ? p : f.P;
   f.radius[p] = pr.r_rewire;
-  const uint32_t m = __ballot_sync(__activemask(), act);
+  const uint32_t am = __activemask();
+  const uint32_t m = __ballot_sync(am, act);
   if (act && (threadIdx.x & 31) == (uint32_t)(__ffs(m) - 1))
     atomicAdd(&f.stats[0], (unsigned long long)__popc(m));
+  // largest tree (the host sizes the scans of later steps with it, read back asynchronously)
+  const uint32_t mx = __reduce_max_sync(am, pr.tree_size);
+  if ((threadIdx.x & 31) == (uint32_t)(__ffs(am) - 1) && mx > f.ctr[7])
+    atomicMax(&f.ctr[7], mx);
 }
 
 // ---- extend: Tree::extend's bookkeeping + the parent phase's candidate set (tree.cpp:130-161, 428-463) -------
@@ -691,6 +696,18 @@ __global__ void __launch_bounds__(128) forest_replay_kernel(ForestDev f)
   }
 }
 
+// {largest tree, steps, edges} in one place for the asynchronous probe
+__global__ void forest_probe_kernel(ForestDev f, uint32_t* out)
+{
+  if (threadIdx.x == 0)
+  {
+    out[0] = f.ctr[7];
+    out[1] = (uint32_t)f.stats[6];
+    out[2] = (uint32_t)f.stats[2];
+    out[3] = (uint32_t)(f.stats[2] >> 32);
+  }
+}
+
 // waits for the host's answer to the last request (if one is outstanding) and installs the new radius factors
 __global__ void forest_radius_wait_kernel(ForestDev f)
 {
@@ -741,6 +758,7 @@ struct gc_forest
   ForestDev dev{};
   std::vector<void*> allocs;
   double *d_lb = nullptr, *d_ub = nullptr, *d_starts = nullptr, *d_samples = nullptr, *d_rrt = nullptr;
+  uint32_t* d_probe = nullptr;
   // host side of the radius callback
   std::vector<double> lb, ub, focii;
   // radius thread: answers the device's requests through mapped pinned memory (see forest_replay_kernel)
@@ -754,6 +772,12 @@ struct gc_forest
   std::atomic<uint64_t> radius_updates{ 0 };
   uint64_t per_edge_states = 2;
   double edgesB_per_step = 0.0;
+  // asynchronous probe of {largest tree, edges so far, steps so far}: keeps the grid sizing of the scans and of the
+  // second edge batch close to the truth between two gc_forest_sync calls without ever blocking
+  uint32_t* h_probe = nullptr;  // pinned [4]: max tree size, steps (low word), edges (64 bit)
+  cudaEvent_t probe_ev = nullptr;
+  bool probe_pending = false;
+  uint64_t probe_step = 0, probe_edges_prev = 0, probe_steps_prev = 0;
   // CUDA graph of one step (see gc_forest_step)
   bool graph_enabled = true;
   cudaGraphExec_t graph_exec = nullptr;
@@ -861,6 +885,10 @@ int forest_free(gc_forest* f)
     cudaFreeHost(f->h_shared);
   if (f->graph_exec)
     cudaGraphExecDestroy(f->graph_exec);
+  if (f->probe_ev)
+    cudaEventDestroy(f->probe_ev);
+  if (f->h_probe)
+    cudaFreeHost(f->h_probe);
   delete f;
   return GC_OK;
 }
@@ -974,6 +1002,7 @@ int gc_forest_create(gc_store_t* s, gc_world_t* w, const gc_forest_config_t* cfg
   FA(d.eB2, (size_t)cfg->edges_cap * D);
   FA(d.okB, cfg->edges_cap);
   FA(d.ctr, 8, true);
+  FA(f->d_probe, 4, true);
   FA(d.chg_p, P);
   FA(d.stats, 16, true);
   FA(d.sol_slot, (size_t)P * cfg->depth_cap);
@@ -1118,6 +1147,12 @@ int gc_forest_create(gc_store_t* s, gc_world_t* w, const gc_forest_config_t* cfg
   f->snapshot_valid = true;
   f->radius_thread = std::thread(forest_radius_loop, f);
   f->graph_enabled = getenv("GCB200_NO_GRAPH") == nullptr;
+  if (cudaMallocHost(&f->h_probe, 4 * sizeof(uint32_t)) != cudaSuccess ||
+      cudaEventCreateWithFlags(&f->probe_ev, cudaEventDisableTiming) != cudaSuccess)
+  {
+    gc::set_error("gc_forest_create: probe buffers");
+    return bail(GC_E_CUDA);
+  }
   *out = f;
   return GC_OK;
 }
@@ -1192,9 +1227,23 @@ int gc_forest_step(gc_forest_t* f, const double* samples, const double* d_sample
   else
     GC_TRY(sample_informed_launch(D, P, f->d_lb, f->d_ub, f->d_starts, d.goals, d.path_cost, seed, first_index,
                                   f->d_samples, st));
-  // every tree grows by at most two nodes per step (the new node and the goal)
+  if (f->probe_pending && cudaEventQuery(f->probe_ev) == cudaSuccess)
   {
-    const uint64_t bound = (uint64_t)f->used_at_sync + 2u * (f->steps - f->steps_at_sync + 1u);
+    f->probe_pending = false;
+    if (f->probe_step >= f->steps_at_sync)
+    {
+      f->used_at_sync = f->h_probe[0];
+      f->steps_at_sync = f->probe_step;
+    }
+    const uint64_t edges = ((uint64_t)f->h_probe[3] << 32) | f->h_probe[2], nsteps = f->h_probe[1];
+    if (nsteps > f->probe_steps_prev)
+      f->edgesB_per_step = std::max(64.0, (double)(edges - f->probe_edges_prev) / (double)(nsteps - f->probe_steps_prev));
+    f->probe_edges_prev = edges;
+    f->probe_steps_prev = nsteps;
+  }
+  // every tree grows by at most one node per step, plus the goal once
+  {
+    const uint64_t bound = (uint64_t)f->used_at_sync + (f->steps - f->steps_at_sync) + 3u;
     s->used_bound = (uint32_t)std::min<uint64_t>(bound, s->cap_seg);
   }
   // grid-sizing hint of the second edge batch: sticky, so that the captured graph stays valid
@@ -1244,6 +1293,16 @@ int gc_forest_step(gc_forest_t* f, const double* samples, const double* d_sample
   }
   f->steps++;
   f->snapshot_valid = false;
+  if (!f->probe_pending && (f->steps & 15u) == 0)
+  {
+    forest_probe_kernel<<<1, 32, 0, st>>>(d, f->d_probe);
+    GC_CUDA(cudaGetLastError());
+    count_launch();
+    GC_CUDA(cudaMemcpyAsync(f->h_probe, f->d_probe, 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    GC_CUDA(cudaEventRecord(f->probe_ev, st));
+    f->probe_pending = true;
+    f->probe_step = f->steps;
+  }
   return GC_OK;
 }
 
