@@ -63,7 +63,8 @@ def parse_args():
                     help="lock-step planner instances per GPU, each with problems/instances problems, its own stream and "
                          "enqueueing host thread: the serial kernels of one instance overlap the wide ones of the others")
     ap.add_argument("--host-replay", action="store_true", help="round-1 path: trees on the host, replay on host threads")
-    ap.add_argument("--skip-nn", action="store_true", help="skip the kNN roofline side measurement")
+    ap.add_argument("--skip-nn", action="store_true", help="skip the kNN measurements")
+    ap.add_argument("--skip-extras", action="store_true", help="skip the informed-sampler arm and the depth sweep")
     ap.add_argument("--cpu-problems", type=int, default=0, help="problems of the CPU baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-optimized", action="store_true", help="reference arm: skip the grid-culled CPU leg")
     ap.add_argument("--kernel-timing", action="store_true", help="with --profile: CUDA events around the check kernels")
@@ -205,6 +206,160 @@ CPU_DESC = {
                  "single-state sphere-arm check from the oracle",
     "port": "CPU restatement of KdTree + checkConnection (-O3 -Ofast)",
 }
+
+
+
+def depth_sweep(g, torch, LockstepRRTStar, sc, root_world, starts, goals, dev, targets=(100, 1000, 10000), problems=1024,
+                window=100, seed=31500, budget_s=90.0):
+    """samples/s of the lock-step step at given tree sizes: `problems` problems are grown with uniform Philox samples
+    until their mean tree size reaches each target, then `window` iterations are timed with CUDA events."""
+    import ctypes as C
+    P = min(problems, len(starts))
+    cap = int(max(targets) * 1.25) + 512
+    w = root_world.clone()
+    st = torch.cuda.Stream()
+    w.set_stream(st.cuda_stream)
+    lk = LockstepRRTStar(sc, w, starts[:P], goals[:P], capacity=cap, device=dev, near_cap=4096)
+    lk.set_stream(st.cuda_stream)
+    lib = g.capi.load()
+    lb = np.ascontiguousarray(sc.lb, dtype=np.float64)
+    ub = np.ascontiguousarray(sc.ub, dtype=np.float64)
+    chunk = 256
+    buf = torch.empty((chunk, P, sc.dim), dtype=torch.float64, device="cuda")
+    state = {"it": 0}
+
+    def run(n):
+        done = 0
+        while done < n:
+            m = min(chunk, n - done)
+            rc = lib.gc_sample_uniform_dev(dev, sc.dim, lb.ctypes.data_as(C.POINTER(C.c_double)),
+                                           ub.ctypes.data_as(C.POINTER(C.c_double)), seed, state["it"] * P, m * P,
+                                           buf.data_ptr(), C.c_void_p(st.cuda_stream))
+            assert rc == 0
+            with torch.cuda.stream(st):
+                for j in range(m):
+                    lk.step_device_samples(buf[j].data_ptr())
+            lk.sync()  # the block is refilled next: wait for its readers
+            state["it"] += m
+            done += m
+
+    def mean_nodes():
+        return float(np.mean([lk.info(p)["tree_size"] for p in range(0, P, max(1, P // 64))]))
+
+    out = []
+    t_start = time.time()
+    for target in targets:
+        while mean_nodes() < target and time.time() - t_start < budget_s:
+            run(chunk)
+        if mean_nodes() < target * 0.8:
+            out.append({"target_nodes": target, "skipped": "time budget of the sweep (%.0f s) reached at %.0f nodes" %
+                        (budget_s, mean_nodes())})
+            break
+        n0 = mean_nodes()
+        s0 = lk.stats()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(st)
+        run(window)
+        e1.record(st)
+        torch.cuda.synchronize()
+        s1 = lk.stats()
+        ms = e0.elapsed_time(e1)
+        out.append({"tree_nodes": [n0, mean_nodes()], "problems": P, "iterations": window,
+                    "samples_per_s": (s1["iterations"] - s0["iterations"]) / (ms * 1e-3), "ms_per_iteration": ms / window,
+                    "near_hits_per_extension": (s1["near_hits"] - s0["near_hits"]) / max(s1["extended"] - s0["extended"], 1)})
+    lk.close()
+    return out
+
+
+def informed_arm(g, torch, LockstepRRTStar, sc, root_world, starts, goals, dev, iters_warm, iters_timed, seed=30900):
+    """The same problems with the planner's own sampler: the device informed sampler draws sample i of problem p from the
+    informed set of p's current path cost (InformedSampler::sample, rrt_star.cpp:147-161); nothing crosses PCIe."""
+    P = len(starts)
+    w = root_world.clone()
+    st = torch.cuda.Stream()
+    w.set_stream(st.cuda_stream)
+    lk = LockstepRRTStar(sc, w, starts, goals, capacity=iters_warm + iters_timed + 64, device=dev)
+    lk.set_stream(st.cuda_stream)
+    with torch.cuda.stream(st):
+        for i in range(iters_warm):
+            lk.step_informed(seed, i * P)
+        lk.sync()
+        s0 = lk.stats()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(st)
+        for i in range(iters_warm, iters_warm + iters_timed):
+            lk.step_informed(seed, i * P)
+        e1.record(st)
+    torch.cuda.synchronize()
+    lk.sync()
+    s1 = lk.stats()
+    ms = e0.elapsed_time(e1)
+    solved = sum(lk.info(p)["solved"] for p in range(0, P, max(1, P // 256))) / len(range(0, P, max(1, P // 256)))
+    lk.close()
+    return {"value": (s1["iterations"] - s0["iterations"]) / (ms * 1e-3), "unit": UNIT, "ms_per_iteration": ms / iters_timed,
+            "problems": P, "iterations": iters_timed, "solved_fraction_at_end": solved,
+            "sampler": "device informed sampler inside the forest (Philox key %d, counter iteration*P + problem)" % seed,
+            "parity": "tests/test_planner_gpu.py::test_rrtstar_informed_sampler_inside_the_planner (oracle fed the same "
+                      "stream, trees bit-exact)"}
+
+
+def knn_c4(g, torch, dist_mod, rank, world, dev, hbm_peak, fp32_peak, n_nodes=1 << 20, dim=12, reps=5):
+    """BASELINE config 4: 2^20-node 12-DoF tree, node-sharded round-robin over the ranks (NCCL all-gather of the per-shard
+    lists + device merge); queries/s = Q / max-over-ranks device time, L2 not flushed (the shard is larger than L2 only at
+    one rank: 50 MB of fp32 SoA per 2^20 nodes)."""
+    from graph_core_b200 import worlds as W
+    from graph_core_b200.sharded import ShardedNodeStore
+    pts = W.c4_nodes(n_nodes, dim)
+    qs = W.c4_queries(4096, dim)
+    st = ShardedNodeStore(dim, n_nodes, device=dev, exchange="nccl", nq_max=4096, cap_max=1024)
+    st.append(pts)
+    torch.cuda.synchronize()
+
+    def timed(fn):
+        times = []
+        for it in range(reps + 2):
+            if world > 1:
+                dist_mod.barrier()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn()
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1)
+            if world > 1:
+                t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+                dist_mod.all_reduce(t, op=dist_mod.ReduceOp.MAX)
+                ms = float(t.item())
+            if it >= 2:
+                times.append(ms)
+        return float(np.median(times))
+
+    res = {"nodes": n_nodes, "dim": dim, "n_gpus": world, "sharding": "round-robin over ranks, NCCL all-gather + merge kernel",
+           "cases": []}
+    for nq in (4096, 1):
+        for k in (1, 16, 64):
+            q = qs[:nq]
+            ms = timed((lambda: st.nearest(q)) if k == 1 else (lambda: st.knn(q, k)))
+            case = {"queries": nq, "k": k, "ms": ms, "queries_per_s": nq / (ms * 1e-3)}
+            if nq == 1:
+                # one pass over the fp32 SoA of every shard: HBM-bound regime
+                case["GBps_aggregate"] = 4.0 * dim * n_nodes / (ms * 1e-3) / 1e9
+                case["frac_of_hbm_peak"] = case["GBps_aggregate"] / (hbm_peak * world)
+            else:
+                case["pairs_per_s"] = nq * float(n_nodes) / (ms * 1e-3)
+                # expanded form: D fused multiply-adds per (node, query) pair
+                case["frac_of_fp32_peak"] = case["pairs_per_s"] * 2.0 * dim / 1e12 / (fp32_peak * world) if fp32_peak else None
+            res["cases"].append(case)
+    head = next(c for c in res["cases"] if c["queries"] == 4096 and c["k"] == 16)
+    res["queries_per_s"] = head["queries_per_s"]
+    res["headline_case"] = "k = 16, 4096 queries"
+    lat = next(c for c in res["cases"] if c["queries"] == 1 and c["k"] == 1)
+    res["roofline"] = {"kernel": "scan_stream_kernel<12,nearest>", "bound": "hbm", "achieved": lat["GBps_aggregate"],
+                       "peak": hbm_peak * world, "unit": "GB/s", "frac": lat["frac_of_hbm_peak"],
+                       "what": "nearest neighbour of ONE query over the whole sharded tree (4*D*N bytes / max-over-ranks "
+                               "time, L2-resident after the first repetition at this size)"}
+    return res
 
 
 def main():
@@ -525,6 +680,27 @@ def main():
                               "abi_calls_per_iteration": vs["gpu_calls"] / nit,
                               "launches_per_iteration": val_run["launches"] / nit / val_run["instances"]}
 
+    # ---- kNN half of BASELINE's metric: C4 node-sharded over the ranks (every rank takes part) ------------------
+    if not args.skip_nn:
+        try:
+            peaks = {}
+            try:
+                peaks = json.loads((ROOT / "MEASURED_PEAKS.json").read_text())
+            except Exception:
+                pass
+            line["knn"] = knn_c4(g, torch, dist if world_size > 1 else None, rank, world_size, dev,
+                                 float(peaks.get("hbm_gbs", 6650.0)), fp32_peak)
+        except Exception as ex:
+            line["knn"] = {"error": str(ex)[:300]}
+    if rank == 0 and not args.skip_extras:
+        try:
+            line["informed"] = informed_arm(g, torch, LockstepRRTStar, sc, root_world, starts, goals, dev, W_ * I, K * I)
+        except Exception as ex:
+            line["informed"] = {"error": str(ex)[:300]}
+        try:
+            line["depth_sweep"] = depth_sweep(g, torch, LockstepRRTStar, sc, root_world, starts, goals, dev)
+        except Exception as ex:
+            line["depth_sweep"] = {"error": str(ex)[:300]}
     if rank == 0:
         # ---- in-bench parity check: 16 problems, full depth, against the oracle on the same samples -----------
         sys.path.insert(0, str(ROOT / "oracle"))

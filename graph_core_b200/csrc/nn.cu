@@ -1077,6 +1077,170 @@ __global__ void sort_lists_kernel(uint32_t* __restrict__ idx, double* __restrict
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Lists longer than one CTA can sort (kSortMax entries): runs of kSortMax entries are sorted in shared
+// memory, then merged pairwise in global memory.  A merge pass is rank based: entry i of the left run
+// lands at i + (entries of the right run strictly before it), entry j of the right run at j + (entries
+// of the left run not after it), each found by a binary search -- every entry is independent, so a
+// pass is one launch over all lists however long they are.  Order: ascending (dist, slot), the
+// multimap order of KdTree / Vector results (kdtree.cpp:362-370, vector.cpp:83-96).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool pair_before(double da, uint32_t sa, double db, uint32_t sb)
+{
+  return da < db || (da == db && sa < sb);
+}
+
+// `count` == nullptr: every list holds `cap` entries.  `stride` = entries between consecutive lists.
+__global__ void __launch_bounds__(1024, 1)
+    sort_runs_kernel(uint32_t* __restrict__ idx, double* __restrict__ dist, const uint32_t* __restrict__ count,
+                     uint32_t cap, size_t stride)
+{
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double* key = reinterpret_cast<double*>(smem_raw);
+  uint32_t* val = reinterpret_cast<uint32_t*>(key + kSortMax);
+  const uint32_t q = blockIdx.y;
+  const uint32_t n = count ? min(count[q], cap) : cap;
+  const uint32_t r0 = blockIdx.x * kSortMax;
+  if (r0 >= n)
+    return;
+  const uint32_t m = min(kSortMax, n - r0);
+  uint32_t p2 = 2;
+  while (p2 < m)
+    p2 <<= 1;
+  uint32_t* li = idx + (size_t)q * stride + r0;
+  double* ld = dist + (size_t)q * stride + r0;
+  for (uint32_t i = threadIdx.x; i < p2; i += blockDim.x)
+  {
+    key[i] = (i < m) ? ld[i] : CUDART_INF;
+    val[i] = (i < m) ? li[i] : GC_NO_NODE;
+  }
+  __syncthreads();
+  bitonic_sort(key, val, p2);
+  for (uint32_t i = threadIdx.x; i < m; i += blockDim.x)
+  {
+    ld[i] = key[i];
+    li[i] = val[i];
+  }
+}
+
+__global__ void __launch_bounds__(256)
+    merge_runs_kernel(const uint32_t* __restrict__ idx_in, const double* __restrict__ dist_in,
+                      uint32_t* __restrict__ idx_out, double* __restrict__ dist_out,
+                      const uint32_t* __restrict__ count, uint32_t cap, size_t stride, uint32_t L)
+{
+  const uint32_t q = blockIdx.y;
+  const uint32_t n = count ? min(count[q], cap) : cap;
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n)
+    return;
+  const uint32_t* li = idx_in + (size_t)q * stride;
+  const double* ld = dist_in + (size_t)q * stride;
+  const double d = ld[i];
+  const uint32_t sl = li[i];
+  const uint32_t run = i / L;
+  const uint32_t pair_base = (run & ~1u) * L;
+  const bool left = (run & 1u) == 0;
+  const uint32_t sib_base = left ? pair_base + L : pair_base;
+  uint32_t rank = 0;
+  if (sib_base < n)
+  {
+    const uint32_t sib_n = min(L, n - sib_base);
+    uint32_t lo = 0, hi = sib_n;
+    while (lo < hi)
+    {
+      const uint32_t mid = (lo + hi) >> 1;
+      const double dm = ld[sib_base + mid];
+      const uint32_t sm = li[sib_base + mid];
+      // left entries go before equal right entries, so the pass is a permutation even with repeated keys
+      const bool sib_first = left ? pair_before(dm, sm, d, sl) : !pair_before(d, sl, dm, sm);
+      if (sib_first)
+        lo = mid + 1;
+      else
+        hi = mid;
+    }
+    rank = lo;
+  }
+  const size_t o = (size_t)q * stride + pair_base + (i - run * L) + rank;
+  idx_out[o] = sl;
+  dist_out[o] = d;
+}
+
+// exact fp64 distance of every slot of the query's segment (tombstones and the padding: +inf, GC_NO_NODE); the
+// k >= N "all nodes, sorted" answer of Tree::nearK (tree.cpp:761-765) and k > kSortMax on large trees
+template <int D>
+__global__ void __launch_bounds__(256)
+    dist_all_kernel(const float* __restrict__ x32, const double* __restrict__ x64, const uint32_t* __restrict__ used,
+                    const double* __restrict__ qd, const uint32_t* __restrict__ segs, uint32_t cap_seg, uint32_t npad,
+                    uint32_t* __restrict__ out_idx, double* __restrict__ out_dist, uint32_t* __restrict__ live_count)
+{
+  __shared__ double qs[D];
+  const uint32_t q = blockIdx.y;
+  if (threadIdx.x < D)
+    qs[threadIdx.x] = qd[(size_t)q * D + threadIdx.x];
+  __syncthreads();
+  const uint32_t seg = segs ? segs[q] : 0u;
+  const uint32_t n_s = used[seg];
+  const size_t seg_base = (size_t)seg * cap_seg;
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  bool live = false;
+  double e = CUDART_INF;
+  if (i < n_s && x32[seg_base + i] < CUDART_INF_F)
+  {
+    e = dist64<D>(x64 + (seg_base + i) * D, qs);
+    live = true;
+  }
+  if (i < npad)
+  {
+    out_idx[(size_t)q * npad + i] = live ? i : GC_NO_NODE;
+    out_dist[(size_t)q * npad + i] = e;
+  }
+  const uint32_t m = __ballot_sync(0xffffffffu, live);
+  if ((threadIdx.x & 31) == 0 && m)
+    atomicAdd(&live_count[q], (uint32_t)__popc(m));
+}
+
+// first min(k, have, out_cap) entries of every sorted list; out_count = min(k, have)
+__global__ void take_first_kernel(const uint32_t* __restrict__ idx, const double* __restrict__ dist,
+                                  const uint32_t* __restrict__ have, size_t stride, unsigned long long k,
+                                  uint32_t out_cap, uint32_t* __restrict__ out_idx, double* __restrict__ out_dist,
+                                  uint32_t* __restrict__ out_count)
+{
+  const uint32_t q = blockIdx.y;
+  const uint32_t h = have[q];
+  const uint32_t want = (k < (unsigned long long)h) ? (uint32_t)k : h;
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < min(want, out_cap))
+  {
+    out_idx[(size_t)q * out_cap + i] = idx[(size_t)q * stride + i];
+    out_dist[(size_t)q * out_cap + i] = dist[(size_t)q * stride + i];
+  }
+  if (i == 0)
+    out_count[q] = want;
+}
+
+// shard lists [G][nq][cap] -> one list per query with global slots (local * G + g), `total` = entries gathered
+__global__ void gather_shard_lists_kernel(const uint32_t* __restrict__ idx, const double* __restrict__ dist,
+                                          const uint32_t* __restrict__ count, uint32_t G, uint32_t nq, uint32_t cap,
+                                          uint32_t* __restrict__ out_idx, double* __restrict__ out_dist,
+                                          uint32_t* __restrict__ total)
+{
+  const uint32_t q = blockIdx.y;
+  uint32_t base = 0;
+  for (uint32_t g = 0; g < G; g++)
+  {
+    const uint32_t n = min(count[(size_t)g * nq + q], cap);
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    {
+      const uint32_t local = idx[((size_t)g * nq + q) * cap + i];
+      out_idx[(size_t)q * G * cap + base + i] = (local == GC_NO_NODE) ? GC_NO_NODE : local * G + g;
+      out_dist[(size_t)q * G * cap + base + i] = dist[((size_t)g * nq + q) * cap + i];
+    }
+    base += n;
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0)
+    total[q] = base;
+}
+
 // k-nearest for segments of at most kSortMax slots (planner regime; also the k >= N "return all,
 // sorted" case of Tree::nearK, src/graph_core/graph/tree.cpp:761-765): exact fp64 distance of
 // every live slot, block-wide sort, first min(k, live) entries.
@@ -1663,6 +1827,27 @@ __global__ void __launch_bounds__(1024, 1)
     out_count[q] = want;
 }
 
+// the same gather with the shard lists read through peer-mapped pointers
+__global__ void gather_shard_lists_p2p_kernel(PeerLists pl, uint32_t G, uint32_t cap, uint32_t* __restrict__ out_idx,
+                                              double* __restrict__ out_dist, uint32_t* __restrict__ total)
+{
+  const uint32_t q = blockIdx.y;
+  uint32_t base = 0;
+  for (uint32_t g = 0; g < G; g++)
+  {
+    const uint32_t n = min(__ldcg(pl.count[g] + q), cap);
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    {
+      const uint32_t local = __ldcg(pl.idx[g] + (size_t)q * cap + i);
+      out_idx[(size_t)q * G * cap + base + i] = (local == GC_NO_NODE) ? GC_NO_NODE : local * G + g;
+      out_dist[(size_t)q * G * cap + base + i] = __ldcg(pl.dist[g] + (size_t)q * cap + i);
+    }
+    base += n;
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0)
+    total[q] = base;
+}
+
 // ---------------------------------------------------------------------------------------------
 // dispatch helpers
 // ---------------------------------------------------------------------------------------------
@@ -1844,6 +2029,48 @@ int nn1_dev(gc_store* s, const double* d_q, const uint32_t* d_seg, uint32_t nq, 
   return GC_OK;
 }
 
+// Sorts nq lists of up to `cap` entries (count == nullptr: exactly cap), `stride` entries apart, of any length:
+// sort_runs_kernel then ceil(log2(cap / kSortMax)) rank-merge passes between the lists and (tmp_idx, tmp_dist).
+static int sort_large(cudaStream_t stream, uint32_t nq, uint32_t cap, size_t stride, uint32_t* d_idx, double* d_dist,
+                      const uint32_t* d_count, uint32_t* tmp_idx, double* tmp_dist)
+{
+  if (nq == 0 || cap == 0)
+    return GC_OK;
+  const size_t smem = (size_t)kSortMax * (sizeof(double) + sizeof(uint32_t));
+  GC_CUDA(cudaFuncSetAttribute(sort_runs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const uint32_t runs = (cap + kSortMax - 1) / kSortMax;
+  for (uint32_t q0 = 0; q0 < nq; q0 += 65535u)  // grid.y limit
+  {
+    const uint32_t nqc = std::min(65535u, nq - q0);
+    uint32_t* li = d_idx + (size_t)q0 * stride;
+    double* ld = d_dist + (size_t)q0 * stride;
+    uint32_t* ti = tmp_idx + (size_t)q0 * stride;
+    double* td = tmp_dist + (size_t)q0 * stride;
+    const uint32_t* cnt = d_count ? d_count + q0 : nullptr;
+    sort_runs_kernel<<<dim3(runs, nqc), 1024, smem, stream>>>(li, ld, cnt, cap, stride);
+    GC_CUDA(cudaGetLastError());
+    count_launch();
+    bool in_tmp = false;
+    for (uint64_t L = kSortMax; L < cap; L <<= 1)
+    {
+      merge_runs_kernel<<<dim3((cap + 255) / 256, nqc), 256, 0, stream>>>(in_tmp ? ti : li, in_tmp ? td : ld,
+                                                                          in_tmp ? li : ti, in_tmp ? ld : td, cnt, cap,
+                                                                          stride, (uint32_t)L);
+      GC_CUDA(cudaGetLastError());
+      count_launch();
+      in_tmp = !in_tmp;
+    }
+    if (in_tmp)
+    {
+      // only the first min(count, cap) entries of a list were written to the other buffer: copy whole rows back
+      const size_t rows = (size_t)(nqc - 1) * stride + cap;
+      GC_CUDA(cudaMemcpyAsync(li, ti, sizeof(uint32_t) * rows, cudaMemcpyDeviceToDevice, stream));
+      GC_CUDA(cudaMemcpyAsync(ld, td, sizeof(double) * rows, cudaMemcpyDeviceToDevice, stream));
+    }
+  }
+  return GC_OK;
+}
+
 static int sort_lists(gc_store* s, uint32_t nq, uint32_t cap, uint32_t* d_idx, double* d_dist, uint32_t* d_count)
 {
   uint32_t P = 2;
@@ -1851,8 +2078,11 @@ static int sort_lists(gc_store* s, uint32_t nq, uint32_t cap, uint32_t* d_idx, d
     P <<= 1;
   if (P > kSortMax)
   {
-    gc::set_error("result lists longer than %u entries are not supported yet (cap %u)", kSortMax, cap);
-    return GC_E_UNSUPPORTED;
+    // cap entries per list, runs of kSortMax merged pairwise through the candidate scratch of the store
+    GC_TRY(s->d_cand_idx.reserve(sizeof(uint32_t) * (size_t)nq * cap));
+    GC_TRY(s->d_cand_dist.reserve(sizeof(double) * (size_t)nq * cap));
+    return sort_large(s->stream, nq, cap, cap, d_idx, d_dist, d_count, s->d_cand_idx.as<uint32_t>(),
+                      s->d_cand_dist.as<double>());
   }
   size_t smem = (size_t)P * (sizeof(double) + sizeof(uint32_t));
   if (!s->sort_attr_set)
@@ -1918,6 +2148,42 @@ int radius_dev(gc_store* s, const double* d_q, const uint32_t* d_seg, const doub
   return sort_lists(s, nq, cap, d_idx, d_dist, d_count);
 }
 
+// k above kSortMax on a segment larger than kSortMax slots -- what Tree::nearK asks for in high dimensions, where
+// k_rrt * ln(N + 1) exceeds N (tree.cpp:52-53, 761-765) and the answer is "every node, sorted": fp64 distance of every
+// slot, full sort (sort_large), first min(k, live) entries.  Queries go in chunks that keep the scratch under ~1 GiB.
+static int knn_full_sort_dev(gc_store* s, const double* d_q, const uint32_t* d_seg, uint32_t nq, uint64_t k, uint32_t cap,
+                             uint32_t* d_idx, double* d_dist, uint32_t* d_count)
+{
+  const uint32_t npad = max_used(s);
+  const uint32_t qchunk =
+      (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(std::min<uint32_t>(nq, 65535u), (1ull << 30) / ((uint64_t)npad * 24ull)));
+  const size_t n = (size_t)qchunk * npad;
+  GC_TRY(s->d_cand_idx.reserve(sizeof(uint32_t) * n * 2));
+  GC_TRY(s->d_cand_dist.reserve(sizeof(double) * n * 2));
+  GC_TRY(s->d_cand_count.reserve(sizeof(uint32_t) * ((size_t)qchunk + 4)));
+  uint32_t* li = s->d_cand_idx.as<uint32_t>();
+  double* ld = s->d_cand_dist.as<double>();
+  uint32_t* live = s->d_cand_count.as<uint32_t>();
+  for (uint32_t q0 = 0; q0 < nq; q0 += qchunk)
+  {
+    const uint32_t nqc = std::min(qchunk, nq - q0);
+    GC_CUDA(cudaMemsetAsync(live, 0, sizeof(uint32_t) * nqc, s->stream));
+    GC_DISPATCH_DIM(s->dim, (dist_all_kernel<DD><<<dim3((npad + 255) / 256, nqc), 256, 0, s->stream>>>(
+                                s->x32, s->x64, s->d_used, d_q + (size_t)q0 * s->dim, d_seg ? d_seg + q0 : nullptr,
+                                s->cap_seg, npad, li, ld, live)));
+    GC_CUDA(cudaGetLastError());
+    count_launch();
+    GC_TRY(sort_large(s->stream, nqc, npad, npad, li, ld, nullptr, li + n, ld + n));
+    const uint32_t width = (uint32_t)std::min<uint64_t>(std::min<uint64_t>(k, cap), npad);
+    take_first_kernel<<<dim3((std::max(width, 1u) + 255) / 256, nqc), 256, 0, s->stream>>>(
+        li, ld, live, npad, (unsigned long long)k, cap, d_idx + (size_t)q0 * cap, d_dist + (size_t)q0 * cap,
+        d_count + q0);
+    GC_CUDA(cudaGetLastError());
+    count_launch();
+  }
+  return GC_OK;
+}
+
 // sample threshold -> one collecting scan -> exact select (see the kernels above).  Queries are processed in
 // chunks so that the candidate lists stay under ~256 MiB.  Returns GC_E_CAPACITY after a synchronisation
 // when a candidate list overflowed its estimate (the caller retries with s->knn_cand_scale doubled).
@@ -1925,11 +2191,7 @@ static int knn_large_dev(gc_store* s, const double* d_q, const uint32_t* d_seg, 
                          uint32_t* d_idx, double* d_dist, uint32_t* d_count)
 {
   if (k > kSortMax)
-  {
-    gc::set_error("gc_knn: k = %llu above %u on a segment larger than %u slots is not supported yet",
-                  (unsigned long long)k, kSortMax, kSortMax);
-    return GC_E_UNSUPPORTED;
-  }
+    return knn_full_sort_dev(s, d_q, d_seg, nq, k, cap, d_idx, d_dist, d_count);
   if (k == 0)
   {
     GC_CUDA(cudaMemsetAsync(d_count, 0, sizeof(uint32_t) * nq, s->stream));
@@ -2398,13 +2660,49 @@ int gc_merge_shard_lists_dev(int device, void* cuda_stream, uint32_t n_shards, u
   uint32_t P = 2;
   while (P < n_shards * cap)
     P <<= 1;
+  GC_SET_DEVICE(device);
   if (P > kSortMax)
   {
-    gc::set_error("gc_merge_shard_lists_dev: %u shards x %u entries exceed the %u-entry merge buffer", n_shards, cap,
-                  kSortMax);
-    return GC_E_UNSUPPORTED;
+    // more entries than one CTA sorts: gather with global slots, full sort, first k_out (stream-ordered scratch)
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(cuda_stream);
+    const size_t W = (size_t)n_shards * cap, n = (size_t)nq * W;
+    void* scratch = nullptr;
+    GC_CUDA(cudaMallocAsync(&scratch, n * 24 + sizeof(uint32_t) * ((size_t)nq + 4), st));
+    double* ld = static_cast<double*>(scratch);
+    double* td = ld + n;
+    uint32_t* li = reinterpret_cast<uint32_t*>(td + n);
+    uint32_t* ti = li + n;
+    uint32_t* total = ti + n;
+    int rc = GC_OK;
+    for (uint32_t q0 = 0; q0 < nq && rc == GC_OK; q0 += 65535u)
+    {
+      const uint32_t nqc = std::min(65535u, nq - q0);
+      // the shard-major layout is addressed with the full nq, so the kernel is given the chunk through offsets
+      gather_shard_lists_kernel<<<dim3(32, nqc), 256, 0, st>>>(d_idx + (size_t)q0 * cap, d_dist + (size_t)q0 * cap,
+                                                              d_count + q0, n_shards, nq, cap, li + (size_t)q0 * W,
+                                                              ld + (size_t)q0 * W, total + q0);
+      if (cudaGetLastError() != cudaSuccess)
+        rc = GC_E_CUDA;
+      count_launch();
+    }
+    if (rc == GC_OK)
+      rc = sort_large(st, nq, (uint32_t)W, W, li, ld, total, ti, td);
+    for (uint32_t q0 = 0; q0 < nq && rc == GC_OK; q0 += 65535u)
+    {
+      const uint32_t nqc = std::min(65535u, nq - q0);
+      const uint32_t width = (uint32_t)std::min<uint64_t>(std::min<uint64_t>(k_out, out_cap), W);
+      take_first_kernel<<<dim3((std::max(width, 1u) + 255) / 256, nqc), 256, 0, st>>>(
+          li + (size_t)q0 * W, ld + (size_t)q0 * W, total + q0, W, (unsigned long long)k_out, out_cap,
+          d_out_idx + (size_t)q0 * out_cap, d_out_dist + (size_t)q0 * out_cap, d_out_count + q0);
+      if (cudaGetLastError() != cudaSuccess)
+        rc = GC_E_CUDA;
+      count_launch();
+    }
+    cudaFreeAsync(scratch, st);
+    if (rc != GC_OK)
+      gc::set_error("gc_merge_shard_lists_dev: large merge failed");
+    return rc;
   }
-  GC_SET_DEVICE(device);
   const size_t smem = (size_t)P * (sizeof(double) + sizeof(uint32_t));
   GC_CUDA(cudaFuncSetAttribute(merge_shard_lists_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                (int)(kSortMax * (sizeof(double) + sizeof(uint32_t)))));
@@ -2425,8 +2723,6 @@ int gc_merge_shard_lists_p2p_dev(int device, void* cuda_stream, uint32_t n_shard
   GC_REQUIRE(d_idx_of_shard && d_dist_of_shard && d_count_of_shard && d_out_idx && d_out_dist && d_out_count,
              "gc_merge_shard_lists_p2p_dev: NULL argument");
   GC_REQUIRE(n_shards >= 1 && n_shards <= 16, "gc_merge_shard_lists_p2p_dev: %u shards (1..16)", n_shards);
-  GC_REQUIRE((uint64_t)n_shards * cap <= kSortMax, "gc_merge_shard_lists_p2p_dev: n_shards*cap = %llu above %u",
-             (unsigned long long)n_shards * cap, kSortMax);
   if (nq == 0)
     return GC_OK;
   GC_SET_DEVICE(device);
@@ -2437,6 +2733,38 @@ int gc_merge_shard_lists_p2p_dev(int device, void* cuda_stream, uint32_t n_shard
     pl.idx[g] = static_cast<const uint32_t*>(d_idx_of_shard[g]);
     pl.dist[g] = static_cast<const double*>(d_dist_of_shard[g]);
     pl.count[g] = static_cast<const uint32_t*>(d_count_of_shard[g]);
+  }
+  if ((uint64_t)n_shards * cap > kSortMax)
+  {
+    GC_REQUIRE(nq <= 65535u, "gc_merge_shard_lists_p2p_dev: %u queries with lists above %u entries (max 65535)", nq,
+               kSortMax);
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(cuda_stream);
+    const size_t W = (size_t)n_shards * cap, n = (size_t)nq * W;
+    void* scratch = nullptr;
+    GC_CUDA(cudaMallocAsync(&scratch, n * 24 + sizeof(uint32_t) * ((size_t)nq + 4), st));
+    double* ld = static_cast<double*>(scratch);
+    double* td = ld + n;
+    uint32_t* li = reinterpret_cast<uint32_t*>(td + n);
+    uint32_t* ti = li + n;
+    uint32_t* total = ti + n;
+    gather_shard_lists_p2p_kernel<<<dim3(32, nq), 256, 0, st>>>(pl, n_shards, cap, li, ld, total);
+    int rc = cudaGetLastError() == cudaSuccess ? GC_OK : GC_E_CUDA;
+    count_launch();
+    if (rc == GC_OK)
+      rc = sort_large(st, nq, (uint32_t)W, W, li, ld, total, ti, td);
+    if (rc == GC_OK)
+    {
+      const uint32_t width = (uint32_t)std::min<uint64_t>(std::min<uint64_t>(k_out, out_cap), W);
+      take_first_kernel<<<dim3((std::max(width, 1u) + 255) / 256, nq), 256, 0, st>>>(
+          li, ld, total, W, (unsigned long long)k_out, out_cap, d_out_idx, d_out_dist, d_out_count);
+      if (cudaGetLastError() != cudaSuccess)
+        rc = GC_E_CUDA;
+      count_launch();
+    }
+    cudaFreeAsync(scratch, st);
+    if (rc != GC_OK)
+      gc::set_error("gc_merge_shard_lists_p2p_dev: large merge failed");
+    return rc;
   }
   uint32_t P = 2;
   while (P < n_shards * cap)

@@ -70,7 +70,7 @@ class LockstepRRTStar:
     work on the stream and the accessors synchronise on demand.  device_trees=False: the host replay of round 1."""
 
     def __init__(self, scenario, world: capi.CollisionWorld, starts, goals, capacity: int = 16384, device: int = 0,
-                 threads: int = 0, device_trees: bool = True):
+                 threads: int = 0, device_trees: bool = True, near_cap: int | None = None):
         self.L = load_host()
         self.dim = scenario.dim
         self.max_distance = float(scenario.max_distance)
@@ -81,14 +81,28 @@ class LockstepRRTStar:
         self.n = starts.shape[0]
         lb, ub = _f64(scenario.lb), _f64(scenario.ub)
         h = C.c_void_p()
-        rc = self.L.gcp_rrtstar_create2(self.dim, scenario.max_distance, scenario.min_distance, scenario.rewire_factor,
+        import os
+        old_cap = os.environ.get("GCB200_NEAR_CAP")
+        if near_cap is not None:  # longest radius-near list the device forest can hold (default 512 entries)
+            os.environ["GCB200_NEAR_CAP"] = str(int(near_cap))
+        try:
+            rc = self._create(scenario, world, device, starts, goals, capacity, threads, device_trees, lb, ub, h)
+        finally:
+            if near_cap is not None:
+                if old_cap is None:
+                    os.environ.pop("GCB200_NEAR_CAP", None)
+                else:
+                    os.environ["GCB200_NEAR_CAP"] = old_cap
+        if rc != 0:
+            raise capi.GcError(rc, self.L.gcp_last_error().decode())
+        self.h = h
+
+    def _create(self, scenario, world, device, starts, goals, capacity, threads, device_trees, lb, ub, h):
+        return self.L.gcp_rrtstar_create2(self.dim, scenario.max_distance, scenario.min_distance, scenario.rewire_factor,
                                         scenario.utopia_tolerance, lb.ctypes.data_as(_dp), ub.ctypes.data_as(_dp),
                                         world.handle, device, self.n, starts.ctypes.data_as(_dp),
                                         goals.ctypes.data_as(_dp), capacity, threads, 1 if device_trees else 0,
                                         C.byref(h))
-        if rc != 0:
-            raise capi.GcError(rc, self.L.gcp_last_error().decode())
-        self.h = h
 
     def close(self):
         if getattr(self, "h", None):

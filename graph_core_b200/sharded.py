@@ -189,6 +189,9 @@ class ShardedNodeStore:
 
     def _exchange(self, lists, k_out, out_cap):
         idx, dd, cnt = lists
+        if self.world == 1 and idx.shape[1] == out_cap:
+            # one shard: its ordered list IS the answer (local slot == global slot), nothing to exchange or merge
+            return idx, dd, torch.clamp(cnt, max=k_out)
         if self.exchange == "p2p" and self.world > 1:
             return self.engine.merge_p2p(idx.shape[0], idx.shape[1], k_out, out_cap)
         return self.engine.merge(self._gather(idx), self._gather(dd), self._gather(cnt), k_out, out_cap)
