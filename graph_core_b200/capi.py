@@ -121,6 +121,16 @@ PROTOTYPES = {
                                  _c_u32_p]),
     "gc_forest_dump": (C.c_int, [C.c_void_p, C.c_uint32, _c_i32_p, _c_double_p, _c_double_p]),
     "gc_forest_solution": (C.c_int, [C.c_void_p, C.c_uint32, _c_i32_p, C.c_uint32]),
+    # device-resident lock-step BiRRT / RRT (csrc/birrt.cu)
+    "gc_birrt_create": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, _c_double_p, _c_double_p, C.POINTER(C.c_void_p)]),
+    "gc_birrt_destroy": (C.c_int, [C.c_void_p]),
+    "gc_birrt_step": (C.c_int, [C.c_void_p, _c_double_p, C.c_void_p]),
+    "gc_birrt_sync": (C.c_int, [C.c_void_p]),
+    "gc_birrt_stats": (C.c_int, [C.c_void_p, _c_u64_p]),
+    "gc_birrt_info": (C.c_int, [C.c_void_p, C.c_uint32, _c_i32_p, _c_u32_p, _c_double_p, _c_u32_p, _c_u32_p]),
+    "gc_birrt_read_solved": (C.c_int, [C.c_void_p, _c_u8_p, _c_double_p]),
+    "gc_birrt_dump": (C.c_int, [C.c_void_p, C.c_uint32, C.c_int, _c_i32_p, _c_double_p, _c_double_p]),
+    "gc_birrt_solution": (C.c_int, [C.c_void_p, C.c_uint32, _c_double_p, _c_double_p, C.c_uint32]),
     "gc_launch_count": (C.c_int, [_c_u64_p]),
     "gc_measure_fp32_peak": (C.c_int, [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "gc_flush_l2": (C.c_int, [C.c_int, C.c_size_t]),

@@ -201,3 +201,94 @@ class LockstepRRTStar:
                 "h2d_bytes", "d2h_bytes", "_", "ns_prologue", "ns_fused_pass", "ns_candidates", "ns_append_edges",
                 "ns_replay"]
         return dict(zip(keys, [int(v) for v in out]))
+
+
+class BirrtConfig(C.Structure):
+    _fields_ = [("max_distance", C.c_double), ("min_distance", C.c_double), ("tolerance", C.c_double),
+                ("bidirectional", C.c_int32), ("extend", C.c_int32), ("capacity", C.c_uint32), ("depth_cap", C.c_uint32)]
+
+
+class LockstepBiRRT:
+    """P independent BiRRT (or, bidirectional=False, RRT) problems advanced together, entirely on the device: one kernel
+    launch per update, one warp per tree, the whole Tree::connect ray inside the kernel (csrc/birrt.cu; reference:
+    src/graph_core/solvers/birrt.cpp:93-152, rrt.cpp:119-157, tree.cpp:217-233).  Light worlds only."""
+
+    STATS = ("updates", "nodes_added", "edges", "states", "object_tests", "scans", "rescans", "solved")
+
+    def __init__(self, scenario, world: capi.CollisionWorld, starts, goals, capacity: int = 4096, bidirectional: bool = True,
+                 extend: bool = False, depth_cap: int = 0):
+        self.L = capi.load()
+        self.dim = scenario.dim
+        starts = _f64(np.atleast_2d(starts))
+        goals = _f64(np.atleast_2d(goals))
+        assert starts.shape == goals.shape and starts.shape[1] == self.dim
+        self.n = starts.shape[0]
+        self.world = world
+        cfg = BirrtConfig(scenario.max_distance, scenario.min_distance, 1e-6, 1 if bidirectional else 0,
+                          1 if extend else 0, int(capacity), int(depth_cap))
+        h = C.c_void_p()
+        capi._check(self.L.gc_birrt_create(world.handle, C.byref(cfg), self.n, starts.ctypes.data_as(_dp),
+                                           goals.ctypes.data_as(_dp), C.byref(h)))
+        self.h = h
+        self.capacity = int(capacity)
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.gc_birrt_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def step(self, samples):
+        """One update of every unsolved problem; samples[p] is problem p's sample (host array, staged through pinned
+        memory)."""
+        s = _f64(samples)
+        assert s.shape == (self.n, self.dim)
+        capi._check(self.L.gc_birrt_step(self.h, s.ctypes.data_as(_dp), None))
+
+    def step_device_samples(self, d_samples_ptr: int):
+        capi._check(self.L.gc_birrt_step(self.h, None, C.c_void_p(d_samples_ptr)))
+
+    def sync(self):
+        capi._check(self.L.gc_birrt_sync(self.h))
+
+    def stats(self):
+        out = (C.c_uint64 * 8)()
+        capi._check(self.L.gc_birrt_stats(self.h, out))
+        return dict(zip(self.STATS, (int(v) for v in out)))
+
+    def info(self, p: int):
+        solved, it, cost = C.c_int32(0), C.c_uint32(0), C.c_double(0.0)
+        ns, ng = C.c_uint32(0), C.c_uint32(0)
+        capi._check(self.L.gc_birrt_info(self.h, p, C.byref(solved), C.byref(it), C.byref(cost), C.byref(ns), C.byref(ng)))
+        return {"solved": bool(solved.value), "solved_iteration": it.value, "cost": cost.value, "size_start": ns.value,
+                "size_goal": ng.value}
+
+    def solved(self):
+        s = np.zeros(self.n, dtype=np.uint8)
+        c = np.zeros(self.n, dtype=np.float64)
+        capi._check(self.L.gc_birrt_read_solved(self.h, s.ctypes.data_as(C.POINTER(C.c_uint8)), c.ctypes.data_as(_dp)))
+        return s.astype(bool), c
+
+    def dump(self, p: int, tree: int):
+        """(parents, connection costs, configurations) of the start (0) or goal (1) tree of problem p in slot order."""
+        par = np.empty(self.capacity, dtype=np.int32)
+        pc = np.empty(self.capacity, dtype=np.float64)
+        cf = np.empty((self.capacity, self.dim), dtype=np.float64)
+        n = self.L.gc_birrt_dump(self.h, p, tree, par.ctypes.data_as(C.POINTER(C.c_int32)), pc.ctypes.data_as(_dp),
+                                 cf.ctypes.data_as(_dp))
+        if n < 0:
+            raise capi.GcError(n, self.L.gc_last_error().decode())
+        return par[:n].copy(), pc[:n].copy(), cf[:n].copy()
+
+    def solution(self, p: int, cap: int = 8192):
+        wp = np.empty((cap, self.dim), dtype=np.float64)
+        cs = np.empty(cap, dtype=np.float64)
+        n = self.L.gc_birrt_solution(self.h, p, wp.ctypes.data_as(_dp), cs.ctypes.data_as(_dp), cap)
+        if n < 0:
+            raise capi.GcError(n, self.L.gc_last_error().decode())
+        return wp[:n].copy(), cs[:max(n - 1, 0)].copy()

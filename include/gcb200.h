@@ -226,6 +226,43 @@ int gc_forest_dump(gc_forest_t* f, uint32_t p, int32_t* parents, double* pcost, 
 /* node ids root -> goal of the current solution (0 when unsolved); returns the length */
 int gc_forest_solution(gc_forest_t* f, uint32_t p, int32_t* ids, uint32_t cap);
 
+/* ---- device-resident lock-step BiRRT / RRT (BASELINE config 2) -------------------------------------------------
+ * P independent problems advance by one BiRRT::update (src/graph_core/solvers/birrt.cpp:93-152) -- or, with
+ * bidirectional = 0, one RRT::update (src/graph_core/solvers/rrt.cpp:119-157) -- per gc_birrt_step: ONE kernel launch,
+ * one warp per tree, the whole Tree::connect ray (src/graph_core/graph/tree.cpp:217-233: nearest node, steer, bisection
+ * edge check, append, repeat) inside the kernel.  Trees (configurations, parent slots, connection costs) live in device
+ * memory owned by the handle; light worlds only (cube, boxes, C-space spheres).  With the same samples every problem
+ * builds the reference's two trees, meets at the same iteration and returns the same path and cost. */
+typedef struct gc_birrt gc_birrt_t;
+typedef struct gc_birrt_config
+{
+  double max_distance;  /* tree_solver.cpp:37 */
+  double min_distance;  /* checker resolution */
+  double tolerance;     /* util.h:80 TOLERANCE (0 = 1e-6) */
+  int32_t bidirectional; /* 1 BiRRT, 0 RRT (goal connection of rrt.cpp:137-153) */
+  int32_t extend;       /* tree_solver.cpp `extend` parameter: 1 = one Tree::extend per tree and update, 0 = connect */
+  uint32_t capacity;    /* nodes per tree */
+  uint32_t depth_cap;   /* longest solution kept (connections, 0 = 4096) */
+} gc_birrt_config_t;
+int gc_birrt_create(gc_world_t* world, const gc_birrt_config_t* cfg, uint32_t n_problems, const double* starts,
+                    const double* goals, gc_birrt_t** out);
+int gc_birrt_destroy(gc_birrt_t* b);
+/* one update of every unsolved problem with sample p for problem p: samples[n_problems][dim] on the host (copied
+ * through pinned memory) or d_samples on the device; exactly one of the two.  Stream-ordered on the world's stream. */
+int gc_birrt_step(gc_birrt_t* b, const double* samples, const double* d_samples);
+/* waits for the stream; GC_E_CAPACITY when a tree or a solution outgrew its capacity since creation */
+int gc_birrt_sync(gc_birrt_t* b);
+/* out[0] updates of unsolved problems, [1] nodes added, [2] edges checked, [3] states evaluated, [4] (state, object)
+ * tests, [5] nearest-neighbour scans, [6] re-scans inside a ray, [7] problems solved */
+int gc_birrt_stats(gc_birrt_t* b, uint64_t out[8]);
+int gc_birrt_info(gc_birrt_t* b, uint32_t p, int32_t* solved, uint32_t* solved_iteration, double* cost,
+                  uint32_t* size_start, uint32_t* size_goal);
+int gc_birrt_read_solved(gc_birrt_t* b, uint8_t* solved, double* cost);
+/* tree 0 = start tree, 1 = goal tree of problem p in slot (= creation) order; returns the number of nodes */
+int gc_birrt_dump(gc_birrt_t* b, uint32_t p, int tree, int32_t* parents, double* pcost, double* conf);
+/* way points start -> goal and the connection costs between them; returns the number of way points (0 = unsolved) */
+int gc_birrt_solution(gc_birrt_t* b, uint32_t p, double* waypoints, double* costs, uint32_t cap);
+
 /* ---- Philox samplers (uniform_sampler.cpp:34-39, informed_sampler.cpp:145-180) -------------- */
 /* n uniform samples in [lb, ub]; sample i uses Philox counter (first_index + i) */
 int gc_sample_uniform(int device, int dim, const double* lb, const double* ub, uint64_t seed, uint64_t first_index,

@@ -88,6 +88,35 @@ def build(verbose=False):
     return True
 
 
+def patched_tree_sources():
+    """INTEGRATION.md section 3 applied to a BUILD-TIME copy of the reference's tree.h / tree.cpp under the git-ignored
+    oracle/_ref/patched/: a process-wide NearestNeighbors factory consulted by Tree::Tree before the stock
+    KdTree / Vector choice (tree.cpp:43-50).  The hook adds two static members (no change of the object layout), so
+    every other reference object stays as compiled from the untouched sources; nothing is copied into the repository."""
+    pdir = OUT / "patched"
+    hdir = pdir / "include" / "graph_core" / "graph"
+    hdir.mkdir(parents=True, exist_ok=True)
+    h = (REF / "include/graph_core/graph/tree.h").read_text()
+    anchor = "  bool use_kdtree_;"
+    assert h.count(anchor) == 1, "tree.h changed upstream: revisit the factory-hook patch"
+    h = h.replace(anchor, anchor + """
+public:
+  using NearestNeighborsFactory = std::function<NearestNeighborsPtr(const cnr_logger::TraceLoggerPtr&)>;
+  static void setNearestNeighborsFactory(NearestNeighborsFactory f) { nn_factory_() = std::move(f); }
+protected:
+  static NearestNeighborsFactory& nn_factory_() { static NearestNeighborsFactory f; return f; }
+""", 1)
+    h = "#include <functional>\n" + h
+    (hdir / "tree.h").write_text(h)
+    c = (REF / "src/graph_core/graph/tree.cpp").read_text()
+    anchor = "  if (use_kdtree)\n  {\n    nodes_ = std::make_shared<KdTree>(logger_);"
+    assert c.count(anchor) == 1, "tree.cpp changed upstream: revisit the factory-hook patch"
+    c = c.replace(anchor, "  if (nn_factory_())\n  {\n    nodes_ = nn_factory_()(logger_);\n  }\n  else if (use_kdtree)\n  {\n"
+                          "    nodes_ = std::make_shared<KdTree>(logger_);", 1)
+    (pdir / "tree.cpp").write_text(c)
+    return pdir
+
+
 def build_dropin(verbose=False):
     """oracle/_ref/libgc_ref_dropin.so: the reference's objects + graph_core_b200/host/cuda_plugins.cpp compiled with
     -DGCB200_WITH_GRAPH_CORE against the GENUINE graph_core headers + oracle/ref_dropin.cpp, linked with libgcb200.so
@@ -111,12 +140,15 @@ def build_dropin(verbose=False):
     inc = ["-I", str(HERE / "ref_shim"), "-I", str(REF / "include"), "-I", str(root / "include"), "-I", str(pkg / "host"),
            "-I", str(HERE), "-include", str(HERE / "ref_shim" / "shim_random.hpp")]
     objdir = OUT / "obj_libgc_ref"
-    objs = [o for o in objdir.glob("*.o") if o.name != "ref_driver.o"]  # ref_dropin.cpp includes ref_driver.cpp
+    # ref_dropin.cpp includes ref_driver.cpp; tree.o is rebuilt from the patched copy (NearestNeighbors factory hook)
+    objs = [o for o in objdir.glob("*.o") if o.name not in ("ref_driver.o", "tree.o")]
+    pdir = patched_tree_sources()
+    inc = ["-I", str(pdir / "include")] + inc
     extra = []
-    for src in (HERE / "ref_dropin.cpp", pkg / "host" / "cuda_plugins.cpp"):
+    for src in (HERE / "ref_dropin.cpp", pkg / "host" / "cuda_plugins.cpp", pdir / "tree.cpp"):
         obj = OUT / ("dropin_" + src.stem + ".o")
-        cmd = [cxx, "-std=c++17", "-fPIC", "-w", "-DNDEBUG", "-DGCB200_WITH_GRAPH_CORE", *flags, *inc, "-c", str(src), "-o",
-               str(obj)]
+        cmd = [cxx, "-std=c++17", "-fPIC", "-w", "-DNDEBUG", "-DGCB200_WITH_GRAPH_CORE", "-DGCB200_TREE_FACTORY_HOOK",
+               *flags, *inc, "-c", str(src), "-o", str(obj)]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError("ref_build: %s failed\n%s" % (src, r.stderr[-4000:]))

@@ -462,6 +462,34 @@ int ref_tree_recheck(void* h)
   return (t && t->recheckCollision()) ? 1 : 0;
 }
 
+// Tree::checkPathToNode (tree.cpp:335-373) towards the tree node closest to `conf` (pass a node's own configuration),
+// with the tree's checker or -- for the duration of the call -- other_checker.  costs[] receives the cost of every
+// connection root -> node afterwards, *n_path their number, *n_checked how many the call actually checked (the
+// "recently checked" ones are skipped, :345-352).  keep_flags == 0 clears the recently-checked marks again.
+int ref_check_path_to_node(void* h, void* other_checker, const double* conf, int keep_flags, int cap, double* costs,
+                           int* n_checked, int* n_path)
+{
+  RefSolver* s = (RefSolver*)h;
+  TreePtr t = s->solver->getStartTree();
+  if (!t)
+    return -1;
+  NodePtr node = t->findClosestNode(toVec(conf, s->dim));
+  CollisionCheckerPtr old = t->getChecker();
+  if (other_checker)
+    t->setChecker(((RefChecker*)other_checker)->c);
+  std::vector<ConnectionPtr> checked, path;
+  const bool ok = t->checkPathToNode(node, checked, path);
+  t->setChecker(old);
+  for (int i = 0; i < (int)path.size() && i < cap; i++)
+    costs[i] = path[i]->getCost();
+  *n_checked = (int)checked.size();
+  *n_path = (int)path.size();
+  if (!keep_flags)
+    for (const ConnectionPtr& c : checked)
+      c->setRecentlyChecked(false);
+  return ok ? 1 : 0;
+}
+
 // ---- Tree YAML (tree.cpp:1188-1227 toYAML, :1272-1389 fromYAML): the document as arrays ---------------------
 // Tree::toYAML() of the start tree: nodes[n][dim] in document order, connections[m][2] = (parent index, child
 // index) in document order.  Returns n (or -1); *nconn = m.

@@ -13,7 +13,10 @@
  */
 #include "ref_driver.cpp"
 
+#include "cuda_batched_helpers.h"
 #include "cuda_plugins.h"
+
+#include <atomic>
 
 namespace
 {
@@ -110,6 +113,127 @@ unsigned long long dropin_checker_device_calls(void* h)
   CudaCollisionChecker* c = dynamic_cast<CudaCollisionChecker*>(s->checker.get());
   return c ? c->deviceCalls() : 0ull;
 }
+#ifdef GCB200_TREE_FACTORY_HOOK
+// with the factory hook (applied to a build-time copy of tree.h / tree.cpp, see
+// oracle/ref_build.py: patched_tree_sources) EVERY Tree the solvers create -- BiRRT's goal tree (birrt.cpp:67),
+// AnytimeRRT's per-round trees (anytime_rrt.cpp:298), RRT's start tree (rrt.cpp:73) -- owns a CudaNearestNeighbors.
+// device < 0 removes the factory (stock KdTree / Vector again).
+static std::atomic<unsigned long long> g_factory_calls{ 0 };
+void dropin_set_nn_factory(int device)
+{
+  if (device < 0)
+  {
+    Tree::setNearestNeighborsFactory(nullptr);
+    return;
+  }
+  Tree::setNearestNeighborsFactory([device](const cnr_logger::TraceLoggerPtr& lg) -> NearestNeighborsPtr {
+    g_factory_calls++;
+    return std::make_shared<CudaNearestNeighbors>(lg, device);
+  });
+}
+unsigned long long dropin_nn_factory_calls() { return g_factory_calls.load(); }
+#endif
+
+// ---- SURVEY 8(f) N1-N3 with the edge checks batched (graph_core_b200/host/cuda_batched_helpers.h) -------------
+static std::shared_ptr<CudaCollisionChecker> cudaCheckerOf(RefSolver* s, void* other_checker)
+{
+  CollisionCheckerPtr c = other_checker ? ((RefChecker*)other_checker)->c : s->checker;
+  return std::dynamic_pointer_cast<CudaCollisionChecker>(c);
+}
+unsigned long long dropin_device_calls_of(void* h, void* other_checker)
+{
+  auto c = cudaCheckerOf((RefSolver*)h, other_checker);
+  return c ? c->deviceCalls() : 0ull;
+}
+// ref_solution_is_valid through cuda_batched::isValid: one device call for the whole path
+int dropin_solution_is_valid_batched(void* h, void* other_checker, int cap, double* costs)
+{
+  RefSolver* s = (RefSolver*)h;
+  PathPtr p = s->solver->getSolution();
+  auto chk = cudaCheckerOf(s, other_checker);
+  if (!p || !s->solver->solved() || !chk)
+    return -1;
+  const bool valid = cuda_batched::isValid(p, chk);
+  const std::vector<ConnectionPtr>& conns = p->getConnectionsConst();
+  for (int i = 0; i < (int)conns.size() && i < cap; i++)
+    costs[i] = conns[i]->getCost();
+  return valid ? 1 : 0;
+}
+int dropin_solution_is_valid_from_batched(void* h, void* other_checker, int conn_idx, double t)
+{
+  RefSolver* s = (RefSolver*)h;
+  PathPtr p = s->solver->getSolution();
+  auto chk = cudaCheckerOf(s, other_checker);
+  if (!p || !s->solver->solved() || !chk)
+    return -1;
+  const std::vector<ConnectionPtr>& conns = p->getConnectionsConst();
+  if (conn_idx < 0 || conn_idx >= (int)conns.size())
+    return -1;
+  const Eigen::VectorXd a = conns[conn_idx]->getParent()->getConfiguration();
+  const Eigen::VectorXd b = conns[conn_idx]->getChild()->getConfiguration();
+  const Eigen::VectorXd conf = a + (b - a) * t;
+  int pos = -1;
+  return cuda_batched::isValidFromConf(p, conf, (size_t)conn_idx, pos, chk) ? 1 : 0;
+}
+int dropin_tree_recheck_batched(void* h)
+{
+  RefSolver* s = (RefSolver*)h;
+  TreePtr t = s->solver->getStartTree();
+  auto chk = cudaCheckerOf(s, nullptr);
+  return (t && chk && cuda_batched::recheckCollision(t, chk)) ? 1 : 0;
+}
+int dropin_check_path_to_node_batched(void* h, void* other_checker, const double* conf, int keep_flags, int cap,
+                                      double* costs, int* n_checked, int* n_path)
+{
+  RefSolver* s = (RefSolver*)h;
+  TreePtr t = s->solver->getStartTree();
+  auto chk = cudaCheckerOf(s, other_checker);
+  if (!t || !chk)
+    return -1;
+  NodePtr node = t->findClosestNode(toVec(conf, s->dim));
+  CollisionCheckerPtr old = t->getChecker();
+  t->setChecker(chk);
+  std::vector<ConnectionPtr> checked, path;
+  const bool ok = cuda_batched::checkPathToNode(t, node, checked, path, chk);
+  t->setChecker(old);
+  for (int i = 0; i < (int)path.size() && i < cap; i++)
+    costs[i] = path[i]->getCost();
+  *n_checked = (int)checked.size();
+  *n_path = (int)path.size();
+  if (!keep_flags)
+    for (const ConnectionPtr& c : checked)
+      c->setRecentlyChecked(false);
+  return ok ? 1 : 0;
+}
+// ref_solution_optimize with cuda_batched::SpeculativePathLocalOptimizer
+int dropin_solution_optimize_speculative(void* h, int mode, int max_iter, int cap, double* conf, double* cost_out)
+{
+  RefSolver* s = (RefSolver*)h;
+  PathPtr p = s->solver->getSolution();
+  auto chk = cudaCheckerOf(s, nullptr);
+  if (!p || !s->solver->solved() || !chk)
+    return 0;
+  PathPtr q = p->clone();
+  cuda_batched::SpeculativePathLocalOptimizer opt(chk, s->metrics, g_logger);
+  opt.config("/ref_driver/path_optimizer");
+  opt.setPath(q);
+  if (mode == 0)
+    for (int i = 0; i < max_iter; i++)
+      opt.warpSpeculative();
+  else if (mode == 1)
+    for (int i = 0; i < max_iter; i++)
+      opt.simplifySpeculative();
+  else
+    opt.solve((unsigned int)max_iter, 1.0e9);
+  std::vector<Eigen::VectorXd> wp = q->getWaypoints();
+  for (int i = 0; i < (int)wp.size() && i < cap; i++)
+    for (int k = 0; k < s->dim; k++)
+      conf[(size_t)i * s->dim + k] = wp[i](k);
+  if (cost_out)
+    *cost_out = q->cost();
+  return (int)wp.size();
+}
+
 int dropin_uses_cuda_nn(void* h)
 {
   RefSolver* s = (RefSolver*)h;

@@ -87,6 +87,7 @@ def lib(fast: bool = False, dropin: bool = False):
         "ref_solution_is_valid_from": (C.c_int, [vp, vp, C.c_int, C.c_double]),
         "ref_solution_optimize": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, _dp, _dp]),
         "ref_tree_recheck": (C.c_int, [vp]),
+        "ref_check_path_to_node": (C.c_int, [vp, vp, _dp, C.c_int, C.c_int, _dp, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
         "ref_srand": (None, [C.c_uint]),
         "ref_sample_informed": (None, [C.c_int, _dp, _dp, _dp, _dp, C.c_double, C.c_int, _dp]),
         "ref_informed_specific_volume": (C.c_double, [C.c_int, _dp, _dp, _dp, _dp, C.c_double]),
@@ -98,6 +99,15 @@ def lib(fast: bool = False, dropin: bool = False):
         sig["dropin_checker_new"] = (vp, [C.c_int, vp, C.c_double])
         sig["dropin_checker_device_calls"] = (C.c_ulonglong, [vp])
         sig["dropin_uses_cuda_nn"] = (C.c_int, [vp])
+        sig["dropin_set_nn_factory"] = (None, [C.c_int])
+        sig["dropin_nn_factory_calls"] = (C.c_ulonglong, [])
+        sig["dropin_device_calls_of"] = (C.c_ulonglong, [vp, vp])
+        sig["dropin_solution_is_valid_batched"] = (C.c_int, [vp, vp, C.c_int, _dp])
+        sig["dropin_solution_is_valid_from_batched"] = (C.c_int, [vp, vp, C.c_int, C.c_double])
+        sig["dropin_tree_recheck_batched"] = (C.c_int, [vp])
+        sig["dropin_check_path_to_node_batched"] = (C.c_int, [vp, vp, _dp, C.c_int, C.c_int, _dp, C.POINTER(C.c_int),
+                                                            C.POINTER(C.c_int)])
+        sig["dropin_solution_optimize_speculative"] = (C.c_int, [vp, C.c_int, C.c_int, C.c_int, _dp, _dp])
     for name, (res, args) in sig.items():
         fn = getattr(L, name)
         fn.restype = res
@@ -343,6 +353,17 @@ class RefSolver:
     def recheck_tree(self):
         return bool(self.L.ref_tree_recheck(self.h))
 
+    def check_path_to_node(self, conf, other_checker=None, keep_flags=False, _fn=None):
+        """Tree::checkPathToNode (tree.cpp:335-373) towards the tree node at `conf`: (ok, costs of the connections
+        root -> node afterwards, number of connections the call checked)."""
+        conf = _f64(conf)
+        costs = np.empty(1 << 14)
+        nc, npth = C.c_int(0), C.c_int(0)
+        fn = _fn or self.L.ref_check_path_to_node
+        r = fn(self.h, other_checker.h if other_checker is not None else None, _p(conf, _dp), 1 if keep_flags else 0,
+               costs.shape[0], _p(costs, _dp), C.byref(nc), C.byref(npth))
+        return r, costs[:npth.value].copy(), nc.value
+
 
 def cuda_ref_checker(cuda_world, min_distance):
     """A RefChecker whose CollisionCheckerBase is graph::core::CudaCollisionChecker over a CUDA world."""
@@ -379,6 +400,33 @@ class DropinSolver(RefSolver):
     @property
     def uses_cuda_nn(self):
         return bool(self.L.dropin_uses_cuda_nn(self.h))
+
+    # SURVEY 8(f) N1-N3 through graph_core_b200/host/cuda_batched_helpers.h (edge checks gathered into device batches)
+    def device_calls_of(self, other_checker=None):
+        return int(self.L.dropin_device_calls_of(self.h, other_checker.h if other_checker is not None else None))
+
+    def solution_is_valid_batched(self, other_checker=None):
+        costs = np.empty(1 << 14)
+        r = self.L.dropin_solution_is_valid_batched(self.h, other_checker.h if other_checker is not None else None,
+                                                    costs.shape[0], _p(costs, _dp))
+        n = max(len(self.solution()) - 1, 0)
+        return r, costs[:n].copy()
+
+    def solution_is_valid_from_batched(self, conn_idx, t, other_checker=None):
+        return self.L.dropin_solution_is_valid_from_batched(self.h, other_checker.h if other_checker is not None else None,
+                                                            conn_idx, t)
+
+    def recheck_tree_batched(self):
+        return bool(self.L.dropin_tree_recheck_batched(self.h))
+
+    def check_path_to_node_batched(self, conf, other_checker=None, keep_flags=False):
+        return self.check_path_to_node(conf, other_checker, keep_flags, _fn=self.L.dropin_check_path_to_node_batched)
+
+    def optimize_solution_speculative(self, mode, max_iter):
+        wp = np.empty((1 << 14, self.dim))
+        cost = C.c_double(0.0)
+        n = self.L.dropin_solution_optimize_speculative(self.h, mode, max_iter, wp.shape[0], _p(wp, _dp), C.byref(cost))
+        return wp[:n].copy(), cost.value
 
 
 def tree_as_edges(conf, parent_conf, pcost):

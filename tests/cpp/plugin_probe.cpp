@@ -2,6 +2,7 @@
 // NearestNeighbors and CollisionCheckerBase (src/graph_core/graph/tree.cpp:56-59, 751-765, 815-825;
 // collision_checker_base.h:166-313), through the cnr_class_loader factory names.
 // Exit code 0 and "PROBE OK" on success.  Needs a CUDA device: without one it must fail loudly.
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -335,6 +336,52 @@ static void testSpeculativeRewire()
   CHECK(nf > 0 && nf < 100, "both outcomes (%d free)", nf);
 }
 
+// Tree::nearK on a large high-dimensional tree (tree.cpp:52-53, 761-765): k = ceil(k_rrt * ln(N + 1)) >= N, so
+// kNearestNeighbors returns every node in ascending (distance, insertion) order -- lists far beyond one CTA's sort
+// capacity -- and near() with a radius that catches most of the tree does the same.
+static void testLargeResultSets()
+{
+  cnr_logger::TraceLoggerPtr logger;
+  cnr::param::set("/probe/nnl/capacity", 65536.0);
+  cnr::param::set("/probe/nnl/device_id", 0.0);
+  auto plugin = cnr_class_loader::createInstance<NearestNeighborsPlugin>("graph::core::CudaNearestNeighborsPlugin");
+  if (!plugin || !plugin->init("/probe/nnl", logger))
+  {
+    CHECK(false, "plugin init failed");
+    return;
+  }
+  NearestNeighborsPtr nn = plugin->getNearestNeighbors();
+  const int d = 12, N = 40000;
+  std::vector<NodePtr> nodes;
+  for (int i = 0; i < N; i++)
+  {
+    nodes.push_back(std::make_shared<Node>(randomConf(d, -3.14, 3.14), logger));
+    nn->insert(nodes.back());
+  }
+  const Eigen::VectorXd q = randomConf(d, -3.14, 3.14);
+  const double k_rrt = 1.1 * std::pow(2.0, d + 1) * std::exp(1.0) * (1.0 + 1.0 / d);
+  const size_t k = (size_t)std::ceil(k_rrt * std::log(N + 1.0));
+  std::multimap<double, NodePtr> all = nn->kNearestNeighbors(q, k);
+  CHECK(all.size() == (size_t)N, "k >= N returns every node (%zu)", all.size());
+  std::vector<std::pair<double, int>> want;
+  for (int i = 0; i < N; i++)
+    want.emplace_back(norm(nodes[i]->getConfiguration(), q), i);
+  std::sort(want.begin(), want.end());
+  size_t j = 0;
+  bool same = all.size() == (size_t)N;
+  for (auto it = all.begin(); same && it != all.end(); ++it, ++j)
+    same = it->first == want[j].first && it->second == nodes[want[j].second];
+  CHECK(same, "k >= N order mismatch at rank %zu", j);
+  const double radius = want[30000].first;  // strict <: exactly the 30000 nearer nodes (no ties in random data)
+  std::multimap<double, NodePtr> nr = nn->near(q, radius);
+  CHECK(nr.size() == 30000, "near() with %zu hits", nr.size());
+  j = 0;
+  same = nr.size() == 30000;
+  for (auto it = nr.begin(); same && it != nr.end(); ++it, ++j)
+    same = it->first == want[j].first && it->second == nodes[want[j].second];
+  CHECK(same, "large near() order mismatch at rank %zu", j);
+}
+
 int main()
 {
   try
@@ -342,6 +389,7 @@ int main()
     testNearestNeighbors();
     testCollisionChecker();
     testSpeculativeRewire();
+    testLargeResultSets();
   }
   catch (const std::exception& e)
   {

@@ -137,3 +137,107 @@ def test_sharded_merge_p2p_kernel_emulated_shards(gc, orc, G):
     ov.insert(pts)
     ri, rd, rc = ov.knn(qs, k, k)
     assert np.array_equal(oi.cpu().numpy(), ri) and np.array_equal(od.cpu().numpy(), rd) and np.array_equal(oc.cpu().numpy(), rc)
+
+
+# ---- beyond one CTA's sort capacity (16 384 entries): run sort + rank-merge passes -------------------------------
+def test_knn_all_nodes_sorted_like_tree_nearK(gc, orc):
+    """Tree::nearK asks for k = ceil(k_rrt * ln(N + 1)) neighbours (tree.cpp:52-53, 761-765); in 12 dimensions k_rrt =
+    1.1 * 2^13 * e * 13/12 is far above N, so the answer is every live node in (distance, slot) order."""
+    dim, n = 12, 1 << 17
+    pts = W.c4_nodes(n, dim, seed=291)
+    qs = W.c4_queries(3, dim, seed=292)
+    k_rrt = 1.1 * 2.0 ** (dim + 1) * np.e * (1.0 + 1.0 / dim)
+    k = int(np.ceil(k_rrt * np.log(n + 1)))
+    assert k >= n
+    st = gc.NodeStore(dim, n)
+    st.append(pts)
+    dead = [5, 70000, n - 1]
+    for s in dead:
+        st.tombstone(s)
+    gi, gd, gcnt = st.knn(qs, k, cap=n)
+    assert np.all(gcnt == n - len(dead))
+    d = np.empty((len(qs), n))
+    for j, q in enumerate(qs):  # Eigen (a-b).norm(): sequential sum of squares
+        s = np.zeros(n)
+        for c in range(dim):
+            t = pts[:, c] - q[c]
+            s = s + t * t
+        d[j] = np.sqrt(s)
+    d[:, dead] = np.inf
+    for j in range(len(qs)):
+        order = np.lexsort((np.arange(n), d[j]))[: n - len(dead)]
+        assert np.array_equal(gi[j, : n - len(dead)].astype(np.int64), order)
+        assert np.array_equal(gd[j, : n - len(dead)], d[j, order])
+
+
+@pytest.mark.parametrize("n,dim,k", [(50000, 7, 20000), (40000, 12, 39999), (33000, 3, 16385)])
+def test_knn_k_above_sort_capacity(gc, orc, n, dim, k):
+    pts = W.c4_nodes(n, dim, seed=293)
+    pts[1000:1400] = pts[:400]  # exact ties across the result: the lower slot comes first
+    qs = np.vstack([W.c4_queries(3, dim, seed=294), pts[:1]])
+    st = gc.NodeStore(dim, n)
+    st.append(pts)
+    ov = orc.OracleNN("vector", dim)
+    ov.insert(pts)
+    gi, gd, gcnt = st.knn(qs, k, cap=k)
+    oi, od, oc = ov.knn(qs, k, k)
+    assert np.array_equal(gcnt.astype(np.int64), oc.astype(np.int64))
+    assert np.array_equal(gd, od)
+    assert np.array_equal(gi.astype(np.int64), oi.astype(np.int64))
+
+
+def test_radius_list_above_sort_capacity(gc, orc):
+    dim, n = 3, 70000
+    pts = W.c4_nodes(n, dim, seed=295)
+    qs = W.c4_queries(4, dim, seed=296)
+    st = gc.NodeStore(dim, n)
+    st.append(pts)
+    ov = orc.OracleNN("vector", dim)
+    ov.insert(pts)
+    radius = 3.2
+    ri, rd, rc = ov.near(qs, radius, n)
+    assert rc.max() > 16384
+    gi, gd, gcnt = st.near(qs, radius, cap=512)  # grows on GC_W_TRUNCATED
+    assert np.array_equal(gcnt.astype(np.int64), rc.astype(np.int64))
+    for q in range(len(qs)):
+        assert np.array_equal(gi[q, :rc[q]].astype(np.int64), ri[q, :rc[q]].astype(np.int64))
+        assert np.array_equal(gd[q, :rc[q]], rd[q, :rc[q]])
+
+
+@pytest.mark.parametrize("p2p", [False, True])
+def test_sharded_merge_above_sort_capacity(gc, orc, p2p):
+    import ctypes as C
+    from graph_core_b200.sharded import CudaShardEngine
+    from graph_core_b200 import capi
+    G, dim, n, k = 4, 5, 60000, 9000  # 4 x 9000 gathered entries > 16 384
+    pts = W.c4_nodes(n, dim, seed=297)
+    qs = W.c4_queries(5, dim, seed=298)
+    engines = []
+    for g in range(G):
+        e = CudaShardEngine(dim, n // G + 2, 0)
+        e.append(pts[g::G])
+        engines.append(e)
+    lists = [e.knn_lists(qs, k) for e in engines]
+    torch.cuda.synchronize()
+    ov = orc.OracleNN("vector", dim)
+    ov.insert(pts)
+    ri, rd, rc = ov.knn(qs, k, k)
+    if not p2p:
+        idx = torch.stack([l[0] for l in lists])
+        dd = torch.stack([l[1] for l in lists])
+        cnt = torch.stack([l[2] for l in lists])
+        oi, od, oc = engines[0].merge(idx, dd, cnt, k, k)
+    else:
+        arr = C.c_void_p * G
+        ip = arr(*[C.c_void_p(l[0].data_ptr()) for l in lists])
+        dp = arr(*[C.c_void_p(l[1].data_ptr()) for l in lists])
+        cp = arr(*[C.c_void_p(l[2].data_ptr()) for l in lists])
+        nq = len(qs)
+        oi = torch.full((nq, k), -1, dtype=torch.int32, device="cuda")
+        od = torch.full((nq, k), float("inf"), dtype=torch.float64, device="cuda")
+        oc = torch.zeros(nq, dtype=torch.int32, device="cuda")
+        capi._check(capi.load().gc_merge_shard_lists_p2p_dev(0, torch.cuda.current_stream().cuda_stream, G, nq, k, ip, dp,
+                                                             cp, k, k, oi.data_ptr(), od.data_ptr(), oc.data_ptr()))
+    torch.cuda.synchronize()
+    assert np.array_equal(oc.cpu().numpy(), rc)
+    assert np.array_equal(od.cpu().numpy(), rd) and np.array_equal(oi.cpu().numpy(), ri)
