@@ -362,6 +362,109 @@ def knn_c4(g, torch, dist_mod, rank, world, dev, hbm_peak, fp32_peak, n_nodes=1 
     return res
 
 
+def c2_legs(g, torch, dev, ncores, problems=16384, iters=64):
+    """BASELINE config 2 (rank 0): (i) the 2^20-segment edge micro-benchmark of SURVEY 8(d) (tools/edge_bench.py) with the
+    reference's checkConnection loop timed beside it on one host core; (ii) lock-step BiRRT (graph_core_b200/csrc/birrt.cu):
+    `problems` independent 6-DoF problems (the 256 start/goal pairs of seed 202, replicated with their own sample streams),
+    `iters` updates each or until solved, samples resident in HBM; a few problems are replayed through the reference's own
+    BiRRT (oracle/_ref) on the same samples as the in-bench parity check."""
+    sys.path.insert(0, str(ROOT / "tools"))
+    import ctypes as C
+    import edge_bench
+    from graph_core_b200 import worlds as W
+    from graph_core_b200.planner import LockstepBiRRT
+    out = {}
+    eb, h1, h2, free = edge_bench.gpu_legs()
+    sys.path.insert(0, str(ROOT / "oracle"))
+    import oracle_py as orc
+    orc.build()
+    sc = W.scenario_c2()
+    ow = orc.OracleWorld.from_scenario(sc, fast=True)
+    m = 20000
+    t0 = time.perf_counter()
+    cok = ow.check_connection(h1[:m], h2[:m], 0.01, 0)
+    dt = time.perf_counter() - t0
+    eb["parity"] = {"verdicts_equal_to_oracle": bool(np.array_equal(np.asarray(cok).astype(bool), free[:m])), "edges": m}
+    eb["cpu_baseline"] = {"value": m / dt, "unit": "edges/s", "cores": 1, "kind": "port",
+                          "sample": "first %d segments of the batch, the restatement of checkConnection "
+                                    "(collision_checker_base.h:207-237) with the reference's Release flags, one host core "
+                                    "(the reference is single-threaded), %.2f s" % (m, dt)}
+    out["edge_microbench"] = eb
+    # ---- lock-step BiRRT ---------------------------------------------------------------------------------------
+    npairs = 256
+    u = W.philox_u01(202, 0, 4 * npairs, 2 * sc.dim)
+    s_all = sc.lb + u[:, :sc.dim] * (sc.ub - sc.lb)
+    g_all = sc.lb + u[:, sc.dim:] * (sc.ub - sc.lb)
+    w = g.CollisionWorld.cspheres(sc.params["centers"], sc.params["radii"], dev)
+    okp = w.check(s_all).astype(bool) & w.check(g_all).astype(bool)
+    s_all, g_all = s_all[okp][:npairs], g_all[okp][:npairs]
+    P = problems
+    starts = np.tile(s_all, (P // len(s_all) + 1, 1))[:P]
+    goals = np.tile(g_all, (P // len(g_all) + 1, 1))[:P]
+    st = torch.cuda.Stream()
+    w.set_stream(st.cuda_stream)
+    lk = LockstepBiRRT(sc, w, starts, goals, capacity=2048, bidirectional=True, extend=False)
+    d_samples = torch.empty((iters, P, sc.dim), dtype=torch.float64, device="cuda")
+    lb64 = np.ascontiguousarray(sc.lb, dtype=np.float64)
+    ub64 = np.ascontiguousarray(sc.ub, dtype=np.float64)
+    dp = C.POINTER(C.c_double)
+    rc = g.capi.load().gc_sample_uniform_dev(dev, sc.dim, lb64.ctypes.data_as(dp), ub64.ctypes.data_as(dp), 20300, 0,
+                                             iters * P, d_samples.data_ptr(), None)
+    assert rc == 0
+    torch.cuda.synchronize()
+    solved0, _ = lk.solved()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with torch.cuda.stream(st):
+        e0.record(st)
+        for i in range(iters):
+            lk.step_device_samples(d_samples[i].data_ptr())
+        e1.record(st)
+    torch.cuda.synchronize()
+    lk.sync()
+    ms = e0.elapsed_time(e1)
+    stt = lk.stats()
+    solved, costs = lk.solved()
+    bi = {"problems": P, "iterations": iters, "ms": ms, "updates": stt["updates"],
+          "updates_per_s": stt["updates"] / (ms * 1e-3), "ms_per_iteration": ms / iters,
+          "solved_by_direct_connection": float(solved0.mean()), "solved_fraction": float(solved.mean()),
+          "nodes_added": stt["nodes_added"], "edges_checked": stt["edges"], "states_evaluated": stt["states"],
+          "launches_per_iteration": 1,
+          "what": "one kernel launch per BiRRT::update of every unsolved problem (birrt.cpp:93-152), one warp per tree, "
+                  "the whole Tree::connect ray inside the kernel; solved problems idle"}
+    # parity + CPU arm on the reference's own BiRRT (same samples)
+    try:
+        import ref_py
+        hs = d_samples.cpu().numpy()
+        npar = 8
+        same = True
+        t0 = time.perf_counter()
+        upd = 0
+        for p in [P * j // npar for j in range(npar)]:
+            chk = ref_py.RefChecker.over_oracle_world(orc.OracleWorld.from_scenario(sc, fast=True), sc.min_distance, fast=True)
+            cpu = ref_py.RefSolver(ref_py.RefSolver.BIRRT, sc, chk, start=starts[p], goal=goals[p], informed=False, fast=True)
+            used = cpu.run(hs[:, p])
+            upd += used if cpu.solved else iters
+            info = lk.info(p)
+            ok = info["solved"] == cpu.solved
+            if ok and cpu.solved and info["solved_iteration"] > 0:
+                wp, _ = lk.solution(p)
+                ok = info["solved_iteration"] == used and abs(info["cost"] - cpu.cost) <= 1e-9 * cpu.cost and \
+                    np.allclose(wp, cpu.solution(), rtol=0, atol=1e-12)
+            same = same and ok
+        dt = time.perf_counter() - t0
+        bi["parity"] = {"same_as_reference_birrt": bool(same), "problems_checked": npar,
+                        "note": "timing build of the reference (-Ofast): iteration, cost and way points compared with "
+                                "1e-9 / 1e-12 tolerances here, bit-exact against the parity build in tests/test_birrt_gpu.py"}
+        bi["cpu_baseline"] = {"value": upd / dt, "unit": "updates/s", "cores": 1, "kind": "reference",
+                              "sample": "%d of the problems through graph_core's own BiRRT (oracle/_ref, Release flags), "
+                                        "one host core, %.2f s" % (npar, dt)}
+    except Exception as ex:
+        bi["parity"] = {"error": str(ex)[:200]}
+    lk.close()
+    out["birrt"] = bi
+    return out
+
+
 def main():
     args = parse_args()
     rank, local_rank, world_size = dist_env()
@@ -701,6 +804,10 @@ def main():
             line["depth_sweep"] = depth_sweep(g, torch, LockstepRRTStar, sc, root_world, starts, goals, dev)
         except Exception as ex:
             line["depth_sweep"] = {"error": str(ex)[:300]}
+        try:
+            line["c2"] = c2_legs(g, torch, dev, ncores)
+        except Exception as ex:
+            line["c2"] = {"error": str(ex)[:300]}
     if rank == 0:
         # ---- in-bench parity check: 16 problems, full depth, against the oracle on the same samples -----------
         sys.path.insert(0, str(ROOT / "oracle"))

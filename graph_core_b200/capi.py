@@ -131,6 +131,10 @@ PROTOTYPES = {
     "gc_birrt_read_solved": (C.c_int, [C.c_void_p, _c_u8_p, _c_double_p]),
     "gc_birrt_dump": (C.c_int, [C.c_void_p, C.c_uint32, C.c_int, _c_i32_p, _c_double_p, _c_double_p]),
     "gc_birrt_solution": (C.c_int, [C.c_void_p, C.c_uint32, _c_double_p, _c_double_p, C.c_uint32]),
+    "gc_informed_extend_batch": (C.c_int, [C.c_void_p, C.c_void_p, _c_double_p, _c_u32_p, _c_double_p, _c_double_p,
+                                           _c_double_p, C.c_uint32, C.c_double, C.c_double, C.c_double, C.c_double,
+                                           C.c_void_p, C.c_void_p, _c_u8_p, _c_u32_p, _c_double_p, _c_double_p,
+                                           _c_double_p, _c_u64_p]),
     "gc_launch_count": (C.c_int, [_c_u64_p]),
     "gc_measure_fp32_peak": (C.c_int, [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "gc_flush_l2": (C.c_int, [C.c_int, C.c_size_t]),
@@ -469,6 +473,33 @@ def extend_batch(store: NodeStore, world: CollisionWorld, q, seg, max_distance, 
                              _ptr(ndist, _c_double_p), _ptr(ncount, _c_u32_p))
     _check(rc)
     return closest, dist, nxt, ok, nidx, ndist, ncount
+
+
+def informed_extend_batch(store: NodeStore, world: CollisionWorld, q, seg, goal, cost2beat, bias, k_rrt, max_distance,
+                          min_distance, d_parent_ptr: int, d_pcost_ptr: int, tolerance=1e-6):
+    """Tree::informedExtend (tree.cpp:235-302) for n (sample, tree) pairs; d_parent_ptr / d_pcost_ptr are device
+    pointers to int32 / float64 arrays indexed by global slot.  Returns a dict of host arrays."""
+    lib = load()
+    q = _f64(q, (-1, store.dim))
+    n = q.shape[0]
+    goal = _f64(goal, (-1, store.dim))
+    seg = np.ascontiguousarray(seg, dtype=np.uint32)
+    c2b = np.ascontiguousarray(np.broadcast_to(np.asarray(cost2beat, dtype=np.float64), (n,)))
+    bs = np.ascontiguousarray(np.broadcast_to(np.asarray(bias, dtype=np.float64), (n,)))
+    ok = np.zeros(n, dtype=np.uint8)
+    node = np.zeros(n, dtype=np.uint32)
+    new = np.zeros((n, store.dim), dtype=np.float64)
+    dist = np.zeros(n, dtype=np.float64)
+    ecost = np.zeros(n, dtype=np.float64)
+    edges = C.c_uint64(0)
+    _check(lib.gc_informed_extend_batch(store.handle, world.handle, _ptr(q, _c_double_p), _ptr(seg, _c_u32_p),
+                                        _ptr(goal, _c_double_p), _ptr(c2b, _c_double_p), _ptr(bs, _c_double_p), n,
+                                        float(k_rrt), float(max_distance), float(min_distance), float(tolerance),
+                                        C.c_void_p(d_parent_ptr), C.c_void_p(d_pcost_ptr), _ptr(ok, _c_u8_p),
+                                        _ptr(node, _c_u32_p), _ptr(new, _c_double_p), _ptr(dist, _c_double_p),
+                                        _ptr(ecost, _c_double_p), C.byref(edges)))
+    return {"ok": ok.astype(bool), "node": node, "new_conf": new, "distance": dist, "edge_cost": ecost,
+            "edges_checked": int(edges.value)}
 
 
 def launch_count() -> int:

@@ -69,6 +69,7 @@ struct BirrtDev
   unsigned long long* stats;  // [0] updates of unsolved problems [1] nodes added [2] edges checked [3] states
                               // [4] (state, object) tests [5] scans [6] re-scans inside a ray [7] problems solved
   uint32_t iteration;
+  int setup;  // 1: TreeSolver::setProblem's direct connection start -> goal instead of an update
   // world
   int kind;
   uint32_t nobj;
@@ -143,7 +144,7 @@ __device__ __forceinline__ void warp_nearest(const double* __restrict__ conf, ui
 // boolean; new_node = the last node appended (valid when true).
 template <int D>
 __device__ bool warp_connect(const BirrtDev& b, const LightWorld& w, uint32_t tree, const double* q, int lane,
-                             int32_t& new_node, RayStats& st)
+                             int32_t& new_node, RayStats& st, bool force_connect)
 {
   double* conf = b.conf + (size_t)tree * b.cap * D;
   BNode* nodes = b.nodes + (size_t)tree * b.cap;
@@ -189,7 +190,7 @@ __device__ bool warp_connect(const BirrtDev& b, const LightWorld& w, uint32_t tr
     }
     __syncwarp();
     new_node = (int32_t)slot;
-    if (b.extend)
+    if (b.extend && !force_connect)
     {
       result = true;
       break;
@@ -221,32 +222,7 @@ __global__ void __launch_bounds__(256) birrt_step_kernel(BirrtDev b)
 {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   LightWorld w;
-  w.kind = b.kind;
-  w.nobj = b.nobj;
-  w.cube_thr = b.cube_thr;
-  {
-    double* slo = reinterpret_cast<double*>(smem_raw);
-    double* shi = slo + (b.kind == GC_WORLD_BOXES ? (size_t)b.nobj * D : 0);
-    float* ssc = reinterpret_cast<float*>(shi + (b.kind == GC_WORLD_BOXES ? (size_t)b.nobj * D : 0));
-    float* ssr = ssc + (b.kind == GC_WORLD_CSPHERES ? (size_t)b.nobj * D : 0);
-    if (b.kind == GC_WORLD_BOXES)
-      for (uint32_t i = threadIdx.x; i < b.nobj * D; i += blockDim.x)
-      {
-        slo[i] = b.lo[i];
-        shi[i] = b.hi[i];
-      }
-    if (b.kind == GC_WORLD_CSPHERES)
-    {
-      for (uint32_t i = threadIdx.x; i < b.nobj * D; i += blockDim.x)
-        ssc[i] = b.sc[i];
-      for (uint32_t i = threadIdx.x; i < b.nobj; i += blockDim.x)
-        ssr[i] = b.sr2[i];
-    }
-    w.lo = slo;
-    w.hi = shi;
-    w.sc = ssc;
-    w.sr2 = ssr;
-  }
+  light_stage<D>(w, smem_raw, b.kind, b.nobj, b.cube_thr, b.lo, b.hi, b.sc, b.sr2);
   __shared__ int s_added[8];
   __shared__ int32_t s_new[8];
   __syncthreads();
@@ -259,12 +235,16 @@ __global__ void __launch_bounds__(256) birrt_step_kernel(BirrtDev b)
   double q[D];
   int32_t new_node = -1;
   bool added = false;
-  if (live && (t == 0 || b.bidirectional))
+  const bool setup = b.setup != 0;
+  if (live && (t == 0 || (b.bidirectional && !setup)))
   {
+    // setup: Tree::connectToNode(goal) (tree.cpp:304-327, through extendToNode :192-215) -- the same ray as connect;
+    // the node that lands on the goal configuration IS the goal node
+    const double* src = setup ? b.goals : b.samples;
 #pragma unroll
     for (int i = 0; i < D; i++)
-      q[i] = b.samples[(size_t)p * D + i];
-    added = warp_connect<D>(b, w, 2u * p + (uint32_t)t, q, lane, new_node, st);
+      q[i] = src[(size_t)p * D + i];
+    added = warp_connect<D>(b, w, 2u * p + (uint32_t)t, q, lane, new_node, st, setup);
   }
   if (lane == 0)
   {
@@ -281,7 +261,40 @@ __global__ void __launch_bounds__(256) birrt_step_kernel(BirrtDev b)
     uint32_t* way = b.sol_slot + (size_t)p * (b.depth_cap + 1);
     double* wcost = b.sol_cost + (size_t)p * b.depth_cap;
     uint32_t len = 0;
-    if (b.bidirectional)
+    if (setup)
+    {
+      // TreeSolver::setProblem (tree_solver.cpp:84-98): a direct connection is the solution
+      if (s_added[wib])
+      {
+        solved = true;
+        if (lane == 0)
+        {
+          uint32_t ls = 0;
+          for (int32_t x = new_s; x != 0; x = nodes_s[x].parent)
+            ls++;
+          len = ls;
+          if (len > b.depth_cap)
+          {
+            atomicOr(b.err, kBirrtErrDepth);
+            len = 0;
+          }
+          else
+          {
+            uint32_t k = ls;
+            way[0] = 0u;
+            for (int32_t x = new_s; x != 0;)
+            {
+              const BNode nd = nodes_s[x];
+              way[k] = (uint32_t)x;
+              wcost[k - 1] = nd.pcost;
+              k--;
+              x = nd.parent;
+            }
+          }
+        }
+      }
+    }
+    else if (b.bidirectional)
     {
       const double* conf_g = b.conf + (size_t)(2u * p + 1u) * b.cap * D;
       const BNode* nodes_g = b.nodes + (size_t)(2u * p + 1u) * b.cap;
@@ -405,7 +418,7 @@ __global__ void __launch_bounds__(256) birrt_step_kernel(BirrtDev b)
       pr.solved = 1u;
       atomicAdd(&b.stats[7], 1ull);
     }
-    if (lane == 0)
+    if (lane == 0 && !setup)
       atomicAdd(&b.stats[0], 1ull);
   }
   // statistics: one atomic per warp and counter
@@ -508,10 +521,7 @@ int gc_birrt_create(gc_world_t* w, const gc_birrt_config_t* cfg, uint32_t n_prob
   d.hi = root->d_hi;
   d.sc = root->d_sc;
   d.sr2 = root->d_sr2;
-  if (w->kind == GC_WORLD_BOXES)
-    b->smem = 2 * sizeof(double) * (size_t)w->nobj * D;
-  else if (w->kind == GC_WORLD_CSPHERES)
-    b->smem = sizeof(float) * ((size_t)w->nobj * D + w->nobj);
+  b->smem = light_smem_bytes(w->kind, w->nobj, D);
   const size_t trees = 2 * (size_t)n_problems;
   auto alloc = [&](void** p, size_t bytes) -> cudaError_t {
     cudaError_t e = cudaMalloc(p, bytes);
@@ -594,6 +604,27 @@ int gc_birrt_create(gc_world_t* w, const gc_birrt_config_t* cfg, uint32_t n_prob
     gc_birrt_destroy(b);
     return GC_E_CUDA;
   }
+  // TreeSolver::setProblem (tree_solver.cpp:84-104): the direct connection start -> goal, which also leaves its ray in
+  // the start tree when it is blocked half way
+  {
+    BirrtDev ds = b->d;
+    ds.setup = 1;
+    ds.iteration = 0;
+    if (b->smem > 48 * 1024)
+      GC_BIRRT_DISPATCH(ds.D, GC_CUDA(cudaFuncSetAttribute(birrt_step_kernel<DD>,
+                                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->smem)));
+    GC_BIRRT_DISPATCH(ds.D, (birrt_step_kernel<DD><<<(ds.P + 3u) / 4u, 256, b->smem, st>>>(ds)));
+    e = cudaGetLastError();
+    count_launch();
+    if (e == cudaSuccess)
+      e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess)
+    {
+      gc::set_error("gc_birrt_create: %s", cudaGetErrorString(e));
+      gc_birrt_destroy(b);
+      return GC_E_CUDA;
+    }
+  }
   *out = b;
   return GC_OK;
 }
@@ -617,6 +648,7 @@ int gc_birrt_step(gc_birrt_t* b, const double* samples, const double* d_samples)
   else
     d.samples = d_samples;
   d.iteration = ++b->d.iteration;
+  d.setup = 0;
   if (b->smem > 48 * 1024)
     GC_BIRRT_DISPATCH(d.D, GC_CUDA(cudaFuncSetAttribute(birrt_step_kernel<DD>,
                                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->smem)));

@@ -51,41 +51,21 @@ struct LightArgs
   unsigned long long* first_bad;
   unsigned long long* counters;
   const uint32_t* n_dev;  // optional: the count lives in device memory (<= n)
+  uint32_t epw;           // edges a warp takes at a time (1 .. 32, set by launch_light)
 };
 
-// MODE 3 = plain state batch (check(q) on n configurations)
+// MODE 3 = plain state batch (check(q) on n configurations).
+// Edge modes: a warp takes 32 edges at a time -- lane j computes the geometry of edge j -- and then walks the
+// CONCATENATION of their state lists 32 states per round, so the lanes stay full whatever the edge lengths are (one
+// warp per edge left 40 % of the lanes idle on the 5 .. 65-state edges of BASELINE config 2).  Inside an edge the states
+// keep the reference's visiting order across rounds; an edge found in collision is marked in a warp-wide mask and its
+// remaining states are skipped (the device analogue of the early `return false`); LINEAR keeps the minimum failing index.
 template <int D, int MODE>
 __global__ void __launch_bounds__(256) edge_warp_kernel(LightArgs a)
 {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  // stage the world in shared memory (read by every lane for every state)
   LightWorld w;
-  w.kind = a.kind;
-  w.nobj = a.nobj;
-  w.cube_thr = a.cube_thr;
-  {
-    double* slo = reinterpret_cast<double*>(smem_raw);
-    double* shi = slo + (a.kind == GC_WORLD_BOXES ? (size_t)a.nobj * D : 0);
-    float* ssc = reinterpret_cast<float*>(shi + (a.kind == GC_WORLD_BOXES ? (size_t)a.nobj * D : 0));
-    float* ssr = ssc + (a.kind == GC_WORLD_CSPHERES ? (size_t)a.nobj * D : 0);
-    if (a.kind == GC_WORLD_BOXES)
-      for (uint32_t i = threadIdx.x; i < a.nobj * D; i += blockDim.x)
-      {
-        slo[i] = a.lo[i];
-        shi[i] = a.hi[i];
-      }
-    if (a.kind == GC_WORLD_CSPHERES)
-    {
-      for (uint32_t i = threadIdx.x; i < a.nobj * D; i += blockDim.x)
-        ssc[i] = a.sc[i];
-      for (uint32_t i = threadIdx.x; i < a.nobj; i += blockDim.x)
-        ssr[i] = a.sr2[i];
-    }
-    w.lo = slo;
-    w.hi = shi;
-    w.sc = ssc;
-    w.sr2 = ssr;
-  }
+  light_stage<D>(w, smem_raw, a.kind, a.nobj, a.cube_thr, a.lo, a.hi, a.sc, a.sr2);
   __syncthreads();
 
   const int lane = threadIdx.x & 31;
@@ -109,45 +89,104 @@ __global__ void __launch_bounds__(256) edge_warp_kernel(LightArgs a)
   }
   else
   {
-    for (uint32_t e = gwarp; e < n_act; e += nwarps)
+    const uint32_t epw = a.epw;
+    for (uint32_t e0 = gwarp * epw; e0 < n_act; e0 += nwarps * epw)
     {
-      double c1[D], c2[D], c3[D];
+      // lane j: geometry of edge e0 + j
+      EdgeGeom g;
+      g.dist = 0.0;
+      g.aux = 0.0;
+      g.nstates = 0u;
+      const uint32_t my_e = e0 + (uint32_t)lane;
+      const bool mine_valid = (uint32_t)lane < epw && my_e < n_act;
+      if (mine_valid)
+      {
+        double c1[D], c2[D], c3[D];
 #pragma unroll
-      for (int d = 0; d < D; d++)
-      {
-        c1[d] = a.c1[(size_t)e * D + d];
-        c2[d] = a.c2[(size_t)e * D + d];
-        c3[d] = (MODE == GC_EDGE_FROM_CONF) ? a.c3[(size_t)e * D + d] : 0.0;
-      }
-      const EdgeGeom g = edge_geom<D, MODE>(c1, c2, c3, a.min_d);
-      uint8_t result = (g.nstates == 0u) ? 255 : 1;
-      unsigned long long first = ~0ull;
-      for (uint32_t s0 = 0; s0 < g.nstates; s0 += 32u)
-      {
-        const uint32_t s = s0 + lane;
-        bool bad = false;
-        if (s < g.nstates)
+        for (int d = 0; d < D; d++)
         {
-          double conf[D];
-          if (state_conf<D, MODE>(c1, c2, c3, g, s, conf))
+          c1[d] = a.c1[(size_t)my_e * D + d];
+          c2[d] = a.c2[(size_t)my_e * D + d];
+          c3[d] = (MODE == GC_EDGE_FROM_CONF) ? a.c3[(size_t)my_e * D + d] : 0.0;
+        }
+        g = edge_geom<D, MODE>(c1, c2, c3, a.min_d);
+      }
+      // exclusive prefix of the state counts
+      uint32_t incl = g.nstates;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1)
+      {
+        const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o)
+          incl += v;
+      }
+      const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+      const uint32_t excl = incl - g.nstates;
+      uint32_t dead = 0u;  // edges of this batch already known to collide
+      unsigned long long first = ~0ull;
+      for (uint32_t t0 = 0; t0 < total; t0 += 32u)
+      {
+        const uint32_t t = t0 + (uint32_t)lane;
+        // edge j with excl[j] <= t < excl[j] + nstates[j]: binary search over the lanes' prefix values
+        uint32_t j = 0;
+#pragma unroll
+        for (int step = 16; step > 0; step >>= 1)
+        {
+          const uint32_t cand = j + (uint32_t)step;
+          const uint32_t ex = __shfl_sync(0xffffffffu, excl, (int)(cand & 31u));
+          if (cand < 32u && ex <= t)
+            j = cand;
+        }
+        const uint32_t ex_j = __shfl_sync(0xffffffffu, excl, (int)j);
+        EdgeGeom gj;
+        gj.dist = __shfl_sync(0xffffffffu, g.dist, (int)j);
+        gj.aux = __shfl_sync(0xffffffffu, g.aux, (int)j);
+        gj.nstates = __shfl_sync(0xffffffffu, g.nstates, (int)j);
+        bool bad = false;
+        uint32_t s = 0;
+        if (t < total && !((dead >> j) & 1u))
+        {
+          s = t - ex_j;
+          const uint32_t e = e0 + j;
+          double c1[D], c2[D], c3[D], conf[D];
+#pragma unroll
+          for (int d = 0; d < D; d++)
+          {
+            c1[d] = a.c1[(size_t)e * D + d];
+            c2[d] = a.c2[(size_t)e * D + d];
+            c3[d] = (MODE == GC_EDGE_FROM_CONF) ? a.c3[(size_t)e * D + d] : 0.0;
+          }
+          if (state_conf<D, MODE>(c1, c2, c3, gj, s, conf))
           {
             bad = !light_check<D>(w, conf, pairs);
             states++;
           }
         }
-        const uint32_t m = __ballot_sync(0xffffffffu, bad);
-        if (m)
+        const uint32_t newly = __reduce_or_sync(0xffffffffu, bad ? (1u << j) : 0u);
+        if (MODE == GC_EDGE_LINEAR && newly)
         {
-          result = 0;
-          first = s0 + (uint32_t)(__ffs((int)m) - 1);
-          break;  // ballot early exit: the reference returns at its first colliding state
+          // minimum failing index of each newly dead edge: its states of this round sit on consecutive lanes in
+          // ascending order, earlier rounds held none
+          const uint32_t mine = (newly >> lane) & 1u;  // lane j collects for edge j
+          unsigned long long f = ~0ull;
+          for (int l = 0; l < 32; l++)
+          {
+            const uint32_t jl = __shfl_sync(0xffffffffu, j, l);
+            const uint32_t sl = __shfl_sync(0xffffffffu, s, l);
+            const bool bl = __shfl_sync(0xffffffffu, bad ? 1 : 0, l) != 0;
+            if (bl && jl == (uint32_t)lane && (unsigned long long)sl < f)
+              f = sl;
+          }
+          if (mine)
+            first = f;
         }
+        dead |= newly;
       }
-      if (lane == 0)
+      if (mine_valid)
       {
-        a.ok[e] = result;
+        a.ok[my_e] = (g.nstates == 0u) ? 255 : (((dead >> lane) & 1u) ? 0 : 1);
         if (MODE == GC_EDGE_LINEAR && a.first_bad)
-          a.first_bad[e] = first;
+          a.first_bad[my_e] = first;
       }
     }
   }
@@ -1239,17 +1278,10 @@ __global__ void __launch_bounds__(kGridWarps * 32) arm_grid_kernel(ArmArgs a)
     default: gc::set_error("unknown edge mode %d", mode); return GC_E_INVALID;       \
   }
 
-static size_t light_smem(const gc_world* w)
-{
-  if (w->kind == GC_WORLD_BOXES)
-    return 2 * sizeof(double) * (size_t)w->nobj * w->dim;
-  if (w->kind == GC_WORLD_CSPHERES)
-    return sizeof(float) * ((size_t)w->nobj * w->dim + w->nobj);
-  return 0;
-}
+static size_t light_smem(const gc_world* w) { return light_smem_bytes(w->kind, w->nobj, w->dim); }
 
 template <int D, int MODE>
-static int launch_light(gc_world* w, const LightArgs& a, cudaStream_t st)
+static int launch_light(gc_world* w, const LightArgs& a_in, cudaStream_t st)
 {
   const size_t smem = light_smem(w);
   if (smem > 200 * 1024)
@@ -1259,7 +1291,14 @@ static int launch_light(gc_world* w, const LightArgs& a, cudaStream_t st)
   }
   if (smem > 48 * 1024)
     GC_CUDA(cudaFuncSetAttribute(edge_warp_kernel<D, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  const uint32_t warps_needed = (MODE == 3) ? (a.n + 31) / 32 : a.n;
+  // a warp takes 32 states (MODE 3) or epw edges at a time: as many as keep every SM supplied with warps, so that small
+  // (planner-sized) batches still spread over the machine and large ones pack their states densely
+  LightArgs a = a_in;
+  uint32_t epw = 1;
+  while (epw < 32u && (uint64_t)a.n >= (uint64_t)w->sms * 64u * (epw * 2u))
+    epw *= 2u;
+  a.epw = epw;
+  const uint32_t warps_needed = (MODE == 3) ? (a.n + 31) / 32 : (a.n + epw - 1) / epw;
   uint32_t blocks = (warps_needed + 7) / 8;
   const uint32_t max_blocks = (uint32_t)w->sms * 8u;
   if (blocks > max_blocks)

@@ -140,6 +140,12 @@ __device__ __forceinline__ bool state_conf(const double* c1, const double* c2, c
 // =================================================================================================
 //  light worlds: true = collision free
 // =================================================================================================
+// C-space spheres are staged as records of light_rec_floats(D) floats: centre[0..D-1], radius^2, padding to a multiple
+// of four floats, so that a state reads a sphere with 128-bit shared-memory loads; the list is padded to a multiple of
+// four spheres with radius^2 = -1 (never hit).
+__host__ __device__ constexpr int light_rec_floats(int D) { return ((D + 1 + 3) / 4) * 4; }
+__host__ __device__ inline uint32_t light_padded_spheres(uint32_t n) { return (n + 3u) & ~3u; }
+
 struct LightWorld
 {
   int kind;
@@ -147,9 +153,55 @@ struct LightWorld
   double cube_thr;
   const double* lo;  // smem copies
   const double* hi;
-  const float* sc;
-  const float* sr2;
+  const float* rec;  // C-space spheres: packed records (see above)
 };
+
+inline size_t light_smem_bytes(int kind, uint32_t nobj, int D)
+{
+  if (kind == GC_WORLD_BOXES)
+    return 2 * sizeof(double) * (size_t)nobj * D;
+  if (kind == GC_WORLD_CSPHERES)
+    return sizeof(float) * (size_t)light_padded_spheres(nobj) * light_rec_floats(D);
+  return 0;
+}
+
+// every thread of the CTA calls this once; the caller synchronises afterwards
+template <int D>
+__device__ __forceinline__ void light_stage(LightWorld& w, unsigned char* smem_raw, int kind, uint32_t nobj,
+                                            double cube_thr, const double* g_lo, const double* g_hi, const float* g_sc,
+                                            const float* g_sr2)
+{
+  w.kind = kind;
+  w.nobj = nobj;
+  w.cube_thr = cube_thr;
+  double* slo = reinterpret_cast<double*>(smem_raw);
+  double* shi = slo + (kind == GC_WORLD_BOXES ? (size_t)nobj * D : 0);
+  float* rec = reinterpret_cast<float*>(smem_raw);
+  if (kind == GC_WORLD_BOXES)
+    for (uint32_t i = threadIdx.x; i < nobj * D; i += blockDim.x)
+    {
+      slo[i] = g_lo[i];
+      shi[i] = g_hi[i];
+    }
+  if (kind == GC_WORLD_CSPHERES)
+  {
+    constexpr int R = light_rec_floats(D);
+    const uint32_t np = light_padded_spheres(nobj);
+    for (uint32_t i = threadIdx.x; i < np * R; i += blockDim.x)
+    {
+      const uint32_t sp = i / R, k = i % R;
+      float v = 0.0f;
+      if (sp < nobj)
+        v = (k < (uint32_t)D) ? g_sc[(size_t)sp * D + k] : (k == (uint32_t)D ? g_sr2[sp] : 0.0f);
+      else if (k == (uint32_t)D)
+        v = -1.0f;
+      rec[i] = v;
+    }
+  }
+  w.lo = slo;
+  w.hi = shi;
+  w.rec = rec;
+}
 
 template <int D>
 __device__ __forceinline__ bool light_check(const LightWorld& w, const double* q, unsigned long long& pairs)
@@ -177,27 +229,44 @@ __device__ __forceinline__ bool light_check(const LightWorld& w, const double* q
     }
     return true;
   }
-  // C-space hyperspheres, fp32 (include/gcb200_spec.h)
+  // C-space hyperspheres, fp32 (include/gcb200_spec.h): acc = t0*t0, then fma(t_i, t_i, acc); hit = acc < r^2.
+  // Four spheres per trip (independent chains), early exit between trips.
+  constexpr int R = light_rec_floats(D);
   float qf[D];
 #pragma unroll
   for (int i = 0; i < D; i++)
     qf[i] = (float)q[i];
   bool hit = false;
   uint32_t s = 0;
-  for (; s < w.nobj && !hit; s++)
+  const uint32_t np = light_padded_spheres(w.nobj);
+  for (; s < np && !hit; s += 4)
   {
-    const float* c = w.sc + (size_t)s * D;
-    const float t0 = __fsub_rn(qf[0], c[0]);
-    float acc = __fmul_rn(t0, t0);
 #pragma unroll
-    for (int i = 1; i < D; i++)
+    for (int u = 0; u < 4; u++)
     {
-      const float t = __fsub_rn(qf[i], c[i]);
-      acc = __fmaf_rn(t, t, acc);
+      float r[R];
+      const float4* rp = reinterpret_cast<const float4*>(w.rec + (size_t)(s + u) * R);
+#pragma unroll
+      for (int k = 0; k < R / 4; k++)
+      {
+        const float4 v = rp[k];
+        r[4 * k + 0] = v.x;
+        r[4 * k + 1] = v.y;
+        r[4 * k + 2] = v.z;
+        r[4 * k + 3] = v.w;
+      }
+      const float t0 = __fsub_rn(qf[0], r[0]);
+      float acc = __fmul_rn(t0, t0);
+#pragma unroll
+      for (int i = 1; i < D; i++)
+      {
+        const float t = __fsub_rn(qf[i], r[i]);
+        acc = __fmaf_rn(t, t, acc);
+      }
+      hit = hit || (acc < r[D]);
     }
-    hit = acc < w.sr2[s];
   }
-  pairs += s;
+  pairs += min(s, w.nobj);
   return !hit;
 }
 }  // namespace gc

@@ -263,6 +263,23 @@ int gc_birrt_dump(gc_birrt_t* b, uint32_t p, int tree, int32_t* parents, double*
 /* way points start -> goal and the connection costs between them; returns the number of way points (0 = unsolved) */
 int gc_birrt_solution(gc_birrt_t* b, uint32_t p, double* waypoints, double* costs, uint32_t cap);
 
+/* ---- Tree::informedExtend for n trees at once (src/graph_core/graph/tree.cpp:235-302; AnytimeRRT's improve rounds,
+ * src/graph_core/solvers/anytime_rrt.cpp:356-427) ---------------------------------------------------------------
+ * Query i: sample q[i] against segment seg[i] of `store` with goal[i], cost2beat[i], bias[i].  The candidates are the
+ * nearK neighbours (k = ceil(k_rrt * ln(live nodes + 1)), tree.cpp:761-765; k_rrt <= 0: every node) in (distance, slot)
+ * order; each is steered towards the sample (tree.cpp:110-128), kept when cost-to-come + distance + |goal - next| <
+ * cost2beat and ranked by bias * distance + (1 - bias) * cost-to-come; the first candidate in that order whose
+ * distance is below `tolerance` or whose edge is collision free wins.  d_parent / d_pcost are DEVICE arrays indexed by
+ * global slot (segment * capacity + slot): parent slot (-1 root / not connected) and the cost of the connection to it,
+ * from which Tree::costToNode (tree.cpp:767-789) is walked.  Outputs (host): ok[i], tree_node[i] (slot of the chosen
+ * node), new_conf[i][dim], distance[i] (sample to node, unclamped), edge_cost[i] (= |node - new|, the connection cost of
+ * extendOnly); the caller appends the node.  Trees of at most 8 192 nodes. */
+int gc_informed_extend_batch(gc_store_t* store, gc_world_t* world, const double* q, const uint32_t* seg,
+                             const double* goal, const double* cost2beat, const double* bias, uint32_t n, double k_rrt,
+                             double max_distance, double min_distance, double tolerance, const int32_t* d_parent,
+                             const double* d_pcost, uint8_t* ok, uint32_t* tree_node, double* new_conf,
+                             double* distance, double* edge_cost, uint64_t* edges_checked);
+
 /* ---- Philox samplers (uniform_sampler.cpp:34-39, informed_sampler.cpp:145-180) -------------- */
 /* n uniform samples in [lb, ub]; sample i uses Philox counter (first_index + i) */
 int gc_sample_uniform(int device, int dim, const double* lb, const double* ub, uint64_t seed, uint64_t first_index,

@@ -490,6 +490,47 @@ int ref_check_path_to_node(void* h, void* other_checker, const double* conf, int
   return ok ? 1 : 0;
 }
 
+// Tree::informedExtend (tree.cpp:235-302) on a tree given as arrays: conf[n][dim], parent[n] (index, -1 for the root =
+// node 0) and the connection costs pcost[n].  Nodes enter the NearestNeighbors structure in index order.  Returns the
+// reference's boolean; new_conf / parent_index describe the node it appended.
+int ref_informed_extend(int dim, void* checker, int n, const double* conf, const int* parent, const double* pcost,
+                        double max_distance, int use_kdtree, const double* q, const double* goal, double cost2beat,
+                        double bias, double* new_conf, int* parent_index)
+{
+  RefChecker* rc = (RefChecker*)checker;
+  MetricsPtr metrics = std::make_shared<EuclideanMetrics>(g_logger);
+  std::vector<NodePtr> nodes;
+  for (int i = 0; i < n; i++)
+    nodes.push_back(std::make_shared<Node>(toVec(conf + (size_t)i * dim, dim), g_logger));
+  TreePtr tree = std::make_shared<Tree>(nodes[0], max_distance, rc->c, metrics, g_logger, use_kdtree != 0);
+  for (int i = 1; i < n; i++)
+  {
+    ConnectionPtr c = std::make_shared<Connection>(nodes[parent[i]], nodes[i], g_logger);
+    c->setCost(pcost[i]);
+    c->add();
+  }
+  for (int i = 1; i < n; i++)
+    tree->addNode(nodes[i], false);
+  NodePtr new_node;
+  const bool ok = tree->informedExtend(toVec(q, dim), new_node, toVec(goal, dim), cost2beat, bias);
+  *parent_index = -1;
+  if (ok && new_node)
+  {
+    for (int k = 0; k < dim; k++)
+      new_conf[k] = new_node->getConfiguration()(k);
+    NodePtr par = new_node->getParents().at(0);
+    for (int i = 0; i < n; i++)
+      if (nodes[i] == par)
+        *parent_index = i;
+  }
+  // break the shared_ptr cycles of the reference's graph objects
+  for (NodePtr& nd : nodes)
+    nd->disconnect();
+  if (new_node)
+    new_node->disconnect();
+  return ok ? 1 : 0;
+}
+
 // ---- Tree YAML (tree.cpp:1188-1227 toYAML, :1272-1389 fromYAML): the document as arrays ---------------------
 // Tree::toYAML() of the start tree: nodes[n][dim] in document order, connections[m][2] = (parent index, child
 // index) in document order.  Returns n (or -1); *nconn = m.

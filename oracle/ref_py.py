@@ -87,6 +87,8 @@ def lib(fast: bool = False, dropin: bool = False):
         "ref_solution_is_valid_from": (C.c_int, [vp, vp, C.c_int, C.c_double]),
         "ref_solution_optimize": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, _dp, _dp]),
         "ref_tree_recheck": (C.c_int, [vp]),
+        "ref_informed_extend": (C.c_int, [C.c_int, vp, C.c_int, _dp, C.POINTER(C.c_int), _dp, C.c_double, C.c_int, _dp, _dp,
+                                          C.c_double, C.c_double, _dp, C.POINTER(C.c_int)]),
         "ref_check_path_to_node": (C.c_int, [vp, vp, _dp, C.c_int, C.c_int, _dp, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
         "ref_srand": (None, [C.c_uint]),
         "ref_sample_informed": (None, [C.c_int, _dp, _dp, _dp, _dp, C.c_double, C.c_int, _dp]),
@@ -467,3 +469,19 @@ def ref_tree_from_yaml(conf, connections, max_distance=None, use_kdtree=True, fa
     if r < 0:
         return None
     return oc[:r].copy(), op[:r].copy(), pc[:r].copy(), md.value
+
+
+def informed_extend(checker: RefChecker, conf, parent, pcost, max_distance, q, goal, cost2beat, bias, use_kdtree=True):
+    """The reference's Tree::informedExtend (tree.cpp:235-302) on a tree given as arrays; (ok, new_conf, parent index)."""
+    L = checker.L
+    conf = _f64(conf)
+    n, dim = conf.shape
+    parent = np.ascontiguousarray(parent, dtype=np.int32)
+    pcost = _f64(pcost)
+    q, goal = _f64(q), _f64(goal)
+    new = np.full(dim, np.nan)
+    pi = C.c_int(-1)
+    ok = L.ref_informed_extend(dim, checker.h, n, _p(conf, _dp), parent.ctypes.data_as(C.POINTER(C.c_int)), _p(pcost, _dp),
+                               max_distance, 1 if use_kdtree else 0, _p(q, _dp), _p(goal, _dp), cost2beat, bias,
+                               _p(new, _dp), C.byref(pi))
+    return bool(ok), new, pi.value

@@ -89,7 +89,8 @@ def test_lockstep_birrt_matches_the_reference_birrt(gc, orc, ref, name, n_prob, 
         assert info["solved"] == cpu.solved, p
         if cpu.solved:
             n_solved += 1
-            assert info["solved_iteration"] == used, p
+            if info["solved_iteration"] > 0:  # 0: solved by setProblem's direct connection (tree_solver.cpp:84-98)
+                assert info["solved_iteration"] == used, p
             assert info["cost"] == cpu.cost, p
             wp, cs = lk.solution(p)
             assert np.array_equal(wp, cpu.solution()), p
@@ -119,7 +120,7 @@ def test_lockstep_rrt_matches_the_reference_rrt(gc, orc, ref, name, extend, iter
         assert info["solved"] == cpu.solved, p
         if cpu.solved:
             n_solved += 1
-            assert info["solved_iteration"] == used and info["cost"] == cpu.cost, p
+            assert info["solved_iteration"] in (0, used) and info["cost"] == cpu.cost, p
             wp, cs = lk.solution(p)
             assert np.array_equal(wp, cpu.solution()), p
         assert info["size_start"] == cpu.tree_size, p

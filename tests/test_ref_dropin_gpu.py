@@ -252,7 +252,8 @@ def test_batched_path_and_tree_revalidation_counts_device_calls(gc, orc, ref):
     c1 = gpu.device_calls
     assert gpu.recheck_tree_batched()
     c2 = gpu.device_calls
-    assert c1 - c0 == gpu.tree_size - 1 and c2 - c1 == 1
+    # (the connections of the path are still in the cache of the batched isValid above)
+    assert gpu.tree_size - 1 - n_conn <= c1 - c0 <= gpu.tree_size - 1 and c2 - c1 == 1
     # the same scene with a new obstacle on the path
     sc2 = _box_scene_with_new_obstacle(sc, path)
     ow2 = orc.OracleWorld.from_scenario(sc2)
