@@ -120,6 +120,7 @@ struct gc_store
   int stream_occ[GC_MAX_DIM + 1] = {};
   bool sort_attr_set = false;
   bool knn_attr_set[GC_MAX_DIM + 1] = {};
+  size_t small_knn_err_words = 0;  // layout for which the error word of the two-launch k-nearest path is known clear
   // scratch
   gc::DevBuf d_q, d_seg, d_radius, d_idx, d_dist, d_count, d_part, d_misc, d_rows, d_slots;
   gc::PinBuf h_in, h_out;

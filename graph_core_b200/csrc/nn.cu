@@ -1849,6 +1849,290 @@ __global__ void gather_shard_lists_p2p_kernel(PeerLists pl, uint32_t G, uint32_t
 }
 
 // ---------------------------------------------------------------------------------------------
+// k-nearest of a FEW queries over a large single-segment store in two launches (the latency path of BASELINE config 4:
+// one planner asking for its 16 nearest nodes among 2^20).  The sample -> collect -> re-threshold -> collect -> select
+// pipeline above costs five launches, three of them single-CTA (120 us for one query); here
+//   1. knn_small_scan_kernel: every CTA owns a contiguous strip of nodes, computes the fp32 distance of each node to
+//      each query once, finds the exact k-th smallest fp32 value OF ITS STRIP by a radix select in shared memory and
+//      keeps the nodes under the error-widened bound of it (stream_thr).  A node among the true k nearest can be pushed
+//      out of a strip's list only by k strip nodes that are strictly nearer in fp64 -- impossible -- so the union of the
+//      lists holds the answer;
+//   2. knn_small_merge_kernel: per query, the k-th smallest fp32 value of the union (radix select), the exact fp64
+//      distance only for the entries under its widened bound (k + a handful), sort by (d64, slot).
+// Lists that overflow their fixed capacity (massive ties) raise a flag and the call falls back to the pipeline above.
+// ---------------------------------------------------------------------------------------------
+constexpr int kSmThreads = 512;
+constexpr uint32_t kSmMaxQ = 8;
+constexpr uint32_t kSmMaxK = 64;
+constexpr uint32_t kSmRefine = 2048;
+
+// k-th smallest (1-based) of n unsigned keys in shared or global memory, block-wide (blockDim >= 256); hist[256], sh[16]
+__device__ __forceinline__ uint32_t block_kth_u32(const uint32_t* keys, uint32_t n, uint32_t k, uint32_t* hist,
+                                                  uint32_t* sh)
+{
+  uint32_t prefix = 0, mask = 0;
+  const uint32_t tid = threadIdx.x, lane = tid & 31u;
+  for (int r = 3; r >= 0; r--)
+  {
+    if (tid < 256)
+      hist[tid] = 0;
+    __syncthreads();
+    for (uint32_t i = tid; i < n; i += blockDim.x)
+    {
+      const uint32_t key = keys[i];
+      if ((key & mask) == prefix)
+        atomicAdd(&hist[(key >> (8 * r)) & 255u], 1u);
+    }
+    __syncthreads();
+    uint32_t c = 0, incl = 0;
+    if (tid < 256)
+    {
+      c = hist[tid];
+      incl = c;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1)
+      {
+        const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= (uint32_t)o)
+          incl += v;
+      }
+      if (lane == 31)
+        sh[tid >> 5] = incl;
+    }
+    __syncthreads();
+    if (tid < 256)
+    {
+      uint32_t off = 0;
+      for (uint32_t w = 0; w < (tid >> 5); w++)
+        off += sh[w];
+      incl += off;
+      const uint32_t excl = incl - c;
+      if (excl < k && k <= incl)
+      {
+        sh[8] = tid;
+        sh[9] = k - excl;
+      }
+    }
+    __syncthreads();
+    prefix |= sh[8] << (8 * r);
+    mask |= 0xffu << (8 * r);
+    k = sh[9];
+    __syncthreads();
+  }
+  return prefix;
+}
+
+struct SmallKnnArgs
+{
+  const float* x32;
+  const double* x64;
+  const uint32_t* used;
+  size_t row_stride;
+  const double* q;  // [nq][D]
+  uint32_t nq, k, G, chunk, capC;
+  float xn_max, slack_abs;
+  float* cand_c2;       // [nq][G][capC]
+  uint32_t* cand_slot;  // [nq][G][capC]
+  uint32_t* cand_cnt;   // [nq][G]
+  uint32_t* err;
+  uint32_t out_cap;
+  uint32_t* out_idx;
+  double* out_dist;
+  uint32_t* out_count;
+};
+
+template <int D>
+__global__ void __launch_bounds__(kSmThreads) knn_small_scan_kernel(SmallKnnArgs a)
+{
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float* vals = reinterpret_cast<float*>(smem_raw);  // [nq][chunk]
+  __shared__ float qf[kSmMaxQ][D];
+  __shared__ float e2s[kSmMaxQ];
+  __shared__ uint32_t nfin[kSmMaxQ];
+  __shared__ uint32_t hist[256];
+  __shared__ uint32_t sh[16];
+  __shared__ uint32_t scnt;
+  const uint32_t tid = threadIdx.x;
+  const uint32_t n = a.used[0];
+  const uint32_t lo = blockIdx.x * a.chunk;
+  const uint32_t len = (lo < n) ? min(a.chunk, n - lo) : 0u;
+  if (tid < a.nq)
+  {
+    float qn = 0.0f;
+    for (int d = 0; d < D; d++)
+    {
+      const float v = (float)a.q[(size_t)tid * D + d];
+      qf[tid][d] = v;
+      qn = fmaf(v, v, qn);
+    }
+    e2s[tid] = (float)(3 * D + 8) * 5.9604645e-8f * 1.5f * (a.xn_max + qn) * 2.0f + FLT_MIN;
+    nfin[tid] = 0;
+  }
+  __syncthreads();
+  uint32_t fin[kSmMaxQ];
+#pragma unroll
+  for (uint32_t qq = 0; qq < kSmMaxQ; qq++)
+    fin[qq] = 0;
+  for (uint32_t i = tid; i < len; i += kSmThreads)
+  {
+    float x[D];
+#pragma unroll
+    for (int d = 0; d < D; d++)
+      x[d] = __ldg(a.x32 + (size_t)d * a.row_stride + lo + i);
+#pragma unroll
+    for (uint32_t qq = 0; qq < kSmMaxQ; qq++)
+      if (qq < a.nq)
+      {
+        float acc = 0.0f;
+#pragma unroll
+        for (int d = 0; d < D; d++)
+        {
+          const float t = x[d] - qf[qq][d];
+          acc = fmaf(t, t, acc);
+        }
+        vals[(size_t)qq * a.chunk + i] = acc;  // +inf for a tombstone (row 0 carries the mark)
+        fin[qq] += (acc < CUDART_INF_F) ? 1u : 0u;
+      }
+  }
+#pragma unroll
+  for (uint32_t qq = 0; qq < kSmMaxQ; qq++)
+    if (qq < a.nq && fin[qq])
+      atomicAdd(&nfin[qq], fin[qq]);
+  __syncthreads();
+  for (uint32_t qq = 0; qq < a.nq; qq++)
+  {
+    const uint32_t kk = min(a.k, nfin[qq]);
+    const float* v = vals + (size_t)qq * a.chunk;
+    float thr = -1.0f;
+    if (kk > 0)
+    {
+      const uint32_t kth = block_kth_u32(reinterpret_cast<const uint32_t*>(v), len, kk, hist, sh);
+      thr = stream_thr(__uint_as_float(kth), e2s[qq], a.slack_abs);
+    }
+    if (tid == 0)
+      scnt = 0;
+    __syncthreads();
+    float* oc = a.cand_c2 + ((size_t)qq * a.G + blockIdx.x) * a.capC;
+    uint32_t* os = a.cand_slot + ((size_t)qq * a.G + blockIdx.x) * a.capC;
+    for (uint32_t i = tid; i < len; i += kSmThreads)
+    {
+      const float c = v[i];
+      if (c <= thr && c < CUDART_INF_F)
+      {
+        const uint32_t pos = atomicAdd(&scnt, 1u);
+        if (pos < a.capC)
+        {
+          oc[pos] = c;
+          os[pos] = lo + i;
+        }
+      }
+    }
+    __syncthreads();
+    for (uint32_t pos = min(scnt, a.capC) + tid; pos < a.capC; pos += kSmThreads)
+      oc[pos] = CUDART_INF_F;  // unused entries sort behind every candidate in the merge kernel's select
+    if (tid == 0)
+    {
+      a.cand_cnt[(size_t)qq * a.G + blockIdx.x] = min(scnt, a.capC);
+      if (scnt > a.capC)
+        atomicOr(a.err, 1u);
+    }
+    __syncthreads();
+  }
+}
+
+template <int D>
+__global__ void __launch_bounds__(1024, 1) knn_small_merge_kernel(SmallKnnArgs a)
+{
+  __shared__ double rkey[kSmRefine];
+  __shared__ uint32_t rval[kSmRefine];
+  __shared__ double qs[D];
+  __shared__ uint32_t hist[256];
+  __shared__ uint32_t sh[16];
+  __shared__ uint32_t tot, nref;
+  const uint32_t qq = blockIdx.x, tid = threadIdx.x;
+  if (tid < D)
+    qs[tid] = a.q[(size_t)qq * D + tid];
+  if (tid == 0)
+  {
+    tot = 0;
+    nref = 0;
+  }
+  __syncthreads();
+  // the union of the strip lists, read in place (L2): unused entries hold +inf
+  const uint32_t ncand = a.G * a.capC;
+  const float* cc = a.cand_c2 + (size_t)qq * ncand;
+  const uint32_t* cs = a.cand_slot + (size_t)qq * ncand;
+  const uint32_t* cn = a.cand_cnt + (size_t)qq * a.G;
+  uint32_t mine = 0;
+  for (uint32_t c = tid; c < a.G; c += blockDim.x)
+    mine += cn[c];
+  if (mine)
+    atomicAdd(&tot, mine);
+  __syncthreads();
+  const uint32_t T = tot;
+  const uint32_t want = min(a.k, T);  // every strip handed over min(k, its live nodes): T >= min(k, live nodes)
+  uint32_t m = 0;
+  if (want > 0)
+  {
+    float qn = 0.0f;
+    for (int d = 0; d < D; d++)
+    {
+      const float v = (float)qs[d];
+      qn = fmaf(v, v, qn);
+    }
+    const float e2 = (float)(3 * D + 8) * 5.9604645e-8f * 1.5f * (a.xn_max + qn) * 2.0f + FLT_MIN;
+    // stage the values once: the four histogram passes of the select then run out of shared memory
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float* sk = reinterpret_cast<float*>(smem_raw);
+    for (uint32_t i = tid; i < ncand; i += blockDim.x)
+      sk[i] = __ldg(cc + i);
+    __syncthreads();
+    const uint32_t kth = block_kth_u32(reinterpret_cast<const uint32_t*>(sk), ncand, want, hist, sh);
+    const float thr = stream_thr(__uint_as_float(kth), e2, a.slack_abs);
+    for (uint32_t i = tid; i < ncand; i += blockDim.x)
+    {
+      const float c = sk[i];
+      if (c <= thr && c < CUDART_INF_F)
+      {
+        const uint32_t pos = atomicAdd(&nref, 1u);
+        if (pos < kSmRefine)
+        {
+          const uint32_t slot = cs[i];
+          rkey[pos] = dist64<D>(a.x64 + (size_t)slot * D, qs);
+          rval[pos] = slot;
+        }
+      }
+    }
+    __syncthreads();
+    if (nref > kSmRefine)
+    {
+      if (tid == 0)
+        atomicOr(a.err, 2u);
+      m = kSmRefine;
+    }
+    else
+      m = nref;
+  }
+  uint32_t p2 = 2;
+  while (p2 < m)
+    p2 <<= 1;
+  for (uint32_t i = m + tid; i < p2; i += blockDim.x)
+  {
+    rkey[i] = CUDART_INF;
+    rval[i] = GC_NO_NODE;
+  }
+  __syncthreads();
+  bitonic_sort(rkey, rval, p2);
+  for (uint32_t i = tid; i < min(want, a.out_cap); i += blockDim.x)
+  {
+    a.out_idx[(size_t)qq * a.out_cap + i] = rval[i];
+    a.out_dist[(size_t)qq * a.out_cap + i] = rkey[i];
+  }
+  if (tid == 0)
+    a.out_count[qq] = want;
+}
+
+// ---------------------------------------------------------------------------------------------
 // dispatch helpers
 // ---------------------------------------------------------------------------------------------
 #define GC_DISPATCH_DIM(dim, ...)                                  \
@@ -2325,6 +2609,82 @@ static int knn_large_dev(gc_store* s, const double* d_q, const uint32_t* d_seg, 
   return GC_OK;
 }
 
+// the two-launch latency path (see knn_small_scan_kernel); GC_E_CAPACITY = a list overflowed, use the general pipeline
+static int knn_small_dev(gc_store* s, const double* d_q, uint32_t nq, uint32_t k, uint32_t cap, uint32_t* d_idx,
+                         double* d_dist, uint32_t* d_count)
+{
+  SmallKnnArgs a{};
+  const uint32_t n = s->used[0];
+  // strips: a multiple of the SM count, more of them when several queries share a strip's shared memory
+  uint32_t mult = 2u;
+  if (const char* e = getenv("GCB200_SMALL_KNN_STRIPS"))
+    mult = (uint32_t)std::max(1, atoi(e));
+  for (;;)
+  {
+    a.G = (uint32_t)s->sms * mult;
+    a.chunk = (n + a.G - 1) / a.G;
+    a.chunk = (a.chunk + 3u) & ~3u;
+    if (sizeof(float) * (size_t)nq * a.chunk <= 64 * 1024 || mult >= 16u)
+      break;
+    mult *= 2u;
+  }
+  a.G = (n + a.chunk - 1) / a.chunk;
+  a.capC = k + 16u;
+  const size_t smem1 = sizeof(float) * (size_t)nq * a.chunk;
+  const size_t ncand = (size_t)a.G * a.capC;
+  const size_t smem2 = sizeof(float) * ncand;
+  if (smem1 > 100 * 1024 || smem2 > 160 * 1024)
+    return GC_E_CAPACITY;
+  GC_TRY(s->d_cand_dist.reserve(sizeof(float) * nq * ncand));
+  GC_TRY(s->d_cand_idx.reserve(sizeof(uint32_t) * nq * ncand));
+  GC_TRY(s->d_cand_count.reserve(sizeof(uint32_t) * ((size_t)nq * a.G + 4)));
+  a.x32 = s->x32;
+  a.x64 = s->x64;
+  a.used = s->d_used;
+  a.row_stride = s->cap_total + kRowPad;
+  a.q = d_q;
+  a.nq = nq;
+  a.k = k;
+  double xm = 0.0;
+  for (double v : s->max_abs)
+    xm = fmax(xm, v);
+  a.xn_max = (float)fmin((double)s->dim * xm * xm * 1.000001, 3.0e38);
+  a.slack_abs = (float)(store_slack(s) * 1.0000001) + FLT_MIN;
+  a.cand_c2 = reinterpret_cast<float*>(s->d_cand_dist.p);
+  a.cand_slot = s->d_cand_idx.as<uint32_t>();
+  a.cand_cnt = s->d_cand_count.as<uint32_t>();
+  a.err = a.cand_cnt + (size_t)nq * a.G;
+  a.out_cap = cap;
+  a.out_idx = d_idx;
+  a.out_dist = d_dist;
+  a.out_count = d_count;
+  if (s->small_knn_err_words != (size_t)nq * a.G + 4)
+  {
+    // the error word sits behind the counts: cleared when the layout changes and after it was raised, not per call
+    GC_CUDA(cudaMemsetAsync(a.err, 0, sizeof(uint32_t), s->stream));
+    s->small_knn_err_words = (size_t)nq * a.G + 4;
+  }
+  GC_DISPATCH_DIM(s->dim,
+                  if (smem1 > 48 * 1024) GC_CUDA(cudaFuncSetAttribute(
+                      knn_small_scan_kernel<DD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
+                  // (static + dynamic shared memory of the merge kernel exceeds the 48 KB default long before smem2 does)
+                  GC_CUDA(cudaFuncSetAttribute(knn_small_merge_kernel<DD>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                               (int)(160 * 1024)));
+                  (knn_small_scan_kernel<DD><<<a.G, kSmThreads, smem1, s->stream>>>(a));
+                  (knn_small_merge_kernel<DD><<<nq, 1024, smem2, s->stream>>>(a)));
+  GC_CUDA(cudaGetLastError());
+  count_launch(2);
+  uint32_t err = 0;
+  GC_CUDA(cudaMemcpyAsync(&err, a.err, sizeof(uint32_t), cudaMemcpyDeviceToHost, s->stream));
+  GC_CUDA(cudaStreamSynchronize(s->stream));
+  if (getenv("GCB200_DEBUG"))
+    fprintf(stderr, "knn_small_dev: n=%u nq=%u k=%u G=%u chunk=%u capC=%u smem1=%zu smem2=%zu err=%u\n", n, nq, k, a.G,
+            a.chunk, a.capC, smem1, smem2, err);
+  if (err)
+    s->small_knn_err_words = 0;  // cleared by the next call
+  return err ? GC_E_CAPACITY : GC_OK;
+}
+
 int knn_dev(gc_store* s, const double* d_q, const uint32_t* d_seg, uint32_t nq, uint64_t k, uint32_t cap,
             uint32_t* d_idx, double* d_dist, uint32_t* d_count)
 {
@@ -2335,6 +2695,13 @@ int knn_dev(gc_store* s, const double* d_q, const uint32_t* d_seg, uint32_t nq, 
   if (mu > kSortMax)
   {
     int rc;
+    if (nq <= kSmMaxQ && k >= 1 && k <= kSmMaxK && use_stream(s, d_seg) && !s->knn_force_fp64 &&
+        !getenv("GCB200_NO_SMALL_KNN"))
+    {
+      rc = knn_small_dev(s, d_q, nq, (uint32_t)k, cap, d_idx, d_dist, d_count);
+      if (rc != GC_E_CAPACITY)
+        return rc;
+    }
     do
       rc = knn_large_dev(s, d_q, d_seg, nq, k, cap, d_idx, d_dist, d_count);
     while (rc == GC_E_CAPACITY);

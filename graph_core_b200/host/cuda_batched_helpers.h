@@ -92,8 +92,15 @@ inline bool checkPathToNode(const TreePtr& tree, const NodePtr& node, std::vecto
 {
   std::vector<ConnectionPtr> todo;
   for (const ConnectionPtr& c : tree->getConnectionToNode(node))
+  {
     if (!c->isRecentlyChecked())
       todo.push_back(c);
+    else if (c->getCost() == std::numeric_limits<double>::infinity())
+    {
+      todo.clear();  // the reference returns false before checking anything (tree.cpp:345-349)
+      break;
+    }
+  }
   prefetch(chk, todo);
   return tree->checkPathToNode(node, checked_connections, path_connections);
 }

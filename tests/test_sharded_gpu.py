@@ -241,3 +241,50 @@ def test_sharded_merge_above_sort_capacity(gc, orc, p2p):
     torch.cuda.synchronize()
     assert np.array_equal(oc.cpu().numpy(), rc)
     assert np.array_equal(od.cpu().numpy(), rd) and np.array_equal(oi.cpu().numpy(), ri)
+
+
+# ---- the two-launch latency path: a few queries, small k, large single tree (knn_small_scan / knn_small_merge) --------
+@pytest.mark.parametrize("n,dim,k,nq", [(50000, 12, 16, 1), (70001, 7, 64, 8), (40000, 3, 5, 3), (1 << 20, 12, 16, 2),
+                                        (33000, 2, 1, 8)])
+def test_knn_few_queries_latency_path(gc, orc, n, dim, k, nq):
+    pts = W.c4_nodes(n, dim, seed=391)
+    qs = W.c4_queries(nq, dim, seed=392)
+    st = gc.NodeStore(dim, n)
+    st.append(pts)
+    l0 = gc.capi.launch_count()
+    gi, gd, gcnt = st.knn(qs, k, cap=k)
+    assert gc.capi.launch_count() - l0 == 2  # scan + merge, nothing else
+    ov = orc.OracleNN("vector", dim)
+    ov.insert(pts)
+    oi, od, oc = ov.knn(qs, k, k)
+    assert np.array_equal(gcnt.astype(np.int64), oc.astype(np.int64))
+    assert np.array_equal(gd, od)
+    assert np.array_equal(gi.astype(np.int64), oi.astype(np.int64))
+
+
+def test_knn_few_queries_ties_tombstones_and_fallback(gc, orc):
+    base = W.c4_nodes(9000, 5, seed=393)
+    pts = np.vstack([base, base, base, base])  # every configuration four times: exact ties across the k-th rank
+    st = gc.NodeStore(5, len(pts))
+    st.append(pts)
+    ov = orc.OracleNN("vector", 5)
+    ov.insert(pts)
+    qs = np.vstack([base[:3], W.c4_queries(3, 5, seed=394)])
+    for k in (1, 2, 6, 50):
+        gi, gd, gcnt = st.knn(qs, k, cap=k)
+        oi, od, oc = ov.knn(qs, k, k)
+        assert np.array_equal(gi.astype(np.int64), oi.astype(np.int64)) and np.array_equal(gd, od)
+    dead = sorted(set(ov.knn(qs, 3, 3)[0].ravel().tolist()))
+    for s in dead:
+        st.tombstone(s)
+        ov.delete(s)
+    gi, gd, gcnt = st.knn(qs, 20, cap=20)
+    oi, od, oc = ov.knn(qs, 20, 20)
+    assert np.array_equal(gd, od)
+    assert not np.isin(gi, dead).any()
+    # 40 000 copies of one point: every strip list overflows -> the general pipeline answers (lowest slots win)
+    same = np.tile(W.c4_nodes(1, 4, seed=395), (40000, 1))
+    st2 = gc.NodeStore(4, len(same))
+    st2.append(same)
+    gi, gd, gcnt = st2.knn(same[:2], 7, cap=7)
+    assert np.array_equal(gi, np.tile(np.arange(7, dtype=np.uint32), (2, 1))) and np.all(gd == 0.0)

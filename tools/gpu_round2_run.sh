@@ -1,5 +1,6 @@
-mkdir -p gpurun_out/r2s9
-O=gpurun_out/r2s9
-timeout 1500 python -m pytest tests -q -m gpu > $O/pytest.log 2>&1; echo "pytest rc=$?" >> $O/pytest.log
-timeout 900 python bench.py > $O/bench.json 2> $O/bench.err; echo "rc=$?" >> $O/bench.err
-du -sh $O; ls -la $O
+mkdir -p gpurun_out/r2s13
+O=gpurun_out/r2s13
+timeout 600 python -m pytest tests/test_sharded_gpu.py -q -m gpu -k "few_queries or knn_large" > $O/pytest.log 2>&1; echo "pytest rc=$?" >> $O/pytest.log
+timeout 300 python tools/nn_bench.py --ops knn --tiles 1,8 > $O/nn_bench2.jsonl 2>&1
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/nn_launches.csv python tools/nn_bench.py --ops knn --tiles 1 --reps 2 > $O/ncu_nn.log 2>&1
+python tools/launch_summary.py $O/nn_launches.csv > $O/nn_launches_summary.txt 2>&1
