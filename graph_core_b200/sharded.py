@@ -68,6 +68,8 @@ class CudaShardEngine:
         self.lib = capi.load()
         self.store.set_stream(torch.cuda.current_stream(self.torch_device).cuda_stream)
         self.peer = None  # PeerBuffers when the p2p exchange is enabled
+        self._bufs = {}   # (nq, cap) -> result buffers; a result is valid until the next query of the same shape
+        self._flags = None
 
     def enable_p2p(self, group, nq_max: int, cap_max: int):
         self.peer = PeerBuffers(group, self.torch_device, nq_max, cap_max)
@@ -94,33 +96,51 @@ class CudaShardEngine:
         if len(rows):
             self.store.append(rows)
 
-    def _q(self, q: np.ndarray) -> torch.Tensor:
-        return torch.from_numpy(np.ascontiguousarray(q, dtype=np.float64)).to(self.torch_device)
+    def _q(self, q) -> torch.Tensor:
+        """Queries on the device: a float64 CUDA tensor is used as it is (resident queries), anything else is copied."""
+        if isinstance(q, torch.Tensor) and q.is_cuda and q.dtype == torch.float64:
+            return q.contiguous().view(-1, self.dim)
+        return torch.from_numpy(np.ascontiguousarray(q, dtype=np.float64).reshape(-1, self.dim)).to(self.torch_device)
 
-    def _out(self, nq, cap):
+    def _out(self, nq, cap, fill=True):
+        """Result buffers (kept per shape: a query loop does not allocate).  fill=False: the kernel writes every entry
+        the caller reads (k-nearest and nearest write counts / sentinels themselves)."""
         if self.peer is not None:
             idx, dd, cnt = self.peer.views(nq, cap)
-            idx.fill_(-1)
+        else:
+            key = (nq, cap)
+            if key not in self._bufs:
+                if len(self._bufs) > 32:
+                    self._bufs.clear()
+                self._bufs[key] = (torch.empty((nq, cap), dtype=torch.int32, device=self.torch_device),
+                                   torch.empty((nq, cap), dtype=torch.float64, device=self.torch_device),
+                                   torch.empty(nq, dtype=torch.int32, device=self.torch_device))
+            idx, dd, cnt = self._bufs[key]
+        if fill:
+            idx.fill_(-1)  # 0xFFFFFFFF = no node
             dd.fill_(float("inf"))
             cnt.zero_()
-            return idx, dd, cnt
-        idx = torch.full((nq, cap), -1, dtype=torch.int32, device=self.torch_device)  # 0xFFFFFFFF = no node
-        dd = torch.full((nq, cap), float("inf"), dtype=torch.float64, device=self.torch_device)
-        cnt = torch.zeros(nq, dtype=torch.int32, device=self.torch_device)
         return idx, dd, cnt
 
-    def nearest_lists(self, q):
+    def nearest_lists(self, q, want_counts=True):
         dq = self._q(q)
         nq = dq.shape[0]
-        idx, dd, cnt = self._out(nq, 1)
+        idx, dd, cnt = self._out(nq, 1, fill=False)  # gc_nn1_dev writes (NO_NODE, inf) for an empty tree
         capi._check(self.lib.gc_nn1_dev(self.store.handle, dq.data_ptr(), None, nq, idx.data_ptr(), dd.data_ptr()))
-        cnt.copy_((idx[:, 0] != -1).to(torch.int32))
+        if want_counts:
+            torch.ne(idx[:, 0], -1, out=self._flag(nq))
+            cnt.copy_(self._flag(nq))
         return idx, dd, cnt
+
+    def _flag(self, nq):
+        if self._flags is None or self._flags.shape[0] != nq:
+            self._flags = torch.empty(nq, dtype=torch.bool, device=self.torch_device)
+        return self._flags
 
     def knn_lists(self, q, k):
         dq = self._q(q)
         nq = dq.shape[0]
-        idx, dd, cnt = self._out(nq, k)
+        idx, dd, cnt = self._out(nq, k, fill=False)  # entries [0, count) and the counts are written by the kernels
         capi._check(self.lib.gc_knn_dev(self.store.handle, dq.data_ptr(), None, nq, k, k, idx.data_ptr(), dd.data_ptr(),
                                         cnt.data_ptr()))
         return idx, dd, cnt
@@ -198,6 +218,9 @@ class ShardedNodeStore:
 
     def nearest(self, q):
         """(global slot [nq], dist [nq]); NO_NODE / inf when the tree is empty."""
+        if self.world == 1 and isinstance(self.engine, CudaShardEngine):
+            oi, od, _ = self.engine.nearest_lists(q, want_counts=False)  # one shard: its answer is the answer
+            return oi[:, 0], od[:, 0]
         oi, od, oc = self._exchange(self.engine.nearest_lists(q), 1, 1)
         return oi[:, 0], od[:, 0]
 
