@@ -70,6 +70,27 @@ class CudaShardEngine:
         self.peer = None  # PeerBuffers when the p2p exchange is enabled
         self._bufs = {}   # (nq, cap) -> result buffers; a result is valid until the next query of the same shape
         self._flags = None
+        self._last = None  # packed buffer of the lists produced by the latest query
+
+    def merge_gathered_packed(self, gathered: torch.Tensor, world: int, nq: int, cap: int, k_out: int, out_cap: int):
+        """Merge after ONE all-gather of the packed result buffers: gathered is [world][nbytes] uint8, shard g's arrays
+        sit at the packed offsets inside row g (gc_merge_shard_lists_p2p_dev takes one pointer per shard and array)."""
+        _, off_idx, off_cnt, nbytes = self._last[:4]
+        base = gathered.data_ptr()
+        arr = C.c_void_p * world
+        idx_p = arr(*[C.c_void_p(base + g * nbytes + off_idx) for g in range(world)])
+        dist_p = arr(*[C.c_void_p(base + g * nbytes) for g in range(world)])
+        cnt_p = arr(*[C.c_void_p(base + g * nbytes + off_cnt) for g in range(world)])
+        key = ("out", nq, out_cap)
+        if key not in self._bufs:
+            self._bufs[key] = (torch.empty((nq, out_cap), dtype=torch.int32, device=self.torch_device),
+                               torch.empty((nq, out_cap), dtype=torch.float64, device=self.torch_device),
+                               torch.empty(nq, dtype=torch.int32, device=self.torch_device))
+        oi, od, oc = self._bufs[key]
+        stream = torch.cuda.current_stream(self.torch_device).cuda_stream
+        capi._check(self.lib.gc_merge_shard_lists_p2p_dev(self.device, stream, world, nq, cap, idx_p, dist_p, cnt_p, k_out,
+                                                          out_cap, oi.data_ptr(), od.data_ptr(), oc.data_ptr()))
+        return oi, od, oc
 
     def enable_p2p(self, group, nq_max: int, cap_max: int):
         self.peer = PeerBuffers(group, self.torch_device, nq_max, cap_max)
@@ -112,10 +133,19 @@ class CudaShardEngine:
             if key not in self._bufs:
                 if len(self._bufs) > 32:
                     self._bufs.clear()
-                self._bufs[key] = (torch.empty((nq, cap), dtype=torch.int32, device=self.torch_device),
-                                   torch.empty((nq, cap), dtype=torch.float64, device=self.torch_device),
-                                   torch.empty(nq, dtype=torch.int32, device=self.torch_device))
-            idx, dd, cnt = self._bufs[key]
+                # ONE buffer per shape -- dist f64 | idx u32 | count u32 -- so that the NCCL exchange is a single
+                # all-gather of it and the merge kernel reads every shard's three arrays through per-shard pointers
+                n = nq * cap
+                off_idx = 8 * n
+                off_cnt = off_idx + 4 * n
+                nbytes = (off_cnt + 4 * nq + 15) // 16 * 16
+                buf = torch.empty(nbytes, dtype=torch.uint8, device=self.torch_device)
+                self._bufs[key] = (buf, off_idx, off_cnt, nbytes,
+                                   buf[off_idx:off_idx + 4 * n].view(torch.int32).view(nq, cap),
+                                   buf[:8 * n].view(torch.float64).view(nq, cap),
+                                   buf[off_cnt:off_cnt + 4 * nq].view(torch.int32))
+            self._last = self._bufs[key]
+            idx, dd, cnt = self._last[4:7]
         if fill:
             idx.fill_(-1)  # 0xFFFFFFFF = no node
             dd.fill_(float("inf"))
@@ -214,6 +244,15 @@ class ShardedNodeStore:
             return idx, dd, torch.clamp(cnt, max=k_out)
         if self.exchange == "p2p" and self.world > 1:
             return self.engine.merge_p2p(idx.shape[0], idx.shape[1], k_out, out_cap)
+        if self.world > 1 and isinstance(self.engine, CudaShardEngine) and self.engine._last is not None and \
+                self.engine._last[4].data_ptr() == idx.data_ptr():
+            buf, nbytes = self.engine._last[0], self.engine._last[3]
+            key = ("gather", nbytes)
+            if key not in self.engine._bufs:
+                self.engine._bufs[key] = torch.empty(self.world * nbytes, dtype=torch.uint8, device=buf.device)
+            out = self.engine._bufs[key]
+            dist.all_gather_into_tensor(out, buf, group=self.group)
+            return self.engine.merge_gathered_packed(out, self.world, idx.shape[0], idx.shape[1], k_out, out_cap)
         return self.engine.merge(self._gather(idx), self._gather(dd), self._gather(cnt), k_out, out_cap)
 
     def nearest(self, q):

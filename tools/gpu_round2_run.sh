@@ -1,6 +1,7 @@
-mkdir -p gpurun_out/r2s13
-O=gpurun_out/r2s13
-timeout 600 python -m pytest tests/test_sharded_gpu.py -q -m gpu -k "few_queries or knn_large" > $O/pytest.log 2>&1; echo "pytest rc=$?" >> $O/pytest.log
-timeout 300 python tools/nn_bench.py --ops knn --tiles 1,8 > $O/nn_bench2.jsonl 2>&1
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/nn_launches.csv python tools/nn_bench.py --ops knn --tiles 1 --reps 2 > $O/ncu_nn.log 2>&1
-python tools/launch_summary.py $O/nn_launches.csv > $O/nn_launches_summary.txt 2>&1
+mkdir -p gpurun_out/r2s15
+O=gpurun_out/r2s15
+N=${GC_NGPU:-2}
+for ex in nccl p2p; do for q in 1 4096; do
+timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29518 tools/sharded_knn_bench.py --check --exchange $ex --queries $q >> $O/sharded_${N}gpu_$ex.jsonl 2>> $O/sharded_${N}gpu.err
+done; done
+tail -c 2000 $O/sharded_${N}gpu.err > $O/err.tail; rm -f $O/sharded_${N}gpu.err
