@@ -9,8 +9,8 @@ Layout
   tree_yaml.py  the reference's tree YAML format, written from / read into the SoA store
 """
 from . import capi  # noqa: F401
-from .capi import (CollisionWorld, GcError, NodeStore, device_count, device_info, extend_batch,  # noqa: F401
+from .capi import (CollisionWorld, GcError, NodeStore, ShardedStore, device_count, device_info, extend_batch,  # noqa: F401
                    sample_uniform)
 
-__all__ = ["capi", "NodeStore", "CollisionWorld", "GcError", "device_count", "device_info", "extend_batch",
+__all__ = ["capi", "NodeStore", "ShardedStore", "CollisionWorld", "GcError", "device_count", "device_info", "extend_batch",
            "sample_uniform"]

@@ -135,6 +135,19 @@ PROTOTYPES = {
                                            _c_double_p, C.c_uint32, C.c_double, C.c_double, C.c_double, C.c_double,
                                            C.c_void_p, C.c_void_p, _c_u8_p, _c_u32_p, _c_double_p, _c_double_p,
                                            _c_double_p, _c_u64_p]),
+    # node-sharded tree behind the C ABI (csrc/sharded.cu)
+    "gc_comm_init": (C.c_int, [C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_void_p)]),
+    "gc_comm_size": (C.c_int, [C.c_void_p]),
+    "gc_comm_destroy": (C.c_int, [C.c_void_p]),
+    "gc_store_create_sharded": (C.c_int, [C.c_void_p, C.c_int, C.c_uint64, C.POINTER(C.c_void_p)]),
+    "gc_sharded_store_destroy": (C.c_int, [C.c_void_p]),
+    "gc_sharded_store_size": (C.c_int, [C.c_void_p, _c_u64_p, _c_u32_p]),
+    "gc_sharded_store_append": (C.c_int, [C.c_void_p, _c_double_p, C.c_uint32, _c_u64_p]),
+    "gc_sharded_nn1": (C.c_int, [C.c_void_p, _c_double_p, C.c_uint32, _c_u32_p, _c_double_p]),
+    "gc_sharded_knn": (C.c_int, [C.c_void_p, _c_double_p, C.c_uint32, C.c_uint64, C.c_uint32, _c_u32_p, _c_double_p,
+                                 _c_u32_p]),
+    "gc_sharded_radius": (C.c_int, [C.c_void_p, _c_double_p, _c_double_p, C.c_uint32, C.c_uint32, _c_u32_p, _c_double_p,
+                                    _c_u32_p]),
     "gc_launch_count": (C.c_int, [_c_u64_p]),
     "gc_measure_fp32_peak": (C.c_int, [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "gc_flush_l2": (C.c_int, [C.c_int, C.c_size_t]),
@@ -322,6 +335,82 @@ class NodeStore:
         _check(self._lib.gc_knn(self._h, _ptr(q, _c_double_p), segp, nq, int(k), cap, _ptr(idx, _c_u32_p),
                                 _ptr(dist, _c_double_p), _ptr(count, _c_u32_p)))
         return idx, dist, count
+
+
+class ShardedStore:
+    """A tree node-sharded over the GPUs of one box, driven by ONE process through the C ABI (gc_comm_init /
+    gc_store_create_sharded): node i on shard i mod G, exchange fused into the merge kernel (peer loads)."""
+
+    def __init__(self, dim: int, capacity_total: int, devices):
+        self._lib = load()
+        self.dim = int(dim)
+        devs = (C.c_int * len(devices))(*[int(d) for d in devices])
+        c = C.c_void_p()
+        _check(self._lib.gc_comm_init(len(devices), devs, C.byref(c)))
+        self._comm = c
+        h = C.c_void_p()
+        rc = self._lib.gc_store_create_sharded(c, self.dim, int(capacity_total), C.byref(h))
+        if rc < 0:
+            self._lib.gc_comm_destroy(c)
+            _check(rc)
+        self._h = h
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.gc_sharded_store_destroy(self._h)
+            self._lib.gc_comm_destroy(self._comm)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def append(self, q) -> int:
+        q = _f64(q, (-1, self.dim))
+        first = C.c_uint64(0)
+        _check(self._lib.gc_sharded_store_append(self._h, _ptr(q, _c_double_p), q.shape[0], C.byref(first)))
+        return first.value
+
+    def size(self):
+        n, g = C.c_uint64(0), C.c_uint32(0)
+        _check(self._lib.gc_sharded_store_size(self._h, C.byref(n), C.byref(g)))
+        return n.value, g.value
+
+    def nearest(self, q):
+        q = _f64(q, (-1, self.dim))
+        nq = q.shape[0]
+        idx = np.empty(nq, dtype=np.uint32)
+        dist = np.empty(nq, dtype=np.float64)
+        _check(self._lib.gc_sharded_nn1(self._h, _ptr(q, _c_double_p), nq, _ptr(idx, _c_u32_p), _ptr(dist, _c_double_p)))
+        return idx, dist
+
+    def knn(self, q, k: int, cap: int | None = None):
+        q = _f64(q, (-1, self.dim))
+        nq = q.shape[0]
+        cap = int(k) if cap is None else int(cap)
+        idx = np.full((nq, cap), GC_NO_NODE, dtype=np.uint32)
+        dist = np.full((nq, cap), np.inf, dtype=np.float64)
+        count = np.zeros(nq, dtype=np.uint32)
+        _check(self._lib.gc_sharded_knn(self._h, _ptr(q, _c_double_p), nq, int(k), cap, _ptr(idx, _c_u32_p),
+                                        _ptr(dist, _c_double_p), _ptr(count, _c_u32_p)))
+        return idx, dist, count
+
+    def near(self, q, radius, cap: int = 256, grow: bool = True):
+        q = _f64(q, (-1, self.dim))
+        nq = q.shape[0]
+        radius = np.ascontiguousarray(np.broadcast_to(np.asarray(radius, dtype=np.float64), (nq,)))
+        while True:
+            idx = np.full((nq, cap), GC_NO_NODE, dtype=np.uint32)
+            dist = np.full((nq, cap), np.inf, dtype=np.float64)
+            count = np.zeros(nq, dtype=np.uint32)
+            rc = _check(self._lib.gc_sharded_radius(self._h, _ptr(q, _c_double_p), _ptr(radius, _c_double_p), nq, cap,
+                                                    _ptr(idx, _c_u32_p), _ptr(dist, _c_double_p), _ptr(count, _c_u32_p)))
+            if rc == GC_W_TRUNCATED and grow:
+                cap = int(2 ** np.ceil(np.log2(int(count.max()))))
+                continue
+            return idx, dist, count
 
 
 class CollisionWorld:

@@ -226,6 +226,30 @@ int gc_forest_dump(gc_forest_t* f, uint32_t p, int32_t* parents, double* pcost, 
 /* node ids root -> goal of the current solution (0 when unsolved); returns the length */
 int gc_forest_solution(gc_forest_t* f, uint32_t p, int32_t* ids, uint32_t cap);
 
+/* ---- node-sharded tree over the GPUs of one box ------------------------------------------
+ * One process (a graph_core planner is one) drives ndev shards: node i lives on shard i mod ndev at local slot
+ * i div ndev.  Queries are broadcast, every shard answers on its slice with the single-store kernels on its own
+ * stream, and the merge kernel on shard 0's device reads the other shards' lists through peer-mapped pointers
+ * (cudaDeviceEnablePeerAccess: NVLink / NVSwitch loads, no collective library).  Results carry GLOBAL slots and are
+ * ordered by (fp64 distance, global slot): what one KdTree / Vector over all nodes returns (kdtree.cpp:354-380,
+ * vector.cpp:55-96).  devices == NULL: shard g on device g; several shards may share a device. */
+typedef struct gc_comm gc_comm_t;
+typedef struct gc_sharded_store gc_sharded_store_t;
+int gc_comm_init(int ndev, const int* devices, gc_comm_t** out);
+int gc_comm_size(gc_comm_t* c);
+int gc_comm_destroy(gc_comm_t* c);
+int gc_store_create_sharded(gc_comm_t* c, int dim, uint64_t capacity_total, gc_sharded_store_t** out);
+int gc_sharded_store_destroy(gc_sharded_store_t* s);
+int gc_sharded_store_size(gc_sharded_store_t* s, uint64_t* nodes, uint32_t* shards);
+/* insert n nodes; they receive the global slots *first_global_slot .. + n - 1 (insertion order, as Vector's indices) */
+int gc_sharded_store_append(gc_sharded_store_t* s, const double* q, uint32_t n, uint64_t* first_global_slot);
+int gc_sharded_nn1(gc_sharded_store_t* s, const double* q, uint32_t nq, uint32_t* idx, double* dist);
+int gc_sharded_knn(gc_sharded_store_t* s, const double* q, uint32_t nq, uint64_t k, uint32_t cap, uint32_t* idx,
+                   double* dist, uint32_t* count);
+/* GC_W_TRUNCATED when a query has more than cap neighbours (count holds the true number), as gc_radius */
+int gc_sharded_radius(gc_sharded_store_t* s, const double* q, const double* radius, uint32_t nq, uint32_t cap,
+                      uint32_t* idx, double* dist, uint32_t* count);
+
 /* ---- device-resident lock-step BiRRT / RRT (BASELINE config 2) -------------------------------------------------
  * P independent problems advance by one BiRRT::update (src/graph_core/solvers/birrt.cpp:93-152) -- or, with
  * bidirectional = 0, one RRT::update (src/graph_core/solvers/rrt.cpp:119-157) -- per gc_birrt_step: ONE kernel launch,

@@ -288,3 +288,56 @@ def test_knn_few_queries_ties_tombstones_and_fallback(gc, orc):
     st2.append(same)
     gi, gd, gcnt = st2.knn(same[:2], 7, cap=7)
     assert np.array_equal(gi, np.tile(np.arange(7, dtype=np.uint32), (2, 1))) and np.all(gd == 0.0)
+
+
+# ---- the node-sharded tree behind the C ABI (gc_comm_init / gc_store_create_sharded, csrc/sharded.cu) ----------------
+@pytest.mark.parametrize("G", [1, 3, 8])
+def test_c_abi_sharded_store_matches_vector(gc, orc, G):
+    """All shards on device 0 here (the driver's GPU tests have one GPU): the per-shard kernels, the global-slot
+    arithmetic, the event ordering between the shards' streams and the peer-pointer merge are what a multi-GPU box runs
+    (tools/sharded_capi_check.py repeats this with one shard per GPU)."""
+    dim, n = 12, 40013
+    pts = W.c4_nodes(n, dim, seed=491)
+    qs = W.c4_queries(20, dim, seed=492)
+    st = gc.ShardedStore(dim, n + 64, [0] * G)
+    first = st.append(pts[:1000])
+    assert first == 0
+    assert st.append(pts[1000:1007]) == 1000      # a batch that does not divide by G
+    assert st.append(pts[1007:]) == 1007
+    assert st.size() == (n, G)
+    ov = orc.OracleNN("vector", dim)
+    ov.insert(pts)
+    gi, gd = st.nearest(qs)
+    ri, rd = ov.nearest(qs)
+    assert np.array_equal(gi.astype(np.int64), ri.astype(np.int64)) and np.array_equal(gd, rd)
+    for k in (1, 7, 300):
+        gi, gd, gcnt = st.knn(qs, k)
+        ri, rd, rc = ov.knn(qs, k, k)
+        assert np.array_equal(gcnt.astype(np.int64), rc.astype(np.int64))
+        assert np.array_equal(gi.astype(np.int64), ri.astype(np.int64)) and np.array_equal(gd, rd)
+    radius = W.c4_radius(60, n, dim)
+    gi, gd, gcnt = st.near(qs, radius, cap=16)  # too small on purpose: GC_W_TRUNCATED, the wrapper grows it
+    ri, rd, rc = ov.near(qs, radius, 4096)
+    assert np.array_equal(gcnt.astype(np.int64), rc.astype(np.int64)) and rc.max() > 16
+    for q in range(len(qs)):
+        assert np.array_equal(gi[q, :rc[q]].astype(np.int64), ri[q, :rc[q]].astype(np.int64))
+        assert np.array_equal(gd[q, :rc[q]], rd[q, :rc[q]])
+
+
+def test_c_abi_sharded_store_edge_cases(gc, orc):
+    from graph_core_b200 import capi
+    st = gc.ShardedStore(3, 100, [0, 0, 0, 0])
+    gi, gd = st.nearest(np.zeros((2, 3)))
+    assert np.all(gi == capi.GC_NO_NODE) and np.all(np.isinf(gd))   # empty tree (kdtree.cpp:356-358)
+    pts = W.c4_nodes(2, 3, seed=493)                                 # fewer nodes than shards
+    st.append(pts)
+    gi, gd, gcnt = st.knn(pts[:1], 5)
+    assert gcnt[0] == 2 and gi[0, 0] == 0 and gd[0, 0] == 0.0 and gi[0, 1] == 1
+    dup = np.tile(pts[:1], (9, 1))                                   # exact ties across shards: lowest global slot first
+    st.append(dup)
+    gi, gd, gcnt = st.knn(pts[:1], 6)
+    assert list(gi[0]) == [0, 2, 3, 4, 5, 6] and np.all(gd[0] == 0.0)
+    with pytest.raises(capi.GcError):
+        st.append(np.zeros((200, 3)))                                # beyond the capacity
+    with pytest.raises(capi.GcError):
+        gc.ShardedStore(3, 100, [0, 99])                             # no such device
