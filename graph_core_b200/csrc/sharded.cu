@@ -8,8 +8,14 @@
 // by (fp64 distance, global slot), i.e. exactly what one Vector / KdTree over all the nodes returns.
 // Several shards may sit on the same device (testing on one GPU; oversubscription).
 #include <algorithm>
+#include <condition_variable>
 #include <cstring>
+#include <functional>
 #include <limits>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <thread>
 #include <vector>
 
 #include "gc_common.cuh"
@@ -31,12 +37,73 @@ struct gc_comm
   std::vector<int> devices;
 };
 
+// One persistent host thread per shard (beyond shard 0, which the caller's thread serves): the per-shard query calls
+// enqueue several launches each and the k-nearest path ends with a one-word read-back, so issuing them from one thread
+// would serialise the shards.
+struct ShardWorker
+{
+  std::thread th;
+  std::mutex m;
+  std::condition_variable cv;
+  std::function<int()> job;
+  bool has = false, stop = false, done = true;
+  int rc = 0;
+  std::string err;
+  ShardWorker() { th = std::thread([this] { run(); }); }
+  ~ShardWorker()
+  {
+    {
+      std::lock_guard<std::mutex> lk(m);
+      stop = true;
+    }
+    cv.notify_all();
+    th.join();
+  }
+  void run()
+  {
+    for (;;)
+    {
+      std::unique_lock<std::mutex> lk(m);
+      cv.wait(lk, [&] { return has || stop; });
+      if (stop)
+        return;
+      std::function<int()> j = std::move(job);
+      has = false;
+      lk.unlock();
+      const int r = j();
+      std::string e = (r < 0) ? std::string(gc_last_error()) : std::string();
+      lk.lock();
+      rc = r;
+      err = std::move(e);
+      done = true;
+      cv.notify_all();
+    }
+  }
+  void submit(std::function<int()> f)
+  {
+    {
+      std::lock_guard<std::mutex> lk(m);
+      job = std::move(f);
+      has = true;
+      done = false;
+    }
+    cv.notify_all();
+  }
+  int wait()
+  {
+    std::unique_lock<std::mutex> lk(m);
+    cv.wait(lk, [&] { return done; });
+    return rc;
+  }
+};
+
 struct gc_shard
 {
   int device = 0;
   gc_store_t* store = nullptr;
   cudaEvent_t done = nullptr;
   gc::DevBuf d_q, d_radius, d_idx, d_dist, d_count;
+  std::unique_ptr<ShardWorker> worker;  // shards 1 .. G-1
 };
 
 struct gc_sharded_store
@@ -122,6 +189,8 @@ int gc_sharded_store_destroy(gc_sharded_store_t* s)
     return GC_OK;
   gc::CtxGuard guard;
   for (gc_shard& sh : s->shards)
+    sh.worker.reset();
+  for (gc_shard& sh : s->shards)
   {
     cudaSetDevice(sh.device);
     if (sh.store)
@@ -177,6 +246,8 @@ int gc_store_create_sharded(gc_comm_t* c, int dim, uint64_t capacity_total, gc_s
       return rc;
     }
   }
+  for (size_t g = 1; g < G; g++)
+    s->shards[g].worker.reset(new ShardWorker());
   s->root_stream = s->shards[0].store->stream;
   *out = s;
   return GC_OK;
@@ -244,9 +315,9 @@ static int sharded_query(gc_sharded_store* s, int mode, const double* q, uint32_
   const void* idx_p[16];
   const void* dist_p[16];
   const void* cnt_p[16];
-  for (uint32_t g = 0; g < G; g++)
-  {
+  auto shard_job = [=](uint32_t g) -> int {
     gc_shard& sh = s->shards[g];
+    gc::CtxGuard job_guard;
     GC_CUDA(cudaSetDevice(sh.device));
     cudaStream_t st = sh.store->stream;
     GC_TRY(sh.d_q.reserve(qb));
@@ -272,9 +343,27 @@ static int sharded_query(gc_sharded_store* s, int mode, const double* q, uint32_
                            sh.d_idx.as<uint32_t>(), sh.d_dist.as<double>(), sh.d_count.as<uint32_t>()));
     }
     GC_CUDA(cudaEventRecord(sh.done, st));
-    idx_p[g] = sh.d_idx.p;
-    dist_p[g] = sh.d_dist.p;
-    cnt_p[g] = sh.d_count.p;
+    return GC_OK;
+  };
+  for (uint32_t g = 1; g < G; g++)
+    s->shards[g].worker->submit([=] { return shard_job(g); });
+  int rc0 = shard_job(0);
+  for (uint32_t g = 1; g < G; g++)
+  {
+    const int r = s->shards[g].worker->wait();
+    if (r < 0 && rc0 >= 0)
+    {
+      gc::set_error("shard %u: %s", g, s->shards[g].worker->err.c_str());
+      rc0 = r;
+    }
+  }
+  if (rc0 < 0)
+    return rc0;
+  for (uint32_t g = 0; g < G; g++)
+  {
+    idx_p[g] = s->shards[g].d_idx.p;
+    dist_p[g] = s->shards[g].d_dist.p;
+    cnt_p[g] = s->shards[g].d_count.p;
   }
   // merge on shard 0's device, reading the other shards' lists through peer pointers
   gc_shard& root = s->shards[0];
