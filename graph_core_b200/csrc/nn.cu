@@ -1416,18 +1416,40 @@ __device__ __forceinline__ unsigned long long radix_select(uint32_t n, unsigned 
           atomicAdd(&hist[(uint32_t)(key >> (8 * r)) & 255u], 1u);
       }
     __syncthreads();
-    if (threadIdx.x == 0)
+    // bin holding the k-th key: inclusive scan of the 256 counts by the first 8 warps (was a 255-step serial walk by one
+    // thread, the largest single cost of the single-CTA select kernels); blockDim >= 256 at every call site
     {
-      unsigned long long cum = 0;
-      uint32_t d = 0;
-      for (; d < 255; d++)
+      __shared__ uint32_t warp_tot[8];
+      const uint32_t tid = threadIdx.x, lane = tid & 31u;
+      uint32_t c = 0, incl = 0;
+      if (tid < 256)
       {
-        if (cum + hist[d] >= k)
-          break;
-        cum += hist[d];
+        c = hist[tid];
+        incl = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1)
+        {
+          const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+          if (lane >= (uint32_t)o)
+            incl += v;
+        }
+        if (lane == 31)
+          warp_tot[tid >> 5] = incl;
       }
-      sh[0] = (unsigned long long)d;
-      sh[1] = k - cum;
+      __syncthreads();
+      if (tid < 256)
+      {
+        unsigned long long off = 0;
+        for (uint32_t w = 0; w < (tid >> 5); w++)
+          off += warp_tot[w];
+        const unsigned long long in = off + incl, ex = in - c;
+        // the last bin takes whatever is left (k <= number of eligible keys by contract)
+        if (ex < k && (k <= in || tid == 255))
+        {
+          sh[0] = (unsigned long long)tid;
+          sh[1] = k - ex;
+        }
+      }
     }
     __syncthreads();
     prefix |= sh[0] << (8 * r);
