@@ -1056,16 +1056,37 @@ __device__ __forceinline__ bool arm_check_grid(const ArmSmem& w, const ArmArgs& 
       if (!(fx >= 0.0f && fy >= 0.0f && fz >= 0.0f && fx < (float)a.gn[0] && fy < (float)a.gn[1] && fz < (float)a.gn[2]))
         continue;
       const uint32_t cell = ((uint32_t)fx * (uint32_t)a.gn[1] + (uint32_t)fy) * (uint32_t)a.gn[2] + (uint32_t)fz;
-      const uint32_t i0 = __ldg(a.gstart + cell), i1 = __ldg(a.gstart + cell + 1);
-      if (i0 == i1)
+      // cell record (arm_grid_records): up to three obstacle indices inline, so that most look-ups cost ONE gather
+      // before the shared-memory obstacle records instead of start/end plus the item list
+      const uint2 rec = __ldg(reinterpret_cast<const uint2*>(a.gstart) + cell);
+      const uint32_t cn = rec.x & 0xffffu;
+      if (cn == 0u)
         continue;
       const SphereK sk = sphere_consts(o[0], o[1], o[2], loc.w);
-      for (uint32_t i = i0; i < i1; i++)
+      if (cn <= 3u)
       {
-        const uint32_t idx = __ldg(a.gitems + i);
-        hit |= pair_hit(w.obs[idx], w.obs_na[idx], sk);
+        const uint32_t i0 = rec.x >> 16;
+        hit |= pair_hit(w.obs[i0], w.obs_na[i0], sk);
+        if (cn > 1u)
+        {
+          const uint32_t i1 = rec.y & 0xffffu;
+          hit |= pair_hit(w.obs[i1], w.obs_na[i1], sk);
+        }
+        if (cn > 2u)
+        {
+          const uint32_t i2 = rec.y >> 16;
+          hit |= pair_hit(w.obs[i2], w.obs_na[i2], sk);
+        }
       }
-      done += i1 - i0;
+      else
+      {
+        for (uint32_t i = rec.y; i < rec.y + cn; i++)
+        {
+          const uint32_t idx = __ldg(a.gitems + i);
+          hit |= pair_hit(w.obs[idx], w.obs_na[idx], sk);
+        }
+      }
+      done += cn;
     }
     if (j < J)
       fk_advance(AR, At, BR, w.joint + 12 * j);
@@ -1998,6 +2019,35 @@ int gc_world_create_sphere_arm(int njoints, const float* base_tf, const float* j
   std::vector<uint32_t> gstart;
   std::vector<uint16_t> gitems;
   arm_grid_build(w, njoints, base_tf, joint_tf, nrs, rs_local, nobs, cloud.data(), gstart, gitems);
+  // device form of the cell table (arm_check_grid): two words per cell -- count | first index << 16, then second |
+  // third << 16 for lists of at most three obstacles, or the offset of the list in gitems for longer ones
+  if (w->grid_cells)
+  {
+    std::vector<uint32_t> rec(2 * (size_t)w->grid_cells, 0u);
+    bool fits = true;
+    for (uint32_t c = 0; c < w->grid_cells; c++)
+    {
+      const uint32_t i0 = gstart[c], n = gstart[c + 1] - gstart[c];
+      if (n > 0xffffu)
+        fits = false;
+      if (n == 0)
+        continue;
+      if (n <= 3)
+      {
+        rec[2 * (size_t)c] = n | ((uint32_t)gitems[i0] << 16);
+        rec[2 * (size_t)c + 1] = (n > 1 ? (uint32_t)gitems[i0 + 1] : 0u) | ((n > 2 ? (uint32_t)gitems[i0 + 2] : 0u) << 16);
+      }
+      else
+      {
+        rec[2 * (size_t)c] = n;
+        rec[2 * (size_t)c + 1] = i0;
+      }
+    }
+    if (fits)
+      gstart.swap(rec);
+    else
+      w->grid_cells = 0;  // a cell with more than 65 535 obstacles: no grid for this world
+  }
   if (rc == GC_OK && w->grid_cells)
   {
     rc = upload(&w->d_grid_start, gstart.data(), gstart.size());

@@ -150,7 +150,7 @@ struct gc_world
   uint32_t nblk = 0;       // 0 = no block culling for this world
   // uniform grid over the part of the workspace where a robot sphere can touch an obstacle (edge.cu, "grid culling"):
   // cell -> the obstacles no sphere centred in the cell can rule out.  grid_cells == 0: no grid for this world
-  uint32_t* d_grid_start = nullptr;  // [grid_cells + 1]
+  uint32_t* d_grid_start = nullptr;  // [grid_cells][2] cell records (count + up to three inline indices, or the list offset)
   uint16_t* d_grid_items = nullptr;  // obstacle indices (positions in d_obs)
   uint32_t grid_cells = 0;
   int grid_n[3] = { 0, 0, 0 };
