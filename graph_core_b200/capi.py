@@ -135,6 +135,19 @@ PROTOTYPES = {
                                            _c_double_p, C.c_uint32, C.c_double, C.c_double, C.c_double, C.c_double,
                                            C.c_void_p, C.c_void_p, _c_u8_p, _c_u32_p, _c_double_p, _c_double_p,
                                            _c_double_p, _c_u64_p]),
+    # lock-step AnytimeRRT (csrc/anytime.cu)
+    "gc_anytime_create": (C.c_int, [C.c_void_p, C.c_void_p, _c_double_p, _c_double_p, C.c_uint32, _c_double_p,
+                                    _c_double_p, _c_double_p, C.POINTER(C.c_void_p)]),
+    "gc_anytime_destroy": (C.c_int, [C.c_void_p]),
+    "gc_anytime_step": (C.c_int, [C.c_void_p]),
+    "gc_anytime_run": (C.c_int, [C.c_void_p, C.c_uint64]),
+    "gc_anytime_stats": (C.c_int, [C.c_void_p, _c_u64_p]),
+    "gc_anytime_info": (C.c_int, [C.c_void_p, C.c_uint32, _c_i32_p, _c_i32_p, _c_double_p, _c_double_p, _c_double_p,
+                                  _c_u64_p, _c_u32_p, _c_u32_p]),
+    "gc_anytime_read_solved": (C.c_int, [C.c_void_p, _c_u8_p, _c_double_p]),
+    "gc_anytime_log": (C.c_int, [C.c_void_p, C.c_uint32, _c_double_p, C.c_uint32]),
+    "gc_anytime_solution": (C.c_int, [C.c_void_p, C.c_uint32, _c_double_p, _c_double_p, C.c_uint32]),
+    "gc_anytime_dump": (C.c_int, [C.c_void_p, C.c_uint32, C.c_int, _c_i32_p, _c_double_p, _c_double_p, C.c_uint32]),
     # node-sharded tree behind the C ABI (csrc/sharded.cu)
     "gc_comm_init": (C.c_int, [C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_void_p)]),
     "gc_comm_size": (C.c_int, [C.c_void_p]),

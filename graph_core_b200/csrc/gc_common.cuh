@@ -78,6 +78,36 @@ struct PinBuf
   T* as() { return reinterpret_cast<T*>(p); }
 };
 
+// cached device blocks for call sequences whose scratch sizes vary from call to call (informed.cu, anytime.cu):
+// get() hands out the smallest free cached block that fits (cudaMalloc otherwise), put() / reset() return blocks
+struct DevArena
+{
+  struct Block
+  {
+    void* p;
+    size_t bytes;
+    bool in_use;
+  };
+  std::vector<Block> blocks;
+  ~DevArena();
+  cudaError_t get_bytes(void** out, size_t bytes);
+  template <typename T>
+  cudaError_t get(T** out, size_t count)
+  {
+    void* p = nullptr;
+    const cudaError_t e = get_bytes(&p, sizeof(T) * (count ? count : 1));
+    *out = static_cast<T*>(p);
+    return e;
+  }
+  void put(void* p)
+  {
+    for (Block& b : blocks)
+      if (b.p == p)
+        b.in_use = false;
+  }
+  void reset();
+};
+
 int num_sms(int device);
 
 // every kernel launch site bumps this (bench.py reports it as "gpu_launches")
@@ -191,6 +221,21 @@ int steer_launch(const gc_store* s, const double* d_q, const uint32_t* d_seg, co
 int sample_informed_launch(int dim, uint32_t n, const double* d_lb, const double* d_ub, const double* d_f1,
                            const double* d_f2, const double* d_cost, unsigned long long seed,
                            unsigned long long first, double* d_out, cudaStream_t st);
+// Tree::informedExtend for n queries with device inputs and outputs (informed.cu); the outputs live in `arena`
+struct IeOut
+{
+  uint8_t* d_ok;
+  uint32_t* d_node;
+  double *d_new, *d_dist, *d_ecost;
+};
+int informed_extend_core(gc_store* s, gc_world* w, const double* d_q, const uint32_t* d_seg, const uint32_t* h_seg,
+                         const double* d_goal, const double* d_c2b, const double* d_bias, uint32_t n, double k_rrt,
+                         double max_distance, double min_distance, double tolerance, const int32_t* d_parent,
+                         const double* d_pcost, DevArena& arena, IeOut* out, uint64_t* edges_checked);
+// row i samples for problem d_prob[i] (rows d_prob[i] of d_f1 / d_f2 / d_out, cost d_cost[i]) from Philox counter d_ctr[i]
+int sample_informed_rows_launch(int dim, uint32_t n, const double* d_lb, const double* d_ub, const double* d_f1,
+                                const double* d_f2, const double* d_cost, unsigned long long seed,
+                                const uint32_t* d_prob, const unsigned long long* d_ctr, double* d_out, cudaStream_t st);
 // floats between consecutive rows of the fp32 SoA (cap_total + the padding the scans read past the last tile)
 constexpr int kStoreRowPad = 1024;
 static inline size_t store_row_stride(const gc_store* s) { return s->cap_total + kStoreRowPad; }

@@ -319,56 +319,78 @@ __global__ void ie_pick_kernel(IeRound r)
     default: gc::set_error("dimension %d not supported", dim); return GC_E_INVALID; \
   }
 
-struct DevScratch
+__global__ void ie_iota_kernel(uint32_t* v, uint32_t n)
 {
-  std::vector<void*> ptrs;
-  ~DevScratch()
-  {
-    for (void* p : ptrs)
-      cudaFree(p);
-  }
-  template <typename T>
-  cudaError_t get(T** out, size_t count)
-  {
-    void* p = nullptr;
-    cudaError_t e = cudaMalloc(&p, sizeof(T) * std::max<size_t>(count, 1));
-    if (e == cudaSuccess)
-      ptrs.push_back(p);
-    *out = static_cast<T*>(p);
-    return e;
-  }
-};
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n)
+    v[i] = i;
+}
 }  // namespace gc
 
 using namespace gc;
 
-extern "C" {
-
-int gc_informed_extend_batch(gc_store_t* s, gc_world_t* w, const double* q, const uint32_t* seg, const double* goal,
-                             const double* cost2beat, const double* bias, uint32_t n, double k_rrt,
-                             double max_distance, double min_distance, double tolerance, const int32_t* d_parent,
-                             const double* d_pcost, uint8_t* ok, uint32_t* tree_node, double* new_conf, double* distance,
-                             double* edge_cost, uint64_t* edges_checked)
+namespace gc
 {
-  GC_REQUIRE(s && w && q && seg && goal && cost2beat && bias && d_parent && d_pcost && ok && tree_node && new_conf,
-             "gc_informed_extend_batch: NULL argument");
-  GC_REQUIRE(s->dim == w->dim && s->device == w->device, "gc_informed_extend_batch: store and world do not match");
-  if (edges_checked)
-    *edges_checked = 0;
-  if (n == 0)
-    return GC_OK;
-  GC_SET_DEVICE(s->device);
+// DevArena (gc_common.cuh): cached device blocks, handed out best-fit and returned by reset()
+DevArena::~DevArena()
+{
+  for (Block& b : blocks)
+    cudaFree(b.p);
+}
+cudaError_t DevArena::get_bytes(void** out, size_t bytes)
+{
+  bytes = std::max<size_t>(align_up(bytes, 256), 256);
+  int best = -1;
+  for (size_t i = 0; i < blocks.size(); i++)
+    if (!blocks[i].in_use && blocks[i].bytes >= bytes && (best < 0 || blocks[i].bytes < blocks[(size_t)best].bytes))
+      best = (int)i;
+  if (best >= 0)
+  {
+    blocks[(size_t)best].in_use = true;
+    *out = blocks[(size_t)best].p;
+    return cudaSuccess;
+  }
+  void* p = nullptr;
+  // grow with head-room so that slowly growing requests (tree sizes) do not reallocate every call
+  const size_t want = bytes + bytes / 2;
+  cudaError_t e = cudaMalloc(&p, want);
+  size_t got = want;
+  if (e != cudaSuccess)
+  {
+    cudaGetLastError();
+    e = cudaMalloc(&p, bytes);
+    got = bytes;
+  }
+  if (e != cudaSuccess)
+    return e;
+  blocks.push_back(Block{ p, got, true });
+  *out = p;
+  return cudaSuccess;
+}
+void DevArena::reset()
+{
+  for (Block& b : blocks)
+    b.in_use = false;
+}
+
+// Tree::informedExtend for n queries, every input and output in device memory (see gc_informed_extend_batch for the
+// contract).  h_seg is the host copy of d_seg (k per query is derived from the host mirror of the store).  The
+// stream is synchronised between the candidate rounds (the number of undecided queries decides the next launch).
+int informed_extend_core(gc_store* s, gc_world* w, const double* d_q, const uint32_t* d_seg, const uint32_t* h_seg,
+                         const double* d_goal, const double* d_c2b, const double* d_bias, uint32_t n, double k_rrt,
+                         double max_distance, double min_distance, double tolerance, const int32_t* d_parent,
+                         const double* d_pcost, DevArena& arena, IeOut* out, uint64_t* edges_checked)
+{
   const int D = s->dim;
   cudaStream_t st = s->stream;
-  GC_CUDA(cudaStreamSynchronize(st));
   uint32_t mu = 1;
   std::vector<unsigned long long> kq(n);
   for (uint32_t i = 0; i < n; i++)
   {
-    GC_REQUIRE(seg[i] < s->nseg, "gc_informed_extend_batch: query %u: segment %u of %u", i, seg[i], s->nseg);
-    mu = std::max(mu, s->used[seg[i]]);
+    GC_REQUIRE(h_seg[i] < s->nseg, "gc_informed_extend_batch: query %u: segment %u of %u", i, h_seg[i], s->nseg);
+    mu = std::max(mu, s->used[h_seg[i]]);
     // Tree::nearK (tree.cpp:761-765): k = ceil(k_rrt * ln(size + 1)), size = live nodes
-    const double kd = (k_rrt > 0.0) ? std::ceil(k_rrt * std::log((double)s->live[seg[i]] + 1.0)) : 1.0e18;
+    const double kd = (k_rrt > 0.0) ? std::ceil(k_rrt * std::log((double)s->live[h_seg[i]] + 1.0)) : 1.0e18;
     kq[i] = (kd >= 1.0e18) ? ~0ull : (unsigned long long)kd;
   }
   GC_REQUIRE(mu <= kIeMaxNodes, "gc_informed_extend_batch: trees of more than %u nodes are not supported (%u)",
@@ -376,26 +398,13 @@ int gc_informed_extend_batch(gc_store_t* s, gc_world_t* w, const double* q, cons
   uint32_t P2 = 2;
   while (P2 < mu)
     P2 <<= 1;
-  DevScratch sc;
   IeArgs a{};
-  double *d_q, *d_goal, *d_c2b, *d_bias;
-  uint32_t* d_seg;
   unsigned long long* d_k;
-  GC_CUDA(sc.get(&d_q, (size_t)n * D));
-  GC_CUDA(sc.get(&d_goal, (size_t)n * D));
-  GC_CUDA(sc.get(&d_c2b, n));
-  GC_CUDA(sc.get(&d_bias, n));
-  GC_CUDA(sc.get(&d_seg, n));
-  GC_CUDA(sc.get(&d_k, n));
-  GC_CUDA(sc.get(&a.cand_d, (size_t)n * P2));
-  GC_CUDA(sc.get(&a.cand_slot, (size_t)n * P2));
-  GC_CUDA(sc.get(&a.order, (size_t)n * P2));
-  GC_CUDA(sc.get(&a.n_adm, n));
-  GC_CUDA(cudaMemcpyAsync(d_q, q, sizeof(double) * (size_t)n * D, cudaMemcpyHostToDevice, st));
-  GC_CUDA(cudaMemcpyAsync(d_goal, goal, sizeof(double) * (size_t)n * D, cudaMemcpyHostToDevice, st));
-  GC_CUDA(cudaMemcpyAsync(d_c2b, cost2beat, sizeof(double) * n, cudaMemcpyHostToDevice, st));
-  GC_CUDA(cudaMemcpyAsync(d_bias, bias, sizeof(double) * n, cudaMemcpyHostToDevice, st));
-  GC_CUDA(cudaMemcpyAsync(d_seg, seg, sizeof(uint32_t) * n, cudaMemcpyHostToDevice, st));
+  GC_CUDA(arena.get(&d_k, n));
+  GC_CUDA(arena.get(&a.cand_d, (size_t)n * P2));
+  GC_CUDA(arena.get(&a.cand_slot, (size_t)n * P2));
+  GC_CUDA(arena.get(&a.order, (size_t)n * P2));
+  GC_CUDA(arena.get(&a.n_adm, n));
   GC_CUDA(cudaMemcpyAsync(d_k, kq.data(), sizeof(unsigned long long) * n, cudaMemcpyHostToDevice, st));
   a.x32 = s->x32;
   a.x64 = s->x64;
@@ -424,32 +433,28 @@ int gc_informed_extend_batch(gc_store_t* s, gc_world_t* w, const double* q, cons
   uint32_t* d_node;
   double *d_new, *d_dist, *d_ecost;
   uint32_t *d_unres[2], *d_ctr;
-  GC_CUDA(sc.get(&d_ok, n));
-  GC_CUDA(sc.get(&d_node, n));
-  GC_CUDA(sc.get(&d_new, (size_t)n * D));
-  GC_CUDA(sc.get(&d_dist, n));
-  GC_CUDA(sc.get(&d_ecost, n));
-  GC_CUDA(sc.get(&d_unres[0], n));
-  GC_CUDA(sc.get(&d_unres[1], n));
-  GC_CUDA(sc.get(&d_ctr, 4));
+  GC_CUDA(arena.get(&d_ok, n));
+  GC_CUDA(arena.get(&d_node, n));
+  GC_CUDA(arena.get(&d_new, (size_t)n * D));
+  GC_CUDA(arena.get(&d_dist, n));
+  GC_CUDA(arena.get(&d_ecost, n));
+  GC_CUDA(arena.get(&d_unres[0], n));
+  GC_CUDA(arena.get(&d_unres[1], n));
+  GC_CUDA(arena.get(&d_ctr, 4));
   GC_CUDA(cudaMemsetAsync(d_ok, 0, n, st));
   GC_CUDA(cudaMemsetAsync(d_dist, 0, sizeof(double) * n, st));
   GC_CUDA(cudaMemsetAsync(d_ecost, 0, sizeof(double) * n, st));
   GC_CUDA(cudaMemsetAsync(d_new, 0, sizeof(double) * (size_t)n * D, st));
-  {
-    std::vector<uint32_t> all(n);
-    for (uint32_t i = 0; i < n; i++)
-      all[i] = i;
-    GC_CUDA(cudaMemcpyAsync(d_unres[0], all.data(), sizeof(uint32_t) * n, cudaMemcpyHostToDevice, st));
-    GC_CUDA(cudaStreamSynchronize(st));  // `all` and kq leave scope / are reused
-  }
+  ie_iota_kernel<<<(n + 255) / 256, 256, 0, st>>>(d_unres[0], n);
+  GC_CUDA(cudaGetLastError());
+  count_launch();
+  GC_CUDA(cudaStreamSynchronize(st));  // kq leaves scope
   uint32_t U = n, lo = 0, width = 4;
   int cur = 0;
   uint64_t edges_total = 0;
   while (U > 0)
   {
     const size_t ne = (size_t)U * width;
-    DevScratch round;
     IeRound r{};
     r.a = a;
     r.unres = d_unres[cur];
@@ -458,10 +463,15 @@ int gc_informed_extend_batch(gc_store_t* s, gc_world_t* w, const double* q, cons
     r.lo = lo;
     r.width = width;
     uint8_t* d_oke;
-    GC_CUDA(round.get(&r.c1, ne * D));
-    GC_CUDA(round.get(&r.c2, ne * D));
-    GC_CUDA(round.get(&r.edge_of, ne));
-    GC_CUDA(round.get(&d_oke, ne));
+    void* round_blocks[4];
+    GC_CUDA(arena.get(&r.c1, ne * D));
+    GC_CUDA(arena.get(&r.c2, ne * D));
+    GC_CUDA(arena.get(&r.edge_of, ne));
+    GC_CUDA(arena.get(&d_oke, ne));
+    round_blocks[0] = r.c1;
+    round_blocks[1] = r.c2;
+    round_blocks[2] = r.edge_of;
+    round_blocks[3] = d_oke;
     r.ctr = d_ctr;
     r.ok_edge = d_oke;
     r.ok = d_ok;
@@ -487,21 +497,67 @@ int gc_informed_extend_batch(gc_store_t* s, gc_world_t* w, const double* q, cons
     count_launch();
     GC_CUDA(cudaMemcpyAsync(hctr, d_ctr, sizeof(uint32_t) * 2, cudaMemcpyDeviceToHost, st));
     GC_CUDA(cudaStreamSynchronize(st));
+    for (void* b : round_blocks)
+      arena.put(b);
     U = hctr[1];
     cur ^= 1;
     lo += width;
     width = std::min<uint32_t>(width * 4u, 4096u);
   }
-  GC_CUDA(cudaMemcpyAsync(ok, d_ok, n, cudaMemcpyDeviceToHost, st));
-  GC_CUDA(cudaMemcpyAsync(tree_node, d_node, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost, st));
-  GC_CUDA(cudaMemcpyAsync(new_conf, d_new, sizeof(double) * (size_t)n * D, cudaMemcpyDeviceToHost, st));
-  if (distance)
-    GC_CUDA(cudaMemcpyAsync(distance, d_dist, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
-  if (edge_cost)
-    GC_CUDA(cudaMemcpyAsync(edge_cost, d_ecost, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
-  GC_CUDA(cudaStreamSynchronize(st));
+  out->d_ok = d_ok;
+  out->d_node = d_node;
+  out->d_new = d_new;
+  out->d_dist = d_dist;
+  out->d_ecost = d_ecost;
   if (edges_checked)
     *edges_checked = edges_total;
+  return GC_OK;
+}
+}  // namespace gc
+
+extern "C" {
+
+int gc_informed_extend_batch(gc_store_t* s, gc_world_t* w, const double* q, const uint32_t* seg, const double* goal,
+                             const double* cost2beat, const double* bias, uint32_t n, double k_rrt,
+                             double max_distance, double min_distance, double tolerance, const int32_t* d_parent,
+                             const double* d_pcost, uint8_t* ok, uint32_t* tree_node, double* new_conf, double* distance,
+                             double* edge_cost, uint64_t* edges_checked)
+{
+  GC_REQUIRE(s && w && q && seg && goal && cost2beat && bias && d_parent && d_pcost && ok && tree_node && new_conf,
+             "gc_informed_extend_batch: NULL argument");
+  GC_REQUIRE(s->dim == w->dim && s->device == w->device, "gc_informed_extend_batch: store and world do not match");
+  if (edges_checked)
+    *edges_checked = 0;
+  if (n == 0)
+    return GC_OK;
+  GC_SET_DEVICE(s->device);
+  const int D = s->dim;
+  cudaStream_t st = s->stream;
+  GC_CUDA(cudaStreamSynchronize(st));
+  DevArena arena;  // freed on return
+  double *d_q, *d_goal, *d_c2b, *d_bias;
+  uint32_t* d_seg;
+  GC_CUDA(arena.get(&d_q, (size_t)n * D));
+  GC_CUDA(arena.get(&d_goal, (size_t)n * D));
+  GC_CUDA(arena.get(&d_c2b, n));
+  GC_CUDA(arena.get(&d_bias, n));
+  GC_CUDA(arena.get(&d_seg, n));
+  GC_CUDA(cudaMemcpyAsync(d_q, q, sizeof(double) * (size_t)n * D, cudaMemcpyHostToDevice, st));
+  GC_CUDA(cudaMemcpyAsync(d_goal, goal, sizeof(double) * (size_t)n * D, cudaMemcpyHostToDevice, st));
+  GC_CUDA(cudaMemcpyAsync(d_c2b, cost2beat, sizeof(double) * n, cudaMemcpyHostToDevice, st));
+  GC_CUDA(cudaMemcpyAsync(d_bias, bias, sizeof(double) * n, cudaMemcpyHostToDevice, st));
+  GC_CUDA(cudaMemcpyAsync(d_seg, seg, sizeof(uint32_t) * n, cudaMemcpyHostToDevice, st));
+  IeOut o{};
+  GC_TRY(informed_extend_core(s, w, d_q, d_seg, seg, d_goal, d_c2b, d_bias, n, k_rrt, max_distance, min_distance,
+                              tolerance, d_parent, d_pcost, arena, &o, edges_checked));
+  GC_CUDA(cudaMemcpyAsync(ok, o.d_ok, n, cudaMemcpyDeviceToHost, st));
+  GC_CUDA(cudaMemcpyAsync(tree_node, o.d_node, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost, st));
+  GC_CUDA(cudaMemcpyAsync(new_conf, o.d_new, sizeof(double) * (size_t)n * D, cudaMemcpyDeviceToHost, st));
+  if (distance)
+    GC_CUDA(cudaMemcpyAsync(distance, o.d_dist, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
+  if (edge_cost)
+    GC_CUDA(cudaMemcpyAsync(edge_cost, o.d_ecost, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
+  GC_CUDA(cudaStreamSynchronize(st));
   return GC_OK;
 }
 

@@ -148,6 +148,10 @@ struct InformedArgs
   unsigned long long seed, first;
   double* out;         // [n][dim]
   uint32_t* attempts;  // optional [n]: rejection rounds used (101 = fallback, 0 = infinite cost)
+  // optional (lock-step AnytimeRRT, anytime.cu): row i works for problem prob[i] -- foci and output are rows prob[i] of
+  // f1 / f2 / out -- and draws from Philox counter ctr[i] instead of first + i
+  const uint32_t* prob;
+  const unsigned long long* ctr;
 };
 
 __global__ void sample_informed_kernel(InformedArgs a)
@@ -156,7 +160,8 @@ __global__ void sample_informed_kernel(InformedArgs a)
   if (i >= a.n)
     return;
   const int D = a.dim;
-  const unsigned long long ctr = a.first + i;
+  const unsigned long long ctr = a.ctr ? a.ctr[i] : a.first + i;
+  const size_t row = a.prob ? a.prob[i] : i;
   uint32_t cached_block = 0xFFFFFFFFu;
   uint32_t r[4];
   auto draw = [&](uint32_t j) {
@@ -174,7 +179,7 @@ __global__ void sample_informed_kernel(InformedArgs a)
       const double u = draw(j0 + (uint32_t)d);
       const double c = __dmul_rn(0.5, __dadd_rn(a.lb[d], a.ub[d]));
       const double hw = __dmul_rn(0.5, __dsub_rn(a.lb[d], a.ub[d]));
-      a.out[(size_t)i * D + d] = __dadd_rn(c, __dmul_rn(__dsub_rn(__dmul_rn(2.0, u), 1.0), hw));
+      a.out[row * D + d] = __dadd_rn(c, __dmul_rn(__dsub_rn(__dmul_rn(2.0, u), 1.0), hw));
     }
   };
   double cost = a.cost[i];
@@ -185,8 +190,8 @@ __global__ void sample_informed_kernel(InformedArgs a)
       a.attempts[i] = 0;
     return;
   }
-  const double* f1 = a.f1 + (size_t)i * D;
-  const double* f2 = a.f2 + (size_t)i * D;
+  const double* f1 = a.f1 + row * D;
+  const double* f2 = a.f2 + row * D;
   double R[GC_MAX_DIM][GC_MAX_DIM];  // R[row][col]
   double v[GC_MAX_DIM], centre[GC_MAX_DIM], axis[GC_MAX_DIM];
   double s2 = 0.0;
@@ -273,7 +278,7 @@ __global__ void sample_informed_kernel(InformedArgs a)
     if (inside)
     {
       for (int d = 0; d < D; d++)
-        a.out[(size_t)i * D + d] = q[d];
+        a.out[row * D + d] = q[d];
       if (a.attempts)
         a.attempts[i] = t + 1u;
       return;
@@ -310,6 +315,30 @@ int sample_informed_launch(int dim, uint32_t n, const double* d_lb, const double
   a.first = first;
   a.out = d_out;
   a.attempts = nullptr;
+  sample_informed_kernel<<<(n + 127) / 128, 128, 0, st>>>(a);
+  GC_CUDA(cudaGetLastError());
+  count_launch();
+  return GC_OK;
+}
+
+int sample_informed_rows_launch(int dim, uint32_t n, const double* d_lb, const double* d_ub, const double* d_f1,
+                                const double* d_f2, const double* d_cost, unsigned long long seed,
+                                const uint32_t* d_prob, const unsigned long long* d_ctr, double* d_out, cudaStream_t st)
+{
+  InformedArgs a{};
+  a.dim = dim;
+  a.n = n;
+  a.lb = d_lb;
+  a.ub = d_ub;
+  a.f1 = d_f1;
+  a.f2 = d_f2;
+  a.cost = d_cost;
+  a.seed = seed;
+  a.first = 0;
+  a.out = d_out;
+  a.attempts = nullptr;
+  a.prob = d_prob;
+  a.ctr = d_ctr;
   sample_informed_kernel<<<(n + 127) / 128, 128, 0, st>>>(a);
   GC_CUDA(cudaGetLastError());
   count_launch();

@@ -292,3 +292,110 @@ class LockstepBiRRT:
         if n < 0:
             raise capi.GcError(n, self.L.gc_last_error().decode())
         return wp[:n].copy(), cs[:max(n - 1, 0)].copy()
+
+
+class AnytimeConfig(C.Structure):
+    _fields_ = [("max_distance", C.c_double), ("min_distance", C.c_double), ("tolerance", C.c_double),
+                ("utopia_tolerance", C.c_double), ("delta", C.c_double), ("cost_impr", C.c_double), ("seed", C.c_uint64),
+                ("max_iter", C.c_uint32), ("capacity", C.c_uint32), ("extend", C.c_int32),
+                ("improve_in_solve", C.c_int32), ("keep_trees", C.c_int32), ("reserved", C.c_int32)]
+
+
+class LockstepAnytimeRRT:
+    """P independent AnytimeRRT queries (src/graph_core/solvers/anytime_rrt.cpp, BASELINE config 5) advanced together:
+    RRT::update during the first phase, AnytimeRRT::improve rounds (Tree::informedExtend) afterwards; csrc/anytime.cu.
+    Problem p draws its k-th sample from the informed Philox sampler with counter k * P + p."""
+
+    STATS = ("steps", "samples", "rrt_rows", "improve_rows", "nodes_added", "goal_edges", "improve_edges", "solved")
+    LOG_COLUMNS = ("phase", "iterations", "success", "path_cost", "tree_nodes", "bias", "cost2beat", "set_up")
+
+    def __init__(self, scenario, world: capi.CollisionWorld, starts, goals, max_iter: int, seed: int,
+                 sampler_cost0=None, capacity: int = 8192, extend: bool = False, improve_in_solve: bool = True,
+                 delta: float = 0.1, cost_impr: float = 0.1, keep_trees: bool = False):
+        self.L = capi.load()
+        self.dim = scenario.dim
+        starts = _f64(np.atleast_2d(starts))
+        goals = _f64(np.atleast_2d(goals))
+        assert starts.shape == goals.shape and starts.shape[1] == self.dim
+        self.n = starts.shape[0]
+        self.world = world
+        lb, ub = _f64(scenario.lb), _f64(scenario.ub)
+        c0 = None
+        if sampler_cost0 is not None:
+            c0 = np.ascontiguousarray(np.broadcast_to(np.asarray(sampler_cost0, dtype=np.float64), (self.n,)))
+        cfg = AnytimeConfig(scenario.max_distance, scenario.min_distance, 1e-6, scenario.utopia_tolerance, delta,
+                            cost_impr, int(seed), int(max_iter), int(capacity), 1 if extend else 0,
+                            1 if improve_in_solve else 0, 1 if keep_trees else 0, 0)
+        h = C.c_void_p()
+        capi._check(self.L.gc_anytime_create(world.handle, C.byref(cfg), lb.ctypes.data_as(_dp), ub.ctypes.data_as(_dp),
+                                             self.n, starts.ctypes.data_as(_dp), goals.ctypes.data_as(_dp),
+                                             c0.ctypes.data_as(_dp) if c0 is not None else None, C.byref(h)))
+        self.h = h
+        self.capacity = int(capacity)
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.gc_anytime_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _rc(self, r):
+        if r < 0:
+            raise capi.GcError(r, self.L.gc_last_error().decode())
+        return r
+
+    def step(self) -> int:
+        """One planner update of every live query; returns how many are still live."""
+        return self._rc(self.L.gc_anytime_step(self.h))
+
+    def run(self, max_steps: int = 0) -> int:
+        """AnytimeRRT::solve for all queries; returns how many are still live (0 unless max_steps cut the run)."""
+        return self._rc(self.L.gc_anytime_run(self.h, int(max_steps)))
+
+    def stats(self):
+        out = (C.c_uint64 * 8)()
+        capi._check(self.L.gc_anytime_stats(self.h, out))
+        return dict(zip(self.STATS, (int(v) for v in out)))
+
+    def info(self, p: int):
+        solved, done = C.c_int32(0), C.c_int32(0)
+        cost, bias, c2b = C.c_double(0), C.c_double(0), C.c_double(0)
+        k = C.c_uint64(0)
+        nodes, rows = C.c_uint32(0), C.c_uint32(0)
+        capi._check(self.L.gc_anytime_info(self.h, p, C.byref(solved), C.byref(done), C.byref(cost), C.byref(bias),
+                                           C.byref(c2b), C.byref(k), C.byref(nodes), C.byref(rows)))
+        return {"solved": bool(solved.value), "done": bool(done.value), "cost": cost.value, "bias": bias.value,
+                "cost2beat": c2b.value, "samples": k.value, "tree_nodes": nodes.value, "rounds": rows.value}
+
+    def solved(self):
+        s = np.zeros(self.n, dtype=np.uint8)
+        c = np.zeros(self.n, dtype=np.float64)
+        capi._check(self.L.gc_anytime_read_solved(self.h, s.ctypes.data_as(C.POINTER(C.c_uint8)), c.ctypes.data_as(_dp)))
+        return s.astype(bool), c
+
+    def log(self, p: int):
+        n = self._rc(self.L.gc_anytime_log(self.h, p, None, 0))
+        rows = np.zeros((max(n, 1), 8))
+        self._rc(self.L.gc_anytime_log(self.h, p, rows.ctypes.data_as(_dp), n))
+        return rows[:n]
+
+    def solution(self, p: int, cap: int = 8192):
+        wp = np.empty((cap, self.dim), dtype=np.float64)
+        cs = np.empty(cap, dtype=np.float64)
+        n = self._rc(self.L.gc_anytime_solution(self.h, p, wp.ctypes.data_as(_dp), cs.ctypes.data_as(_dp), cap))
+        return wp[:n].copy(), cs[:max(n - 1, 0)].copy()
+
+    def dump(self, p: int, which: int = 0):
+        """(parents, connection costs, configurations) of the growing tree (0) or the tree holding the solution (1)."""
+        cap = self.capacity + 1
+        par = np.empty(cap, dtype=np.int32)
+        pc = np.empty(cap, dtype=np.float64)
+        cf = np.empty((cap, self.dim), dtype=np.float64)
+        n = self._rc(self.L.gc_anytime_dump(self.h, p, which, par.ctypes.data_as(C.POINTER(C.c_int32)),
+                                            pc.ctypes.data_as(_dp), cf.ctypes.data_as(_dp), cap))
+        return par[:n].copy(), pc[:n].copy(), cf[:n].copy()

@@ -220,6 +220,36 @@ def c3_problems(checker, params, n: int, seed: int = 302):
     return out
 
 
+def c5_problems(checker, params, n: int, seed: int = 501, reach: float = 1.5, cost_factor: float = 1.5):
+    """BASELINE config 5 as benchmarked (C5'): n AnytimeRRT queries in the C3 world.  Start uniform in the joint box
+    (Philox seed 501), goal = start + reach * (uniform direction of the same draw), both collision free and inside the
+    box, straight connection blocked.  The solver's own sampler is an InformedSampler(start, goal, lb, ub, cost =
+    cost_factor * |goal - start|) -- with BASELINE's literal C5 (goals anywhere in the (2 pi)^7 box, unbounded sampler)
+    the reference does not find a first solution within 3 x 2 000 updates, so its improve rounds never start.
+    Returns (starts [n][7], goals [n][7], sampler_cost0 [n])."""
+    starts, goals = [], []
+    first = 0
+    t = np.linspace(0.0, 1.0, 65)[:, None]
+    while len(starts) < n:
+        u = philox_u01(seed, first, 64, 14)
+        first += 64
+        s = -math.pi + u[:, :7] * 2 * math.pi
+        v = 2.0 * u[:, 7:] - 1.0
+        v = v / np.sqrt((v * v).sum(axis=1))[:, None]
+        g = s + reach * v
+        ok = checker(params, s) & checker(params, g) & (np.abs(g) <= math.pi).all(axis=1)
+        for i in np.nonzero(ok)[0]:
+            line = s[i][None, :] + (g[i] - s[i])[None, :] * t
+            if not checker(params, line).all():
+                starts.append(s[i].copy())
+                goals.append(g[i].copy())
+                if len(starts) == n:
+                    break
+    starts, goals = np.array(starts), np.array(goals)
+    d = np.sqrt(((goals - starts) ** 2).sum(axis=1))
+    return starts, goals, cost_factor * d
+
+
 def c3_problem_pairs(n: int, seed: int = 302, first: int = 0):
     """Raw start/goal pairs for the multi-problem C3/C5 runs (before validity filtering)."""
     u = philox_u01(seed, first, n, 14)

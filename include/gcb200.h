@@ -304,6 +304,63 @@ int gc_informed_extend_batch(gc_store_t* store, gc_world_t* world, const double*
                              const double* d_pcost, uint8_t* ok, uint32_t* tree_node, double* new_conf,
                              double* distance, double* edge_cost, uint64_t* edges_checked);
 
+/* ---- lock-step AnytimeRRT (src/graph_core/solvers/anytime_rrt.cpp; BASELINE config 5) ---------------------------
+ * P independent queries over one collision world, problem p owning segment p of a node store the handle creates.
+ * Each gc_anytime_step is one planner update of every live problem: RRT::update (rrt.cpp:116-157: Tree::connect or
+ * Tree::extend towards a sample, then the goal connection) during the first phase -- up to FAILED_ITER = 3 rounds of
+ * max_iter updates, TreeSolver::solve (tree_solver.cpp:107-130) -- and AnytimeRRT::improveUpdate (:356-427:
+ * Tree::informedExtend on the round's tree, goal connection when cheaper) during the improve rounds
+ * (AnytimeRRT::improve :269-330: cost2beat = (1 - cost_impr) * path cost, bias -= delta down to 0.1, informed sampler
+ * of cost cost2beat, fresh tree; three failed rounds in a row end the query, :134-171).  Creation runs
+ * TreeSolver::setProblem (tree_solver.cpp:55-105) including the direct start -> goal ray, whose nodes stay in the tree.
+ * Samples: problem p draws its k-th sample from the informed Philox sampler (gc_sample_informed) with counter
+ * k * P + p, foci start/goal, cost sampler_cost0[p] (NULL or +inf: uniform in [lb, ub]) in the first phase and
+ * cost2beat in a round -- a problem's stream does not depend on the other problems.  With the same stream every
+ * problem makes the reference's decisions: rounds, iterations, tree sizes, path and costs are bit-identical.
+ * improve_in_solve: the reference's RRT::update leaves can_improve_ = false once the goal is connected (rrt.cpp:150), so
+ * AnytimeRRT::solve never enters its own improve loop; 0 reproduces that, 1 runs the loop (improve() is public and is
+ * what callers use).  Trees of at most 8192 nodes (capacity). */
+typedef struct gc_anytime gc_anytime_t;
+typedef struct gc_anytime_config
+{
+  double max_distance;     /* tree_solver.cpp:37 */
+  double min_distance;     /* checker resolution */
+  double tolerance;        /* util.h:80 TOLERANCE (0 = 1e-6) */
+  double utopia_tolerance; /* tree_solver.cpp:40 (1 is added, as TreeSolver::config does) */
+  double delta;            /* anytime_rrt.h:145 (0.1) */
+  double cost_impr;        /* anytime_rrt.h:145 (0.1) */
+  uint64_t seed;           /* Philox key */
+  uint32_t max_iter;       /* updates per round (solve()'s max_iter) */
+  uint32_t capacity;       /* nodes per tree, <= 8192 */
+  int32_t extend;          /* tree_solver.cpp `extend`: 1 = Tree::extend per update, 0 = Tree::connect */
+  int32_t improve_in_solve;
+  int32_t keep_trees;      /* keep a copy of the tree that holds each problem's solution (gc_anytime_dump which = 1) */
+  int32_t reserved;
+} gc_anytime_config_t;
+int gc_anytime_create(gc_world_t* world, const gc_anytime_config_t* cfg, const double* lb, const double* ub,
+                      uint32_t n_problems, const double* starts, const double* goals, const double* sampler_cost0,
+                      gc_anytime_t** out);
+int gc_anytime_destroy(gc_anytime_t* a);
+/* one update of every live problem; returns the number of problems still live (< 0: error) */
+int gc_anytime_step(gc_anytime_t* a);
+/* steps until every query ended or max_steps were made (0 = no limit); returns the number still live */
+int gc_anytime_run(gc_anytime_t* a, uint64_t max_steps);
+/* out: steps, samples drawn, RRT rows, improve rows, nodes appended, goal edges checked, edges checked inside
+ * informedExtend, first solutions found */
+int gc_anytime_stats(gc_anytime_t* a, uint64_t out[8]);
+int gc_anytime_info(gc_anytime_t* a, uint32_t p, int32_t* solved, int32_t* done, double* cost, double* bias,
+                    double* cost2beat, uint64_t* samples, uint32_t* tree_nodes, uint32_t* log_rows);
+int gc_anytime_read_solved(gc_anytime_t* a, uint8_t* solved, double* cost);
+/* one row of 8 doubles per finished round: phase (0 RRT, 1 improve), updates used, success, path cost afterwards, nodes
+ * in the round's tree (goal included when it succeeded), bias, cost2beat, 1 when the round was set up (0: improve()
+ * returned before building a tree); returns the number of rows */
+int gc_anytime_log(gc_anytime_t* a, uint32_t p, double* rows, uint32_t cap_rows);
+/* way points start -> goal and the connection costs between them; returns the number of way points (0 = unsolved) */
+int gc_anytime_solution(gc_anytime_t* a, uint32_t p, double* waypoints, double* costs, uint32_t cap);
+/* which = 0: the tree that is growing; 1: the tree that holds the solution (keep_trees).  Slot order = creation order,
+ * root first; returns the number of nodes */
+int gc_anytime_dump(gc_anytime_t* a, uint32_t p, int which, int32_t* parents, double* pcost, double* conf, uint32_t cap);
+
 /* ---- Philox samplers (uniform_sampler.cpp:34-39, informed_sampler.cpp:145-180) -------------- */
 /* n uniform samples in [lb, ub]; sample i uses Philox counter (first_index + i) */
 int gc_sample_uniform(int device, int dim, const double* lb, const double* ub, uint64_t seed, uint64_t first_index,

@@ -1297,6 +1297,186 @@ struct Solver
   }
 };
 
+
+// ============================================================================
+//  AnytimeRRT (src/graph_core/solvers/anytime_rrt.cpp), BASELINE config 5.
+//  The RRT phase is RRT::solve = TreeSolver::solve (tree_solver.cpp:107-130) over RRT::update (rrt.cpp:116-157);
+//  the improve rounds are AnytimeRRT::improve (:269-330) over improveUpdate (:356-427) and Tree::informedExtend.
+//  NOTE (reference as written): RRT::update leaves can_improve_ = false when it connects the goal (rrt.cpp:150), so the
+//  improve loop of AnytimeRRT::solve (:134) is never entered from solve(); the rounds are reached through the public
+//  improve().  `improve_in_solve` runs the loop of :134-171 with improve() called unconditionally, which is what a
+//  caller who wants the anytime behaviour writes on top of the public API.
+// ============================================================================
+struct AnytimeSolver
+{
+  static const int kFailedIter = 3;  // anytime_rrt.h:35
+  Solver base;
+  double bias_ = 0.9, delta_ = 0.1, cost_impr_ = 0.1, cost2beat_ = 0.0;  // setParameters (anytime_rrt.h:145-150)
+  std::unique_ptr<Tree> new_tree_;
+  int tmp_goal_node_ = -1;
+  std::vector<double> start_conf, goal_conf;
+  // per round: phase, iterations, success, path cost afterwards, nodes in the round's tree, bias, cost2beat, set up
+  std::vector<double> log;
+  unsigned long long samples_drawn = 0;
+
+  AnytimeSolver(int dim, World* w, const double* lb, const double* ub, const double* start, const double* goal,
+                double max_distance, double min_distance, double utopia_tolerance, bool use_kdtree, bool extend,
+                double delta, double cost_impr)
+    : base(Solver::RRT, dim, w, lb, ub, start, goal, max_distance, min_distance, 1.1, utopia_tolerance, use_kdtree,
+           extend),
+      delta_(delta), cost_impr_(cost_impr), start_conf(start, start + dim), goal_conf(goal, goal + dim)
+  {
+  }
+  void pushLog(int phase, unsigned iters, bool ok, double tree_nodes, bool setup)
+  {
+    const double row[8] = { (double)phase, (double)iters, ok ? 1.0 : 0.0, base.path_cost_, tree_nodes, bias_,
+                            cost2beat_,   setup ? 1.0 : 0.0 };
+    log.insert(log.end(), row, row + 8);
+  }
+  // AnytimeRRT::improve(start, goal, solution, cost2beat, max_iter) up to the loop (:269-315); false: returned early
+  bool improveBegin()
+  {
+    const int d = base.pool.dim;
+    const double cost2beat = (1.0 - cost_impr_) * base.path_cost_;  // :262
+    const double utopia = dist(goal_conf.data(), start_conf.data(), d);
+    base.can_improve_ = true;
+    if (base.cost_ <= base.utopia_tolerance_ * utopia)
+    {
+      base.can_improve_ = false;
+      return false;
+    }
+    if (cost2beat <= utopia)
+      return false;
+    const int tmp_start = base.pool.add(start_conf.data());
+    tmp_goal_node_ = base.pool.add(goal_conf.data());
+    new_tree_.reset(new Tree(&base.pool, tmp_start, base.max_distance_, base.world, base.min_distance_,
+                             base.use_kdtree_));
+    cost2beat_ = cost2beat;
+    bias_ = bias_ - delta_;
+    if (bias_ < 0.1)
+      bias_ = 0.1;
+    return true;
+  }
+  // AnytimeRRT::improveUpdate(point, solution)  :356-427
+  bool improveUpdate(const double* q)
+  {
+    const int d = base.pool.dim;
+    if (!base.can_improve_)
+      return true;
+    int new_node = -1;
+    if (new_tree_->informedExtend(q, new_node, goal_conf.data(), cost2beat_, bias_))
+    {
+      if (dist(base.pool.conf(new_node), goal_conf.data(), d) <= base.max_distance_)
+      {
+        const std::vector<int> chain = new_tree_->getConnectionToNode(new_node);
+        const double cost_node2goal = dist(base.pool.conf(new_node), goal_conf.data(), d);
+        double new_solution_cost = cost_node2goal;
+        for (int id : chain)
+          new_solution_cost += new_tree_->pcost[id];
+        if (new_solution_cost < base.cachedSolutionCost())
+        {
+          if (new_tree_->checkConnection(base.pool.conf(new_node), goal_conf.data()))
+          {
+            base.goal_node_ = tmp_goal_node_;
+            new_tree_->setParent(base.goal_node_, new_node, cost_node2goal);
+            new_tree_->nodes_->insert(base.goal_node_);
+            base.start_tree_ = std::move(new_tree_);
+            base.makeSolution();
+            base.path_cost_ = base.cachedSolutionCost();
+            base.cost_ = base.path_cost_ + base.goal_cost_;
+            return true;
+          }
+        }
+      }
+    }
+    return false;
+  }
+  template <class Sampler>
+  bool rrtRound(unsigned max_iter, Sampler&& sample)  // TreeSolver::solve
+  {
+    double q[GC_MAX_DIM];
+    unsigned it = 0;
+    bool ok = false;
+    for (; it < max_iter; it++)
+    {
+      if (base.solved_)  // RRT::update(PathPtr&) :102-108
+      {
+        base.can_improve_ = false;
+        ok = true;
+        break;
+      }
+      sample(kInf0(), q);
+      if (base.update(q))
+      {
+        ok = true;
+        it++;
+        break;
+      }
+    }
+    pushLog(0, it, ok, (double)base.start_tree_->nodes_->size_, true);
+    return ok;
+  }
+  double sampler_cost0 = kInf;  // cost bound of the solver's own sampler during the RRT phase
+  double kInf0() const { return sampler_cost0; }
+  template <class Sampler>
+  bool improveRound(unsigned max_iter, Sampler&& sample)
+  {
+    if (!improveBegin())
+    {
+      pushLog(1, 0, false, 0.0, false);
+      return false;
+    }
+    double q[GC_MAX_DIM];
+    unsigned it = 0;
+    bool ok = false;
+    for (; it < max_iter; it++)
+    {
+      sample(cost2beat_, q);
+      if (improveUpdate(q))
+      {
+        ok = true;
+        it++;
+        break;
+      }
+    }
+    pushLog(1, it, ok, ok ? (double)base.start_tree_->nodes_->size_ : (double)new_tree_->nodes_->size_, true);
+    return ok;
+  }
+  // AnytimeRRT::solve (:73-236) without the wall clock
+  template <class Sampler>
+  bool solve(unsigned max_iter, bool improve_in_solve, Sampler&& sample)
+  {
+    if (base.solved_ && base.cost_ <= base.utopia_tolerance_ * base.best_utopia_)
+    {
+      base.can_improve_ = false;
+      return true;
+    }
+    int n_failed = 0;
+    while (!base.solved_ && n_failed < kFailedIter)
+      if (!rrtRound(max_iter, sample))
+        n_failed++;
+    if (!base.solved_)
+      return false;
+    if (base.cost_ <= base.utopia_tolerance_ * base.best_utopia_)
+    {
+      base.can_improve_ = false;
+      return true;
+    }
+    n_failed = 0;
+    while ((improve_in_solve || base.can_improve_) && n_failed < kFailedIter)
+    {
+      const bool improved = improveRound(max_iter, sample);
+      improved ? (n_failed = 0) : (n_failed++);
+      if (base.cost_ <= base.utopia_tolerance_ * base.best_utopia_)
+      {
+        base.can_improve_ = false;
+        break;
+      }
+    }
+    return base.solved_;
+  }
+};
+
 }  // namespace orc
 
 // ============================================================================
@@ -1850,6 +2030,84 @@ int orc_solver_solution(void* sh, int* ids, int cap)
   }
   return n;
 }
+// ---- AnytimeRRT: sample k of problem p comes from the informed Philox sampler with counter k * P + p ------------
+struct OrcAnytime
+{
+  std::unique_ptr<AnytimeSolver> s;
+  std::vector<double> lb, ub;
+};
+void* orc_anytime_new(int dim, void* world, const double* lb, const double* ub, const double* start, const double* goal,
+                      double max_distance, double min_distance, double utopia_tolerance, int use_kdtree, int extend,
+                      double delta, double cost_impr, double sampler_cost0)
+{
+  OrcAnytime* a = new OrcAnytime();
+  a->lb.assign(lb, lb + dim);
+  a->ub.assign(ub, ub + dim);
+  a->s.reset(new AnytimeSolver(dim, (World*)world, lb, ub, start, goal, max_distance, min_distance, utopia_tolerance,
+                               use_kdtree != 0, extend != 0, delta, cost_impr));
+  a->s->sampler_cost0 = sampler_cost0;
+  return a;
+}
+void orc_anytime_free(void* h) { delete (OrcAnytime*)h; }
+void* orc_anytime_base(void* h) { return &((OrcAnytime*)h)->s->base; }  // for the orc_solver_* getters
+int orc_anytime_solve(void* h, unsigned int max_iter, int improve_in_solve, unsigned long long seed,
+                      unsigned long long p, unsigned long long P)
+{
+  OrcAnytime* a = (OrcAnytime*)h;
+  AnytimeSolver* s = a->s.get();
+  const int d = s->base.pool.dim;
+  auto sample = [&](double cost, double* q) {
+    PhiloxDraws draw{ s->samples_drawn * P + p, seed };
+    informed_sample(d, a->lb.data(), a->ub.data(), s->start_conf.data(), s->goal_conf.data(), cost, draw, q);
+    s->samples_drawn++;
+  };
+  return s->solve(max_iter, improve_in_solve != 0, sample) ? 1 : 0;
+}
+// step-wise access (the harness that drives the reference's own AnytimeRRT uses the same three calls)
+int orc_anytime_rrt_update(void* h, const double* q) { return ((OrcAnytime*)h)->s->base.update(q) ? 1 : 0; }
+int orc_anytime_improve_begin(void* h) { return ((OrcAnytime*)h)->s->improveBegin() ? 1 : 0; }
+int orc_anytime_improve_update(void* h, const double* q) { return ((OrcAnytime*)h)->s->improveUpdate(q) ? 1 : 0; }
+// out: bias, cost2beat, path_cost, cost, can_improve, solved, nodes in the round tree (0: none), samples drawn
+void orc_anytime_state(void* h, double* out)
+{
+  AnytimeSolver* s = ((OrcAnytime*)h)->s.get();
+  out[0] = s->bias_;
+  out[1] = s->cost2beat_;
+  out[2] = s->base.path_cost_;
+  out[3] = s->base.cost_;
+  out[4] = s->base.can_improve_ ? 1.0 : 0.0;
+  out[5] = s->base.solved_ ? 1.0 : 0.0;
+  out[6] = s->new_tree_ ? (double)s->new_tree_->nodes_->size_ : 0.0;
+  out[7] = (double)s->samples_drawn;
+}
+int orc_anytime_log(void* h, int cap_rows, double* rows)
+{
+  AnytimeSolver* s = ((OrcAnytime*)h)->s.get();
+  const int n = (int)(s->log.size() / 8);
+  for (int i = 0; i < n && i < cap_rows; i++)
+    std::memcpy(rows + (size_t)i * 8, s->log.data() + (size_t)i * 8, sizeof(double) * 8);
+  return n;
+}
+// the solution as configurations root -> goal; returns the number of waypoints
+int orc_anytime_solution(void* h, int cap, double* conf)
+{
+  AnytimeSolver* s = ((OrcAnytime*)h)->s.get();
+  if (!s->base.solved_)
+    return 0;
+  const int d = s->base.pool.dim;
+  int n = 0;
+  if (cap > 0)
+    std::memcpy(conf, s->base.pool.conf(s->base.start_tree_->root_), sizeof(double) * d);
+  n++;
+  for (int id : s->base.solution_)
+  {
+    if (n < cap)
+      std::memcpy(conf + (size_t)n * d, s->base.pool.conf(id), sizeof(double) * d);
+    n++;
+  }
+  return n;
+}
+
 // counters: nn1, near, knn, edges, near_hits, state_checks, pair_tests
 void orc_solver_counters(void* sh, unsigned long long* out)
 {

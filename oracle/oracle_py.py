@@ -86,6 +86,17 @@ def lib(fast: bool = False):
         "orc_solver_dump": (None, [vp, _ip, _dp, _dp]),
         "orc_solver_solution": (C.c_int, [vp, _ip, C.c_int]),
         "orc_solver_counters": (None, [vp, _u64p]),
+        "orc_anytime_new": (vp, [C.c_int, vp, _dp, _dp, _dp, _dp, C.c_double, C.c_double, C.c_double, C.c_int, C.c_int,
+                                 C.c_double, C.c_double, C.c_double]),
+        "orc_anytime_free": (None, [vp]),
+        "orc_anytime_base": (vp, [vp]),
+        "orc_anytime_solve": (C.c_int, [vp, C.c_uint, C.c_int, C.c_ulonglong, C.c_ulonglong, C.c_ulonglong]),
+        "orc_anytime_rrt_update": (C.c_int, [vp, _dp]),
+        "orc_anytime_improve_begin": (C.c_int, [vp]),
+        "orc_anytime_improve_update": (C.c_int, [vp, _dp]),
+        "orc_anytime_state": (None, [vp, _dp]),
+        "orc_anytime_log": (C.c_int, [vp, C.c_int, _dp]),
+        "orc_anytime_solution": (C.c_int, [vp, C.c_int, _dp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)
@@ -362,3 +373,72 @@ class OracleSolver:
         self.L.orc_solver_counters(self.h, out)
         keys = ["nn1", "near", "knn", "edges", "near_hits", "state_checks", "pair_tests"]
         return dict(zip(keys, [int(v) for v in out]))
+
+
+ANYTIME_LOG_COLUMNS = ("phase", "iterations", "success", "path_cost", "tree_nodes", "bias", "cost2beat", "set_up")
+
+
+class OracleAnytime:
+    """AnytimeRRT (src/graph_core/solvers/anytime_rrt.cpp) restated; sample k of problem p of P comes from the informed
+    Philox sampler with counter k * P + p (foci start/goal, cost = sampler_cost0 in the RRT phase, cost2beat in a round).
+    """
+
+    def __init__(self, scenario, world: OracleWorld, start=None, goal=None, use_kdtree=True, extend=False, delta=0.1,
+                 cost_impr=0.1, sampler_cost0=float("inf"), fast=False):
+        self.L = lib(fast)
+        self.world = world
+        self.dim = scenario.dim
+        s = _f64(scenario.start if start is None else start)
+        g = _f64(scenario.goal if goal is None else goal)
+        lb, ub = _f64(scenario.lb), _f64(scenario.ub)
+        self.h = self.L.orc_anytime_new(self.dim, world.h, _p(lb, _dp), _p(ub, _dp), _p(s, _dp), _p(g, _dp),
+                                        scenario.max_distance, scenario.min_distance, scenario.utopia_tolerance,
+                                        1 if use_kdtree else 0, 1 if extend else 0, delta, cost_impr, sampler_cost0)
+
+    def __del__(self):
+        try:
+            self.L.orc_anytime_free(self.h)
+        except Exception:
+            pass
+
+    def solve(self, max_iter, seed, p=0, P=1, improve_in_solve=True):
+        return bool(self.L.orc_anytime_solve(self.h, max_iter, 1 if improve_in_solve else 0, seed, p, P))
+
+    def rrt_update(self, q):
+        q = _f64(q)
+        return bool(self.L.orc_anytime_rrt_update(self.h, _p(q, _dp)))
+
+    def improve_begin(self):
+        return bool(self.L.orc_anytime_improve_begin(self.h))
+
+    def improve_update(self, q):
+        q = _f64(q)
+        return bool(self.L.orc_anytime_improve_update(self.h, _p(q, _dp)))
+
+    def state(self):
+        out = np.zeros(8)
+        self.L.orc_anytime_state(self.h, _p(out, _dp))
+        keys = ["bias", "cost2beat", "path_cost", "cost", "can_improve", "solved", "round_tree_nodes", "samples_drawn"]
+        return dict(zip(keys, out.tolist()))
+
+    def log(self):
+        n = self.L.orc_anytime_log(self.h, 0, None)
+        rows = np.zeros((max(n, 1), 8))
+        self.L.orc_anytime_log(self.h, n, _p(rows, _dp))
+        return rows[:n]
+
+    def solution(self):
+        wp = np.empty((1 << 14, self.dim))
+        n = self.L.orc_anytime_solution(self.h, wp.shape[0], _p(wp, _dp))
+        return wp[:n].copy()
+
+    def dump(self):
+        """parents, connection costs, configurations of every node the solver created (ids = creation order); the
+        tree in use is the one rooted at the last solution's first waypoint."""
+        b = self.L.orc_anytime_base(self.h)
+        n = self.L.orc_solver_num_nodes(b)
+        par = np.empty(n, np.int32)
+        pc = np.empty(n, np.float64)
+        conf = np.empty((n, self.dim), np.float64)
+        self.L.orc_solver_dump(b, _p(par, _ip), _p(pc, _dp), _p(conf, _dp))
+        return par, pc, conf

@@ -394,6 +394,50 @@ double ref_solver_path_cost(void* h)
   return p ? p->cost() : std::numeric_limits<double>::infinity();
 }
 
+// ---- AnytimeRRT step by step (anytime_rrt.cpp:269-427) with injected samples ---------------------------------------
+// improve(start, goal, solution, max_iter = 0) runs the reference's own round set-up (utopia tests, cost2beat, bias,
+// new tree, :269-315) without drawing a sample; improveUpdate(point, solution) is then one iteration of its loop.
+// Returns 1 when a round tree was set up, 0 when improve() returned before (nothing changed but can_improve_).
+int ref_anytime_improve_begin(void* h)
+{
+  RefSolver* s = (RefSolver*)h;
+  AnytimeRRTPtr a = std::dynamic_pointer_cast<AnytimeRRT>(s->solver);
+  if (!a)
+    return -1;
+  TreePtr before = a->getNewTree();
+  NodePtr tmp_start = std::make_shared<Node>(s->start->getConfiguration(), g_logger);
+  NodePtr tmp_goal = std::make_shared<Node>(s->goal->getConfiguration(), g_logger);
+  a->improve(tmp_start, tmp_goal, s->solution, 0u, std::numeric_limits<double>::infinity());
+  return (a->getNewTree() != before) ? 1 : 0;
+}
+int ref_anytime_improve_update(void* h, const double* q)
+{
+  RefSolver* s = (RefSolver*)h;
+  AnytimeRRTPtr a = std::dynamic_pointer_cast<AnytimeRRT>(s->solver);
+  if (!a)
+    return -1;
+  return a->improveUpdate(toVec(q, s->dim), s->solution) ? 1 : 0;
+}
+// out: bias, cost2beat, path_cost, cost, can_improve, solved, nodes in the round tree (0: none)
+void ref_anytime_state(void* h, double* out)
+{
+  RefSolver* s = (RefSolver*)h;
+  AnytimeRRTPtr a = std::dynamic_pointer_cast<AnytimeRRT>(s->solver);
+  out[0] = a->getBias();
+  out[1] = a->getCost2Beat();
+  out[2] = a->getPathCost();
+  out[3] = a->cost();
+  out[4] = a->canImprove() ? 1.0 : 0.0;
+  out[5] = a->solved() ? 1.0 : 0.0;
+  out[6] = a->getNewTree() ? (double)a->getNewTree()->getNumberOfNodes() : 0.0;
+}
+void ref_anytime_set_parameters(void* h, double delta, double cost_impr)
+{
+  AnytimeRRTPtr a = std::dynamic_pointer_cast<AnytimeRRT>(((RefSolver*)h)->solver);
+  if (a)
+    a->setParameters(delta, cost_impr);
+}
+
 // ---- Path validity and local optimisation with the SOLVER'S OWN checker ------------
 // Path::isValid (path.cpp:1230-1260 -> isValidFromConn): every connection of the solution is re-checked, invalid
 // ones get cost +inf.  costs[i] receives the cost of connection i afterwards; returns 1 valid, 0 invalid, -1 no path.

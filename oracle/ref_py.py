@@ -87,6 +87,10 @@ def lib(fast: bool = False, dropin: bool = False):
         "ref_solution_is_valid_from": (C.c_int, [vp, vp, C.c_int, C.c_double]),
         "ref_solution_optimize": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, _dp, _dp]),
         "ref_tree_recheck": (C.c_int, [vp]),
+        "ref_anytime_improve_begin": (C.c_int, [vp]),
+        "ref_anytime_improve_update": (C.c_int, [vp, _dp]),
+        "ref_anytime_state": (None, [vp, _dp]),
+        "ref_anytime_set_parameters": (None, [vp, C.c_double, C.c_double]),
         "ref_informed_extend": (C.c_int, [C.c_int, vp, C.c_int, _dp, C.POINTER(C.c_int), _dp, C.c_double, C.c_int, _dp, _dp,
                                           C.c_double, C.c_double, _dp, C.POINTER(C.c_int)]),
         "ref_check_path_to_node": (C.c_int, [vp, vp, _dp, C.c_int, C.c_int, _dp, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
@@ -329,6 +333,25 @@ class RefSolver:
         n = self.L.ref_solver_solution(self.h, wp.shape[0], _p(wp, _dp))
         return wp[:n].copy()
 
+    # ---- AnytimeRRT step by step (kind ANYTIME only) -------------------------------------------------------------
+    def improve_begin(self):
+        r = self.L.ref_anytime_improve_begin(self.h)
+        assert r >= 0, "not an AnytimeRRT"
+        return bool(r)
+
+    def improve_update(self, q):
+        q = _f64(q)
+        return bool(self.L.ref_anytime_improve_update(self.h, _p(q, _dp)))
+
+    def anytime_state(self):
+        out = np.zeros(8)
+        self.L.ref_anytime_state(self.h, _p(out, _dp))
+        keys = ["bias", "cost2beat", "path_cost", "cost", "can_improve", "solved", "round_tree_nodes"]
+        return dict(zip(keys, out.tolist()))
+
+    def set_anytime_parameters(self, delta=0.1, cost_impr=0.1):
+        self.L.ref_anytime_set_parameters(self.h, delta, cost_impr)
+
     @property
     def path_cost(self):
         return self.L.ref_solver_path_cost(self.h)
@@ -485,3 +508,65 @@ def informed_extend(checker: RefChecker, conf, parent, pcost, max_distance, q, g
                                max_distance, 1 if use_kdtree else 0, _p(q, _dp), _p(goal, _dp), cost2beat, bias,
                                _p(new, _dp), C.byref(pi))
     return bool(ok), new, pi.value
+
+
+def anytime_solve(solver, sample_fn, max_iter, improve_in_solve=True, failed_iter=3, utopia_tolerance=None,
+                  best_utopia=None):
+    """AnytimeRRT::solve (anytime_rrt.cpp:73-236) driven through the reference's own public methods with injected
+    samples: RRT::update(configuration) for the first phase (TreeSolver::solve's loop, tree_solver.cpp:117-127),
+    improve(max_iter = 0) + improveUpdate(configuration) for the rounds.  sample_fn(k, cost) -> the k-th sample of this
+    problem from the informed set of that cost.  improve_in_solve: enter the improve loop although RRT::update left
+    can_improve_ false (rrt.cpp:150) -- see oracle/gc_oracle.cpp AnytimeSolver.  Returns (solved, log rows) with the
+    columns of oracle_py.ANYTIME_LOG_COLUMNS (tree_nodes / set_up / bias / cost2beat read from the solver)."""
+    log = []
+    k = 0
+
+    def row(phase, iters, ok, setup, tree_nodes):
+        st = solver.anytime_state()
+        # cost2beat_ is uninitialised in the reference until the first improve()
+        log.append([phase, iters, 1.0 if ok else 0.0, st["path_cost"], tree_nodes, st["bias"],
+                    st["cost2beat"] if phase == 1 else 0.0, 1.0 if setup else 0.0])
+
+    tol_utopia = utopia_tolerance * best_utopia
+    if solver.solved and solver.cost <= tol_utopia:
+        return True, np.array(log).reshape(-1, 8)
+    n_failed = 0
+    while (not solver.solved) and n_failed < failed_iter:
+        ok = False
+        it = 0
+        while it < max_iter:
+            q = sample_fn(k, None)
+            k += 1
+            it += 1
+            if solver.update(q):
+                ok = True
+                break
+        row(0, it, ok, True, solver.tree_size)
+        if not ok:
+            n_failed += 1
+    if not solver.solved:
+        return False, np.array(log).reshape(-1, 8)
+    if solver.cost <= tol_utopia:
+        return True, np.array(log).reshape(-1, 8)
+    n_failed = 0
+    while (improve_in_solve or solver.can_improve) and n_failed < failed_iter:
+        if not solver.improve_begin():
+            row(1, 0, False, False, 0.0)
+            improved = False
+        else:
+            c2b = solver.anytime_state()["cost2beat"]
+            improved = False
+            it = 0
+            while it < max_iter:
+                q = sample_fn(k, c2b)
+                k += 1
+                it += 1
+                if solver.improve_update(q):
+                    improved = True
+                    break
+            st = solver.anytime_state()
+            row(1, it, improved, True, solver.tree_size if improved else st["round_tree_nodes"])
+        n_failed = 0 if improved else n_failed + 1
+        if solver.cost <= tol_utopia:
+            break
+    return solver.solved, np.array(log).reshape(-1, 8)

@@ -354,3 +354,70 @@ def test_informed_sampler_distribution_matches_reference(orc, ref, dim):
     got, att = orc.sample_informed(lb, ub, f1[None], f2[None], 0.5 * fd, seed=5)
     t = (got[0] - f2) @ (f1 - f2) / fd ** 2
     assert np.allclose(f2 + t * (f1 - f2), got[0], atol=1e-12) and -1e-12 <= t <= 1 + 1e-12
+
+
+# ---------------------------------------------------------------------------------------------------
+# AnytimeRRT (BASELINE config 5): the restatement against the reference's own update / improve / improveUpdate
+# ---------------------------------------------------------------------------------------------------
+def _anytime_pair(orc, ref, sc, start, goal, cost0, max_iter, seed, p, P, extend, improve_in_solve=True):
+    o = orc.OracleAnytime(sc, orc.OracleWorld.from_scenario(sc), start=start, goal=goal, extend=extend,
+                          sampler_cost0=cost0)
+    so = o.solve(max_iter, seed, p, P, improve_in_solve=improve_in_solve)
+    rc = ref.RefChecker.over_oracle_world(orc.OracleWorld.from_scenario(sc), sc.min_distance)
+    r = ref.RefSolver(ref.RefSolver.ANYTIME, sc, rc, start=start, goal=goal, extend=extend, informed=True)
+    lb, ub = np.asarray(sc.lb, float), np.asarray(sc.ub, float)
+
+    def sample_fn(k, cost):
+        c = cost0 if cost is None else cost
+        q, _ = orc.sample_informed(lb, ub, start[None, :], goal[None, :], np.array([c]), seed, k * P + p)
+        return q[0]
+
+    sr, log_r = ref.anytime_solve(r, sample_fn, max_iter, improve_in_solve=improve_in_solve,
+                                  utopia_tolerance=1.0 + sc.utopia_tolerance,
+                                  best_utopia=float(np.sqrt(((goal - start) ** 2).sum())))
+    return o, so, r, sr, log_r
+
+
+@pytest.mark.parametrize("extend", [False, True])
+def test_anytime_rrt_matches_reference_c1(orc, ref, extend):
+    """2-D boxes: nearK really cuts the neighbourhood (k < N), several improve rounds succeed."""
+    sc = W.scenario_c1()
+    s, g = np.asarray(sc.start, float), np.asarray(sc.goal, float)
+    rounds = 0
+    for seed, p, P in ((11, 0, 1), (12, 3, 8), (13, 5, 8)):
+        o, so, r, sr, log_r = _anytime_pair(orc, ref, sc, s, g, float("inf"), 400, seed, p, P, extend)
+        assert so == sr and so
+        assert np.array_equal(o.log(), log_r)
+        assert np.array_equal(o.solution(), r.solution())
+        assert o.state()["cost"] == r.cost
+        rounds += int(log_r[:, 2].sum())
+    assert rounds >= 5  # first solutions + successful improve rounds
+
+
+def test_anytime_rrt_solve_as_written_never_improves(orc, ref):
+    """rrt.cpp:150 leaves can_improve_ false, so AnytimeRRT::solve's own improve loop (:134) is a no-op: the
+    reference's solve() and the restatement with improve_in_solve = False both stop after the first solution."""
+    sc = W.scenario_c1()
+    s, g = np.asarray(sc.start, float), np.asarray(sc.goal, float)
+    o, so, r, sr, log_r = _anytime_pair(orc, ref, sc, s, g, float("inf"), 400, 11, 0, 1, False, improve_in_solve=False)
+    assert so and sr and log_r.shape[0] == 1 and np.array_equal(o.log(), log_r)
+    r2 = ref.RefSolver(ref.RefSolver.ANYTIME, sc, ref.RefChecker.over_oracle_world(orc.OracleWorld.from_scenario(sc),
+                                                                                   sc.min_distance), informed=True)
+    assert r2.solve(400) and not r2.can_improve
+    assert r2.anytime_state()["bias"] == 0.9  # no improve() was ever called
+
+
+def test_anytime_rrt_matches_reference_c5(orc, ref, c3):
+    """C5' queries (7-DoF sphere arm, informed first phase): rounds, iterations, tree sizes, costs and paths."""
+    arm = orc.arm_checker()
+    starts, goals, cost0 = W.c5_problems(arm, c3.params, 3)
+    solved = 0
+    for p in range(3):
+        o, so, r, sr, log_r = _anytime_pair(orc, ref, c3, starts[p], goals[p], float(cost0[p]), 250, 501, p, 3, False)
+        assert so == sr
+        assert np.array_equal(o.log(), log_r)
+        if so:
+            solved += 1
+            assert np.array_equal(o.solution(), r.solution())
+            assert o.state()["cost"] == r.cost
+    assert solved >= 1

@@ -1,4 +1,5 @@
-mkdir -p gpurun_out/r2s20
-O=gpurun_out/r2s20
-timeout 900 python -m pytest tests/test_edge_gpu.py tests/test_planner_gpu.py tests/test_golden_gpu.py -q -m gpu > $O/pytest.log 2>&1; echo "pytest rc=$?" >> $O/pytest.log
-timeout 600 python bench.py --skip-nn --skip-extras > $O/bench.json 2> $O/bench.err; echo "rc=$?" >> $O/bench.err
+mkdir -p gpurun_out/r2s21
+O=gpurun_out/r2s21
+timeout 900 python -m pytest tests/test_anytime_gpu.py tests/test_informed_extend_gpu.py tests/test_sampler_gpu.py -x -q -m gpu > $O/pytest.log 2>&1; echo "pytest rc=$?" >> $O/pytest.log
+timeout 600 python tools/c5_probe.py 256 500 > $O/c5_probe.json 2> $O/c5_probe.err
+timeout 600 python tools/c5_probe.py 1024 2000 >> $O/c5_probe.json 2>> $O/c5_probe.err
