@@ -142,6 +142,7 @@ PROTOTYPES = {
     "gc_anytime_step": (C.c_int, [C.c_void_p]),
     "gc_anytime_run": (C.c_int, [C.c_void_p, C.c_uint64]),
     "gc_anytime_stats": (C.c_int, [C.c_void_p, _c_u64_p]),
+    "gc_anytime_timing": (C.c_int, [C.c_void_p, _c_double_p]),
     "gc_anytime_info": (C.c_int, [C.c_void_p, C.c_uint32, _c_i32_p, _c_i32_p, _c_double_p, _c_double_p, _c_double_p,
                                   _c_u64_p, _c_u32_p, _c_u32_p]),
     "gc_anytime_read_solved": (C.c_int, [C.c_void_p, _c_u8_p, _c_double_p]),

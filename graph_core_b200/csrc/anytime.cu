@@ -24,6 +24,7 @@
 // mirror from which solution costs are summed in the reference's order.  Per step: one H2D of the row lists, one D2H
 // of the row results, a handful of launches over all problems.
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <limits>
 #include <string>
@@ -108,6 +109,7 @@ struct gc_anytime
   PinBuf h_in, h_out;
   std::vector<AnyProb> pr;
   uint32_t active = 0;
+  double t_phase[8] = {};  // host wall clock: control | RRT rows | improve rows | wait | decisions | appends | goals
   uint64_t stats[8] = {};  // steps, samples, RRT rows, improve rows, nodes appended, goal edges, improve edges, solved
   // per-step scratch (host)
   std::vector<uint32_t> rowsS, rowsR, rowsI, app_seg, app_gslot, goal_row;
@@ -294,6 +296,11 @@ static int any_step(gc_anytime* a)
   const int D = a->D;
   const uint32_t P = a->P;
   cudaStream_t st = s->stream;
+  auto now = [] { return std::chrono::steady_clock::now(); };
+  auto secs = [](std::chrono::steady_clock::time_point a0, std::chrono::steady_clock::time_point a1) {
+    return std::chrono::duration<double>(a1 - a0).count();
+  };
+  auto t0 = now();
   // ---- control: bring every live problem to its next sample
   std::vector<uint32_t> truncate;
   a->rowsS.clear();
@@ -385,6 +392,8 @@ static int any_step(gc_anytime* a)
   const size_t o_node = o_closest + sizeof(uint32_t) * nR, o_okR = o_node + sizeof(uint32_t) * nI, o_okI = o_okR + nR;
   GC_TRY(a->h_out.reserve(o_okI + nI + 16));
   char* hout = static_cast<char*>(a->h_out.p);
+  auto t1 = now();
+  a->t_phase[0] += secs(t0, t1);
   if (nR)
   {
     double *d_q, *d_c1, *d_c2, *d_dist;
@@ -413,6 +422,8 @@ static int any_step(gc_anytime* a)
     GC_CUDA(cudaMemcpyAsync(hout + o_closest, d_closest, sizeof(uint32_t) * nR, cudaMemcpyDeviceToHost, st));
     GC_CUDA(cudaMemcpyAsync(hout + o_okR, d_ok, nR, cudaMemcpyDeviceToHost, st));
   }
+  auto t2 = now();
+  a->t_phase[1] += secs(t1, t2);
   if (nI)
   {
     double *d_q, *d_g;
@@ -433,7 +444,11 @@ static int any_step(gc_anytime* a)
     GC_CUDA(cudaMemcpyAsync(hout + o_node, o.d_node, sizeof(uint32_t) * nI, cudaMemcpyDeviceToHost, st));
     GC_CUDA(cudaMemcpyAsync(hout + o_okI, o.d_ok, nI, cudaMemcpyDeviceToHost, st));
   }
+  auto t3 = now();
+  a->t_phase[2] += secs(t2, t3);
   GC_CUDA(cudaStreamSynchronize(st));
+  auto t4 = now();
+  a->t_phase[3] += secs(t3, t4);
   // ---- host: the decisions of RRT::update / improveUpdate on the row results
   const double* h_q = reinterpret_cast<const double*>(hout + o_q);
   const double* h_next = reinterpret_cast<const double*>(hout + o_next);
@@ -579,6 +594,8 @@ static int any_step(gc_anytime* a)
       }
     }
   }
+  auto t5 = now();
+  a->t_phase[4] += secs(t4, t5);
   // ---- appends: node store + parent / cost arrays
   const uint32_t nA = (uint32_t)a->app_seg.size();
   if (nA)
@@ -605,6 +622,8 @@ static int any_step(gc_anytime* a)
     count_launch();
     a->stats[4] += nA;
   }
+  auto t6 = now();
+  a->t_phase[5] += secs(t5, t6);
   // ---- goal connections
   const uint32_t nG = (uint32_t)a->goal_row.size();
   if (nG)
@@ -656,6 +675,7 @@ static int any_step(gc_anytime* a)
       }
     }
   }
+  a->t_phase[6] += secs(t6, now());
   return GC_OK;
 }
 }  // namespace gc
@@ -833,6 +853,14 @@ int gc_anytime_stats(gc_anytime_t* a, uint64_t out[8])
   GC_REQUIRE(a && out, "gc_anytime_stats: NULL argument");
   for (int i = 0; i < 8; i++)
     out[i] = a->stats[i];
+  return GC_OK;
+}
+
+int gc_anytime_timing(gc_anytime_t* a, double out[8])
+{
+  GC_REQUIRE(a && out, "gc_anytime_timing: NULL argument");
+  for (int i = 0; i < 8; i++)
+    out[i] = a->t_phase[i];
   return GC_OK;
 }
 

@@ -1484,6 +1484,8 @@ int check_edges_dev(gc_world* w, const double* d_c1, const double* d_c2, const d
     return GC_OK;
   GC_REQUIRE(min_distance > 0.0, "min_distance must be > 0 (got %g)", min_distance);
   GC_REQUIRE(mode >= 0 && mode <= 2, "unknown edge mode %d", mode);
+  if (states_hint == 0)
+    states_hint = 16ull * n;  // no estimate from the caller: never size the grid for an empty batch
   GC_TRY(time_begin(w, st));
   if (w->kind != GC_WORLD_SPHERE_ARM)
   {

@@ -9,7 +9,7 @@
 //      (1 - bias) * cost-to-come; kept only when cost-to-come + distance + |goal - next| < cost2beat;
 //   3. the kept candidates in (heuristic, rank of step 1) order -- the order of the reference's two multimaps;
 //   4. the first candidate whose distance is below TOLERANCE or whose edge node -> next is collision free wins.
-// Step 4 is sequential with an early exit in the reference; here the edges are checked in rounds of 4, 16, 64, ...
+// Step 4 is sequential with an early exit in the reference; here the edges are checked in rounds of 4, 32, 256, ...
 // candidates per still-undecided query (one gc_check_edges launch per round over all queries), and the first free one in
 // order is taken, so the decision is the reference's while almost every query is settled by the first round.
 #include <math_constants.h>
@@ -105,6 +105,97 @@ __global__ void __launch_bounds__(512) ie_rank_kernel(IeArgs a)
     s_adm = 0;
   }
   __syncthreads();
+  if (a.k[qi] >= (unsigned long long)n_s)
+  {
+    // Every live node is a candidate (k >= N: always so in seven dimensions, tree.cpp:761-765).  The reference orders
+    // the kept candidates by (heuristic, position in (distance, slot) order); with all nodes taking part that is the
+    // order of (heuristic, distance, slot), so the distance sort is not needed: evaluate every node, compact the kept
+    // ones and sort those alone.  Positions are the slots themselves (cand_d / cand_slot indexed by slot).
+    double* dd = reinterpret_cast<double*>(val + a.P2);  // distance by slot, for ties of the heuristic
+    double* cd = a.cand_d + (size_t)qi * a.P2;
+    uint32_t* cs = a.cand_slot + (size_t)qi * a.P2;
+    const double bias = a.bias[qi], c2b = a.cost2beat[qi];
+    for (uint32_t i = threadIdx.x; i < n_s; i += blockDim.x)
+    {
+      double d = CUDART_INF;
+      if (a.x32[base + i] < CUDART_INF_F)
+      {
+        double node[D], nx[D];
+#pragma unroll
+        for (int c = 0; c < D; c++)
+          node[c] = a.x64[(base + i) * D + c];
+        d = norm_diff<D>(node, qs);
+        ie_next_conf<D>(node, qs, d, a.max_distance, nx);
+        double c2n = 0.0;  // Tree::costToNode
+        for (int32_t x = (int32_t)i; x != 0;)
+        {
+          const int32_t par = a.parent[base + x];
+          if (par < 0)
+          {
+            c2n = CUDART_INF;
+            break;
+          }
+          c2n = __dadd_rn(c2n, a.pcost[base + x]);
+          x = par;
+        }
+        const double heur = __dadd_rn(__dmul_rn(bias, d), __dmul_rn(__dsub_rn(1.0, bias), c2n));
+        if (__dadd_rn(__dadd_rn(c2n, d), norm_diff<D>(gs, nx)) < c2b)
+        {
+          const uint32_t pos = atomicAdd(&s_adm, 1u);
+          key[pos] = heur;
+          val[pos] = i;
+        }
+      }
+      dd[i] = d;
+      cd[i] = d;
+      cs[i] = i;
+    }
+    __syncthreads();
+    const uint32_t na = s_adm;
+    uint32_t q2 = 2;
+    while (q2 < na)
+      q2 <<= 1;
+    for (uint32_t i = na + threadIdx.x; i < q2; i += blockDim.x)
+    {
+      key[i] = CUDART_INF;
+      val[i] = GC_NO_NODE;
+    }
+    __syncthreads();
+    if (na > 1)
+      for (uint32_t k = 2; k <= q2; k <<= 1)
+        for (uint32_t j = k >> 1; j > 0; j >>= 1)
+        {
+          for (uint32_t i = threadIdx.x; i < q2; i += blockDim.x)
+          {
+            const uint32_t ixj = i ^ j;
+            if (ixj > i)
+            {
+              const double ka = key[i], kb = key[ixj];
+              const uint32_t va = val[i], vb = val[ixj];
+              bool gt = ka > kb;
+              if (ka == kb)
+              {
+                const double da = (va < n_s) ? dd[va] : CUDART_INF, db = (vb < n_s) ? dd[vb] : CUDART_INF;
+                gt = (da > db) || (da == db && va > vb);
+              }
+              if (gt == ((i & k) == 0))
+              {
+                key[i] = kb;
+                key[ixj] = ka;
+                val[i] = vb;
+                val[ixj] = va;
+              }
+            }
+          }
+          __syncthreads();
+        }
+    uint32_t* od = a.order + (size_t)qi * a.P2;
+    for (uint32_t j = threadIdx.x; j < na; j += blockDim.x)
+      od[j] = val[j];
+    if (threadIdx.x == 0)
+      a.n_adm[qi] = na;
+    return;
+  }
   uint32_t p2 = 2;
   while (p2 < n_s)
     p2 <<= 1;
@@ -421,7 +512,7 @@ int informed_extend_core(gc_store* s, gc_world* w, const double* d_q, const uint
   a.max_distance = max_distance;
   a.tolerance = tolerance;
   a.P2 = P2;
-  const size_t smem = (size_t)P2 * (sizeof(double) + sizeof(uint32_t));
+  const size_t smem = (size_t)P2 * (2 * sizeof(double) + sizeof(uint32_t));  // key | val | distance by slot
   GC_REQUIRE(P2 <= 16u * 512u, "gc_informed_extend_batch: internal: per-thread heuristic buffer too small");
   GC_IE_DISPATCH(D, if (smem > 48 * 1024) GC_CUDA(cudaFuncSetAttribute(
                         ie_rank_kernel<DD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -452,6 +543,10 @@ int informed_extend_core(gc_store* s, gc_world* w, const double* d_q, const uint
   uint32_t U = n, lo = 0, width = 4;
   int cur = 0;
   uint64_t edges_total = 0;
+  // states of an edge of length max_distance (grid sizing of the check kernels only)
+  uint64_t per_edge = 2;
+  for (double nn = 2; max_distance > nn * min_distance && per_edge < (1u << 20); nn *= 2)
+    per_edge += (uint64_t)(nn / 2);
   while (U > 0)
   {
     const size_t ne = (size_t)U * width;
@@ -489,7 +584,8 @@ int informed_extend_core(gc_store* s, gc_world* w, const double* d_q, const uint
     if (hctr[0] > 0)
     {
       gc_world_set_stream(w, st);
-      GC_TRY(check_edges_dev(w, r.c1, r.c2, nullptr, hctr[0], min_distance, GC_EDGE_BISECT, d_oke, nullptr, 0, st));
+      GC_TRY(check_edges_dev(w, r.c1, r.c2, nullptr, hctr[0], min_distance, GC_EDGE_BISECT, d_oke, nullptr,
+                             per_edge * hctr[0], st));
       edges_total += hctr[0];
     }
     GC_IE_DISPATCH(D, (ie_pick_kernel<DD><<<(U + 127) / 128, 128, 0, st>>>(r)));
@@ -502,7 +598,7 @@ int informed_extend_core(gc_store* s, gc_world* w, const double* d_q, const uint
     U = hctr[1];
     cur ^= 1;
     lo += width;
-    width = std::min<uint32_t>(width * 4u, 4096u);
+    width = std::min<uint32_t>(width * 8u, 4096u);  // 4, 32, 256, 2048, 4096: the late rounds hold few queries
   }
   out->d_ok = d_ok;
   out->d_node = d_node;

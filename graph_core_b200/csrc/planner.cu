@@ -152,11 +152,14 @@ struct InformedArgs
   // f1 / f2 / out -- and draws from Philox counter ctr[i] instead of first + i
   const uint32_t* prob;
   const unsigned long long* ctr;
+  uint32_t lanes_per_sample;  // 0 / 1: one thread per sample; 32: a warp per sample, its lanes share the rejection rounds
 };
 
 __global__ void sample_informed_kernel(InformedArgs a)
 {
-  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t lps = a.lanes_per_sample ? a.lanes_per_sample : 1u;  // 1 or 32
+  const uint32_t gid = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t i = gid / lps, sub = gid % lps;
   if (i >= a.n)
     return;
   const int D = a.dim;
@@ -253,37 +256,51 @@ __global__ void sample_informed_kernel(InformedArgs a)
   const double rmax = __dmul_rn(0.5, cost);
   for (int d = 0; d < D; d++)
     axis[d] = (d == 0) ? rmax : rmin;
-  for (uint32_t t = 0; t < 100u; t++)
+  // rejection rounds: with lps == 32 the 32 lanes that share a sample try 32 consecutive rounds at once and the
+  // first accepted round in order wins -- the same draws and arithmetic per round as the one-thread form
+  for (uint32_t tb = 0; tb < 100u; tb += lps)
   {
-    const uint32_t j0 = t * (uint32_t)(D + 1);
-    double ball[GC_MAX_DIM];
-    double b2 = 0.0;
-    for (int d = 0; d < D; d++)
-    {
-      ball[d] = __dsub_rn(__dmul_rn(2.0, draw(j0 + (uint32_t)d)), 1.0);
-      b2 = __dadd_rn(b2, __dmul_rn(ball[d], ball[d]));
-    }
-    const double scale = __ddiv_rn(informed_root(draw(j0 + (uint32_t)D), D), __dsqrt_rn(b2));
-    bool inside = true;
+    const uint32_t t = tb + sub;
+    bool inside = false;
     double q[GC_MAX_DIM];
-    for (int r0 = 0; r0 < D; r0++)
+    if (t < 100u)
     {
-      double acc = 0.0;
-      for (int c0 = 0; c0 < D; c0++)
-        acc = __dadd_rn(acc, __dmul_rn(__dmul_rn(R[r0][c0], axis[c0]), __dmul_rn(ball[c0], scale)));
-      q[r0] = __dadd_rn(acc, centre[r0]);
-      if (q[r0] > a.ub[r0] || q[r0] < a.lb[r0])
-        inside = false;
-    }
-    if (inside)
-    {
+      const uint32_t j0 = t * (uint32_t)(D + 1);
+      double ball[GC_MAX_DIM];
+      double b2 = 0.0;
       for (int d = 0; d < D; d++)
-        a.out[row * D + d] = q[d];
-      if (a.attempts)
-        a.attempts[i] = t + 1u;
+      {
+        ball[d] = __dsub_rn(__dmul_rn(2.0, draw(j0 + (uint32_t)d)), 1.0);
+        b2 = __dadd_rn(b2, __dmul_rn(ball[d], ball[d]));
+      }
+      const double scale = __ddiv_rn(informed_root(draw(j0 + (uint32_t)D), D), __dsqrt_rn(b2));
+      inside = true;
+      for (int r0 = 0; r0 < D; r0++)
+      {
+        double acc = 0.0;
+        for (int c0 = 0; c0 < D; c0++)
+          acc = __dadd_rn(acc, __dmul_rn(__dmul_rn(R[r0][c0], axis[c0]), __dmul_rn(ball[c0], scale)));
+        q[r0] = __dadd_rn(acc, centre[r0]);
+        if (q[r0] > a.ub[r0] || q[r0] < a.lb[r0])
+          inside = false;
+      }
+    }
+    const uint32_t mask = (lps == 32u) ? __ballot_sync(0xffffffffu, inside) : (inside ? 1u : 0u);
+    if (mask)
+    {
+      const uint32_t winner = (uint32_t)__ffs((int)mask) - 1u;
+      if (sub == winner)
+      {
+        for (int d = 0; d < D; d++)
+          a.out[row * D + d] = q[d];
+        if (a.attempts)
+          a.attempts[i] = tb + winner + 1u;
+      }
       return;
     }
   }
+  if (sub != 0u)
+    return;
   uniform(100u * (uint32_t)(D + 1));
   if (a.attempts)
     a.attempts[i] = 101u;
@@ -339,7 +356,9 @@ int sample_informed_rows_launch(int dim, uint32_t n, const double* d_lb, const d
   a.attempts = nullptr;
   a.prob = d_prob;
   a.ctr = d_ctr;
-  sample_informed_kernel<<<(n + 127) / 128, 128, 0, st>>>(a);
+  // few samples per call and up to 100 rejection rounds each: the max over the batch sets the kernel time
+  a.lanes_per_sample = 32;
+  sample_informed_kernel<<<(n + 3) / 4, 128, 0, st>>>(a);
   GC_CUDA(cudaGetLastError());
   count_launch();
   return GC_OK;

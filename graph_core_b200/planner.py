@@ -362,6 +362,12 @@ class LockstepAnytimeRRT:
         capi._check(self.L.gc_anytime_stats(self.h, out))
         return dict(zip(self.STATS, (int(v) for v in out)))
 
+    def timing(self):
+        out = (C.c_double * 8)()
+        capi._check(self.L.gc_anytime_timing(self.h, out))
+        keys = ("control", "rrt_rows", "improve_rows", "wait", "decisions", "appends", "goal_edges")
+        return dict(zip(keys, (float(v) for v in out)))
+
     def info(self, p: int):
         solved, done = C.c_int32(0), C.c_int32(0)
         cost, bias, c2b = C.c_double(0), C.c_double(0), C.c_double(0)

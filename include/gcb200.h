@@ -348,6 +348,10 @@ int gc_anytime_run(gc_anytime_t* a, uint64_t max_steps);
 /* out: steps, samples drawn, RRT rows, improve rows, nodes appended, goal edges checked, edges checked inside
  * informedExtend, first solutions found */
 int gc_anytime_stats(gc_anytime_t* a, uint64_t out[8]);
+/* host wall-clock seconds spent per part of gc_anytime_step since creation: control flow, enqueueing the RRT rows,
+ * Tree::informedExtend for the improve rows (includes its round synchronisations), waiting for the device, the
+ * decisions on the row results, appends, goal connections */
+int gc_anytime_timing(gc_anytime_t* a, double out[8]);
 int gc_anytime_info(gc_anytime_t* a, uint32_t p, int32_t* solved, int32_t* done, double* cost, double* bias,
                     double* cost2beat, uint64_t* samples, uint32_t* tree_nodes, uint32_t* log_rows);
 int gc_anytime_read_solved(gc_anytime_t* a, uint8_t* solved, double* cost);

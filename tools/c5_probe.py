@@ -17,10 +17,11 @@ starts, goals, cost0 = W.c5_problems(arm, sc.params, P)
 t1 = time.time()
 lk = LockstepAnytimeRRT(sc, sc.make_world(), starts, goals, max_iter=max_iter, seed=501, sampler_cost0=cost0, capacity=8192)
 t2 = time.time()
-live = lk.run()
+max_steps = int(sys.argv[3]) if len(sys.argv) > 3 else 0
+live = lk.run(max_steps)
 t3 = time.time()
 solved, cost = lk.solved()
 st = lk.stats()
 print(json.dumps({"P": P, "max_iter": max_iter, "gen_s": t1 - t0, "create_s": t2 - t1, "run_s": t3 - t2, "live": live,
                   "queries_per_s": P / (t3 - t2), "solved": int(solved.sum()), "mean_cost": float(cost[solved].mean()) if solved.any() else None,
-                  "stats": st, "us_per_step": 1e6 * (t3 - t2) / max(st["steps"], 1)}))
+                  "stats": st, "timing": lk.timing(), "us_per_step": 1e6 * (t3 - t2) / max(st["steps"], 1)}))
