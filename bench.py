@@ -365,6 +365,106 @@ def knn_c4(g, torch, dist_mod, rank, world, dev, hbm_peak, fp32_peak, n_nodes=1 
     return res
 
 
+def c5_leg(g, torch, dist_mod, rank, world, dev, sc, root_world, ncores, total=4096, max_iter=2000, seed=501):
+    """BASELINE config 5: `total` independent AnytimeRRT queries in the C3 world, query j on GPU j mod G (no data-path
+    collective; a query's sample stream depends on j only, so the results do not depend on G).  The queries are C5'
+    (graph_core_b200/worlds.py c5_problems: goal 1.5 rad from the start, informed first phase) because with BASELINE's
+    literal C5 the reference finds no first solution and its improve rounds never start.  Timed region: creation
+    (TreeSolver::setProblem rays) + AnytimeRRT::solve with the improve loop for every query of this rank; whole-job
+    queries/s = total / max over ranks.  Rank 0 replays a few queries through the oracle (bit-identical round logs) and
+    times the reference's own AnytimeRRT (oracle/_ref) on the host cores beside it."""
+    from graph_core_b200 import worlds as W
+    from graph_core_b200.planner import LockstepAnytimeRRT
+    starts, goals, cost0 = W.c5_problems(cuda_checker(dev), sc.params, total, seed=seed)
+    mine = np.arange(rank, total, world)
+    if world > 1:
+        dist_mod.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    lk = LockstepAnytimeRRT(sc, root_world, starts[mine], goals[mine], max_iter=max_iter, seed=seed,
+                            sampler_cost0=cost0[mine], capacity=8192)
+    lk.set_streams(total, mine)
+    live = lk.run()
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    if world > 1:
+        tt = torch.tensor([dt], dtype=torch.float64, device="cuda")
+        dist_mod.all_reduce(tt, op=dist_mod.ReduceOp.MAX)
+        dt_all = float(tt.item())
+    else:
+        dt_all = dt
+    solved, cost = lk.solved()
+    st = lk.stats()
+    agg = torch.tensor([float(solved.sum()), float(cost[solved].sum()), float(st["samples"]), float(st["steps"]),
+                        float(st["improve_edges"] + st["goal_edges"] + st["rrt_rows"])], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist_mod.all_reduce(agg)
+    out = {"queries_per_s": total / dt_all, "unit": "queries/s", "queries": total, "queries_per_gpu": len(mine),
+           "max_iter_per_round": max_iter, "seconds": dt_all, "live_after_run": int(live),
+           "solved": int(agg[0].item()), "mean_cost": float(agg[1].item() / max(agg[0].item(), 1.0)),
+           "planner_updates": int(agg[2].item()), "lockstep_steps_rank0": st["steps"],
+           "edges_checked": int(agg[4].item()), "scaling": "strong (BASELINE: the same 4 096 queries over 1/2/4/8 GPUs)",
+           "workload": "C5': C3 world, start uniform (seed 501), goal 1.5 rad away, InformedSampler(cost 1.5 |goal - "
+                       "start|) in the first phase, delta 0.1, cost_impr 0.1, improve loop run (improve_in_solve)",
+           "host_seconds_rank0": lk.timing()}
+    if rank != 0:
+        return out
+    sys.path.insert(0, str(ROOT / "oracle"))
+    import ctypes as C
+    import threading
+    import oracle_py as orc
+    orc.build()
+    # parity: a few queries of this rank through the oracle's restatement (pinned to the reference's AnytimeRRT)
+    ok_all, checked = True, 0
+    for i in range(0, len(mine), max(1, len(mine) // 4))[:4]:
+        j = int(mine[i])
+        o = orc.OracleAnytime(sc, orc.OracleWorld.from_scenario(sc), start=starts[j], goal=goals[j],
+                              sampler_cost0=float(cost0[j]))
+        so = o.solve(max_iter, seed, j, total)
+        ok = bool(so == bool(solved[i]) and np.array_equal(o.log(), lk.log(i)))
+        if so:
+            ok = ok and bool(np.array_equal(o.solution(), lk.solution(i)[0]) and o.state()["cost"] == cost[i])
+        ok_all = ok_all and ok
+        checked += 1
+    out["parity"] = {"round_logs_paths_costs_bit_exact": ok_all, "queries_checked": checked}
+    # CPU arm: the reference's own AnytimeRRT, its state check answered by the oracle world with the grid culling
+    try:
+        import ref_py
+        L = ref_py.lib(fast=True)
+        fn = C.cast(orc.lib(fast=True).orc_sample_informed, C.c_void_p)
+        ncpu = min(total, 2 * ncores)
+        res = [None] * ncpu
+
+        def work(tid):
+            for j in range(tid, ncpu, ncores):
+                ow = orc.OracleWorld.from_scenario(sc, fast=True)
+                ow.enable_grid(True)
+                rc = ref_py.RefChecker.over_oracle_world(ow, sc.min_distance, fast=True)
+                r = ref_py.RefSolver(ref_py.RefSolver.ANYTIME, sc, rc, start=starts[j], goal=goals[j], informed=True,
+                                     fast=True)
+                res[j] = r.anytime_solve_injected(max_iter, fn, sc.lb, sc.ub, float(cost0[j]), seed, j, total,
+                                                  sc.utopia_tolerance)
+
+        ts = [threading.Thread(target=work, args=(t,)) for t in range(min(ncores, ncpu))]
+        t0 = time.perf_counter()
+        for t in ts:
+            t.start()
+        for t in ts:
+            t.join()
+        dtc = time.perf_counter() - t0
+        out["cpu_baseline_optimized"] = {
+            "value": ncpu / dtc, "unit": "queries/s", "cores": min(ncores, ncpu), "kind": "reference",
+            "sample": "the first %d queries, graph_core's own AnytimeRRT (update / improve / improveUpdate, oracle/_ref, "
+                      "Release flags) on the same sample streams, its state check answered by the oracle world WITH the "
+                      "CUDA path's grid culling (the plain per-state loop is ~20x slower), one query per thread, %.1f s"
+                      % (ncpu, dtc),
+            "solved": int(sum(1 for r in res if r and r[0])), "updates": int(sum(r[2] for r in res if r)),
+            "gpu_over_cpu": out["queries_per_s"] / (ncpu / dtc)}
+    except Exception as ex:
+        out["cpu_baseline_optimized"] = {"error": str(ex)[:300]}
+    return out
+
+
 def c2_legs(g, torch, dev, ncores, problems=16384, iters=64):
     """BASELINE config 2 (rank 0): (i) the 2^20-segment edge micro-benchmark of SURVEY 8(d) (tools/edge_bench.py) with the
     reference's checkConnection loop timed beside it on one host core; (ii) lock-step BiRRT (graph_core_b200/csrc/birrt.cu):
@@ -802,6 +902,11 @@ def main():
                                  float(peaks.get("hbm_gbs", 6650.0)), fp32_peak)
         except Exception as ex:
             line["knn"] = {"error": str(ex)[:300]}
+    if not args.skip_extras:
+        try:
+            line["c5"] = c5_leg(g, torch, dist if world_size > 1 else None, rank, world_size, dev, sc, root_world, ncores)
+        except Exception as ex:
+            line["c5"] = {"error": str(ex)[:300]}
     if rank == 0 and not args.skip_extras:
         try:
             line["informed"] = informed_arm(g, torch, LockstepRRTStar, sc, root_world, starts, goals, dev, W_ * I, K * I)

@@ -139,6 +139,7 @@ PROTOTYPES = {
     "gc_anytime_create": (C.c_int, [C.c_void_p, C.c_void_p, _c_double_p, _c_double_p, C.c_uint32, _c_double_p,
                                     _c_double_p, _c_double_p, C.POINTER(C.c_void_p)]),
     "gc_anytime_destroy": (C.c_int, [C.c_void_p]),
+    "gc_anytime_set_streams": (C.c_int, [C.c_void_p, C.c_uint64, _c_u64_p]),
     "gc_anytime_step": (C.c_int, [C.c_void_p]),
     "gc_anytime_run": (C.c_int, [C.c_void_p, C.c_uint64]),
     "gc_anytime_stats": (C.c_int, [C.c_void_p, _c_u64_p]),

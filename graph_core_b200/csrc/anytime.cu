@@ -108,6 +108,8 @@ struct gc_anytime
   DevArena arena;
   PinBuf h_in, h_out;
   std::vector<AnyProb> pr;
+  std::vector<uint64_t> stream_index;  // Philox counter of sample k of problem p: k * stream_stride + stream_index[p]
+  uint64_t stream_stride = 0;
   uint32_t active = 0;
   double t_phase[8] = {};  // host wall clock: control | RRT rows | improve rows | wait | decisions | appends | goals
   uint64_t stats[8] = {};  // steps, samples, RRT rows, improve rows, nodes appended, goal edges, improve edges, solved
@@ -361,7 +363,7 @@ static int any_step(gc_anytime* a)
     for (uint32_t i = 0; i < nS; i++)
     {
       AnyProb& p = a->pr[a->rowsS[i]];
-      ctr[i] = p.k * (uint64_t)P + a->rowsS[i];  // sample k of problem p: Philox counter k * P + p
+      ctr[i] = p.k * a->stream_stride + a->stream_index[a->rowsS[i]];  // sample k of problem p: counter k * P + p
       p.k++;
       cost[i] = (p.phase == kAnyImprove) ? p.cost2beat : a->cost0[a->rowsS[i]];
     }
@@ -784,6 +786,10 @@ int gc_anytime_create(gc_world_t* w, const gc_anytime_config_t* cfg, const doubl
     return rc;
   }
   a->pr.resize(n_problems);
+  a->stream_stride = n_problems;
+  a->stream_index.resize(n_problems);
+  for (uint32_t i = 0; i < n_problems; i++)
+    a->stream_index[i] = i;
   a->active = n_problems;
   for (uint32_t i = 0; i < n_problems; i++)
   {
@@ -828,6 +834,17 @@ int gc_anytime_create(gc_world_t* w, const gc_anytime_config_t* cfg, const doubl
   for (uint64_t& v : a->stats)
     v = 0;
   *out = a;
+  return GC_OK;
+}
+
+int gc_anytime_set_streams(gc_anytime_t* a, uint64_t stride, const uint64_t* index)
+{
+  GC_REQUIRE(a != nullptr && stride > 0, "gc_anytime_set_streams: NULL handle or zero stride");
+  for (const AnyProb& p : a->pr)
+    GC_REQUIRE(p.k == 0, "gc_anytime_set_streams: samples were already drawn");
+  a->stream_stride = stride;
+  for (uint32_t i = 0; i < a->P; i++)
+    a->stream_index[i] = index ? index[i] : i;
   return GC_OK;
 }
 

@@ -349,6 +349,13 @@ class LockstepAnytimeRRT:
             raise capi.GcError(r, self.L.gc_last_error().decode())
         return r
 
+    def set_streams(self, stride: int, index):
+        """These queries are positions `index` of a set of `stride` queries (sharding over GPUs): sample k of local
+        query i uses Philox counter k * stride + index[i]."""
+        idx = np.ascontiguousarray(index, dtype=np.uint64)
+        assert idx.shape == (self.n,)
+        capi._check(self.L.gc_anytime_set_streams(self.h, int(stride), idx.ctypes.data_as(C.POINTER(C.c_uint64))))
+
     def step(self) -> int:
         """One planner update of every live query; returns how many are still live."""
         return self._rc(self.L.gc_anytime_step(self.h))

@@ -341,6 +341,10 @@ int gc_anytime_create(gc_world_t* world, const gc_anytime_config_t* cfg, const d
                       uint32_t n_problems, const double* starts, const double* goals, const double* sampler_cost0,
                       gc_anytime_t** out);
 int gc_anytime_destroy(gc_anytime_t* a);
+/* queries that are a shard of a larger set (problem j on GPU j mod G): sample k of local problem i then uses Philox
+ * counter k * stride + index[i] (stride = size of the whole set, index[i] = its position there), so that a query's
+ * result does not depend on how the set is sharded.  Default: stride = n_problems, index[i] = i.  Before any step. */
+int gc_anytime_set_streams(gc_anytime_t* a, uint64_t stride, const uint64_t* index);
 /* one update of every live problem; returns the number of problems still live (< 0: error) */
 int gc_anytime_step(gc_anytime_t* a);
 /* steps until every query ended or max_steps were made (0 = no limit); returns the number still live */

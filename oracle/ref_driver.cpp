@@ -431,6 +431,92 @@ void ref_anytime_state(void* h, double* out)
   out[5] = a->solved() ? 1.0 : 0.0;
   out[6] = a->getNewTree() ? (double)a->getNewTree()->getNumberOfNodes() : 0.0;
 }
+// AnytimeRRT::solve (anytime_rrt.cpp:73-236) without the wall clock, samples injected: sample k of this problem comes
+// from `sampler` (the oracle's orc_sample_informed) with Philox counter k * P + p, foci start/goal, cost = cost0 during
+// the RRT phase and cost2beat during an improve round.  Every planner decision is the reference's own update() /
+// improve(max_iter = 0) / improveUpdate(); the loop around them restates solve()'s (see ref_py.anytime_solve).
+// out: rounds, updates, improved rounds.  Returns solved.
+typedef void (*informed_sampler_fn)(int dim, int n, const double* lb, const double* ub, const double* f1, const double* f2,
+                                    const double* cost, unsigned long long seed, unsigned long long first, double* out,
+                                    unsigned int* attempts);
+int ref_anytime_solve_injected(void* h, unsigned int max_iter, int improve_in_solve, informed_sampler_fn sampler,
+                               const double* lb, const double* ub, double cost0, unsigned long long seed,
+                               unsigned long long p, unsigned long long P, double utopia_tolerance, double* out)
+{
+  RefSolver* s = (RefSolver*)h;
+  AnytimeRRTPtr a = std::dynamic_pointer_cast<AnytimeRRT>(s->solver);
+  if (!a)
+    return -1;
+  const int d = s->dim;
+  std::vector<double> f1(d), f2(d), q(d);
+  for (int i = 0; i < d; i++)
+  {
+    f1[i] = s->start->getConfiguration()(i);
+    f2[i] = s->goal->getConfiguration()(i);
+  }
+  const double best_utopia = (s->goal->getConfiguration() - s->start->getConfiguration()).norm();
+  const double tol = (1.0 + (utopia_tolerance > 0.0 ? utopia_tolerance : 0.0)) * best_utopia;
+  unsigned long long k = 0, rounds = 0, updates = 0, improved_rounds = 0;
+  auto draw = [&](double cost) {
+    sampler(d, 1, lb, ub, f1.data(), f2.data(), &cost, seed, k * P + p, q.data(), nullptr);
+    k++;
+    updates++;
+    return toVec(q.data(), d);
+  };
+  auto finish = [&]() {
+    if (out)
+    {
+      out[0] = (double)rounds;
+      out[1] = (double)updates;
+      out[2] = (double)improved_rounds;
+    }
+    return a->solved() ? 1 : 0;
+  };
+  if (a->solved() && a->cost() <= tol)
+    return finish();
+  int n_failed = 0;
+  while (!a->solved() && n_failed < FAILED_ITER)
+  {
+    bool ok = false;
+    rounds++;
+    for (unsigned int it = 0; it < max_iter; it++)
+      if (s->solver->update(draw(cost0), s->solution))  // RRT::update (AnytimeRRT hides the overload by name)
+      {
+        ok = true;
+        break;
+      }
+    if (!ok)
+      n_failed++;
+  }
+  if (!a->solved() || a->cost() <= tol)
+    return finish();
+  n_failed = 0;
+  while ((improve_in_solve || a->canImprove()) && n_failed < FAILED_ITER)
+  {
+    bool improved = false;
+    rounds++;
+    if (ref_anytime_improve_begin(h) == 1)
+    {
+      const double c2b = a->getCost2Beat();
+      for (unsigned int it = 0; it < max_iter; it++)
+        if (a->improveUpdate(draw(c2b), s->solution))
+        {
+          improved = true;
+          break;
+        }
+    }
+    if (improved)
+    {
+      n_failed = 0;
+      improved_rounds++;
+    }
+    else
+      n_failed++;
+    if (a->cost() <= tol)
+      break;
+  }
+  return finish();
+}
 void ref_anytime_set_parameters(void* h, double delta, double cost_impr)
 {
   AnytimeRRTPtr a = std::dynamic_pointer_cast<AnytimeRRT>(((RefSolver*)h)->solver);

@@ -87,6 +87,8 @@ def lib(fast: bool = False, dropin: bool = False):
         "ref_solution_is_valid_from": (C.c_int, [vp, vp, C.c_int, C.c_double]),
         "ref_solution_optimize": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, _dp, _dp]),
         "ref_tree_recheck": (C.c_int, [vp]),
+        "ref_anytime_solve_injected": (C.c_int, [vp, C.c_uint, C.c_int, vp, _dp, _dp, C.c_double, C.c_ulonglong,
+                                               C.c_ulonglong, C.c_ulonglong, C.c_double, _dp]),
         "ref_anytime_improve_begin": (C.c_int, [vp]),
         "ref_anytime_improve_update": (C.c_int, [vp, _dp]),
         "ref_anytime_state": (None, [vp, _dp]),
@@ -348,6 +350,18 @@ class RefSolver:
         self.L.ref_anytime_state(self.h, _p(out, _dp))
         keys = ["bias", "cost2beat", "path_cost", "cost", "can_improve", "solved", "round_tree_nodes"]
         return dict(zip(keys, out.tolist()))
+
+    def anytime_solve_injected(self, max_iter, sampler_fn_ptr, lb, ub, cost0, seed, p, P, utopia_tolerance,
+                               improve_in_solve=True):
+        """AnytimeRRT::solve in one C++ call (no Python in the loop): samples from the C function sampler_fn_ptr
+        (orc_sample_informed of the oracle library) with Philox counter k * P + p.  Returns (solved, rounds, updates,
+        improved rounds)."""
+        lb, ub = _f64(lb), _f64(ub)
+        out = np.zeros(4)
+        r = self.L.ref_anytime_solve_injected(self.h, max_iter, 1 if improve_in_solve else 0, sampler_fn_ptr, _p(lb, _dp),
+                                              _p(ub, _dp), float(cost0), seed, p, P, utopia_tolerance, _p(out, _dp))
+        assert r >= 0, "not an AnytimeRRT"
+        return bool(r), int(out[0]), int(out[1]), int(out[2])
 
     def set_anytime_parameters(self, delta=0.1, cost_impr=0.1):
         self.L.ref_anytime_set_parameters(self.h, delta, cost_impr)

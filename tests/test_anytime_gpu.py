@@ -154,3 +154,24 @@ def test_lockstep_anytime_step_by_step_equals_run(gc, orc):
     for p in range(3):
         assert np.array_equal(full.log(p), again.log(p))
         assert full.info(p) == again.info(p)
+
+
+def test_lockstep_anytime_results_do_not_depend_on_sharding(gc, orc):
+    """BASELINE config 5 shards the queries over the GPUs (query j on GPU j mod G): with gc_anytime_set_streams a query
+    draws the same samples in a shard as in the full set, so every shard reproduces the full run."""
+    from graph_core_b200.planner import LockstepAnytimeRRT
+    sc = W.scenario_c1()
+    P = 6
+    starts, goals = _free_pairs(sc, orc, P, 4600)
+    full = LockstepAnytimeRRT(sc, sc.make_world(), starts, goals, max_iter=250, seed=91, capacity=4096)
+    assert full.run() == 0
+    for shard in (np.arange(0, P, 2), np.arange(1, P, 2)):
+        part = LockstepAnytimeRRT(sc, sc.make_world(), starts[shard], goals[shard], max_iter=250, seed=91, capacity=4096)
+        part.set_streams(P, shard)
+        assert part.run() == 0
+        for i, j in enumerate(shard):
+            assert np.array_equal(part.log(i), full.log(int(j)))
+            a, b = part.info(i), full.info(int(j))
+            assert a == b
+            if a["solved"]:
+                assert np.array_equal(part.solution(i)[0], full.solution(int(j))[0])
