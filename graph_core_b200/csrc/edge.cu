@@ -1016,6 +1016,55 @@ __global__ void __launch_bounds__(G == 1 ? 128 : 256, G == 1 ? (NRS <= 16 ? 4 : 
 #define GC_GRID_FK_UNROLL 1
 #endif
 constexpr int kGridFkUnroll = GC_GRID_FK_UNROLL;  // 1: the joint loop stays a loop (instruction cache), 8: unrolled
+// cell of the uniform grid a sphere centre falls in; inside = false (index 0) outside the grid or for a NaN centre: no
+// obstacle is within reach of such a sphere.  Cell record (arm_grid_records): up to three obstacle indices inline, so
+// that most look-ups cost ONE gather before the shared-memory obstacle records instead of start/end plus the item list
+__device__ __forceinline__ uint32_t grid_cell_index(const ArmArgs& a, const float* o, bool& inside)
+{
+  const float fx = __fmul_rn(__fsub_rn(o[0], a.glo[0]), a.ginv);
+  const float fy = __fmul_rn(__fsub_rn(o[1], a.glo[1]), a.ginv);
+  const float fz = __fmul_rn(__fsub_rn(o[2], a.glo[2]), a.ginv);
+  inside = fx >= 0.0f && fy >= 0.0f && fz >= 0.0f && fx < (float)a.gn[0] && fy < (float)a.gn[1] && fz < (float)a.gn[2];
+  const uint32_t cell = ((uint32_t)fx * (uint32_t)a.gn[1] + (uint32_t)fy) * (uint32_t)a.gn[2] + (uint32_t)fz;
+  return inside ? cell : 0u;
+}
+
+// pair tests of one robot sphere (centre o, radius rs) against the obstacle list of its cell record
+__device__ __forceinline__ bool grid_cell_pairs(const ArmSmem& w, const ArmArgs& a, const uint2 rec, const float* o,
+                                                float rs, uint32_t& done)
+{
+  const uint32_t cn = rec.x & 0xffffu;
+  if (cn == 0u)
+    return false;
+  bool hit = false;
+  const SphereK sk = sphere_consts(o[0], o[1], o[2], rs);
+  if (cn <= 3u)
+  {
+    const uint32_t i0 = rec.x >> 16;
+    hit |= pair_hit(w.obs[i0], w.obs_na[i0], sk);
+    if (cn > 1u)
+    {
+      const uint32_t i1 = rec.y & 0xffffu;
+      hit |= pair_hit(w.obs[i1], w.obs_na[i1], sk);
+    }
+    if (cn > 2u)
+    {
+      const uint32_t i2 = rec.y >> 16;
+      hit |= pair_hit(w.obs[i2], w.obs_na[i2], sk);
+    }
+  }
+  else
+  {
+    for (uint32_t i = rec.y; i < rec.y + cn; i++)
+    {
+      const uint32_t idx = __ldg(a.gitems + i);
+      hit |= pair_hit(w.obs[idx], w.obs_na[idx], sk);
+    }
+  }
+  done += cn;
+  return hit;
+}
+
 template <int J>
 __device__ __forceinline__ bool arm_check_grid(const ArmSmem& w, const ArmArgs& a, const float* qf,
                                                unsigned long long& pairs)
@@ -1043,50 +1092,30 @@ __device__ __forceinline__ bool arm_check_grid(const ArmSmem& w, const ArmArgs& 
         BR[i] = AR[i];
     }
     const int k1 = lfirst[j + 1];
+    // two spheres per trip: both cell records are requested before either list is walked, so the two gathers (L1 / L2
+    // latency, the main stall of this kernel) overlap
 #pragma unroll 1
-    for (int k = lfirst[j]; k < k1; k++)
+    for (int k = lfirst[j]; k < k1; k += 2)
     {
-      const float4 loc = loc4[k];
-      float o[3];
-      mat3_vec(BR, At, loc.x, loc.y, loc.z, o);
-      const float fx = __fmul_rn(__fsub_rn(o[0], a.glo[0]), a.ginv);
-      const float fy = __fmul_rn(__fsub_rn(o[1], a.glo[1]), a.ginv);
-      const float fz = __fmul_rn(__fsub_rn(o[2], a.glo[2]), a.ginv);
-      // outside the grid (or NaN): no obstacle within reach of this sphere
-      if (!(fx >= 0.0f && fy >= 0.0f && fz >= 0.0f && fx < (float)a.gn[0] && fy < (float)a.gn[1] && fz < (float)a.gn[2]))
-        continue;
-      const uint32_t cell = ((uint32_t)fx * (uint32_t)a.gn[1] + (uint32_t)fy) * (uint32_t)a.gn[2] + (uint32_t)fz;
-      // cell record (arm_grid_records): up to three obstacle indices inline, so that most look-ups cost ONE gather
-      // before the shared-memory obstacle records instead of start/end plus the item list
-      const uint2 rec = __ldg(reinterpret_cast<const uint2*>(a.gstart) + cell);
-      const uint32_t cn = rec.x & 0xffffu;
-      if (cn == 0u)
-        continue;
-      const SphereK sk = sphere_consts(o[0], o[1], o[2], loc.w);
-      if (cn <= 3u)
-      {
-        const uint32_t i0 = rec.x >> 16;
-        hit |= pair_hit(w.obs[i0], w.obs_na[i0], sk);
-        if (cn > 1u)
-        {
-          const uint32_t i1 = rec.y & 0xffffu;
-          hit |= pair_hit(w.obs[i1], w.obs_na[i1], sk);
-        }
-        if (cn > 2u)
-        {
-          const uint32_t i2 = rec.y >> 16;
-          hit |= pair_hit(w.obs[i2], w.obs_na[i2], sk);
-        }
-      }
-      else
-      {
-        for (uint32_t i = rec.y; i < rec.y + cn; i++)
-        {
-          const uint32_t idx = __ldg(a.gitems + i);
-          hit |= pair_hit(w.obs[idx], w.obs_na[idx], sk);
-        }
-      }
-      done += cn;
+      const bool two = (k + 1 < k1);
+      const float4 locA = loc4[k];
+      const float4 locB = loc4[two ? k + 1 : k];
+      float oA[3], oB[3];
+      mat3_vec(BR, At, locA.x, locA.y, locA.z, oA);
+      mat3_vec(BR, At, locB.x, locB.y, locB.z, oB);
+      // branch-free cell look-up (a sphere outside the grid, or a NaN centre, reads cell 0 and drops the record): the two
+      // loads sit in straight-line code and are issued back to back
+      bool inA, inB;
+      const uint32_t cellA = grid_cell_index(a, oA, inA);
+      const uint32_t cellB = grid_cell_index(a, oB, inB);
+      uint2 recA = __ldg(reinterpret_cast<const uint2*>(a.gstart) + cellA);
+      uint2 recB = __ldg(reinterpret_cast<const uint2*>(a.gstart) + cellB);
+      if (!inA)
+        recA = make_uint2(0u, 0u);
+      if (!(inB && two))
+        recB = make_uint2(0u, 0u);
+      hit |= grid_cell_pairs(w, a, recA, oA, locA.w, done);
+      hit |= grid_cell_pairs(w, a, recB, oB, locB.w, done);
     }
     if (j < J)
       fk_advance(AR, At, BR, w.joint + 12 * j);
