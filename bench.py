@@ -57,7 +57,7 @@ def parse_args():
     ap.add_argument("--iters-per-step", type=int, default=50,
                     help="lock-step RRT* iterations per step (one step = this many samples per problem)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--problems", type=int, default=8192, help="independent planning problems per GPU")
+    ap.add_argument("--problems", type=int, default=32768, help="independent planning problems per GPU")
     ap.add_argument("--threads", type=int, default=0, help="host replay threads (0 = all cores)")
     ap.add_argument("--instances", type=int, default=1,
                     help="lock-step planner instances per GPU, each with problems/instances problems, its own stream and "
@@ -365,7 +365,8 @@ def knn_c4(g, torch, dist_mod, rank, world, dev, hbm_peak, fp32_peak, n_nodes=1 
     return res
 
 
-def c5_leg(g, torch, dist_mod, rank, world, dev, sc, root_world, ncores, total=4096, max_iter=2000, seed=501):
+def c5_leg(g, torch, dist_mod, rank, world, dev, sc, root_world, ncores, total=4096, max_iter=2000, seed=501,
+           instances=4):
     """BASELINE config 5: `total` independent AnytimeRRT queries in the C3 world, query j on GPU j mod G (no data-path
     collective; a query's sample stream depends on j only, so the results do not depend on G).  The queries are C5'
     (graph_core_b200/worlds.py c5_problems: goal 1.5 rad from the start, informed first phase) because with BASELINE's
@@ -377,24 +378,57 @@ def c5_leg(g, torch, dist_mod, rank, world, dev, sc, root_world, ncores, total=4
     from graph_core_b200.planner import LockstepAnytimeRRT
     starts, goals, cost0 = W.c5_problems(cuda_checker(dev), sc.params, total, seed=seed)
     mine = np.arange(rank, total, world)
+    import threading
+    # `instances` lock-step planners per GPU, each with its own stream and host thread: a step is a chain of short
+    # launches and read-backs, so the instances overlap one another's latencies (results do not depend on the split)
+    parts = [mine[i::instances] for i in range(instances)]
+    lks = [None] * instances
+    errs = []
+    create_lock = threading.Lock()  # gc_world_clone of one parent handle is not meant to run concurrently
+
+    def work(i):
+        try:
+            with create_lock:
+                lk_i = LockstepAnytimeRRT(sc, root_world, starts[parts[i]], goals[parts[i]], max_iter=max_iter,
+                                          seed=seed, sampler_cost0=cost0[parts[i]], capacity=8192)
+            lk_i.set_streams(total, parts[i])
+            lks[i] = lk_i
+            lk_i.run()
+        except Exception as ex:  # noqa: BLE001
+            errs.append(str(ex))
+
     if world > 1:
         dist_mod.barrier()
     torch.cuda.synchronize()
     t0 = time.perf_counter()
-    lk = LockstepAnytimeRRT(sc, root_world, starts[mine], goals[mine], max_iter=max_iter, seed=seed,
-                            sampler_cost0=cost0[mine], capacity=8192)
-    lk.set_streams(total, mine)
-    live = lk.run()
+    ts = [threading.Thread(target=work, args=(i,)) for i in range(instances)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
+    if errs:
+        raise RuntimeError(errs[0])
     if world > 1:
         tt = torch.tensor([dt], dtype=torch.float64, device="cuda")
         dist_mod.all_reduce(tt, op=dist_mod.ReduceOp.MAX)
         dt_all = float(tt.item())
     else:
         dt_all = dt
-    solved, cost = lk.solved()
-    st = lk.stats()
+    solved = np.zeros(len(mine), bool)
+    cost = np.zeros(len(mine))
+    st = {k: 0 for k in LockstepAnytimeRRT.STATS}
+    local_of = {}
+    for i, lk_i in enumerate(lks):
+        s_i, c_i = lk_i.solved()
+        solved[i::instances] = s_i
+        cost[i::instances] = c_i
+        for k, v in lk_i.stats().items():
+            st[k] = max(st[k], v) if k == "steps" else st[k] + v
+        for j in range(len(parts[i])):
+            local_of[i + j * instances] = (lk_i, j)
+    live = 0
     agg = torch.tensor([float(solved.sum()), float(cost[solved].sum()), float(st["samples"]), float(st["steps"]),
                         float(st["improve_edges"] + st["goal_edges"] + st["rrt_rows"])], dtype=torch.float64, device="cuda")
     if world > 1:
@@ -406,7 +440,7 @@ def c5_leg(g, torch, dist_mod, rank, world, dev, sc, root_world, ncores, total=4
            "edges_checked": int(agg[4].item()), "scaling": "strong (BASELINE: the same 4 096 queries over 1/2/4/8 GPUs)",
            "workload": "C5': C3 world, start uniform (seed 501), goal 1.5 rad away, InformedSampler(cost 1.5 |goal - "
                        "start|) in the first phase, delta 0.1, cost_impr 0.1, improve loop run (improve_in_solve)",
-           "host_seconds_rank0": lk.timing()}
+           "instances_per_gpu": instances, "host_seconds_rank0_instance0": lks[0].timing()}
     if rank != 0:
         return out
     sys.path.insert(0, str(ROOT / "oracle"))
@@ -421,9 +455,10 @@ def c5_leg(g, torch, dist_mod, rank, world, dev, sc, root_world, ncores, total=4
         o = orc.OracleAnytime(sc, orc.OracleWorld.from_scenario(sc), start=starts[j], goal=goals[j],
                               sampler_cost0=float(cost0[j]))
         so = o.solve(max_iter, seed, j, total)
-        ok = bool(so == bool(solved[i]) and np.array_equal(o.log(), lk.log(i)))
+        lk, li = local_of[i]
+        ok = bool(so == bool(solved[i]) and np.array_equal(o.log(), lk.log(li)))
         if so:
-            ok = ok and bool(np.array_equal(o.solution(), lk.solution(i)[0]) and o.state()["cost"] == cost[i])
+            ok = ok and bool(np.array_equal(o.solution(), lk.solution(li)[0]) and o.state()["cost"] == cost[i])
         ok_all = ok_all and ok
         checked += 1
     out["parity"] = {"round_logs_paths_costs_bit_exact": ok_all, "queries_checked": checked}

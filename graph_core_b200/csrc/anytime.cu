@@ -47,14 +47,31 @@ __global__ void any_gather_kernel(const double* __restrict__ src, const uint32_t
 
 // parent slot and connection cost of freshly appended nodes (global slot = segment * capacity + slot)
 __global__ void any_links_kernel(const uint32_t* __restrict__ gslot, const int32_t* __restrict__ parent,
-                                 const double* __restrict__ pcost, uint32_t n, int32_t* d_parent, double* d_pcost)
+                                 const double* __restrict__ pcost, const double* __restrict__ c2n, uint32_t n,
+                                 int32_t* d_parent, double* d_pcost, double* d_c2n)
 {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n)
   {
     d_parent[gslot[i]] = parent[i];
     d_pcost[gslot[i]] = pcost[i];
+    d_c2n[gslot[i]] = c2n[i];
   }
+}
+
+// Tree::costToNode (tree.cpp:767-789): the connection costs summed from the node up to the root
+static double cost_to_node(const std::vector<int32_t>& parent, const std::vector<double>& pcost, uint32_t slot)
+{
+  double c = 0.0;
+  for (int32_t x = (int32_t)slot; x != 0;)
+  {
+    const int32_t par = parent[(size_t)x];
+    if (par < 0)
+      return std::numeric_limits<double>::infinity();
+    c += pcost[(size_t)x];
+    x = par;
+  }
+  return c;
 }
 
 // EuclideanMetrics::cost / (a - b).norm(): sequential, individually rounded (no contraction in host code)
@@ -105,8 +122,11 @@ struct gc_anytime
   double *d_lb = nullptr, *d_ub = nullptr, *d_start = nullptr, *d_goal = nullptr, *d_samples = nullptr;
   int32_t* d_parent = nullptr;
   double* d_pcost = nullptr;
+  double* d_basis = nullptr;  // informed-sampler basis of every problem (its foci never change)
+  double* d_c2n = nullptr;  // Tree::costToNode of every node, summed node -> root when it was appended
   DevArena arena;
   PinBuf h_in, h_out;
+  PinBuf h_links;  // staging of the appended nodes' links: its upload may still be in flight when the next step fills h_in
   std::vector<AnyProb> pr;
   std::vector<uint64_t> stream_index;  // Philox counter of sample k of problem p: k * stream_stride + stream_index[p]
   uint64_t stream_stride = 0;
@@ -116,7 +136,7 @@ struct gc_anytime
   // per-step scratch (host)
   std::vector<uint32_t> rowsS, rowsR, rowsI, app_seg, app_gslot, goal_row;
   std::vector<int32_t> app_parent;
-  std::vector<double> app_conf, app_pcost, goal_c1, goal_c2, goal_cost;
+  std::vector<double> app_conf, app_pcost, app_c2n, goal_c1, goal_c2, goal_cost;
   std::vector<uint8_t> goal_kind, goal_ok;
   std::vector<uint32_t> app_slots, goal_new;
 };
@@ -385,7 +405,8 @@ static int any_step(gc_anytime* a)
   if (nS)
     GC_TRY(sample_informed_rows_launch(D, nS, a->d_lb, a->d_ub, a->d_start, a->d_goal,
                                        reinterpret_cast<const double*>(d_in + off_cost), a->cfg.seed, d_rowsS,
-                                       reinterpret_cast<const unsigned long long*>(d_in + off_ctr), a->d_samples, st));
+                                       reinterpret_cast<const unsigned long long*>(d_in + off_ctr), a->d_samples, st,
+                                       a->d_basis));
   // ---- D2H staging: R: q[nR][D] | next[nR][D] | near[nR][D] | dist[nR] | closest[nR] | ok[nR]
   //                   I: new[nI][D] | node conf -> not needed | ecost[nI] | node[nI] | ok[nI]
   const size_t o_q = 0, o_next = o_q + sizeof(double) * (size_t)nR * D, o_near = o_next + sizeof(double) * (size_t)nR * D;
@@ -439,7 +460,8 @@ static int any_step(gc_anytime* a)
     uint64_t edges = 0;
     GC_TRY(informed_extend_core(s, w, d_q, d_rowsI, a->rowsI.data(), d_g, reinterpret_cast<const double*>(d_in + off_c2b),
                                 reinterpret_cast<const double*>(d_in + off_bias), nI, a->k_rrt, a->cfg.max_distance,
-                                a->cfg.min_distance, a->tolerance, a->d_parent, a->d_pcost, a->arena, &o, &edges));
+                                a->cfg.min_distance, a->tolerance, a->d_parent, a->d_pcost, a->arena, &o, &edges,
+                                a->d_c2n));
     a->stats[6] += edges;
     GC_CUDA(cudaMemcpyAsync(hout + o_new, o.d_new, sizeof(double) * (size_t)nI * D, cudaMemcpyDeviceToHost, st));
     GC_CUDA(cudaMemcpyAsync(hout + o_ecost, o.d_ecost, sizeof(double) * nI, cudaMemcpyDeviceToHost, st));
@@ -465,6 +487,7 @@ static int any_step(gc_anytime* a)
   a->app_conf.clear();
   a->app_parent.clear();
   a->app_pcost.clear();
+  a->app_c2n.clear();
   a->goal_row.clear();
   a->goal_c1.clear();
   a->goal_c2.clear();
@@ -514,6 +537,7 @@ static int any_step(gc_anytime* a)
     a->app_conf.insert(a->app_conf.end(), newc, newc + D);
     a->app_parent.push_back((int32_t)h_closest[i]);
     a->app_pcost.push_back(cost);
+    a->app_c2n.push_back(0.0);  // only the improve rounds rank by cost-to-come
     const bool reached = dist64(newc, q, D) < a->tolerance;
     if (init)
     {
@@ -571,6 +595,7 @@ static int any_step(gc_anytime* a)
     a->app_conf.insert(a->app_conf.end(), newc, newc + D);
     a->app_parent.push_back((int32_t)h_node[i]);
     a->app_pcost.push_back(cost);
+    a->app_c2n.push_back(cost_to_node(p.parent, p.pcost, slot));
     // improveUpdate (:370-388)
     const double dg = dist64(newc, goal, D);
     if (dg <= max_distance)
@@ -605,21 +630,23 @@ static int any_step(gc_anytime* a)
     a->app_slots.resize(nA);
     GC_TRY(gc_store_append_multi(s, a->app_seg.data(), a->app_conf.data(), nA, a->app_slots.data()));
     const size_t lb = align_up(sizeof(uint32_t) * nA, 16), lp = align_up(sizeof(int32_t) * nA, 16);
-    GC_TRY(a->h_in.reserve(lb + lp + sizeof(double) * nA));
-    GC_CUDA(cudaStreamSynchronize(st));  // h_in is reused
-    char* h = static_cast<char*>(a->h_in.p);
+    const size_t lc = sizeof(double) * nA, lbytes = lb + lp + 2 * lc;
+    GC_CUDA(cudaStreamSynchronize(st));  // the previous step's upload from h_links has completed
+    GC_TRY(a->h_links.reserve(lbytes));
+    char* h = static_cast<char*>(a->h_links.p);
     uint32_t* g = reinterpret_cast<uint32_t*>(h);
     for (uint32_t i = 0; i < nA; i++)
       g[i] = a->app_seg[i] * s->cap_seg + a->app_slots[i];
     memcpy(h + lb, a->app_parent.data(), sizeof(int32_t) * nA);
-    memcpy(h + lb + lp, a->app_pcost.data(), sizeof(double) * nA);
+    memcpy(h + lb + lp, a->app_pcost.data(), lc);
+    memcpy(h + lb + lp + lc, a->app_c2n.data(), lc);
     char* d_l;
-    GC_CUDA(a->arena.get(&d_l, lb + lp + sizeof(double) * nA));
-    GC_CUDA(cudaMemcpyAsync(d_l, h, lb + lp + sizeof(double) * nA, cudaMemcpyHostToDevice, st));
-    any_links_kernel<<<(nA + 255) / 256, 256, 0, st>>>(reinterpret_cast<const uint32_t*>(d_l),
-                                                       reinterpret_cast<const int32_t*>(d_l + lb),
-                                                       reinterpret_cast<const double*>(d_l + lb + lp), nA, a->d_parent,
-                                                       a->d_pcost);
+    GC_CUDA(a->arena.get(&d_l, lbytes));
+    GC_CUDA(cudaMemcpyAsync(d_l, h, lbytes, cudaMemcpyHostToDevice, st));
+    any_links_kernel<<<(nA + 255) / 256, 256, 0, st>>>(
+        reinterpret_cast<const uint32_t*>(d_l), reinterpret_cast<const int32_t*>(d_l + lb),
+        reinterpret_cast<const double*>(d_l + lb + lp), reinterpret_cast<const double*>(d_l + lb + lp + lc), nA,
+        a->d_parent, a->d_pcost, a->d_c2n);
     GC_CUDA(cudaGetLastError());
     count_launch();
     a->stats[4] += nA;
@@ -692,11 +719,12 @@ int gc_anytime_destroy(gc_anytime_t* a)
   if (a->store)
     cudaStreamSynchronize(a->store->stream);
   for (void* p : { (void*)a->d_lb, (void*)a->d_start, (void*)a->d_goal, (void*)a->d_samples, (void*)a->d_parent,
-                   (void*)a->d_pcost })
+                   (void*)a->d_pcost, (void*)a->d_c2n, (void*)a->d_basis })
     if (p)
       cudaFree(p);
   a->h_in.release();
   a->h_out.release();
+  a->h_links.release();
   if (a->world)
     gc_world_destroy(a->world);
   if (a->store)
@@ -765,6 +793,9 @@ int gc_anytime_create(gc_world_t* w, const gc_anytime_config_t* cfg, const doubl
     return fail(e, "parent slots");
   if ((e = cudaMalloc(&a->d_pcost, sizeof(double) * a->store->cap_total)) != cudaSuccess)
     return fail(e, "connection costs");
+  if ((e = cudaMalloc(&a->d_c2n, sizeof(double) * a->store->cap_total)) != cudaSuccess)
+    return fail(e, "costs to come");
+  cudaMemsetAsync(a->d_c2n, 0, sizeof(double) * a->store->cap_total, st);  // roots: cost-to-come 0
   cudaMemcpyAsync(a->d_lb, lb, sizeof(double) * D, cudaMemcpyHostToDevice, st);
   cudaMemcpyAsync(a->d_ub, ub, sizeof(double) * D, cudaMemcpyHostToDevice, st);
   cudaMemcpyAsync(a->d_start, starts, sizeof(double) * nd, cudaMemcpyHostToDevice, st);
@@ -773,6 +804,10 @@ int gc_anytime_create(gc_world_t* w, const gc_anytime_config_t* cfg, const doubl
   cudaMemcpyAsync(a->d_samples, goals, sizeof(double) * nd, cudaMemcpyHostToDevice, st);
   cudaMemsetAsync(a->d_parent, 0xFF, sizeof(int32_t) * a->store->cap_total, st);  // -1: root / not connected
   cudaMemsetAsync(a->d_pcost, 0, sizeof(double) * a->store->cap_total, st);
+  if ((e = cudaMalloc(&a->d_basis, sizeof(double) * (size_t)n_problems * (D * D + D + 1))) != cudaSuccess)
+    return fail(e, "sampler bases");
+  if (informed_basis_launch(D, n_problems, a->d_start, a->d_goal, a->d_basis, st) != GC_OK)
+    return fail(cudaGetLastError(), "sampler bases");
   if ((e = cudaStreamSynchronize(st)) != cudaSuccess)
     return fail(e, "uploads");
   // roots: RRT::addStart (rrt.cpp:58-78)

@@ -231,11 +231,15 @@ struct IeOut
 int informed_extend_core(gc_store* s, gc_world* w, const double* d_q, const uint32_t* d_seg, const uint32_t* h_seg,
                          const double* d_goal, const double* d_c2b, const double* d_bias, uint32_t n, double k_rrt,
                          double max_distance, double min_distance, double tolerance, const int32_t* d_parent,
-                         const double* d_pcost, DevArena& arena, IeOut* out, uint64_t* edges_checked);
+                         const double* d_pcost, DevArena& arena, IeOut* out, uint64_t* edges_checked,
+                         const double* d_c2n = nullptr);
 // row i samples for problem d_prob[i] (rows d_prob[i] of d_f1 / d_f2 / d_out, cost d_cost[i]) from Philox counter d_ctr[i]
 int sample_informed_rows_launch(int dim, uint32_t n, const double* d_lb, const double* d_ub, const double* d_f1,
                                 const double* d_f2, const double* d_cost, unsigned long long seed,
-                                const uint32_t* d_prob, const unsigned long long* d_ctr, double* d_out, cudaStream_t st);
+                                const uint32_t* d_prob, const unsigned long long* d_ctr, double* d_out, cudaStream_t st,
+                                const double* d_basis = nullptr);
+// d_basis[n][dim * dim + dim + 1]: the rotation basis, centre and focal distance of n (f1, f2) pairs
+int informed_basis_launch(int dim, uint32_t n, const double* d_f1, const double* d_f2, double* d_basis, cudaStream_t st);
 // floats between consecutive rows of the fp32 SoA (cap_total + the padding the scans read past the last tile)
 constexpr int kStoreRowPad = 1024;
 static inline size_t store_row_stride(const gc_store* s) { return s->cap_total + kStoreRowPad; }

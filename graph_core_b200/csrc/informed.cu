@@ -65,6 +65,8 @@ struct IeArgs
   const unsigned long long* k;  // [n] neighbours asked for
   const int32_t* parent;    // [segments * cap_seg]
   const double* pcost;
+  const double* c2n;        // optional [segments * cap_seg]: Tree::costToNode of every node, summed node -> root (the
+                            // reference's order) when the node was appended; trees that only grow never change it
   double max_distance, tolerance;
   uint32_t P2;              // scratch row length (power of two >= the largest tree)
   double* cand_d;           // [n][P2] distances in nearK order
@@ -127,17 +129,20 @@ __global__ void __launch_bounds__(512) ie_rank_kernel(IeArgs a)
         d = norm_diff<D>(node, qs);
         ie_next_conf<D>(node, qs, d, a.max_distance, nx);
         double c2n = 0.0;  // Tree::costToNode
-        for (int32_t x = (int32_t)i; x != 0;)
-        {
-          const int32_t par = a.parent[base + x];
-          if (par < 0)
+        if (a.c2n)
+          c2n = a.c2n[base + i];
+        else
+          for (int32_t x = (int32_t)i; x != 0;)
           {
-            c2n = CUDART_INF;
-            break;
+            const int32_t par = a.parent[base + x];
+            if (par < 0)
+            {
+              c2n = CUDART_INF;
+              break;
+            }
+            c2n = __dadd_rn(c2n, a.pcost[base + x]);
+            x = par;
           }
-          c2n = __dadd_rn(c2n, a.pcost[base + x]);
-          x = par;
-        }
         const double heur = __dadd_rn(__dmul_rn(bias, d), __dmul_rn(__dsub_rn(1.0, bias), c2n));
         if (__dadd_rn(__dadd_rn(c2n, d), norm_diff<D>(gs, nx)) < c2b)
         {
@@ -470,7 +475,8 @@ void DevArena::reset()
 int informed_extend_core(gc_store* s, gc_world* w, const double* d_q, const uint32_t* d_seg, const uint32_t* h_seg,
                          const double* d_goal, const double* d_c2b, const double* d_bias, uint32_t n, double k_rrt,
                          double max_distance, double min_distance, double tolerance, const int32_t* d_parent,
-                         const double* d_pcost, DevArena& arena, IeOut* out, uint64_t* edges_checked)
+                         const double* d_pcost, DevArena& arena, IeOut* out, uint64_t* edges_checked,
+                         const double* d_c2n)
 {
   const int D = s->dim;
   cudaStream_t st = s->stream;
@@ -509,6 +515,7 @@ int informed_extend_core(gc_store* s, gc_world* w, const double* d_q, const uint
   a.k = d_k;
   a.parent = d_parent;
   a.pcost = d_pcost;
+  a.c2n = d_c2n;
   a.max_distance = max_distance;
   a.tolerance = tolerance;
   a.P2 = P2;
@@ -539,7 +546,7 @@ int informed_extend_core(gc_store* s, gc_world* w, const double* d_q, const uint
   ie_iota_kernel<<<(n + 255) / 256, 256, 0, st>>>(d_unres[0], n);
   GC_CUDA(cudaGetLastError());
   count_launch();
-  GC_CUDA(cudaStreamSynchronize(st));  // kq leaves scope
+  // (kq is pageable memory: cudaMemcpyAsync has staged it before returning, no synchronisation needed)
   uint32_t U = n, lo = 0, width = 4;
   int cur = 0;
   uint64_t edges_total = 0;
@@ -645,7 +652,7 @@ int gc_informed_extend_batch(gc_store_t* s, gc_world_t* w, const double* q, cons
   GC_CUDA(cudaMemcpyAsync(d_seg, seg, sizeof(uint32_t) * n, cudaMemcpyHostToDevice, st));
   IeOut o{};
   GC_TRY(informed_extend_core(s, w, d_q, d_seg, seg, d_goal, d_c2b, d_bias, n, k_rrt, max_distance, min_distance,
-                              tolerance, d_parent, d_pcost, arena, &o, edges_checked));
+                              tolerance, d_parent, d_pcost, arena, &o, edges_checked, nullptr));
   GC_CUDA(cudaMemcpyAsync(ok, o.d_ok, n, cudaMemcpyDeviceToHost, st));
   GC_CUDA(cudaMemcpyAsync(tree_node, o.d_node, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost, st));
   GC_CUDA(cudaMemcpyAsync(new_conf, o.d_new, sizeof(double) * (size_t)n * D, cudaMemcpyDeviceToHost, st));

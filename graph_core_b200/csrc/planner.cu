@@ -152,8 +152,82 @@ struct InformedArgs
   // f1 / f2 / out -- and draws from Philox counter ctr[i] instead of first + i
   const uint32_t* prob;
   const unsigned long long* ctr;
+  const double* basis;        // optional [rows][D*D + D + 1]: informed_basis_kernel's output for rows prob[i] (or i)
   uint32_t lanes_per_sample;  // 0 / 1: one thread per sample; 32: a warp per sample, its lanes share the rejection rounds
 };
+
+// rotation basis of the prolate hyperspheroid (informed_sampler.cpp:107-143): R[row][col], centre, distance of the foci
+__device__ __forceinline__ void informed_basis(int D, const double* f1, const double* f2, double (*R)[GC_MAX_DIM],
+                                               double* centre, double& fd)
+{
+  double v[GC_MAX_DIM];
+  double s2 = 0.0;
+  for (int d = 0; d < D; d++)
+  {
+    v[d] = __dsub_rn(f1[d], f2[d]);
+    s2 = __dadd_rn(s2, __dmul_rn(v[d], v[d]));
+    centre[d] = __dmul_rn(0.5, __dadd_rn(f1[d], f2[d]));
+  }
+  fd = __dsqrt_rn(s2);
+  for (int d = 0; d < D; d++)
+    v[d] = __ddiv_rn(v[d], fd);
+  for (int r0 = 0; r0 < D; r0++)
+    for (int c0 = 0; c0 < D; c0++)
+      R[r0][c0] = (r0 == c0) ? 1.0 : 0.0;
+  bool standard = false;
+  for (int ic = 0; ic < D; ic++)
+    if (fabs(v[ic]) > 0.999)
+    {
+      standard = true;  // swap columns ic and 0 of the identity
+      for (int r0 = 0; r0 < D; r0++)
+      {
+        const double t = R[r0][ic];
+        R[r0][ic] = R[r0][0];
+        R[r0][0] = t;
+      }
+      break;
+    }
+  if (!standard)
+  {
+    for (int r0 = 0; r0 < D; r0++)
+      R[r0][0] = v[r0];
+    for (int ic = 1; ic < D; ic++)
+    {
+      for (int il = 0; il < ic; il++)
+      {
+        double dot = 0.0;
+        for (int r0 = 0; r0 < D; r0++)
+          dot = __dadd_rn(dot, __dmul_rn(R[r0][ic], R[r0][il]));
+        for (int r0 = 0; r0 < D; r0++)
+          R[r0][ic] = __dsub_rn(R[r0][ic], __dmul_rn(dot, R[r0][il]));
+      }
+      double n2 = 0.0;
+      for (int r0 = 0; r0 < D; r0++)
+        n2 = __dadd_rn(n2, __dmul_rn(R[r0][ic], R[r0][ic]));
+      const double nn = __dsqrt_rn(n2);
+      for (int r0 = 0; r0 < D; r0++)
+        R[r0][ic] = __ddiv_rn(R[r0][ic], nn);
+    }
+  }
+}
+
+// the basis depends on the foci only: lock-step planners whose foci are fixed per problem compute it once
+// (basis[p] = R row-major [D][D] | centre[D] | fd)
+__global__ void informed_basis_kernel(int D, uint32_t n, const double* f1, const double* f2, double* basis)
+{
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n)
+    return;
+  double R[GC_MAX_DIM][GC_MAX_DIM], centre[GC_MAX_DIM], fd;
+  informed_basis(D, f1 + (size_t)i * D, f2 + (size_t)i * D, R, centre, fd);
+  double* b = basis + (size_t)i * (D * D + D + 1);
+  for (int r0 = 0; r0 < D; r0++)
+    for (int c0 = 0; c0 < D; c0++)
+      b[r0 * D + c0] = R[r0][c0];
+  for (int d = 0; d < D; d++)
+    b[D * D + d] = centre[d];
+  b[D * D + D] = fd;
+}
 
 __global__ void sample_informed_kernel(InformedArgs a)
 {
@@ -196,55 +270,20 @@ __global__ void sample_informed_kernel(InformedArgs a)
   const double* f1 = a.f1 + row * D;
   const double* f2 = a.f2 + row * D;
   double R[GC_MAX_DIM][GC_MAX_DIM];  // R[row][col]
-  double v[GC_MAX_DIM], centre[GC_MAX_DIM], axis[GC_MAX_DIM];
-  double s2 = 0.0;
-  for (int d = 0; d < D; d++)
+  double centre[GC_MAX_DIM], axis[GC_MAX_DIM];
+  double fd;
+  if (a.basis)
   {
-    v[d] = __dsub_rn(f1[d], f2[d]);
-    s2 = __dadd_rn(s2, __dmul_rn(v[d], v[d]));
-    centre[d] = __dmul_rn(0.5, __dadd_rn(f1[d], f2[d]));
-  }
-  const double fd = __dsqrt_rn(s2);
-  for (int d = 0; d < D; d++)
-    v[d] = __ddiv_rn(v[d], fd);
-  for (int r0 = 0; r0 < D; r0++)
-    for (int c0 = 0; c0 < D; c0++)
-      R[r0][c0] = (r0 == c0) ? 1.0 : 0.0;
-  bool standard = false;
-  for (int ic = 0; ic < D; ic++)
-    if (fabs(v[ic]) > 0.999)
-    {
-      standard = true;  // swap columns ic and 0 of the identity
-      for (int r0 = 0; r0 < D; r0++)
-      {
-        const double t = R[r0][ic];
-        R[r0][ic] = R[r0][0];
-        R[r0][0] = t;
-      }
-      break;
-    }
-  if (!standard)
-  {
+    const double* b = a.basis + row * (size_t)(D * D + D + 1);
     for (int r0 = 0; r0 < D; r0++)
-      R[r0][0] = v[r0];
-    for (int ic = 1; ic < D; ic++)
-    {
-      for (int il = 0; il < ic; il++)
-      {
-        double dot = 0.0;
-        for (int r0 = 0; r0 < D; r0++)
-          dot = __dadd_rn(dot, __dmul_rn(R[r0][ic], R[r0][il]));
-        for (int r0 = 0; r0 < D; r0++)
-          R[r0][ic] = __dsub_rn(R[r0][ic], __dmul_rn(dot, R[r0][il]));
-      }
-      double n2 = 0.0;
-      for (int r0 = 0; r0 < D; r0++)
-        n2 = __dadd_rn(n2, __dmul_rn(R[r0][ic], R[r0][ic]));
-      const double nn = __dsqrt_rn(n2);
-      for (int r0 = 0; r0 < D; r0++)
-        R[r0][ic] = __ddiv_rn(R[r0][ic], nn);
-    }
+      for (int c0 = 0; c0 < D; c0++)
+        R[r0][c0] = b[r0 * D + c0];
+    for (int d = 0; d < D; d++)
+      centre[d] = b[D * D + d];
+    fd = b[D * D + D];
   }
+  else
+    informed_basis(D, f1, f2, R, centre, fd);
   double rmin;
   if (cost < fd)
   {
@@ -340,9 +379,11 @@ int sample_informed_launch(int dim, uint32_t n, const double* d_lb, const double
 
 int sample_informed_rows_launch(int dim, uint32_t n, const double* d_lb, const double* d_ub, const double* d_f1,
                                 const double* d_f2, const double* d_cost, unsigned long long seed,
-                                const uint32_t* d_prob, const unsigned long long* d_ctr, double* d_out, cudaStream_t st)
+                                const uint32_t* d_prob, const unsigned long long* d_ctr, double* d_out, cudaStream_t st,
+                                const double* d_basis)
 {
   InformedArgs a{};
+  a.basis = d_basis;
   a.dim = dim;
   a.n = n;
   a.lb = d_lb;
@@ -359,6 +400,14 @@ int sample_informed_rows_launch(int dim, uint32_t n, const double* d_lb, const d
   // few samples per call and up to 100 rejection rounds each: the max over the batch sets the kernel time
   a.lanes_per_sample = 32;
   sample_informed_kernel<<<(n + 3) / 4, 128, 0, st>>>(a);
+  GC_CUDA(cudaGetLastError());
+  count_launch();
+  return GC_OK;
+}
+
+int informed_basis_launch(int dim, uint32_t n, const double* d_f1, const double* d_f2, double* d_basis, cudaStream_t st)
+{
+  informed_basis_kernel<<<(n + 127) / 128, 128, 0, st>>>(dim, n, d_f1, d_f2, d_basis);
   GC_CUDA(cudaGetLastError());
   count_launch();
   return GC_OK;

@@ -207,16 +207,20 @@ def c3_problems(checker, params, n: int, seed: int = 302):
     out = []
     first = 0
     t = np.linspace(0.0, 1.0, 65)[:, None]
+    chunk = 64 if n <= 256 else 4096  # candidates per round (the stream is counter based: chunking does not change it)
     while len(out) < n:
-        s, g = c3_problem_pairs(64, seed, first)
-        first += 64
-        ok = checker(params, s) & checker(params, g)
-        for i in np.nonzero(ok)[0]:
-            line = s[i][None, :] + (g[i] - s[i])[None, :] * t
-            if not checker(params, line).all():
-                out.append((s[i].copy(), g[i].copy()))
-                if len(out) == n:
-                    break
+        s, g = c3_problem_pairs(chunk, seed, first)
+        first += chunk
+        ok = np.nonzero(checker(params, s) & checker(params, g))[0]
+        if ok.size == 0:
+            continue
+        # the 65 states of every candidate's straight line, one checker call for the whole chunk
+        lines = s[ok][:, None, :] + (g[ok] - s[ok])[:, None, :] * t[None, :, :]
+        free = checker(params, lines.reshape(-1, s.shape[1])).reshape(ok.size, t.shape[0]).all(axis=1)
+        for i in ok[~free]:
+            out.append((s[i].copy(), g[i].copy()))
+            if len(out) == n:
+                break
     return out
 
 
@@ -230,21 +234,24 @@ def c5_problems(checker, params, n: int, seed: int = 501, reach: float = 1.5, co
     starts, goals = [], []
     first = 0
     t = np.linspace(0.0, 1.0, 65)[:, None]
+    chunk = 64 if n <= 256 else 4096  # candidates per round (counter-based stream: chunking does not change it)
     while len(starts) < n:
-        u = philox_u01(seed, first, 64, 14)
-        first += 64
+        u = philox_u01(seed, first, chunk, 14)
+        first += chunk
         s = -math.pi + u[:, :7] * 2 * math.pi
         v = 2.0 * u[:, 7:] - 1.0
         v = v / np.sqrt((v * v).sum(axis=1))[:, None]
         g = s + reach * v
-        ok = checker(params, s) & checker(params, g) & (np.abs(g) <= math.pi).all(axis=1)
-        for i in np.nonzero(ok)[0]:
-            line = s[i][None, :] + (g[i] - s[i])[None, :] * t
-            if not checker(params, line).all():
-                starts.append(s[i].copy())
-                goals.append(g[i].copy())
-                if len(starts) == n:
-                    break
+        ok = np.nonzero(checker(params, s) & checker(params, g) & (np.abs(g) <= math.pi).all(axis=1))[0]
+        if ok.size == 0:
+            continue
+        lines = s[ok][:, None, :] + (g[ok] - s[ok])[:, None, :] * t[None, :, :]
+        free = checker(params, lines.reshape(-1, 7)).reshape(ok.size, t.shape[0]).all(axis=1)
+        for i in ok[~free]:
+            starts.append(s[i].copy())
+            goals.append(g[i].copy())
+            if len(starts) == n:
+                break
     starts, goals = np.array(starts), np.array(goals)
     d = np.sqrt(((goals - starts) ** 2).sum(axis=1))
     return starts, goals, cost_factor * d

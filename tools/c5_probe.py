@@ -15,13 +15,43 @@ sc = W.scenario_c3(1000, arm)
 t0 = time.time()
 starts, goals, cost0 = W.c5_problems(arm, sc.params, P)
 t1 = time.time()
-lk = LockstepAnytimeRRT(sc, sc.make_world(), starts, goals, max_iter=max_iter, seed=501, sampler_cost0=cost0, capacity=8192)
-t2 = time.time()
+inst = int(sys.argv[4]) if len(sys.argv) > 4 else 1
 max_steps = int(sys.argv[3]) if len(sys.argv) > 3 else 0
-live = lk.run(max_steps)
+import threading
+world = sc.make_world()
+parts = [np.arange(i, P, inst) for i in range(inst)]
+lks = [None] * inst
+t2 = time.time()
+
+
+lock = threading.Lock()
+
+
+def work(i):
+    idx = parts[i]
+    with lock:
+            lk = LockstepAnytimeRRT(sc, world, starts[idx], goals[idx], max_iter=max_iter, seed=501, sampler_cost0=cost0[idx],
+                                capacity=8192)
+    lk.set_streams(P, idx)
+    lks[i] = lk
+    lk.run(max_steps)
+
+
+ts = [threading.Thread(target=work, args=(i,)) for i in range(inst)]
+for t in ts:
+    t.start()
+for t in ts:
+    t.join()
 t3 = time.time()
-solved, cost = lk.solved()
-st = lk.stats()
-print(json.dumps({"P": P, "max_iter": max_iter, "gen_s": t1 - t0, "create_s": t2 - t1, "run_s": t3 - t2, "live": live,
-                  "queries_per_s": P / (t3 - t2), "solved": int(solved.sum()), "mean_cost": float(cost[solved].mean()) if solved.any() else None,
-                  "stats": st, "timing": lk.timing(), "us_per_step": 1e6 * (t3 - t2) / max(st["steps"], 1)}))
+solved = np.zeros(P, bool)
+cost = np.zeros(P)
+steps = 0
+for i, lk in enumerate(lks):
+    s_, c_ = lk.solved()
+    solved[parts[i]] = s_
+    cost[parts[i]] = c_
+    steps = max(steps, lk.stats()["steps"])
+print(json.dumps({"P": P, "max_iter": max_iter, "instances": inst, "gen_s": t1 - t0, "run_s": t3 - t2,
+                  "queries_per_s": P / (t3 - t2), "solved": int(solved.sum()),
+                  "mean_cost": float(cost[solved].mean()) if solved.any() else None, "steps": steps,
+                  "stats0": lks[0].stats(), "timing0": lks[0].timing()}))
