@@ -1152,9 +1152,13 @@ __device__ __forceinline__ void arm_grid_body(const ArmArgs& a, const ArmSmem& w
     // ---- fill: scan slots until 32 live items are queued or the list is exhausted
     while (qn < 32u && tb < total)
     {
+      // hand-out counter: a PREDICATED atomic (lane 0), no divergent region -- with a branch around it the whole warp
+      // waited for the atomic's round trip at the reconvergence point (22 % of the stall samples of this kernel); now the
+      // value is only waited for at the shuffle below, after the loads and the queueing of this batch
       unsigned long long nb = 0;
-      if (lane == 0)
-        nb = atomicAdd(ctr, 32ull);
+      asm volatile("{\n\t.reg .pred p;\n\tsetp.eq.u32 p, %2, 0;\n\t@p atom.global.add.u64 %0, [%1], 32;\n\t}"
+                   : "+l"(nb)
+                   : "l"(ctr), "r"(lane));
       const T t = tb + lane;
       bool live = t < total;
       uint32_t e = 0, st = 0;
@@ -1174,9 +1178,9 @@ __device__ __forceinline__ void arm_grid_body(const ArmArgs& a, const ArmSmem& w
           {
             // early exit: the reference stops at its first colliding state
             if (MODE == GC_EDGE_LINEAR)
-              live = !(*reinterpret_cast<volatile unsigned long long*>(a.first_bad + e) < (unsigned long long)st);
+              live = !(__ldcg(a.first_bad + e) < (unsigned long long)st);  // L2: where other SMs' verdicts land
             else
-              live = (*reinterpret_cast<volatile uint8_t*>(a.ok + e) == 1);
+              live = (__ldcg(a.ok + e) == 1);
           }
         }
       }
