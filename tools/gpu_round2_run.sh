@@ -1,5 +1,4 @@
-mkdir -p gpurun_out/r2s33
-O=gpurun_out/r2s33
-timeout 900 python -m pytest tests/test_edge_gpu.py tests/test_planner_gpu.py tests/test_golden_gpu.py tests/test_anytime_gpu.py -x -q -m gpu > $O/pytest.log 2>&1; echo "pytest rc=$?" >> $O/pytest.log
-timeout 600 python bench.py --skip-nn --skip-extras > $O/bench.json 2> $O/bench.err; echo "rc=$?" >> $O/bench.err
-timeout 600 python bench.py --skip-nn --skip-extras --problems 8192 > $O/bench_8k.json 2> $O/bench_8k.err
+mkdir -p gpurun_out/r2s34
+O=gpurun_out/r2s34
+( time timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29533 bench.py --gpus 8 > $O/bench_8gpu.json 2> $O/bench_8gpu.err ) 2> $O/bench.time; echo "rc=$?" >> $O/bench_8gpu.err
+tail -c 1500 $O/bench_8gpu.err > $O/bench_8gpu.err.tail; rm $O/bench_8gpu.err
