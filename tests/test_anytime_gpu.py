@@ -175,3 +175,15 @@ def test_lockstep_anytime_results_do_not_depend_on_sharding(gc, orc):
             assert a == b
             if a["solved"]:
                 assert np.array_equal(part.solution(i)[0], full.solution(int(j))[0])
+
+
+def test_lockstep_anytime_reports_a_full_tree(gc, orc):
+    """A tree that outgrows its segment is an error (GC_E_CAPACITY with the problem named), never a silent truncation."""
+    from graph_core_b200.planner import LockstepAnytimeRRT
+    sc = W.scenario_c1()
+    starts, goals = _free_pairs(sc, orc, 2, 4700)
+    # the scenario's own pair needs a few hundred nodes; 32 slots are exhausted during the first round
+    lk = LockstepAnytimeRRT(sc, sc.make_world(), starts[:1], goals[:1], max_iter=2000, seed=5, capacity=32)
+    with pytest.raises(gc.GcError) as ei:
+        lk.run()
+    assert "capacity" in str(ei.value)
