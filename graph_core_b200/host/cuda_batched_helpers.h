@@ -11,11 +11,15 @@
 //
 //   N1  Tree::checkPathToNode          src/graph_core/graph/tree.cpp:335-373
 //       Tree::recheckCollision         src/graph_core/graph/tree.cpp:1405-1429
+//       Tree::rewireOnlyWithPathCheck  src/graph_core/graph/tree.cpp:522-679
 //   N2  Path::isValid / isValidFromConn / isValidFromConf   src/graph_core/graph/path.cpp:1230-1407
 //   N3  PathLocalOptimizer::bisection / warp / simplify / step
 //       src/graph_core/solvers/path_optimizers/path_local_optimizer.cpp:59-246
 #pragma once
 #ifdef GCB200_WITH_GRAPH_CORE
+
+#include <algorithm>
+#include <map>
 
 #include <graph_core/graph/path.h>
 #include <graph_core/graph/tree.h>
@@ -103,6 +107,59 @@ inline bool checkPathToNode(const TreePtr& tree, const NodePtr& node, std::vecto
   }
   prefetch(chk, todo);
   return tree->checkPathToNode(node, checked_connections, path_connections);
+}
+
+// N1: Tree::rewireOnlyWithPathCheck (tree.cpp:522-679): rewiring around `node` on a tree whose connections may have
+// become invalid (replanning).  The function asks, one at a time and depending on the costs met so far, for
+//   * the connections root -> node and root -> n of the near nodes n it considers (checkPathToNode, not yet flagged),
+//   * the edge n -> node of every parent candidate and the edge node -> n of every child candidate.
+// All of them are known before the walk starts -- the near set, both directions of every (node, near node) pair and
+// every unflagged connection on the way to those nodes -- so they go to the device as ONE batch; the reference's own
+// function then runs unchanged on the cached verdicts.  r_rewire <= 0 selects nearK as in the reference (:557-560).
+inline bool rewireOnlyWithPathCheck(const TreePtr& tree, NodePtr& node, std::vector<ConnectionPtr>& checked_connections,
+                                    double r_rewire, const std::vector<NodePtr>& white_list, const int& what_rewire,
+                                    const CudaCheckerPtr& chk)
+{
+  const std::multimap<double, NodePtr> near_nodes = (r_rewire <= 0) ? tree->nearK(node) : tree->near(node, r_rewire);
+  std::vector<const double*> from, to;
+  std::vector<ConnectionPtr> on_paths;
+  std::vector<Connection*> seen;
+  auto addPath = [&](const NodePtr& n) {
+    if (n == tree->getRoot())
+      return;
+    for (const ConnectionPtr& c : tree->getConnectionToNode(n))
+      if (!c->isRecentlyChecked() && std::find(seen.begin(), seen.end(), c.get()) == seen.end())
+      {
+        seen.push_back(c.get());
+        on_paths.push_back(c);
+      }
+  };
+  addPath(node);
+  const double* nc = node->getConfiguration().data();
+  for (const std::pair<const double, NodePtr>& p : near_nodes)
+  {
+    const NodePtr& n = p.second;
+    if (n == node)
+      continue;
+    addPath(n);
+    if (what_rewire != 2)  // parent phase: checkConnection(n, node)  (:589)
+    {
+      from.push_back(n->getConfiguration().data());
+      to.push_back(nc);
+    }
+    if (what_rewire != 1)  // children phase: checkConnection(node, n)  (:661)
+    {
+      from.push_back(nc);
+      to.push_back(n->getConfiguration().data());
+    }
+  }
+  for (const ConnectionPtr& c : on_paths)
+  {
+    from.push_back(c->getParent()->getConfiguration().data());
+    to.push_back(c->getChild()->getConfiguration().data());
+  }
+  chk->prefetchConnections(from, to);
+  return tree->rewireOnlyWithPathCheck(node, checked_connections, r_rewire, white_list, what_rewire);
 }
 
 // N3: PathLocalOptimizer with speculative batches.  bisection() (path_local_optimizer.cpp:60-136) tries at most five

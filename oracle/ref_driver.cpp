@@ -620,6 +620,29 @@ int ref_check_path_to_node(void* h, void* other_checker, const double* conf, int
   return ok ? 1 : 0;
 }
 
+// Tree::rewireOnlyWithPathCheck (tree.cpp:522-679) around the tree node at `conf`, with `other_checker` (may be NULL) as
+// the tree's checker for the call.  Returns the reference's boolean; n_checked = connections it flagged.
+int ref_rewire_only_with_path_check(void* h, void* other_checker, const double* conf, double r_rewire, int what_rewire,
+                                    int keep_flags, int* n_checked)
+{
+  RefSolver* s = (RefSolver*)h;
+  TreePtr t = s->solver->getStartTree();
+  if (!t)
+    return -1;
+  NodePtr node = t->findClosestNode(toVec(conf, s->dim));
+  CollisionCheckerPtr old = t->getChecker();
+  if (other_checker)
+    t->setChecker(((RefChecker*)other_checker)->c);
+  std::vector<ConnectionPtr> checked;
+  const bool ok = t->rewireOnlyWithPathCheck(node, checked, r_rewire, what_rewire);
+  t->setChecker(old);
+  *n_checked = (int)checked.size();
+  if (!keep_flags)
+    for (const ConnectionPtr& c : checked)
+      c->setRecentlyChecked(false);
+  return ok ? 1 : 0;
+}
+
 // Tree::informedExtend (tree.cpp:235-302) on a tree given as arrays: conf[n][dim], parent[n] (index, -1 for the root =
 // node 0) and the connection costs pcost[n].  Nodes enter the NearestNeighbors structure in index order.  Returns the
 // reference's boolean; new_conf / parent_index describe the node it appended.

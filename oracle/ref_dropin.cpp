@@ -205,6 +205,29 @@ int dropin_check_path_to_node_batched(void* h, void* other_checker, const double
       c->setRecentlyChecked(false);
   return ok ? 1 : 0;
 }
+// ref_rewire_only_with_path_check through cuda_batched::rewireOnlyWithPathCheck: one device call for the near set's
+// edges and every connection on the way to those nodes
+int dropin_rewire_only_with_path_check_batched(void* h, void* other_checker, const double* conf, double r_rewire,
+                                               int what_rewire, int keep_flags, int* n_checked)
+{
+  RefSolver* s = (RefSolver*)h;
+  TreePtr t = s->solver->getStartTree();
+  auto chk = cudaCheckerOf(s, other_checker);
+  if (!t || !chk)
+    return -1;
+  NodePtr node = t->findClosestNode(toVec(conf, s->dim));
+  CollisionCheckerPtr old = t->getChecker();
+  t->setChecker(chk);
+  std::vector<ConnectionPtr> checked;
+  std::vector<NodePtr> white_list;
+  const bool ok = cuda_batched::rewireOnlyWithPathCheck(t, node, checked, r_rewire, white_list, what_rewire, chk);
+  t->setChecker(old);
+  *n_checked = (int)checked.size();
+  if (!keep_flags)
+    for (const ConnectionPtr& c : checked)
+      c->setRecentlyChecked(false);
+  return ok ? 1 : 0;
+}
 // ref_solution_optimize with cuda_batched::SpeculativePathLocalOptimizer
 int dropin_solution_optimize_speculative(void* h, int mode, int max_iter, int cap, double* conf, double* cost_out)
 {

@@ -96,6 +96,7 @@ def lib(fast: bool = False, dropin: bool = False):
         "ref_informed_extend": (C.c_int, [C.c_int, vp, C.c_int, _dp, C.POINTER(C.c_int), _dp, C.c_double, C.c_int, _dp, _dp,
                                           C.c_double, C.c_double, _dp, C.POINTER(C.c_int)]),
         "ref_check_path_to_node": (C.c_int, [vp, vp, _dp, C.c_int, C.c_int, _dp, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+        "ref_rewire_only_with_path_check": (C.c_int, [vp, vp, _dp, C.c_double, C.c_int, C.c_int, C.POINTER(C.c_int)]),
         "ref_srand": (None, [C.c_uint]),
         "ref_sample_informed": (None, [C.c_int, _dp, _dp, _dp, _dp, C.c_double, C.c_int, _dp]),
         "ref_informed_specific_volume": (C.c_double, [C.c_int, _dp, _dp, _dp, _dp, C.c_double]),
@@ -115,6 +116,8 @@ def lib(fast: bool = False, dropin: bool = False):
         sig["dropin_tree_recheck_batched"] = (C.c_int, [vp])
         sig["dropin_check_path_to_node_batched"] = (C.c_int, [vp, vp, _dp, C.c_int, C.c_int, _dp, C.POINTER(C.c_int),
                                                             C.POINTER(C.c_int)])
+        sig["dropin_rewire_only_with_path_check_batched"] = (C.c_int, [vp, vp, _dp, C.c_double, C.c_int, C.c_int,
+                                                                     C.POINTER(C.c_int)])
         sig["dropin_solution_optimize_speculative"] = (C.c_int, [vp, C.c_int, C.c_int, C.c_int, _dp, _dp])
     for name, (res, args) in sig.items():
         fn = getattr(L, name)
@@ -404,6 +407,17 @@ class RefSolver:
         return r, costs[:npth.value].copy(), nc.value
 
 
+    def rewire_only_with_path_check(self, conf, r_rewire, other_checker=None, what_rewire=0, keep_flags=False, _fn=None):
+        """Tree::rewireOnlyWithPathCheck (tree.cpp:522-679) around the tree node at `conf`: (improved, connections the
+        call checked)."""
+        conf = _f64(conf)
+        nc = C.c_int(0)
+        fn = _fn or self.L.ref_rewire_only_with_path_check
+        r = fn(self.h, other_checker.h if other_checker is not None else None, _p(conf, _dp), float(r_rewire),
+               int(what_rewire), 1 if keep_flags else 0, C.byref(nc))
+        return r, nc.value
+
+
 def cuda_ref_checker(cuda_world, min_distance):
     """A RefChecker whose CollisionCheckerBase is graph::core::CudaCollisionChecker over a CUDA world."""
     L = lib(dropin=True)
@@ -460,6 +474,10 @@ class DropinSolver(RefSolver):
 
     def check_path_to_node_batched(self, conf, other_checker=None, keep_flags=False):
         return self.check_path_to_node(conf, other_checker, keep_flags, _fn=self.L.dropin_check_path_to_node_batched)
+
+    def rewire_only_with_path_check_batched(self, conf, r_rewire, other_checker=None, what_rewire=0, keep_flags=False):
+        return self.rewire_only_with_path_check(conf, r_rewire, other_checker, what_rewire, keep_flags,
+                                                _fn=self.L.dropin_rewire_only_with_path_check_batched)
 
     def optimize_solution_speculative(self, mode, max_iter):
         wp = np.empty((1 << 14, self.dim))

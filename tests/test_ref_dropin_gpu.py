@@ -317,3 +317,37 @@ def test_speculative_local_optimizer_counts_device_calls(gc, orc, ref):
             # warp: at most one device call per bisection instead of up to ten
             assert k2 - k1 <= iters * (len(cpu.solution()) - 2)
             assert (k1 - k0) >= 2 * (k2 - k1)
+
+
+def test_rewire_only_with_path_check_batched(gc, orc, ref):
+    """SURVEY 8f N1: Tree::rewireOnlyWithPathCheck (tree.cpp:522-679), the replanning form of rewireOnly that re-validates
+    the connections it relies on.  cuda_batched::rewireOnlyWithPathCheck hands the near set's edges (both directions) and
+    every unflagged connection on the way to those nodes to the device as ONE batch and then runs the reference's own
+    function: the boolean, the connections it flagged and the rewired tree (infinite costs of the blocked connections
+    included) must be those of the CPU reference with its per-state checker on the changed scene."""
+    import ctypes as C
+    sc = W.scenario_c1()
+    cpu, gpu, L = _solved_pair(gc, orc, ref, sc, 9500, 2500)
+    path = cpu.solution()
+    sc2 = _box_scene_with_new_obstacle(sc, path)
+    ow2 = orc.OracleWorld.from_scenario(sc2)
+    cpu_chk2 = ref.RefChecker(L.ref_checker_callback(sc.dim, C.cast(ow2.L.orc_check_states, C.c_void_p), ow2.h,
+                                                     sc.min_distance), sc.dim, L, sc.min_distance, keep=(ow2,))
+    gpu_chk2 = ref.cuda_ref_checker(sc2.make_world(), sc.min_distance)
+    n_improved = n_flagged = 0
+    calls = []
+    for node, what, r in ((path[-1], 0, 0.15), (path[len(path) // 2 + 1], 0, 0.15), (path[2], 2, 0.15),
+                          (path[len(path) // 2 - 1], 1, 0.2), (path[-2], 0, 0.0)):
+        want = cpu.rewire_only_with_path_check(node, r, cpu_chk2, what_rewire=what, keep_flags=True)
+        k0 = gpu.device_calls_of(gpu_chk2)
+        got = gpu.rewire_only_with_path_check_batched(node, r, gpu_chk2, what_rewire=what, keep_flags=True)
+        calls.append(gpu.device_calls_of(gpu_chk2) - k0)
+        assert got == want, (what, r, got, want)
+        _same(ref, cpu, gpu)
+        n_improved += want[0]
+        n_flagged += want[1]
+    assert n_improved >= 2 and n_flagged >= 50
+    # one device call per rewiring (the prefetch); nothing the reference asked for was outside the batch
+    assert max(calls) <= 1, calls
+    conf, par, pc = gpu.dump()
+    assert np.isinf(pc).any()  # the connections under the new obstacle were found and marked
