@@ -375,9 +375,9 @@ def c5_leg(g, torch, dist_mod, rank, world, dev, sc, root_world, ncores, total=4
     queries/s = total / max over ranks.  Rank 0 replays a few queries through the oracle (bit-identical round logs) and
     times the reference's own AnytimeRRT (oracle/_ref) on the host cores beside it."""
     from graph_core_b200 import worlds as W
-    from graph_core_b200.planner import LockstepAnytimeRRT
+    from graph_core_b200.planner import LockstepAnytimeRRT, query_shard
     starts, goals, cost0 = W.c5_problems(cuda_checker(dev), sc.params, total, seed=seed)
-    mine = np.arange(rank, total, world)
+    mine = query_shard(total, rank, world)
     import threading
     # `instances` lock-step planners per GPU, each with its own stream and host thread: a step is a chain of short
     # launches and read-backs, so the instances overlap one another's latencies (results do not depend on the split)

@@ -294,6 +294,30 @@ class LockstepBiRRT:
         return wp[:n].copy(), cs[:max(n - 1, 0)].copy()
 
 
+def query_shard(total: int, rank: int, world: int) -> np.ndarray:
+    """BASELINE config 5's partition of `total` independent queries over `world` GPUs: query j runs on GPU j mod world.
+    The returned positions are also the queries' sample-stream indices (LockstepAnytimeRRT.set_streams(total, idx))."""
+    return np.arange(rank, total, world, dtype=np.int64)
+
+
+def gather_query_results(dist_mod, total: int, mine: np.ndarray, solved: np.ndarray, cost: np.ndarray, device=None):
+    """Whole-set (solved, cost) arrays from the per-rank shards of query_shard: one all-reduce of two vectors of length
+    `total` (every query is owned by exactly one rank).  dist_mod = torch.distributed or None for a single process."""
+    import torch
+    full_s = torch.zeros(total, dtype=torch.float64, device=device)
+    full_c = torch.zeros(total, dtype=torch.float64, device=device)
+    idx = torch.as_tensor(np.asarray(mine), dtype=torch.long, device=device)
+    full_s[idx] = torch.as_tensor(np.asarray(solved, dtype=np.float64), device=device)
+    c = np.where(np.asarray(solved, dtype=bool), np.asarray(cost, dtype=np.float64), 0.0)
+    full_c[idx] = torch.as_tensor(c, device=device)
+    if dist_mod is not None and dist_mod.is_initialized() and dist_mod.get_world_size() > 1:
+        dist_mod.all_reduce(full_s)
+        dist_mod.all_reduce(full_c)
+    s_np = full_s.cpu().numpy() > 0.5
+    c_np = np.where(s_np, full_c.cpu().numpy(), np.inf)
+    return s_np, c_np
+
+
 class AnytimeConfig(C.Structure):
     _fields_ = [("max_distance", C.c_double), ("min_distance", C.c_double), ("tolerance", C.c_double),
                 ("utopia_tolerance", C.c_double), ("delta", C.c_double), ("cost_impr", C.c_double), ("seed", C.c_uint64),

@@ -110,3 +110,46 @@ def test_sharded_store_two_ranks_gloo(tmp_path):
     port = 29600 + os.getpid() % 300
     mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
     assert (tmp_path / "ok0").exists() and (tmp_path / "ok1").exists()
+
+
+def _c5_worker(rank, world, port, tmp):
+    """BASELINE config 5's sharding on CPU: query j on rank j mod world, per-query sample streams (k * total + j), one
+    all-reduce gather of (solved, cost).  The planner is the oracle's AnytimeRRT restatement (test double of
+    LockstepAnytimeRRT, which takes the same (stride, index) stream arguments)."""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    sys.path.insert(0, str(ROOT))
+    sys.path.insert(0, str(ROOT / "oracle"))
+    import oracle_py
+    from graph_core_b200 import worlds as W
+    from graph_core_b200.planner import gather_query_results, query_shard
+    sc = W.scenario_c1()
+    total, max_iter, seed = 5, 150, 61
+    ow = oracle_py.OracleWorld.from_scenario(sc)
+    u = W.philox_u01(62, 0, 64, 4)
+    pts = sc.lb + u.reshape(-1, 2) * (sc.ub - sc.lb)
+    pts = pts[ow.check(pts).astype(bool)][:2 * total]
+    starts, goals = pts[:total], pts[total:2 * total]
+
+    def solve(j):
+        o = oracle_py.OracleAnytime(sc, oracle_py.OracleWorld.from_scenario(sc), start=starts[j], goal=goals[j])
+        ok = o.solve(max_iter, seed, j, total)
+        return ok, o.state()["cost"]
+
+    mine = query_shard(total, rank, world)
+    assert mine.tolist() == list(range(rank, total, world))
+    res = [solve(int(j)) for j in mine]
+    s_all, c_all = gather_query_results(dist, total, mine, np.array([r[0] for r in res]), np.array([r[1] for r in res]))
+    want = [solve(j) for j in range(total)]  # the whole set in one process
+    assert s_all.tolist() == [w[0] for w in want]
+    assert all((c == w[1]) or (not w[0] and np.isinf(c)) for c, w in zip(c_all.tolist(), want))
+    dist.barrier()
+    Path(tmp, "c5ok%d" % rank).write_text("ok")
+    dist.destroy_process_group()
+
+
+def test_c5_query_sharding_two_ranks_gloo(tmp_path):
+    port = 29900 + os.getpid() % 90
+    mp.spawn(_c5_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    assert (tmp_path / "c5ok0").exists() and (tmp_path / "c5ok1").exists()
