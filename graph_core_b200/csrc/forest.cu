@@ -81,6 +81,7 @@ struct ForestDev
   const double* goals;       // [P][D]
   const double* samples;     // [P][D]
   uint32_t* seg_q;           // [P] segment queried by problem p: p, or P (empty) when inactive
+  uint32_t* seg_near;        // [P] the same for the radius-near pass: P also when the extension of this step failed
   double* radius;
   uint32_t* closest;
   double* dist;
@@ -187,6 +188,18 @@ __global__ void forest_prologue_kernel(ForestDev f)
   const uint32_t mx = __reduce_max_sync(am, pr.tree_size);
   if ((threadIdx.x & 31) == (uint32_t)(__ffs(am) - 1) && mx > f.ctr[7])
     atomicMax(&f.ctr[7], mx);
+}
+
+// ---- gate: only the problems whose extension succeeded (Tree::tryExtendFromNode, tree.cpp:69-81) go on to the
+// radius-near pass -- three quarters of the C3 samples end at a colliding extension edge, and their near scans were
+// read for nothing
+__global__ void forest_gate_kernel(ForestDev f)
+{
+  const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= f.P)
+    return;
+  const bool ok = f.seg_q[p] == p && f.closest[p] != GC_NO_NODE && ((f.dist[p] < f.tolerance) ? true : f.ok_ext[p] != 0);
+  f.seg_near[p] = ok ? p : f.P;
 }
 
 // ---- extend: Tree::extend's bookkeeping + the parent phase's candidate set (tree.cpp:130-161, 428-463) -------
@@ -980,6 +993,7 @@ int gc_forest_create(gc_store_t* s, gc_world_t* w, const gc_forest_config_t* cfg
   FA(f->d_ub, D);
   FA(f->d_samples, PD);
   FA(d.seg_q, P);
+  FA(d.seg_near, P);
   FA(d.radius, P);
   FA(d.closest, P);
   FA(d.dist, P);
@@ -1183,7 +1197,10 @@ static int forest_enqueue(gc_forest* f, const ForestDev& d, cudaStream_t st)
   GC_TRY(steer_launch(s, d.samples, d.seg_q, d.closest, d.dist, P, f->cfg.max_distance, d.c1, d.c2, st));
   GC_TRY(check_edges_dev(w, d.c1, d.c2, nullptr, P, f->cfg.min_distance, GC_EDGE_BISECT, d.ok_ext, nullptr,
                          f->per_edge_states * P, st));
-  GC_TRY(radius_dev(s, d.c2, d.seg_q, d.radius, P, d.near_cap, d.near_idx, d.near_dist, d.near_count));
+  forest_gate_kernel<<<(P + 255) / 256, 256, 0, st>>>(d);
+  GC_CUDA(cudaGetLastError());
+  count_launch();
+  GC_TRY(radius_dev(s, d.c2, d.seg_near, d.radius, P, d.near_cap, d.near_idx, d.near_dist, d.near_count));
   forest_extend_kernel<<<P, 128, 0, st>>>(d);
   GC_CUDA(cudaGetLastError());
   count_launch();
