@@ -99,3 +99,27 @@ def test_cuda_path_reproduces_reference_golden(gc, orc):
     for section in want:
         for key in want[section]:
             assert got[section][key] == want[section][key], (section, key)
+
+
+def test_cuda_anytime_reproduces_reference_golden(gc, orc):
+    """The lock-step AnytimeRRT (csrc/anytime.cu) against tests/golden/anytime_golden.json = round logs, costs and way
+    points of the reference's own AnytimeRRT on the same per-problem sample streams (2-D boxes with connect / extend /
+    solve() as written, 7-DoF sphere arm)."""
+    import make_anytime_golden as m
+    from graph_core_b200 import worlds as W
+    from graph_core_b200.planner import LockstepAnytimeRRT
+    want = json.loads((GOLD / "anytime_golden.json").read_text())
+    for name, scn, n, max_iter, seed, extend, iis in m.CASES:
+        case = want["cases"][name]
+        sc, starts, goals, cost0 = m.problems(orc, W, scn, n)
+        lk = LockstepAnytimeRRT(sc, sc.make_world(), starts, goals, max_iter=max_iter, seed=seed, extend=extend,
+                                improve_in_solve=iis, sampler_cost0=cost0, capacity=8192)
+        assert lk.run() == 0
+        for p in range(n):
+            w = case["results"][p]
+            info = lk.info(p)
+            assert info["solved"] == w["solved"], (name, p)
+            assert m.hexf(lk.log(p)) == w["log"], (name, p)
+            if w["solved"]:
+                assert float(info["cost"]).hex() == w["cost"], (name, p)
+                assert m.hexf(lk.solution(p)[0]) == w["solution"], (name, p)

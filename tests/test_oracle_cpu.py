@@ -241,3 +241,26 @@ def test_oracle_grid_culling_keeps_every_verdict(orc):
         plain.check(q[:500])
         if nobs >= 1000:
             assert grid.counters()["pair_tests"] * 20 < plain.counters()["pair_tests"]
+
+
+def test_anytime_golden(orc):
+    """tests/golden/anytime_golden.json holds the round logs, costs and way points of the REFERENCE's own AnytimeRRT
+    (oracle/_ref, minted by tests/golden/make_anytime_golden.py) on 2-D box and 7-DoF sphere-arm queries: the
+    restatement reproduces every one of them bit for bit, also where oracle/_ref is not available."""
+    import make_anytime_golden as m
+    from graph_core_b200 import worlds as W
+    want = json.loads((GOLD / "anytime_golden.json").read_text())
+    assert want["columns"] == list(orc.ANYTIME_LOG_COLUMNS)
+    for name, scn, n, max_iter, seed, extend, iis in m.CASES:
+        case = want["cases"][name]
+        sc, starts, goals, cost0 = m.problems(orc, W, scn, n)
+        for p in range(n):
+            o = orc.OracleAnytime(sc, orc.OracleWorld.from_scenario(sc), start=starts[p], goal=goals[p], extend=extend,
+                                  sampler_cost0=float(cost0[p]))
+            solved = o.solve(max_iter, seed, p, n, improve_in_solve=iis)
+            w = case["results"][p]
+            assert solved == w["solved"], (name, p)
+            assert m.hexf(o.log()) == w["log"], (name, p)
+            if solved:
+                assert float(o.state()["cost"]).hex() == w["cost"], (name, p)
+                assert m.hexf(o.solution()) == w["solution"], (name, p)
