@@ -802,6 +802,13 @@ struct gc_forest
   std::vector<double> snap_path_cost;
   unsigned long long stats[16] = {};
   uint32_t err_bits = 0;
+  // host sample blocks go H2D on a copy stream into one of two staging buffers while the previous iteration computes;
+  // the step's own stream only waits for the block and moves it into place with a device copy
+  cudaStream_t copy_stream = nullptr;
+  double* d_stage[2] = { nullptr, nullptr };
+  cudaEvent_t ev_ready[2] = { nullptr, nullptr }, ev_consumed[2] = { nullptr, nullptr };
+  bool stage_used[2] = { false, false };
+  uint32_t stage_next = 0;
 };
 
 namespace
@@ -902,6 +909,15 @@ int forest_free(gc_forest* f)
     cudaEventDestroy(f->probe_ev);
   if (f->h_probe)
     cudaFreeHost(f->h_probe);
+  for (int b = 0; b < 2; b++)
+  {
+    if (f->ev_ready[b])
+      cudaEventDestroy(f->ev_ready[b]);
+    if (f->ev_consumed[b])
+      cudaEventDestroy(f->ev_consumed[b]);
+  }
+  if (f->copy_stream)
+    cudaStreamDestroy(f->copy_stream);
   delete f;
   return GC_OK;
 }
@@ -1233,7 +1249,29 @@ int gc_forest_step(gc_forest_t* f, const double* samples, const double* d_sample
   // records per-call timing events or GCB200_NO_GRAPH is set; the samples then go through the forest's own block.
   const bool use_graph = f->graph_enabled && !w->timing;
   if (samples)
-    GC_CUDA(cudaMemcpyAsync(f->d_samples, samples, sizeof(double) * (size_t)P * D, cudaMemcpyHostToDevice, st));
+  {
+    const size_t bytes = sizeof(double) * (size_t)P * D;
+    if (!f->copy_stream)
+    {
+      GC_CUDA(cudaStreamCreateWithFlags(&f->copy_stream, cudaStreamNonBlocking));
+      for (int b = 0; b < 2; b++)
+      {
+        GC_TRY(forest_alloc(f, &f->d_stage[b], (size_t)P * D));
+        GC_CUDA(cudaEventCreateWithFlags(&f->ev_ready[b], cudaEventDisableTiming));
+        GC_CUDA(cudaEventCreateWithFlags(&f->ev_consumed[b], cudaEventDisableTiming));
+      }
+    }
+    const uint32_t b = f->stage_next;
+    f->stage_next ^= 1u;
+    if (f->stage_used[b])  // the step that last read this staging buffer must have moved it out
+      GC_CUDA(cudaStreamWaitEvent(f->copy_stream, f->ev_consumed[b], 0));
+    GC_CUDA(cudaMemcpyAsync(f->d_stage[b], samples, bytes, cudaMemcpyHostToDevice, f->copy_stream));
+    GC_CUDA(cudaEventRecord(f->ev_ready[b], f->copy_stream));
+    GC_CUDA(cudaStreamWaitEvent(st, f->ev_ready[b], 0));
+    GC_CUDA(cudaMemcpyAsync(f->d_samples, f->d_stage[b], bytes, cudaMemcpyDeviceToDevice, st));
+    GC_CUDA(cudaEventRecord(f->ev_consumed[b], st));
+    f->stage_used[b] = true;
+  }
   else if (d_samples)
   {
     if (use_graph)
