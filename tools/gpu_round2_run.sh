@@ -1,3 +1,3 @@
-mkdir -p gpurun_out/r2s42
-O=gpurun_out/r2s42
-( time timeout 600 python bench.py > $O/bench.json 2> $O/bench.err ) 2> $O/bench.time; echo "rc=$?" >> $O/bench.err
+mkdir -p gpurun_out/r2s43
+O=gpurun_out/r2s43
+timeout 150 python -m pytest tests -x -q -m gpu > $O/pytest_all.log 2>&1; echo "pytest rc=$?" >> $O/pytest_all.log
